@@ -1,0 +1,262 @@
+// extern "C" surface declared in include/w2x.h.  Nothing throws across this boundary.
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <cstring>
+#include <filesystem>
+
+#include "engine.h"
+
+using namespace w2x;
+
+struct w2x_engine {
+    Engine impl;
+};
+
+namespace {
+void setErr(char* err, int cap, const std::string& s) {
+    if (err && cap > 0) {
+        std::strncpy(err, s.c_str(), (size_t)cap - 1);
+        err[cap - 1] = 0;
+    }
+}
+
+struct DevBufs {
+    std::vector<void*> v;
+    ~DevBufs() { for (void* p : v) cudaFree(p); }
+    template <class T> T* alloc(size_t count) {
+        void* p = nullptr;
+        W2X_CUDA(cudaMalloc(&p, count * sizeof(T) + 16));
+        v.push_back(p);
+        return (T*)p;
+    }
+};
+}  // namespace
+
+extern "C" {
+
+void w2x_default_build_config(w2x_build_config* c) {
+    if (!c) return;
+    *c = w2x_build_config{0, W2X_PRECISION_FP16, 1, 1, 4, 3, 3, 3, 64, 256, 640, 64, 256, 640};  // config.h:12-31
+}
+
+void w2x_default_render_config(w2x_render_config* c) {
+    if (!c) return;
+    *c = w2x_render_config{0, W2X_PRECISION_FP16, 1, 3, 256, 256, 4, 0.0625, 0.0625, 0};  // config.h:33-43
+}
+
+w2x_engine* w2x_create(void) {
+    try { return new w2x_engine(); } catch (...) { return nullptr; }
+}
+
+void w2x_destroy(w2x_engine* e) { delete e; }
+
+void w2x_set_message_callback(w2x_engine* e, w2x_message_cb cb, void* user) { if (e) e->impl.setMessageCallback(cb, user); }
+void w2x_set_progress_callback(w2x_engine* e, w2x_progress_cb cb, void* user) { if (e) e->impl.setProgressCallback(cb, user); }
+
+int w2x_build(w2x_engine* e, const char* onnx_path, const w2x_build_config* cfg) {
+    if (!e || !onnx_path || !cfg) return 0;
+    return e->impl.build(onnx_path, *cfg) ? 1 : 0;
+}
+
+int w2x_load(w2x_engine* e, const char* onnx_path, const w2x_render_config* cfg) {
+    if (!e || !onnx_path || !cfg) return 0;
+    return e->impl.load(onnx_path, *cfg) ? 1 : 0;
+}
+
+int w2x_render(w2x_engine* e, const uint8_t* src, int width, int height, size_t src_stride, uint8_t* dst, size_t dst_stride) {
+    if (!e || !src || !dst) return 0;
+    return e->impl.render(src, width, height, src_stride, dst, dst_stride) ? 1 : 0;
+}
+
+int w2x_render_device(w2x_engine* e, const uint8_t* src, int width, int height, size_t src_stride, uint8_t* dst, size_t dst_stride) {
+    if (!e || !src || !dst) return 0;
+    return e->impl.renderDevice(src, width, height, src_stride, dst, dst_stride) ? 1 : 0;
+}
+
+int w2x_submit(w2x_engine* e, const uint8_t* src, int width, int height, size_t src_stride, uint8_t* dst, size_t dst_stride) {
+    if (!e || !src || !dst) return -1;
+    return e->impl.submit(src, width, height, src_stride, dst, dst_stride);
+}
+
+int w2x_wait(w2x_engine* e, int ticket) { return e && e->impl.wait(ticket) ? 1 : 0; }
+int w2x_sync(w2x_engine* e) { return e && e->impl.sync() ? 1 : 0; }
+
+void* w2x_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+void w2x_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+void* w2x_device_alloc(w2x_engine* e, size_t bytes) {
+    if (!e || cudaSetDevice(e->impl.device()) != cudaSuccess) return nullptr;
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+    return p;
+}
+void w2x_device_free(w2x_engine* e, void* p) {
+    if (e) cudaSetDevice(e->impl.device());
+    if (p) cudaFree(p);
+}
+int w2x_memcpy_h2d(w2x_engine* e, void* dst, const void* src, size_t bytes) {
+    if (!e || cudaSetDevice(e->impl.device()) != cudaSuccess) return 0;
+    return cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice) == cudaSuccess;
+}
+int w2x_memcpy_d2h(w2x_engine* e, void* dst, const void* src, size_t bytes) {
+    if (!e || cudaSetDevice(e->impl.device()) != cudaSuccess) return 0;
+    return cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost) == cudaSuccess;
+}
+
+const char* w2x_last_error(w2x_engine* e) { return e ? e->impl.lastError() : "null engine"; }
+int w2x_output_tile_size(w2x_engine* e) { return e ? e->impl.outputTile() : 0; }
+long long w2x_launch_count(w2x_engine* e) { return e ? e->impl.launchCount() : 0; }
+double w2x_model_flops_per_tile(w2x_engine* e) { return e ? e->impl.flopsPerTile() : 0.0; }
+int w2x_last_stage_ms(w2x_engine* e, float* out, int n) { return e && out ? e->impl.lastStageMs(out, n) : 0; }
+int w2x_profile_layers(w2x_engine* e, int repeats, char (*names)[48], float* ms, double* flops, int n) {
+    return e ? e->impl.profileLayers(repeats < 1 ? 1 : repeats, names, ms, flops, n) : -1;
+}
+int w2x_infer(w2x_engine* e, const float* in, int n, float* out) { return e && in && out && e->impl.infer(in, n, out) ? 1 : 0; }
+
+// ---- stage entry points ---------------------------------------------------------------------------------
+int w2x_calculate_tiles(int in_w, int in_h, int out_w, int out_h, int tile_w, int tile_h, int out_tile_w, int out_tile_h,
+                        int scaling, double overlap_x, double overlap_y, w2x_rect* in_rects, w2x_rect* out_rects, int cap,
+                        int* grid_out) {
+    try {
+        TileGrid g = calculateTiles(in_w, in_h, out_w, out_h, tile_w, tile_h, out_tile_w, out_tile_h, scaling, overlap_x, overlap_y);
+        for (int i = 0; i < g.count && i < cap; ++i) {
+            if (in_rects) in_rects[i] = g.inRects[i];
+            if (out_rects) out_rects[i] = g.outRects[i];
+        }
+        if (grid_out) {
+            const int v[8] = {g.nx, g.ny, g.scaledInW, g.scaledInH, g.inOvX, g.inOvY, g.outOvX, g.outOvY};
+            std::memcpy(grid_out, v, sizeof(v));
+        }
+        return g.count;
+    } catch (...) {
+        return -1;
+    }
+}
+
+int w2x_blend_ramp(int overlap, float* ramp) {
+    if (overlap < 0) return -1;
+    std::vector<float> r = blendRamp(overlap);
+    if (ramp) std::memcpy(ramp, r.data(), r.size() * sizeof(float));
+    return (int)r.size();
+}
+
+int w2x_unpack_tiles(int device, const uint8_t* src, int width, int height, size_t src_stride, const w2x_rect* rects,
+                     const int* aug, int n, int tile, uint16_t* out) {
+    try {
+        if (!src || !rects || !out || n <= 0 || tile <= 0) return 0;
+        W2X_CUDA(cudaSetDevice(device));
+        DevBufs b;
+        uint8_t* dSrc = b.alloc<uint8_t>((size_t)width * 3 * height);
+        W2X_CUDA(cudaMemcpy2D(dSrc, (size_t)width * 3, src, src_stride, (size_t)width * 3, height, cudaMemcpyHostToDevice));
+        std::vector<TileSlot> slots(n);
+        for (int i = 0; i < n; ++i) slots[i] = {rects[i].x, rects[i].y, aug ? aug[i] : 0, 1};
+        TileSlot* dSlots = b.alloc<TileSlot>(n);
+        W2X_CUDA(cudaMemcpy(dSlots, slots.data(), sizeof(TileSlot) * n, cudaMemcpyHostToDevice));
+        const size_t elems = (size_t)n * tile * tile * 4;
+        __half* dOut = b.alloc<__half>(elems);
+        launchUnpack(dSrc, width, height, (size_t)width * 3, dSlots, n, tile, dOut, nullptr);
+        W2X_CUDA(cudaGetLastError());
+        W2X_CUDA(cudaMemcpy(out, dOut, elems * 2, cudaMemcpyDeviceToHost));
+        return 1;
+    } catch (const std::exception& ex) {
+        std::fprintf(stderr, "w2x_unpack_tiles: %s\n", ex.what());
+        return 0;
+    }
+}
+
+int w2x_stitch_tiles(int device, const uint16_t* tiles, int count, int out_tile, int nx, int ny, int overlap_x, int overlap_y,
+                     int canvas_w, int canvas_h, uint8_t* dst, size_t dst_stride) {
+    try {
+        if (!tiles || !dst || count != nx * ny) return 0;
+        W2X_CUDA(cudaSetDevice(device));
+        DevBufs b;
+        const size_t elems = (size_t)count * out_tile * out_tile * 4;
+        __half* dT = b.alloc<__half>(elems);
+        W2X_CUDA(cudaMemcpy(dT, tiles, elems * 2, cudaMemcpyHostToDevice));
+        std::vector<float> rx = blendRamp(overlap_x), ry = blendRamp(overlap_y);
+        float* dRx = b.alloc<float>(rx.size() + 1);
+        float* dRy = b.alloc<float>(ry.size() + 1);
+        if (!rx.empty()) W2X_CUDA(cudaMemcpy(dRx, rx.data(), rx.size() * 4, cudaMemcpyHostToDevice));
+        if (!ry.empty()) W2X_CUDA(cudaMemcpy(dRy, ry.data(), ry.size() * 4, cudaMemcpyHostToDevice));
+        uint8_t* dDst = b.alloc<uint8_t>((size_t)canvas_w * 3 * canvas_h);
+        StitchParams sp{};
+        sp.tiles = dT; sp.f32 = 0; sp.outT = out_tile; sp.nx = nx; sp.ny = ny; sp.ovx = overlap_x; sp.ovy = overlap_y;
+        sp.cw = canvas_w; sp.ch = canvas_h; sp.rampx = dRx; sp.rampy = dRy; sp.dst = dDst; sp.pitch = (size_t)canvas_w * 3;
+        launchStitch(sp, nullptr);
+        W2X_CUDA(cudaGetLastError());
+        W2X_CUDA(cudaMemcpy2D(dst, dst_stride, dDst, (size_t)canvas_w * 3, (size_t)canvas_w * 3, canvas_h, cudaMemcpyDeviceToHost));
+        return 1;
+    } catch (const std::exception& ex) {
+        std::fprintf(stderr, "w2x_stitch_tiles: %s\n", ex.what());
+        return 0;
+    }
+}
+
+int w2x_tta_reduce(int device, const uint16_t* outs, int tiles, int out_tile, float* mean) {
+    try {
+        if (!outs || !mean || tiles <= 0) return 0;
+        W2X_CUDA(cudaSetDevice(device));
+        DevBufs b;
+        const size_t plane = (size_t)out_tile * out_tile * 4;
+        __half* dIn = b.alloc<__half>(plane * 8 * tiles);
+        float* dOut = b.alloc<float>(plane * tiles);
+        W2X_CUDA(cudaMemcpy(dIn, outs, plane * 8 * tiles * 2, cudaMemcpyHostToDevice));
+        launchTtaReduce(dIn, tiles, out_tile, dOut, nullptr);
+        W2X_CUDA(cudaGetLastError());
+        W2X_CUDA(cudaMemcpy(mean, dOut, plane * tiles * 4, cudaMemcpyDeviceToHost));
+        return 1;
+    } catch (const std::exception& ex) {
+        std::fprintf(stderr, "w2x_tta_reduce: %s\n", ex.what());
+        return 0;
+    }
+}
+
+double w2x_selftest_conv(int device, int kind, int n, int h, int w, int cin, int cout, unsigned seed) {
+    try {
+        return selftestConv(device, kind, n, h, w, cin, cout, seed);
+    } catch (...) {
+        return -1.0;
+    }
+}
+
+void w2x_config_hash(const char* device_name, const w2x_build_config* cfg, char out_hex[65]) {
+    if (!out_hex) return;
+    out_hex[0] = 0;
+    if (!device_name || !cfg) return;
+    const std::string h = configHash(device_name, *cfg);
+    std::memcpy(out_hex, h.c_str(), 65);
+}
+
+int w2x_pack_onnx(const char* onnx_path, const char* out_path, int precision, char* err, int cap) {
+    try {
+        if (!onnx_path || !out_path) throw Error("null path");
+        OnnxGraph g = parseOnnx(readFile(onnx_path));
+        PackedModel pm = packFromOnnx(g, precision);
+        const std::vector<uint8_t> blob = serializePack(pm);
+        writeFile(out_path, blob.data(), blob.size());
+        return 1;
+    } catch (const std::exception& ex) {
+        setErr(err, cap, ex.what());
+        return 0;
+    }
+}
+
+int w2x_pack_info(const char* pack_path, int* arch, int* scale, int* offset, int* layers) {
+    try {
+        PackedModel pm = deserializePack(readFile(pack_path));
+        if (arch) *arch = (int)pm.arch;
+        if (scale) *scale = (int)pm.scale;
+        if (offset) *offset = (int)pm.offset;
+        if (layers) *layers = (int)pm.layers.size();
+        return 1;
+    } catch (...) {
+        return 0;
+    }
+}
+
+}  // extern "C"

@@ -1,0 +1,813 @@
+#include "engine.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <filesystem>
+#include <random>
+
+namespace w2x {
+
+namespace fs = std::filesystem;
+
+// ------------------------------------------------------------------------------------------------
+// implicit-GEMM views of the four layer kinds (see conv_params.h / model_pack.h)
+// ------------------------------------------------------------------------------------------------
+static void plainView(ConvParams& p, const Act& in) {
+    p.in = in.p;
+    p.dimc = in.c; p.dimx = in.w; p.dimz = 1; p.dimy = in.h;
+    p.sx = in.c; p.sz = (long long)in.w * in.c; p.sy = (long long)in.w * in.c; p.sn = (long long)in.h * in.w * in.c;
+    p.cin = in.c;
+    p.gn = in.n;
+}
+
+static void setOut(ConvParams& p, const Act& out) {
+    p.out = out.p; p.out_h = out.h; p.out_w = out.w; p.out_c = out.c;
+}
+
+ConvParams makeConv3Params(const Act& in, const Act& out, const __half* w, const float* bias, int npad, int mode, float slope, int storeC) {
+    ConvParams p{};
+    plainView(p, in);
+    p.ntaps = 9;
+    for (int ky = 0; ky < 3; ++ky)
+        for (int kx = 0; kx < 3; ++kx) p.tap[ky * 3 + kx] = {0, kx, 0, ky};
+    p.gx = in.w - 2; p.gy = in.h - 2;
+    p.npad = npad; p.ktot = 9 * in.c;
+    p.w = w; p.bias = bias;
+    p.mode = mode; p.slope = slope; p.cout = storeC;
+    setOut(p, out);
+    return p;
+}
+
+ConvParams makeDown2Params(const Act& in, const Act& out, const __half* w, const float* bias, int npad, float slope) {
+    ConvParams p{};
+    p.in = in.p;
+    p.dimc = 2 * in.c; p.dimx = in.w / 2; p.dimz = 2; p.dimy = in.h / 2;
+    p.sx = 2 * in.c; p.sz = (long long)in.w * in.c; p.sy = 2ll * in.w * in.c; p.sn = (long long)in.h * in.w * in.c;
+    p.cin = in.c; p.gn = in.n;
+    p.ntaps = 4;
+    for (int dy = 0; dy < 2; ++dy)
+        for (int dx = 0; dx < 2; ++dx) p.tap[dy * 2 + dx] = {dx * in.c, 0, dy, 0};
+    p.gx = in.w / 2; p.gy = in.h / 2;
+    p.npad = npad; p.ktot = 4 * in.c;
+    p.w = w; p.bias = bias;
+    p.mode = EPI_STORE; p.slope = slope; p.cout = npad;
+    setOut(p, out);
+    return p;
+}
+
+ConvParams makeUp2Params(const Act& in, const Act& out, const __half* w, const float* bias, int cout, float slope, const Act* skip, int skipOff) {
+    ConvParams p{};
+    plainView(p, in);
+    p.ntaps = 1;
+    p.tap[0] = {0, 0, 0, 0};
+    p.gx = in.w; p.gy = in.h;
+    p.npad = 4 * cout; p.ktot = in.c;
+    p.w = w; p.bias = bias;
+    p.mode = EPI_D2S; p.slope = slope; p.cout = cout;
+    setOut(p, out);
+    if (skip) { p.skip = skip->p; p.skip_h = skip->h; p.skip_w = skip->w; p.skip_c = skip->c; p.skip_off = skipOff; }
+    return p;
+}
+
+ConvParams makeUp4Params(const Act& in, const Act& out, const __half* w, const float* bias) {
+    ConvParams p{};
+    plainView(p, in);
+    p.ntaps = 4;
+    for (int wy = 0; wy < 2; ++wy)
+        for (int wx = 0; wx < 2; ++wx) p.tap[wy * 2 + wx] = {0, wx, 0, wy};
+    p.gx = in.w - 1; p.gy = in.h - 1;
+    p.npad = 16; p.ktot = 4 * in.c;
+    p.w = w; p.bias = bias;
+    p.mode = EPI_UP4; p.slope = 1.f; p.cout = 4;
+    setOut(p, out);
+    return p;
+}
+
+// ------------------------------------------------------------------------------------------------
+Engine::Engine() {}
+
+Engine::~Engine() {
+    try { unload(); } catch (...) {}
+}
+
+void Engine::log(int severity, const std::string& msg, const char* func, int line) {
+    // "[func@line] msg", /root/reference/src/tensorrt/logger.cpp:19-22
+    std::string full = std::string("[") + func + "@" + std::to_string(line) + "] " + msg;
+    if (severity <= W2X_ERROR) lastErr = full;
+    if (msgCb) msgCb(severity, full.c_str(), msgUser);
+}
+#define ELOG(sev, msg) log(sev, msg, __FUNCTION__, __LINE__)
+
+void* Engine::dalloc(size_t bytes) {
+    void* p = nullptr;
+    W2X_CUDA(cudaMalloc(&p, bytes ? bytes : 16));
+    allocs.push_back(p);
+    return p;
+}
+
+Act Engine::allocAct(int h, int w, int c) {
+    if (h <= 0 || w <= 0) throw Error("tile size too small for this model");
+    Act a;
+    a.n = batch; a.h = h; a.w = w; a.c = c;
+    a.p = (__half*)dalloc(a.elems() * sizeof(__half) + 256);
+    return a;
+}
+
+cudaEvent_t Engine::nextEvent() {
+    if (evUsed == (int)evPool.size()) {
+        cudaEvent_t e;
+        W2X_CUDA(cudaEventCreate(&e));
+        evPool.push_back(e);
+    }
+    return evPool[evUsed++];
+}
+
+void Engine::unload() {
+    if (stream) cudaStreamSynchronize(stream);
+    if (h2dStream) cudaStreamSynchronize(h2dStream);
+    if (d2hStream) cudaStreamSynchronize(d2hStream);
+    for (auto& L : layers)
+        if (L.plan) igemmDestroyPlan(L.plan);
+    layers.clear();
+    for (void* p : allocs) cudaFree(p);
+    allocs.clear();
+    dW.clear(); dBias.clear();
+    auto freep = [](auto*& p) { if (p) { cudaFree(p); p = nullptr; } };
+    freep(dSlots); freep(dTileOut); freep(dTtaMean); freep(dRampX); freep(dRampY); freep(dFrameIn); freep(dFrameOut);
+    slotCap = tileOutCap = ttaCap = frameInCap = frameOutCap = 0;
+    rampXLen = rampYLen = -1;
+    for (auto& s : pipe) {
+        freep(s.dIn); freep(s.dOut);
+        s.inCap = s.outCap = 0;
+        if (s.evH2D) { cudaEventDestroy(s.evH2D); s.evH2D = nullptr; }
+        if (s.evComp) { cudaEventDestroy(s.evComp); s.evComp = nullptr; }
+        if (s.evDone) { cudaEventDestroy(s.evDone); s.evDone = nullptr; }
+        s.busy = false;
+    }
+    for (auto e : evPool) cudaEventDestroy(e);
+    evPool.clear(); evUsed = 0; spans.clear();
+    if (stream) { cudaStreamDestroy(stream); stream = nullptr; }
+    if (h2dStream) { cudaStreamDestroy(h2dStream); h2dStream = nullptr; }
+    if (d2hStream) { cudaStreamDestroy(d2hStream); d2hStream = nullptr; }
+    frameW = frameH = 0;
+    isLoaded = false;
+}
+
+// ------------------------------------------------------------------------------------------------
+// build: ONNX -> packed weights + json sidecar, named like the reference's engine files
+// (img2img_build.cpp:151-166)
+// ------------------------------------------------------------------------------------------------
+static std::string deviceNameOf(int id) {
+    cudaDeviceProp prop{};
+    W2X_CUDA(cudaGetDeviceProperties(&prop, id));
+    return prop.name;
+}
+
+static int deviceIdOf(const std::string& name) {  // helper.h:47-56
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return -1;
+    for (int i = 0; i < n; ++i) {
+        cudaDeviceProp prop{};
+        if (cudaGetDeviceProperties(&prop, i) == cudaSuccess && name == prop.name) return i;
+    }
+    return -1;
+}
+
+bool Engine::build(const std::string& onnxPath, const w2x_build_config& bc) {
+    try {
+        cudaError_t e = cudaSetDevice(bc.deviceId);
+        if (e != cudaSuccess) {
+            ELOG(W2X_ERROR, "Failed to set cuda device to device id " + std::to_string(bc.deviceId) + ": " + cudaGetErrorString(e) + ".");
+            return false;
+        }
+        if (bc.precision != W2X_PRECISION_FP16) {
+            ELOG(W2X_ERROR, "Failed to set precision: the tf32 kernel set is not available in this build (fp16 storage, fp32 accumulate only)");
+            return false;
+        }
+        OnnxGraph g;
+        try {
+            g = parseOnnx(readFile(onnxPath));
+        } catch (const std::exception& ex) {
+            ELOG(W2X_ERROR, std::string("Failed to parse ONNX model: ") + ex.what() + ".");
+            return false;
+        }
+        PackedModel pm = packFromOnnx(g, bc.precision);
+        const std::string name = deviceNameOf(bc.deviceId);
+        const std::string base = fs::path(onnxPath).replace_extension("").string() + "_" + configHash(name, bc).substr(0, 16);
+        Sidecar sc;
+        sc.deviceName = name;
+        sc.cfg = bc;
+        writeSidecar(base + ".json", sc);
+        const std::vector<uint8_t> blob = serializePack(pm);
+        writeFile(base + ".w2x", blob.data(), blob.size());
+        ELOG(W2X_INFO, "Packed " + std::to_string(pm.layers.size()) + " layers into \"" + base + ".w2x\"");
+        return true;
+    } catch (const std::exception& ex) {
+        ELOG(W2X_ERROR, std::string("Engine build failed unexpectedly: ") + ex.what() + ".");
+        return false;
+    }
+}
+
+// getEnginePath, img2img_load.cpp:79-114.  Deviation: the name must be exactly <stem>_<16 hex>.w2x, and
+// candidates are visited in sorted order so the choice is deterministic.
+static std::string findEngine(const std::string& modelPath, const w2x_render_config& rc) {
+    if (!fs::exists(modelPath)) throw Error("model file does not exist");
+    const std::string stem = fs::path(modelPath).stem().string();
+    fs::path dir = fs::path(modelPath).parent_path();
+    if (dir.empty()) dir = ".";
+    std::vector<fs::path> cands;
+    for (const auto& entry : fs::directory_iterator(dir)) {
+        if (!entry.is_regular_file()) continue;
+        const fs::path& p = entry.path();
+        const std::string fn = p.filename().string();
+        if (p.extension().string() != ".w2x" || fn.size() != stem.size() + 1 + 16 + 4) continue;
+        if (fn.compare(0, stem.size(), stem) != 0 || fn[stem.size()] != '_') continue;
+        bool hex = true;
+        for (size_t i = stem.size() + 1; i < stem.size() + 17; ++i) hex = hex && std::isxdigit((unsigned char)fn[i]);
+        if (hex) cands.push_back(p);
+    }
+    std::sort(cands.begin(), cands.end());
+    std::string chosen;
+    for (const auto& p : cands) {
+        const std::string cfgPath = fs::path(p).replace_extension("").string() + ".json";
+        if (!fs::exists(cfgPath)) continue;
+        Sidecar sc = readSidecar(cfgPath);
+        sc.cfg.deviceId = deviceIdOf(sc.deviceName);
+        if (isCompatible(rc, sc.cfg)) {
+            if (isOptimized(rc, sc.cfg)) return p.string();
+            if (chosen.empty()) chosen = p.string();
+        }
+    }
+    if (chosen.empty()) throw Error("could not satisfy render configuration");
+    return chosen;
+}
+
+// ------------------------------------------------------------------------------------------------
+// load: packed weights -> HBM, activation arena, execution plan, streams (img2img_load.cpp:117-291)
+// ------------------------------------------------------------------------------------------------
+bool Engine::load(const std::string& onnxPath, const w2x_render_config& rc) {
+    try {
+        std::string enginePath;
+        try {
+            enginePath = findEngine(onnxPath, rc);
+        } catch (const std::exception& ex) {
+            ELOG(W2X_ERROR, "Failed to find engine file for model \"" + onnxPath + "\": " + ex.what() + ".");
+            return false;
+        }
+        cudaError_t e = cudaSetDevice(rc.deviceId);
+        if (e != cudaSuccess) {
+            ELOG(W2X_ERROR, "Failed to set cuda device to device id " + std::to_string(rc.deviceId) + ": " + cudaGetErrorString(e) + ".");
+            return false;
+        }
+        if (rc.channels != 3 || rc.width != rc.height || rc.batchSize < 1) {
+            ELOG(W2X_ERROR, "Failed to set input tensor shape.");
+            return false;
+        }
+        if (rc.precision != W2X_PRECISION_FP16) {
+            ELOG(W2X_ERROR, "precision tf32 is not available in this build");
+            return false;
+        }
+        unload();
+        model = deserializePack(readFile(enginePath));
+        if ((int)model.scale != rc.scaling) {
+            ELOG(W2X_ERROR, "Render scaling " + std::to_string(rc.scaling) + " does not match the model's scale " + std::to_string(model.scale) + ".");
+            return false;
+        }
+        cfg = rc;
+        tile = rc.width;
+        batch = rc.batchSize;
+        scale = (int)model.scale;
+        const char* impl = std::getenv("W2X_CONV_IMPL");
+        useDirect = impl && std::string(impl) == "direct";
+        W2X_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));  // img2img_load.cpp:206
+        W2X_CUDA(cudaStreamCreateWithFlags(&h2dStream, cudaStreamNonBlocking));
+        W2X_CUDA(cudaStreamCreateWithFlags(&d2hStream, cudaStreamNonBlocking));
+        buildPlan();
+        isLoaded = true;
+        return true;
+    } catch (const std::exception& ex) {
+        ELOG(W2X_ERROR, std::string("Engine load failed unexpectedly: ") + ex.what() + ".");
+        try { unload(); } catch (...) {}
+        return false;
+    }
+}
+
+void Engine::buildPlan() {
+    if (model.arch != ARCH_CUNET && model.arch != ARCH_UPCUNET) throw Error("unknown model architecture in pack file");
+    const bool up = model.arch == ARCH_UPCUNET;
+    // weights -> HBM
+    for (const auto& L : model.layers) {
+        __half* w = (__half*)dalloc(L.w.size() * 2);
+        float* b = (float*)dalloc(L.bias.size() * 4);
+        W2X_CUDA(cudaMemcpy(w, L.w.data(), L.w.size() * 2, cudaMemcpyHostToDevice));
+        W2X_CUDA(cudaMemcpy(b, L.bias.data(), L.bias.size() * 4, cudaMemcpyHostToDevice));
+        dW.push_back(w);
+        dBias.push_back(b);
+    }
+    auto upload = [&](const std::vector<float>& v) {
+        float* d = (float*)dalloc(v.size() * 4);
+        W2X_CUDA(cudaMemcpy(d, v.data(), v.size() * 4, cudaMemcpyHostToDevice));
+        return d;
+    };
+    auto even = [](int v, const char* what) {
+        if (v <= 0 || (v & 1)) throw Error(std::string("tile size is not supported by this model (") + what + " must be even and positive)");
+        return v;
+    };
+    const float S = 0.1f;
+    auto push = [&](int li, const ConvParams& p, double flops, bool fin = false) {
+        LayerExec E;
+        const PackedLayer& L = model.layers[li];
+        E.name = L.name;
+        E.p = p;
+        E.flops = flops;
+        E.isFinal = fin;
+        if (useDirect) E.impl = IMPL_DIRECT;
+        else if (L.kind == L_CONV3 && L.cin == 4 && L.npad == 32 && p.mode == EPI_STORE) E.impl = IMPL_FIRST;
+        else if (igemmSupported(p)) { E.impl = IMPL_IGEMM; E.plan = igemmCreatePlan(p); }
+        else throw Error("no kernel for layer " + L.name);
+        if (L.se_r) {
+            E.seR = (int)L.se_r;
+            E.seW1 = upload(L.se_w1); E.seB1 = upload(L.se_b1); E.seW2 = upload(L.se_w2); E.seB2 = upload(L.se_b2);
+            E.seBlocks = 32;
+            E.sePartial = (float*)dalloc((size_t)batch * E.seBlocks * L.cout * 4);
+            E.seScale = (float*)dalloc((size_t)batch * L.cout * 4);
+        }
+        layers.push_back(E);
+    };
+    auto conv3 = [&](int li, const Act& in, int cout, int mode = EPI_STORE, float slope = 0.1f, const Act* skip = nullptr, int skipOff = 0, bool fin = false) {
+        const PackedLayer& L = model.layers[li];
+        Act out = allocAct(in.h - 2, in.w - 2, cout < 8 ? 4 : cout);
+        ConvParams p = makeConv3Params(in, out, dW[li], dBias[li], (int)L.npad, mode, slope, cout < 8 ? 4 : cout);
+        if (skip) { p.skip = skip->p; p.skip_h = skip->h; p.skip_w = skip->w; p.skip_c = skip->c; p.skip_off = skipOff; }
+        const int cinReal = L.cin == 4 ? 3 : (int)L.cin;
+        push(li, p, 2.0 * p.gx * p.gy * (double)L.cout * 9 * cinReal, fin);
+        return out;
+    };
+    auto down2 = [&](int li, const Act& in) {
+        const PackedLayer& L = model.layers[li];
+        even(in.h, "down-sampled extent");
+        Act out = allocAct(in.h / 2, in.w / 2, (int)L.cout);
+        ConvParams p = makeDown2Params(in, out, dW[li], dBias[li], (int)L.npad, S);
+        push(li, p, 2.0 * p.gx * p.gy * (double)L.cout * 4 * L.cin);
+        return out;
+    };
+    auto up2 = [&](int li, const Act& in, const Act& skip, int off) {
+        const PackedLayer& L = model.layers[li];
+        Act out = allocAct(in.h * 2, in.w * 2, (int)L.cout);
+        if (skip.h - 2 * off != out.h || skip.c != out.c) throw Error("tile size is not supported by this model (skip connection mismatch)");
+        ConvParams p = makeUp2Params(in, out, dW[li], dBias[li], (int)L.cout, S, &skip, off);
+        push(li, p, 2.0 * p.gx * p.gy * 4.0 * L.cout * L.cin);
+        return out;
+    };
+
+    actIn = allocAct(tile, tile, 4);
+    // ---- UNet1 ----
+    Act a0 = conv3(0, actIn, 32);
+    Act x1 = conv3(1, a0, 64);
+    Act d1 = down2(2, x1);
+    Act b0 = conv3(3, d1, 128);
+    Act b1 = conv3(4, b0, 64);  // + SE
+    Act u1 = up2(5, b1, x1, 4);
+    Act c3 = conv3(6, u1, 64);
+    Act z1;
+    if (up) {
+        const PackedLayer& L = model.layers[7];
+        z1 = allocAct(2 * c3.h - 4, 2 * c3.w - 4, 4);
+        ConvParams p = makeUp4Params(c3, z1, dW[7], dBias[7]);
+        push(7, p, 2.0 * c3.h * c3.w * 16.0 * L.cout * L.cin);
+    } else {
+        z1 = conv3(7, c3, 3, EPI_STORE, 1.f);
+    }
+    // ---- UNet2 ----
+    Act e0 = conv3(8, z1, 32);
+    Act y1 = conv3(9, e0, 64);
+    Act f1 = down2(10, y1);
+    Act g0 = conv3(11, f1, 64);
+    Act y2 = conv3(12, g0, 128);  // + SE
+    Act f2 = down2(13, y2);
+    Act h0 = conv3(14, f2, 256);
+    Act h1 = conv3(15, h0, 128);  // + SE
+    Act u3 = up2(16, h1, y2, 4);
+    Act k0 = conv3(17, u3, 64);
+    Act k1 = conv3(18, k0, 64);  // + SE
+    Act u4 = up2(19, k1, y1, 16);
+    Act c5 = conv3(20, u4, 64);
+    if (z1.h - 40 != c5.h - 2) throw Error("tile size is not supported by this model (head crop mismatch)");
+    actOut = conv3(21, c5, 3, EPI_FINAL, 1.f, &z1, 20, true);
+    outTile = actOut.h;
+    const int expect = up ? 2 * tile - 72 : tile - 56;
+    if (outTile != expect) throw Error("internal: output tile size mismatch");
+}
+
+double Engine::flopsPerTile() const {
+    double f = 0;
+    for (const auto& L : layers) f += L.flops;
+    return f;
+}
+
+void Engine::runModel(cudaStream_t s, __half* finalOut) {
+    for (auto& L : layers) {
+        __half* outp = (L.isFinal && finalOut) ? finalOut : L.p.out;
+        if (L.impl == IMPL_IGEMM) {
+            igemmLaunch(L.plan, s, outp);
+        } else {
+            ConvParams p = L.p;
+            p.out = outp;
+            if (L.impl == IMPL_FIRST) launchConvFirst(p, s);
+            else launchConvDirect(p, s);
+        }
+        ++launches;
+        if (L.seR) {
+            launchSeSqueeze(L.p.out, L.p.gn, L.p.out_h, L.p.out_w, L.p.out_c, L.sePartial, L.seBlocks, s);
+            launchSeExcite(L.sePartial, L.seBlocks, L.p.gn, L.p.out_c, L.seR, L.p.out_h * L.p.out_w, L.seW1, L.seB1, L.seW2, L.seB2, L.seScale, s);
+            launchSeScale(L.p.out, L.p.gn, L.p.out_h, L.p.out_w, L.p.out_c, L.seScale, s);
+            launches += 3;
+        }
+    }
+    W2X_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------
+// render (img2img_render.cpp:224-348)
+// ------------------------------------------------------------------------------------------------
+void Engine::ensureFrameBuffers(int w, int h) {
+    if (w == frameW && h == frameH) return;
+    if (w <= 0 || h <= 0) throw Error("invalid frame size");
+    W2X_CUDA(cudaStreamSynchronize(stream));
+    grid = calculateTiles(w, h, w * scale, h * scale, tile, tile, outTile, outTile, scale, cfg.overlapX, cfg.overlapY);
+    if (grid.count <= 0) throw Error("frame is too small for the configured tile overlap");
+    const int stepsPerTile = cfg.tta ? 8 : 1;
+    batchCount = (int)std::lround(std::ceil((double)(grid.count * stepsPerTile) / batch));  // render.cpp:249
+    stepCount = batchCount * batch;
+    std::vector<TileSlot> slots((size_t)stepCount);
+    for (int step = 0; step < stepCount; ++step) {
+        const int ti = step / stepsPerTile, aug = step % stepsPerTile;  // render.cpp:264-265
+        if (ti < grid.count) slots[step] = {grid.inRects[ti].x, grid.inRects[ti].y, aug, 1};
+        else slots[step] = {0, 0, 0, 0};  // zero dummy tile, render.cpp:281
+    }
+    if ((size_t)stepCount > slotCap) {
+        if (dSlots) cudaFree(dSlots);
+        W2X_CUDA(cudaMalloc(&dSlots, sizeof(TileSlot) * stepCount));
+        slotCap = stepCount;
+    }
+    W2X_CUDA(cudaMemcpy(dSlots, slots.data(), sizeof(TileSlot) * stepCount, cudaMemcpyHostToDevice));
+    const size_t tileElems = (size_t)outTile * outTile * 4;
+    if ((size_t)stepCount * tileElems > tileOutCap) {
+        if (dTileOut) cudaFree(dTileOut);
+        W2X_CUDA(cudaMalloc(&dTileOut, (size_t)stepCount * tileElems * sizeof(__half)));
+        tileOutCap = (size_t)stepCount * tileElems;
+    }
+    if (cfg.tta && (size_t)grid.count * tileElems > ttaCap) {
+        if (dTtaMean) cudaFree(dTtaMean);
+        W2X_CUDA(cudaMalloc(&dTtaMean, (size_t)grid.count * tileElems * sizeof(float)));
+        ttaCap = (size_t)grid.count * tileElems;
+    }
+    if (rampXLen != grid.outOvX) {
+        if (dRampX) { cudaFree(dRampX); dRampX = nullptr; }
+        std::vector<float> r = blendRamp(grid.outOvX);
+        W2X_CUDA(cudaMalloc(&dRampX, std::max<size_t>(r.size(), 1) * 4));
+        if (!r.empty()) W2X_CUDA(cudaMemcpy(dRampX, r.data(), r.size() * 4, cudaMemcpyHostToDevice));
+        rampXLen = grid.outOvX;
+    }
+    if (rampYLen != grid.outOvY) {
+        if (dRampY) { cudaFree(dRampY); dRampY = nullptr; }
+        std::vector<float> r = blendRamp(grid.outOvY);
+        W2X_CUDA(cudaMalloc(&dRampY, std::max<size_t>(r.size(), 1) * 4));
+        if (!r.empty()) W2X_CUDA(cudaMemcpy(dRampY, r.data(), r.size() * 4, cudaMemcpyHostToDevice));
+        rampYLen = grid.outOvY;
+    }
+    frameW = w;
+    frameH = h;
+}
+
+void Engine::renderOnStream(const uint8_t* dSrc, int w, int h, size_t srcPitch, uint8_t* dDst, size_t dstPitch, cudaStream_t s, bool timed) {
+    ensureFrameBuffers(w, h);
+    if (timed) { evUsed = 0; spans.clear(); }
+    auto span = [&](int kind, auto&& fn) {
+        if (!timed) { fn(); return; }
+        cudaEvent_t e0 = nextEvent();
+        const int i0 = evUsed - 1;
+        W2X_CUDA(cudaEventRecord(e0, s));
+        fn();
+        cudaEvent_t e1 = nextEvent();
+        W2X_CUDA(cudaEventRecord(e1, s));
+        spans.push_back({kind, i0, evUsed - 1});
+    };
+    const size_t tileElems = (size_t)outTile * outTile * 4;
+    for (int b = 0; b < batchCount; ++b) {
+        const auto t0 = std::chrono::steady_clock::now();
+        span(0, [&] {
+            launchUnpack(dSrc, w, h, srcPitch, dSlots + (size_t)b * batch, batch, tile, actIn.p, s);
+            ++launches;
+        });
+        span(1, [&] { runModel(s, dTileOut + (size_t)b * batch * tileElems); });
+        if (progCb) {
+            const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            progCb(b + 1, batchCount, 1000.0 / std::max(ms, 1e-6), progUser);  // render.cpp:336-338
+        }
+    }
+    span(2, [&] {
+        StitchParams sp{};
+        sp.outT = outTile; sp.nx = grid.nx; sp.ny = grid.ny; sp.ovx = grid.outOvX; sp.ovy = grid.outOvY;
+        sp.cw = w * scale; sp.ch = h * scale;
+        sp.rampx = dRampX; sp.rampy = dRampY;
+        sp.dst = dDst; sp.pitch = dstPitch;
+        if (cfg.tta) {
+            launchTtaReduce(dTileOut, grid.count, outTile, dTtaMean, s);
+            ++launches;
+            sp.tiles = dTtaMean; sp.f32 = 1;
+        } else {
+            sp.tiles = dTileOut; sp.f32 = 0;
+        }
+        launchStitch(sp, s);
+        ++launches;
+    });
+    W2X_CUDA(cudaGetLastError());
+}
+
+int Engine::lastStageMs(float* out, int n) {
+    if (!stream) return 0;
+    cudaStreamSynchronize(stream);
+    float acc[4] = {0, 0, 0, 0};
+    for (const auto& sp : spans) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, evPool[sp.e0], evPool[sp.e1]) == cudaSuccess) acc[sp.kind] += ms;
+    }
+    if (!spans.empty()) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, evPool[spans.front().e0], evPool[spans.back().e1]) == cudaSuccess) acc[3] = ms;
+    }
+    const int k = std::min(n, 4);
+    for (int i = 0; i < k; ++i) out[i] = acc[i];
+    return k;
+}
+
+bool Engine::renderDevice(const uint8_t* dSrc, int w, int h, size_t srcStride, uint8_t* dDst, size_t dstStride) {
+    try {
+        if (!isLoaded) throw Error("no engine loaded");
+        W2X_CUDA(cudaSetDevice(cfg.deviceId));
+        renderOnStream(dSrc, w, h, srcStride, dDst, dstStride, stream, true);
+        return true;
+    } catch (const std::exception& ex) {
+        ELOG(W2X_ERROR, std::string("Render failed unexpectedly: ") + ex.what() + ".");
+        return false;
+    }
+}
+
+bool Engine::render(const uint8_t* src, int w, int h, size_t srcStride, uint8_t* dst, size_t dstStride) {
+    try {
+        if (!isLoaded) throw Error("no engine loaded");
+        W2X_CUDA(cudaSetDevice(cfg.deviceId));
+        const size_t inBytes = (size_t)w * 3 * h, outBytes = (size_t)w * scale * 3 * h * scale;
+        if (inBytes > frameInCap) {
+            if (dFrameIn) cudaFree(dFrameIn);
+            W2X_CUDA(cudaMalloc(&dFrameIn, inBytes));
+            frameInCap = inBytes;
+        }
+        if (outBytes > frameOutCap) {
+            if (dFrameOut) cudaFree(dFrameOut);
+            W2X_CUDA(cudaMalloc(&dFrameOut, outBytes));
+            frameOutCap = outBytes;
+        }
+        W2X_CUDA(cudaMemcpy2DAsync(dFrameIn, (size_t)w * 3, src, srcStride, (size_t)w * 3, h, cudaMemcpyHostToDevice, stream));  // render.cpp:226
+        renderOnStream(dFrameIn, w, h, (size_t)w * 3, dFrameOut, (size_t)w * scale * 3, stream, true);
+        W2X_CUDA(cudaMemcpy2DAsync(dst, dstStride, dFrameOut, (size_t)w * scale * 3, (size_t)w * scale * 3, (size_t)h * scale,
+                                   cudaMemcpyDeviceToHost, stream));  // render.cpp:344
+        W2X_CUDA(cudaStreamSynchronize(stream));  // the sync the reference leaves commented out (render.cpp:345)
+        return true;
+    } catch (const std::exception& ex) {
+        ELOG(W2X_ERROR, std::string("Render failed unexpectedly: ") + ex.what() + ".");
+        return false;
+    }
+}
+
+// Pipelined frames: H2D (copy stream) -> compute (engine stream) -> D2H (copy stream), kSlots frames in flight.
+int Engine::submit(const uint8_t* src, int w, int h, size_t srcStride, uint8_t* dst, size_t dstStride) {
+    try {
+        if (!isLoaded) throw Error("no engine loaded");
+        W2X_CUDA(cudaSetDevice(cfg.deviceId));
+        const int ticket = nextTicket;
+        PipeSlot& ps = pipe[ticket % kSlots];
+        if (!ps.evH2D) {
+            W2X_CUDA(cudaEventCreateWithFlags(&ps.evH2D, cudaEventDisableTiming));
+            W2X_CUDA(cudaEventCreateWithFlags(&ps.evComp, cudaEventDisableTiming));
+            W2X_CUDA(cudaEventCreateWithFlags(&ps.evDone, cudaEventDisableTiming));
+        }
+        if (ps.busy) { W2X_CUDA(cudaEventSynchronize(ps.evDone)); ps.busy = false; }
+        const size_t inBytes = (size_t)w * 3 * h, outBytes = (size_t)w * scale * 3 * h * scale;
+        if (inBytes > ps.inCap) {
+            if (ps.dIn) cudaFree(ps.dIn);
+            W2X_CUDA(cudaMalloc(&ps.dIn, inBytes));
+            ps.inCap = inBytes;
+        }
+        if (outBytes > ps.outCap) {
+            if (ps.dOut) cudaFree(ps.dOut);
+            W2X_CUDA(cudaMalloc(&ps.dOut, outBytes));
+            ps.outCap = outBytes;
+        }
+        ensureFrameBuffers(w, h);
+        W2X_CUDA(cudaMemcpy2DAsync(ps.dIn, (size_t)w * 3, src, srcStride, (size_t)w * 3, h, cudaMemcpyHostToDevice, h2dStream));
+        W2X_CUDA(cudaEventRecord(ps.evH2D, h2dStream));
+        W2X_CUDA(cudaStreamWaitEvent(stream, ps.evH2D, 0));
+        renderOnStream(ps.dIn, w, h, (size_t)w * 3, ps.dOut, (size_t)w * scale * 3, stream, false);
+        W2X_CUDA(cudaEventRecord(ps.evComp, stream));
+        W2X_CUDA(cudaStreamWaitEvent(d2hStream, ps.evComp, 0));
+        W2X_CUDA(cudaMemcpy2DAsync(dst, dstStride, ps.dOut, (size_t)w * scale * 3, (size_t)w * scale * 3, (size_t)h * scale,
+                                   cudaMemcpyDeviceToHost, d2hStream));
+        W2X_CUDA(cudaEventRecord(ps.evDone, d2hStream));
+        ps.busy = true;
+        ++nextTicket;
+        return ticket;
+    } catch (const std::exception& ex) {
+        ELOG(W2X_ERROR, std::string("Submit failed unexpectedly: ") + ex.what() + ".");
+        return -1;
+    }
+}
+
+bool Engine::wait(int ticket) {
+    try {
+        if (ticket < 0 || ticket >= nextTicket) throw Error("invalid ticket");
+        if (nextTicket - ticket > kSlots) return true;  // slot already recycled => that frame completed
+        PipeSlot& ps = pipe[ticket % kSlots];
+        if (ps.busy) { W2X_CUDA(cudaEventSynchronize(ps.evDone)); ps.busy = false; }
+        return true;
+    } catch (const std::exception& ex) {
+        ELOG(W2X_ERROR, std::string("Wait failed: ") + ex.what() + ".");
+        return false;
+    }
+}
+
+bool Engine::sync() {
+    try {
+        if (h2dStream) W2X_CUDA(cudaStreamSynchronize(h2dStream));
+        if (stream) W2X_CUDA(cudaStreamSynchronize(stream));
+        if (d2hStream) W2X_CUDA(cudaStreamSynchronize(d2hStream));
+        for (auto& s : pipe) s.busy = false;
+        return true;
+    } catch (const std::exception& ex) {
+        ELOG(W2X_ERROR, std::string("Sync failed: ") + ex.what() + ".");
+        return false;
+    }
+}
+
+// Img2Img::infer-shaped entry (img2img_infer.cpp:41-93): NCHW f32 host -> NCHW f32 host.
+bool Engine::infer(const float* inNchw, int n, float* outNchw) {
+    try {
+        if (!isLoaded) throw Error("no engine loaded");
+        if (n < 1 || n > batch) {
+            ELOG(W2X_ERROR, "Input has invalid batch size: expected " + std::to_string(batch) + ", got " + std::to_string(n) + ".");
+            return false;
+        }
+        W2X_CUDA(cudaSetDevice(cfg.deviceId));
+        const size_t inElems = (size_t)n * 3 * tile * tile, outElems = (size_t)n * 3 * outTile * outTile;
+        float *dIn = nullptr, *dOut = nullptr;
+        __half* dOutH = nullptr;
+        W2X_CUDA(cudaMalloc(&dIn, inElems * 4));
+        W2X_CUDA(cudaMalloc(&dOut, outElems * 4));
+        W2X_CUDA(cudaMalloc(&dOutH, (size_t)batch * outTile * outTile * 4 * 2));
+        try {
+            W2X_CUDA(cudaMemcpyAsync(dIn, inNchw, inElems * 4, cudaMemcpyHostToDevice, stream));
+            W2X_CUDA(cudaMemsetAsync(actIn.p, 0, actIn.elems() * 2, stream));
+            launchNchwToNhwc4(dIn, n, tile, actIn.p, stream);
+            runModel(stream, dOutH);
+            launchNhwc4ToNchw(dOutH, n, outTile, dOut, stream);
+            launches += 2;
+            W2X_CUDA(cudaMemcpyAsync(outNchw, dOut, outElems * 4, cudaMemcpyDeviceToHost, stream));
+            W2X_CUDA(cudaStreamSynchronize(stream));
+        } catch (...) {
+            cudaFree(dIn); cudaFree(dOut); cudaFree(dOutH);
+            throw;
+        }
+        cudaFree(dIn); cudaFree(dOut); cudaFree(dOutH);
+        return true;
+    } catch (const std::exception& ex) {
+        ELOG(W2X_ERROR, std::string("Engine inference failed unexpectedly: ") + ex.what() + ".");
+        return false;
+    }
+}
+
+int Engine::profileLayers(int repeats, char (*names)[48], float* ms, double* flops, int cap) {
+    try {
+        if (!isLoaded) throw Error("no engine loaded");
+        W2X_CUDA(cudaSetDevice(cfg.deviceId));
+        cudaEvent_t e0, e1;
+        W2X_CUDA(cudaEventCreate(&e0));
+        W2X_CUDA(cudaEventCreate(&e1));
+        runModel(stream, nullptr);  // warm-up, and populates every activation
+        W2X_CUDA(cudaStreamSynchronize(stream));
+        int i = 0;
+        for (auto& L : layers) {
+            if (i >= cap) break;
+            W2X_CUDA(cudaEventRecord(e0, stream));
+            for (int r = 0; r < repeats; ++r) {
+                if (L.impl == IMPL_IGEMM) igemmLaunch(L.plan, stream, nullptr);
+                else if (L.impl == IMPL_FIRST) launchConvFirst(L.p, stream);
+                else launchConvDirect(L.p, stream);
+                if (L.seR) {
+                    launchSeSqueeze(L.p.out, L.p.gn, L.p.out_h, L.p.out_w, L.p.out_c, L.sePartial, L.seBlocks, stream);
+                    launchSeExcite(L.sePartial, L.seBlocks, L.p.gn, L.p.out_c, L.seR, L.p.out_h * L.p.out_w, L.seW1, L.seB1, L.seW2, L.seB2, L.seScale, stream);
+                    launchSeScale(L.p.out, L.p.gn, L.p.out_h, L.p.out_w, L.p.out_c, L.seScale, stream);
+                }
+            }
+            W2X_CUDA(cudaEventRecord(e1, stream));
+            W2X_CUDA(cudaEventSynchronize(e1));
+            float t = 0;
+            W2X_CUDA(cudaEventElapsedTime(&t, e0, e1));
+            std::snprintf(names[i], 48, "%s", L.name.c_str());
+            ms[i] = t / repeats;
+            flops[i] = L.flops * batch;
+            ++i;
+        }
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        return i;
+    } catch (const std::exception& ex) {
+        ELOG(W2X_ERROR, std::string("Profile failed: ") + ex.what() + ".");
+        return -1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// On-device self-check: tcgen05 implicit GEMM vs the scalar CUDA-core reference on random data.
+// ------------------------------------------------------------------------------------------------
+double selftestConv(int device, int kind, int n, int h, int w, int cin, int cout, unsigned seed) {
+    if (cudaSetDevice(device) != cudaSuccess) return -1.0;
+    std::vector<void*> bufs;
+    auto dmal = [&](size_t bytes) { void* p = nullptr; W2X_CUDA(cudaMalloc(&p, bytes + 256)); bufs.push_back(p); return p; };
+    double result = -1.0;
+    IgemmPlan* plan = nullptr;
+    try {
+        std::mt19937 rng(seed);
+        std::uniform_real_distribution<float> U(-1.f, 1.f);
+        auto randHalf = [&](size_t cnt, float scale_) {
+            std::vector<uint16_t> v(cnt);
+            for (auto& x : v) x = floatToHalfBits(U(rng) * scale_);
+            return v;
+        };
+        auto upH = [&](const std::vector<uint16_t>& v) { __half* d = (__half*)dmal(v.size() * 2); W2X_CUDA(cudaMemcpy(d, v.data(), v.size() * 2, cudaMemcpyHostToDevice)); return d; };
+        Act in{nullptr, n, h, w, cin};
+        in.p = upH(randHalf(in.elems(), 1.f));
+        Act out{}, skip{};
+        ConvParams p{};
+        int npad = 0, ktot = 0;
+        if (kind == 0) { npad = (cout + 15) / 16 * 16; ktot = 9 * cin; out = {nullptr, n, h - 2, w - 2, cout}; }
+        else if (kind == 1) { npad = (cout + 15) / 16 * 16; ktot = 4 * cin; out = {nullptr, n, h / 2, w / 2, cout}; }
+        else if (kind == 2) { npad = 4 * cout; ktot = cin; out = {nullptr, n, 2 * h, 2 * w, cout}; skip = {nullptr, n, 2 * h + 8, 2 * w + 8, cout}; }
+        else if (kind == 3) { npad = 16; ktot = 4 * cin; out = {nullptr, n, 2 * h - 4, 2 * w - 4, 4}; }
+        else if (kind == 4) { npad = 16; ktot = 9 * cin; out = {nullptr, n, h - 2, w - 2, 4}; skip = {nullptr, n, h - 2 + 40, w - 2 + 40, 4}; }
+        else throw Error("bad kind");
+        const float wscale = 1.0f / std::sqrt((float)ktot);
+        std::vector<uint16_t> wh = randHalf((size_t)npad * ktot, wscale);
+        if (kind == 3 || kind == 4) {  // zero the padding columns like the packer does
+            for (int nn = 0; nn < npad; ++nn) {
+                const bool real = kind == 3 ? (nn % 4) < 3 : nn < 3;
+                if (!real) for (int k = 0; k < ktot; ++k) wh[(size_t)nn * ktot + k] = 0;
+            }
+        }
+        __half* dWt = upH(wh);
+        std::vector<float> bias(npad);
+        for (int i = 0; i < npad; ++i) bias[i] = ((kind == 3 && (i % 4) == 3) || (kind == 4 && i >= 3)) ? 0.f : U(rng) * 0.1f;
+        float* dB = (float*)dmal(npad * 4);
+        W2X_CUDA(cudaMemcpy(dB, bias.data(), npad * 4, cudaMemcpyHostToDevice));
+        if (skip.n) skip.p = upH(randHalf(skip.elems(), 0.5f));
+        __half* outA = (__half*)dmal(out.elems() * 2);
+        __half* outB = (__half*)dmal(out.elems() * 2);
+        W2X_CUDA(cudaMemset(outA, 0, out.elems() * 2));
+        W2X_CUDA(cudaMemset(outB, 0, out.elems() * 2));
+        out.p = outA;
+        if (kind == 0) p = makeConv3Params(in, out, dWt, dB, npad, EPI_STORE, 0.1f, cout);
+        else if (kind == 1) p = makeDown2Params(in, out, dWt, dB, npad, 0.1f);
+        else if (kind == 2) p = makeUp2Params(in, out, dWt, dB, cout, 0.1f, &skip, 4);
+        else if (kind == 3) p = makeUp4Params(in, out, dWt, dB);
+        else {
+            p = makeConv3Params(in, out, dWt, dB, npad, EPI_FINAL, 1.f, 4);
+            p.skip = skip.p; p.skip_h = skip.h; p.skip_w = skip.w; p.skip_c = 4; p.skip_off = 20;
+        }
+        launchConvDirect(p, nullptr);
+        W2X_CUDA(cudaDeviceSynchronize());
+        plan = igemmCreatePlan(p);
+        igemmLaunch(plan, nullptr, outB);
+        W2X_CUDA(cudaDeviceSynchronize());
+        std::vector<uint16_t> ha(out.elems()), hb(out.elems());
+        W2X_CUDA(cudaMemcpy(ha.data(), outA, ha.size() * 2, cudaMemcpyDeviceToHost));
+        W2X_CUDA(cudaMemcpy(hb.data(), outB, hb.size() * 2, cudaMemcpyDeviceToHost));
+        double md = 0, ma = 0;
+        for (size_t i = 0; i < ha.size(); ++i) {
+            const double a = halfBitsToFloat(ha[i]), b = halfBitsToFloat(hb[i]);
+            md = std::max(md, std::fabs(a - b));
+            ma = std::max(ma, std::fabs(a));
+        }
+        result = (ma > 0) ? md : 1e9;  // an all-zero reference means the check itself is broken
+    } catch (const std::exception& ex) {
+        std::fprintf(stderr, "w2x selftest: %s\n", ex.what());
+        result = -1.0;
+    }
+    if (plan) igemmDestroyPlan(plan);
+    for (void* b : bufs) cudaFree(b);
+    return result;
+}
+
+}  // namespace w2x

@@ -1,0 +1,143 @@
+// Engine: the B200-native replacement for trt::Img2Img (/root/reference/src/tensorrt/img2img.h:14-50).
+// Owns the packed model in HBM, all activation/tile workspaces, streams and events.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "hostutil.h"
+#include "kernels/conv_params.h"
+#include "model_pack.h"
+
+namespace w2x {
+
+#define W2X_CUDA(expr)                                                                                  \
+    do {                                                                                                \
+        cudaError_t _e = (expr);                                                                        \
+        if (_e != cudaSuccess) throw ::w2x::Error(std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+
+struct Act {
+    __half* p = nullptr;
+    int n = 0, h = 0, w = 0, c = 0;
+    size_t elems() const { return (size_t)n * h * w * c; }
+};
+
+enum ConvImpl { IMPL_DIRECT = 0, IMPL_FIRST = 1, IMPL_IGEMM = 2 };
+
+struct LayerExec {
+    std::string name;
+    ConvParams p{};
+    int impl = IMPL_DIRECT;
+    IgemmPlan* plan = nullptr;
+    double flops = 0;  // algorithmic 2*MAC for ONE tile
+    bool isFinal = false;
+    // squeeze/excite applied to p.out after the conv
+    int seR = 0;
+    const float *seW1 = nullptr, *seB1 = nullptr, *seW2 = nullptr, *seB2 = nullptr;
+    float* sePartial = nullptr;
+    float* seScale = nullptr;
+    int seBlocks = 0;
+};
+
+// Builders for the implicit-GEMM views (shared with the self-test).
+ConvParams makeConv3Params(const Act& in, const Act& out, const __half* w, const float* bias, int npad, int mode, float slope, int storeC);
+ConvParams makeDown2Params(const Act& in, const Act& out, const __half* w, const float* bias, int npad, float slope);
+ConvParams makeUp2Params(const Act& in, const Act& out, const __half* w, const float* bias, int cout, float slope, const Act* skip, int skipOff);
+ConvParams makeUp4Params(const Act& in, const Act& out, const __half* w, const float* bias);
+
+class Engine {
+public:
+    Engine();
+    ~Engine();
+
+    bool build(const std::string& onnxPath, const w2x_build_config& cfg);
+    bool load(const std::string& onnxPath, const w2x_render_config& cfg);
+    bool render(const uint8_t* src, int w, int h, size_t srcStride, uint8_t* dst, size_t dstStride);
+    bool renderDevice(const uint8_t* dSrc, int w, int h, size_t srcStride, uint8_t* dDst, size_t dstStride);
+    int submit(const uint8_t* src, int w, int h, size_t srcStride, uint8_t* dst, size_t dstStride);
+    bool wait(int ticket);
+    bool sync();
+    bool infer(const float* inNchw, int n, float* outNchw);
+    int profileLayers(int repeats, char (*names)[48], float* ms, double* flops, int cap);
+
+    void setMessageCallback(w2x_message_cb cb, void* user) { msgCb = cb; msgUser = user; }
+    void setProgressCallback(w2x_progress_cb cb, void* user) { progCb = cb; progUser = user; }
+    const char* lastError() const { return lastErr.c_str(); }
+    int outputTile() const { return outTile; }
+    long long launchCount() const { return launches; }
+    double flopsPerTile() const;
+    int lastStageMs(float* out, int n);
+    int device() const { return cfg.deviceId; }
+    bool loaded() const { return isLoaded; }
+
+    void log(int severity, const std::string& msg, const char* func, int line);
+
+private:
+    void unload();
+    void buildPlan();
+    void runModel(cudaStream_t s, __half* finalOut);
+    void ensureFrameBuffers(int w, int h);
+    void renderOnStream(const uint8_t* dSrc, int w, int h, size_t srcPitch, uint8_t* dDst, size_t dstPitch, cudaStream_t s, bool timed);
+    void* dalloc(size_t bytes);
+    Act allocAct(int h, int w, int c);
+
+    w2x_message_cb msgCb = nullptr;
+    void* msgUser = nullptr;
+    w2x_progress_cb progCb = nullptr;
+    void* progUser = nullptr;
+    std::string lastErr;
+
+    bool isLoaded = false;
+    w2x_render_config cfg{};
+    PackedModel model;
+    int tile = 0, outTile = 0, scale = 1, batch = 1;
+    bool useDirect = false;
+
+    std::vector<void*> allocs;       // freed in unload()
+    std::vector<__half*> dW;         // per layer
+    std::vector<float*> dBias;
+    std::vector<LayerExec> layers;
+    Act actIn;                       // [batch][tile][tile][4]
+    Act actOut;                      // final layer output view (pointer overridden per batch)
+    cudaStream_t stream = nullptr, h2dStream = nullptr, d2hStream = nullptr;
+    long long launches = 0;
+
+    // frame-level state
+    int frameW = 0, frameH = 0;
+    TileGrid grid;
+    int stepCount = 0, batchCount = 0;
+    TileSlot* dSlots = nullptr;
+    size_t slotCap = 0;
+    __half* dTileOut = nullptr;      // [steps][outT][outT][4] fp16
+    size_t tileOutCap = 0;
+    float* dTtaMean = nullptr;       // [tiles][outT][outT][4] f32 (TTA only)
+    size_t ttaCap = 0;
+    float *dRampX = nullptr, *dRampY = nullptr;
+    int rampXLen = -1, rampYLen = -1;
+    // host-buffer paths
+    uint8_t *dFrameIn = nullptr, *dFrameOut = nullptr;
+    size_t frameInCap = 0, frameOutCap = 0;
+    // pipelined submit
+    static constexpr int kSlots = 3;
+    struct PipeSlot {
+        uint8_t *dIn = nullptr, *dOut = nullptr;
+        size_t inCap = 0, outCap = 0;
+        cudaEvent_t evH2D = nullptr, evComp = nullptr, evDone = nullptr;
+        bool busy = false;
+    } pipe[kSlots];
+    int nextTicket = 0;
+    // stage timing
+    std::vector<cudaEvent_t> evPool;
+    int evUsed = 0;
+    struct StageSpan { int kind, e0, e1; };
+    std::vector<StageSpan> spans;
+    cudaEvent_t nextEvent();
+};
+
+// On-device self-check of one implicit-GEMM layer (tcgen05 vs scalar reference); see w2x.h.
+double selftestConv(int device, int kind, int n, int h, int w, int cin, int cout, unsigned seed);
+
+}  // namespace w2x

@@ -1,0 +1,161 @@
+// Shared description of one implicit-GEMM convolution launch (host + device), and the fused epilogues.
+//
+// Every dense layer of the model hot path is expressed as
+//     D[pixel, n] = sum_{tap, c} A(pixel + tap, c) * B[n, tap*cin + c]
+// over a 5-D strided view (c, x, z, y, img) of an NHWC fp16 activation, followed by one of four epilogues that
+// fuse bias + LeakyReLU(0.1), depth-to-space (ConvTranspose), the cropped skip-add, and the final add + clamp.
+#pragma once
+#include <cuda_fp16.h>
+#include <cstdint>
+
+namespace w2x {
+
+enum EpiMode : int {
+    EPI_STORE = 0,  // out[img][y][x][0..cout) = lrelu(acc + bias)
+    EPI_D2S = 1,    // ConvTranspose 2x2 s2: column (q*cout+co) -> out[img][2y+q/2][2x+q%2][co] = lrelu(acc+bias) + skip
+    EPI_UP4 = 2,    // ConvTranspose 4x4 s2 p3 head: column (q*4+co) -> out[img][2y-1+q/2][2x-1+q%2][co] = acc + bias
+    EPI_FINAL = 3,  // image head: out[img][y][x][0..4) = clamp(acc + bias + skip[img][y+off][x+off], 0, 1)
+};
+
+struct ConvTap {
+    int c0, dx, dz, dy;  // offsets along (c, x, z, y) of the 5-D view
+};
+
+struct ConvParams {
+    // A operand view (element strides; c is contiguous)
+    const __half* in;
+    long long sx, sz, sy, sn;
+    int dimc, dimx, dimz, dimy;  // view extents (for the TMA map)
+    int cin;                     // channels per tap
+    int ntaps;
+    ConvTap tap[9];
+    // GEMM extents
+    int gx, gy, gn;  // pixel grid per image (x, y) and image count
+    int npad, ktot;
+    const __half* w;    // B: [npad][ktot], K-major
+    const float* bias;  // [npad]
+    // epilogue
+    int mode;
+    float slope;  // LeakyReLU negative slope; 1.0f = linear
+    __half* out;
+    int out_h, out_w, out_c;
+    int cout;  // EPI_STORE: channels stored (4 or a multiple of 8); EPI_D2S: channels per phase
+    const __half* skip;
+    int skip_h, skip_w, skip_c, skip_off;
+    const float* skip_scale;  // optional per-(img, channel) multiplier applied to skip (SE fold), or nullptr
+    float* se_sum;            // optional [gn][cout] fp32: per-channel sums of the stored activations (SE squeeze)
+};
+
+#ifdef __CUDACC__
+
+__device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.f ? v : v * slope; }
+
+struct alignas(16) Half8 { __half2 a, b, c, d; };
+struct alignas(8) Half4 { __half2 a, b; };
+
+// Epilogue for 8 consecutive GEMM columns [j0, j0+8) of pixel (img, y, x); v = raw fp32 accumulators.
+// The caller guarantees y < gy, x < gx, img < gn and j0 % 8 == 0.
+__device__ __forceinline__ void conv_epilogue8(const ConvParams& p, int img, int y, int x, int j0, const float* v) {
+    float r[8];
+    if (p.mode == EPI_STORE) {
+        if (j0 >= p.cout) return;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r[i] = lrelu(v[i] + __ldg(p.bias + j0 + i), p.slope);
+        __half* o = p.out + (((long long)img * p.out_h + y) * p.out_w + x) * p.out_c + j0;
+        if (p.cout - j0 >= 8) {
+            Half8 h{__floats2half2_rn(r[0], r[1]), __floats2half2_rn(r[2], r[3]), __floats2half2_rn(r[4], r[5]),
+                    __floats2half2_rn(r[6], r[7])};
+            *reinterpret_cast<Half8*>(o) = h;
+        } else {
+            Half4 h{__floats2half2_rn(r[0], r[1]), __floats2half2_rn(r[2], r[3])};
+            *reinterpret_cast<Half4*>(o) = h;
+        }
+    } else if (p.mode == EPI_D2S) {
+        const int q = j0 / p.cout, co = j0 - q * p.cout;
+        const int oy = 2 * y + (q >> 1), ox = 2 * x + (q & 1);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r[i] = lrelu(v[i] + __ldg(p.bias + j0 + i), p.slope);
+        if (p.skip) {
+            const __half* s = p.skip + (((long long)img * p.skip_h + oy + p.skip_off) * p.skip_w + ox + p.skip_off) * p.skip_c + co;
+            const Half8 sv = *reinterpret_cast<const Half8*>(s);
+            float f[8];
+            float2 t;
+            t = __half22float2(sv.a); f[0] = t.x; f[1] = t.y;
+            t = __half22float2(sv.b); f[2] = t.x; f[3] = t.y;
+            t = __half22float2(sv.c); f[4] = t.x; f[5] = t.y;
+            t = __half22float2(sv.d); f[6] = t.x; f[7] = t.y;
+            if (p.skip_scale) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[i] *= __ldg(p.skip_scale + (long long)img * p.skip_c + co + i);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) r[i] += f[i];
+        }
+        __half* o = p.out + (((long long)img * p.out_h + oy) * p.out_w + ox) * p.out_c + co;
+        Half8 h{__floats2half2_rn(r[0], r[1]), __floats2half2_rn(r[2], r[3]), __floats2half2_rn(r[4], r[5]),
+                __floats2half2_rn(r[6], r[7])};
+        *reinterpret_cast<Half8*>(o) = h;
+    } else if (p.mode == EPI_UP4) {
+        if (j0 >= 16) return;
+#pragma unroll
+        for (int hsel = 0; hsel < 2; ++hsel) {
+            const int q = (j0 >> 2) + hsel;
+            const int oy = 2 * y - 1 + (q >> 1), ox = 2 * x - 1 + (q & 1);
+            if (oy < 0 || ox < 0 || oy >= p.out_h || ox >= p.out_w) continue;
+            const float* vv = v + 4 * hsel;
+            const float* bb = p.bias + j0 + 4 * hsel;
+            Half4 h{__floats2half2_rn(vv[0] + __ldg(bb + 0), vv[1] + __ldg(bb + 1)),
+                    __floats2half2_rn(vv[2] + __ldg(bb + 2), vv[3] + __ldg(bb + 3))};
+            *reinterpret_cast<Half4*>(p.out + (((long long)img * p.out_h + oy) * p.out_w + ox) * p.out_c) = h;
+        }
+    } else {  // EPI_FINAL
+        if (j0 != 0) return;
+        const Half4 sv = *reinterpret_cast<const Half4*>(
+            p.skip + (((long long)img * p.skip_h + y + p.skip_off) * p.skip_w + x + p.skip_off) * p.skip_c);
+        const float2 s0 = __half22float2(sv.a), s1 = __half22float2(sv.b);
+        r[0] = fminf(fmaxf(v[0] + __ldg(p.bias + 0) + s0.x, 0.f), 1.f);
+        r[1] = fminf(fmaxf(v[1] + __ldg(p.bias + 1) + s0.y, 0.f), 1.f);
+        r[2] = fminf(fmaxf(v[2] + __ldg(p.bias + 2) + s1.x, 0.f), 1.f);
+        r[3] = 0.f;
+        Half4 h{__floats2half2_rn(r[0], r[1]), __floats2half2_rn(r[2], r[3])};
+        *reinterpret_cast<Half4*>(p.out + (((long long)img * p.out_h + y) * p.out_w + x) * p.out_c) = h;
+    }
+}
+
+#endif  // __CUDACC__
+
+// host-side launchers (kernels/*.cu)
+void launchConvDirect(const ConvParams& p, cudaStream_t s);       // scalar CUDA-core reference (tests / self-check only)
+void launchConvFirst(const ConvParams& p, cudaStream_t s);        // cin=4 -> 32 first layer (CUDA cores)
+struct IgemmPlan;                                                 // opaque: tensor maps + launch geometry
+IgemmPlan* igemmCreatePlan(const ConvParams& p);                  // throws w2x::Error when unsupported
+void igemmDestroyPlan(IgemmPlan* plan);
+void igemmLaunch(const IgemmPlan* plan, cudaStream_t s, __half* outOverride = nullptr);
+bool igemmSupported(const ConvParams& p);
+
+// squeeze/excite
+void launchSeSqueeze(const __half* x, int n, int h, int w, int c, float* partial, int nblk, cudaStream_t s);
+void launchSeExcite(const float* partial, int nblk, int n, int c, int r, int hw, const float* w1, const float* b1,
+                    const float* w2, const float* b2, float* scale, cudaStream_t s);
+void launchSeScale(__half* x, int n, int h, int w, int c, const float* scale, cudaStream_t s);
+
+// tiling (kernels/tiling.cu)
+struct TileSlot { int x, y, aug, valid; };  // input rect origin, D4 op, 0 = zero dummy slot (img2img_render.cpp:281)
+void launchUnpack(const uint8_t* frame, int w, int h, size_t pitch, const TileSlot* slots, int nslots, int tile,
+                  __half* out, cudaStream_t s);
+struct StitchParams {
+    const void* tiles;   // [count][outT][outT][4] fp16 or f32
+    int f32;             // element type of tiles
+    int outT, nx, ny, ovx, ovy, cw, ch;
+    const float* rampx;  // [ovx]
+    const float* rampy;  // [ovy]
+    uint8_t* dst;
+    size_t pitch;
+};
+void launchStitch(const StitchParams& p, cudaStream_t s);
+void launchTtaReduce(const __half* outs, int tiles, int outT, float* mean, cudaStream_t s);
+// NCHW f32 <-> NHWC4 fp16 (Img2Img::infer host entry, tests)
+void launchNchwToNhwc4(const float* in, int n, int t, __half* out, cudaStream_t s);
+void launchNhwc4ToNchw(const __half* in, int n, int t, float* out, cudaStream_t s);
+
+}  // namespace w2x

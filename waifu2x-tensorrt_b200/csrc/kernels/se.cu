@@ -1,0 +1,103 @@
+// Squeeze/excite (SEBlock of the CUNet family): per-tile global mean -> FC -> ReLU -> FC -> sigmoid ->
+// per-(tile, channel) scale.  Deterministic two-stage reduction (no float atomics): the result must not depend on
+// scheduling, because tile outputs are compared bit-for-bit between 1-GPU and N-GPU runs.
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include "conv_params.h"
+
+namespace w2x {
+
+// grid (nblk, n), 256 threads.  Thread t owns channel pair (t % (c/2)) of pixels p = t / (c/2) + k * (256 / (c/2)).
+__global__ void __launch_bounds__(256) se_squeeze_kernel(const __half* __restrict__ x, int hw, int c,
+                                                         float* __restrict__ partial, int nblk) {
+    extern __shared__ float red[];  // [256][2]
+    const int img = blockIdx.y, blk = blockIdx.x;
+    const int cp = c >> 1;
+    const int lane_c = threadIdx.x % cp, lane_p = threadIdx.x / cp, pstride = 256 / cp;
+    const int per = (hw + nblk - 1) / nblk;
+    const int p0 = blk * per, p1 = min(hw, p0 + per);
+    const __half2* base = reinterpret_cast<const __half2*>(x + (size_t)img * hw * c);
+    float s0 = 0.f, s1 = 0.f;
+    for (int p = p0 + lane_p; p < p1; p += pstride) {
+        const float2 v = __half22float2(base[(size_t)p * cp + lane_c]);
+        s0 += v.x;
+        s1 += v.y;
+    }
+    red[threadIdx.x * 2] = s0;
+    red[threadIdx.x * 2 + 1] = s1;
+    __syncthreads();
+    if (threadIdx.x < cp) {
+        float a = 0.f, b = 0.f;
+        for (int k = 0; k < pstride; ++k) {
+            a += red[(k * cp + threadIdx.x) * 2];
+            b += red[(k * cp + threadIdx.x) * 2 + 1];
+        }
+        float* o = partial + ((size_t)img * nblk + blk) * c + 2 * threadIdx.x;
+        o[0] = a;
+        o[1] = b;
+    }
+}
+
+void launchSeSqueeze(const __half* x, int n, int h, int w, int c, float* partial, int nblk, cudaStream_t s) {
+    dim3 grid(nblk, n);
+    se_squeeze_kernel<<<grid, 256, 256 * 2 * sizeof(float), s>>>(x, h * w, c, partial, nblk);
+}
+
+// grid n, block 256.  mean -> relu(W1 mean + b1) -> sigmoid(W2 h + b2)
+__global__ void __launch_bounds__(256) se_excite_kernel(const float* __restrict__ partial, int nblk, int c, int r, float inv_hw,
+                                                        const float* __restrict__ w1, const float* __restrict__ b1,
+                                                        const float* __restrict__ w2, const float* __restrict__ b2,
+                                                        float* __restrict__ scale) {
+    __shared__ float mean[256];
+    __shared__ float hid[64];
+    const int img = blockIdx.x;
+    for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+        float s = 0.f;
+        for (int b = 0; b < nblk; ++b) s += partial[((size_t)img * nblk + b) * c + ch];
+        mean[ch] = s * inv_hw;
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < r; j += blockDim.x) {
+        float s = b1[j];
+        for (int ch = 0; ch < c; ++ch) s = fmaf(w1[j * c + ch], mean[ch], s);
+        hid[j] = fmaxf(s, 0.f);
+    }
+    __syncthreads();
+    for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+        float s = b2[ch];
+        for (int j = 0; j < r; ++j) s = fmaf(w2[ch * r + j], hid[j], s);
+        scale[(size_t)img * c + ch] = 1.f / (1.f + expf(-s));
+    }
+}
+
+void launchSeExcite(const float* partial, int nblk, int n, int c, int r, int hw, const float* w1, const float* b1,
+                    const float* w2, const float* b2, float* scale, cudaStream_t s) {
+    se_excite_kernel<<<n, 256, 0, s>>>(partial, nblk, c, r, 1.0f / (float)hw, w1, b1, w2, b2, scale);
+}
+
+// in-place x *= scale[img][ch], 8 channels (16 B) per thread
+__global__ void __launch_bounds__(256) se_scale_kernel(__half* __restrict__ x, long long vec_per_img, int c,
+                                                       const float* __restrict__ scale) {
+    const int img = blockIdx.y;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= vec_per_img) return;
+    const int c0 = (int)((i * 8) % c);
+    const float* sc = scale + (size_t)img * c + c0;
+    Half8* px = reinterpret_cast<Half8*>(x) + (size_t)img * vec_per_img + i;
+    Half8 v = *px;
+    float2 t;
+    t = __half22float2(v.a); v.a = __floats2half2_rn(t.x * sc[0], t.y * sc[1]);
+    t = __half22float2(v.b); v.b = __floats2half2_rn(t.x * sc[2], t.y * sc[3]);
+    t = __half22float2(v.c); v.c = __floats2half2_rn(t.x * sc[4], t.y * sc[5]);
+    t = __half22float2(v.d); v.d = __floats2half2_rn(t.x * sc[6], t.y * sc[7]);
+    *px = v;
+}
+
+void launchSeScale(__half* x, int n, int h, int w, int c, const float* scale, cudaStream_t s) {
+    const long long vec = (long long)h * w * c / 8;
+    dim3 grid((unsigned)((vec + 255) / 256), n);
+    se_scale_kernel<<<grid, 256, 0, s>>>(x, vec, c, scale);
+}
+
+}  // namespace w2x

@@ -1,0 +1,454 @@
+#include "model_pack.h"
+
+#include <cmath>
+#include <cstring>
+
+#include "hostutil.h"
+
+namespace w2x {
+
+// ------------------------------------------------------------------------------------------------
+// fp16 <-> fp32 on the host (round-to-nearest-even), so packing needs no CUDA.
+// ------------------------------------------------------------------------------------------------
+uint16_t floatToHalfBits(float f) {
+    uint32_t x;
+    std::memcpy(&x, &f, 4);
+    const uint32_t sign = (x >> 16) & 0x8000u;
+    x &= 0x7fffffffu;
+    if (x >= 0x7f800000u) return (uint16_t)(sign | 0x7c00u | (x > 0x7f800000u ? 0x200u : 0));  // inf / nan
+    if (x >= 0x477ff000u) return (uint16_t)(sign | 0x7c00u);                                     // overflow -> inf
+    if (x < 0x33000001u) return (uint16_t)sign;                                                  // underflow -> 0
+    int e = (int)(x >> 23) - 127;
+    uint32_t m = x & 0x7fffffu;
+    if (e < -14) {  // subnormal half
+        m |= 0x800000u;
+        const int shift = -14 - e + 13;  // bits to drop
+        const uint32_t rem = m & ((1u << shift) - 1), half = 1u << (shift - 1);
+        uint32_t r = m >> shift;
+        if (rem > half || (rem == half && (r & 1))) ++r;
+        return (uint16_t)(sign | r);
+    }
+    uint32_t r = ((uint32_t)(e + 15) << 10) | (m >> 13);
+    const uint32_t rem = m & 0x1fffu;
+    if (rem > 0x1000u || (rem == 0x1000u && (r & 1))) ++r;  // carries into the exponent correctly
+    return (uint16_t)(sign | r);
+}
+
+float halfBitsToFloat(uint16_t h) {
+    const uint32_t sign = (uint32_t)(h & 0x8000u) << 16;
+    uint32_t e = (h >> 10) & 0x1f, m = h & 0x3ffu, x;
+    if (e == 0) {
+        if (m == 0) x = sign;
+        else {
+            int s = 0;
+            while (!(m & 0x400u)) { m <<= 1; ++s; }
+            m &= 0x3ffu;
+            x = sign | ((uint32_t)(127 - 15 - s + 1) << 23) | (m << 13);
+        }
+    } else if (e == 31) x = sign | 0x7f800000u | (m << 13);
+    else x = sign | ((e + 112) << 23) | (m << 13);
+    float f;
+    std::memcpy(&f, &x, 4);
+    return f;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Protobuf wire-format reader (just enough for ONNX ModelProto / GraphProto / NodeProto / TensorProto).
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct Span {
+    const uint8_t* p;
+    size_t n;
+};
+struct Field {
+    uint32_t id, wt;
+    uint64_t v;   // varint / fixed
+    Span bytes;   // length-delimited
+};
+struct Reader {
+    const uint8_t* p;
+    const uint8_t* end;
+    explicit Reader(Span s) : p(s.p), end(s.p + s.n) {}
+    bool done() const { return p >= end; }
+    uint64_t varint() {
+        uint64_t v = 0;
+        int s = 0;
+        while (true) {
+            if (p >= end) throw Error("onnx: truncated varint");
+            const uint8_t c = *p++;
+            v |= (uint64_t)(c & 0x7f) << s;
+            if (!(c & 0x80)) return v;
+            s += 7;
+            if (s > 63) throw Error("onnx: varint too long");
+        }
+    }
+    Field next() {
+        Field f{};
+        const uint64_t key = varint();
+        f.id = (uint32_t)(key >> 3);
+        f.wt = (uint32_t)(key & 7);
+        switch (f.wt) {
+            case 0: f.v = varint(); break;
+            case 1:
+                if (end - p < 8) throw Error("onnx: truncated fixed64");
+                std::memcpy(&f.v, p, 8); p += 8; break;
+            case 5: {
+                if (end - p < 4) throw Error("onnx: truncated fixed32");
+                uint32_t t; std::memcpy(&t, p, 4); f.v = t; p += 4; break;
+            }
+            case 2: {
+                const uint64_t n = varint();
+                if ((uint64_t)(end - p) < n) throw Error("onnx: truncated bytes field");
+                f.bytes = {p, (size_t)n};
+                p += n;
+                break;
+            }
+            default: throw Error("onnx: unsupported wire type");
+        }
+        return f;
+    }
+};
+
+std::string str(Span s) { return std::string((const char*)s.p, s.n); }
+
+void readInts(const Field& f, std::vector<int64_t>& out) {
+    if (f.wt == 2) {
+        Reader r(f.bytes);
+        while (!r.done()) out.push_back((int64_t)r.varint());
+    } else out.push_back((int64_t)f.v);
+}
+
+OnnxTensor parseTensor(Span s) {
+    OnnxTensor t;
+    int dtype = 1;
+    Span raw{nullptr, 0};
+    std::vector<float> fdata;
+    std::vector<double> ddata;
+    Reader r(s);
+    while (!r.done()) {
+        Field f = r.next();
+        switch (f.id) {
+            case 1: readInts(f, t.dims); break;
+            case 2: dtype = (int)f.v; break;
+            case 4:
+                if (f.wt == 2) {
+                    for (size_t i = 0; i + 4 <= f.bytes.n; i += 4) { float v; std::memcpy(&v, f.bytes.p + i, 4); fdata.push_back(v); }
+                } else { uint32_t u = (uint32_t)f.v; float v; std::memcpy(&v, &u, 4); fdata.push_back(v); }
+                break;
+            case 7: readInts(f, t.idata); break;
+            case 8: t.name = str(f.bytes); break;
+            case 9: raw = f.bytes; break;
+            case 10:
+                if (f.wt == 2) {
+                    for (size_t i = 0; i + 8 <= f.bytes.n; i += 8) { double v; std::memcpy(&v, f.bytes.p + i, 8); ddata.push_back(v); }
+                } else { double v; std::memcpy(&v, &f.v, 8); ddata.push_back(v); }
+                break;
+            default: break;
+        }
+    }
+    if (dtype == 1) {  // FLOAT
+        if (raw.n) { t.data.resize(raw.n / 4); std::memcpy(t.data.data(), raw.p, t.data.size() * 4); }
+        else t.data = fdata;
+    } else if (dtype == 10) {  // FLOAT16
+        t.data.resize(raw.n / 2);
+        for (size_t i = 0; i < t.data.size(); ++i) { uint16_t h; std::memcpy(&h, raw.p + 2 * i, 2); t.data[i] = halfBitsToFloat(h); }
+    } else if (dtype == 11) {  // DOUBLE
+        if (raw.n) { t.data.resize(raw.n / 8); for (size_t i = 0; i < t.data.size(); ++i) { double d; std::memcpy(&d, raw.p + 8 * i, 8); t.data[i] = (float)d; } }
+        else for (double d : ddata) t.data.push_back((float)d);
+    } else if (dtype == 7) {  // INT64
+        if (raw.n) { t.idata.resize(raw.n / 8); std::memcpy(t.idata.data(), raw.p, t.idata.size() * 8); }
+    }
+    return t;
+}
+
+OnnxNode parseNode(Span s, std::vector<OnnxTensor>& constants) {
+    OnnxNode n;
+    std::vector<Span> attrs;
+    Reader r(s);
+    while (!r.done()) {
+        Field f = r.next();
+        switch (f.id) {
+            case 1: n.inputs.push_back(str(f.bytes)); break;
+            case 2: n.outputs.push_back(str(f.bytes)); break;
+            case 3: n.name = str(f.bytes); break;
+            case 4: n.op = str(f.bytes); break;
+            case 5: attrs.push_back(f.bytes); break;
+            default: break;
+        }
+    }
+    for (Span a : attrs) {
+        std::string an;
+        std::vector<int64_t> ints;
+        Span tens{nullptr, 0};
+        Reader ar(a);
+        while (!ar.done()) {
+            Field f = ar.next();
+            if (f.id == 1) an = str(f.bytes);
+            else if (f.id == 8) readInts(f, ints);
+            else if (f.id == 5 && f.wt == 2) tens = f.bytes;
+        }
+        if (an == "kernel_shape") n.kernel_shape = ints;
+        else if (an == "strides") n.strides = ints;
+        else if (an == "pads") n.pads = ints;
+        else if (an == "value" && n.op == "Constant" && tens.p && !n.outputs.empty()) {
+            OnnxTensor t = parseTensor(tens);
+            t.name = n.outputs[0];
+            constants.push_back(std::move(t));
+        }
+    }
+    return n;
+}
+}  // namespace
+
+const OnnxTensor* OnnxGraph::find(const std::string& name) const {
+    for (const auto& t : initializers)
+        if (t.name == name) return &t;
+    return nullptr;
+}
+
+OnnxGraph parseOnnx(const std::vector<uint8_t>& blob) {
+    Span graph{nullptr, 0};
+    {
+        Reader r(Span{blob.data(), blob.size()});
+        while (!r.done()) {
+            Field f = r.next();
+            if (f.id == 7 && f.wt == 2) graph = f.bytes;
+        }
+    }
+    if (!graph.p) throw Error("onnx: no graph in model");
+    OnnxGraph g;
+    Reader r(graph);
+    while (!r.done()) {
+        Field f = r.next();
+        if (f.id == 1 && f.wt == 2) g.nodes.push_back(parseNode(f.bytes, g.initializers));
+        else if (f.id == 5 && f.wt == 2) g.initializers.push_back(parseTensor(f.bytes));
+    }
+    return g;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Architecture template match + packing.
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct ConvNode {
+    std::string name;
+    bool transpose = false;
+    int cout = 0, cin = 0, kh = 0, kw = 0, stride = 1, pad = 0;
+    const OnnxTensor* w = nullptr;
+    const OnnxTensor* b = nullptr;
+};
+
+std::vector<ConvNode> collectConvs(const OnnxGraph& g) {
+    std::vector<ConvNode> out;
+    for (const auto& n : g.nodes) {
+        if (n.op != "Conv" && n.op != "ConvTranspose") continue;
+        if (n.inputs.size() < 2) throw Error("onnx: conv node without weight input");
+        ConvNode c;
+        c.name = n.name;
+        c.transpose = n.op == "ConvTranspose";
+        c.w = g.find(n.inputs[1]);
+        if (!c.w || c.w->dims.size() != 4) throw Error("onnx: conv weight '" + n.inputs[1] + "' is not a 4-d initializer");
+        if (n.inputs.size() > 2 && !n.inputs[2].empty()) c.b = g.find(n.inputs[2]);
+        const auto& d = c.w->dims;
+        c.cout = (int)(c.transpose ? d[1] : d[0]);
+        c.cin = (int)(c.transpose ? d[0] : d[1]);
+        c.kh = (int)d[2];
+        c.kw = (int)d[3];
+        c.stride = n.strides.empty() ? 1 : (int)n.strides[0];
+        c.pad = n.pads.empty() ? 0 : (int)n.pads[0];
+        if ((size_t)(d[0] * d[1] * d[2] * d[3]) != c.w->data.size()) throw Error("onnx: conv weight '" + c.w->name + "' has no float data");
+        out.push_back(c);
+    }
+    return out;
+}
+
+inline float W4(const OnnxTensor* t, int a, int b, int c, int d) {
+    const auto& s = t->dims;
+    return t->data[(((size_t)a * s[1] + b) * s[2] + c) * s[3] + d];
+}
+
+PackedLayer packLayer(const ConvNode& c) {
+    PackedLayer L;
+    L.name = c.name;
+    L.cout = (uint32_t)c.cout;
+    const int cinp = c.cin < 8 ? 4 : c.cin;  // RGB first layers are stored with 4 channels
+    if (cinp < c.cin || (cinp % 4)) throw Error("pack: unsupported cin in " + c.name);
+    L.cin = (uint32_t)cinp;
+    auto bias = [&](int co) { return c.b ? c.b->data[(size_t)co] : 0.0f; };
+    if (!c.transpose && c.kh == 3 && c.kw == 3 && c.stride == 1 && c.pad == 0) {
+        L.kind = L_CONV3; L.taps = 9;
+        L.npad = (uint32_t)((c.cout + 15) / 16 * 16);
+        L.ktot = 9 * L.cin;
+        L.w.assign((size_t)L.npad * L.ktot, 0);
+        L.bias.assign(L.npad, 0.f);
+        for (int co = 0; co < c.cout; ++co) {
+            L.bias[co] = bias(co);
+            for (int ky = 0; ky < 3; ++ky)
+                for (int kx = 0; kx < 3; ++kx)
+                    for (int ci = 0; ci < c.cin; ++ci)
+                        L.w[(size_t)co * L.ktot + (ky * 3 + kx) * L.cin + ci] = floatToHalfBits(W4(c.w, co, ci, ky, kx));
+        }
+    } else if (!c.transpose && c.kh == 2 && c.kw == 2 && c.stride == 2 && c.pad == 0) {
+        L.kind = L_DOWN2; L.taps = 4;
+        L.npad = (uint32_t)((c.cout + 15) / 16 * 16);
+        L.ktot = 4 * L.cin;
+        L.w.assign((size_t)L.npad * L.ktot, 0);
+        L.bias.assign(L.npad, 0.f);
+        for (int co = 0; co < c.cout; ++co) {
+            L.bias[co] = bias(co);
+            for (int dy = 0; dy < 2; ++dy)
+                for (int dx = 0; dx < 2; ++dx)
+                    for (int ci = 0; ci < c.cin; ++ci)
+                        L.w[(size_t)co * L.ktot + (dy * 2 + dx) * L.cin + ci] = floatToHalfBits(W4(c.w, co, ci, dy, dx));
+        }
+    } else if (c.transpose && c.kh == 2 && c.kw == 2 && c.stride == 2 && c.pad == 0) {
+        if (c.cout % 8) throw Error("pack: convT 2x2 cout must be a multiple of 8 in " + c.name);
+        L.kind = L_UP2; L.taps = 1;
+        L.npad = (uint32_t)(4 * c.cout);
+        L.ktot = L.cin;
+        L.w.assign((size_t)L.npad * L.ktot, 0);
+        L.bias.assign(L.npad, 0.f);
+        for (int q = 0; q < 4; ++q)
+            for (int co = 0; co < c.cout; ++co) {
+                const int n = q * c.cout + co;
+                L.bias[n] = bias(co);
+                for (int ci = 0; ci < c.cin; ++ci)
+                    L.w[(size_t)n * L.ktot + ci] = floatToHalfBits(W4(c.w, ci, co, q >> 1, q & 1));
+            }
+    } else if (c.transpose && c.kh == 4 && c.kw == 4 && c.stride == 2 && c.pad == 3) {
+        if (c.cout > 4) throw Error("pack: convT 4x4 head supports cout <= 4 in " + c.name);
+        L.kind = L_UP4; L.taps = 4;
+        L.npad = 16;
+        L.ktot = 4 * L.cin;
+        L.w.assign((size_t)L.npad * L.ktot, 0);
+        L.bias.assign(L.npad, 0.f);
+        for (int py = 0; py < 2; ++py)
+            for (int px = 0; px < 2; ++px)
+                for (int co = 0; co < c.cout; ++co) {
+                    const int n = (py * 2 + px) * 4 + co;
+                    L.bias[n] = bias(co);
+                    for (int wy = 0; wy < 2; ++wy)
+                        for (int wx = 0; wx < 2; ++wx)
+                            for (int ci = 0; ci < c.cin; ++ci)
+                                L.w[(size_t)n * L.ktot + (wy * 2 + wx) * L.cin + ci] =
+                                    floatToHalfBits(W4(c.w, ci, co, 2 + py - 2 * wy, 2 + px - 2 * wx));
+                }
+    } else {
+        throw Error("pack: unsupported convolution '" + c.name + "' (k=" + std::to_string(c.kh) + " s=" +
+                    std::to_string(c.stride) + " p=" + std::to_string(c.pad) + (c.transpose ? " transposed)" : ")"));
+    }
+    return L;
+}
+
+struct Expect { uint32_t kind; int cin, cout; bool se; };
+}  // namespace
+
+PackedModel packFromOnnx(const OnnxGraph& g, int precision) {
+    std::vector<ConvNode> convs = collectConvs(g);
+    PackedModel m;
+    m.precision = (uint32_t)precision;
+    for (size_t i = 0; i < convs.size(); ++i) {
+        const ConvNode& c = convs[i];
+        if (!c.transpose && c.kh == 1 && c.kw == 1) {
+            // squeeze/excite pair: fc1 (C -> C/r) then fc2 (C/r -> C), attached to the previous layer
+            if (m.layers.empty() || i + 1 >= convs.size()) throw Error("pack: dangling 1x1 conv " + c.name);
+            const ConvNode& c2 = convs[i + 1];
+            PackedLayer& L = m.layers.back();
+            if (c2.transpose || c2.kh != 1 || c.cin != (int)L.cout || c2.cout != (int)L.cout || c2.cin != c.cout)
+                throw Error("pack: 1x1 convs after " + L.name + " do not form a squeeze/excite block");
+            L.se_r = (uint32_t)c.cout;
+            L.se_w1.assign(c.w->data.begin(), c.w->data.end());   // [r][c][1][1]
+            L.se_w2.assign(c2.w->data.begin(), c2.w->data.end()); // [c][r][1][1]
+            L.se_b1.assign((size_t)c.cout, 0.f);
+            L.se_b2.assign((size_t)c2.cout, 0.f);
+            if (c.b) L.se_b1 = c.b->data;
+            if (c2.b) L.se_b2 = c2.b->data;
+            ++i;
+            continue;
+        }
+        m.layers.push_back(packLayer(c));
+    }
+    // template: UNet1 (8 layers) + UNet2 (14 layers), SURVEY 2.2
+    const bool up = m.layers.size() > 7 && m.layers[7].kind == L_UP4;
+    const std::vector<Expect> tmpl = {
+        {L_CONV3, 4, 32, false},  {L_CONV3, 32, 64, false},  {L_DOWN2, 64, 64, false},   {L_CONV3, 64, 128, false},
+        {L_CONV3, 128, 64, true}, {L_UP2, 64, 64, false},    {L_CONV3, 64, 64, false},   {up ? L_UP4 : L_CONV3, 64, 3, false},
+        {L_CONV3, 4, 32, false},  {L_CONV3, 32, 64, false},  {L_DOWN2, 64, 64, false},   {L_CONV3, 64, 64, false},
+        {L_CONV3, 64, 128, true}, {L_DOWN2, 128, 128, false}, {L_CONV3, 128, 256, false}, {L_CONV3, 256, 128, true},
+        {L_UP2, 128, 128, false}, {L_CONV3, 128, 64, false}, {L_CONV3, 64, 64, true},    {L_UP2, 64, 64, false},
+        {L_CONV3, 64, 64, false}, {L_CONV3, 64, 3, false}};
+    if (m.layers.size() != tmpl.size())
+        throw Error("pack: graph has " + std::to_string(m.layers.size()) + " convolution layers; the cunet template needs " +
+                    std::to_string(tmpl.size()) + " (swin_unet import is not available in this build)");
+    for (size_t i = 0; i < tmpl.size(); ++i) {
+        const PackedLayer& L = m.layers[i];
+        if (L.kind != tmpl[i].kind || (int)L.cin != tmpl[i].cin || (int)L.cout != tmpl[i].cout || (L.se_r != 0) != tmpl[i].se)
+            throw Error("pack: layer " + std::to_string(i) + " ('" + L.name + "') does not match the cunet template");
+    }
+    m.arch = up ? ARCH_UPCUNET : ARCH_CUNET;
+    m.scale = up ? 2 : 1;
+    m.offset = up ? 36 : 28;
+    return m;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Flat file:  "W2XPACK1" | arch scale offset precision nlayers | per layer: header + blobs (4-byte aligned)
+// ------------------------------------------------------------------------------------------------
+namespace {
+void put32(std::vector<uint8_t>& o, uint32_t v) { for (int i = 0; i < 4; ++i) o.push_back((uint8_t)(v >> (8 * i))); }
+template <class T>
+void putVec(std::vector<uint8_t>& o, const std::vector<T>& v) {
+    put32(o, (uint32_t)v.size());
+    const size_t n = v.size() * sizeof(T);
+    const size_t at = o.size();
+    o.resize(at + ((n + 3) & ~size_t(3)), 0);
+    if (n) std::memcpy(o.data() + at, v.data(), n);
+}
+struct In {
+    const uint8_t* p; size_t n, i = 0;
+    uint32_t u32() { if (i + 4 > n) throw Error("pack file truncated"); uint32_t v; std::memcpy(&v, p + i, 4); i += 4; return v; }
+    template <class T> void vec(std::vector<T>& v) {
+        const uint32_t cnt = u32();
+        const size_t bytes = (size_t)cnt * sizeof(T), padded = (bytes + 3) & ~size_t(3);
+        if (i + padded > n) throw Error("pack file truncated");
+        v.resize(cnt);
+        if (bytes) std::memcpy(v.data(), p + i, bytes);
+        i += padded;
+    }
+};
+}  // namespace
+
+std::vector<uint8_t> serializePack(const PackedModel& m) {
+    std::vector<uint8_t> o;
+    const char magic[8] = {'W', '2', 'X', 'P', 'A', 'C', 'K', '1'};
+    o.insert(o.end(), magic, magic + 8);
+    put32(o, m.arch); put32(o, m.scale); put32(o, m.offset); put32(o, m.precision); put32(o, (uint32_t)m.layers.size());
+    for (const auto& L : m.layers) {
+        std::vector<char> nm(L.name.begin(), L.name.end());
+        putVec(o, nm);
+        put32(o, L.kind); put32(o, L.cin); put32(o, L.cout); put32(o, L.npad); put32(o, L.ktot); put32(o, L.taps); put32(o, L.se_r);
+        putVec(o, L.w); putVec(o, L.bias); putVec(o, L.se_w1); putVec(o, L.se_b1); putVec(o, L.se_w2); putVec(o, L.se_b2);
+    }
+    return o;
+}
+
+PackedModel deserializePack(const std::vector<uint8_t>& blob) {
+    if (blob.size() < 28 || std::memcmp(blob.data(), "W2XPACK1", 8) != 0) throw Error("not a W2XPACK1 file");
+    In in{blob.data(), blob.size(), 8};
+    PackedModel m;
+    m.arch = in.u32(); m.scale = in.u32(); m.offset = in.u32(); m.precision = in.u32();
+    const uint32_t nl = in.u32();
+    if (nl > 4096) throw Error("pack file corrupt");
+    m.layers.resize(nl);
+    for (auto& L : m.layers) {
+        std::vector<char> nm;
+        in.vec(nm);
+        L.name.assign(nm.begin(), nm.end());
+        L.kind = in.u32(); L.cin = in.u32(); L.cout = in.u32(); L.npad = in.u32(); L.ktot = in.u32(); L.taps = in.u32(); L.se_r = in.u32();
+        in.vec(L.w); in.vec(L.bias); in.vec(L.se_w1); in.vec(L.se_b1); in.vec(L.se_w2); in.vec(L.se_b2);
+        if (L.w.size() != (size_t)L.npad * L.ktot || L.bias.size() != L.npad) throw Error("pack file: layer '" + L.name + "' has inconsistent sizes");
+    }
+    return m;
+}
+
+}  // namespace w2x

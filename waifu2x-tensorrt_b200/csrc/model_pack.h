@@ -1,0 +1,69 @@
+// ONNX import + kernel-native weight packing ("build" in the B200 engine).
+// Replaces nvonnxparser::parseFromFile + buildSerializedNetwork (/root/reference/src/tensorrt/img2img_build.cpp:87-147):
+// instead of a TensorRT plan the artefact is a flat file of fp16 GEMM-operand matrices laid out exactly as the
+// tcgen05 implicit-GEMM kernels consume them.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace w2x {
+
+// ---- minimal ONNX view -----------------------------------------------------------------------------
+struct OnnxTensor {
+    std::string name;
+    std::vector<int64_t> dims;
+    std::vector<float> data;  // FLOAT / FLOAT16 / DOUBLE initialisers widened to f32; INT64 left empty
+    std::vector<int64_t> idata;
+};
+struct OnnxNode {
+    std::string op, name;
+    std::vector<std::string> inputs, outputs;
+    std::vector<int64_t> kernel_shape, strides, pads;
+};
+struct OnnxGraph {
+    std::vector<OnnxNode> nodes;
+    std::vector<OnnxTensor> initializers;
+    const OnnxTensor* find(const std::string& name) const;
+};
+OnnxGraph parseOnnx(const std::vector<uint8_t>& blob);
+
+// ---- packed model ----------------------------------------------------------------------------------
+enum LayerKind : uint32_t {
+    L_CONV3 = 0,  // 3x3 valid stride-1 conv:            B[npad][9*cin],  k = (ky*3+kx)*cin + ci
+    L_DOWN2 = 1,  // 2x2 stride-2 conv:                  B[npad][4*cin],  k = (dy*2+dx)*cin + ci
+    L_UP2 = 2,    // ConvTranspose 2x2 stride 2:         B[4*cout][cin],  n = (dy*2+dx)*cout + co
+    L_UP4 = 3,    // ConvTranspose 4x4 stride 2 pad 3 as a 2x2 window conv with 4 output phases:
+                  //                                     B[16][4*cin],    n = (py*2+px)*4 + co,  k = (wy*2+wx)*cin + ci,
+                  //                                     tap (ky,kx) = (2+py-2*wy, 2+px-2*wx)
+};
+
+enum Arch : uint32_t { ARCH_CUNET = 1, ARCH_UPCUNET = 2 };
+
+struct PackedLayer {
+    std::string name;
+    uint32_t kind = 0;
+    uint32_t cin = 0;    // channels per tap as stored (3 padded to 4)
+    uint32_t cout = 0;   // real output channels
+    uint32_t npad = 0;   // GEMM N (rows of B)
+    uint32_t ktot = 0;   // GEMM K (= taps * cin)
+    uint32_t taps = 0;
+    uint32_t se_r = 0;   // squeeze/excite hidden width (0 = no SE after this layer)
+    std::vector<uint16_t> w;     // fp16 bits, [npad][ktot] K-major
+    std::vector<float> bias;     // [npad]
+    std::vector<float> se_w1, se_b1, se_w2, se_b2;  // [r][c], [r], [c][r], [c]
+};
+
+struct PackedModel {
+    uint32_t arch = 0, scale = 0, offset = 0, precision = 1;
+    std::vector<PackedLayer> layers;
+};
+
+PackedModel packFromOnnx(const OnnxGraph& g, int precision);
+std::vector<uint8_t> serializePack(const PackedModel& m);
+PackedModel deserializePack(const std::vector<uint8_t>& blob);
+
+uint16_t floatToHalfBits(float f);
+float halfBitsToFloat(uint16_t h);
+
+}  // namespace w2x

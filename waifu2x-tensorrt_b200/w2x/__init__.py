@@ -1,0 +1,368 @@
+"""ctypes binding of libw2x.so (include/w2x.h) + a Python mirror of the reference's operator surface.
+
+`Img2Img` mirrors trt::Img2Img (/root/reference/src/tensorrt/img2img.h:14-50): build / load / render /
+setMessageCallback / setProgressCallback with the reference's argument meaning and bool-return error
+convention; `BuildConfig` / `RenderConfig` mirror src/tensorrt/config.h:12-43 field-for-field.
+
+There is NO CPU fallback: if the CUDA library is missing, importing `lib()` raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+from typing import Callable, List, Optional, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libw2x.so")
+
+PRECISION_TF32, PRECISION_FP16 = 0, 1
+SEVERITY_NAMES = ["critical", "error", "warn", "info", "debug", "trace"]
+
+
+class _BuildConfig(C.Structure):
+    _fields_ = [(n, C.c_int) for n in (
+        "deviceId", "precision", "minBatchSize", "optBatchSize", "maxBatchSize", "minChannels", "optChannels",
+        "maxChannels", "minWidth", "optWidth", "maxWidth", "minHeight", "optHeight", "maxHeight")]
+
+
+class _RenderConfig(C.Structure):
+    _fields_ = [("deviceId", C.c_int), ("precision", C.c_int), ("batchSize", C.c_int), ("channels", C.c_int),
+                ("height", C.c_int), ("width", C.c_int), ("scaling", C.c_int), ("overlapX", C.c_double),
+                ("overlapY", C.c_double), ("tta", C.c_int)]
+
+
+class _Rect(C.Structure):
+    _fields_ = [("x", C.c_int), ("y", C.c_int), ("width", C.c_int), ("height", C.c_int)]
+
+
+MESSAGE_CB = C.CFUNCTYPE(None, C.c_int, C.c_char_p, C.c_void_p)
+PROGRESS_CB = C.CFUNCTYPE(None, C.c_int, C.c_int, C.c_double, C.c_void_p)
+
+
+@dataclass
+class BuildConfig:  # src/tensorrt/config.h:12-31
+    deviceId: int = 0
+    precision: int = PRECISION_FP16
+    minBatchSize: int = 1
+    optBatchSize: int = 1
+    maxBatchSize: int = 4
+    minChannels: int = 3
+    optChannels: int = 3
+    maxChannels: int = 3
+    minWidth: int = 64
+    optWidth: int = 256
+    maxWidth: int = 640
+    minHeight: int = 64
+    optHeight: int = 256
+    maxHeight: int = 640
+
+    @staticmethod
+    def fixed(batch: int, tile: int, device: int = 0, precision: int = PRECISION_FP16) -> "BuildConfig":
+        """The config the reference CLI builds with (src/main.cpp:276-291): min = opt = max."""
+        return BuildConfig(device, precision, batch, batch, batch, 3, 3, 3, tile, tile, tile, tile, tile, tile)
+
+    def _c(self) -> _BuildConfig:
+        return _BuildConfig(*[getattr(self, f[0]) for f in _BuildConfig._fields_])
+
+
+@dataclass
+class RenderConfig:  # src/tensorrt/config.h:33-43
+    deviceId: int = 0
+    precision: int = PRECISION_FP16
+    batchSize: int = 1
+    channels: int = 3
+    height: int = 256
+    width: int = 256
+    scaling: int = 4
+    overlap: Tuple[float, float] = (0.0625, 0.0625)
+    tta: bool = False
+
+    def _c(self) -> _RenderConfig:
+        return _RenderConfig(self.deviceId, self.precision, self.batchSize, self.channels, self.height, self.width,
+                             self.scaling, float(self.overlap[0]), float(self.overlap[1]), int(self.tta))
+
+
+_lib = None
+
+_SIGNATURES = {
+    "w2x_default_build_config": (None, [C.POINTER(_BuildConfig)]),
+    "w2x_default_render_config": (None, [C.POINTER(_RenderConfig)]),
+    "w2x_create": (C.c_void_p, []),
+    "w2x_destroy": (None, [C.c_void_p]),
+    "w2x_set_message_callback": (None, [C.c_void_p, MESSAGE_CB, C.c_void_p]),
+    "w2x_set_progress_callback": (None, [C.c_void_p, PROGRESS_CB, C.c_void_p]),
+    "w2x_build": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(_BuildConfig)]),
+    "w2x_load": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(_RenderConfig)]),
+    "w2x_render": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_size_t]),
+    "w2x_render_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_size_t]),
+    "w2x_submit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_size_t]),
+    "w2x_wait": (C.c_int, [C.c_void_p, C.c_int]),
+    "w2x_sync": (C.c_int, [C.c_void_p]),
+    "w2x_host_alloc": (C.c_void_p, [C.c_size_t]),
+    "w2x_host_free": (None, [C.c_void_p]),
+    "w2x_device_alloc": (C.c_void_p, [C.c_void_p, C.c_size_t]),
+    "w2x_device_free": (None, [C.c_void_p, C.c_void_p]),
+    "w2x_memcpy_h2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "w2x_memcpy_d2h": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "w2x_last_error": (C.c_char_p, [C.c_void_p]),
+    "w2x_output_tile_size": (C.c_int, [C.c_void_p]),
+    "w2x_launch_count": (C.c_longlong, [C.c_void_p]),
+    "w2x_model_flops_per_tile": (C.c_double, [C.c_void_p]),
+    "w2x_last_stage_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_int]),
+    "w2x_profile_layers": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_double), C.c_int]),
+    "w2x_calculate_tiles": (C.c_int, [C.c_int] * 9 + [C.c_double, C.c_double, C.POINTER(_Rect), C.POINTER(_Rect), C.c_int, C.POINTER(C.c_int)]),
+    "w2x_blend_ramp": (C.c_int, [C.c_int, C.POINTER(C.c_float)]),
+    "w2x_unpack_tiles": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.POINTER(_Rect), C.POINTER(C.c_int), C.c_int, C.c_int, C.c_void_p]),
+    "w2x_stitch_tiles": (C.c_int, [C.c_int, C.c_void_p] + [C.c_int] * 8 + [C.c_void_p, C.c_size_t]),
+    "w2x_tta_reduce": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "w2x_infer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "w2x_selftest_conv": (C.c_double, [C.c_int] * 7 + [C.c_uint]),
+    "w2x_config_hash": (None, [C.c_char_p, C.POINTER(_BuildConfig), C.c_char_p]),
+    "w2x_pack_onnx": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, C.c_int]),
+    "w2x_pack_info": (C.c_int, [C.c_char_p] + [C.POINTER(C.c_int)] * 4),
+}
+
+EXPORTED_SYMBOLS = sorted(_SIGNATURES)
+
+
+def lib() -> C.CDLL:
+    """Load libw2x.so (built in-tree by `make -C waifu2x-tensorrt_b200/csrc` / __graft_entry__.build())."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: build it with __graft_entry__.build(); there is no CPU fallback")
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(l, name)  # AttributeError here == the library does not export what w2x.h declares
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def _ptr(a: np.ndarray) -> C.c_void_p:
+    return C.c_void_p(a.ctypes.data)
+
+
+# ---- host-only helpers ------------------------------------------------------------------------------
+def calculate_tiles(in_w, in_h, out_w, out_h, tile_w, tile_h, out_tile_w, out_tile_h, scaling, overlap_x, overlap_y):
+    """calculateTiles (img2img_render.cpp:7-66) -> (count, grid[8], in_rects, out_rects)."""
+    l = lib()
+    grid = (C.c_int * 8)()
+    n = l.w2x_calculate_tiles(in_w, in_h, out_w, out_h, tile_w, tile_h, out_tile_w, out_tile_h, scaling,
+                              overlap_x, overlap_y, None, None, 0, grid)
+    if n < 0:
+        raise ValueError("calculate_tiles failed")
+    ir = (_Rect * max(n, 1))()
+    orr = (_Rect * max(n, 1))()
+    l.w2x_calculate_tiles(in_w, in_h, out_w, out_h, tile_w, tile_h, out_tile_w, out_tile_h, scaling,
+                          overlap_x, overlap_y, ir, orr, n, grid)
+    conv = lambda rs: [(r.x, r.y, r.width, r.height) for r in rs[:n]]
+    return n, list(grid), conv(ir), conv(orr)
+
+
+def blend_ramp(overlap: int) -> np.ndarray:
+    out = np.zeros(max(overlap, 1), np.float32)
+    n = lib().w2x_blend_ramp(overlap, out.ctypes.data_as(C.POINTER(C.c_float)))
+    return out[:n]
+
+
+def config_hash(device_name: str, cfg: BuildConfig) -> str:
+    buf = C.create_string_buffer(65)
+    lib().w2x_config_hash(device_name.encode(), C.byref(cfg._c()), buf)
+    return buf.value.decode()
+
+
+def pack_onnx(onnx_path: str, out_path: str, precision: int = PRECISION_FP16) -> None:
+    err = C.create_string_buffer(512)
+    if not lib().w2x_pack_onnx(onnx_path.encode(), out_path.encode(), precision, err, 512):
+        raise RuntimeError(err.value.decode())
+
+
+def pack_info(path: str):
+    v = [C.c_int() for _ in range(4)]
+    if not lib().w2x_pack_info(path.encode(), *[C.byref(x) for x in v]):
+        raise RuntimeError("not a pack file: " + path)
+    return dict(arch=v[0].value, scale=v[1].value, offset=v[2].value, layers=v[3].value)
+
+
+# ---- stage entry points (GPU) ------------------------------------------------------------------------
+def unpack_tiles(src_bgr: np.ndarray, rects: List[Tuple[int, int, int, int]], aug: List[int], tile: int, device: int = 0) -> np.ndarray:
+    """-> float16 [n, tile, tile, 4] (RGB0)."""
+    src = np.ascontiguousarray(src_bgr)
+    n = len(rects)
+    cr = (_Rect * n)(*[_Rect(*r) for r in rects])
+    ca = (C.c_int * n)(*aug)
+    out = np.empty((n, tile, tile, 4), np.float16)
+    ok = lib().w2x_unpack_tiles(device, _ptr(src), src.shape[1], src.shape[0], src.strides[0], cr, ca, n, tile, _ptr(out))
+    if not ok:
+        raise RuntimeError("w2x_unpack_tiles failed")
+    return out
+
+
+def stitch_tiles(tiles_f16: np.ndarray, nx: int, ny: int, ov_x: int, ov_y: int, canvas_w: int, canvas_h: int, device: int = 0) -> np.ndarray:
+    t = np.ascontiguousarray(tiles_f16, dtype=np.float16)
+    count, out_tile = t.shape[0], t.shape[1]
+    dst = np.empty((canvas_h, canvas_w, 3), np.uint8)
+    ok = lib().w2x_stitch_tiles(device, _ptr(t), count, out_tile, nx, ny, ov_x, ov_y, canvas_w, canvas_h, _ptr(dst), dst.strides[0])
+    if not ok:
+        raise RuntimeError("w2x_stitch_tiles failed")
+    return dst
+
+
+def tta_reduce(outs_f16: np.ndarray, device: int = 0) -> np.ndarray:
+    t = np.ascontiguousarray(outs_f16, dtype=np.float16)  # [tiles, 8, T, T, 4]
+    tiles, _, ot = t.shape[0], t.shape[1], t.shape[2]
+    mean = np.empty((tiles, ot, ot, 4), np.float32)
+    if not lib().w2x_tta_reduce(device, _ptr(t), tiles, ot, _ptr(mean)):
+        raise RuntimeError("w2x_tta_reduce failed")
+    return mean
+
+
+def selftest_conv(kind: int, n: int, h: int, w: int, cin: int, cout: int, seed: int = 1, device: int = 0) -> float:
+    return float(lib().w2x_selftest_conv(device, kind, n, h, w, cin, cout, seed))
+
+
+# ---- the operator surface ---------------------------------------------------------------------------
+class Img2Img:
+    """Python mirror of trt::Img2Img (src/tensorrt/img2img.h:14-50)."""
+
+    def __init__(self):
+        self._l = lib()
+        self._h = self._l.w2x_create()
+        if not self._h:
+            raise RuntimeError("w2x_create failed")
+        self._msg_cb = None
+        self._prog_cb = None
+        self.scaling = 1
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._l.w2x_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def setMessageCallback(self, cb: Optional[Callable[[int, str], None]]):
+        self._msg_cb = MESSAGE_CB(lambda sev, msg, user: cb(sev, msg.decode(errors="replace"))) if cb else MESSAGE_CB()
+        self._l.w2x_set_message_callback(self._h, self._msg_cb, None)
+
+    def setProgressCallback(self, cb: Optional[Callable[[int, int, float], None]]):
+        self._prog_cb = PROGRESS_CB(lambda cur, tot, speed, user: cb(cur, tot, speed)) if cb else PROGRESS_CB()
+        self._l.w2x_set_progress_callback(self._h, self._prog_cb, None)
+
+    def build(self, path: str, config: BuildConfig) -> bool:
+        return bool(self._l.w2x_build(self._h, path.encode(), C.byref(config._c())))
+
+    def load(self, path: str, config: RenderConfig) -> bool:
+        ok = bool(self._l.w2x_load(self._h, path.encode(), C.byref(config._c())))
+        if ok:
+            self.scaling = config.scaling
+        return ok
+
+    def render(self, src: np.ndarray, dst: Optional[np.ndarray] = None) -> Optional[np.ndarray]:
+        """src: uint8 [H, W, 3] BGR.  Returns dst (uint8 [H*s, W*s, 3] BGR) or None on failure."""
+        src = np.ascontiguousarray(src, dtype=np.uint8)
+        h, w = src.shape[:2]
+        if dst is None:
+            dst = np.empty((h * self.scaling, w * self.scaling, 3), np.uint8)
+        ok = self._l.w2x_render(self._h, _ptr(src), w, h, src.strides[0], _ptr(dst), dst.strides[0])
+        return dst if ok else None
+
+    # extensions
+    def infer(self, x_nchw: np.ndarray) -> Optional[np.ndarray]:
+        x = np.ascontiguousarray(x_nchw, dtype=np.float32)
+        n = x.shape[0]
+        ot = self.output_tile_size
+        out = np.empty((n, 3, ot, ot), np.float32)
+        return out if self._l.w2x_infer(self._h, _ptr(x), n, _ptr(out)) else None
+
+    @property
+    def output_tile_size(self) -> int:
+        return int(self._l.w2x_output_tile_size(self._h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._l.w2x_launch_count(self._h))
+
+    @property
+    def flops_per_tile(self) -> float:
+        return float(self._l.w2x_model_flops_per_tile(self._h))
+
+    @property
+    def last_error(self) -> str:
+        return (self._l.w2x_last_error(self._h) or b"").decode(errors="replace")
+
+    def last_stage_ms(self):
+        buf = (C.c_float * 4)()
+        n = self._l.w2x_last_stage_ms(self._h, buf, 4)
+        return dict(zip(["unpack", "model", "stitch", "total"], list(buf)[:n]))
+
+    def profile_layers(self, repeats: int = 5):
+        names = ((C.c_char * 48) * 64)()
+        ms = (C.c_float * 64)()
+        fl = (C.c_double * 64)()
+        n = self._l.w2x_profile_layers(self._h, repeats, names, ms, fl, 64)
+        if n < 0:
+            raise RuntimeError(self.last_error)
+        return [(names[i].value.decode(), ms[i], fl[i]) for i in range(n)]
+
+    def render_device(self, d_src: int, w: int, h: int, d_dst: int) -> bool:
+        return bool(self._l.w2x_render_device(self._h, C.c_void_p(d_src), w, h, w * 3, C.c_void_p(d_dst), w * self.scaling * 3))
+
+    def submit(self, src_ptr: int, w: int, h: int, dst_ptr: int) -> int:
+        return int(self._l.w2x_submit(self._h, C.c_void_p(src_ptr), w, h, w * 3, C.c_void_p(dst_ptr), w * self.scaling * 3))
+
+    def wait(self, ticket: int) -> bool:
+        return bool(self._l.w2x_wait(self._h, ticket))
+
+    def sync(self) -> bool:
+        return bool(self._l.w2x_sync(self._h))
+
+    def device_alloc(self, nbytes: int) -> int:
+        p = self._l.w2x_device_alloc(self._h, nbytes)
+        if not p:
+            raise MemoryError("w2x_device_alloc")
+        return int(p)
+
+    def device_free(self, p: int):
+        self._l.w2x_device_free(self._h, C.c_void_p(p))
+
+    def h2d(self, dptr: int, arr: np.ndarray):
+        a = np.ascontiguousarray(arr)
+        if not self._l.w2x_memcpy_h2d(self._h, C.c_void_p(dptr), _ptr(a), a.nbytes):
+            raise RuntimeError("h2d failed")
+
+    def d2h(self, arr: np.ndarray, dptr: int):
+        if not self._l.w2x_memcpy_d2h(self._h, _ptr(arr), C.c_void_p(dptr), arr.nbytes):
+            raise RuntimeError("d2h failed")
+
+
+class PinnedArray:
+    """uint8 ndarray over cudaHostAlloc memory (for the pipelined submit path)."""
+
+    def __init__(self, shape):
+        self.nbytes = int(np.prod(shape))
+        self.ptr = lib().w2x_host_alloc(self.nbytes)
+        if not self.ptr:
+            raise MemoryError("w2x_host_alloc")
+        buf = (C.c_uint8 * self.nbytes).from_address(self.ptr)
+        self.array = np.frombuffer(buf, np.uint8).reshape(shape)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            lib().w2x_host_free(self.ptr)
+            self.ptr = None
+
+
+def model_path(models_dir: str, model: str, noise: int, scale: int) -> str:
+    """models/<model>/[noiseN_][scaleSx].onnx, src/main.cpp:201-204 (trailing underscore for scale 1 kept)."""
+    return os.path.join(models_dir, model, ("" if noise == -1 else f"noise{noise}_") + ("" if scale == 1 else f"scale{scale}x") + ".onnx")
