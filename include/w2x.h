@@ -117,6 +117,10 @@ W2X_API double w2x_model_flops_per_tile(w2x_engine* e);   /* algorithmic 2*MAC o
 /* Per-stage device time of the LAST completed render, from CUDA events on the engine's stream:
  * out[0]=unpack ms, out[1]=model ms, out[2]=stitch/pack ms, out[3]=total ms; returns count written. */
 W2X_API int w2x_last_stage_ms(w2x_engine* e, float* out, int n);
+/* CUDA-event timer on the engine's streams (which: 0 compute, 1 H2D copy, 2 D2H copy): mark idx in [0,16), then
+ * w2x_timer_elapsed_ms synchronises both events and returns milliseconds between them (negative on error). */
+W2X_API int w2x_timer_mark(w2x_engine* e, int idx, int which);
+W2X_API float w2x_timer_elapsed_ms(w2x_engine* e, int idx0, int idx1);
 /* Layer-level timing of the model (names + ms) for profiling; returns number of layers, fills up to n. */
 W2X_API int w2x_profile_layers(w2x_engine* e, int repeats, char (*names)[48], float* ms, double* flops, int n);
 

@@ -113,6 +113,8 @@ int w2x_output_tile_size(w2x_engine* e) { return e ? e->impl.outputTile() : 0; }
 long long w2x_launch_count(w2x_engine* e) { return e ? e->impl.launchCount() : 0; }
 double w2x_model_flops_per_tile(w2x_engine* e) { return e ? e->impl.flopsPerTile() : 0.0; }
 int w2x_last_stage_ms(w2x_engine* e, float* out, int n) { return e && out ? e->impl.lastStageMs(out, n) : 0; }
+int w2x_timer_mark(w2x_engine* e, int idx, int which) { return e && e->impl.timerMark(idx, which) ? 1 : 0; }
+float w2x_timer_elapsed_ms(w2x_engine* e, int i0, int i1) { return e ? e->impl.timerElapsedMs(i0, i1) : -1.f; }
 int w2x_profile_layers(w2x_engine* e, int repeats, char (*names)[48], float* ms, double* flops, int n) {
     return e ? e->impl.profileLayers(repeats < 1 ? 1 : repeats, names, ms, flops, n) : -1;
 }

@@ -147,6 +147,7 @@ void Engine::unload() {
         if (s.evDone) { cudaEventDestroy(s.evDone); s.evDone = nullptr; }
         s.busy = false;
     }
+    for (auto& e : timerEv) if (e) { cudaEventDestroy(e); e = nullptr; }
     for (auto e : evPool) cudaEventDestroy(e);
     evPool.clear(); evUsed = 0; spans.clear();
     if (stream) { cudaStreamDestroy(stream); stream = nullptr; }
@@ -543,6 +544,22 @@ int Engine::lastStageMs(float* out, int n) {
     const int k = std::min(n, 4);
     for (int i = 0; i < k; ++i) out[i] = acc[i];
     return k;
+}
+
+bool Engine::timerMark(int idx, int which) {
+    if (idx < 0 || idx >= 16 || !stream) return false;
+    if (cudaSetDevice(cfg.deviceId) != cudaSuccess) return false;
+    if (!timerEv[idx] && cudaEventCreate(&timerEv[idx]) != cudaSuccess) return false;
+    cudaStream_t s = which == 1 ? h2dStream : which == 2 ? d2hStream : stream;
+    return cudaEventRecord(timerEv[idx], s) == cudaSuccess;
+}
+
+float Engine::timerElapsedMs(int i0, int i1) {
+    if (i0 < 0 || i1 < 0 || i0 >= 16 || i1 >= 16 || !timerEv[i0] || !timerEv[i1]) return -1.f;
+    if (cudaEventSynchronize(timerEv[i0]) != cudaSuccess || cudaEventSynchronize(timerEv[i1]) != cudaSuccess) return -1.f;
+    float ms = -1.f;
+    if (cudaEventElapsedTime(&ms, timerEv[i0], timerEv[i1]) != cudaSuccess) return -1.f;
+    return ms;
 }
 
 bool Engine::renderDevice(const uint8_t* dSrc, int w, int h, size_t srcStride, uint8_t* dDst, size_t dstStride) {

@@ -70,6 +70,8 @@ public:
     long long launchCount() const { return launches; }
     double flopsPerTile() const;
     int lastStageMs(float* out, int n);
+    bool timerMark(int idx, int which);
+    float timerElapsedMs(int i0, int i1);
     int device() const { return cfg.deviceId; }
     bool loaded() const { return isLoaded; }
 
@@ -135,6 +137,7 @@ private:
     struct StageSpan { int kind, e0, e1; };
     std::vector<StageSpan> spans;
     cudaEvent_t nextEvent();
+    cudaEvent_t timerEv[16] = {};
 };
 
 // On-device self-check of one implicit-GEMM layer (tcgen05 vs scalar reference); see w2x.h.

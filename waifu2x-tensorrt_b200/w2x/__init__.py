@@ -112,6 +112,8 @@ _SIGNATURES = {
     "w2x_launch_count": (C.c_longlong, [C.c_void_p]),
     "w2x_model_flops_per_tile": (C.c_double, [C.c_void_p]),
     "w2x_last_stage_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_int]),
+    "w2x_timer_mark": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "w2x_timer_elapsed_ms": (C.c_float, [C.c_void_p, C.c_int, C.c_int]),
     "w2x_profile_layers": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_double), C.c_int]),
     "w2x_calculate_tiles": (C.c_int, [C.c_int] * 9 + [C.c_double, C.c_double, C.POINTER(_Rect), C.POINTER(_Rect), C.c_int, C.POINTER(C.c_int)]),
     "w2x_blend_ramp": (C.c_int, [C.c_int, C.POINTER(C.c_float)]),
@@ -304,6 +306,12 @@ class Img2Img:
         buf = (C.c_float * 4)()
         n = self._l.w2x_last_stage_ms(self._h, buf, 4)
         return dict(zip(["unpack", "model", "stitch", "total"], list(buf)[:n]))
+
+    def timer_mark(self, idx: int, which: int = 0) -> bool:
+        return bool(self._l.w2x_timer_mark(self._h, idx, which))
+
+    def timer_elapsed_ms(self, i0: int, i1: int) -> float:
+        return float(self._l.w2x_timer_elapsed_ms(self._h, i0, i1))
 
     def profile_layers(self, repeats: int = 5):
         names = ((C.c_char * 48) * 64)()
