@@ -154,6 +154,11 @@ W2X_API int w2x_infer(w2x_engine* e, const float* in_nchw, int n, float* out_nch
  * 2 convT2x2s2(+skip), 3 convT4x4s2p3->4ch, 4 conv3x3->3ch final(+skip,clamp). */
 W2X_API double w2x_selftest_conv(int device, int kind, int n, int h, int w, int cin, int cout, unsigned seed);
 
+/* Development probe: which UMMA smem-descriptor base_offset convention lets a 3x3 tap read a SHIFTED view of one
+ * TMA-loaded 128B-swizzled patch (mode 0: base_offset=(start>>7)&7, mode 1: 0; pitch = patch row pitch in pixels).
+ * err9[tap] = max |device - host|.  Returns 0 on success. */
+W2X_API int w2x_probe_umma(int device, int mode, int pitch, float* err9);
+
 /* Host-only helpers (no GPU needed). */
 /* getConfigHash (img2img_build.cpp:8-27) on an explicit device name: writes 64 hex chars + NUL. */
 W2X_API void w2x_config_hash(const char* device_name, const w2x_build_config* cfg, char out_hex[65]);

@@ -6,7 +6,10 @@ pytestmark = pytest.mark.gpu
 
 # kind: 0 conv3x3, 1 conv2x2s2, 2 convT2x2s2(+skip), 3 convT4x4s2p3 head, 4 conv3x3 image head (+skip, clamp)
 CASES = [
-    (0, 1, 20, 24, 64, 64),     # one M tile with edges
+    (0, 1, 20, 24, 64, 64),     # one M tile with edges (patch kernel)
+    (0, 8, 100, 100, 64, 64),   # > 148 tiles: persistent loop, stage ring wrap, double-buffered staging
+    (0, 1, 60, 52, 128, 64),    # patch kernel, two 64-channel chunks
+    (0, 3, 45, 77, 64, 128),    # patch kernel, two output-channel slices
     (0, 2, 61, 45, 32, 64),     # cin 32 -> 64-byte swizzle path, odd sizes
     (0, 1, 126, 126, 64, 128),  # u1.conv2.0 at T=256
     (0, 1, 40, 40, 128, 256),   # N = 256

@@ -226,6 +226,15 @@ double w2x_selftest_conv(int device, int kind, int n, int h, int w, int cin, int
     }
 }
 
+int w2x_probe_umma(int device, int mode, int pitch, float* err9) {
+    try {
+        if (!err9 || cudaSetDevice(device) != cudaSuccess) return -1;
+        return probeUmma(mode, pitch, err9);
+    } catch (...) {
+        return -2;
+    }
+}
+
 void w2x_config_hash(const char* device_name, const w2x_build_config* cfg, char out_hex[65]) {
     if (!out_hex) return;
     out_hex[0] = 0;

@@ -31,6 +31,7 @@ ConvParams makeConv3Params(const Act& in, const Act& out, const __half* w, const
     ConvParams p{};
     plainView(p, in);
     p.ntaps = 9;
+    p.is3x3 = 1;
     for (int ky = 0; ky < 3; ++ky)
         for (int kx = 0; kx < 3; ++kx) p.tap[ky * 3 + kx] = {0, kx, 0, ky};
     p.gx = in.w - 2; p.gy = in.h - 2;
@@ -734,6 +735,11 @@ int Engine::profileLayers(int repeats, char (*names)[48], float* ms, double* flo
             float t = 0;
             W2X_CUDA(cudaEventElapsedTime(&t, e0, e1));
             std::snprintf(names[i], 48, "%s", L.name.c_str());
+            if (std::getenv("W2X_VERBOSE")) {
+                char d[256] = "";
+                if (L.plan) igemmDescribe(L.plan, d, sizeof(d));
+                std::fprintf(stderr, "[w2x] %-28s %s\n", L.name.c_str(), L.plan ? d : (L.impl == IMPL_FIRST ? "first-layer cuda-core" : "direct"));
+            }
             ms[i] = t / repeats;
             flops[i] = L.flops * batch;
             ++i;
@@ -805,8 +811,9 @@ double selftestConv(int device, int kind, int n, int h, int w, int cin, int cout
         }
         launchConvDirect(p, nullptr);
         W2X_CUDA(cudaDeviceSynchronize());
+        p.out = outB;  // the tensor-core kernel writes its own buffer (TMA-store layers bake the pointer into the tensor map)
         plan = igemmCreatePlan(p);
-        igemmLaunch(plan, nullptr, outB);
+        igemmLaunch(plan, nullptr, nullptr);
         W2X_CUDA(cudaDeviceSynchronize());
         std::vector<uint16_t> ha(out.elems()), hb(out.elems());
         W2X_CUDA(cudaMemcpy(ha.data(), outA, ha.size() * 2, cudaMemcpyDeviceToHost));

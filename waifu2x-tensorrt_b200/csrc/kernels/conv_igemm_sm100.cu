@@ -1,135 +1,81 @@
-// Implicit-GEMM convolution on the sm_100a tensor cores (tcgen05.mma, accumulators in TMEM, operands staged by TMA).
+// Convolutions on the sm_100a tensor cores (tcgen05.mma, accumulators in TMEM, operands staged by TMA).
 //
-// This is the kernel behind every dense CUNet layer with cin >= 32, replacing the
-// opaque TensorRT engine the reference enqueues at /root/reference/src/tensorrt/img2img_infer.cpp:80.
+// These two kernels are the dense model hot path: together they replace the opaque TensorRT
+// engine the reference enqueues at /root/reference/src/tensorrt/img2img_infer.cpp:80.
 //
-//   D[128 pixels, BN] (fp32, TMEM)  +=  A[128 pixels, KC] (fp16, smem, K-major, 128B/64B swizzle)
-//                                     x B[BN, KC]         (fp16, smem, K-major, same swizzle)
+//   conv3x3_patch_kernel  3x3 valid convolutions with cin in {64,128}: the layer's weights for one 64-wide output slice
+//                         stay RESIDENT in shared memory for the CTA's lifetime; each 16x8-pixel output tile loads ONE
+//                         18x10-pixel input patch per 64-channel chunk by TMA (128B swizzle) and all nine taps are MMA'd
+//                         from SHIFTED VIEWS of that patch (descriptor start moved by whole 128-byte pixel rows, 8-row groups
+//                         SBO = 10 pixels apart).  L2->SM traffic per output pixel drops ~6x versus per-tap loads.
+//   igemm_kernel          generic implicit GEMM: per-tap TMA box loads of A and a B tile per K block.  Used for the
+//                         2x2/s2 convs, the ConvTranspose layers (depth-to-space epilogue), cin=32 and the 256-wide layers.
 //
-// * A is never materialised (no im2col buffer): for each filter tap the TMA engine loads a BH x BW pixel box of the
-//   NHWC activation, shifted by the tap offset, straight into the swizzled K-major operand layout (box rows are
-//   pixels, the 64/128-byte inner box is the channel chunk).  Out-of-range pixels are zero-filled by TMA and their
-//   rows are dropped in the epilogue, so valid convolutions of any (odd) size need no padding pass.
-// * Persistent CTAs (one per SM), static round-robin tile schedule, warp-specialised: warp 0 = TMA producer,
-//   warp 1 = TMEM allocator + single-thread tcgen05.mma issuer, warps 2..5 = epilogue (tcgen05.ld -> bias,
-//   LeakyReLU, depth-to-space / skip-add / clamp -> global).  Two TMEM accumulator buffers so the epilogue of tile i
-//   overlaps the MMAs of tile i+1; a multi-stage smem ring between TMA and MMA, all synchronised with mbarriers.
+//   D[128 pixels, N] (fp32, TMEM)  +=  A[128 pixels, K] (fp16 smem, K-major, swizzled)  x  B[N, K] (fp16 smem, K-major)
+//
+// Shared structure: persistent CTAs (one per SM), warp-specialised: warp 0 = TMA producer, warp 1 = TMEM allocator +
+// single-thread tcgen05.mma issuer, warps 2..5 = epilogue.  Two TMEM accumulator buffers (epilogue of tile i overlaps the
+// MMAs of tile i+1), an mbarrier smem ring between TMA and MMA.  Epilogue: tcgen05.ld -> bias + LeakyReLU (+ skip tile that
+// was TMA-loaded into the staging buffer) -> 128B-swizzled smem staging -> TMA store (coalesced, clips image edges); the
+// depth-to-space of ConvTranspose 2x2 is expressed in the store's 5-D tensor map.  3-channel heads store directly.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <string>
+#include <vector>
 
 #include "../hostutil.h"
+#include "../model_pack.h"
 #include "conv_params.h"
+#include "sm100_common.cuh"
 
 namespace w2x {
 
-struct IgemmArgs {
-    CUtensorMap tmA;
-    CUtensorMap tmB;
+using namespace sm100;
+
+struct ConvArgs {
+    CUtensorMap tmA;     // activation loads (igemm: per-tap box; patch kernel: 18x10 patch box)
+    CUtensorMap tmB;     // weights [npad][ktot]
+    CUtensorMap tmOut;   // TMA-store view of the output (useTma)
+    CUtensorMap tmSkip;  // TMA-load view of the skip tensor (hasSkip)
     ConvParams p;
     int kc, bn, bw, bh, bwShift;
     int tilesX, tilesY, tilesN, totalTiles;
     int stages, cchunks, kblocks;
-    uint32_t idesc, tmemCols, bytesA, bytesB, descHi;
+    uint32_t idesc, tmemCols, bytesA, bytesB, descHiA, descHiB;
+    int useTma, nsub, nbuf, hasSkip;
+    uint32_t stageStride, wBytes, stagingBytes;
+    int nSplit;
 };
 
 struct IgemmPlan {
-    IgemmArgs args;
+    ConvArgs args;
     int grid = 0;
     size_t smem = 0;
+    bool patch = false;
 };
 
 namespace {
 
 constexpr int kThreads = 192;
 constexpr int kHeaderBytes = 1024;
+constexpr int kPatchW = 10, kPatchH = 18;
+constexpr uint32_t kPatchBytes = kPatchW * kPatchH * 128;   // 23040
+constexpr uint32_t kPatchStride = 23 * 1024;                // 1024-aligned stage stride
 
-// ---- PTX wrappers ---------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smemU32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbarInit(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbarExpectTx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbarArrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbarWait(uint32_t bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t"
-            "}"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void tmaLoad5d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
-    asm volatile(
-        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
-        "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-        : "memory");
-}
-__device__ __forceinline__ void tmaLoad2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-                 "l"(tm), "r"(bar), "r"(c0), "r"(c1)
-                 : "memory");
-}
-__device__ __forceinline__ void tcFenceBefore() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcFenceAfter() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcCommit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void umma(uint32_t tmemD, uint64_t descA, uint64_t descB, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(tmemD),
-        "l"(descA), "l"(descB), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void tmemLd32(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-}
-__device__ __forceinline__ void tmemLd16(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-}
-__device__ __forceinline__ void tmemLdWait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major swizzled operand descriptor (cute::UMMA::SmemDescriptor layout): start>>4 [0,14), LBO>>4 [16,30),
-// SBO>>4 [32,46), version=1 [46,48), layout type [61,64).
-__device__ __forceinline__ uint64_t makeDesc(uint32_t smemAddr, uint32_t descHi) {
-    return (uint64_t)((smemAddr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)descHi << 32);
-}
+// header layout (byte offsets from the 1024-aligned smem base)
+constexpr uint32_t kOffFull = 0, kOffEmpty = 64, kOffTFull = 128, kOffTEmpty = 144, kOffSkip = 160, kOffW = 184, kOffSlot = 256;
 
 struct TileCoord {
     int img, y0, x0, n0;
 };
-__device__ __forceinline__ TileCoord decodeTile(const IgemmArgs& a, int t) {
+
+__device__ __forceinline__ TileCoord decodeIgemm(const ConvArgs& a, int t) {
     TileCoord c;
     const int nt = t % a.tilesN;
     t /= a.tilesN;
@@ -143,50 +89,190 @@ __device__ __forceinline__ TileCoord decodeTile(const IgemmArgs& a, int t) {
     return c;
 }
 
-__global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constant__ IgemmArgs a) {
-    extern __shared__ uint8_t smemRaw[];
-    const uint32_t rawAddr = smemU32(smemRaw);
-    const uint32_t base = (rawAddr + 1023u) & ~1023u;  // 1024-byte alignment for the 128B swizzle atoms
-    uint8_t* sm = smemRaw + (base - rawAddr);
-    // header: full[stages] | empty[stages] | tmemFull[2] | tmemEmpty[2] | tmem base slot
-    const uint32_t barFull = base, barEmpty = base + 8u * a.stages;
-    const uint32_t barTFull = base + 16u * a.stages, barTEmpty = barTFull + 16u;
-    volatile uint32_t* tmemSlot = reinterpret_cast<volatile uint32_t*>(sm + 16 * a.stages + 32);
-    const uint32_t stage0 = base + kHeaderBytes;
-    const uint32_t stageBytes = a.bytesA + a.bytesB;
+__device__ __forceinline__ TileCoord decodePatch(const ConvArgs& a, int t, int n0) {
+    TileCoord c;
+    const int tx = t % a.tilesX;
+    t /= a.tilesX;
+    const int ty = t % a.tilesY;
+    c.img = t / a.tilesY;
+    c.y0 = ty * a.bh;
+    c.x0 = tx * a.bw;
+    c.n0 = n0;
+    return c;
+}
 
+// coordinates of 64-channel sub-tile `s` of an N tile in the output / skip tensor-map views
+__device__ __forceinline__ void subTileCoords(const ConvArgs& a, const TileCoord& tc, int s, int& c0, int& cz) {
+    const int j = tc.n0 + 64 * s;
+    if (a.p.mode == EPI_D2S) {
+        const int q = j / a.p.cout;
+        c0 = (q & 1) * a.p.cout + (j - q * a.p.cout);  // (dx * C + channel) inside the merged [2][C] inner dimension
+        cz = q >> 1;                                    // dy
+    } else {
+        c0 = j;
+        cz = 0;
+    }
+}
+
+// ---- epilogue shared by both kernels (executed by warps 2..5 = 128 threads) ------------------------------------------
+template <class CoordOf>
+__device__ __forceinline__ void epilogueWarps(const ConvArgs& a, uint32_t base, uint32_t tmemBase, int nMine, CoordOf coordOf) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int quarter = warp & 3;
+    const bool leader = threadIdx.x == 64;
+    const int m = quarter * 32 + lane;
+    const int yy = m >> a.bwShift, xx = m & (a.bw - 1);
+    const uint32_t barTFull = base + kOffTFull, barTEmpty = base + kOffTEmpty, barSkip = base + kOffSkip;
+    const uint32_t staging = base + kHeaderBytes;
+    const uint32_t bufBytes = (uint32_t)a.nsub * 16384u;
+    const int skipHalf = a.p.skip_off >> 1;
 
+    auto issueSkip = [&](int k) {
+        const TileCoord tc = coordOf(k);
+        const int b = k % a.nbuf;
+        mbarExpectTx(barSkip + 8u * b, bufBytes);
+        for (int s = 0; s < a.nsub; ++s) {
+            int c0, cz;
+            subTileCoords(a, tc, s, c0, cz);
+            tmaLoad5d(staging + b * bufBytes + s * 16384u, &a.tmSkip, barSkip + 8u * b, c0, tc.x0 + skipHalf, cz, tc.y0 + skipHalf, tc.img);
+        }
+    };
+    if (a.useTma && a.hasSkip && leader) {
+        for (int k = 0; k < a.nbuf - 1 && k < nMine; ++k) issueSkip(k);
+    }
+
+    int acc = 0;
+    uint32_t accPhase = 0;
+    for (int k = 0; k < nMine; ++k) {
+        const TileCoord tc = coordOf(k);
+        const int b = k % a.nbuf;
+        const uint32_t stg = staging + b * bufBytes;
+        if (a.useTma && !a.hasSkip) {
+            if (leader) bulkWaitRead(a.nbuf - 1);  // staging buffer b is no longer being read by the store of tile k - nbuf
+            namedBarSync(1, 128);
+        }
+        mbarWait(barTFull + 8u * acc, accPhase);
+        tcFenceAfter();
+        if (a.useTma && a.hasSkip) mbarWait(barSkip + 8u * b, (uint32_t)(k / a.nbuf) & 1u);
+        const int y = tc.y0 + yy, x = tc.x0 + xx;
+        const bool valid = y < a.p.gy && x < a.p.gx;
+        const uint32_t taddr = tmemBase + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * a.bn);
+        uint32_t r[32];
+        if (a.bn >= 32) {
+            for (int c0 = 0; c0 < a.bn; c0 += 32) {
+                tmemLd32(taddr + (uint32_t)c0, r);
+                tmemLdWait();
+                if (a.useTma) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int j0 = c0 + 8 * q;
+                        const uint32_t addr = stg + (uint32_t)(j0 >> 6) * 16384u + (uint32_t)m * 128u + ((uint32_t)(((j0 & 63) >> 3) ^ (m & 7)) << 4);
+                        float v[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) v[i] = lrelu(__uint_as_float(r[8 * q + i]) + __ldg(a.p.bias + tc.n0 + j0 + i), a.p.slope);
+                        if (a.hasSkip) {
+                            const uint4 sv = ldsV4(addr);
+                            const __half2* sh = reinterpret_cast<const __half2*>(&sv);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const float2 f = __half22float2(sh[i]);
+                                v[2 * i] += f.x;
+                                v[2 * i + 1] += f.y;
+                            }
+                        }
+                        uint4 o;
+                        __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) oh[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+                        stsV4(addr, o);
+                    }
+                } else if (valid) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        conv_epilogue8(a.p, tc.img, y, x, tc.n0 + c0 + 8 * q, reinterpret_cast<const float*>(r) + 8 * q);
+                }
+            }
+        } else {
+            tmemLd16(taddr, r);
+            tmemLdWait();
+            if (valid) {
+#pragma unroll
+                for (int q = 0; q < 2; ++q) conv_epilogue8(a.p, tc.img, y, x, tc.n0 + 8 * q, reinterpret_cast<const float*>(r) + 8 * q);
+            }
+        }
+        tcFenceBefore();
+        __syncwarp();
+        if (lane == 0) mbarArrive(barTEmpty + 8u * acc);  // accumulator buffer may be overwritten by the next-but-one tile
+        if (++acc == 2) { acc = 0; accPhase ^= 1u; }
+        if (a.useTma) {
+            fenceProxyAsync();
+            namedBarSync(1, 128);
+            if (leader) {
+                for (int s = 0; s < a.nsub; ++s) {
+                    int c0, cz;
+                    subTileCoords(a, tc, s, c0, cz);
+                    tmaStore5d(&a.tmOut, stg + s * 16384u, c0, tc.x0, cz, tc.y0, tc.img);
+                }
+                bulkCommit();
+                if (a.hasSkip) {
+                    const int kn = k + a.nbuf - 1;
+                    if (kn < nMine) {
+                        bulkWaitRead(1);  // the store of tile k-1 (same buffer as tile kn) has finished reading smem
+                        issueSkip(kn);
+                    }
+                }
+            }
+        }
+    }
+    if (a.useTma && leader) bulkWaitAll();
+}
+
+__device__ __forceinline__ void setupCommon(const ConvArgs& a, uint32_t base, uint8_t* sm, int warp) {
     if (threadIdx.x == 0) {
-        for (int s = 0; s < a.stages; ++s) {
-            mbarInit(barFull + 8u * s, 1);
-            mbarInit(barEmpty + 8u * s, 1);
+        for (int s = 0; s < 8; ++s) {
+            mbarInit(base + kOffFull + 8u * s, 1);
+            mbarInit(base + kOffEmpty + 8u * s, 1);
         }
         for (int i = 0; i < 2; ++i) {
-            mbarInit(barTFull + 8u * i, 1);
-            mbarInit(barTEmpty + 8u * i, 4);
+            mbarInit(base + kOffTFull + 8u * i, 1);
+            mbarInit(base + kOffTEmpty + 8u * i, 4);
         }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&a.tmA) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&a.tmB) : "memory");
+        for (int i = 0; i < 3; ++i) mbarInit(base + kOffSkip + 8u * i, 1);
+        mbarInit(base + kOffW, 1);
+        mbarInitFence();
+        tmaPrefetchDesc(&a.tmA);
+        tmaPrefetchDesc(&a.tmB);
+        if (a.useTma) tmaPrefetchDesc(&a.tmOut);
+        if (a.hasSkip) tmaPrefetchDesc(&a.tmSkip);
     }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smemU32((const void*)tmemSlot)), "r"(a.tmemCols)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
+    if (warp == 1) tmemAlloc(smemU32(sm + kOffSlot), a.tmemCols);
     tcFenceBefore();
     __syncthreads();
     tcFenceAfter();
-    const uint32_t tmemBase = *tmemSlot;
+}
+
+// ======================================================================================================================
+// generic implicit GEMM (per-tap A loads)
+// ======================================================================================================================
+__global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constant__ ConvArgs a) {
+    extern __shared__ uint8_t smemRaw[];
+    const uint32_t rawAddr = smemU32(smemRaw);
+    const uint32_t base = (rawAddr + 1023u) & ~1023u;
+    uint8_t* sm = smemRaw + (base - rawAddr);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    setupCommon(a, base, sm, warp);
+    const uint32_t tmemBase = *reinterpret_cast<volatile uint32_t*>(sm + kOffSlot);
+    const uint32_t stage0 = base + kHeaderBytes + a.stagingBytes;
+    const uint32_t stageBytes = a.bytesA + a.bytesB;
+    const uint32_t barFull = base + kOffFull, barEmpty = base + kOffEmpty, barTFull = base + kOffTFull, barTEmpty = base + kOffTEmpty;
+    const int nMine = a.totalTiles > (int)blockIdx.x ? (a.totalTiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
     if (warp == 0) {
-        // ================= TMA producer (one thread) =================
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int t = blockIdx.x; t < a.totalTiles; t += gridDim.x) {
-                const TileCoord tc = decodeTile(a, t);
+            for (int k = 0; k < nMine; ++k) {
+                const TileCoord tc = decodeIgemm(a, blockIdx.x + k * gridDim.x);
                 for (int tap = 0; tap < a.p.ntaps; ++tap) {
                     const ConvTap tp = a.p.tap[tap];
                     for (int cc = 0; cc < a.cchunks; ++cc) {
@@ -202,14 +288,11 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
             }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer (one thread) =================
         if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            int acc = 0;
-            uint32_t accPhase = 0;
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, accPhase = 0;
             const int kSteps = a.kc / 16;
-            for (int t = blockIdx.x; t < a.totalTiles; t += gridDim.x) {
+            for (int k = 0; k < nMine; ++k) {
                 mbarWait(barTEmpty + 8u * acc, accPhase ^ 1u);
                 tcFenceAfter();
                 const uint32_t tmemD = tmemBase + (uint32_t)(acc * a.bn);
@@ -218,65 +301,179 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
                     tcFenceAfter();
                     const uint32_t sA = stage0 + stage * stageBytes;
                     const uint32_t sB = sA + a.bytesA;
-                    for (int k = 0; k < kSteps; ++k) {
-                        umma(tmemD, makeDesc(sA + 32u * k, a.descHi), makeDesc(sB + 32u * k, a.descHi), a.idesc,
-                             (kb | k) != 0 ? 1u : 0u);
-                    }
-                    tcCommit(barEmpty + 8u * stage);  // frees the smem slot when these MMAs retire
+                    for (int ks = 0; ks < kSteps; ++ks)
+                        umma(tmemD, makeDesc(sA + 32u * ks, a.descHiA), makeDesc(sB + 32u * ks, a.descHiB), a.idesc, (kb | ks) != 0 ? 1u : 0u);
+                    tcCommit(barEmpty + 8u * stage);
                     if (++stage == a.stages) { stage = 0; phase ^= 1u; }
                 }
-                tcCommit(barTFull + 8u * acc);  // accumulator complete
+                tcCommit(barTFull + 8u * acc);
                 if (++acc == 2) { acc = 0; accPhase ^= 1u; }
             }
         }
     } else {
-        // ================= epilogue warps (TMEM lanes 32*(warp%4) .. +31) =================
-        const int quarter = warp & 3;
-        const int m = quarter * 32 + lane;
-        const int yy = m >> a.bwShift, xx = m & (a.bw - 1);
-        int acc = 0;
-        uint32_t accPhase = 0;
-        for (int t = blockIdx.x; t < a.totalTiles; t += gridDim.x) {
-            const TileCoord tc = decodeTile(a, t);
-            const int y = tc.y0 + yy, x = tc.x0 + xx;
-            const bool valid = y < a.p.gy && x < a.p.gx;
-            mbarWait(barTFull + 8u * acc, accPhase);
-            tcFenceAfter();
-            const uint32_t taddr = tmemBase + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * a.bn);
-            uint32_t r[32];
-            if (a.bn >= 32) {
-                for (int c0 = 0; c0 < a.bn; c0 += 32) {
-                    tmemLd32(taddr + (uint32_t)c0, r);
-                    tmemLdWait();
-                    if (valid) {
-#pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            conv_epilogue8(a.p, tc.img, y, x, tc.n0 + c0 + 8 * q, reinterpret_cast<const float*>(r) + 8 * q);
-                    }
-                }
-            } else {
-                tmemLd16(taddr, r);
-                tmemLdWait();
-                if (valid) {
-#pragma unroll
-                    for (int q = 0; q < 2; ++q)
-                        conv_epilogue8(a.p, tc.img, y, x, tc.n0 + 8 * q, reinterpret_cast<const float*>(r) + 8 * q);
-                }
-            }
-            tcFenceBefore();
-            __syncwarp();
-            if (lane == 0) mbarArrive(barTEmpty + 8u * acc);
-            if (++acc == 2) { acc = 0; accPhase ^= 1u; }
-        }
+        epilogueWarps(a, base, tmemBase, nMine, [&](int k) { return decodeIgemm(a, blockIdx.x + k * gridDim.x); });
     }
 
     tcFenceBefore();
     __syncthreads();
     if (warp == 1) {
         tcFenceAfter();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmemBase), "r"(a.tmemCols) : "memory");
+        tmemDealloc(tmemBase, a.tmemCols);
     }
 }
+
+// ======================================================================================================================
+// 3x3 convolution from one input patch per tile, weights resident in shared memory
+// ======================================================================================================================
+__global__ void __launch_bounds__(kThreads, 1) conv3x3_patch_kernel(const __grid_constant__ ConvArgs a) {
+    extern __shared__ uint8_t smemRaw[];
+    const uint32_t rawAddr = smemU32(smemRaw);
+    const uint32_t base = (rawAddr + 1023u) & ~1023u;
+    uint8_t* sm = smemRaw + (base - rawAddr);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    setupCommon(a, base, sm, warp);
+    const uint32_t tmemBase = *reinterpret_cast<volatile uint32_t*>(sm + kOffSlot);
+    const uint32_t wBase = base + kHeaderBytes + a.stagingBytes;
+    const uint32_t stage0 = wBase + a.wBytes;
+    const uint32_t barFull = base + kOffFull, barEmpty = base + kOffEmpty, barTFull = base + kOffTFull, barTEmpty = base + kOffTEmpty;
+    const uint32_t barW = base + kOffW;
+    // this CTA owns output-channel slice `slice` and every (gridDim/nSplit)-th pixel tile
+    const int slice = blockIdx.x % a.nSplit, first = blockIdx.x / a.nSplit, step = gridDim.x / a.nSplit;
+    const int n0 = slice * a.bn;
+    const int nMine = a.totalTiles > first ? (a.totalTiles - 1 - first) / step + 1 : 0;
+    const uint32_t tapBytes = (uint32_t)a.bn * 128u;  // one (tap, 64-channel chunk) block of B: [bn rows][64 k]
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // resident weights: 9 * cchunks TMA boxes, one barrier
+            mbarExpectTx(barW, a.wBytes);
+            for (int tap = 0; tap < 9; ++tap)
+                for (int cc = 0; cc < a.cchunks; ++cc)
+                    tmaLoad2d(wBase + (uint32_t)(tap * a.cchunks + cc) * tapBytes, &a.tmB, barW, tap * a.p.cin + cc * 64, n0);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int k = 0; k < nMine; ++k) {
+                const TileCoord tc = decodePatch(a, first + k * step, n0);
+                for (int cc = 0; cc < a.cchunks; ++cc) {
+                    mbarWait(barEmpty + 8u * stage, phase ^ 1u);
+                    const uint32_t full = barFull + 8u * stage;
+                    mbarExpectTx(full, kPatchBytes);
+                    tmaLoad5d(stage0 + stage * kPatchStride, &a.tmA, full, cc * 64, tc.x0, 0, tc.y0, tc.img);
+                    if (++stage == a.stages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, accPhase = 0;
+            mbarWait(barW, 0);
+            for (int k = 0; k < nMine; ++k) {
+                mbarWait(barTEmpty + 8u * acc, accPhase ^ 1u);
+                tcFenceAfter();
+                const uint32_t tmemD = tmemBase + (uint32_t)(acc * a.bn);
+                for (int cc = 0; cc < a.cchunks; ++cc) {
+                    mbarWait(barFull + 8u * stage, phase);
+                    tcFenceAfter();
+                    const uint32_t sP = stage0 + stage * kPatchStride;
+#pragma unroll
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const uint32_t sA = sP + (uint32_t)((tap / 3) * kPatchW + (tap % 3)) * 128u;  // shifted view of the patch
+                        const uint32_t sB = wBase + (uint32_t)(tap * a.cchunks + cc) * tapBytes;
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks)
+                            umma(tmemD, makeDesc(sA + 32u * ks, a.descHiA), makeDesc(sB + 32u * ks, a.descHiB), a.idesc, (cc | tap | ks) != 0 ? 1u : 0u);
+                    }
+                    tcCommit(barEmpty + 8u * stage);
+                    if (++stage == a.stages) { stage = 0; phase ^= 1u; }
+                }
+                tcCommit(barTFull + 8u * acc);
+                if (++acc == 2) { acc = 0; accPhase ^= 1u; }
+            }
+        }
+    } else {
+        epilogueWarps(a, base, tmemBase, nMine, [&](int k) { return decodePatch(a, first + k * step, n0); });
+    }
+
+    tcFenceBefore();
+    __syncthreads();
+    if (warp == 1) {
+        tcFenceAfter();
+        tmemDealloc(tmemBase, a.tmemCols);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// UMMA descriptor probe (development aid, reachable through w2x_probe_umma): one TMA-loaded, 128B-swizzled patch of
+// 18 x 16 pixels x 64 channels; for every 3x3 tap the A operand is a SHIFTED VIEW of that patch (start address moved by
+// (ky*16+kx) pixels = 128-byte rows, 8-row groups SBO = 16 pixels apart).  Checks which base_offset convention makes
+// shifted views of a swizzled tile read the right data.  mode 0: base_offset = (start >> 7) & 7, mode 1: 0.
+// ------------------------------------------------------------------------------------------------------------
+struct ProbeArgs {
+    CUtensorMap tmP, tmB;
+    float* out;  // [9][128][64]
+    int mode, pitch, sbo;
+};
+
+__global__ void __launch_bounds__(128, 1) umma_probe_kernel(const __grid_constant__ ProbeArgs a) {
+    extern __shared__ uint8_t smemRaw[];
+    const uint32_t rawAddr = smemU32(smemRaw);
+    const uint32_t base = (rawAddr + 1023u) & ~1023u;
+    uint8_t* sm = smemRaw + (base - rawAddr);
+    const uint32_t bar = base, barMma = base + 8;
+    volatile uint32_t* tmemSlot = reinterpret_cast<volatile uint32_t*>(sm + 32);
+    const uint32_t sPatch = base + 1024, sB = sPatch + 40960;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        mbarInit(bar, 1);
+        mbarInit(barMma, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smemU32((const void*)tmemSlot)), "r"(64u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcFenceBefore();
+    __syncthreads();
+    tcFenceAfter();
+    const uint32_t tmemBase = *tmemSlot;
+    if (threadIdx.x == 0) {
+        mbarExpectTx(bar, 18u * a.pitch * 128u + 64u * 128u);
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(sPatch),
+                     "l"(&a.tmP), "r"(bar), "r"(0), "r"(0), "r"(0)
+                     : "memory");
+        tmaLoad2d(sB, &a.tmB, bar, 0, 0);
+    }
+    mbarWait(bar, 0);
+    const uint32_t idesc = (1u << 4) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+    for (int tap = 0; tap < 9; ++tap) {
+        if (threadIdx.x == 0) {
+            tcFenceAfter();
+            const int ky = tap / 3, kx = tap % 3;
+            const uint32_t start = sPatch + (uint32_t)(ky * a.pitch + kx) * 128u;
+            const uint32_t bo = a.mode == 0 ? ((start >> 7) & 7u) : 0u;
+            const uint32_t descHiA = ((uint32_t)a.sbo >> 4) | (1u << 14) | (bo << 17) | (2u << 29);
+            const uint32_t descHiB = (1024u >> 4) | (1u << 14) | (2u << 29);
+            for (int k = 0; k < 4; ++k) umma(tmemBase, makeDesc(start + 32u * k, descHiA), makeDesc(sB + 32u * k, descHiB), idesc, k != 0);
+            tcCommit(barMma);
+        }
+        mbarWait(barMma, tap & 1);
+        tcFenceAfter();
+        uint32_t r[32];
+        for (int c0 = 0; c0 < 64; c0 += 32) {
+            tmemLd32(tmemBase + ((uint32_t)(warp * 32) << 16) + c0, r);
+            tmemLdWait();
+            for (int i = 0; i < 32; ++i) a.out[((size_t)tap * 128 + warp * 32 + lane) * 64 + c0 + i] = __uint_as_float(r[i]);
+        }
+        tcFenceBefore();
+        __syncthreads();
+    }
+    if (warp == 0) {
+        tcFenceAfter();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmemBase), "r"(64u) : "memory");
+    }
+}
+
 
 // ---- host side -------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -306,26 +503,133 @@ int numSMs() {
     return n;
 }
 
-}  // namespace
+constexpr size_t kSmemLimit = 227 * 1024;
 
-bool igemmSupported(const ConvParams& p) {
-    if (p.cin % 32 != 0 || p.npad % 16 != 0) return false;
-    if (p.npad > 256 && p.npad % 256 != 0) return false;
-    if (p.npad < 256 && (p.npad & (p.npad - 1)) != 0) return false;  // 16, 32, 64, 128
-    if (p.ntaps < 1 || p.ntaps > 9) return false;
+void checkCuda(cudaError_t e) {
+    if (e != cudaSuccess) throw Error(std::string("cuda: ") + cudaGetErrorString(e));
+}
+
+// 5-D fp16 tensor map over (c, x, z, y, img) with element strides for x, z, y, img
+void encode5d(CUtensorMap* tm, const void* ptr, const long long dims[5], const long long stridesElems[4], const int box[5], bool sw128,
+              const char* what) {
+    cuuint64_t d[5], s[4];
+    cuuint32_t b[5], es[5] = {1, 1, 1, 1, 1};
+    for (int i = 0; i < 5; ++i) { d[i] = (cuuint64_t)dims[i]; b[i] = (cuuint32_t)box[i]; }
+    for (int i = 0; i < 4; ++i) s[i] = (cuuint64_t)stridesElems[i] * 2;
+    CUresult r = encodeTiled()(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, (void*)ptr, d, s, b, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               sw128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw Error(std::string("cuTensorMapEncodeTiled(") + what + ") failed with code " + std::to_string((int)r));
+}
+
+void encodeWeights(CUtensorMap* tm, const ConvParams& p, int kc, int rows, bool sw128) {
+    cuuint64_t dims[2] = {(cuuint64_t)p.ktot, (cuuint64_t)p.npad};
+    cuuint64_t strides[1] = {(cuuint64_t)p.ktot * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)rows};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = encodeTiled()(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)p.w, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               sw128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw Error("cuTensorMapEncodeTiled(weights) failed with code " + std::to_string((int)r));
+}
+
+// can the epilogue go through swizzled smem staging + TMA store?
+bool tmaEpilogueOk(const ConvParams& p) {
+    if (p.mode == EPI_STORE) return p.cout % 64 == 0 && p.npad == p.cout && p.out_c == p.cout;
+    if (p.mode == EPI_D2S) {
+        if (p.cout % 64 != 0 || p.out_c != p.cout || (p.out_w & 1) || (p.out_h & 1)) return false;
+        if (p.skip && ((p.skip_off & 1) || (p.skip_w & 1) || (p.skip_h & 1) || p.skip_c != p.cout || p.skip_scale)) return false;
+        return true;
+    }
+    return false;
+}
+
+void encodeOutMaps(ConvArgs& a) {
+    const ConvParams& p = a.p;
+    const int box[5] = {64, a.bw, 1, a.bh, 1};
+    if (p.mode == EPI_STORE) {
+        const long long dims[5] = {p.out_c, p.out_w, 1, p.out_h, p.gn};
+        const long long st[4] = {p.out_c, (long long)p.out_w * p.out_c, (long long)p.out_w * p.out_c, (long long)p.out_h * p.out_w * p.out_c};
+        encode5d(&a.tmOut, p.out, dims, st, box, true, "out");
+    } else {  // EPI_D2S: (2C | W/2 | dy | H/2 | img) view so that the depth-to-space scatter is a plain box store
+        const long long C = p.cout;
+        const long long dims[5] = {2 * C, p.out_w / 2, 2, p.out_h / 2, p.gn};
+        const long long st[4] = {2 * C, (long long)p.out_w * C, 2ll * p.out_w * C, (long long)p.out_h * p.out_w * C};
+        encode5d(&a.tmOut, p.out, dims, st, box, true, "out(d2s)");
+        if (p.skip) {
+            const long long sd[5] = {2 * C, p.skip_w / 2, 2, p.skip_h / 2, p.gn};
+            const long long ss[4] = {2 * C, (long long)p.skip_w * C, 2ll * p.skip_w * C, (long long)p.skip_h * p.skip_w * C};
+            encode5d(&a.tmSkip, p.skip, sd, ss, box, true, "skip(d2s)");
+        }
+    }
+}
+
+bool wantsPatchKernel(const ConvParams& p) {
+    if (!p.is3x3 || p.cin % 64 != 0 || p.cin > 128) return false;
+    if (!(p.npad % 64 == 0 || p.npad == 16)) return false;
+    if (p.npad % 64 == 0 && !tmaEpilogueOk(p)) return false;
     return true;
 }
 
-IgemmPlan* igemmCreatePlan(const ConvParams& p) {
-    if (!igemmSupported(p)) throw Error("igemm: unsupported layer shape");
-    IgemmPlan* plan = new IgemmPlan();
-    IgemmArgs& a = plan->args;
-    a.p = p;
+void planPatch(IgemmPlan* plan) {
+    ConvArgs& a = plan->args;
+    const ConvParams& p = a.p;
+    plan->patch = true;
+    a.kc = 64;
+    a.bn = p.npad % 64 == 0 ? 64 : 16;
+    a.nSplit = p.npad / a.bn;
+    a.cchunks = p.cin / 64;
+    a.kblocks = a.cchunks;
+    a.bw = 8; a.bh = 16; a.bwShift = 3;
+    a.tilesX = (p.gx + 7) / 8;
+    a.tilesY = (p.gy + 15) / 16;
+    a.tilesN = 1;
+    a.totalTiles = a.tilesX * a.tilesY * p.gn;  // per output-channel slice
+    a.useTma = a.bn == 64 ? 1 : 0;
+    a.hasSkip = 0;
+    a.nsub = 1;
+    a.nbuf = a.useTma ? 2 : 1;
+    a.stagingBytes = a.useTma ? a.nbuf * 16384u : 0u;
+    a.wBytes = 9u * a.cchunks * a.bn * 128u;
+    a.stageStride = kPatchStride;
+    const size_t fixed = 1024 + kHeaderBytes + a.stagingBytes + a.wBytes;
+    if (fixed + 2 * (size_t)kPatchStride > kSmemLimit) throw Error("conv3x3 patch kernel: weights do not fit in shared memory");
+    a.stages = (int)std::min<size_t>(8, (kSmemLimit - fixed) / kPatchStride);
+    uint32_t cols = 32;
+    while (cols < (uint32_t)(2 * a.bn)) cols *= 2;
+    a.tmemCols = cols;
+    a.idesc = instrDescF16(128, a.bn);
+    a.descHiA = (1280u >> 4) | (1u << 14) | (2u << 29);  // 8-pixel row groups are one patch row (10 pixels x 128 B) apart
+    a.descHiB = (1024u >> 4) | (1u << 14) | (2u << 29);
+    a.bytesA = kPatchBytes;
+    a.bytesB = 0;
+    {
+        const long long dims[5] = {p.dimc, p.dimx, p.dimz, p.dimy, p.gn};
+        const long long st[4] = {p.sx, p.sz, p.sy, p.sn};
+        const int box[5] = {64, kPatchW, 1, kPatchH, 1};
+        encode5d(&a.tmA, p.in, dims, st, box, true, "patch");
+    }
+    encodeWeights(&a.tmB, p, 64, a.bn, true);
+    if (a.useTma) encodeOutMaps(a);
+    const int sms = numSMs();
+    int grid = std::min(sms, a.totalTiles * a.nSplit);
+    grid = std::max(a.nSplit, grid / a.nSplit * a.nSplit);
+    plan->grid = grid;
+    plan->smem = fixed + (size_t)a.stages * kPatchStride;
+}
+
+void planIgemm(IgemmPlan* plan) {
+    ConvArgs& a = plan->args;
+    const ConvParams& p = a.p;
+    plan->patch = false;
     a.kc = (p.cin % 64 == 0) ? 64 : 32;
+    a.useTma = tmaEpilogueOk(p) ? 1 : 0;
+    a.hasSkip = (a.useTma && p.mode == EPI_D2S && p.skip) ? 1 : 0;
     a.bn = std::min(p.npad, 256);
+    if (p.mode == EPI_D2S && a.useTma) a.bn = 128;  // 128 columns = one or two depth-to-space phases per tile
+    a.nSplit = 1;
     a.cchunks = p.cin / a.kc;
     a.kblocks = p.ntaps * a.cchunks;
-    // pixel tile: pick the BH x BW (= 128) split that wastes the fewest rows
     long long best = -1;
     for (int bw = 8; bw <= 128; bw *= 2) {
         const int bh = 128 / bw;
@@ -340,62 +644,147 @@ IgemmPlan* igemmCreatePlan(const ConvParams& p) {
     a.totalTiles = a.tilesX * a.tilesY * a.tilesN * p.gn;
     a.bytesA = 128u * a.kc * 2u;
     a.bytesB = (uint32_t)a.bn * a.kc * 2u;
-    const size_t budget = 200 * 1024;
-    a.stages = (int)std::min<size_t>(8, budget / (a.bytesA + a.bytesB));
-    if (a.stages < 2) throw Error("igemm: stage does not fit in shared memory");
+    a.nsub = a.useTma ? a.bn / 64 : 0;
+    const size_t stageBytes = a.bytesA + a.bytesB;
+    const size_t avail = kSmemLimit - 1024 - kHeaderBytes;
+    a.nbuf = 1;
+    a.stagingBytes = 0;
+    if (a.useTma) {
+        const size_t buf = (size_t)a.nsub * 16384;
+        int nbuf = a.hasSkip ? 3 : 2;
+        const int minBuf = a.hasSkip ? 2 : 1;
+        while (nbuf > minBuf && (avail - nbuf * buf) / stageBytes < 3) --nbuf;
+        a.nbuf = nbuf;
+        a.stagingBytes = (uint32_t)(nbuf * buf);
+    }
+    if (avail < a.stagingBytes + 2 * stageBytes) throw Error("igemm: tile does not fit in shared memory");
+    a.stages = (int)std::min<size_t>(8, (avail - a.stagingBytes) / stageBytes);
     uint32_t cols = 32;
     while (cols < (uint32_t)(2 * a.bn)) cols *= 2;
     a.tmemCols = cols;
-    // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 [4,6), A=B=F16, both K-major, N>>3 [17,23), M>>4 [24,29)
-    a.idesc = (1u << 4) | ((uint32_t)(a.bn >> 3) << 17) | ((128u >> 4) << 24);
+    a.idesc = instrDescF16(128, a.bn);
     const bool sw128 = a.kc == 64;
-    const uint32_t sbo = sw128 ? 1024u : 512u;  // 8 rows x (128 | 64) bytes
-    a.descHi = (sbo >> 4) | (1u << 14) | ((sw128 ? 2u : 4u) << 29);
-
-    // A: 5-D view (c, x, z, y, img)
+    const uint32_t sbo = sw128 ? 1024u : 512u;
+    a.descHiA = a.descHiB = (sbo >> 4) | (1u << 14) | ((sw128 ? 2u : 4u) << 29);
     {
-        cuuint64_t dims[5] = {(cuuint64_t)p.dimc, (cuuint64_t)p.dimx, (cuuint64_t)p.dimz, (cuuint64_t)p.dimy, (cuuint64_t)p.gn};
-        cuuint64_t strides[4] = {(cuuint64_t)p.sx * 2, (cuuint64_t)p.sz * 2, (cuuint64_t)p.sy * 2, (cuuint64_t)p.sn * 2};
-        cuuint32_t box[5] = {(cuuint32_t)a.kc, (cuuint32_t)a.bw, 1, (cuuint32_t)a.bh, 1};
-        cuuint32_t es[5] = {1, 1, 1, 1, 1};
-        CUresult r = encodeTiled()(&a.tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, (void*)p.in, dims, strides, box, es,
-                                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
-                                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) { delete plan; throw Error("igemm: cuTensorMapEncodeTiled(A) failed with code " + std::to_string((int)r)); }
+        const long long dims[5] = {p.dimc, p.dimx, p.dimz, p.dimy, p.gn};
+        const long long st[4] = {p.sx, p.sz, p.sy, p.sn};
+        const int box[5] = {a.kc, a.bw, 1, a.bh, 1};
+        encode5d(&a.tmA, p.in, dims, st, box, sw128, "A");
     }
-    // B: [npad][ktot]
-    {
-        cuuint64_t dims[2] = {(cuuint64_t)p.ktot, (cuuint64_t)p.npad};
-        cuuint64_t strides[1] = {(cuuint64_t)p.ktot * 2};
-        cuuint32_t box[2] = {(cuuint32_t)a.kc, (cuuint32_t)a.bn};
-        cuuint32_t es[2] = {1, 1};
-        CUresult r = encodeTiled()(&a.tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)p.w, dims, strides, box, es,
-                                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
-                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) { delete plan; throw Error("igemm: cuTensorMapEncodeTiled(B) failed with code " + std::to_string((int)r)); }
-    }
+    encodeWeights(&a.tmB, p, a.kc, a.bn, sw128);
+    if (a.useTma) encodeOutMaps(a);
     plan->grid = std::min(a.totalTiles, numSMs());
-    plan->smem = 1024 + kHeaderBytes + (size_t)a.stages * (a.bytesA + a.bytesB);
-    static bool attrSet = false;
-    if (!attrSet) {
-        cudaError_t e = cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) { delete plan; throw Error(std::string("igemm: cudaFuncSetAttribute: ") + cudaGetErrorString(e)); }
-        attrSet = true;
+    plan->smem = 1024 + kHeaderBytes + a.stagingBytes + (size_t)a.stages * stageBytes;
+}
+
+}  // namespace
+
+bool igemmSupported(const ConvParams& p) {
+    if (p.cin % 32 != 0 || p.npad % 16 != 0) return false;
+    if (p.npad > 256 && p.npad % 256 != 0) return false;
+    if (p.npad < 256 && (p.npad & (p.npad - 1)) != 0) return false;  // 16, 32, 64, 128
+    if (p.ntaps < 1 || p.ntaps > 9) return false;
+    return true;
+}
+
+IgemmPlan* igemmCreatePlan(const ConvParams& p) {
+    if (!igemmSupported(p)) throw Error("igemm: unsupported layer shape");
+    IgemmPlan* plan = new IgemmPlan();
+    plan->args = ConvArgs{};
+    plan->args.p = p;
+    try {
+        static const bool noPatch = [] { const char* e = std::getenv("W2X_NO_PATCH"); return e && *e == '1'; }();
+        if (!noPatch && wantsPatchKernel(p)) planPatch(plan);
+        else planIgemm(plan);
+        static bool attrSet = false;
+        if (!attrSet) {
+            checkCuda(cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+            checkCuda(cudaFuncSetAttribute(conv3x3_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+            attrSet = true;
+        }
+    } catch (...) {
+        delete plan;
+        throw;
     }
     return plan;
 }
 
 void igemmDestroyPlan(IgemmPlan* plan) { delete plan; }
 
+const char* igemmDescribe(const IgemmPlan* plan, char* buf, int cap) {
+    const ConvArgs& a = plan->args;
+    std::snprintf(buf, cap, "%s bn=%d kc=%d tile=%dx%d stages=%d nbuf=%d tma=%d skip=%d split=%d grid=%d smem=%zu", plan->patch ? "patch3x3" : "igemm",
+                  a.bn, a.kc, a.bh, a.bw, a.stages, a.nbuf, a.useTma, a.hasSkip, a.nSplit, plan->grid, plan->smem);
+    return buf;
+}
+
 void igemmLaunch(const IgemmPlan* plan, cudaStream_t s, __half* outOverride) {
     if (plan->grid <= 0) return;
-    if (outOverride && outOverride != plan->args.p.out) {
-        IgemmArgs a = plan->args;  // only the epilogue's destination changes; the tensor maps stay valid
-        a.p.out = outOverride;
-        igemm_kernel<<<plan->grid, kThreads, plan->smem, s>>>(a);
-    } else {
-        igemm_kernel<<<plan->grid, kThreads, plan->smem, s>>>(plan->args);
+    const bool redirect = outOverride && outOverride != plan->args.p.out;
+    if (redirect && plan->args.useTma) throw Error("igemm: output redirection is not available for TMA-store layers");
+    ConvArgs local;
+    const ConvArgs* a = &plan->args;
+    if (redirect) {
+        local = plan->args;  // only the epilogue's destination changes; the tensor maps stay valid
+        local.p.out = outOverride;
+        a = &local;
     }
+    if (plan->patch) conv3x3_patch_kernel<<<plan->grid, kThreads, plan->smem, s>>>(*a);
+    else igemm_kernel<<<plan->grid, kThreads, plan->smem, s>>>(*a);
 }
+
+
+// returns 0 on success; err9[tap] = max |device - host| for the given base_offset mode
+int probeUmma(int mode, int pitch, float* err9) {
+    if (pitch % 8 != 0 && mode < 2) { /* allowed: explores non-1024 SBO */ }
+    const int rows = 18, pix = rows * pitch;
+    std::vector<uint16_t> hp((size_t)pix * 64), hb(64 * 64);
+    uint32_t st = 12345u;
+    auto rnd = [&]() { st = st * 1664525u + 1013904223u; return ((st >> 9) & 0xFFFF) / 65536.0f - 0.5f; };
+    for (auto& v : hp) v = floatToHalfBits(rnd());
+    for (auto& v : hb) v = floatToHalfBits(rnd());
+    __half *dP = nullptr, *dB = nullptr;
+    float* dOut = nullptr;
+    if (cudaMalloc(&dP, hp.size() * 2) || cudaMalloc(&dB, hb.size() * 2) || cudaMalloc(&dOut, 9 * 128 * 64 * 4)) return 1;
+    cudaMemcpy(dP, hp.data(), hp.size() * 2, cudaMemcpyHostToDevice);
+    cudaMemcpy(dB, hb.data(), hb.size() * 2, cudaMemcpyHostToDevice);
+    cudaMemset(dOut, 0, 9 * 128 * 64 * 4);
+    ProbeArgs a{};
+    a.out = dOut; a.mode = mode; a.pitch = pitch; a.sbo = pitch * 128;
+    {
+        cuuint64_t dims[3] = {64, (cuuint64_t)pitch, (cuuint64_t)rows};
+        cuuint64_t strides[2] = {128, (cuuint64_t)pitch * 128};
+        cuuint32_t box[3] = {64, (cuuint32_t)pitch, (cuuint32_t)rows};
+        cuuint32_t es[3] = {1, 1, 1};
+        if (encodeTiled()(&a.tmP, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, dP, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return 2;
+        cuuint64_t dimsB[2] = {64, 64};
+        cuuint64_t stridesB[1] = {128};
+        cuuint32_t boxB[2] = {64, 64};
+        if (encodeTiled()(&a.tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, dB, dimsB, stridesB, boxB, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return 2;
+    }
+    cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    umma_probe_kernel<<<1, 128, 2048 + 40960 + 8192, nullptr>>>(a);
+    if (cudaDeviceSynchronize() != cudaSuccess) return 3;
+    std::vector<float> ho(9 * 128 * 64);
+    cudaMemcpy(ho.data(), dOut, ho.size() * 4, cudaMemcpyDeviceToHost);
+    for (int tap = 0; tap < 9; ++tap) {
+        const int ky = tap / 3, kx = tap % 3;
+        double md = 0;
+        for (int m = 0; m < 128; ++m)
+            for (int n = 0; n < 64; ++n) {
+                double acc = 0;
+                const int px = (ky + m / 8) * pitch + kx + (m % 8);
+                for (int c = 0; c < 64; ++c) acc += (double)halfBitsToFloat(hp[(size_t)px * 64 + c]) * halfBitsToFloat(hb[(size_t)n * 64 + c]);
+                md = std::max(md, std::fabs(acc - ho[((size_t)tap * 128 + m) * 64 + n]));
+            }
+        err9[tap] = (float)md;
+    }
+    cudaFree(dP); cudaFree(dB); cudaFree(dOut);
+    return 0;
+}
+
 
 }  // namespace w2x

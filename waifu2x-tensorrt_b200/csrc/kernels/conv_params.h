@@ -29,6 +29,7 @@ struct ConvParams {
     int cin;                     // channels per tap
     int ntaps;
     ConvTap tap[9];
+    int is3x3;                   // plain 3x3 stride-1 valid conv on an NHWC view (eligible for the patch kernel)
     // GEMM extents
     int gx, gy, gn;  // pixel grid per image (x, y) and image count
     int npad, ktot;
@@ -132,6 +133,8 @@ IgemmPlan* igemmCreatePlan(const ConvParams& p);                  // throws w2x:
 void igemmDestroyPlan(IgemmPlan* plan);
 void igemmLaunch(const IgemmPlan* plan, cudaStream_t s, __half* outOverride = nullptr);
 bool igemmSupported(const ConvParams& p);
+const char* igemmDescribe(const IgemmPlan* plan, char* buf, int cap);
+int probeUmma(int mode, int pitch, float* err9);
 
 // squeeze/excite
 void launchSeSqueeze(const __half* x, int n, int h, int w, int c, float* partial, int nblk, cudaStream_t s);
