@@ -43,8 +43,9 @@ void launchConvDirect(const ConvParams& p, cudaStream_t s) {
 }
 
 // ---- first layer: NHWC4 fp16 -> 32 channels, 3x3 valid, bias + LeakyReLU -----------------------------------
-// Block = 128 threads covering a 64 x 4 output patch... each thread: 2 horizontally adjacent pixels x 32 channels.
-__global__ void __launch_bounds__(128) conv_first_kernel(ConvParams p) {
+// Persistent blocks (grid = a few per SM): the 36x32 weight table is converted to fp32 in shared memory ONCE per block,
+// then the block strides over 64x4-pixel work items.  Each thread: 2 horizontally adjacent pixels x 32 channels.
+__global__ void __launch_bounds__(128) conv_first_kernel(ConvParams p, int itemsX, int itemsY, int totalItems) {
     __shared__ float sw[36 * 32];  // [k][co], k = (ky*3+kx)*4 + ci
     __shared__ float sb[32];
     for (int i = threadIdx.x; i < 36 * 32; i += blockDim.x) {
@@ -53,72 +54,85 @@ __global__ void __launch_bounds__(128) conv_first_kernel(ConvParams p) {
     }
     if (threadIdx.x < 32) sb[threadIdx.x] = p.bias[threadIdx.x];
     __syncthreads();
-    const int x = (blockIdx.x * 32 + (threadIdx.x & 31)) * 2;
-    const int y = blockIdx.y * 4 + (threadIdx.x >> 5);
-    const int img = blockIdx.z;
-    if (x >= p.gx || y >= p.gy) return;
-    const bool two = x + 1 < p.gx;
-    // 3 rows x 4 columns x 4 channels neighbourhood (the 4th column only when the second pixel exists)
-    float in[3][4][3];
+    for (int item = blockIdx.x; item < totalItems; item += gridDim.x) {
+        const int ix = item % itemsX;
+        const int iy = (item / itemsX) % itemsY;
+        const int img = item / (itemsX * itemsY);
+        const int x = (ix * 32 + (threadIdx.x & 31)) * 2;
+        const int y = iy * 4 + (threadIdx.x >> 5);
+        if (x >= p.gx || y >= p.gy) continue;
+        const bool two = x + 1 < p.gx;
+        // 3 rows x 4 columns x 3 channels neighbourhood (the 4th column only when the second pixel exists)
+        float in[3][4][3];
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
-        const __half* row = p.in + (long long)img * p.sn + (long long)(y + ky) * p.sy + (long long)x * p.sx;
+        for (int ky = 0; ky < 3; ++ky) {
+            const __half* row = p.in + (long long)img * p.sn + (long long)(y + ky) * p.sy + (long long)x * p.sx;
 #pragma unroll
-        for (int kx = 0; kx < 4; ++kx) {
-            if (kx < 3 || two) {
-                const Half4 v = *reinterpret_cast<const Half4*>(row + (long long)kx * p.sx);
-                const float2 a = __half22float2(v.a), b = __half22float2(v.b);
-                in[ky][kx][0] = a.x; in[ky][kx][1] = a.y; in[ky][kx][2] = b.x;
-            } else {
-                in[ky][kx][0] = in[ky][kx][1] = in[ky][kx][2] = 0.f;
-            }
-        }
-    }
-    float acc0[32], acc1[32];
-#pragma unroll
-    for (int co = 0; co < 32; ++co) { acc0[co] = sb[co]; acc1[co] = sb[co]; }
-#pragma unroll
-    for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-        for (int kx = 0; kx < 3; ++kx)
-#pragma unroll
-            for (int ci = 0; ci < 3; ++ci) {
-                const float a0 = in[ky][kx][ci], a1 = in[ky][kx + 1][ci];
-                const float4* wrow = reinterpret_cast<const float4*>(sw + ((ky * 3 + kx) * 4 + ci) * 32);
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const float4 wv = wrow[q];
-                    acc0[4 * q + 0] = fmaf(a0, wv.x, acc0[4 * q + 0]); acc1[4 * q + 0] = fmaf(a1, wv.x, acc1[4 * q + 0]);
-                    acc0[4 * q + 1] = fmaf(a0, wv.y, acc0[4 * q + 1]); acc1[4 * q + 1] = fmaf(a1, wv.y, acc1[4 * q + 1]);
-                    acc0[4 * q + 2] = fmaf(a0, wv.z, acc0[4 * q + 2]); acc1[4 * q + 2] = fmaf(a1, wv.z, acc1[4 * q + 2]);
-                    acc0[4 * q + 3] = fmaf(a0, wv.w, acc0[4 * q + 3]); acc1[4 * q + 3] = fmaf(a1, wv.w, acc1[4 * q + 3]);
+            for (int kx = 0; kx < 4; ++kx) {
+                if (kx < 3 || two) {
+                    const Half4 v = *reinterpret_cast<const Half4*>(row + (long long)kx * p.sx);
+                    const float2 a = __half22float2(v.a), b = __half22float2(v.b);
+                    in[ky][kx][0] = a.x; in[ky][kx][1] = a.y; in[ky][kx][2] = b.x;
+                } else {
+                    in[ky][kx][0] = in[ky][kx][1] = in[ky][kx][2] = 0.f;
                 }
             }
-    __half* o = p.out + (((long long)img * p.out_h + y) * p.out_w + x) * p.out_c;
+        }
+        float acc0[32], acc1[32];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        Half8 h{__floats2half2_rn(lrelu(acc0[8 * q + 0], p.slope), lrelu(acc0[8 * q + 1], p.slope)),
-                __floats2half2_rn(lrelu(acc0[8 * q + 2], p.slope), lrelu(acc0[8 * q + 3], p.slope)),
-                __floats2half2_rn(lrelu(acc0[8 * q + 4], p.slope), lrelu(acc0[8 * q + 5], p.slope)),
-                __floats2half2_rn(lrelu(acc0[8 * q + 6], p.slope), lrelu(acc0[8 * q + 7], p.slope))};
-        reinterpret_cast<Half8*>(o)[q] = h;
-    }
-    if (two) {
+        for (int co = 0; co < 32; ++co) { acc0[co] = sb[co]; acc1[co] = sb[co]; }
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                for (int ci = 0; ci < 3; ++ci) {
+                    const float a0 = in[ky][kx][ci], a1 = in[ky][kx + 1][ci];
+                    const float4* wrow = reinterpret_cast<const float4*>(sw + ((ky * 3 + kx) * 4 + ci) * 32);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 wv = wrow[q];
+                        acc0[4 * q + 0] = fmaf(a0, wv.x, acc0[4 * q + 0]); acc1[4 * q + 0] = fmaf(a1, wv.x, acc1[4 * q + 0]);
+                        acc0[4 * q + 1] = fmaf(a0, wv.y, acc0[4 * q + 1]); acc1[4 * q + 1] = fmaf(a1, wv.y, acc1[4 * q + 1]);
+                        acc0[4 * q + 2] = fmaf(a0, wv.z, acc0[4 * q + 2]); acc1[4 * q + 2] = fmaf(a1, wv.z, acc1[4 * q + 2]);
+                        acc0[4 * q + 3] = fmaf(a0, wv.w, acc0[4 * q + 3]); acc1[4 * q + 3] = fmaf(a1, wv.w, acc1[4 * q + 3]);
+                    }
+                }
+        __half* o = p.out + (((long long)img * p.out_h + y) * p.out_w + x) * p.out_c;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            Half8 h{__floats2half2_rn(lrelu(acc1[8 * q + 0], p.slope), lrelu(acc1[8 * q + 1], p.slope)),
-                    __floats2half2_rn(lrelu(acc1[8 * q + 2], p.slope), lrelu(acc1[8 * q + 3], p.slope)),
-                    __floats2half2_rn(lrelu(acc1[8 * q + 4], p.slope), lrelu(acc1[8 * q + 5], p.slope)),
-                    __floats2half2_rn(lrelu(acc1[8 * q + 6], p.slope), lrelu(acc1[8 * q + 7], p.slope))};
-            reinterpret_cast<Half8*>(o + p.out_c)[q] = h;
+            Half8 h{__floats2half2_rn(lrelu(acc0[8 * q + 0], p.slope), lrelu(acc0[8 * q + 1], p.slope)),
+                    __floats2half2_rn(lrelu(acc0[8 * q + 2], p.slope), lrelu(acc0[8 * q + 3], p.slope)),
+                    __floats2half2_rn(lrelu(acc0[8 * q + 4], p.slope), lrelu(acc0[8 * q + 5], p.slope)),
+                    __floats2half2_rn(lrelu(acc0[8 * q + 6], p.slope), lrelu(acc0[8 * q + 7], p.slope))};
+            reinterpret_cast<Half8*>(o)[q] = h;
+        }
+        if (two) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                Half8 h{__floats2half2_rn(lrelu(acc1[8 * q + 0], p.slope), lrelu(acc1[8 * q + 1], p.slope)),
+                        __floats2half2_rn(lrelu(acc1[8 * q + 2], p.slope), lrelu(acc1[8 * q + 3], p.slope)),
+                        __floats2half2_rn(lrelu(acc1[8 * q + 4], p.slope), lrelu(acc1[8 * q + 5], p.slope)),
+                        __floats2half2_rn(lrelu(acc1[8 * q + 6], p.slope), lrelu(acc1[8 * q + 7], p.slope))};
+                reinterpret_cast<Half8*>(o + p.out_c)[q] = h;
+            }
         }
     }
 }
 
 void launchConvFirst(const ConvParams& p, cudaStream_t s) {
     // contract: 3x3 taps in (ky,kx) order on a plain NHWC4 view, npad == 32, EPI_STORE with cout == 32
-    dim3 grid((p.gx + 63) / 64, (p.gy + 3) / 4, p.gn);
-    conv_first_kernel<<<grid, 128, 0, s>>>(p);
+    const int itemsX = (p.gx + 63) / 64, itemsY = (p.gy + 3) / 4;
+    const int total = itemsX * itemsY * p.gn;
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    const int grid = total < sms * 4 ? total : sms * 4;
+    conv_first_kernel<<<grid, 128, 0, s>>>(p, itemsX, itemsY, total);
 }
 
 }  // namespace w2x

@@ -62,44 +62,50 @@ struct IgemmPlan {
 
 namespace {
 
-constexpr int kThreads = 192;
-constexpr int kHeaderBytes = 1024;
+constexpr int kEpiWarps = 8;                       // two warps per TMEM lane quarter, splitting the columns
+constexpr int kThreads = 64 + 32 * kEpiWarps;      // warp 0 = TMA producer, warp 1 = MMA issuer, warps 2.. = epilogue
+constexpr int kEpiThreads = 32 * kEpiWarps;
+constexpr int kHeaderBytes = 3072;                 // barriers + TMEM slot (1 KB) | bias[npad <= 512] fp32 (2 KB)
 constexpr int kPatchW = 10, kPatchH = 18;
-constexpr uint32_t kPatchBytes = kPatchW * kPatchH * 128;   // 23040
-constexpr uint32_t kPatchStride = 23 * 1024;                // 1024-aligned stage stride
 
 // header layout (byte offsets from the 1024-aligned smem base)
-constexpr uint32_t kOffFull = 0, kOffEmpty = 64, kOffTFull = 128, kOffTEmpty = 144, kOffSkip = 160, kOffW = 184, kOffSlot = 256;
+constexpr uint32_t kOffFull = 0, kOffEmpty = 64, kOffTFull = 128, kOffTEmpty = 144, kOffSkip = 160, kOffW = 184, kOffSlot = 256, kOffBias = 1024;
+
+enum EpiKind { EPI_K_DIRECT = 0, EPI_K_TMA = 1, EPI_K_TMA_SKIP = 2 };
 
 struct TileCoord {
     int img, y0, x0, n0;
 };
 
-__device__ __forceinline__ TileCoord decodeIgemm(const ConvArgs& a, int t) {
-    TileCoord c;
-    const int nt = t % a.tilesN;
-    t /= a.tilesN;
-    const int tx = t % a.tilesX;
-    t /= a.tilesX;
-    const int ty = t % a.tilesY;
-    c.img = t / a.tilesY;
-    c.y0 = ty * a.bh;
-    c.x0 = tx * a.bw;
-    c.n0 = nt * a.bn;
-    return c;
-}
-
-__device__ __forceinline__ TileCoord decodePatch(const ConvArgs& a, int t, int n0) {
-    TileCoord c;
-    const int tx = t % a.tilesX;
-    t /= a.tilesX;
-    const int ty = t % a.tilesY;
-    c.img = t / a.tilesY;
-    c.y0 = ty * a.bh;
-    c.x0 = tx * a.bw;
-    c.n0 = n0;
-    return c;
-}
+// Walks this CTA's tile sequence t = first, first + step, ... without divisions in the loop.
+struct TileWalker {
+    int tn, tx, ty, img;          // current tile indices
+    int sn, sx, sy, simg;         // step decomposition
+    int tilesN, tilesX, tilesY;
+    __device__ __forceinline__ void init(int first, int step, int tilesN_, int tilesX_, int tilesY_) {
+        tilesN = tilesN_; tilesX = tilesX_; tilesY = tilesY_;
+        int t = first;
+        tn = t % tilesN; t /= tilesN;
+        tx = t % tilesX; t /= tilesX;
+        ty = t % tilesY; img = t / tilesY;
+        t = step;
+        sn = t % tilesN; t /= tilesN;
+        sx = t % tilesX; t /= tilesX;
+        sy = t % tilesY; simg = t / tilesY;
+    }
+    __device__ __forceinline__ void next() {
+        tn += sn;
+        int c = tn >= tilesN; tn -= c * tilesN;
+        tx += sx + c;
+        c = tx >= tilesX; tx -= c * tilesX;
+        ty += sy + c;
+        c = ty >= tilesY; ty -= c * tilesY;
+        img += simg + c;
+    }
+    __device__ __forceinline__ TileCoord coord(int bh, int bw, int bn, int nBase) const {
+        return TileCoord{img, ty * bh, tx * bw, nBase + tn * bn};
+    }
+};
 
 // coordinates of 64-channel sub-tile `s` of an N tile in the output / skip tensor-map views
 __device__ __forceinline__ void subTileCoords(const ConvArgs& a, const TileCoord& tc, int s, int& c0, int& cz) {
@@ -114,21 +120,34 @@ __device__ __forceinline__ void subTileCoords(const ConvArgs& a, const TileCoord
     }
 }
 
-// ---- epilogue shared by both kernels (executed by warps 2..5 = 128 threads) ------------------------------------------
-template <class CoordOf>
-__device__ __forceinline__ void epilogueWarps(const ConvArgs& a, uint32_t base, uint32_t tmemBase, int nMine, CoordOf coordOf) {
+// ---- epilogue shared by both kernels (warps 2..9 = 256 threads) --------------------------------------------------------
+// Warp w may only touch TMEM lanes 32*(w%4)..+31; the two warps of a lane quarter split the accumulator columns.
+template <int kEpi>
+__device__ __forceinline__ void epilogueWarps(const ConvArgs& a, uint32_t base, uint32_t tmemBase, int nMine, int first, int step, int nBase) {
+    constexpr bool kTma = kEpi != EPI_K_DIRECT;
+    constexpr bool kSkip = kEpi == EPI_K_TMA_SKIP;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
     const bool leader = threadIdx.x == 64;
     const int m = quarter * 32 + lane;
     const int yy = m >> a.bwShift, xx = m & (a.bw - 1);
     const uint32_t barTFull = base + kOffTFull, barTEmpty = base + kOffTEmpty, barSkip = base + kOffSkip;
     const uint32_t staging = base + kHeaderBytes;
     const uint32_t bufBytes = (uint32_t)a.nsub * 16384u;
+    const uint32_t biasS = base + kOffBias;
     const int skipHalf = a.p.skip_off >> 1;
+    const int colsPerWarp = a.bn >= 64 ? a.bn >> 1 : a.bn;   // bn = 16 heads: only the first warp of each quarter works
+    const int colBegin = a.bn >= 64 ? half * colsPerWarp : 0;
+    const bool active = a.bn >= 64 || half == 0;
 
+    TileWalker w;
+    w.init(first, step, a.tilesN, a.tilesX, a.tilesY);
+    TileWalker ws = w;  // lookahead walker for skip-tile prefetch (leader only)
+    int ksNext = 0;
     auto issueSkip = [&](int k) {
-        const TileCoord tc = coordOf(k);
+        // ws points at tile k
+        const TileCoord tc = ws.coord(a.bh, a.bw, a.bn, nBase);
         const int b = k % a.nbuf;
         mbarExpectTx(barSkip + 8u * b, bufBytes);
         for (int s = 0; s < a.nsub; ++s) {
@@ -136,77 +155,98 @@ __device__ __forceinline__ void epilogueWarps(const ConvArgs& a, uint32_t base, 
             subTileCoords(a, tc, s, c0, cz);
             tmaLoad5d(staging + b * bufBytes + s * 16384u, &a.tmSkip, barSkip + 8u * b, c0, tc.x0 + skipHalf, cz, tc.y0 + skipHalf, tc.img);
         }
+        ws.next();
+        ksNext = k + 1;
     };
-    if (a.useTma && a.hasSkip && leader) {
+    if (kSkip && leader) {
         for (int k = 0; k < a.nbuf - 1 && k < nMine; ++k) issueSkip(k);
     }
 
     int acc = 0;
     uint32_t accPhase = 0;
-    for (int k = 0; k < nMine; ++k) {
-        const TileCoord tc = coordOf(k);
+    for (int k = 0; k < nMine; ++k, w.next()) {
+        const TileCoord tc = w.coord(a.bh, a.bw, a.bn, nBase);
         const int b = k % a.nbuf;
         const uint32_t stg = staging + b * bufBytes;
-        if (a.useTma && !a.hasSkip) {
+        if (kTma && !kSkip) {
             if (leader) bulkWaitRead(a.nbuf - 1);  // staging buffer b is no longer being read by the store of tile k - nbuf
-            namedBarSync(1, 128);
+            namedBarSync(1, kEpiThreads);
         }
+        // image head: fetch this pixel's skip value (z1 crop) BEFORE blocking on the accumulator, so its latency is hidden
+        Half4 preSkip{};
+        const int py = tc.y0 + yy, px = tc.x0 + xx;
+        const bool pvalid = py < a.p.gy && px < a.p.gx;
+        if (!kTma && a.p.mode == EPI_FINAL && active && pvalid)
+            preSkip = *reinterpret_cast<const Half4*>(a.p.skip + (((long long)tc.img * a.p.skip_h + py + a.p.skip_off) * a.p.skip_w + px + a.p.skip_off) * a.p.skip_c);
         mbarWait(barTFull + 8u * acc, accPhase);
         tcFenceAfter();
-        if (a.useTma && a.hasSkip) mbarWait(barSkip + 8u * b, (uint32_t)(k / a.nbuf) & 1u);
-        const int y = tc.y0 + yy, x = tc.x0 + xx;
-        const bool valid = y < a.p.gy && x < a.p.gx;
+        if (kSkip) mbarWait(barSkip + 8u * b, (uint32_t)(k / a.nbuf) & 1u);
         const uint32_t taddr = tmemBase + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * a.bn);
         uint32_t r[32];
-        if (a.bn >= 32) {
-            for (int c0 = 0; c0 < a.bn; c0 += 32) {
+        if (kTma) {
+            for (int c0 = colBegin; c0 < colBegin + colsPerWarp; c0 += 32) {
                 tmemLd32(taddr + (uint32_t)c0, r);
                 tmemLdWait();
-                if (a.useTma) {
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const int j0 = c0 + 8 * q;
-                        const uint32_t addr = stg + (uint32_t)(j0 >> 6) * 16384u + (uint32_t)m * 128u + ((uint32_t)(((j0 & 63) >> 3) ^ (m & 7)) << 4);
-                        float v[8];
+                for (int q = 0; q < 4; ++q) {
+                    const int j0 = c0 + 8 * q;
+                    const uint32_t addr = stg + (uint32_t)(j0 >> 6) * 16384u + (uint32_t)m * 128u + ((uint32_t)(((j0 & 63) >> 3) ^ (m & 7)) << 4);
+                    const uint4 b0 = ldsV4(biasS + (uint32_t)(tc.n0 + j0) * 4u), b1 = ldsV4(biasS + (uint32_t)(tc.n0 + j0 + 4) * 4u);
+                    const float bias[8] = {__uint_as_float(b0.x), __uint_as_float(b0.y), __uint_as_float(b0.z), __uint_as_float(b0.w),
+                                           __uint_as_float(b1.x), __uint_as_float(b1.y), __uint_as_float(b1.z), __uint_as_float(b1.w)};
+                    float v[8];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) v[i] = lrelu(__uint_as_float(r[8 * q + i]) + __ldg(a.p.bias + tc.n0 + j0 + i), a.p.slope);
-                        if (a.hasSkip) {
-                            const uint4 sv = ldsV4(addr);
-                            const __half2* sh = reinterpret_cast<const __half2*>(&sv);
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const float2 f = __half22float2(sh[i]);
-                                v[2 * i] += f.x;
-                                v[2 * i + 1] += f.y;
-                            }
-                        }
-                        uint4 o;
-                        __half2* oh = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) oh[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
-                        stsV4(addr, o);
+                    for (int i = 0; i < 8; ++i) {
+                        const float t = __uint_as_float(r[8 * q + i]) + bias[i];
+                        v[i] = fmaxf(t, t * a.p.slope);  // LeakyReLU for 0 < slope <= 1
                     }
-                } else if (valid) {
+                    if (kSkip) {
+                        const uint4 sv = ldsV4(addr);
+                        const __half2* sh = reinterpret_cast<const __half2*>(&sv);
 #pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        conv_epilogue8(a.p, tc.img, y, x, tc.n0 + c0 + 8 * q, reinterpret_cast<const float*>(r) + 8 * q);
+                        for (int i = 0; i < 4; ++i) {
+                            const float2 f = __half22float2(sh[i]);
+                            v[2 * i] += f.x;
+                            v[2 * i + 1] += f.y;
+                        }
+                    }
+                    uint4 o;
+                    __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) oh[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+                    stsV4(addr, o);
                 }
             }
-        } else {
-            tmemLd16(taddr, r);
-            tmemLdWait();
-            if (valid) {
+        } else if (active) {
+            const int y = py, x = px;
+            const bool valid = pvalid;
+            const Half4* pre = a.p.mode == EPI_FINAL ? &preSkip : nullptr;
+            if (a.bn >= 32) {
+                for (int c0 = colBegin; c0 < colBegin + colsPerWarp; c0 += 32) {
+                    tmemLd32(taddr + (uint32_t)c0, r);
+                    tmemLdWait();
+                    if (valid) {
 #pragma unroll
-                for (int q = 0; q < 2; ++q) conv_epilogue8(a.p, tc.img, y, x, tc.n0 + 8 * q, reinterpret_cast<const float*>(r) + 8 * q);
+                        for (int q = 0; q < 4; ++q)
+                            conv_epilogue8(a.p, tc.img, y, x, tc.n0 + c0 + 8 * q, reinterpret_cast<const float*>(r) + 8 * q);
+                    }
+                }
+            } else {
+                tmemLd16(taddr, r);
+                tmemLdWait();
+                if (valid) {
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) conv_epilogue8(a.p, tc.img, y, x, tc.n0 + 8 * q, reinterpret_cast<const float*>(r) + 8 * q, pre);
+                }
             }
         }
         tcFenceBefore();
         __syncwarp();
         if (lane == 0) mbarArrive(barTEmpty + 8u * acc);  // accumulator buffer may be overwritten by the next-but-one tile
         if (++acc == 2) { acc = 0; accPhase ^= 1u; }
-        if (a.useTma) {
+        if (kTma) {
             fenceProxyAsync();
-            namedBarSync(1, 128);
+            namedBarSync(1, kEpiThreads);
             if (leader) {
                 for (int s = 0; s < a.nsub; ++s) {
                     int c0, cz;
@@ -214,7 +254,7 @@ __device__ __forceinline__ void epilogueWarps(const ConvArgs& a, uint32_t base, 
                     tmaStore5d(&a.tmOut, stg + s * 16384u, c0, tc.x0, cz, tc.y0, tc.img);
                 }
                 bulkCommit();
-                if (a.hasSkip) {
+                if (kSkip) {
                     const int kn = k + a.nbuf - 1;
                     if (kn < nMine) {
                         bulkWaitRead(1);  // the store of tile k-1 (same buffer as tile kn) has finished reading smem
@@ -224,7 +264,7 @@ __device__ __forceinline__ void epilogueWarps(const ConvArgs& a, uint32_t base, 
             }
         }
     }
-    if (a.useTma && leader) bulkWaitAll();
+    if (kTma && leader) bulkWaitAll();
 }
 
 __device__ __forceinline__ void setupCommon(const ConvArgs& a, uint32_t base, uint8_t* sm, int warp) {
@@ -235,7 +275,7 @@ __device__ __forceinline__ void setupCommon(const ConvArgs& a, uint32_t base, ui
         }
         for (int i = 0; i < 2; ++i) {
             mbarInit(base + kOffTFull + 8u * i, 1);
-            mbarInit(base + kOffTEmpty + 8u * i, 4);
+            mbarInit(base + kOffTEmpty + 8u * i, kEpiWarps);
         }
         for (int i = 0; i < 3; ++i) mbarInit(base + kOffSkip + 8u * i, 1);
         mbarInit(base + kOffW, 1);
@@ -245,6 +285,8 @@ __device__ __forceinline__ void setupCommon(const ConvArgs& a, uint32_t base, ui
         if (a.useTma) tmaPrefetchDesc(&a.tmOut);
         if (a.hasSkip) tmaPrefetchDesc(&a.tmSkip);
     }
+    float* biasS = reinterpret_cast<float*>(sm + kOffBias);
+    for (int i = threadIdx.x; i < a.p.npad && i < 512; i += blockDim.x) biasS[i] = a.p.bias[i];
     if (warp == 1) tmemAlloc(smemU32(sm + kOffSlot), a.tmemCols);
     tcFenceBefore();
     __syncthreads();
@@ -254,6 +296,7 @@ __device__ __forceinline__ void setupCommon(const ConvArgs& a, uint32_t base, ui
 // ======================================================================================================================
 // generic implicit GEMM (per-tap A loads)
 // ======================================================================================================================
+template <int kEpi>
 __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constant__ ConvArgs a) {
     extern __shared__ uint8_t smemRaw[];
     const uint32_t rawAddr = smemU32(smemRaw);
@@ -265,14 +308,17 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
     const uint32_t stage0 = base + kHeaderBytes + a.stagingBytes;
     const uint32_t stageBytes = a.bytesA + a.bytesB;
     const uint32_t barFull = base + kOffFull, barEmpty = base + kOffEmpty, barTFull = base + kOffTFull, barTEmpty = base + kOffTEmpty;
-    const int nMine = a.totalTiles > (int)blockIdx.x ? (a.totalTiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int first = blockIdx.x, step = gridDim.x;
+    const int nMine = a.totalTiles > first ? (a.totalTiles - 1 - first) / step + 1 : 0;
 
     if (warp == 0) {
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int k = 0; k < nMine; ++k) {
-                const TileCoord tc = decodeIgemm(a, blockIdx.x + k * gridDim.x);
+            TileWalker w;
+            w.init(first, step, a.tilesN, a.tilesX, a.tilesY);
+            for (int k = 0; k < nMine; ++k, w.next()) {
+                const TileCoord tc = w.coord(a.bh, a.bw, a.bn, 0);
                 for (int tap = 0; tap < a.p.ntaps; ++tap) {
                     const ConvTap tp = a.p.tap[tap];
                     for (int cc = 0; cc < a.cchunks; ++cc) {
@@ -288,30 +334,32 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            int stage = 0, acc = 0;
-            uint32_t phase = 0, accPhase = 0;
-            const int kSteps = a.kc / 16;
-            for (int k = 0; k < nMine; ++k) {
-                mbarWait(barTEmpty + 8u * acc, accPhase ^ 1u);
+        // whole warp converged; one elected lane issues the MMAs and commits (keeps the issue loop on the uniform datapath)
+        int stage = 0, acc = 0;
+        uint32_t phase = 0, accPhase = 0;
+        const int kSteps = a.kc / 16;
+        for (int k = 0; k < nMine; ++k) {
+            mbarWait(barTEmpty + 8u * acc, accPhase ^ 1u);
+            tcFenceAfter();
+            const uint32_t tmemD = tmemBase + (uint32_t)(acc * a.bn);
+            for (int kb = 0; kb < a.kblocks; ++kb) {
+                mbarWait(barFull + 8u * stage, phase);
                 tcFenceAfter();
-                const uint32_t tmemD = tmemBase + (uint32_t)(acc * a.bn);
-                for (int kb = 0; kb < a.kblocks; ++kb) {
-                    mbarWait(barFull + 8u * stage, phase);
-                    tcFenceAfter();
-                    const uint32_t sA = stage0 + stage * stageBytes;
-                    const uint32_t sB = sA + a.bytesA;
+                if (electOne()) {
+                    const uint32_t aLo = descLo(stage0 + stage * stageBytes), bLo = descLo(stage0 + stage * stageBytes + a.bytesA);
                     for (int ks = 0; ks < kSteps; ++ks)
-                        umma(tmemD, makeDesc(sA + 32u * ks, a.descHiA), makeDesc(sB + 32u * ks, a.descHiB), a.idesc, (kb | ks) != 0 ? 1u : 0u);
+                        ummaLoHi(tmemD, aLo + 2u * ks, a.descHiA, bLo + 2u * ks, a.descHiB, a.idesc, (kb | ks) != 0 ? 1u : 0u);
                     tcCommit(barEmpty + 8u * stage);
-                    if (++stage == a.stages) { stage = 0; phase ^= 1u; }
                 }
-                tcCommit(barTFull + 8u * acc);
-                if (++acc == 2) { acc = 0; accPhase ^= 1u; }
+                __syncwarp();
+                if (++stage == a.stages) { stage = 0; phase ^= 1u; }
             }
+            if (electOne()) tcCommit(barTFull + 8u * acc);
+            __syncwarp();
+            if (++acc == 2) { acc = 0; accPhase ^= 1u; }
         }
     } else {
-        epilogueWarps(a, base, tmemBase, nMine, [&](int k) { return decodeIgemm(a, blockIdx.x + k * gridDim.x); });
+        epilogueWarps<kEpi>(a, base, tmemBase, nMine, first, step, 0);
     }
 
     tcFenceBefore();
@@ -325,6 +373,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
 // ======================================================================================================================
 // 3x3 convolution from one input patch per tile, weights resident in shared memory
 // ======================================================================================================================
+template <int kEpi, int kKC>
 __global__ void __launch_bounds__(kThreads, 1) conv3x3_patch_kernel(const __grid_constant__ ConvArgs a) {
     extern __shared__ uint8_t smemRaw[];
     const uint32_t rawAddr = smemU32(smemRaw);
@@ -341,7 +390,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_patch_kernel(const __grid
     const int slice = blockIdx.x % a.nSplit, first = blockIdx.x / a.nSplit, step = gridDim.x / a.nSplit;
     const int n0 = slice * a.bn;
     const int nMine = a.totalTiles > first ? (a.totalTiles - 1 - first) / step + 1 : 0;
-    const uint32_t tapBytes = (uint32_t)a.bn * 128u;  // one (tap, 64-channel chunk) block of B: [bn rows][64 k]
+    const uint32_t rowBytes = (uint32_t)a.kc * 2u;     // one pixel / one weight row of a K chunk: 128 B (kc=64) or 64 B (kc=32)
+    const uint32_t tapBytes = (uint32_t)a.bn * rowBytes;  // one (tap, K chunk) block of B: [bn rows][kc]
 
     if (warp == 0) {
         if (lane == 0) {
@@ -349,50 +399,59 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_patch_kernel(const __grid
             mbarExpectTx(barW, a.wBytes);
             for (int tap = 0; tap < 9; ++tap)
                 for (int cc = 0; cc < a.cchunks; ++cc)
-                    tmaLoad2d(wBase + (uint32_t)(tap * a.cchunks + cc) * tapBytes, &a.tmB, barW, tap * a.p.cin + cc * 64, n0);
+                    tmaLoad2d(wBase + (uint32_t)(tap * a.cchunks + cc) * tapBytes, &a.tmB, barW, tap * a.p.cin + cc * a.kc, n0);
             int stage = 0;
             uint32_t phase = 0;
-            for (int k = 0; k < nMine; ++k) {
-                const TileCoord tc = decodePatch(a, first + k * step, n0);
+            TileWalker w;
+            w.init(first, step, 1, a.tilesX, a.tilesY);
+            for (int k = 0; k < nMine; ++k, w.next()) {
+                const TileCoord tc = w.coord(a.bh, a.bw, a.bn, n0);
                 for (int cc = 0; cc < a.cchunks; ++cc) {
                     mbarWait(barEmpty + 8u * stage, phase ^ 1u);
                     const uint32_t full = barFull + 8u * stage;
-                    mbarExpectTx(full, kPatchBytes);
-                    tmaLoad5d(stage0 + stage * kPatchStride, &a.tmA, full, cc * 64, tc.x0, 0, tc.y0, tc.img);
+                    mbarExpectTx(full, a.bytesA);
+                    tmaLoad5d(stage0 + stage * a.stageStride, &a.tmA, full, cc * a.kc, tc.x0, 0, tc.y0, tc.img);
                     if (++stage == a.stages) { stage = 0; phase ^= 1u; }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            int stage = 0, acc = 0;
-            uint32_t phase = 0, accPhase = 0;
-            mbarWait(barW, 0);
-            for (int k = 0; k < nMine; ++k) {
-                mbarWait(barTEmpty + 8u * acc, accPhase ^ 1u);
+        int stage = 0, acc = 0;
+        uint32_t phase = 0, accPhase = 0;
+        mbarWait(barW, 0);
+        const uint32_t bTapStep = ((uint32_t)a.cchunks * tapBytes) >> 4;  // descriptor-lo distance between consecutive taps of B
+        for (int k = 0; k < nMine; ++k) {
+            mbarWait(barTEmpty + 8u * acc, accPhase ^ 1u);
+            tcFenceAfter();
+            const uint32_t tmemD = tmemBase + (uint32_t)(acc * a.bn);
+            for (int cc = 0; cc < a.cchunks; ++cc) {
+                mbarWait(barFull + 8u * stage, phase);
                 tcFenceAfter();
-                const uint32_t tmemD = tmemBase + (uint32_t)(acc * a.bn);
-                for (int cc = 0; cc < a.cchunks; ++cc) {
-                    mbarWait(barFull + 8u * stage, phase);
-                    tcFenceAfter();
-                    const uint32_t sP = stage0 + stage * kPatchStride;
+                if (electOne()) {
+                    const uint32_t aLo = descLo(stage0 + stage * a.stageStride);
+                    uint32_t bLo = descLo(wBase + (uint32_t)cc * tapBytes);
 #pragma unroll
                     for (int tap = 0; tap < 9; ++tap) {
-                        const uint32_t sA = sP + (uint32_t)((tap / 3) * kPatchW + (tap % 3)) * 128u;  // shifted view of the patch
-                        const uint32_t sB = wBase + (uint32_t)(tap * a.cchunks + cc) * tapBytes;
+                        // shifted view of the patch: whole pixel rows (kRowBytes each) into the swizzled tile
+                        constexpr uint32_t kRowBytes = kKC * 2;
+                        const uint32_t aTap = aLo + (uint32_t)(((tap / 3) * kPatchW + (tap % 3)) * kRowBytes >> 4);
 #pragma unroll
-                        for (int ks = 0; ks < 4; ++ks)
-                            umma(tmemD, makeDesc(sA + 32u * ks, a.descHiA), makeDesc(sB + 32u * ks, a.descHiB), a.idesc, (cc | tap | ks) != 0 ? 1u : 0u);
+                        for (int ks = 0; ks < kKC / 16; ++ks)
+                            ummaLoHi(tmemD, aTap + 2u * ks, a.descHiA, bLo + 2u * ks, a.descHiB, a.idesc, (cc | tap | ks) != 0 ? 1u : 0u);
+                        bLo += bTapStep;
                     }
                     tcCommit(barEmpty + 8u * stage);
-                    if (++stage == a.stages) { stage = 0; phase ^= 1u; }
                 }
-                tcCommit(barTFull + 8u * acc);
-                if (++acc == 2) { acc = 0; accPhase ^= 1u; }
+                __syncwarp();
+                if (++stage == a.stages) { stage = 0; phase ^= 1u; }
             }
+            if (electOne()) tcCommit(barTFull + 8u * acc);
+            __syncwarp();
+            if (++acc == 2) { acc = 0; accPhase ^= 1u; }
         }
     } else {
-        epilogueWarps(a, base, tmemBase, nMine, [&](int k) { return decodePatch(a, first + k * step, n0); });
+        // tilesN == 1 for this kernel: the walker's N index stays 0 and the slice offset comes in as nBase
+        epilogueWarps<kEpi>(a, base, tmemBase, nMine, first, step, n0);
     }
 
     tcFenceBefore();
@@ -565,7 +624,7 @@ void encodeOutMaps(ConvArgs& a) {
 }
 
 bool wantsPatchKernel(const ConvParams& p) {
-    if (!p.is3x3 || p.cin % 64 != 0 || p.cin > 128) return false;
+    if (!p.is3x3 || !(p.cin == 32 || p.cin == 64 || p.cin == 128)) return false;
     if (!(p.npad % 64 == 0 || p.npad == 16)) return false;
     if (p.npad % 64 == 0 && !tmaEpilogueOk(p)) return false;
     return true;
@@ -575,10 +634,11 @@ void planPatch(IgemmPlan* plan) {
     ConvArgs& a = plan->args;
     const ConvParams& p = a.p;
     plan->patch = true;
-    a.kc = 64;
+    a.kc = p.cin % 64 == 0 ? 64 : 32;
+    const bool sw128 = a.kc == 64;
     a.bn = p.npad % 64 == 0 ? 64 : 16;
     a.nSplit = p.npad / a.bn;
-    a.cchunks = p.cin / 64;
+    a.cchunks = p.cin / a.kc;
     a.kblocks = a.cchunks;
     a.bw = 8; a.bh = 16; a.bwShift = 3;
     a.tilesX = (p.gx + 7) / 8;
@@ -590,32 +650,33 @@ void planPatch(IgemmPlan* plan) {
     a.nsub = 1;
     a.nbuf = a.useTma ? 2 : 1;
     a.stagingBytes = a.useTma ? a.nbuf * 16384u : 0u;
-    a.wBytes = 9u * a.cchunks * a.bn * 128u;
-    a.stageStride = kPatchStride;
+    a.wBytes = 9u * a.cchunks * a.bn * a.kc * 2u;
+    a.bytesA = (uint32_t)(kPatchW * kPatchH) * a.kc * 2u;     // 23040 (kc=64) / 11520 (kc=32)
+    a.stageStride = (a.bytesA + 1023u) & ~1023u;
     const size_t fixed = 1024 + kHeaderBytes + a.stagingBytes + a.wBytes;
-    if (fixed + 2 * (size_t)kPatchStride > kSmemLimit) throw Error("conv3x3 patch kernel: weights do not fit in shared memory");
-    a.stages = (int)std::min<size_t>(8, (kSmemLimit - fixed) / kPatchStride);
+    if (fixed + 2 * (size_t)a.stageStride > kSmemLimit) throw Error("conv3x3 patch kernel: weights do not fit in shared memory");
+    a.stages = (int)std::min<size_t>(8, (kSmemLimit - fixed) / a.stageStride);
     uint32_t cols = 32;
     while (cols < (uint32_t)(2 * a.bn)) cols *= 2;
     a.tmemCols = cols;
     a.idesc = instrDescF16(128, a.bn);
-    a.descHiA = (1280u >> 4) | (1u << 14) | (2u << 29);  // 8-pixel row groups are one patch row (10 pixels x 128 B) apart
-    a.descHiB = (1024u >> 4) | (1u << 14) | (2u << 29);
-    a.bytesA = kPatchBytes;
+    const uint32_t rowBytes = a.kc * 2u, layout = sw128 ? 2u : 4u;
+    a.descHiA = ((kPatchW * rowBytes) >> 4) | (1u << 14) | (layout << 29);  // 8-pixel row groups are one patch row (10 pixels) apart
+    a.descHiB = ((8u * rowBytes) >> 4) | (1u << 14) | (layout << 29);
     a.bytesB = 0;
     {
         const long long dims[5] = {p.dimc, p.dimx, p.dimz, p.dimy, p.gn};
         const long long st[4] = {p.sx, p.sz, p.sy, p.sn};
-        const int box[5] = {64, kPatchW, 1, kPatchH, 1};
-        encode5d(&a.tmA, p.in, dims, st, box, true, "patch");
+        const int box[5] = {a.kc, kPatchW, 1, kPatchH, 1};
+        encode5d(&a.tmA, p.in, dims, st, box, sw128, "patch");
     }
-    encodeWeights(&a.tmB, p, 64, a.bn, true);
+    encodeWeights(&a.tmB, p, a.kc, a.bn, sw128);
     if (a.useTma) encodeOutMaps(a);
     const int sms = numSMs();
     int grid = std::min(sms, a.totalTiles * a.nSplit);
     grid = std::max(a.nSplit, grid / a.nSplit * a.nSplit);
     plan->grid = grid;
-    plan->smem = fixed + (size_t)a.stages * kPatchStride;
+    plan->smem = fixed + (size_t)a.stages * a.stageStride;
 }
 
 void planIgemm(IgemmPlan* plan) {
@@ -699,8 +760,13 @@ IgemmPlan* igemmCreatePlan(const ConvParams& p) {
         else planIgemm(plan);
         static bool attrSet = false;
         if (!attrSet) {
-            checkCuda(cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
-            checkCuda(cudaFuncSetAttribute(conv3x3_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+            checkCuda(cudaFuncSetAttribute(igemm_kernel<EPI_K_DIRECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+            checkCuda(cudaFuncSetAttribute(igemm_kernel<EPI_K_TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+            checkCuda(cudaFuncSetAttribute(igemm_kernel<EPI_K_TMA_SKIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+            checkCuda(cudaFuncSetAttribute(conv3x3_patch_kernel<EPI_K_DIRECT, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+            checkCuda(cudaFuncSetAttribute(conv3x3_patch_kernel<EPI_K_TMA, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+            checkCuda(cudaFuncSetAttribute(conv3x3_patch_kernel<EPI_K_DIRECT, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+            checkCuda(cudaFuncSetAttribute(conv3x3_patch_kernel<EPI_K_TMA, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
             attrSet = true;
         }
     } catch (...) {
@@ -730,8 +796,19 @@ void igemmLaunch(const IgemmPlan* plan, cudaStream_t s, __half* outOverride) {
         local.p.out = outOverride;
         a = &local;
     }
-    if (plan->patch) conv3x3_patch_kernel<<<plan->grid, kThreads, plan->smem, s>>>(*a);
-    else igemm_kernel<<<plan->grid, kThreads, plan->smem, s>>>(*a);
+    if (plan->patch) {
+        if (a->kc == 64) {
+            if (a->useTma) conv3x3_patch_kernel<EPI_K_TMA, 64><<<plan->grid, kThreads, plan->smem, s>>>(*a);
+            else conv3x3_patch_kernel<EPI_K_DIRECT, 64><<<plan->grid, kThreads, plan->smem, s>>>(*a);
+        } else {
+            if (a->useTma) conv3x3_patch_kernel<EPI_K_TMA, 32><<<plan->grid, kThreads, plan->smem, s>>>(*a);
+            else conv3x3_patch_kernel<EPI_K_DIRECT, 32><<<plan->grid, kThreads, plan->smem, s>>>(*a);
+        }
+    } else {
+        if (a->hasSkip) igemm_kernel<EPI_K_TMA_SKIP><<<plan->grid, kThreads, plan->smem, s>>>(*a);
+        else if (a->useTma) igemm_kernel<EPI_K_TMA><<<plan->grid, kThreads, plan->smem, s>>>(*a);
+        else igemm_kernel<EPI_K_DIRECT><<<plan->grid, kThreads, plan->smem, s>>>(*a);
+    }
 }
 
 

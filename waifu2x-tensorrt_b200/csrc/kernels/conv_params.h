@@ -56,7 +56,7 @@ struct alignas(8) Half4 { __half2 a, b; };
 
 // Epilogue for 8 consecutive GEMM columns [j0, j0+8) of pixel (img, y, x); v = raw fp32 accumulators.
 // The caller guarantees y < gy, x < gx, img < gn and j0 % 8 == 0.
-__device__ __forceinline__ void conv_epilogue8(const ConvParams& p, int img, int y, int x, int j0, const float* v) {
+__device__ __forceinline__ void conv_epilogue8(const ConvParams& p, int img, int y, int x, int j0, const float* v, const Half4* preSkip = nullptr) {
     float r[8];
     if (p.mode == EPI_STORE) {
         if (j0 >= p.cout) return;
@@ -111,7 +111,7 @@ __device__ __forceinline__ void conv_epilogue8(const ConvParams& p, int img, int
         }
     } else {  // EPI_FINAL
         if (j0 != 0) return;
-        const Half4 sv = *reinterpret_cast<const Half4*>(
+        const Half4 sv = preSkip ? *preSkip : *reinterpret_cast<const Half4*>(
             p.skip + (((long long)img * p.skip_h + y + p.skip_off) * p.skip_w + x + p.skip_off) * p.skip_c);
         const float2 s0 = __half22float2(sv.a), s1 = __half22float2(sv.b);
         r[0] = fminf(fmaxf(v[0] + __ldg(p.bias + 0) + s0.x, 0.f), 1.f);

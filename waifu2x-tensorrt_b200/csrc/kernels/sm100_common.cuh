@@ -98,6 +98,33 @@ __device__ __forceinline__ void umma(uint32_t tmemD, uint64_t descA, uint64_t de
         "l"(descA), "l"(descB), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// same, with the descriptors given as (lo, hi) 32-bit halves so the issue loop only does 32-bit adds on `lo`
+__device__ __forceinline__ void ummaLoHi(uint32_t tmemD, uint32_t aLo, uint32_t aHi, uint32_t bLo, uint32_t bHi, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+        "}" ::"r"(tmemD),
+        "r"(aLo), "r"(aHi), "r"(bLo), "r"(bHi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// one elected lane of a fully converged warp
+__device__ __forceinline__ bool electOne() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ uint32_t descLo(uint32_t smemAddr) { return ((smemAddr >> 4) & 0x3FFFu) | (1u << 16); }
 __device__ __forceinline__ void tmemLd32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
