@@ -328,13 +328,25 @@ void Engine::buildPlan() {
         E.isFinal = fin;
         if (useDirect) E.impl = IMPL_DIRECT;
         else if (L.kind == L_CONV3 && L.cin == 4 && L.npad == 32 && p.mode == EPI_STORE) E.impl = IMPL_FIRST;
-        else if (igemmSupported(p)) { E.impl = IMPL_IGEMM; E.plan = igemmCreatePlan(p); }
+        else if (igemmSupported(p)) {
+            E.impl = IMPL_IGEMM;
+            if (L.se_r) {
+                // fused squeeze: the conv epilogue writes deterministic per-CTA partial sums (<= 4 slots per CTA)
+                E.sePartialBytes = (size_t)batch * 148 * 8 * L.npad * 4;
+                E.sePartial = (float*)dalloc(E.sePartialBytes);
+                E.p.se_sum = E.sePartial;
+            }
+            E.plan = igemmCreatePlan(E.p);
+            if (L.se_r) { E.seBlocks = igemmSeSlots(E.plan); E.seFused = true; E.sePartialBytes = (size_t)batch * E.seBlocks * L.npad * 4; }
+        }
         else throw Error("no kernel for layer " + L.name);
         if (L.se_r) {
             E.seR = (int)L.se_r;
             E.seW1 = upload(L.se_w1); E.seB1 = upload(L.se_b1); E.seW2 = upload(L.se_w2); E.seB2 = upload(L.se_b2);
-            E.seBlocks = 32;
-            E.sePartial = (float*)dalloc((size_t)batch * E.seBlocks * L.cout * 4);
+            if (!E.seFused) {
+                E.seBlocks = 32;
+                E.sePartial = (float*)dalloc((size_t)batch * E.seBlocks * L.cout * 4);
+            }
             E.seScale = (float*)dalloc((size_t)batch * L.cout * 4);
         }
         layers.push_back(E);
@@ -413,6 +425,7 @@ double Engine::flopsPerTile() const {
 void Engine::runModel(cudaStream_t s, __half* finalOut) {
     for (auto& L : layers) {
         __half* outp = (L.isFinal && finalOut) ? finalOut : L.p.out;
+        if (L.seFused) W2X_CUDA(cudaMemsetAsync(L.sePartial, 0, L.sePartialBytes, s));
         if (L.impl == IMPL_IGEMM) {
             igemmLaunch(L.plan, s, outp);
         } else {
@@ -423,10 +436,10 @@ void Engine::runModel(cudaStream_t s, __half* finalOut) {
         }
         ++launches;
         if (L.seR) {
-            launchSeSqueeze(L.p.out, L.p.gn, L.p.out_h, L.p.out_w, L.p.out_c, L.sePartial, L.seBlocks, s);
+            if (!L.seFused) { launchSeSqueeze(L.p.out, L.p.gn, L.p.out_h, L.p.out_w, L.p.out_c, L.sePartial, L.seBlocks, s); ++launches; }
             launchSeExcite(L.sePartial, L.seBlocks, L.p.gn, L.p.out_c, L.seR, L.p.out_h * L.p.out_w, L.seW1, L.seB1, L.seW2, L.seB2, L.seScale, s);
             launchSeScale(L.p.out, L.p.gn, L.p.out_h, L.p.out_w, L.p.out_c, L.seScale, s);
-            launches += 3;
+            launches += 2;
         }
     }
     W2X_CUDA(cudaGetLastError());
@@ -721,11 +734,12 @@ int Engine::profileLayers(int repeats, char (*names)[48], float* ms, double* flo
             if (i >= cap) break;
             W2X_CUDA(cudaEventRecord(e0, stream));
             for (int r = 0; r < repeats; ++r) {
+                if (L.seFused) W2X_CUDA(cudaMemsetAsync(L.sePartial, 0, L.sePartialBytes, stream));
                 if (L.impl == IMPL_IGEMM) igemmLaunch(L.plan, stream, nullptr);
                 else if (L.impl == IMPL_FIRST) launchConvFirst(L.p, stream);
                 else launchConvDirect(L.p, stream);
                 if (L.seR) {
-                    launchSeSqueeze(L.p.out, L.p.gn, L.p.out_h, L.p.out_w, L.p.out_c, L.sePartial, L.seBlocks, stream);
+                    if (!L.seFused) launchSeSqueeze(L.p.out, L.p.gn, L.p.out_h, L.p.out_w, L.p.out_c, L.sePartial, L.seBlocks, stream);
                     launchSeExcite(L.sePartial, L.seBlocks, L.p.gn, L.p.out_c, L.seR, L.p.out_h * L.p.out_w, L.seW1, L.seB1, L.seW2, L.seB2, L.seScale, stream);
                     launchSeScale(L.p.out, L.p.gn, L.p.out_h, L.p.out_w, L.p.out_c, L.seScale, stream);
                 }

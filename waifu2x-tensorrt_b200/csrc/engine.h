@@ -40,6 +40,8 @@ struct LayerExec {
     float* sePartial = nullptr;
     float* seScale = nullptr;
     int seBlocks = 0;
+    bool seFused = false;        // squeeze sums come from the conv epilogue (ConvParams::se_sum)
+    size_t sePartialBytes = 0;
 };
 
 // Builders for the implicit-GEMM views (shared with the self-test).

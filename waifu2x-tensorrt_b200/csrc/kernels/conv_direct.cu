@@ -3,8 +3,7 @@
 //  * conv_direct_kernel: scalar reference of the implicit-GEMM contract in conv_params.h.  NOT on the product path:
 //    it exists so the tcgen05 kernels can be checked on the device at full layer sizes (w2x_selftest_conv, tests).
 //  * conv_first_kernel: the RGB first layers (cin = 3 stored as 4, K = 27): far below a UMMA K-block and bound by the
-//    32-channel fp16 store, so it runs on CUDA cores with the 3x3x4 neighbourhood in registers and the weights
-//    broadcast from shared memory.  Two pixels per thread so each weight read feeds two FMAs.
+//    32-channel fp16 store, so it uses warp-level mma.sync with register-resident weight fragments (see below).
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
@@ -43,87 +42,93 @@ void launchConvDirect(const ConvParams& p, cudaStream_t s) {
 }
 
 // ---- first layer: NHWC4 fp16 -> 32 channels, 3x3 valid, bias + LeakyReLU -----------------------------------
-// Persistent blocks (grid = a few per SM): the 36x32 weight table is converted to fp32 in shared memory ONCE per block,
-// then the block strides over 64x4-pixel work items.  Each thread: 2 horizontally adjacent pixels x 32 channels.
-__global__ void __launch_bounds__(128) conv_first_kernel(ConvParams p, int itemsX, int itemsY, int totalItems) {
-    __shared__ float sw[36 * 32];  // [k][co], k = (ky*3+kx)*4 + ci
-    __shared__ float sb[32];
-    for (int i = threadIdx.x; i < 36 * 32; i += blockDim.x) {
-        const int k = i >> 5, co = i & 31;
-        sw[i] = __half2float(p.w[(long long)co * p.ktot + k]);
-    }
-    if (threadIdx.x < 32) sb[threadIdx.x] = p.bias[threadIdx.x];
-    __syncthreads();
-    for (int item = blockIdx.x; item < totalItems; item += gridDim.x) {
-        const int ix = item % itemsX;
-        const int iy = (item / itemsX) % itemsY;
-        const int img = item / (itemsX * itemsY);
-        const int x = (ix * 32 + (threadIdx.x & 31)) * 2;
-        const int y = iy * 4 + (threadIdx.x >> 5);
-        if (x >= p.gx || y >= p.gy) continue;
-        const bool two = x + 1 < p.gx;
-        // 3 rows x 4 columns x 3 channels neighbourhood (the 4th column only when the second pixel exists)
-        float in[3][4][3];
+// K = 27 is far below a UMMA K block and the layer is bound by its 64-byte-per-pixel store, so it runs on warp-level
+// mma.sync (m16n8k16, fp16 in / fp32 accumulate): one warp = 16 consecutive output pixels x 32 channels, three K steps
+// (one per filter row: 3 taps x 4 stored channels + one zero-weight pad tap).  A fragments are loaded straight from the
+// NHWC4 tile (4-byte loads, L1-resident), the weight fragments live in registers for the warp's lifetime, and a quad
+// transpose (3 shuffles) turns the accumulator layout into 16-byte, fully coalesced channel-contiguous stores.
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+constexpr int kFirstRows = 32;  // output rows per work unit (a warp walks down a 16-pixel-wide column strip)
+
+__global__ void __launch_bounds__(256) conv_first_kernel(ConvParams p, int segsX, int chunksY, int totalUnits) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int warpId = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int warpCount = gridDim.x * (blockDim.x >> 5);
+    // B fragments: b[ky][j][0..1]; k index kk -> (kx = kk >> 2, ci = kk & 3); kx == 3 is the zero pad tap
+    uint32_t bf[3][4][2];
+    float bias[4][2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int n = 8 * j + g;
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
-            const __half* row = p.in + (long long)img * p.sn + (long long)(y + ky) * p.sy + (long long)x * p.sx;
-#pragma unroll
-            for (int kx = 0; kx < 4; ++kx) {
-                if (kx < 3 || two) {
-                    const Half4 v = *reinterpret_cast<const Half4*>(row + (long long)kx * p.sx);
-                    const float2 a = __half22float2(v.a), b = __half22float2(v.b);
-                    in[ky][kx][0] = a.x; in[ky][kx][1] = a.y; in[ky][kx][2] = b.x;
-                } else {
-                    in[ky][kx][0] = in[ky][kx][1] = in[ky][kx][2] = 0.f;
-                }
-            }
+            const __half* wrow = p.w + (long long)n * p.ktot + ky * 12;
+            bf[ky][j][0] = *reinterpret_cast<const uint32_t*>(wrow + (t >> 1) * 4 + (t & 1) * 2);
+            bf[ky][j][1] = (t >> 1) == 0 ? *reinterpret_cast<const uint32_t*>(wrow + 8 + (t & 1) * 2) : 0u;
         }
-        float acc0[32], acc1[32];
+        bias[j][0] = p.bias[8 * j + 2 * t];
+        bias[j][1] = p.bias[8 * j + 2 * t + 1];
+    }
+    // A fragment of one input row for this lane: pixels (x0+g, x0+g+8) and the same shifted by two taps.  Reads past the
+    // row end only meet zero weights or discarded pixels (activation buffers carry slack).
+    auto loadRow = [&](const __half* row, uint32_t (&a)[4]) {
+        a[0] = *reinterpret_cast<const uint32_t*>(row);
+        a[1] = *reinterpret_cast<const uint32_t*>(row + 8 * 4);
+        a[2] = *reinterpret_cast<const uint32_t*>(row + 2 * 4);
+        a[3] = *reinterpret_cast<const uint32_t*>(row + 10 * 4);
+    };
+    for (int unit = warpId; unit < totalUnits; unit += warpCount) {
+        const int sx = unit % segsX;
+        const int rest = unit / segsX;
+        const int cy = rest % chunksY;
+        const int img = rest / chunksY;
+        const int x0 = sx * 16, y0 = cy * kFirstRows;
+        const int y1 = min(p.gy, y0 + kFirstRows);
+        const __half* in = p.in + (long long)img * p.sn + (long long)y0 * p.sy + (long long)(x0 + g + (t >> 1)) * 4 + (t & 1) * 2;
+        __half* out = p.out + (((long long)img * p.out_h + y0) * p.out_w + x0 + g) * p.out_c + 2 * t;
+        const bool okLo = x0 + g < p.gx, okHi = x0 + g + 8 < p.gx;
+        uint32_t a0[4], a1[4], a2[4], a3[4];
+        loadRow(in, a0);
+        loadRow(in + p.sy, a1);
+        loadRow(in + 2 * p.sy, a2);
+        for (int y = y0; y < y1; ++y) {
+            // the row after next is in flight while this row's MMAs run (the last prefetch of a strip stays inside the tile:
+            // input rows y+3 <= gy+1 = H-1 ... except the very last, which is clamped)
+            const int yn = min(y + 3, p.gy + 1) - y0;
+            loadRow(in + (long long)yn * p.sy, a3);
+            float d[4][4];
 #pragma unroll
-        for (int co = 0; co < 32; ++co) { acc0[co] = sb[co]; acc1[co] = sb[co]; }
+            for (int j = 0; j < 4; ++j) { d[j][0] = bias[j][0]; d[j][1] = bias[j][1]; d[j][2] = bias[j][0]; d[j][3] = bias[j][1]; }
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky)
+            for (int j = 0; j < 4; ++j) mma16816(d[j], a0, bf[0][j][0], bf[0][j][1]);
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx)
+            for (int j = 0; j < 4; ++j) mma16816(d[j], a1, bf[1][j][0], bf[1][j][1]);
 #pragma unroll
-                for (int ci = 0; ci < 3; ++ci) {
-                    const float a0 = in[ky][kx][ci], a1 = in[ky][kx + 1][ci];
-                    const float4* wrow = reinterpret_cast<const float4*>(sw + ((ky * 3 + kx) * 4 + ci) * 32);
+            for (int j = 0; j < 4; ++j) mma16816(d[j], a2, bf[2][j][0], bf[2][j][1]);
+            // LeakyReLU + pack; a quad writes 16 contiguous bytes per (pixel, n-tile), four n-tiles complete the 64-byte pixel
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const float4 wv = wrow[q];
-                        acc0[4 * q + 0] = fmaf(a0, wv.x, acc0[4 * q + 0]); acc1[4 * q + 0] = fmaf(a1, wv.x, acc1[4 * q + 0]);
-                        acc0[4 * q + 1] = fmaf(a0, wv.y, acc0[4 * q + 1]); acc1[4 * q + 1] = fmaf(a1, wv.y, acc1[4 * q + 1]);
-                        acc0[4 * q + 2] = fmaf(a0, wv.z, acc0[4 * q + 2]); acc1[4 * q + 2] = fmaf(a1, wv.z, acc1[4 * q + 2]);
-                        acc0[4 * q + 3] = fmaf(a0, wv.w, acc0[4 * q + 3]); acc1[4 * q + 3] = fmaf(a1, wv.w, acc1[4 * q + 3]);
-                    }
-                }
-        __half* o = p.out + (((long long)img * p.out_h + y) * p.out_w + x) * p.out_c;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            Half8 h{__floats2half2_rn(lrelu(acc0[8 * q + 0], p.slope), lrelu(acc0[8 * q + 1], p.slope)),
-                    __floats2half2_rn(lrelu(acc0[8 * q + 2], p.slope), lrelu(acc0[8 * q + 3], p.slope)),
-                    __floats2half2_rn(lrelu(acc0[8 * q + 4], p.slope), lrelu(acc0[8 * q + 5], p.slope)),
-                    __floats2half2_rn(lrelu(acc0[8 * q + 6], p.slope), lrelu(acc0[8 * q + 7], p.slope))};
-            reinterpret_cast<Half8*>(o)[q] = h;
-        }
-        if (two) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                Half8 h{__floats2half2_rn(lrelu(acc1[8 * q + 0], p.slope), lrelu(acc1[8 * q + 1], p.slope)),
-                        __floats2half2_rn(lrelu(acc1[8 * q + 2], p.slope), lrelu(acc1[8 * q + 3], p.slope)),
-                        __floats2half2_rn(lrelu(acc1[8 * q + 4], p.slope), lrelu(acc1[8 * q + 5], p.slope)),
-                        __floats2half2_rn(lrelu(acc1[8 * q + 6], p.slope), lrelu(acc1[8 * q + 7], p.slope))};
-                reinterpret_cast<Half8*>(o + p.out_c)[q] = h;
+            for (int j = 0; j < 4; ++j) {
+                const __half2 l = __floats2half2_rn(fmaxf(d[j][0], d[j][0] * p.slope), fmaxf(d[j][1], d[j][1] * p.slope));
+                const __half2 h = __floats2half2_rn(fmaxf(d[j][2], d[j][2] * p.slope), fmaxf(d[j][3], d[j][3] * p.slope));
+                if (okLo) *reinterpret_cast<__half2*>(out + 8 * j) = l;
+                if (okHi) *reinterpret_cast<__half2*>(out + 8 * p.out_c + 8 * j) = h;
             }
+            out += (long long)p.out_w * p.out_c;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { a0[q] = a1[q]; a1[q] = a2[q]; a2[q] = a3[q]; }
         }
     }
 }
 
 void launchConvFirst(const ConvParams& p, cudaStream_t s) {
-    // contract: 3x3 taps in (ky,kx) order on a plain NHWC4 view, npad == 32, EPI_STORE with cout == 32
-    const int itemsX = (p.gx + 63) / 64, itemsY = (p.gy + 3) / 4;
-    const int total = itemsX * itemsY * p.gn;
+    // contract: 3x3 taps in (ky,kx) order on a plain NHWC4 view, ktot == 36, npad == 32, EPI_STORE with cout == out_c == 32
+    const int segsX = (p.gx + 15) / 16, chunksY = (p.gy + kFirstRows - 1) / kFirstRows;
+    const int total = segsX * chunksY * p.gn;
     static int sms = 0;
     if (!sms) {
         int dev = 0;
@@ -131,8 +136,9 @@ void launchConvFirst(const ConvParams& p, cudaStream_t s) {
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (sms <= 0) sms = 148;
     }
-    const int grid = total < sms * 4 ? total : sms * 4;
-    conv_first_kernel<<<grid, 128, 0, s>>>(p, itemsX, itemsY, total);
+    const int blocksNeeded = (total + 7) / 8;
+    const int grid = blocksNeeded < sms * 3 ? blocksNeeded : sms * 3;
+    conv_first_kernel<<<grid, 256, 0, s>>>(p, segsX, chunksY, total);
 }
 
 }  // namespace w2x

@@ -65,11 +65,11 @@ namespace {
 constexpr int kEpiWarps = 8;                       // two warps per TMEM lane quarter, splitting the columns
 constexpr int kThreads = 64 + 32 * kEpiWarps;      // warp 0 = TMA producer, warp 1 = MMA issuer, warps 2.. = epilogue
 constexpr int kEpiThreads = 32 * kEpiWarps;
-constexpr int kHeaderBytes = 3072;                 // barriers + TMEM slot (1 KB) | bias[npad <= 512] fp32 (2 KB)
+constexpr int kHeaderBytes = 4096;                 // barriers + TMEM slot (1 KB) | bias[npad <= 512] fp32 (2 KB) | SE scratch (1 KB)
 constexpr int kPatchW = 10, kPatchH = 18;
 
 // header layout (byte offsets from the 1024-aligned smem base)
-constexpr uint32_t kOffFull = 0, kOffEmpty = 64, kOffTFull = 128, kOffTEmpty = 144, kOffSkip = 160, kOffW = 184, kOffSlot = 256, kOffBias = 1024;
+constexpr uint32_t kOffFull = 0, kOffEmpty = 64, kOffTFull = 128, kOffTEmpty = 144, kOffSkip = 160, kOffW = 184, kOffSlot = 256, kOffBias = 1024, kOffSeScratch = 3072;
 
 enum EpiKind { EPI_K_DIRECT = 0, EPI_K_TMA = 1, EPI_K_TMA_SKIP = 2 };
 
@@ -161,6 +161,29 @@ __device__ __forceinline__ void epilogueWarps(const ConvArgs& a, uint32_t base, 
     if (kSkip && leader) {
         for (int k = 0; k < a.nbuf - 1 && k < nMine; ++k) issueSkip(k);
     }
+
+    // fused SE squeeze: thread (channel seC, row group seG) sums its channel over the valid rows of every tile of one image
+    const bool doSe = kTma && !kSkip && a.p.se_sum != nullptr;
+    const int et = threadIdx.x - 64;
+    const int seC = et & (a.bn - 1);
+    const int seG = et / a.bn;                         // 256 / bn row groups
+    const int seRows = (128 * a.bn) / kEpiThreads;     // rows per group
+    const int seGroups = kEpiThreads / a.bn;
+    float seAcc = 0.f;
+    int seImg = -1;
+    // image boundary (uniform across the epilogue threads): combine the row groups in a fixed order, one slot per CTA
+    auto seFlush = [&]() {
+        if (seImg < 0) return;
+        float* scratch = reinterpret_cast<float*>(__cvta_shared_to_generic((size_t)(base + kOffSeScratch)));
+        scratch[et] = seAcc;
+        namedBarSync(2, kEpiThreads);
+        if (seG == 0) {
+            float t = 0.f;
+            for (int g = 0; g < seGroups; ++g) t += scratch[g * a.bn + seC];
+            a.p.se_sum[((size_t)seImg * a.p.se_slots + first) * a.p.npad + nBase + seC] = t;
+        }
+        namedBarSync(2, kEpiThreads);
+    };
 
     int acc = 0;
     uint32_t accPhase = 0;
@@ -254,6 +277,23 @@ __device__ __forceinline__ void epilogueWarps(const ConvArgs& a, uint32_t base, 
                     tmaStore5d(&a.tmOut, stg + s * 16384u, c0, tc.x0, cz, tc.y0, tc.img);
                 }
                 bulkCommit();
+            }
+            if (doSe) {
+                if (tc.img != seImg) { seFlush(); seImg = tc.img; seAcc = 0.f; }
+                const uint32_t colOff = (uint32_t)(seC >> 6) * 16384u;
+                const int cc = seC & 63;
+                float sacc = 0.f;
+                for (int i = 0; i < seRows; ++i) {
+                    const int mm = seG * seRows + i;
+                    const bool ok = (tc.y0 + (mm >> a.bwShift)) < a.p.gy && (tc.x0 + (mm & (a.bw - 1))) < a.p.gx;
+                    const uint32_t addr = stg + colOff + (uint32_t)mm * 128u + ((uint32_t)((cc >> 3) ^ (mm & 7)) << 4) + (uint32_t)(cc & 7) * 2u;
+                    unsigned short hv;
+                    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hv) : "r"(addr));
+                    if (ok) sacc += __half2float(__ushort_as_half(hv));
+                }
+                seAcc += sacc;
+            }
+            if (leader) {
                 if (kSkip) {
                     const int kn = k + a.nbuf - 1;
                     if (kn < nMine) {
@@ -264,6 +304,7 @@ __device__ __forceinline__ void epilogueWarps(const ConvArgs& a, uint32_t base, 
             }
         }
     }
+    if (doSe) seFlush();
     if (kTma && leader) bulkWaitAll();
 }
 
@@ -758,6 +799,10 @@ IgemmPlan* igemmCreatePlan(const ConvParams& p) {
         static const bool noPatch = [] { const char* e = std::getenv("W2X_NO_PATCH"); return e && *e == '1'; }();
         if (!noPatch && wantsPatchKernel(p)) planPatch(plan);
         else planIgemm(plan);
+        if (p.se_sum) {
+            plan->args.p.se_slots = igemmSeSlots(plan);
+            if (plan->args.p.se_slots <= 0) throw Error("igemm: fused SE squeeze is not available for this layer shape");
+        }
         static bool attrSet = false;
         if (!attrSet) {
             checkCuda(cudaFuncSetAttribute(igemm_kernel<EPI_K_DIRECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
@@ -777,6 +822,12 @@ IgemmPlan* igemmCreatePlan(const ConvParams& p) {
 }
 
 void igemmDestroyPlan(IgemmPlan* plan) { delete plan; }
+
+int igemmSeSlots(const IgemmPlan* plan) {
+    const ConvArgs& a = plan->args;
+    if (!a.useTma || a.hasSkip || a.nbuf < 2 || a.tilesN != 1 || a.bn < 64) return 0;
+    return plan->grid / a.nSplit;  // one slot per CTA of an output-channel slice
+}
 
 const char* igemmDescribe(const IgemmPlan* plan, char* buf, int cap) {
     const ConvArgs& a = plan->args;

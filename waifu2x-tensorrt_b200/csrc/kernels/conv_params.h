@@ -44,7 +44,9 @@ struct ConvParams {
     const __half* skip;
     int skip_h, skip_w, skip_c, skip_off;
     const float* skip_scale;  // optional per-(img, channel) multiplier applied to skip (SE fold), or nullptr
-    float* se_sum;            // optional [gn][cout] fp32: per-channel sums of the stored activations (SE squeeze)
+    float* se_sum;            // optional [gn][se_slots][npad] fp32: deterministic per-CTA partial sums of the stored
+                              // activations (fused SE squeeze); the buffer must be zeroed before the launch
+    int se_slots;             // filled in by igemmCreatePlan
 };
 
 #ifdef __CUDACC__
@@ -134,6 +136,7 @@ void igemmDestroyPlan(IgemmPlan* plan);
 void igemmLaunch(const IgemmPlan* plan, cudaStream_t s, __half* outOverride = nullptr);
 bool igemmSupported(const ConvParams& p);
 const char* igemmDescribe(const IgemmPlan* plan, char* buf, int cap);
+int igemmSeSlots(const IgemmPlan* plan);  // partial-sum slots per image when ConvParams::se_sum is set (0 = unsupported)
 int probeUmma(int mode, int pitch, float* err9);
 
 // squeeze/excite

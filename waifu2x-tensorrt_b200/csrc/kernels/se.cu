@@ -52,10 +52,27 @@ __global__ void __launch_bounds__(256) se_excite_kernel(const float* __restrict_
     __shared__ float mean[256];
     __shared__ float hid[64];
     const int img = blockIdx.x;
-    for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
-        float s = 0.f;
-        for (int b = 0; b < nblk; ++b) s += partial[((size_t)img * nblk + b) * c + ch];
-        mean[ch] = s * inv_hw;
+    {
+        // all 256 threads reduce the partial sums: (256 / c) slot groups per channel, fixed combination order
+        __shared__ float part[256];
+        const int groups = 256 / c, ch = threadIdx.x % c, g = threadIdx.x / c;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        const float* pb = partial + (size_t)img * nblk * c + ch;
+        int b = g;
+        for (; b + 3 * groups < nblk; b += 4 * groups) {
+            s0 += pb[(size_t)b * c];
+            s1 += pb[(size_t)(b + groups) * c];
+            s2 += pb[(size_t)(b + 2 * groups) * c];
+            s3 += pb[(size_t)(b + 3 * groups) * c];
+        }
+        for (; b < nblk; b += groups) s0 += pb[(size_t)b * c];
+        part[threadIdx.x] = (s0 + s1) + (s2 + s3);
+        __syncthreads();
+        if (threadIdx.x < c) {
+            float s = 0.f;
+            for (int q = 0; q < groups; ++q) s += part[q * c + threadIdx.x];
+            mean[threadIdx.x] = s * inv_hw;
+        }
     }
     __syncthreads();
     for (int j = threadIdx.x; j < r; j += blockDim.x) {
