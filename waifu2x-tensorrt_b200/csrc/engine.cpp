@@ -237,7 +237,14 @@ static std::string findEngine(const std::string& modelPath, const w2x_render_con
         const std::string cfgPath = fs::path(p).replace_extension("").string() + ".json";
         if (!fs::exists(cfgPath)) continue;
         Sidecar sc = readSidecar(cfgPath);
+        // The reference maps the sidecar's device NAME back to the FIRST device with that name (helper.h:47-56), so on a box
+        // of identical GPUs only device 0 can ever load an engine.  Deviation: a plan is compatible with every device that
+        // carries the recorded name (needed for one-engine-per-GPU frame sharding).
         sc.cfg.deviceId = deviceIdOf(sc.deviceName);
+        {
+            cudaDeviceProp prop{};
+            if (cudaGetDeviceProperties(&prop, rc.deviceId) == cudaSuccess && sc.deviceName == prop.name) sc.cfg.deviceId = rc.deviceId;
+        }
         if (isCompatible(rc, sc.cfg)) {
             if (isOptimized(rc, sc.cfg)) return p.string();
             if (chosen.empty()) chosen = p.string();
