@@ -168,6 +168,8 @@ def synth_init_(model: nn.Module, seed: int = 1234) -> nn.Module:
 
 
 def make_model(family: str, scale: int, seed: int = 1234) -> nn.Module:
+    if family == "swin_unet":
+        return synth_init_swin_(SwinUNet(scale), seed)
     if family == "cunet":
         if scale == 1:
             return synth_init_(CUNet(), seed)
@@ -175,3 +177,128 @@ def make_model(family: str, scale: int, seed: int = 1234) -> nn.Module:
             return synth_init_(UpCUNet(), seed)
         raise ValueError("cunet/art does not support scale factor 4.")  # main.cpp:142-143
     raise ValueError(family)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# SwinUNet family (swin_unet/{art,art_scan,photo}): nunif `waifu2x/models/swin_unet.py` restated.
+# Blocks are torchvision's SwinTransformerBlock v1 (pre-LN, W-MSA / SW-MSA with relative position bias, GELU MLP).
+# ------------------------------------------------------------------------------------------------------------------
+class SwinBlocks(nn.Module):
+    def __init__(self, dim: int, heads: int, layers: int, window: int = 6, mlp_ratio: float = 2.0):
+        super().__init__()
+        from torchvision.models.swin_transformer import SwinTransformerBlock
+        self.block = nn.Sequential(*[
+            SwinTransformerBlock(dim, heads, window_size=[window, window],
+                                 shift_size=[0 if i % 2 == 0 else window // 2] * 2, mlp_ratio=mlp_ratio,
+                                 dropout=0.0, attention_dropout=0.0, stochastic_depth_prob=0.0, norm_layer=nn.LayerNorm)
+            for i in range(layers)])
+
+    def forward(self, x):  # BHWC
+        return self.block(x)
+
+
+class PatchDown(nn.Module):
+    def __init__(self, cin: int, cout: int):
+        super().__init__()
+        self.conv = nn.Conv2d(cin, cout, 2, 2, 0)
+
+    def forward(self, x):  # BHWC
+        return self.conv(x.permute(0, 3, 1, 2)).permute(0, 2, 3, 1)
+
+
+class PatchUp(nn.Module):
+    def __init__(self, cin: int, cout: int):
+        super().__init__()
+        self.proj = nn.Linear(cin, cout * 4)
+
+    def forward(self, x):  # BHWC
+        x = self.proj(x).permute(0, 3, 1, 2)
+        return F.pixel_shuffle(x, 2).permute(0, 2, 3, 1)
+
+
+class ToImage(nn.Module):
+    def __init__(self, cin: int, cout: int, scale: int):
+        super().__init__()
+        self.scale = scale
+        self.proj = nn.Linear(cin, cout * scale * scale)
+
+    def forward(self, x):  # BHWC -> BCHW
+        x = self.proj(x).permute(0, 3, 1, 2)
+        return F.pixel_shuffle(x, self.scale) if self.scale > 1 else x
+
+
+class SwinUNet(nn.Module):
+    """offset = 8 * scale output pixels per side; out = (T - 16) * scale; needs (T - 16) % 48 == 0."""
+
+    def __init__(self, scale: int = 4, base_dim: int = 96, base_layers: int = 2, window: int = 6):
+        super().__init__()
+        assert scale in (1, 2, 4)
+        C, H, L = base_dim, base_dim // 16, base_layers
+        self.scale = scale
+        self.offset = 8 * scale
+        self.patch = nn.Sequential(nn.Conv2d(3, C // 2, 3, 1, 0), nn.LeakyReLU(0.1), nn.Conv2d(C // 2, C, 3, 1, 0), nn.LeakyReLU(0.1))
+        self.swin1 = SwinBlocks(C, H, L, window)
+        self.down1 = PatchDown(C, C * 2)
+        self.swin2 = SwinBlocks(C * 2, H, L, window)
+        self.down2 = PatchDown(C * 2, C * 2)
+        self.swin3 = SwinBlocks(C * 2, H, L * 3, window)
+        self.up2 = PatchUp(C * 2, C * 2)
+        self.swin4 = SwinBlocks(C * 2, H, L, window)
+        self.up1 = PatchUp(C * 2, C)
+        self.swin5 = SwinBlocks(C, H, L, window)
+        if scale == 4:
+            self.up0 = PatchUp(C, C)
+            self.to_image = ToImage(C, 3, 2)
+        else:
+            self.up0 = None
+            self.to_image = ToImage(C, 3, scale)
+
+    def forward(self, x):
+        x2 = F.pad(self.patch(x), (-6, -6, -6, -6)).permute(0, 2, 3, 1)  # BHWC
+        x3 = self.swin1(x2)
+        x4 = self.swin2(self.down1(x3))
+        x5 = self.swin3(self.down2(x4))
+        x = self.swin4(self.up2(x5) + x4)
+        x = self.swin5(self.up1(x) + x3)
+        if self.up0 is not None:
+            x = self.up0(x)
+        return torch.clamp(self.to_image(x), 0.0, 1.0)
+
+
+def swin_out_size(scale: int, tile: int) -> int:
+    return (tile - 16) * scale
+
+
+def synth_init_swin_(model: nn.Module, seed: int = 1234) -> nn.Module:
+    """Seeded synthetic SwinUNet weights: unit-variance token stream, small residual branches, image head centred at 0.5."""
+    g = torch.Generator().manual_seed(seed)
+    gain = math.sqrt(2.0 / (1.0 + 0.1 ** 2))
+    with torch.no_grad():
+        for name, m in model.named_modules():
+            if isinstance(m, nn.Conv2d):
+                fan = m.weight.shape[1] * m.weight.shape[2] * m.weight.shape[3]
+                std = (gain if name.startswith("patch") else 1.0) / math.sqrt(fan)
+                m.weight.copy_(torch.randn(m.weight.shape, generator=g) * std)
+                m.bias.copy_(torch.randn(m.bias.shape, generator=g) * 0.05)
+            elif isinstance(m, nn.Linear):
+                fan = m.weight.shape[1]
+                std = 1.0 / math.sqrt(fan)
+                if name.endswith("attn.proj") or name.endswith("mlp.3"):
+                    std *= 0.5  # residual branches
+                if name == "to_image.proj":
+                    std *= 0.2
+                m.weight.copy_(torch.randn(m.weight.shape, generator=g) * std)
+                if m.bias is not None:
+                    m.bias.copy_(torch.randn(m.bias.shape, generator=g) * 0.02)
+                    if name == "to_image.proj":
+                        m.bias.add_(0.5)
+            elif isinstance(m, nn.LayerNorm):
+                m.weight.copy_(1.0 + 0.1 * torch.randn(m.weight.shape, generator=g))
+                m.bias.copy_(0.05 * torch.randn(m.bias.shape, generator=g))
+        for name, p in model.named_parameters():
+            if name.endswith("relative_position_bias_table"):
+                p.copy_(torch.randn(p.shape, generator=g) * 0.5)
+        m = model.patch[0]
+        m.weight.mul_(3.0)
+        m.bias.sub_(0.5 * m.weight.sum(dim=(1, 2, 3)))
+    return model.eval()

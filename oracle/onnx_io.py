@@ -316,3 +316,91 @@ def read_model(blob: bytes):
             n, a = _parse_tensor(v)
             inits[n] = a
     return nodes, inits
+
+
+# ---- SwinUNet emitter ---------------------------------------------------------------------------------------------------
+# Weight-bearing nodes (Conv, LayerNormalization, MatMul + Add(bias), Add(relative position bias)) are emitted exactly as a
+# constant-folded torch export carries them (MatMul weights as [in, out]; the relative-position bias pre-gathered to
+# [1, heads, 36, 36]).  The data-movement nodes between them (roll / window partition / head split) are emitted as a
+# best-effort Reshape/Transpose/Softmax skeleton: the real nunif exports are unobtainable here, no generic ONNX
+# runtime in the image can execute window attention graphs, and the product's importer keys on the weight-bearing nodes only.
+def _emit_linear(g: GraphBuilder, x: str, m, name: str) -> str:
+    w = g.init(name + ".weight_t", m.weight.detach().numpy().T.copy())  # [in, out]
+    y = g._new("matmul")
+    g.nodes.append(node("MatMul", [x, w], [y], name + ".matmul"))
+    if m.bias is not None:
+        b = g.init(name + ".bias", m.bias.detach().numpy())
+        y2 = g._new("addb")
+        g.nodes.append(node("Add", [y, b], [y2], name + ".add"))
+        y = y2
+    return y
+
+
+def _emit_layernorm(g: GraphBuilder, x: str, m, name: str) -> str:
+    s = g.init(name + ".weight", m.weight.detach().numpy())
+    b = g.init(name + ".bias", m.bias.detach().numpy())
+    y = g._new("ln")
+    g.nodes.append(node("LayerNormalization", [x, s, b], [y], name, [attr_i("axis", -1), attr_f("epsilon", float(m.eps))]))
+    return y
+
+
+def _emit_swin_block(g: GraphBuilder, x: str, blk, name: str) -> str:
+    h = _emit_layernorm(g, x, blk.norm1, name + ".norm1")
+    qkv = _emit_linear(g, h, blk.attn.qkv, name + ".attn.qkv")
+    q = g.unary("Transpose", g.unary("Reshape", qkv))   # skeleton: roll + window partition + head split
+    scores = g.binary("MatMul", q, q)
+    bias = blk.attn.get_relative_position_bias().detach().numpy()  # [1, heads, N, N]
+    bname = g.init(name + ".attn.relative_position_bias", bias)
+    scores = g.binary("Add", scores, bname)
+    p = g.unary("Softmax", scores, [attr_i("axis", -1)])
+    o = g.unary("Reshape", g.unary("Transpose", g.binary("MatMul", p, q)))
+    o = _emit_linear(g, o, blk.attn.proj, name + ".attn.proj")
+    x = g.binary("Add", x, o)
+    h = _emit_layernorm(g, x, blk.norm2, name + ".norm2")
+    h = _emit_linear(g, h, blk.mlp[0], name + ".mlp.0")
+    h = g.binary("Mul", h, g.unary("Erf", h))  # skeleton of the erf-GELU decomposition
+    h = _emit_linear(g, h, blk.mlp[3], name + ".mlp.3")
+    return g.binary("Add", x, h)
+
+
+def export_swin(model_t, path: str | None = None) -> bytes:
+    """Emit oracle.models.SwinUNet as ONNX (see the note above about the skeleton nodes)."""
+    g = GraphBuilder()
+    x = g.lrelu(g.conv("x", model_t.patch[0], "patch.0"))
+    x = g.lrelu(g.conv(x, model_t.patch[2], "patch.2"))
+    x = g.unary("Transpose", g.crop(x, 6), [attr_ints("perm", [0, 2, 3, 1])])
+
+    def blocks(x, stage, name):
+        for i, blk in enumerate(stage.block):
+            x = _emit_swin_block(g, x, blk, f"{name}.block.{i}")
+        return x
+
+    def down(x, m, name):
+        x = g.unary("Transpose", x, [attr_ints("perm", [0, 3, 1, 2])])
+        x = g.conv(x, m.conv, name + ".conv")
+        return g.unary("Transpose", x, [attr_ints("perm", [0, 2, 3, 1])])
+
+    def up(x, m, name):
+        x = _emit_linear(g, x, m.proj, name + ".proj")
+        x = g.unary("DepthToSpace", g.unary("Transpose", x, [attr_ints("perm", [0, 3, 1, 2])]), [attr_i("blocksize", 2)])
+        return g.unary("Transpose", x, [attr_ints("perm", [0, 2, 3, 1])])
+
+    x3 = blocks(x, model_t.swin1, "swin1")
+    x4 = blocks(down(x3, model_t.down1, "down1"), model_t.swin2, "swin2")
+    x5 = blocks(down(x4, model_t.down2, "down2"), model_t.swin3, "swin3")
+    x = blocks(g.binary("Add", up(x5, model_t.up2, "up2"), x4), model_t.swin4, "swin4")
+    x = blocks(g.binary("Add", up(x, model_t.up1, "up1"), x3), model_t.swin5, "swin5")
+    if model_t.up0 is not None:
+        x = up(x, model_t.up0, "up0")
+    x = _emit_linear(g, x, model_t.to_image.proj, "to_image.proj")
+    x = g.unary("Transpose", x, [attr_ints("perm", [0, 3, 1, 2])])
+    if model_t.to_image.scale > 1:
+        x = g.unary("DepthToSpace", x, [attr_i("blocksize", model_t.to_image.scale)])
+    y = g.clip01(x)
+    g.nodes.append(node("Identity", [y], ["y"]))
+    blob = model(g.nodes, g.inits, [value_info("x", ["batch", 3, "height", "width"])],
+                 [value_info("y", ["batch", 3, "out_height", "out_width"])], name="w2x_swin_unet", opset=17)
+    if path:
+        with open(path, "wb") as f:
+            f.write(blob)
+    return blob

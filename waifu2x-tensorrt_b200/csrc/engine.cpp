@@ -305,7 +305,12 @@ bool Engine::load(const std::string& onnxPath, const w2x_render_config& rc) {
 }
 
 void Engine::buildPlan() {
-    if (model.arch != ARCH_CUNET && model.arch != ARCH_UPCUNET) throw Error("unknown model architecture in pack file");
+    if (model.arch == ARCH_SWINUNET) buildPlanSwin();
+    else if (model.arch == ARCH_CUNET || model.arch == ARCH_UPCUNET) buildPlanCunet();
+    else throw Error("unknown model architecture in pack file");
+}
+
+void Engine::buildPlanCunet() {
     const bool up = model.arch == ARCH_UPCUNET;
     // weights -> HBM
     for (const auto& L : model.layers) {
@@ -423,6 +428,201 @@ void Engine::buildPlan() {
     if (outTile != expect) throw Error("internal: output tile size mismatch");
 }
 
+void Engine::launchLayer(LayerExec& L, cudaStream_t s, __half* outp) {
+    switch (L.impl) {
+        case IMPL_IGEMM: igemmLaunch(L.plan, s, outp); break;
+        case IMPL_LAYERNORM:
+            launchLayerNorm(L.tokIn, L.tokOut, (long long)L.tokN * L.tokH * L.tokW, L.tokC, L.gamma, L.beta, L.eps, s);
+            break;
+        case IMPL_ATTENTION:
+            launchWindowAttention(L.tokIn, L.tokOut, L.tokN, L.tokH, L.tokW, L.tokC, L.heads, L.window, L.shift, L.relpos, s);
+            break;
+        default: {
+            ConvParams p = L.p;
+            if (outp) p.out = outp;
+            if (L.impl == IMPL_FIRST) launchConvFirst(p, s);
+            else launchConvDirect(p, s);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// SwinUNet execution plan: token tensors are NHWC fp16 [batch][h][w][C]; the residual stream is updated in
+// place by the proj / fc2 epilogues (each thread reads exactly the element it then overwrites).
+// ------------------------------------------------------------------------------------------------
+void Engine::buildPlanSwin() {
+    const int C = (int)model.dim, S = (int)model.scale;
+    if (C % 32 || tile < 64 || (tile - 16) % 48 != 0)
+        throw Error("tile size is not supported by swin_unet ((tile - 16) must be a multiple of 48; SURVEY q10)");
+    std::vector<float*> dAux0(model.layers.size(), nullptr), dAux1(model.layers.size(), nullptr);
+    auto uploadF = [&](const std::vector<float>& v) {
+        float* d = (float*)dalloc(std::max<size_t>(v.size(), 1) * 4);
+        if (!v.empty()) W2X_CUDA(cudaMemcpy(d, v.data(), v.size() * 4, cudaMemcpyHostToDevice));
+        return d;
+    };
+    for (size_t i = 0; i < model.layers.size(); ++i) {
+        const auto& L = model.layers[i];
+        __half* w = nullptr;
+        float* b = nullptr;
+        if (!L.w.empty()) {
+            w = (__half*)dalloc(L.w.size() * 2);
+            W2X_CUDA(cudaMemcpy(w, L.w.data(), L.w.size() * 2, cudaMemcpyHostToDevice));
+            b = uploadF(L.bias);
+        }
+        dW.push_back(w);
+        dBias.push_back(b);
+        if (L.kind == L_LN) { dAux0[i] = uploadF(L.gamma); dAux1[i] = uploadF(L.beta); }
+        if (L.kind == L_ATTN) dAux0[i] = uploadF(L.relpos);
+    }
+    size_t li = 0;
+    auto next = [&](uint32_t kind) -> size_t {
+        if (li >= model.layers.size() || model.layers[li].kind != kind) throw Error("swin plan: unexpected layer order in pack file");
+        return li++;
+    };
+    auto pushConv = [&](size_t i, const ConvParams& p, double flops, bool fin = false) {
+        LayerExec E;
+        E.name = model.layers[i].name;
+        E.p = p;
+        E.flops = flops;
+        E.isFinal = fin;
+        if (useDirect) E.impl = IMPL_DIRECT;
+        else if (model.layers[i].kind == L_CONV3 && model.layers[i].cin == 4) E.impl = IMPL_FIRST;
+        else if (igemmSupported(p)) { E.impl = IMPL_IGEMM; E.plan = igemmCreatePlan(E.p); }
+        else throw Error("no kernel for layer " + E.name);
+        layers.push_back(E);
+    };
+    // ---- patch embedding: conv3x3(3->C/2) + lrelu, conv3x3(C/2->C) + lrelu, crop 6 ----
+    actIn = allocAct(tile, tile, 4);
+    const int T0 = tile - 16;  // token grid at level 1
+    {
+        const size_t i0 = next(L_CONV3);
+        Act a0 = allocAct(tile - 2, tile - 2, 64);
+        ConvParams p = makeConv3Params(actIn, a0, dW[i0], dBias[i0], 64, EPI_STORE, 0.1f, 64);
+        pushConv(i0, p, 2.0 * p.gx * p.gy * (double)model.layers[i0].cout * 27);
+        const size_t i1 = next(L_CONV3);
+        // second conv computed directly on the cropped region: output (y, x) = full-conv output (y + 6, x + 6)
+        Act view = a0;
+        view.p = a0.p + ((size_t)6 * a0.w + 6) * a0.c;
+        Act x1 = allocAct(T0, T0, C);
+        ConvParams q = makeConv3Params(view, x1, dW[i1], dBias[i1], C, EPI_STORE, 0.1f, C);
+        q.dimx = a0.w - 6; q.dimy = a0.h - 6;
+        q.gx = T0; q.gy = T0;
+        pushConv(i1, q, 2.0 * T0 * T0 * (double)C * 9 * model.layers[i1 - 1].cout);
+        actOut = x1;
+    }
+    // scratch sized for level 1 (the largest token count)
+    Act lnBuf = allocAct(T0, T0, C), qkvBuf = allocAct(T0, T0, 3 * C), attBuf = allocAct(T0, T0, C), hidBuf = allocAct(T0, T0, 2 * C);
+    auto viewOf = [&](const Act& buf, int h, int w, int c) {
+        Act v = buf;
+        v.h = h; v.w = w; v.c = c;
+        if (v.elems() > buf.elems()) throw Error("swin plan: scratch buffer too small");
+        return v;
+    };
+    auto linear = [&](size_t i, const Act& in, const Act& out, int act, const Act* residual) {
+        const PackedLayer& L = model.layers[i];
+        ConvParams p{};
+        p.in = in.p;
+        p.dimc = in.c; p.dimx = in.w; p.dimz = 1; p.dimy = in.h;
+        p.sx = in.c; p.sz = (long long)in.w * in.c; p.sy = (long long)in.w * in.c; p.sn = (long long)in.h * in.w * in.c;
+        p.cin = in.c; p.gn = in.n;
+        p.ntaps = 1; p.tap[0] = {0, 0, 0, 0};
+        p.gx = in.w; p.gy = in.h;
+        p.npad = (int)L.npad; p.ktot = (int)L.ktot;
+        p.w = dW[i]; p.bias = dBias[i];
+        p.mode = EPI_STORE; p.slope = 1.f; p.act = act; p.cout = (int)L.npad;
+        p.out = out.p; p.out_h = out.h; p.out_w = out.w; p.out_c = out.c;
+        if (residual) { p.skip = residual->p; p.skip_h = residual->h; p.skip_w = residual->w; p.skip_c = residual->c; p.skip_off = 0; }
+        pushConv(i, p, 2.0 * in.h * in.w * (double)L.npad * L.ktot);
+    };
+    int blockIndex = 0;
+    auto block = [&](Act& x) {
+        const int h = x.h, w = x.w, c = x.c;
+        const size_t n1 = next(L_LN), qk = next(L_LINEAR), at = next(L_ATTN), pj = next(L_LINEAR), n2 = next(L_LN), f1 = next(L_LINEAR), f2 = next(L_LINEAR);
+        Act ln = viewOf(lnBuf, h, w, c), qkv = viewOf(qkvBuf, h, w, 3 * c), att = viewOf(attBuf, h, w, c), hid = viewOf(hidBuf, h, w, (int)model.layers[f1].npad);
+        auto pushLn = [&](size_t i) {
+            LayerExec E;
+            E.name = model.layers[i].name; E.impl = IMPL_LAYERNORM;
+            E.tokIn = x.p; E.tokOut = ln.p; E.tokN = x.n; E.tokH = h; E.tokW = w; E.tokC = c;
+            E.gamma = dAux0[i]; E.beta = dAux1[i]; E.eps = model.layers[i].eps;
+            layers.push_back(E);
+        };
+        pushLn(n1);
+        linear(qk, ln, qkv, ACT_LRELU, nullptr);
+        {
+            const PackedLayer& L = model.layers[at];
+            if (L.window != 6 || (c / (int)L.heads != 16 && c / (int)L.heads != 32) || h % 6 || w % 6)
+                throw Error("swin plan: unsupported attention geometry (window 6, head dim 16/32 only)");
+            LayerExec E;
+            E.name = L.name; E.impl = IMPL_ATTENTION;
+            E.tokIn = qkv.p; E.tokOut = att.p; E.tokN = x.n; E.tokH = h; E.tokW = w; E.tokC = c;
+            E.heads = (int)L.heads; E.window = (int)L.window; E.shift = (blockIndex % 2) ? (int)L.window / 2 : 0;
+            E.relpos = dAux0[at];
+            E.flops = 4.0 * (h / 6) * (w / 6) * 36.0 * 36.0 * c;
+            layers.push_back(E);
+        }
+        linear(pj, att, x, ACT_LRELU, &x);   // x += proj(attn)
+        pushLn(n2);
+        linear(f1, ln, hid, ACT_GELU, nullptr);
+        linear(f2, hid, x, ACT_LRELU, &x);   // x += fc2(gelu(fc1(ln)))
+        ++blockIndex;
+    };
+    auto stage = [&](Act& x) {
+        blockIndex = 0;  // shift alternates from 0 inside every stage
+        while (li < model.layers.size() && model.layers[li].kind == L_LN) block(x);
+    };
+    auto down = [&](const Act& in) {
+        const size_t i = next(L_DOWN2);
+        const PackedLayer& L = model.layers[i];
+        Act out = allocAct(in.h / 2, in.w / 2, (int)L.cout);
+        ConvParams p = makeDown2Params(in, out, dW[i], dBias[i], (int)L.npad, 1.f);
+        pushConv(i, p, 2.0 * p.gx * p.gy * (double)L.cout * 4 * L.cin);
+        return out;
+    };
+    auto up = [&](const Act& in, const Act* skip) {
+        const size_t i = next(L_UPLIN);
+        const PackedLayer& L = model.layers[i];
+        Act out = allocAct(in.h * 2, in.w * 2, (int)L.cout);
+        if (skip && (skip->h != out.h || skip->c != out.c)) throw Error("swin plan: skip connection mismatch");
+        ConvParams p = makeUp2Params(in, out, dW[i], dBias[i], (int)L.cout, 1.f, skip, 0);
+        pushConv(i, p, 2.0 * p.gx * p.gy * 4.0 * L.cout * L.cin);
+        return out;
+    };
+    Act x1 = actOut;
+    stage(x1);
+    Act x2 = down(x1);
+    stage(x2);
+    Act x3 = down(x2);
+    stage(x3);
+    Act y2 = up(x3, &x2);
+    stage(y2);
+    Act y1 = up(y2, &x1);
+    stage(y1);
+    Act top = y1;
+    if (S == 4) top = up(y1, nullptr);
+    {
+        const size_t i = next(L_TOIMG);
+        const PackedLayer& L = model.layers[i];
+        const int s = (int)L.upscale;
+        Act out = allocAct(top.h * s, top.w * s, 4);
+        ConvParams p{};
+        p.in = top.p;
+        p.dimc = top.c; p.dimx = top.w; p.dimz = 1; p.dimy = top.h;
+        p.sx = top.c; p.sz = (long long)top.w * top.c; p.sy = (long long)top.w * top.c; p.sn = (long long)top.h * top.w * top.c;
+        p.cin = top.c; p.gn = top.n;
+        p.ntaps = 1; p.tap[0] = {0, 0, 0, 0};
+        p.gx = top.w; p.gy = top.h;
+        p.npad = 16; p.ktot = (int)L.ktot;
+        p.w = dW[i]; p.bias = dBias[i];
+        p.mode = EPI_TOIMG; p.slope = 1.f; p.cout = s;
+        p.out = out.p; p.out_h = out.h; p.out_w = out.w; p.out_c = 4;
+        pushConv(i, p, 2.0 * top.h * top.w * 3.0 * s * s * L.ktot, true);
+        actOut = out;
+    }
+    if (li != model.layers.size()) throw Error("swin plan: trailing layers in pack file");
+    outTile = actOut.h;
+    if (outTile != (tile - 16) * S) throw Error("internal: swin output tile size mismatch");
+}
+
 double Engine::flopsPerTile() const {
     double f = 0;
     for (const auto& L : layers) f += L.flops;
@@ -433,14 +633,7 @@ void Engine::runModel(cudaStream_t s, __half* finalOut) {
     for (auto& L : layers) {
         __half* outp = (L.isFinal && finalOut) ? finalOut : L.p.out;
         if (L.seFused) W2X_CUDA(cudaMemsetAsync(L.sePartial, 0, L.sePartialBytes, s));
-        if (L.impl == IMPL_IGEMM) {
-            igemmLaunch(L.plan, s, outp);
-        } else {
-            ConvParams p = L.p;
-            p.out = outp;
-            if (L.impl == IMPL_FIRST) launchConvFirst(p, s);
-            else launchConvDirect(p, s);
-        }
+        launchLayer(L, s, outp);
         ++launches;
         if (L.seR) {
             if (!L.seFused) { launchSeSqueeze(L.p.out, L.p.gn, L.p.out_h, L.p.out_w, L.p.out_c, L.sePartial, L.seBlocks, s); ++launches; }
@@ -742,9 +935,7 @@ int Engine::profileLayers(int repeats, char (*names)[48], float* ms, double* flo
             W2X_CUDA(cudaEventRecord(e0, stream));
             for (int r = 0; r < repeats; ++r) {
                 if (L.seFused) W2X_CUDA(cudaMemsetAsync(L.sePartial, 0, L.sePartialBytes, stream));
-                if (L.impl == IMPL_IGEMM) igemmLaunch(L.plan, stream, nullptr);
-                else if (L.impl == IMPL_FIRST) launchConvFirst(L.p, stream);
-                else launchConvDirect(L.p, stream);
+                launchLayer(L, stream, nullptr);
                 if (L.seR) {
                     if (!L.seFused) launchSeSqueeze(L.p.out, L.p.gn, L.p.out_h, L.p.out_w, L.p.out_c, L.sePartial, L.seBlocks, stream);
                     launchSeExcite(L.sePartial, L.seBlocks, L.p.gn, L.p.out_c, L.seR, L.p.out_h * L.p.out_w, L.seW1, L.seB1, L.seW2, L.seB2, L.seScale, stream);

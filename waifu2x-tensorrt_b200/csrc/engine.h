@@ -25,7 +25,7 @@ struct Act {
     size_t elems() const { return (size_t)n * h * w * c; }
 };
 
-enum ConvImpl { IMPL_DIRECT = 0, IMPL_FIRST = 1, IMPL_IGEMM = 2 };
+enum ConvImpl { IMPL_DIRECT = 0, IMPL_FIRST = 1, IMPL_IGEMM = 2, IMPL_LAYERNORM = 3, IMPL_ATTENTION = 4 };
 
 struct LayerExec {
     std::string name;
@@ -42,6 +42,12 @@ struct LayerExec {
     int seBlocks = 0;
     bool seFused = false;        // squeeze sums come from the conv epilogue (ConvParams::se_sum)
     size_t sePartialBytes = 0;
+    // SwinUNet token ops (IMPL_LAYERNORM / IMPL_ATTENTION)
+    const __half* tokIn = nullptr;
+    __half* tokOut = nullptr;
+    int tokN = 0, tokH = 0, tokW = 0, tokC = 0, heads = 0, window = 0, shift = 0;
+    const float *gamma = nullptr, *beta = nullptr, *relpos = nullptr;
+    float eps = 0.f;
 };
 
 // Builders for the implicit-GEMM views (shared with the self-test).
@@ -82,6 +88,9 @@ public:
 private:
     void unload();
     void buildPlan();
+    void buildPlanCunet();
+    void buildPlanSwin();
+    void launchLayer(LayerExec& L, cudaStream_t s, __half* outOverride);
     void runModel(cudaStream_t s, __half* finalOut);
     void ensureFrameBuffers(int w, int h);
     void renderOnStream(const uint8_t* dSrc, int w, int h, size_t srcPitch, uint8_t* dDst, size_t dstPitch, cudaStream_t s, bool timed);

@@ -55,15 +55,16 @@ __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], 
 
 constexpr int kFirstRows = 32;  // output rows per work unit (a warp walks down a 16-pixel-wide column strip)
 
+template <int NT>  // n-tiles of 8 output channels: 4 (CUNet, 32 ch) or 8 (SwinUNet patch embed, 64 stored ch)
 __global__ void __launch_bounds__(256) conv_first_kernel(ConvParams p, int segsX, int chunksY, int totalUnits) {
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const int warpId = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int warpCount = gridDim.x * (blockDim.x >> 5);
     // B fragments: b[ky][j][0..1]; k index kk -> (kx = kk >> 2, ci = kk & 3); kx == 3 is the zero pad tap
-    uint32_t bf[3][4][2];
-    float bias[4][2];
+    uint32_t bf[3][NT][2];
+    float bias[NT][2];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < NT; ++j) {
         const int n = 8 * j + g;
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
@@ -101,18 +102,18 @@ __global__ void __launch_bounds__(256) conv_first_kernel(ConvParams p, int segsX
             // input rows y+3 <= gy+1 = H-1 ... except the very last, which is clamped)
             const int yn = min(y + 3, p.gy + 1) - y0;
             loadRow(in + (long long)yn * p.sy, a3);
-            float d[4][4];
+            float d[NT][4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { d[j][0] = bias[j][0]; d[j][1] = bias[j][1]; d[j][2] = bias[j][0]; d[j][3] = bias[j][1]; }
+            for (int j = 0; j < NT; ++j) { d[j][0] = bias[j][0]; d[j][1] = bias[j][1]; d[j][2] = bias[j][0]; d[j][3] = bias[j][1]; }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) mma16816(d[j], a0, bf[0][j][0], bf[0][j][1]);
+            for (int j = 0; j < NT; ++j) mma16816(d[j], a0, bf[0][j][0], bf[0][j][1]);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) mma16816(d[j], a1, bf[1][j][0], bf[1][j][1]);
+            for (int j = 0; j < NT; ++j) mma16816(d[j], a1, bf[1][j][0], bf[1][j][1]);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) mma16816(d[j], a2, bf[2][j][0], bf[2][j][1]);
+            for (int j = 0; j < NT; ++j) mma16816(d[j], a2, bf[2][j][0], bf[2][j][1]);
             // LeakyReLU + pack; a quad writes 16 contiguous bytes per (pixel, n-tile), four n-tiles complete the 64-byte pixel
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < NT; ++j) {
                 const __half2 l = __floats2half2_rn(fmaxf(d[j][0], d[j][0] * p.slope), fmaxf(d[j][1], d[j][1] * p.slope));
                 const __half2 h = __floats2half2_rn(fmaxf(d[j][2], d[j][2] * p.slope), fmaxf(d[j][3], d[j][3] * p.slope));
                 if (okLo) *reinterpret_cast<__half2*>(out + 8 * j) = l;
@@ -126,7 +127,7 @@ __global__ void __launch_bounds__(256) conv_first_kernel(ConvParams p, int segsX
 }
 
 void launchConvFirst(const ConvParams& p, cudaStream_t s) {
-    // contract: 3x3 taps in (ky,kx) order on a plain NHWC4 view, ktot == 36, npad == 32, EPI_STORE with cout == out_c == 32
+    // contract: 3x3 taps in (ky,kx) order on a plain NHWC4 view, ktot == 36, npad == out_c in {32, 64}, EPI_STORE
     const int segsX = (p.gx + 15) / 16, chunksY = (p.gy + kFirstRows - 1) / kFirstRows;
     const int total = segsX * chunksY * p.gn;
     static int sms = 0;
@@ -138,7 +139,8 @@ void launchConvFirst(const ConvParams& p, cudaStream_t s) {
     }
     const int blocksNeeded = (total + 7) / 8;
     const int grid = blocksNeeded < sms * 3 ? blocksNeeded : sms * 3;
-    conv_first_kernel<<<grid, 256, 0, s>>>(p, segsX, chunksY, total);
+    if (p.npad == 64) conv_first_kernel<8><<<grid, 256, 0, s>>>(p, segsX, chunksY, total);
+    else conv_first_kernel<4><<<grid, 256, 0, s>>>(p, segsX, chunksY, total);
 }
 
 }  // namespace w2x

@@ -65,11 +65,11 @@ namespace {
 constexpr int kEpiWarps = 8;                       // two warps per TMEM lane quarter, splitting the columns
 constexpr int kThreads = 64 + 32 * kEpiWarps;      // warp 0 = TMA producer, warp 1 = MMA issuer, warps 2.. = epilogue
 constexpr int kEpiThreads = 32 * kEpiWarps;
-constexpr int kHeaderBytes = 4096;                 // barriers + TMEM slot (1 KB) | bias[npad <= 512] fp32 (2 KB) | SE scratch (1 KB)
+constexpr int kHeaderBytes = 6144;                 // barriers + TMEM slot (1 KB) | bias[npad <= 1024] fp32 (4 KB) | SE scratch (1 KB)
 constexpr int kPatchW = 10, kPatchH = 18;
 
 // header layout (byte offsets from the 1024-aligned smem base)
-constexpr uint32_t kOffFull = 0, kOffEmpty = 64, kOffTFull = 128, kOffTEmpty = 144, kOffSkip = 160, kOffW = 184, kOffSlot = 256, kOffBias = 1024, kOffSeScratch = 3072;
+constexpr uint32_t kOffFull = 0, kOffEmpty = 64, kOffTFull = 128, kOffTEmpty = 144, kOffSkip = 160, kOffW = 184, kOffSlot = 256, kOffBias = 1024, kOffSeScratch = 5120;
 
 enum EpiKind { EPI_K_DIRECT = 0, EPI_K_TMA = 1, EPI_K_TMA_SKIP = 2 };
 
@@ -137,9 +137,10 @@ __device__ __forceinline__ void epilogueWarps(const ConvArgs& a, uint32_t base, 
     const uint32_t bufBytes = (uint32_t)a.nsub * 16384u;
     const uint32_t biasS = base + kOffBias;
     const int skipHalf = a.p.skip_off >> 1;
-    const int colsPerWarp = a.bn >= 64 ? a.bn >> 1 : a.bn;   // bn = 16 heads: only the first warp of each quarter works
-    const int colBegin = a.bn >= 64 ? half * colsPerWarp : 0;
-    const bool active = a.bn >= 64 || half == 0;
+    const bool split = a.bn >= 64 && (a.bn & 31) == 0;       // two warps per lane quarter split the columns
+    const int colsPerWarp = split ? a.bn >> 1 : a.bn;        // small heads: only the first warp of each quarter works
+    const int colBegin = split ? half * colsPerWarp : 0;
+    const bool active = split || half == 0;
 
     TileWalker w;
     w.init(first, step, a.tilesN, a.tilesX, a.tilesY);
@@ -245,12 +246,22 @@ __device__ __forceinline__ void epilogueWarps(const ConvArgs& a, uint32_t base, 
             const bool valid = pvalid;
             const Half4* pre = a.p.mode == EPI_FINAL ? &preSkip : nullptr;
             if (a.bn >= 32) {
-                for (int c0 = colBegin; c0 < colBegin + colsPerWarp; c0 += 32) {
+                int c0 = colBegin;
+                for (; c0 + 32 <= colBegin + colsPerWarp; c0 += 32) {
                     tmemLd32(taddr + (uint32_t)c0, r);
                     tmemLdWait();
                     if (valid) {
 #pragma unroll
                         for (int q = 0; q < 4; ++q)
+                            conv_epilogue8(a.p, tc.img, y, x, tc.n0 + c0 + 8 * q, reinterpret_cast<const float*>(r) + 8 * q);
+                    }
+                }
+                if (c0 < colBegin + colsPerWarp) {  // 16-column tail (bn = 96: 48 columns per warp)
+                    tmemLd16(taddr + (uint32_t)c0, r);
+                    tmemLdWait();
+                    if (valid) {
+#pragma unroll
+                        for (int q = 0; q < 2; ++q)
                             conv_epilogue8(a.p, tc.img, y, x, tc.n0 + c0 + 8 * q, reinterpret_cast<const float*>(r) + 8 * q);
                     }
                 }
@@ -327,7 +338,7 @@ __device__ __forceinline__ void setupCommon(const ConvArgs& a, uint32_t base, ui
         if (a.hasSkip) tmaPrefetchDesc(&a.tmSkip);
     }
     float* biasS = reinterpret_cast<float*>(sm + kOffBias);
-    for (int i = threadIdx.x; i < a.p.npad && i < 512; i += blockDim.x) biasS[i] = a.p.bias[i];
+    for (int i = threadIdx.x; i < a.p.npad && i < 1024; i += blockDim.x) biasS[i] = a.p.bias[i];
     if (warp == 1) tmemAlloc(smemU32(sm + kOffSlot), a.tmemCols);
     tcFenceBefore();
     __syncthreads();
@@ -635,7 +646,7 @@ void encodeWeights(CUtensorMap* tm, const ConvParams& p, int kc, int rows, bool 
 
 // can the epilogue go through swizzled smem staging + TMA store?
 bool tmaEpilogueOk(const ConvParams& p) {
-    if (p.mode == EPI_STORE) return p.cout % 64 == 0 && p.npad == p.cout && p.out_c == p.cout;
+    if (p.mode == EPI_STORE) return p.cout % 64 == 0 && p.npad == p.cout && p.out_c == p.cout && p.act == ACT_LRELU && !p.skip;
     if (p.mode == EPI_D2S) {
         if (p.cout % 64 != 0 || p.out_c != p.cout || (p.out_w & 1) || (p.out_h & 1)) return false;
         if (p.skip && ((p.skip_off & 1) || (p.skip_w & 1) || (p.skip_h & 1) || p.skip_c != p.cout || p.skip_scale)) return false;
@@ -662,6 +673,14 @@ void encodeOutMaps(ConvArgs& a) {
             encode5d(&a.tmSkip, p.skip, sd, ss, box, true, "skip(d2s)");
         }
     }
+}
+
+// N tile: the largest divisor of npad that is a multiple of 32 and <= 256 (16-wide heads stay 16)
+int pickBn(int npad) {
+    if (npad <= 32) return npad;
+    for (int bn = 256; bn >= 32; bn -= 32)
+        if (npad % bn == 0) return bn;
+    return 0;
 }
 
 bool wantsPatchKernel(const ConvParams& p) {
@@ -727,8 +746,8 @@ void planIgemm(IgemmPlan* plan) {
     a.kc = (p.cin % 64 == 0) ? 64 : 32;
     a.useTma = tmaEpilogueOk(p) ? 1 : 0;
     a.hasSkip = (a.useTma && p.mode == EPI_D2S && p.skip) ? 1 : 0;
-    a.bn = std::min(p.npad, 256);
-    if (p.mode == EPI_D2S && a.useTma) a.bn = 128;  // 128 columns = one or two depth-to-space phases per tile
+    a.bn = pickBn(p.npad);
+    if (p.mode == EPI_D2S && a.useTma) a.bn = (p.cout % 128 == 0 || 128 % p.cout == 0) ? 128 : 64;  // whole 64-channel sub-tiles of one phase
     a.nSplit = 1;
     a.cchunks = p.cin / a.kc;
     a.kblocks = p.ntaps * a.cchunks;
@@ -783,9 +802,8 @@ void planIgemm(IgemmPlan* plan) {
 }  // namespace
 
 bool igemmSupported(const ConvParams& p) {
-    if (p.cin % 32 != 0 || p.npad % 16 != 0) return false;
-    if (p.npad > 256 && p.npad % 256 != 0) return false;
-    if (p.npad < 256 && (p.npad & (p.npad - 1)) != 0) return false;  // 16, 32, 64, 128
+    if (p.cin % 32 != 0 || p.npad % 16 != 0 || p.npad > 1024) return false;
+    if (p.npad > 32 && p.npad % 32 != 0) return false;
     if (p.ntaps < 1 || p.ntaps > 9) return false;
     return true;
 }

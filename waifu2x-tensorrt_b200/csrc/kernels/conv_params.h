@@ -15,7 +15,9 @@ enum EpiMode : int {
     EPI_D2S = 1,    // ConvTranspose 2x2 s2: column (q*cout+co) -> out[img][2y+q/2][2x+q%2][co] = lrelu(acc+bias) + skip
     EPI_UP4 = 2,    // ConvTranspose 4x4 s2 p3 head: column (q*4+co) -> out[img][2y-1+q/2][2x-1+q%2][co] = acc + bias
     EPI_FINAL = 3,  // image head: out[img][y][x][0..4) = clamp(acc + bias + skip[img][y+off][x+off], 0, 1)
+    EPI_TOIMG = 4,  // SwinUNet ToImage: column (q*4+c) -> out[img][s*y+q/2][s*x+q%2][c] = clamp(acc + bias, 0, 1), s = cout (1|2)
 };
+enum ActKind : int { ACT_LRELU = 0, ACT_GELU = 1 };  // ACT_LRELU with slope 1 == identity
 
 struct ConvTap {
     int c0, dx, dz, dy;  // offsets along (c, x, z, y) of the 5-D view
@@ -38,6 +40,7 @@ struct ConvParams {
     // epilogue
     int mode;
     float slope;  // LeakyReLU negative slope; 1.0f = linear
+    int act;      // ActKind (EPI_STORE only)
     __half* out;
     int out_h, out_w, out_c;
     int cout;  // EPI_STORE: channels stored (4 or a multiple of 8); EPI_D2S: channels per phase
@@ -52,6 +55,7 @@ struct ConvParams {
 #ifdef __CUDACC__
 
 __device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.f ? v : v * slope; }
+__device__ __forceinline__ float geluErf(float v) { return 0.5f * v * (1.f + erff(v * 0.70710678118654752f)); }  // nn.GELU()
 
 struct alignas(16) Half8 { __half2 a, b, c, d; };
 struct alignas(8) Half4 { __half2 a, b; };
@@ -62,8 +66,22 @@ __device__ __forceinline__ void conv_epilogue8(const ConvParams& p, int img, int
     float r[8];
     if (p.mode == EPI_STORE) {
         if (j0 >= p.cout) return;
+        if (p.act == ACT_GELU) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) r[i] = lrelu(v[i] + __ldg(p.bias + j0 + i), p.slope);
+            for (int i = 0; i < 8; ++i) r[i] = geluErf(v[i] + __ldg(p.bias + j0 + i));
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) r[i] = lrelu(v[i] + __ldg(p.bias + j0 + i), p.slope);
+        }
+        if (p.skip && p.cout - j0 >= 8) {  // residual add (token-wise Linear + skip of the same geometry)
+            const Half8 sv = *reinterpret_cast<const Half8*>(
+                p.skip + (((long long)img * p.skip_h + y + p.skip_off) * p.skip_w + x + p.skip_off) * p.skip_c + j0);
+            float2 t;
+            t = __half22float2(sv.a); r[0] += t.x; r[1] += t.y;
+            t = __half22float2(sv.b); r[2] += t.x; r[3] += t.y;
+            t = __half22float2(sv.c); r[4] += t.x; r[5] += t.y;
+            t = __half22float2(sv.d); r[6] += t.x; r[7] += t.y;
+        }
         __half* o = p.out + (((long long)img * p.out_h + y) * p.out_w + x) * p.out_c + j0;
         if (p.cout - j0 >= 8) {
             Half8 h{__floats2half2_rn(r[0], r[1]), __floats2half2_rn(r[2], r[3]), __floats2half2_rn(r[4], r[5]),
@@ -111,6 +129,20 @@ __device__ __forceinline__ void conv_epilogue8(const ConvParams& p, int img, int
                     __floats2half2_rn(vv[2] + __ldg(bb + 2), vv[3] + __ldg(bb + 3))};
             *reinterpret_cast<Half4*>(p.out + (((long long)img * p.out_h + oy) * p.out_w + ox) * p.out_c) = h;
         }
+    } else if (p.mode == EPI_TOIMG) {
+        const int s = p.cout;  // pixel-shuffle factor
+        if (j0 >= 4 * s * s) return;
+#pragma unroll
+        for (int hsel = 0; hsel < 2; ++hsel) {
+            const int q = (j0 >> 2) + hsel;
+            if (q >= s * s) continue;
+            const int oy = s * y + (q >> 1), ox = s * x + (q & 1);
+            const float* vv = v + 4 * hsel;
+            const float* bb = p.bias + j0 + 4 * hsel;
+            Half4 h{__floats2half2_rn(fminf(fmaxf(vv[0] + __ldg(bb + 0), 0.f), 1.f), fminf(fmaxf(vv[1] + __ldg(bb + 1), 0.f), 1.f)),
+                    __floats2half2_rn(fminf(fmaxf(vv[2] + __ldg(bb + 2), 0.f), 1.f), 0.f)};
+            *reinterpret_cast<Half4*>(p.out + (((long long)img * p.out_h + oy) * p.out_w + ox) * p.out_c) = h;
+        }
     } else {  // EPI_FINAL
         if (j0 != 0) return;
         const Half4 sv = preSkip ? *preSkip : *reinterpret_cast<const Half4*>(
@@ -138,6 +170,11 @@ bool igemmSupported(const ConvParams& p);
 const char* igemmDescribe(const IgemmPlan* plan, char* buf, int cap);
 int igemmSeSlots(const IgemmPlan* plan);  // partial-sum slots per image when ConvParams::se_sum is set (0 = unsupported)
 int probeUmma(int mode, int pitch, float* err9);
+
+// SwinUNet token kernels (kernels/swin.cu)
+void launchLayerNorm(const __half* x, __half* y, long long tokens, int c, const float* gamma, const float* beta, float eps, cudaStream_t s);
+void launchWindowAttention(const __half* qkv, __half* out, int n, int h, int w, int c, int heads, int window, int shift,
+                           const float* relpos, cudaStream_t s);
 
 // squeeze/excite
 void launchSeSqueeze(const __half* x, int n, int h, int w, int c, float* partial, int nblk, cudaStream_t s);

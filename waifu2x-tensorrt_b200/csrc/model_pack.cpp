@@ -180,16 +180,19 @@ OnnxNode parseNode(Span s, std::vector<OnnxTensor>& constants) {
         std::string an;
         std::vector<int64_t> ints;
         Span tens{nullptr, 0};
+        float fval = 0.f;
         Reader ar(a);
         while (!ar.done()) {
             Field f = ar.next();
             if (f.id == 1) an = str(f.bytes);
+            else if (f.id == 2 && f.wt == 5) { uint32_t u = (uint32_t)f.v; std::memcpy(&fval, &u, 4); }
             else if (f.id == 8) readInts(f, ints);
             else if (f.id == 5 && f.wt == 2) tens = f.bytes;
         }
         if (an == "kernel_shape") n.kernel_shape = ints;
         else if (an == "strides") n.strides = ints;
         else if (an == "pads") n.pads = ints;
+        else if (an == "epsilon") n.epsilon = fval;
         else if (an == "value" && n.op == "Constant" && tens.p && !n.outputs.empty()) {
             OnnxTensor t = parseTensor(tens);
             t.name = n.outputs[0];
@@ -267,17 +270,17 @@ inline float W4(const OnnxTensor* t, int a, int b, int c, int d) {
     return t->data[(((size_t)a * s[1] + b) * s[2] + c) * s[3] + d];
 }
 
-PackedLayer packLayer(const ConvNode& c) {
+PackedLayer packLayer(const ConvNode& c, int cinStore = 0, int npadTo = 0) {
     PackedLayer L;
     L.name = c.name;
     L.cout = (uint32_t)c.cout;
-    const int cinp = c.cin < 8 ? 4 : c.cin;  // RGB first layers are stored with 4 channels
+    const int cinp = cinStore > 0 ? cinStore : (c.cin < 8 ? 4 : c.cin);  // RGB first layers are stored with 4 channels
     if (cinp < c.cin || (cinp % 4)) throw Error("pack: unsupported cin in " + c.name);
     L.cin = (uint32_t)cinp;
     auto bias = [&](int co) { return c.b ? c.b->data[(size_t)co] : 0.0f; };
     if (!c.transpose && c.kh == 3 && c.kw == 3 && c.stride == 1 && c.pad == 0) {
         L.kind = L_CONV3; L.taps = 9;
-        L.npad = (uint32_t)((c.cout + 15) / 16 * 16);
+        L.npad = (uint32_t)(npadTo > 0 ? npadTo : (c.cout + 15) / 16 * 16);
         L.ktot = 9 * L.cin;
         L.w.assign((size_t)L.npad * L.ktot, 0);
         L.bias.assign(L.npad, 0.f);
@@ -341,9 +344,195 @@ PackedLayer packLayer(const ConvNode& c) {
 }
 
 struct Expect { uint32_t kind; int cin, cout; bool se; };
+
+// ---- SwinUNet: weight-bearing nodes in graph order -> typed records ------------------------------------------------
+PackedLayer packLinear(const std::string& name, const OnnxTensor* w, const OnnxTensor* b, uint32_t kind, int cout4 = 0, int upscale = 0) {
+    // ONNX MatMul weight is [K, N] (torch weight transposed)
+    if (!w || w->dims.size() != 2) throw Error("pack: MatMul weight of '" + name + "' is not a 2-d initializer");
+    const int K = (int)w->dims[0], N = (int)w->dims[1];
+    if ((size_t)K * N != w->data.size()) throw Error("pack: MatMul weight of '" + name + "' has no float data");
+    if (K % 32) throw Error("pack: linear '" + name + "' needs K % 32 == 0");
+    PackedLayer L;
+    L.name = name;
+    L.kind = kind;
+    L.cin = (uint32_t)K; L.ktot = (uint32_t)K; L.taps = 1;
+    auto W = [&](int k, int n) { return w->data[(size_t)k * N + n]; };
+    auto B = [&](int n) { return b ? b->data[(size_t)n] : 0.f; };
+    if (kind == L_LINEAR) {
+        if (N % 16) throw Error("pack: linear '" + name + "' needs N % 16 == 0");
+        L.cout = (uint32_t)N; L.npad = (uint32_t)N;
+        L.w.assign((size_t)N * K, 0); L.bias.assign(N, 0.f);
+        for (int n = 0; n < N; ++n) {
+            L.bias[n] = B(n);
+            for (int k = 0; k < K; ++k) L.w[(size_t)n * K + k] = floatToHalfBits(W(k, n));
+        }
+    } else if (kind == L_UPLIN) {  // pixel_shuffle(2): torch channel index c*4 + i*2 + j  ->  row (i*2+j)*cout + c
+        if (N % 4 || (N / 4) % 8) throw Error("pack: PatchUp '" + name + "' has an unsupported width");
+        const int cout = N / 4;
+        L.cout = (uint32_t)cout; L.npad = (uint32_t)N;
+        L.w.assign((size_t)N * K, 0); L.bias.assign(N, 0.f);
+        for (int q = 0; q < 4; ++q)
+            for (int c = 0; c < cout; ++c) {
+                const int src = c * 4 + q, dst = q * cout + c;
+                L.bias[dst] = B(src);
+                for (int k = 0; k < K; ++k) L.w[(size_t)dst * K + k] = floatToHalfBits(W(k, src));
+            }
+    } else {  // L_TOIMG: N = 3*s*s -> 16 rows, row (i*2+j)*4 + c  (s = 1: row c)
+        const int s = upscale;
+        if (N != 3 * s * s || (s != 1 && s != 2)) throw Error("pack: ToImage '" + name + "' has an unsupported width");
+        L.cout = 3; L.npad = 16; L.upscale = (uint32_t)s;
+        L.w.assign((size_t)16 * K, 0); L.bias.assign(16, 0.f);
+        for (int c = 0; c < 3; ++c)
+            for (int q = 0; q < s * s; ++q) {
+                const int src = c * s * s + q, dst = q * 4 + c;
+                L.bias[dst] = B(src);
+                for (int k = 0; k < K; ++k) L.w[(size_t)dst * K + k] = floatToHalfBits(W(k, src));
+            }
+    }
+    (void)cout4;
+    return L;
+}
+
+PackedModel packSwin(const OnnxGraph& g, int precision) {
+    PackedModel m;
+    m.precision = (uint32_t)precision;
+    m.arch = ARCH_SWINUNET;
+    // pass 1: collect records in node order
+    struct Rec { int type; ConvNode conv; const OnnxTensor *a = nullptr, *b = nullptr; std::string name; float eps = 1e-5f; };
+    enum { R_CONV, R_LN, R_LIN, R_ATTN };
+    std::vector<Rec> recs;
+    std::vector<ConvNode> convs = collectConvs(g);
+    size_t ci = 0;
+    int pendingLin = -1;
+    std::string pendingOut;
+    for (const auto& n : g.nodes) {
+        if (n.op == "Conv" || n.op == "ConvTranspose") {
+            Rec r; r.type = R_CONV; r.conv = convs.at(ci++); r.name = n.name;
+            recs.push_back(r);
+        } else if (n.op == "LayerNormalization") {
+            if (n.inputs.size() < 3) throw Error("pack: LayerNormalization without scale/bias");
+            Rec r; r.type = R_LN; r.a = g.find(n.inputs[1]); r.b = g.find(n.inputs[2]); r.name = n.name; r.eps = n.epsilon;
+            if (!r.a || !r.b) throw Error("pack: LayerNormalization parameters are not initializers");
+            recs.push_back(r);
+        } else if (n.op == "MatMul" && n.inputs.size() == 2) {
+            const OnnxTensor* w = g.find(n.inputs[1]);
+            if (w && w->dims.size() == 2) {
+                Rec r; r.type = R_LIN; r.a = w; r.name = n.name;
+                recs.push_back(r);
+                pendingLin = (int)recs.size() - 1;
+                pendingOut = n.outputs.empty() ? "" : n.outputs[0];
+            }
+        } else if (n.op == "Add" && n.inputs.size() == 2) {
+            const OnnxTensor* t = g.find(n.inputs[1]);
+            const std::string other = n.inputs[0];
+            if (!t) { t = g.find(n.inputs[0]); }
+            if (!t) continue;
+            if (t->dims.size() == 1 && pendingLin >= 0 && (n.inputs[0] == pendingOut || n.inputs[1] == pendingOut)) {
+                recs[pendingLin].b = t;  // bias of the preceding MatMul
+                pendingLin = -1;
+            } else if (t->dims.size() >= 3 && t->dims[t->dims.size() - 1] == t->dims[t->dims.size() - 2]) {
+                Rec r; r.type = R_ATTN; r.a = t; r.name = n.name;
+                recs.push_back(r);
+            }
+        }
+    }
+    // pass 2: template  conv conv | blocks*L | down | blocks*L | down | blocks*3L | up | blocks*L | up | blocks*L | [up] | to_image
+    size_t p = 0;
+    auto need = [&](int type, const char* what) -> const Rec& {
+        if (p >= recs.size() || recs[p].type != type) throw Error(std::string("pack: swin_unet template mismatch, expected ") + what + " at record " + std::to_string(p));
+        return recs[p++];
+    };
+    const Rec& c0 = need(R_CONV, "patch conv 0");
+    const Rec& c1 = need(R_CONV, "patch conv 1");
+    if (c0.conv.cin != 3 || c0.conv.kh != 3 || c1.conv.kh != 3 || c1.conv.cin != c0.conv.cout || c0.conv.cout > 64 || c1.conv.cout % 32)
+        throw Error("pack: unexpected swin_unet patch embedding");
+    const int C = c1.conv.cout;
+    m.dim = (uint32_t)C;
+    m.layers.push_back(packLayer(c0.conv, 0, 64));   // 3 -> 64 stored channels (zero weights above cout)
+    m.layers.push_back(packLayer(c1.conv, 64, 0));   // 64 stored -> C
+    auto block = [&](int dim) {
+        const Rec& n1 = need(R_LN, "norm1");
+        const Rec& qkv = need(R_LIN, "qkv");
+        const Rec& at = need(R_ATTN, "relative position bias");
+        const Rec& pr = need(R_LIN, "proj");
+        const Rec& n2 = need(R_LN, "norm2");
+        const Rec& f1 = need(R_LIN, "mlp fc1");
+        const Rec& f2 = need(R_LIN, "mlp fc2");
+        auto ln = [&](const Rec& r) {
+            if ((int)r.a->data.size() != dim || (int)r.b->data.size() != dim) throw Error("pack: LayerNorm width mismatch in " + r.name);
+            PackedLayer L; L.name = r.name; L.kind = L_LN; L.cin = L.cout = (uint32_t)dim; L.eps = r.eps; L.gamma = r.a->data; L.beta = r.b->data;
+            return L;
+        };
+        m.layers.push_back(ln(n1));
+        PackedLayer q = packLinear(qkv.name, qkv.a, qkv.b, L_LINEAR);
+        if ((int)q.cin != dim || (int)q.cout != 3 * dim) throw Error("pack: qkv shape mismatch in " + qkv.name);
+        m.layers.push_back(q);
+        {
+            const auto& d = at.a->dims;
+            const int nn = (int)d[d.size() - 1], heads = (int)d[d.size() - 3];
+            int win = 1;
+            while (win * win < nn) ++win;
+            if (win * win != nn || dim % heads || (size_t)heads * nn * nn != at.a->data.size()) throw Error("pack: bad relative position bias in " + at.name);
+            PackedLayer L; L.name = at.name; L.kind = L_ATTN; L.cin = L.cout = (uint32_t)dim; L.heads = (uint32_t)heads; L.window = (uint32_t)win; L.relpos = at.a->data;
+            m.layers.push_back(L);
+        }
+        PackedLayer pj = packLinear(pr.name, pr.a, pr.b, L_LINEAR);
+        if ((int)pj.cin != dim || (int)pj.cout != dim) throw Error("pack: proj shape mismatch in " + pr.name);
+        m.layers.push_back(pj);
+        m.layers.push_back(ln(n2));
+        PackedLayer l1 = packLinear(f1.name, f1.a, f1.b, L_LINEAR), l2 = packLinear(f2.name, f2.a, f2.b, L_LINEAR);
+        if ((int)l1.cin != dim || l2.cin != l1.cout || (int)l2.cout != dim) throw Error("pack: mlp shape mismatch in " + f1.name);
+        m.layers.push_back(l1);
+        m.layers.push_back(l2);
+    };
+    auto blocksUntil = [&](int dim) {  // consume blocks while the next record is a LayerNorm
+        int nb = 0;
+        while (p < recs.size() && recs[p].type == R_LN) { block(dim); ++nb; }
+        if (nb == 0) throw Error("pack: swin stage without blocks");
+        return nb;
+    };
+    auto down = [&](int cin, int cout) {
+        const Rec& r = need(R_CONV, "patch down conv");
+        if (r.conv.kh != 2 || r.conv.stride != 2 || r.conv.cin != cin || r.conv.cout != cout) throw Error("pack: unexpected PatchDown " + r.name);
+        m.layers.push_back(packLayer(r.conv));
+    };
+    auto upl = [&](int cin, int cout) {
+        const Rec& r = need(R_LIN, "patch up linear");
+        PackedLayer L = packLinear(r.name, r.a, r.b, L_UPLIN);
+        if ((int)L.cin != cin || (int)L.cout != cout) throw Error("pack: unexpected PatchUp " + r.name);
+        m.layers.push_back(L);
+    };
+    blocksUntil(C);
+    down(C, 2 * C);
+    blocksUntil(2 * C);
+    down(2 * C, 2 * C);
+    blocksUntil(2 * C);
+    upl(2 * C, 2 * C);
+    blocksUntil(2 * C);
+    upl(2 * C, C);
+    blocksUntil(C);
+    // [up0] to_image
+    if (p + 2 == recs.size()) {
+        upl(C, C);
+        const Rec& r = need(R_LIN, "to_image");
+        m.layers.push_back(packLinear(r.name, r.a, r.b, L_TOIMG, 0, 2));
+        m.scale = 4;
+    } else if (p + 1 == recs.size()) {
+        const Rec& r = need(R_LIN, "to_image");
+        const int N = (int)r.a->dims[1];
+        m.scale = N == 3 ? 1 : 2;
+        m.layers.push_back(packLinear(r.name, r.a, r.b, L_TOIMG, 0, (int)m.scale));
+    } else {
+        throw Error("pack: swin_unet template mismatch at the image head");
+    }
+    m.offset = 8 * m.scale;
+    return m;
+}
 }  // namespace
 
 PackedModel packFromOnnx(const OnnxGraph& g, int precision) {
+    for (const auto& n : g.nodes)
+        if (n.op == "LayerNormalization") return packSwin(g, precision);
     std::vector<ConvNode> convs = collectConvs(g);
     PackedModel m;
     m.precision = (uint32_t)precision;
@@ -379,7 +568,7 @@ PackedModel packFromOnnx(const OnnxGraph& g, int precision) {
         {L_CONV3, 64, 64, false}, {L_CONV3, 64, 3, false}};
     if (m.layers.size() != tmpl.size())
         throw Error("pack: graph has " + std::to_string(m.layers.size()) + " convolution layers; the cunet template needs " +
-                    std::to_string(tmpl.size()) + " (swin_unet import is not available in this build)");
+                    std::to_string(tmpl.size()));
     for (size_t i = 0; i < tmpl.size(); ++i) {
         const PackedLayer& L = m.layers[i];
         if (L.kind != tmpl[i].kind || (int)L.cin != tmpl[i].cin || (int)L.cout != tmpl[i].cout || (L.se_r != 0) != tmpl[i].se)
@@ -392,7 +581,7 @@ PackedModel packFromOnnx(const OnnxGraph& g, int precision) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Flat file:  "W2XPACK1" | arch scale offset precision nlayers | per layer: header + blobs (4-byte aligned)
+// Flat file:  "W2XPACK2" | arch scale offset precision dim nlayers | per layer: header + blobs (4-byte aligned)
 // ------------------------------------------------------------------------------------------------
 namespace {
 void put32(std::vector<uint8_t>& o, uint32_t v) { for (int i = 0; i < 4; ++i) o.push_back((uint8_t)(v >> (8 * i))); }
@@ -420,23 +609,26 @@ struct In {
 
 std::vector<uint8_t> serializePack(const PackedModel& m) {
     std::vector<uint8_t> o;
-    const char magic[8] = {'W', '2', 'X', 'P', 'A', 'C', 'K', '1'};
+    const char magic[8] = {'W', '2', 'X', 'P', 'A', 'C', 'K', '2'};
     o.insert(o.end(), magic, magic + 8);
-    put32(o, m.arch); put32(o, m.scale); put32(o, m.offset); put32(o, m.precision); put32(o, (uint32_t)m.layers.size());
+    put32(o, m.arch); put32(o, m.scale); put32(o, m.offset); put32(o, m.precision); put32(o, m.dim); put32(o, (uint32_t)m.layers.size());
     for (const auto& L : m.layers) {
         std::vector<char> nm(L.name.begin(), L.name.end());
         putVec(o, nm);
         put32(o, L.kind); put32(o, L.cin); put32(o, L.cout); put32(o, L.npad); put32(o, L.ktot); put32(o, L.taps); put32(o, L.se_r);
+        put32(o, L.heads); put32(o, L.window); put32(o, L.upscale);
+        uint32_t e; std::memcpy(&e, &L.eps, 4); put32(o, e);
         putVec(o, L.w); putVec(o, L.bias); putVec(o, L.se_w1); putVec(o, L.se_b1); putVec(o, L.se_w2); putVec(o, L.se_b2);
+        putVec(o, L.gamma); putVec(o, L.beta); putVec(o, L.relpos);
     }
     return o;
 }
 
 PackedModel deserializePack(const std::vector<uint8_t>& blob) {
-    if (blob.size() < 28 || std::memcmp(blob.data(), "W2XPACK1", 8) != 0) throw Error("not a W2XPACK1 file");
+    if (blob.size() < 32 || std::memcmp(blob.data(), "W2XPACK2", 8) != 0) throw Error("not a W2XPACK2 file");
     In in{blob.data(), blob.size(), 8};
     PackedModel m;
-    m.arch = in.u32(); m.scale = in.u32(); m.offset = in.u32(); m.precision = in.u32();
+    m.arch = in.u32(); m.scale = in.u32(); m.offset = in.u32(); m.precision = in.u32(); m.dim = in.u32();
     const uint32_t nl = in.u32();
     if (nl > 4096) throw Error("pack file corrupt");
     m.layers.resize(nl);
@@ -445,7 +637,10 @@ PackedModel deserializePack(const std::vector<uint8_t>& blob) {
         in.vec(nm);
         L.name.assign(nm.begin(), nm.end());
         L.kind = in.u32(); L.cin = in.u32(); L.cout = in.u32(); L.npad = in.u32(); L.ktot = in.u32(); L.taps = in.u32(); L.se_r = in.u32();
+        L.heads = in.u32(); L.window = in.u32(); L.upscale = in.u32();
+        const uint32_t e = in.u32(); std::memcpy(&L.eps, &e, 4);
         in.vec(L.w); in.vec(L.bias); in.vec(L.se_w1); in.vec(L.se_b1); in.vec(L.se_w2); in.vec(L.se_b2);
+        in.vec(L.gamma); in.vec(L.beta); in.vec(L.relpos);
         if (L.w.size() != (size_t)L.npad * L.ktot || L.bias.size() != L.npad) throw Error("pack file: layer '" + L.name + "' has inconsistent sizes");
     }
     return m;

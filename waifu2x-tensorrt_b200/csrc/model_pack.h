@@ -20,6 +20,7 @@ struct OnnxNode {
     std::string op, name;
     std::vector<std::string> inputs, outputs;
     std::vector<int64_t> kernel_shape, strides, pads;
+    float epsilon = 1e-5f;  // LayerNormalization
 };
 struct OnnxGraph {
     std::vector<OnnxNode> nodes;
@@ -36,9 +37,15 @@ enum LayerKind : uint32_t {
     L_UP4 = 3,    // ConvTranspose 4x4 stride 2 pad 3 as a 2x2 window conv with 4 output phases:
                   //                                     B[16][4*cin],    n = (py*2+px)*4 + co,  k = (wy*2+wx)*cin + ci,
                   //                                     tap (ky,kx) = (2+py-2*wy, 2+px-2*wx)
+    // SwinUNet records
+    L_LINEAR = 4,  // token-wise Linear (ONNX MatMul [K,N] + Add):  B[N][K], bias[N]
+    L_LN = 5,      // LayerNorm over channels: gamma / beta (fp32), eps
+    L_ATTN = 6,    // window attention: relative position bias relpos[heads][n][n] (fp32), n = window^2
+    L_UPLIN = 7,   // PatchUp = Linear(cin -> 4*cout) + pixel_shuffle(2): rows permuted to n = (i*2+j)*cout + c
+    L_TOIMG = 8,   // ToImage = Linear(cin -> 3*s*s) + pixel_shuffle(s): B[16][cin], n = (i*2+j)*4 + c  (s = 1: n = c)
 };
 
-enum Arch : uint32_t { ARCH_CUNET = 1, ARCH_UPCUNET = 2 };
+enum Arch : uint32_t { ARCH_CUNET = 1, ARCH_UPCUNET = 2, ARCH_SWINUNET = 3 };
 
 struct PackedLayer {
     std::string name;
@@ -52,10 +59,15 @@ struct PackedLayer {
     std::vector<uint16_t> w;     // fp16 bits, [npad][ktot] K-major
     std::vector<float> bias;     // [npad]
     std::vector<float> se_w1, se_b1, se_w2, se_b2;  // [r][c], [r], [c][r], [c]
+    // SwinUNet
+    uint32_t heads = 0, window = 0, upscale = 0;     // L_ATTN: heads, window; L_TOIMG: pixel-shuffle factor
+    float eps = 0.f;                                 // L_LN
+    std::vector<float> gamma, beta, relpos;          // L_LN: [c], [c];  L_ATTN: [heads][n][n]
 };
 
 struct PackedModel {
     uint32_t arch = 0, scale = 0, offset = 0, precision = 1;
+    uint32_t dim = 0;  // SwinUNet base width C
     std::vector<PackedLayer> layers;
 };
 
