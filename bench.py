@@ -1,8 +1,10 @@
 #!/usr/bin/env python
 """bench.py — output Mpx/s of the tile -> model -> stitch hot path (BASELINE.json metric).
 
-Workload (config.workload): BASELINE configs[1] = cunet/art scale 2 noise 3, tileSize 256, batchSize 8, fp16, synthetic
-1920x1080 BGR frames -> 3840x2160 (60 tiles + 4 padding slots per frame).  One "step" = one frame.
+Default workload (config.workload): BASELINE configs[1] = cunet/art scale 2 noise 3, tileSize 256, batchSize 8, fp16,
+synthetic 1920x1080 BGR frames -> 3840x2160 (60 tiles + 4 padding slots per frame).  One "step" = one frame.
+`--workload swin` runs BASELINE configs[3] instead (swin_unet/art scale 4 noise 3, tile 256, batch 4: 45 tiles + 3 padding
+slots, 1920x1080 -> 7680x4320); it is an extra measurement, the driver's line is the default workload.
 
   value : whole-job output Mpx/s with the input frames already resident in HBM (w2x_render_device), CUDA events on the
           engine's stream, max over ranks.
@@ -30,8 +32,15 @@ for p in (ROOT, PKG):
     if p not in sys.path:
         sys.path.insert(0, p)
 
-FRAME_W, FRAME_H, TILE, BATCH, SCALE, BLEND = 1920, 1080, 256, 8, 2, 1.0 / 16.0
-WORKLOAD = "cunet/art scale2 noise3 tile256 batch8 fp16, synthetic 1920x1080 -> 3840x2160 frames (BASELINE configs[1])"
+FRAME_W, FRAME_H, BLEND = 1920, 1080, 1.0 / 16.0
+WORKLOADS = {
+    "cunet": dict(model="cunet/art", family="cunet", scale=2, noise=3, tile=256, batch=8, tiles=60,
+                  name="cunet/art scale2 noise3 tile256 batch8 fp16, synthetic 1920x1080 -> 3840x2160 frames (BASELINE configs[1])",
+                  cpu_crop=(640, 360), cpu_note="640x360 crop (8 tiles of 256 -> 1280x720)"),
+    "swin": dict(model="swin_unet/art", family="swin_unet", scale=4, noise=3, tile=256, batch=4, tiles=45,
+                 name="swin_unet/art scale4 noise3 tile256 batch4 fp16, synthetic 1920x1080 -> 7680x4320 frames (BASELINE configs[3])",
+                 cpu_crop=(464, 240), cpu_note="464x240 crop (2 tiles of 256 -> 1856x960)"),
+}
 METRIC, UNIT = "output Mpx/s", "Mpx/s"
 
 
@@ -51,7 +60,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -68,10 +77,10 @@ class ClockSampler:
                 self.proc.wait(timeout=2)
             except Exception:
                 self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         for r in self.rows:
             try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
             except Exception:
                 continue
             for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[3:7]):
@@ -79,18 +88,20 @@ class ClockSampler:
                     reasons.add(name)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(pw), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_oracle_sample(threads: int, repeats: int = 1):
-    """Oracle port on the host cores: a 640x360 crop of the workload's frame (8 tiles of 256 -> 1280x720 output)."""
+def cpu_oracle_sample(wl, threads: int, repeats: int = 1):
+    """Oracle port on the host cores: a crop of the workload's frame through the fp32 PyTorch model + NumPy tiling."""
     import numpy as np
     import torch
     from oracle import tiling
-    from oracle.models import make_model
+    from oracle.models import cunet_out_size, make_model, swin_out_size
     torch.set_num_threads(threads)
-    model = make_model("cunet", SCALE, 1234)
-    frame = tiling.synthetic_frame(FRAME_W, FRAME_H, 0)[:360, :640].copy()
+    model = make_model(wl["family"], wl["scale"], 1234)
+    cw, ch = wl["cpu_crop"]
+    frame = tiling.synthetic_frame(FRAME_W, FRAME_H, 0)[:ch, :cw].copy()
+    out_tile = cunet_out_size(wl["scale"], wl["tile"]) if wl["family"] == "cunet" else swin_out_size(wl["scale"], wl["tile"])
 
     def fn(x):
         with torch.no_grad():
@@ -99,27 +110,25 @@ def cpu_oracle_sample(threads: int, repeats: int = 1):
     times = []
     for _ in range(repeats):
         t0 = time.perf_counter()
-        out = tiling.render(frame, fn, TILE, 2 * TILE - 72, SCALE, BLEND, batch=1)
+        out = tiling.render(frame, fn, wl["tile"], out_tile, wl["scale"], BLEND, batch=1)
         times.append(time.perf_counter() - t0)
-    mpx = out.shape[0] * out.shape[1] / 1e6
-    return mpx, times
+    return out.shape[0] * out.shape[1] / 1e6, times
 
 
-def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+def run_reference(args, wl):
+    if int(os.environ.get("RANK", "0")) != 0:
         return
     threads = len(os.sched_getaffinity(0))
     if args.warmup > 0:
-        cpu_oracle_sample(threads, repeats=1)  # one warm-up pass at most
-    mpx, times = cpu_oracle_sample(threads, repeats=args.steps)
+        cpu_oracle_sample(wl, threads, repeats=1)  # one warm-up pass at most
+    mpx, times = cpu_oracle_sample(wl, threads, repeats=args.steps)
     total = sum(times)
     value = mpx * args.steps / total
-    sample = "640x360 crop of the 1920x1080 synthetic frame (8 tiles of 256) per step, oracle port: PyTorch fp32 CPU + NumPy tiling"
+    sample = f"{wl['cpu_note']} of the 1920x1080 synthetic frame per step, oracle port: PyTorch fp32 CPU + NumPy tiling"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1000.0 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
+        "data": "synthetic", "config": {"workload": wl["name"], "sample": sample},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -134,11 +143,13 @@ def main():
     ap.add_argument("--steps", type=int, default=24)
     ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cunet", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--layers", action="store_true", help="also print a per-layer profile to stderr")
     args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, wl)
 
     import numpy as np
     import torch
@@ -157,10 +168,11 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     w2x.lib()
+    TILE, BATCH, SCALE = wl["tile"], wl["batch"], wl["scale"]
 
     # ---- build + load through the reference-shaped API ----
     tmp = tempfile.mkdtemp(prefix=f"w2x_bench_r{rank}_")
-    _, onnx_path = __graft_entry__.make_synthetic_model(tmp, scale=SCALE, noise=3)
+    _, onnx_path = __graft_entry__.make_synthetic_model(tmp, scale=SCALE, noise=wl["noise"], model=wl["model"])
     eng = w2x.Img2Img()
     msgs = []
     eng.setMessageCallback(lambda sev, m: msgs.append((sev, m)))
@@ -192,8 +204,8 @@ def main():
     sampler = ClockSampler(local)
     sampler.start()
     launches0 = eng.launch_count
-    stage = {"unpack": 0.0, "model": 0.0, "stitch": 0.0}
     eng.timer_mark(0)
+    model_ms_sum = 0.0
     for i in range(args.steps):
         assert eng.render_device(d_in[i % n_in], FRAME_W, FRAME_H, d_out), eng.last_error
     eng.timer_mark(1)
@@ -201,10 +213,7 @@ def main():
     torch.cuda.synchronize()
     ms_total = eng.timer_elapsed_ms(0, 1)
     launches = eng.launch_count - launches0
-    # stage split of the last timed frame (events recorded inside the timed region)
-    last = eng.last_stage_ms()
-    for k in stage:
-        stage[k] = last.get(k, 0.0)
+    stage = eng.last_stage_ms()  # stage split of the last timed frame (events recorded inside the timed region)
     clocks = sampler.stop()
     if world > 1:
         t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
@@ -253,24 +262,24 @@ def main():
 
     if rank == 0:
         peaks, peak_kind = _peaks()
-        flops_frame = eng.flops_per_tile * 60  # 60 real tiles per 1080p frame (padding slots excluded)
-        model_ms = stage["model"]
+        flops_frame = eng.flops_per_tile * wl["tiles"]  # real tiles per 1080p frame (padding slots excluded)
+        model_ms = stage.get("model", 0.0)
         achieved = flops_frame / (model_ms / 1e3) / 1e12 if model_ms > 0 else None
         peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get("model_stage_dram_bytes_per_frame")
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(args.workload)
         except Exception:
             pass
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "fp16 (fp32 accumulate)", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_rank": args.steps, "sharding": "frames round-robin, one engine per GPU, no collective",
+            "config": {"workload": wl["name"], "frames_per_rank": args.steps, "sharding": "frames round-robin, one engine per GPU, no collective",
                        "l2": "each step streams >1 GB of activations + 4 rotating input frames (> 126 MB L2)", "weights": "seeded synthetic (seed 1234)"},
             "fps": world * args.steps / (ms_max / 1e3),
-            "stage_ms_last_frame": stage,
-            "roofline": {"bound": "tensor", "kernel": "model stage (igemm_kernel tcgen05 convs + first-layer + SE kernels)",
+            "stage_ms_last_frame": {k: stage.get(k, 0.0) for k in ("unpack", "model", "stitch")},
+            "roofline": {"bound": "tensor", "kernel": "model stage (tcgen05 conv3x3_patch_kernel / igemm_kernel dominate; + first-layer, SE, LN, attention kernels)",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
                          "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peak_kind})", "flops_per_frame": flops_frame, "traffic": traffic},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
@@ -280,12 +289,12 @@ def main():
         }
         if not args.no_cpu_baseline:
             threads = len(os.sched_getaffinity(0))
-            mpx, times = cpu_oracle_sample(threads, repeats=1)
+            mpx, times = cpu_oracle_sample(wl, threads, repeats=1)
             line["cpu_baseline"] = {"value": mpx / times[0], "unit": UNIT, "cores": threads, "kind": "port",
-                                    "sample": "one 640x360 crop (8 tiles of 256 -> 1280x720), PyTorch fp32 CPU oracle + NumPy tiling, 1 pass"}
+                                    "sample": f"one {wl['cpu_note']}, PyTorch fp32 CPU oracle + NumPy tiling, 1 pass"}
         if args.layers:
             for name, ms, fl in eng.profile_layers(3):
-                print(f"  {name:28s} {ms:8.3f} ms  {fl / ms / 1e9 if ms > 0 else 0:9.1f} TFLOP/s", file=sys.stderr)
+                print(f"  {name:44s} {ms:8.3f} ms  {fl / ms / 1e9 if ms > 0 else 0:9.1f} TFLOP/s", file=sys.stderr)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

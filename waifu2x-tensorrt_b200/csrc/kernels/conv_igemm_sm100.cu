@@ -51,6 +51,9 @@ struct ConvArgs {
     int useTma, nsub, nbuf, hasSkip;
     uint32_t stageStride, wBytes, stagingBytes;
     int nSplit;
+    int staged;                 // EPI_K_STAGED: generic-proxy staging + coalesced copy-out (any N, residual, GELU)
+    uint32_t stagedPitch, stagedBuf;
+    uint32_t headerBytes;       // barriers + TMEM slot (1 KB) | bias[npad] fp32 (1 KB multiple) | SE scratch (1 KB)
 };
 
 struct IgemmPlan {
@@ -65,13 +68,12 @@ namespace {
 constexpr int kEpiWarps = 8;                       // two warps per TMEM lane quarter, splitting the columns
 constexpr int kThreads = 64 + 32 * kEpiWarps;      // warp 0 = TMA producer, warp 1 = MMA issuer, warps 2.. = epilogue
 constexpr int kEpiThreads = 32 * kEpiWarps;
-constexpr int kHeaderBytes = 6144;                 // barriers + TMEM slot (1 KB) | bias[npad <= 1024] fp32 (4 KB) | SE scratch (1 KB)
 constexpr int kPatchW = 10, kPatchH = 18;
 
 // header layout (byte offsets from the 1024-aligned smem base)
-constexpr uint32_t kOffFull = 0, kOffEmpty = 64, kOffTFull = 128, kOffTEmpty = 144, kOffSkip = 160, kOffW = 184, kOffSlot = 256, kOffBias = 1024, kOffSeScratch = 5120;
+constexpr uint32_t kOffFull = 0, kOffEmpty = 64, kOffTFull = 128, kOffTEmpty = 144, kOffSkip = 160, kOffW = 184, kOffSlot = 256, kOffBias = 1024;
 
-enum EpiKind { EPI_K_DIRECT = 0, EPI_K_TMA = 1, EPI_K_TMA_SKIP = 2 };
+enum EpiKind { EPI_K_DIRECT = 0, EPI_K_TMA = 1, EPI_K_TMA_SKIP = 2, EPI_K_STAGED = 3 };
 
 struct TileCoord {
     int img, y0, x0, n0;
@@ -124,8 +126,9 @@ __device__ __forceinline__ void subTileCoords(const ConvArgs& a, const TileCoord
 // Warp w may only touch TMEM lanes 32*(w%4)..+31; the two warps of a lane quarter split the accumulator columns.
 template <int kEpi>
 __device__ __forceinline__ void epilogueWarps(const ConvArgs& a, uint32_t base, uint32_t tmemBase, int nMine, int first, int step, int nBase) {
-    constexpr bool kTma = kEpi != EPI_K_DIRECT;
+    constexpr bool kTma = kEpi == EPI_K_TMA || kEpi == EPI_K_TMA_SKIP;
     constexpr bool kSkip = kEpi == EPI_K_TMA_SKIP;
+    constexpr bool kStaged = kEpi == EPI_K_STAGED;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int quarter = warp & 3;
     const int half = (warp - 2) >> 2;
@@ -133,7 +136,7 @@ __device__ __forceinline__ void epilogueWarps(const ConvArgs& a, uint32_t base, 
     const int m = quarter * 32 + lane;
     const int yy = m >> a.bwShift, xx = m & (a.bw - 1);
     const uint32_t barTFull = base + kOffTFull, barTEmpty = base + kOffTEmpty, barSkip = base + kOffSkip;
-    const uint32_t staging = base + kHeaderBytes;
+    const uint32_t staging = base + a.headerBytes;
     const uint32_t bufBytes = (uint32_t)a.nsub * 16384u;
     const uint32_t biasS = base + kOffBias;
     const int skipHalf = a.p.skip_off >> 1;
@@ -175,7 +178,7 @@ __device__ __forceinline__ void epilogueWarps(const ConvArgs& a, uint32_t base, 
     // image boundary (uniform across the epilogue threads): combine the row groups in a fixed order, one slot per CTA
     auto seFlush = [&]() {
         if (seImg < 0) return;
-        float* scratch = reinterpret_cast<float*>(__cvta_shared_to_generic((size_t)(base + kOffSeScratch)));
+        float* scratch = reinterpret_cast<float*>(__cvta_shared_to_generic((size_t)(base + a.headerBytes - 1024u)));
         scratch[et] = seAcc;
         namedBarSync(2, kEpiThreads);
         if (seG == 0) {
@@ -241,6 +244,39 @@ __device__ __forceinline__ void epilogueWarps(const ConvArgs& a, uint32_t base, 
                     stsV4(addr, o);
                 }
             }
+        } else if (kStaged) {
+            // token-wise Linear layers (any N % 32 == 0): act(acc + bias) -> padded smem rows -> coalesced 16-byte copy-out
+            // (+ residual read at the same address, so the residual stream can be updated in place)
+            const uint32_t sbuf = staging + (uint32_t)(k & (a.nbuf - 1)) * a.stagedBuf;
+            int c0 = colBegin;
+            while (c0 < colBegin + colsPerWarp) {
+                const bool wide = c0 + 32 <= colBegin + colsPerWarp;
+                if (wide) tmemLd32(taddr + (uint32_t)c0, r);
+                else tmemLd16(taddr + (uint32_t)c0, r);
+                tmemLdWait();
+                const int nq = wide ? 4 : 2;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (q < nq) {
+                        const int j0 = c0 + 8 * q;
+                        const uint4 b0 = ldsV4(biasS + (uint32_t)(tc.n0 + j0) * 4u), b1 = ldsV4(biasS + (uint32_t)(tc.n0 + j0 + 4) * 4u);
+                        const float bias[8] = {__uint_as_float(b0.x), __uint_as_float(b0.y), __uint_as_float(b0.z), __uint_as_float(b0.w),
+                                               __uint_as_float(b1.x), __uint_as_float(b1.y), __uint_as_float(b1.z), __uint_as_float(b1.w)};
+                        float v[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float tv = __uint_as_float(r[8 * q + i]) + bias[i];
+                            v[i] = a.p.act == ACT_GELU ? geluErf(tv) : fmaxf(tv, tv * a.p.slope);
+                        }
+                        uint4 o;
+                        __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) oh[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+                        stsV4(sbuf + (uint32_t)m * a.stagedPitch + (uint32_t)j0 * 2u, o);
+                    }
+                }
+                c0 += wide ? 32 : 16;
+            }
         } else if (active) {
             const int y = py, x = px;
             const bool valid = pvalid;
@@ -278,6 +314,31 @@ __device__ __forceinline__ void epilogueWarps(const ConvArgs& a, uint32_t base, 
         __syncwarp();
         if (lane == 0) mbarArrive(barTEmpty + 8u * acc);  // accumulator buffer may be overwritten by the next-but-one tile
         if (++acc == 2) { acc = 0; accPhase ^= 1u; }
+        if (kStaged) {
+            namedBarSync(1, kEpiThreads);  // the tile is complete in smem (and, two tiles later, this buffer is free again)
+            const uint32_t sbuf = staging + (uint32_t)(k & (a.nbuf - 1)) * a.stagedBuf;
+            const int chunksPerRow = a.bn >> 3;
+            const int et2 = threadIdx.x - 64;
+            for (int idx = et2; idx < 128 * chunksPerRow; idx += kEpiThreads) {
+                const int row = idx / chunksPerRow, cc = idx - row * chunksPerRow;
+                const int yy2 = tc.y0 + (row >> a.bwShift), xx2 = tc.x0 + (row & (a.bw - 1));
+                if (yy2 < a.p.gy && xx2 < a.p.gx) {
+                    uint4 v = ldsV4(sbuf + (uint32_t)row * a.stagedPitch + (uint32_t)cc * 16u);
+                    const long long off = (((long long)tc.img * a.p.out_h + yy2) * a.p.out_w + xx2) * a.p.out_c + tc.n0 + cc * 8;
+                    if (a.p.skip) {
+                        const uint4 sv = *reinterpret_cast<const uint4*>(a.p.skip + off);
+                        __half2* vh = reinterpret_cast<__half2*>(&v);
+                        const __half2* sh = reinterpret_cast<const __half2*>(&sv);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float2 x0 = __half22float2(vh[i]), x1 = __half22float2(sh[i]);
+                            vh[i] = __floats2half2_rn(x0.x + x1.x, x0.y + x1.y);
+                        }
+                    }
+                    *reinterpret_cast<uint4*>(a.p.out + off) = v;
+                }
+            }
+        }
         if (kTma) {
             fenceProxyAsync();
             namedBarSync(1, kEpiThreads);
@@ -357,7 +418,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     setupCommon(a, base, sm, warp);
     const uint32_t tmemBase = *reinterpret_cast<volatile uint32_t*>(sm + kOffSlot);
-    const uint32_t stage0 = base + kHeaderBytes + a.stagingBytes;
+    const uint32_t stage0 = base + a.headerBytes + a.stagingBytes;
     const uint32_t stageBytes = a.bytesA + a.bytesB;
     const uint32_t barFull = base + kOffFull, barEmpty = base + kOffEmpty, barTFull = base + kOffTFull, barTEmpty = base + kOffTEmpty;
     const int first = blockIdx.x, step = gridDim.x;
@@ -434,7 +495,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_patch_kernel(const __grid
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     setupCommon(a, base, sm, warp);
     const uint32_t tmemBase = *reinterpret_cast<volatile uint32_t*>(sm + kOffSlot);
-    const uint32_t wBase = base + kHeaderBytes + a.stagingBytes;
+    const uint32_t wBase = base + a.headerBytes + a.stagingBytes;
     const uint32_t stage0 = wBase + a.wBytes;
     const uint32_t barFull = base + kOffFull, barEmpty = base + kOffEmpty, barTFull = base + kOffTFull, barTEmpty = base + kOffTEmpty;
     const uint32_t barW = base + kOffW;
@@ -690,9 +751,12 @@ bool wantsPatchKernel(const ConvParams& p) {
     return true;
 }
 
+uint32_t headerBytesFor(int npad) { return 1024u + (((uint32_t)npad * 4u + 1023u) & ~1023u) + 1024u; }
+
 void planPatch(IgemmPlan* plan) {
     ConvArgs& a = plan->args;
     const ConvParams& p = a.p;
+    a.headerBytes = headerBytesFor(p.npad);
     plan->patch = true;
     a.kc = p.cin % 64 == 0 ? 64 : 32;
     const bool sw128 = a.kc == 64;
@@ -713,7 +777,7 @@ void planPatch(IgemmPlan* plan) {
     a.wBytes = 9u * a.cchunks * a.bn * a.kc * 2u;
     a.bytesA = (uint32_t)(kPatchW * kPatchH) * a.kc * 2u;     // 23040 (kc=64) / 11520 (kc=32)
     a.stageStride = (a.bytesA + 1023u) & ~1023u;
-    const size_t fixed = 1024 + kHeaderBytes + a.stagingBytes + a.wBytes;
+    const size_t fixed = 1024 + a.headerBytes + a.stagingBytes + a.wBytes;
     if (fixed + 2 * (size_t)a.stageStride > kSmemLimit) throw Error("conv3x3 patch kernel: weights do not fit in shared memory");
     a.stages = (int)std::min<size_t>(8, (kSmemLimit - fixed) / a.stageStride);
     uint32_t cols = 32;
@@ -742,6 +806,7 @@ void planPatch(IgemmPlan* plan) {
 void planIgemm(IgemmPlan* plan) {
     ConvArgs& a = plan->args;
     const ConvParams& p = a.p;
+    a.headerBytes = headerBytesFor(p.npad);
     plan->patch = false;
     a.kc = (p.cin % 64 == 0) ? 64 : 32;
     a.useTma = tmaEpilogueOk(p) ? 1 : 0;
@@ -767,9 +832,18 @@ void planIgemm(IgemmPlan* plan) {
     a.bytesB = (uint32_t)a.bn * a.kc * 2u;
     a.nsub = a.useTma ? a.bn / 64 : 0;
     const size_t stageBytes = a.bytesA + a.bytesB;
-    const size_t avail = kSmemLimit - 1024 - kHeaderBytes;
+    const size_t avail = kSmemLimit - 1024 - a.headerBytes;
     a.nbuf = 1;
     a.stagingBytes = 0;
+    // token-wise layers whose shape rules out the TMA epilogue: coalescing staged epilogue
+    a.staged = (!a.useTma && p.mode == EPI_STORE && a.bn >= 32 && p.cout == p.npad && p.out_c == p.npad &&
+                (!p.skip || (p.skip_off == 0 && p.skip_c == p.out_c && p.skip_h == p.out_h && p.skip_w == p.out_w))) ? 1 : 0;
+    if (a.staged) {
+        a.stagedPitch = (uint32_t)a.bn * 2u + 16u;
+        a.stagedBuf = (128u * a.stagedPitch + 1023u) & ~1023u;
+        a.nbuf = 2;
+        a.stagingBytes = 2 * a.stagedBuf;
+    }
     if (a.useTma) {
         const size_t buf = (size_t)a.nsub * 16384;
         int nbuf = a.hasSkip ? 3 : 2;
@@ -796,7 +870,7 @@ void planIgemm(IgemmPlan* plan) {
     encodeWeights(&a.tmB, p, a.kc, a.bn, sw128);
     if (a.useTma) encodeOutMaps(a);
     plan->grid = std::min(a.totalTiles, numSMs());
-    plan->smem = 1024 + kHeaderBytes + a.stagingBytes + (size_t)a.stages * stageBytes;
+    plan->smem = 1024 + a.headerBytes + a.stagingBytes + (size_t)a.stages * stageBytes;
 }
 
 }  // namespace
@@ -826,6 +900,7 @@ IgemmPlan* igemmCreatePlan(const ConvParams& p) {
             checkCuda(cudaFuncSetAttribute(igemm_kernel<EPI_K_DIRECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
             checkCuda(cudaFuncSetAttribute(igemm_kernel<EPI_K_TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
             checkCuda(cudaFuncSetAttribute(igemm_kernel<EPI_K_TMA_SKIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+            checkCuda(cudaFuncSetAttribute(igemm_kernel<EPI_K_STAGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
             checkCuda(cudaFuncSetAttribute(conv3x3_patch_kernel<EPI_K_DIRECT, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
             checkCuda(cudaFuncSetAttribute(conv3x3_patch_kernel<EPI_K_TMA, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
             checkCuda(cudaFuncSetAttribute(conv3x3_patch_kernel<EPI_K_DIRECT, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
@@ -849,14 +924,15 @@ int igemmSeSlots(const IgemmPlan* plan) {
 
 const char* igemmDescribe(const IgemmPlan* plan, char* buf, int cap) {
     const ConvArgs& a = plan->args;
-    std::snprintf(buf, cap, "%s bn=%d kc=%d tile=%dx%d stages=%d nbuf=%d tma=%d skip=%d split=%d grid=%d smem=%zu", plan->patch ? "patch3x3" : "igemm",
-                  a.bn, a.kc, a.bh, a.bw, a.stages, a.nbuf, a.useTma, a.hasSkip, a.nSplit, plan->grid, plan->smem);
+    std::snprintf(buf, cap, "%s bn=%d kc=%d tile=%dx%d stages=%d nbuf=%d tma=%d skip=%d staged=%d split=%d grid=%d smem=%zu", plan->patch ? "patch3x3" : "igemm",
+                  a.bn, a.kc, a.bh, a.bw, a.stages, a.nbuf, a.useTma, a.hasSkip, a.staged, a.nSplit, plan->grid, plan->smem);
     return buf;
 }
 
 void igemmLaunch(const IgemmPlan* plan, cudaStream_t s, __half* outOverride) {
     if (plan->grid <= 0) return;
     const bool redirect = outOverride && outOverride != plan->args.p.out;
+    if (redirect && plan->args.staged) throw Error("igemm: output redirection is not available for staged-epilogue layers");
     if (redirect && plan->args.useTma) throw Error("igemm: output redirection is not available for TMA-store layers");
     ConvArgs local;
     const ConvArgs* a = &plan->args;
@@ -876,6 +952,7 @@ void igemmLaunch(const IgemmPlan* plan, cudaStream_t s, __half* outOverride) {
     } else {
         if (a->hasSkip) igemm_kernel<EPI_K_TMA_SKIP><<<plan->grid, kThreads, plan->smem, s>>>(*a);
         else if (a->useTma) igemm_kernel<EPI_K_TMA><<<plan->grid, kThreads, plan->smem, s>>>(*a);
+        else if (a->staged) igemm_kernel<EPI_K_STAGED><<<plan->grid, kThreads, plan->smem, s>>>(*a);
         else igemm_kernel<EPI_K_DIRECT><<<plan->grid, kThreads, plan->smem, s>>>(*a);
     }
 }

@@ -60,16 +60,28 @@ void launchLayerNorm(const __half* x, __half* y, long long tokens, int c, const 
     layernorm_kernel<<<(unsigned)blocks, 32 * warpsPerBlock, 0, s>>>(x, y, tokens, c, gamma, beta, eps);
 }
 
-// One warp per (window, head).  HD = head dim (16 or 32), window = 6 (n = 36 tokens).
+// One warp per (window, head); window = 6 (36 tokens).  Both GEMMs of the attention run on warp-level mma.sync
+// (m16n8k16, fp16 in / fp32 accumulate): S = Q K^T as 3 row tiles x 5 column tiles (36 -> 48 x 40, padding masked), the
+// softmax works on the accumulator layout (quad shuffles), and the probabilities are re-used in registers as the A operand
+// of O = P V (the accumulator layout of two adjacent 8-column tiles IS the A fragment of one k-step).  Q/K/V fragments are
+// loaded straight from the [token][3C] tensor (4-byte loads, L1-resident): no shared-memory staging, no re-layout.
+__device__ __forceinline__ void mma16816h(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t packHalf2(float a, float b) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+
 template <int HD>
 __global__ void __launch_bounds__(128) window_attention_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int n, int h, int w, int c,
                                                                int heads, int shift, const float* __restrict__ relpos, long long totalUnits) {
-    constexpr int WIN = 6, NT = 36;
-    __shared__ float sk[4][NT][HD + 1];
-    __shared__ float sv[4][NT][HD + 1];
-    __shared__ int stok[4][NT];   // token index (img*h*w + y*w + x) of each window position
-    __shared__ int sreg[4][NT];   // shift-mask region id
-    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int WIN = 6, NT = 36, KS = HD / 16, DT = HD / 8;
+    __shared__ int stok[4][48];   // token index of each (padded) window position; padding points at position 0
+    __shared__ int sreg[4][48];   // shift-mask region id
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const long long unit = (long long)blockIdx.x * 4 + wib;
     if (unit >= totalUnits) return;  // whole warp exits together
     const int head = (int)(unit % heads);
@@ -79,60 +91,125 @@ __global__ void __launch_bounds__(128) window_attention_kernel(const __half* __r
     win /= nwx;
     const int wy = (int)(win % nwy);
     const int img = (int)(win / nwy);
-    // window positions -> source tokens (torch.roll by -shift then partition) and mask regions (computed on shifted coords)
-    for (int t = lane; t < NT; t += 32) {
-        const int ys = wy * WIN + t / WIN, xs = wx * WIN + t % WIN;
-        const int y = (ys + shift) % h, x = (xs + shift) % w;
-        stok[wib][t] = (img * h + y) * w + x;
+    for (int p = lane; p < 48; p += 32) {
+        const int pp = p < NT ? p : 0;
+        const int ys = wy * WIN + pp / WIN, xs = wx * WIN + pp % WIN;     // coordinates in the rolled grid
+        const int y = (ys + shift) % h, x = (xs + shift) % w;             // torch.roll(x, -shift): rolled[p] = x[p + shift]
+        stok[wib][p] = (img * h + y) * w + x;
         const int hid = ys < h - WIN ? 0 : (ys < h - shift ? 1 : 2);
         const int wid = xs < w - WIN ? 0 : (xs < w - shift ? 1 : 2);
-        sreg[wib][t] = hid * 3 + wid;
+        sreg[wib][p] = hid * 3 + wid;
     }
     __syncwarp();
-    // stage K and V of this head (fp32) -- 36 x HD each
-    for (int i = lane; i < NT * HD; i += 32) {
-        const int t = i / HD, d = i - t * HD;
-        const __half* base = qkv + (long long)stok[wib][t] * (3 * c) + head * HD + d;
-        sk[wib][t][d] = __half2float(base[c]);
-        sv[wib][t][d] = __half2float(base[2 * c]);
+    const long long rowStride = 3ll * c;
+    const __half* qbase = qkv + head * HD;
+    // ---- S = Q K^T ----
+    float sacc[3][5][4];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 5; ++j) sacc[i][j][0] = sacc[i][j][1] = sacc[i][j][2] = sacc[i][j][3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+        uint32_t bk[5][2];
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+            const __half* kp = qbase + (long long)stok[wib][8 * j + g] * rowStride + c + 16 * ks + 2 * t;
+            bk[j][0] = *reinterpret_cast<const uint32_t*>(kp);
+            bk[j][1] = *reinterpret_cast<const uint32_t*>(kp + 8);
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const __half* q0 = qbase + (long long)stok[wib][16 * i + g] * rowStride + 16 * ks + 2 * t;
+            const __half* q1 = qbase + (long long)stok[wib][16 * i + g + 8] * rowStride + 16 * ks + 2 * t;
+            const uint32_t a0 = *reinterpret_cast<const uint32_t*>(q0), a1 = *reinterpret_cast<const uint32_t*>(q1);
+            const uint32_t a2 = *reinterpret_cast<const uint32_t*>(q0 + 8), a3 = *reinterpret_cast<const uint32_t*>(q1 + 8);
+#pragma unroll
+            for (int j = 0; j < 5; ++j) mma16816h(sacc[i][j], a0, a1, a2, a3, bk[j][0], bk[j][1]);
+        }
     }
-    __syncwarp();
+    // ---- scale + relative position bias + shift mask + softmax (rows 16i+g and 16i+g+8; columns 8j+2t, 8j+2t+1) ----
     const float scale = rsqrtf((float)HD);
     const float* bias = relpos + (long long)head * NT * NT;
-    for (int r = lane; r < NT; r += 32) {
-        float q[HD];
-        const __half* qp = qkv + (long long)stok[wib][r] * (3 * c) + head * HD;
+    uint32_t pa[3][5][2];  // probabilities as half2: [row tile][col tile][row g | row g+8]
 #pragma unroll
-        for (int d = 0; d < HD; ++d) q[d] = __half2float(qp[d]) * scale;
-        float sc[NT];
-        float mx = -1e30f;
-        const int myReg = sreg[wib][r];
+    for (int i = 0; i < 3; ++i) {
 #pragma unroll
-        for (int t = 0; t < NT; ++t) {
-            float a = 0.f;
+        for (int half = 0; half < 2; ++half) {
+            const int r = 16 * i + g + 8 * half;
+            const bool rowOk = r < NT;
+            const int rr = rowOk ? r : 0;
+            const int myReg = sreg[wib][rr];
+            float v[5][2];
+            float mx = -1e30f;
 #pragma unroll
-            for (int d = 0; d < HD; ++d) a = fmaf(q[d], sk[wib][t][d], a);
-            a += bias[r * NT + t];
-            if (shift > 0 && sreg[wib][t] != myReg) a += -100.f;
-            sc[t] = a;
-            mx = fmaxf(mx, a);
+            for (int j = 0; j < 5; ++j) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int col = 8 * j + 2 * t + e;
+                    float a = -1e30f;
+                    if (col < NT) {
+                        a = sacc[i][j][2 * half + e] * scale + __ldg(bias + rr * NT + col);
+                        if (shift > 0 && sreg[wib][col] != myReg) a += -100.f;
+                    }
+                    v[j][e] = a;
+                    mx = fmaxf(mx, a);
+                }
+            }
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+            float den = 0.f;
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+                v[j][0] = __expf(v[j][0] - mx);
+                v[j][1] = __expf(v[j][1] - mx);
+                den += v[j][0] + v[j][1];
+            }
+            den += __shfl_xor_sync(0xffffffffu, den, 1);
+            den += __shfl_xor_sync(0xffffffffu, den, 2);
+            const float inv = 1.f / den;
+#pragma unroll
+            for (int j = 0; j < 5; ++j) pa[i][j][half] = packHalf2(v[j][0] * inv, v[j][1] * inv);
         }
-        float den = 0.f;
+    }
+    // ---- O = P V : k-steps over 16 tokens (column tiles 2s, 2s+1), n-tiles over the head dim ----
+    float oacc[3][DT][4];
 #pragma unroll
-        for (int t = 0; t < NT; ++t) { sc[t] = __expf(sc[t] - mx); den += sc[t]; }
-        const float inv = 1.f / den;
-        float o[HD];
+    for (int i = 0; i < 3; ++i)
 #pragma unroll
-        for (int d = 0; d < HD; ++d) o[d] = 0.f;
+        for (int jd = 0; jd < DT; ++jd) oacc[i][jd][0] = oacc[i][jd][1] = oacc[i][jd][2] = oacc[i][jd][3] = 0.f;
+    const unsigned short* vbase = reinterpret_cast<const unsigned short*>(qbase + 2 * c);
 #pragma unroll
-        for (int t = 0; t < NT; ++t) {
-            const float pw = sc[t] * inv;
+    for (int s = 0; s < 3; ++s) {
+        // V fragments: b0 = (tokens 16s+2t, +1 ; dim 8jd+g), b1 = (tokens 16s+2t+8, +9); padded tokens carry P = 0
+        const long long r0 = (long long)stok[wib][16 * s + 2 * t] * rowStride, r1 = (long long)stok[wib][16 * s + 2 * t + 1] * rowStride;
+        const long long r2 = (long long)stok[wib][min(16 * s + 2 * t + 8, 47)] * rowStride, r3 = (long long)stok[wib][min(16 * s + 2 * t + 9, 47)] * rowStride;
 #pragma unroll
-            for (int d = 0; d < HD; ++d) o[d] = fmaf(pw, sv[wib][t][d], o[d]);
+        for (int jd = 0; jd < DT; ++jd) {
+            const int d = 8 * jd + g;
+            const uint32_t b0 = (uint32_t)vbase[r0 + d] | ((uint32_t)vbase[r1 + d] << 16);
+            const uint32_t b1 = (uint32_t)vbase[r2 + d] | ((uint32_t)vbase[r3 + d] << 16);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const uint32_t a0 = pa[i][2 * s][0], a1 = pa[i][2 * s][1];
+                const uint32_t a2 = (2 * s + 1 < 5) ? pa[i][(2 * s + 1 < 5) ? 2 * s + 1 : 0][0] : 0u;
+                const uint32_t a3 = (2 * s + 1 < 5) ? pa[i][(2 * s + 1 < 5) ? 2 * s + 1 : 0][1] : 0u;
+                mma16816h(oacc[i][jd], a0, a1, a2, a3, b0, b1);
+            }
         }
-        __half* op = out + (long long)stok[wib][r] * c + head * HD;
+    }
 #pragma unroll
-        for (int d = 0; d < HD; d += 2) *reinterpret_cast<__half2*>(op + d) = __floats2half2_rn(o[d], o[d + 1]);
+    for (int i = 0; i < 3; ++i) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int r = 16 * i + g + 8 * half;
+            if (r < NT) {
+                __half* op = out + (long long)stok[wib][r] * c + head * HD + 2 * t;
+#pragma unroll
+                for (int jd = 0; jd < DT; ++jd)
+                    *reinterpret_cast<__half2*>(op + 8 * jd) = __floats2half2_rn(oacc[i][jd][2 * half], oacc[i][jd][2 * half + 1]);
+            }
+        }
     }
 }
 

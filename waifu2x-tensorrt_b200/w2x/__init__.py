@@ -315,10 +315,11 @@ class Img2Img:
         return float(self._l.w2x_timer_elapsed_ms(self._h, i0, i1))
 
     def profile_layers(self, repeats: int = 5):
-        names = ((C.c_char * 48) * 64)()
-        ms = (C.c_float * 64)()
-        fl = (C.c_double * 64)()
-        n = self._l.w2x_profile_layers(self._h, repeats, names, ms, fl, 64)
+        cap = 256
+        names = ((C.c_char * 48) * cap)()
+        ms = (C.c_float * cap)()
+        fl = (C.c_double * cap)()
+        n = self._l.w2x_profile_layers(self._h, repeats, names, ms, fl, cap)
         if n < 0:
             raise RuntimeError(self.last_error)
         return [(names[i].value.decode(), ms[i], fl[i]) for i in range(n)]
