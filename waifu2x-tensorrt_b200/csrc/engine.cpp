@@ -452,6 +452,7 @@ void Engine::launchLayer(LayerExec& L, cudaStream_t s, __half* outp) {
 // ------------------------------------------------------------------------------------------------
 void Engine::buildPlanSwin() {
     const int C = (int)model.dim, S = (int)model.scale;
+    if (C != 96) throw Error("swin plan: only base_dim 96 (the released swin_unet models) is supported by the LayerNorm/attention kernels");
     if (C % 32 || tile < 64 || (tile - 16) % 48 != 0)
         throw Error("tile size is not supported by swin_unet ((tile - 16) must be a multiple of 48; SURVEY q10)");
     std::vector<float*> dAux0(model.layers.size(), nullptr), dAux1(model.layers.size(), nullptr);

@@ -324,7 +324,14 @@ __device__ __forceinline__ void epilogueWarps(const ConvArgs& a, uint32_t base, 
                 const int yy2 = tc.y0 + (row >> a.bwShift), xx2 = tc.x0 + (row & (a.bw - 1));
                 if (yy2 < a.p.gy && xx2 < a.p.gx) {
                     uint4 v = ldsV4(sbuf + (uint32_t)row * a.stagedPitch + (uint32_t)cc * 16u);
-                    const long long off = (((long long)tc.img * a.p.out_h + yy2) * a.p.out_w + xx2) * a.p.out_c + tc.n0 + cc * 8;
+                    long long off;
+                    if (a.p.mode == EPI_D2S) {  // pixel shuffle: column (q*cout + co) -> output pixel (2y + q/2, 2x + q%2), channel co
+                        const int j = tc.n0 + cc * 8;
+                        const int q = j / a.p.cout, co = j - q * a.p.cout;
+                        off = (((long long)tc.img * a.p.out_h + 2 * yy2 + (q >> 1)) * a.p.out_w + 2 * xx2 + (q & 1)) * a.p.out_c + co;
+                    } else {
+                        off = (((long long)tc.img * a.p.out_h + yy2) * a.p.out_w + xx2) * a.p.out_c + tc.n0 + cc * 8;
+                    }
                     if (a.p.skip) {
                         const uint4 sv = *reinterpret_cast<const uint4*>(a.p.skip + off);
                         __half2* vh = reinterpret_cast<__half2*>(&v);
@@ -836,8 +843,10 @@ void planIgemm(IgemmPlan* plan) {
     a.nbuf = 1;
     a.stagingBytes = 0;
     // token-wise layers whose shape rules out the TMA epilogue: coalescing staged epilogue
-    a.staged = (!a.useTma && p.mode == EPI_STORE && a.bn >= 32 && p.cout == p.npad && p.out_c == p.npad &&
-                (!p.skip || (p.skip_off == 0 && p.skip_c == p.out_c && p.skip_h == p.out_h && p.skip_w == p.out_w))) ? 1 : 0;
+    const bool skipSameGeom = !p.skip || (p.skip_off == 0 && p.skip_c == p.out_c && p.skip_h == p.out_h && p.skip_w == p.out_w && !p.skip_scale);
+    a.staged = (!a.useTma && a.bn >= 32 && skipSameGeom &&
+                ((p.mode == EPI_STORE && p.cout == p.npad && p.out_c == p.npad) ||
+                 (p.mode == EPI_D2S && p.cout % 8 == 0 && p.out_c == p.cout && p.npad == 4 * p.cout && p.act == ACT_LRELU))) ? 1 : 0;
     if (a.staged) {
         a.stagedPitch = (uint32_t)a.bn * 2u + 16u;
         a.stagedBuf = (128u * a.stagedPitch + 1023u) & ~1023u;

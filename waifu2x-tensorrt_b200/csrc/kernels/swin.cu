@@ -12,52 +12,72 @@
 
 namespace w2x {
 
+// Each lane owns one 16-byte chunk (8 channels) of a token: a warp covers 32 / (c/8) tokens per iteration (c = 96 -> 2 full
+// tokens + idle lanes, c = 192 -> 1 token); the reduction runs over the c/8 lanes of a token with segmented shuffles.
+template <int LANES>  // lanes per token = c / 8: 12 (c = 96) or 24 (c = 192)
 __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict__ x, __half* __restrict__ y, long long tokens, int c,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta, float eps) {
-    const long long tok = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (tok >= tokens) return;
+    constexpr int TPW = 32 / LANES;  // tokens per warp iteration (2 or 1)
     const int lane = threadIdx.x & 31;
-    const int pairs = c >> 1;  // c <= 256: at most 4 half2 per lane
-    const __half2* xr = reinterpret_cast<const __half2*>(x + tok * c);
-    float2 v[4];
-    float sum = 0.f;
+    const int sub = lane / LANES, li = lane - sub * LANES;
+    const bool act = sub < TPW;
+    const long long warpId = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long warpCount = (long long)gridDim.x * (blockDim.x >> 5);
+    float gm[8], bt[8];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int p = lane + 32 * i;
-        v[i] = p < pairs ? __half22float2(xr[p]) : make_float2(0.f, 0.f);
-        sum += v[i].x + v[i].y;
-    }
+    for (int i = 0; i < 8; ++i) { gm[i] = act ? gamma[li * 8 + i] : 0.f; bt[i] = act ? beta[li * 8 + i] : 0.f; }
+    const float invc = 1.f / (float)c;
+    for (long long t0 = warpId * TPW; t0 < tokens; t0 += warpCount * TPW) {
+        const long long tok = t0 + sub;
+        const bool ok = act && tok < tokens;
+        float v[8];
+        if (ok) {
+            const uint4 raw = *reinterpret_cast<const uint4*>(x + tok * c + li * 8);
+            const __half2* h = reinterpret_cast<const __half2*>(&raw);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    const float mean = sum / (float)c;
-    float var = 0.f;
+            for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+        } else {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int p = lane + 32 * i;
-        if (p < pairs) {
-            const float a = v[i].x - mean, b = v[i].y - mean;
-            var += a * a + b * b;
+            for (int i = 0; i < 8; ++i) v[i] = 0.f;
         }
-    }
+        float sum = 0.f;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
-    const float rstd = rsqrtf(var / (float)c + eps);
-    __half2* yr = reinterpret_cast<__half2*>(y + tok * c);
+        for (int i = 0; i < 8; ++i) sum += v[i];
+        // all-lanes butterfly over the token's LANES lanes: gather via shuffles from the token's first lane range
+        float tot = 0.f;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int p = lane + 32 * i;
-        if (p < pairs) {
-            const float a = (v[i].x - mean) * rstd * gamma[2 * p] + beta[2 * p];
-            const float b = (v[i].y - mean) * rstd * gamma[2 * p + 1] + beta[2 * p + 1];
-            yr[p] = __floats2half2_rn(a, b);
+        for (int j = 0; j < LANES; ++j) tot += __shfl_sync(0xffffffffu, sum, sub * LANES + j);
+        const float mean = tot * invc;
+        float sq = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { const float d = v[i] - mean; sq += d * d; }
+        float vt = 0.f;
+#pragma unroll
+        for (int j = 0; j < LANES; ++j) vt += __shfl_sync(0xffffffffu, sq, sub * LANES + j);
+        const float rstd = rsqrtf(vt * invc + eps);
+        if (ok) {
+            uint4 o;
+            __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                oh[i] = __floats2half2_rn((v[2 * i] - mean) * rstd * gm[2 * i] + bt[2 * i], (v[2 * i + 1] - mean) * rstd * gm[2 * i + 1] + bt[2 * i + 1]);
+            *reinterpret_cast<uint4*>(y + tok * c + li * 8) = o;
         }
     }
 }
 
 void launchLayerNorm(const __half* x, __half* y, long long tokens, int c, const float* gamma, const float* beta, float eps, cudaStream_t s) {
-    const int warpsPerBlock = 8;
-    const long long blocks = (tokens + warpsPerBlock - 1) / warpsPerBlock;
-    layernorm_kernel<<<(unsigned)blocks, 32 * warpsPerBlock, 0, s>>>(x, y, tokens, c, gamma, beta, eps);
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    const int grid = sms * 8;
+    // contract: c in {96, 192}
+    if (c == 96) layernorm_kernel<12><<<grid, 256, 0, s>>>(x, y, tokens, c, gamma, beta, eps);
+    else layernorm_kernel<24><<<grid, 256, 0, s>>>(x, y, tokens, c, gamma, beta, eps);
 }
 
 // One warp per (window, head); window = 6 (36 tokens).  Both GEMMs of the attention run on warp-level mma.sync
