@@ -372,19 +372,33 @@ void Engine::buildPlanCunet() {
         push(li, p, 2.0 * p.gx * p.gy * (double)L.cout * 9 * cinReal, fin);
         return out;
     };
-    auto down2 = [&](int li, const Act& in) {
+    // SE scale folding: when `in` is the (unscaled) output of an SE layer, the consumer multiplies by the SE scale through
+    // per-image weights W'[img] = W * s[img] (written by the SE layer's excite step) instead of a separate in-place pass.
+    auto foldInto = [&](int seLayerIdx, int li, ConvParams& p) {
+        const PackedLayer& L = model.layers[li];
+        LayerExec& prod = layers[seLayerIdx];
+        if (!prod.seR || useDirect && false) throw Error("internal: SE fold without an SE producer");
+        __half* wImg = (__half*)dalloc((size_t)batch * L.w.size() * 2);
+        prod.foldJobs.push_back({dW[li], wImg, (int)L.npad, (int)L.ktot, (int)L.cin});
+        p.w = wImg;
+        p.w_img_stride = (long long)L.w.size();
+    };
+    auto down2 = [&](int li, const Act& in, int seProducer = -1) {
         const PackedLayer& L = model.layers[li];
         even(in.h, "down-sampled extent");
         Act out = allocAct(in.h / 2, in.w / 2, (int)L.cout);
         ConvParams p = makeDown2Params(in, out, dW[li], dBias[li], (int)L.npad, S);
+        if (seProducer >= 0) foldInto(seProducer, li, p);
         push(li, p, 2.0 * p.gx * p.gy * (double)L.cout * 4 * L.cin);
         return out;
     };
-    auto up2 = [&](int li, const Act& in, const Act& skip, int off) {
+    auto up2 = [&](int li, const Act& in, const Act& skip, int off, int seProducer = -1, int skipSeProducer = -1) {
         const PackedLayer& L = model.layers[li];
         Act out = allocAct(in.h * 2, in.w * 2, (int)L.cout);
         if (skip.h - 2 * off != out.h || skip.c != out.c) throw Error("tile size is not supported by this model (skip connection mismatch)");
         ConvParams p = makeUp2Params(in, out, dW[li], dBias[li], (int)L.cout, S, &skip, off);
+        if (seProducer >= 0) foldInto(seProducer, li, p);
+        if (skipSeProducer >= 0) p.skip_scale = layers[skipSeProducer].seScale;
         push(li, p, 2.0 * p.gx * p.gy * 4.0 * L.cout * L.cin);
         return out;
     };
@@ -395,8 +409,9 @@ void Engine::buildPlanCunet() {
     Act x1 = conv3(1, a0, 64);
     Act d1 = down2(2, x1);
     Act b0 = conv3(3, d1, 128);
-    Act b1 = conv3(4, b0, 64);  // + SE
-    Act u1 = up2(5, b1, x1, 4);
+    Act b1 = conv3(4, b0, 64);  // + SE (scale folded into conv2_up's weights)
+    const int seB1 = (int)layers.size() - 1;
+    Act u1 = up2(5, b1, x1, 4, seB1);
     Act c3 = conv3(6, u1, 64);
     Act z1;
     if (up) {
@@ -412,14 +427,17 @@ void Engine::buildPlanCunet() {
     Act y1 = conv3(9, e0, 64);
     Act f1 = down2(10, y1);
     Act g0 = conv3(11, f1, 64);
-    Act y2 = conv3(12, g0, 128);  // + SE
-    Act f2 = down2(13, y2);
+    Act y2 = conv3(12, g0, 128);  // + SE (folded into conv2_down's weights and conv3_up's skip add)
+    const int seY2 = (int)layers.size() - 1;
+    Act f2 = down2(13, y2, seY2);
     Act h0 = conv3(14, f2, 256);
-    Act h1 = conv3(15, h0, 128);  // + SE
-    Act u3 = up2(16, h1, y2, 4);
+    Act h1 = conv3(15, h0, 128);  // + SE (folded into conv3_up's weights)
+    const int seH1 = (int)layers.size() - 1;
+    Act u3 = up2(16, h1, y2, 4, seH1, seY2);
     Act k0 = conv3(17, u3, 64);
-    Act k1 = conv3(18, k0, 64);  // + SE
-    Act u4 = up2(19, k1, y1, 16);
+    Act k1 = conv3(18, k0, 64);  // + SE (folded into conv4_up's weights)
+    const int seK1 = (int)layers.size() - 1;
+    Act u4 = up2(19, k1, y1, 16, seK1);
     Act c5 = conv3(20, u4, 64);
     if (z1.h - 40 != c5.h - 2) throw Error("tile size is not supported by this model (head crop mismatch)");
     actOut = conv3(21, c5, 3, EPI_FINAL, 1.f, &z1, 20, true);
@@ -639,8 +657,9 @@ void Engine::runModel(cudaStream_t s, __half* finalOut) {
         if (L.seR) {
             if (!L.seFused) { launchSeSqueeze(L.p.out, L.p.gn, L.p.out_h, L.p.out_w, L.p.out_c, L.sePartial, L.seBlocks, s); ++launches; }
             launchSeExcite(L.sePartial, L.seBlocks, L.p.gn, L.p.out_c, L.seR, L.p.out_h * L.p.out_w, L.seW1, L.seB1, L.seW2, L.seB2, L.seScale, s);
-            launchSeScale(L.p.out, L.p.gn, L.p.out_h, L.p.out_w, L.p.out_c, L.seScale, s);
-            launches += 2;
+            ++launches;
+            if (L.foldJobs.empty()) { launchSeScale(L.p.out, L.p.gn, L.p.out_h, L.p.out_w, L.p.out_c, L.seScale, s); ++launches; }
+            for (const auto& j : L.foldJobs) { launchScaleWeights(j.w, j.wOut, L.seScale, L.p.gn, j.npad, j.ktot, j.cin, s); ++launches; }
         }
     }
     W2X_CUDA(cudaGetLastError());
@@ -940,7 +959,8 @@ int Engine::profileLayers(int repeats, char (*names)[48], float* ms, double* flo
                 if (L.seR) {
                     if (!L.seFused) launchSeSqueeze(L.p.out, L.p.gn, L.p.out_h, L.p.out_w, L.p.out_c, L.sePartial, L.seBlocks, stream);
                     launchSeExcite(L.sePartial, L.seBlocks, L.p.gn, L.p.out_c, L.seR, L.p.out_h * L.p.out_w, L.seW1, L.seB1, L.seW2, L.seB2, L.seScale, stream);
-                    launchSeScale(L.p.out, L.p.gn, L.p.out_h, L.p.out_w, L.p.out_c, L.seScale, stream);
+                    if (L.foldJobs.empty()) launchSeScale(L.p.out, L.p.gn, L.p.out_h, L.p.out_w, L.p.out_c, L.seScale, stream);
+                    for (const auto& j : L.foldJobs) launchScaleWeights(j.w, j.wOut, L.seScale, L.p.gn, j.npad, j.ktot, j.cin, stream);
                 }
             }
             W2X_CUDA(cudaEventRecord(e1, stream));

@@ -40,6 +40,8 @@ struct LayerExec {
     float* sePartial = nullptr;
     float* seScale = nullptr;
     int seBlocks = 0;
+    struct FoldJob { const __half* w; __half* wOut; int npad, ktot, cin; };
+    std::vector<FoldJob> foldJobs;  // consumers that take this layer's SE scale through per-image weights
     bool seFused = false;        // squeeze sums come from the conv epilogue (ConvParams::se_sum)
     size_t sePartialBytes = 0;
     // SwinUNet token ops (IMPL_LAYERNORM / IMPL_ATTENTION)

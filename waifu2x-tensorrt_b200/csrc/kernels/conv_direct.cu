@@ -25,7 +25,7 @@ __global__ void __launch_bounds__(256) conv_direct_kernel(ConvParams p) {
         const ConvTap tp = p.tap[t];
         const __half* a = p.in + (long long)img * p.sn + (long long)(y + tp.dy) * p.sy + (long long)tp.dz * p.sz +
                           (long long)(x + tp.dx) * p.sx + tp.c0;
-        const __half* w = p.w + (long long)(jc * 8) * p.ktot + (long long)t * p.cin;
+        const __half* w = p.w + (long long)img * p.w_img_stride + (long long)(jc * 8) * p.ktot + (long long)t * p.cin;
         for (int c = 0; c < p.cin; ++c) {
             const float av = __half2float(a[c]);
 #pragma unroll

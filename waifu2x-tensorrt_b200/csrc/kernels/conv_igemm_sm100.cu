@@ -230,11 +230,22 @@ __device__ __forceinline__ void epilogueWarps(const ConvArgs& a, uint32_t base, 
                     if (kSkip) {
                         const uint4 sv = ldsV4(addr);
                         const __half2* sh = reinterpret_cast<const __half2*>(&sv);
+                        if (a.p.skip_scale) {  // the skip tensor's SE scale, applied here instead of a separate in-place pass
+                            const int co = (tc.n0 + j0) % a.p.cout;
+                            const float* ss = a.p.skip_scale + (long long)tc.img * a.p.skip_c + co;
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const float2 f = __half22float2(sh[i]);
-                            v[2 * i] += f.x;
-                            v[2 * i + 1] += f.y;
+                            for (int i = 0; i < 4; ++i) {
+                                const float2 f = __half22float2(sh[i]);
+                                v[2 * i] = fmaf(f.x, __ldg(ss + 2 * i), v[2 * i]);
+                                v[2 * i + 1] = fmaf(f.y, __ldg(ss + 2 * i + 1), v[2 * i + 1]);
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const float2 f = __half22float2(sh[i]);
+                                v[2 * i] += f.x;
+                                v[2 * i + 1] += f.y;
+                            }
                         }
                     }
                     uint4 o;
@@ -447,7 +458,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
                         const uint32_t dstA = stage0 + stage * stageBytes;
                         mbarExpectTx(full, stageBytes);
                         tmaLoad5d(dstA, &a.tmA, full, tp.c0 + cc * a.kc, tc.x0 + tp.dx, tp.dz, tc.y0 + tp.dy, tc.img);
-                        tmaLoad2d(dstA + a.bytesA, &a.tmB, full, tap * a.p.cin + cc * a.kc, tc.n0);
+                        tmaLoad3d(dstA + a.bytesA, &a.tmB, full, tap * a.p.cin + cc * a.kc, tc.n0, a.p.w_img_stride ? tc.img : 0);
                         if (++stage == a.stages) { stage = 0; phase ^= 1u; }
                     }
                 }
@@ -519,7 +530,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_patch_kernel(const __grid
             mbarExpectTx(barW, a.wBytes);
             for (int tap = 0; tap < 9; ++tap)
                 for (int cc = 0; cc < a.cchunks; ++cc)
-                    tmaLoad2d(wBase + (uint32_t)(tap * a.cchunks + cc) * tapBytes, &a.tmB, barW, tap * a.p.cin + cc * a.kc, n0);
+                    tmaLoad3d(wBase + (uint32_t)(tap * a.cchunks + cc) * tapBytes, &a.tmB, barW, tap * a.p.cin + cc * a.kc, n0, 0);
             int stage = 0;
             uint32_t phase = 0;
             TileWalker w;
@@ -702,11 +713,13 @@ void encode5d(CUtensorMap* tm, const void* ptr, const long long dims[5], const l
 }
 
 void encodeWeights(CUtensorMap* tm, const ConvParams& p, int kc, int rows, bool sw128) {
-    cuuint64_t dims[2] = {(cuuint64_t)p.ktot, (cuuint64_t)p.npad};
-    cuuint64_t strides[1] = {(cuuint64_t)p.ktot * 2};
-    cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)rows};
-    cuuint32_t es[2] = {1, 1};
-    CUresult r = encodeTiled()(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)p.w, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    // (k, n, img): img > 0 only when the layer carries per-image weights (SE scale folded in)
+    const bool perImage = p.w_img_stride != 0;
+    cuuint64_t dims[3] = {(cuuint64_t)p.ktot, (cuuint64_t)p.npad, (cuuint64_t)(perImage ? p.gn : 1)};
+    cuuint64_t strides[2] = {(cuuint64_t)p.ktot * 2, (cuuint64_t)(perImage ? p.w_img_stride : (long long)p.npad * p.ktot) * 2};
+    cuuint32_t box[3] = {(cuuint32_t)kc, (cuuint32_t)rows, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = encodeTiled()(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void*)p.w, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                sw128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) throw Error("cuTensorMapEncodeTiled(weights) failed with code " + std::to_string((int)r));
@@ -717,7 +730,7 @@ bool tmaEpilogueOk(const ConvParams& p) {
     if (p.mode == EPI_STORE) return p.cout % 64 == 0 && p.npad == p.cout && p.out_c == p.cout && p.act == ACT_LRELU && !p.skip;
     if (p.mode == EPI_D2S) {
         if (p.cout % 64 != 0 || p.out_c != p.cout || (p.out_w & 1) || (p.out_h & 1)) return false;
-        if (p.skip && ((p.skip_off & 1) || (p.skip_w & 1) || (p.skip_h & 1) || p.skip_c != p.cout || p.skip_scale)) return false;
+        if (p.skip && ((p.skip_off & 1) || (p.skip_w & 1) || (p.skip_h & 1) || p.skip_c != p.cout)) return false;
         return true;
     }
     return false;
@@ -752,7 +765,7 @@ int pickBn(int npad) {
 }
 
 bool wantsPatchKernel(const ConvParams& p) {
-    if (!p.is3x3 || !(p.cin == 32 || p.cin == 64 || p.cin == 128)) return false;
+    if (!p.is3x3 || !(p.cin == 32 || p.cin == 64 || p.cin == 128) || p.w_img_stride) return false;
     if (!(p.npad % 64 == 0 || p.npad == 16)) return false;
     if (p.npad % 64 == 0 && !tmaEpilogueOk(p)) return false;
     return true;

@@ -36,6 +36,7 @@ struct ConvParams {
     int gx, gy, gn;  // pixel grid per image (x, y) and image count
     int npad, ktot;
     const __half* w;    // B: [npad][ktot], K-major
+    long long w_img_stride;  // elements between per-image copies of B (SE scale folded into the weights), 0 = shared
     const float* bias;  // [npad]
     // epilogue
     int mode;
@@ -181,6 +182,8 @@ void launchSeSqueeze(const __half* x, int n, int h, int w, int c, float* partial
 void launchSeExcite(const float* partial, int nblk, int n, int c, int r, int hw, const float* w1, const float* b1,
                     const float* w2, const float* b2, float* scale, cudaStream_t s);
 void launchSeScale(__half* x, int n, int h, int w, int c, const float* scale, cudaStream_t s);
+// W'[img][n][k] = W[n][k] * scale[img][k % cin]: folds an SE channel scale into the CONSUMER's weights (one copy per image)
+void launchScaleWeights(const __half* w, __half* wOut, const float* scale, int nimg, int npad, int ktot, int cin, cudaStream_t s);
 
 // tiling (kernels/tiling.cu)
 struct TileSlot { int x, y, aug, valid; };  // input rect origin, D4 op, 0 = zero dummy slot (img2img_render.cpp:281)

@@ -111,6 +111,23 @@ __global__ void __launch_bounds__(256) se_scale_kernel(__half* __restrict__ x, l
     *px = v;
 }
 
+__global__ void __launch_bounds__(256) scale_weights_kernel(const __half* __restrict__ w, __half* __restrict__ wOut, const float* __restrict__ scale,
+                                                            int total, int ktot, int cin) {
+    const int img = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;  // pair index
+    if (2 * i >= total) return;
+    const int k = (2 * i) % ktot;
+    const float2 v = __half22float2(reinterpret_cast<const __half2*>(w)[i]);
+    const float* sc = scale + (size_t)img * cin + (k % cin);
+    reinterpret_cast<__half2*>(wOut + (size_t)img * total)[i] = __floats2half2_rn(v.x * sc[0], v.y * sc[1]);
+}
+
+void launchScaleWeights(const __half* w, __half* wOut, const float* scale, int nimg, int npad, int ktot, int cin, cudaStream_t s) {
+    const int total = npad * ktot;  // even; k and k+1 share a tap because cin is even
+    dim3 grid((total / 2 + 255) / 256, nimg);
+    scale_weights_kernel<<<grid, 256, 0, s>>>(w, wOut, scale, total, ktot, cin);
+}
+
 void launchSeScale(__half* x, int n, int h, int w, int c, const float* scale, cudaStream_t s) {
     const long long vec = (long long)h * w * c / 8;
     dim3 grid((unsigned)((vec + 255) / 256), n);
