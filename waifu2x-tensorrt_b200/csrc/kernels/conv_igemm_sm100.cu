@@ -175,6 +175,7 @@ __device__ __forceinline__ void epilogueWarps(const ConvArgs& a, uint32_t base, 
     const int seGroups = kEpiThreads / a.bn;
     float seAcc = 0.f;
     int seImg = -1;
+    int skipScaleImg = -1;
     // image boundary (uniform across the epilogue threads): combine the row groups in a fixed order, one slot per CTA
     auto seFlush = [&]() {
         if (seImg < 0) return;
@@ -205,6 +206,14 @@ __device__ __forceinline__ void epilogueWarps(const ConvArgs& a, uint32_t base, 
         const bool pvalid = py < a.p.gy && px < a.p.gx;
         if (!kTma && a.p.mode == EPI_FINAL && active && pvalid)
             preSkip = *reinterpret_cast<const Half4*>(a.p.skip + (((long long)tc.img * a.p.skip_h + py + a.p.skip_off) * a.p.skip_w + px + a.p.skip_off) * a.p.skip_c);
+        if (kSkip && a.p.skip_scale && tc.img != skipScaleImg) {
+            // per-image SE scale of the skip tensor -> smem scratch (image changes are uniform across the epilogue threads)
+            namedBarSync(2, kEpiThreads);
+            float* scratch = reinterpret_cast<float*>(__cvta_shared_to_generic((size_t)(base + a.headerBytes - 1024u)));
+            if (et < a.p.skip_c) scratch[et] = a.p.skip_scale[(long long)tc.img * a.p.skip_c + et];
+            namedBarSync(2, kEpiThreads);
+            skipScaleImg = tc.img;
+        }
         mbarWait(barTFull + 8u * acc, accPhase);
         tcFenceAfter();
         if (kSkip) mbarWait(barSkip + 8u * b, (uint32_t)(k / a.nbuf) & 1u);
@@ -231,13 +240,15 @@ __device__ __forceinline__ void epilogueWarps(const ConvArgs& a, uint32_t base, 
                         const uint4 sv = ldsV4(addr);
                         const __half2* sh = reinterpret_cast<const __half2*>(&sv);
                         if (a.p.skip_scale) {  // the skip tensor's SE scale, applied here instead of a separate in-place pass
-                            const int co = (tc.n0 + j0) % a.p.cout;
-                            const float* ss = a.p.skip_scale + (long long)tc.img * a.p.skip_c + co;
+                            const uint32_t co = (uint32_t)((tc.n0 + j0) % a.p.cout);
+                            const uint4 s0 = ldsV4(base + a.headerBytes - 1024u + co * 4u), s1 = ldsV4(base + a.headerBytes - 1024u + co * 4u + 16u);
+                            const float ss[8] = {__uint_as_float(s0.x), __uint_as_float(s0.y), __uint_as_float(s0.z), __uint_as_float(s0.w),
+                                                 __uint_as_float(s1.x), __uint_as_float(s1.y), __uint_as_float(s1.z), __uint_as_float(s1.w)};
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
                                 const float2 f = __half22float2(sh[i]);
-                                v[2 * i] = fmaf(f.x, __ldg(ss + 2 * i), v[2 * i]);
-                                v[2 * i + 1] = fmaf(f.y, __ldg(ss + 2 * i + 1), v[2 * i + 1]);
+                                v[2 * i] = fmaf(f.x, ss[2 * i], v[2 * i]);
+                                v[2 * i + 1] = fmaf(f.y, ss[2 * i + 1], v[2 * i + 1]);
                             }
                         } else {
 #pragma unroll

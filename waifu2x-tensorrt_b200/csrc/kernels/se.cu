@@ -51,7 +51,12 @@ __global__ void __launch_bounds__(256) se_excite_kernel(const float* __restrict_
                                                         float* __restrict__ scale) {
     __shared__ float mean[256];
     __shared__ float hid[64];
+    __shared__ float sw1[2048], sw2[2048];  // FC weights (r * c <= 2048 for c <= 128, r = c / 8); larger blocks read global
     const int img = blockIdx.x;
+    const int fcElems = r * c;
+    const bool fcInSmem = fcElems <= 2048;
+    if (fcInSmem)
+        for (int i = threadIdx.x; i < fcElems; i += blockDim.x) { sw1[i] = w1[i]; sw2[i] = w2[i]; }
     {
         // all 256 threads reduce the partial sums: (256 / c) slot groups per channel, fixed combination order
         __shared__ float part[256];
@@ -75,15 +80,23 @@ __global__ void __launch_bounds__(256) se_excite_kernel(const float* __restrict_
         }
     }
     __syncthreads();
-    for (int j = threadIdx.x; j < r; j += blockDim.x) {
-        float s = b1[j];
-        for (int ch = 0; ch < c; ++ch) s = fmaf(w1[j * c + ch], mean[ch], s);
-        hid[j] = fmaxf(s, 0.f);
+    const float* W1 = fcInSmem ? sw1 : w1;
+    const float* W2 = fcInSmem ? sw2 : w2;
+    {
+        // hid[j] = relu(b1[j] + <W1[j], mean>): one warp per j, lanes stride the channels
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        for (int j = warp; j < r; j += (blockDim.x >> 5)) {
+            float s = 0.f;
+            for (int ch = lane; ch < c; ch += 32) s = fmaf(W1[j * c + ch], mean[ch], s);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) hid[j] = fmaxf(s + b1[j], 0.f);
+        }
     }
     __syncthreads();
     for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
         float s = b2[ch];
-        for (int j = 0; j < r; ++j) s = fmaf(w2[ch * r + j], hid[j], s);
+        for (int j = 0; j < r; ++j) s = fmaf(W2[ch * r + j], hid[j], s);
         scale[(size_t)img * c + ch] = 1.f / (1.f + expf(-s));
     }
 }
