@@ -124,6 +124,10 @@ W2X_API float w2x_timer_elapsed_ms(w2x_engine* e, int idx0, int idx1);
 /* Layer-level timing of the model (names + ms) for profiling; returns number of layers, fills up to n. */
 W2X_API int w2x_profile_layers(w2x_engine* e, int repeats, char (*names)[48], float* ms, double* flops, int n);
 
+/* Which kernel runs model layer `index` ("patch3x3 ...", "igemm ...", "first-layer mma.sync", "layernorm", "window-attention");
+ * returns 0 when index is out of range. */
+W2X_API int w2x_layer_kernel(w2x_engine* e, int index, char* buf, int cap);
+
 /* ---- stage entry points (each replaces one reference helper; host buffers; used by the parity tests) ----- */
 
 /* calculateTiles (img2img_render.cpp:7-66).  Writes up to `cap` rects in the reference's column-major order;

@@ -95,7 +95,7 @@ class UNet2(nn.Module):
 
 
 class CUNet(nn.Module):
-    """cunet/art scale 1 (denoise): offset 28, out = T - 56... wait: out = T - 2*28."""
+    """cunet/art scale 1 (denoise): offset 28, out = T - 56."""
     scale = 1
     offset = 28
 

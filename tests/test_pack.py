@@ -50,6 +50,22 @@ def test_pack_onnx(scale, arch, offset, built_lib, models_dir, tmp_path):
     assert info == dict(arch=arch, scale=scale, offset=offset, layers=22)
 
 
+@pytest.mark.parametrize("scale,layers", [(1, 105), (2, 105), (4, 106)])
+def test_pack_swin_unet(scale, layers, built_lib, tmp_path):
+    """swin_unet/*: 2 patch convs + 14 blocks x 7 records + 2 PatchDown + 2 (3 for 4x) PatchUp + ToImage."""
+    import w2x
+    from oracle.models import make_model
+    m = make_model("swin_unet", scale)
+    p = str(tmp_path / "swin.onnx")
+    onnx_io.export_swin(m, p)
+    nodes, inits = onnx_io.read_model(open(p, "rb").read())
+    assert sum(1 for n in nodes if n[0] == "LayerNormalization") == 28
+    assert inits["swin1.block.0.attn.relative_position_bias"].shape == (1, 6, 36, 36)
+    out = str(tmp_path / "swin.w2x")
+    w2x.pack_onnx(p, out)
+    assert w2x.pack_info(out) == dict(arch=3, scale=scale, offset=8 * scale, layers=layers)
+
+
 def test_pack_rejects_garbage(built_lib, tmp_path):
     import w2x
     p = tmp_path / "bad.onnx"

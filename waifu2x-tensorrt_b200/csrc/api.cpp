@@ -118,6 +118,7 @@ float w2x_timer_elapsed_ms(w2x_engine* e, int i0, int i1) { return e ? e->impl.t
 int w2x_profile_layers(w2x_engine* e, int repeats, char (*names)[48], float* ms, double* flops, int n) {
     return e ? e->impl.profileLayers(repeats < 1 ? 1 : repeats, names, ms, flops, n) : -1;
 }
+int w2x_layer_kernel(w2x_engine* e, int index, char* buf, int cap) { return e && buf && cap > 0 ? e->impl.layerKernel(index, buf, cap) : 0; }
 int w2x_infer(w2x_engine* e, const float* in, int n, float* out) { return e && in && out && e->impl.infer(in, n, out) ? 1 : 0; }
 
 // ---- stage entry points ---------------------------------------------------------------------------------

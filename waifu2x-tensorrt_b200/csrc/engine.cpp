@@ -642,6 +642,15 @@ void Engine::buildPlanSwin() {
     if (outTile != (tile - 16) * S) throw Error("internal: swin output tile size mismatch");
 }
 
+int Engine::layerKernel(int index, char* buf, int cap) const {
+    if (index < 0 || index >= (int)layers.size()) return 0;
+    const LayerExec& L = layers[index];
+    if (L.plan) igemmDescribe(L.plan, buf, cap);
+    else std::snprintf(buf, cap, "%s", L.impl == IMPL_FIRST ? "first-layer mma.sync" : L.impl == IMPL_LAYERNORM ? "layernorm" :
+                                       L.impl == IMPL_ATTENTION ? "window-attention mma.sync" : "direct (reference kernel)");
+    return 1;
+}
+
 double Engine::flopsPerTile() const {
     double f = 0;
     for (const auto& L : layers) f += L.flops;

@@ -80,6 +80,7 @@ public:
     long long launchCount() const { return launches; }
     double flopsPerTile() const;
     int lastStageMs(float* out, int n);
+    int layerKernel(int index, char* buf, int cap) const;
     bool timerMark(int idx, int which);
     float timerElapsedMs(int i0, int i1);
     int device() const { return cfg.deviceId; }

@@ -114,6 +114,7 @@ _SIGNATURES = {
     "w2x_last_stage_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_int]),
     "w2x_timer_mark": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "w2x_timer_elapsed_ms": (C.c_float, [C.c_void_p, C.c_int, C.c_int]),
+    "w2x_layer_kernel": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.c_int]),
     "w2x_profile_layers": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_double), C.c_int]),
     "w2x_calculate_tiles": (C.c_int, [C.c_int] * 9 + [C.c_double, C.c_double, C.POINTER(_Rect), C.POINTER(_Rect), C.c_int, C.POINTER(C.c_int)]),
     "w2x_blend_ramp": (C.c_int, [C.c_int, C.POINTER(C.c_float)]),
@@ -323,6 +324,10 @@ class Img2Img:
         if n < 0:
             raise RuntimeError(self.last_error)
         return [(names[i].value.decode(), ms[i], fl[i]) for i in range(n)]
+
+    def layer_kernel(self, index: int) -> Optional[str]:
+        buf = C.create_string_buffer(256)
+        return buf.value.decode() if self._l.w2x_layer_kernel(self._h, index, buf, 256) else None
 
     def render_device(self, d_src: int, w: int, h: int, d_dst: int) -> bool:
         return bool(self._l.w2x_render_device(self._h, C.c_void_p(d_src), w, h, w * 3, C.c_void_p(d_dst), w * self.scaling * 3))
