@@ -97,6 +97,19 @@ def test_render_matches_oracle(w, h, scale, tile, batch, blend, built_lib, model
     e.close()
 
 
+def test_render_tile400_cunet1x(built_lib, models_dir):
+    """BASELINE configs[2] tile size: cunet/art scale 1, tileSize 400 (out tile 344, iov = oov = 25), batch 2."""
+    e, model_t, msgs = _engine(models_dir, 1, 400, 2, 1 / 16)
+    assert e.output_tile_size == 344
+    src = tiling.synthetic_frame(420, 400, 11)
+    dst = e.render(src)
+    assert dst is not None, msgs
+    ref = tiling.render(src, _model_fn(model_t), 400, 344, 1, 1 / 16, 2)
+    diff = np.abs(dst.astype(np.int32) - ref.astype(np.int32))
+    assert (diff <= 1).mean() >= 0.999 and _psnr(dst, ref) >= 50, ((diff <= 1).mean(), diff.max())
+    e.close()
+
+
 def test_render_tta_matches_oracle_mean(built_lib, models_dir):
     """cfg3 shape in miniature: cunet 1x + 8-way TTA (mean)."""
     e, model_t, msgs = _engine(models_dir, 1, 128, 4, 1 / 16, tta=True)

@@ -63,6 +63,21 @@ def test_swin_tile_112_two_window_rows(built_lib, swin_models):
     e.close()
 
 
+def test_swin_infer_tile256_scale4(built_lib, swin_models):
+    """BASELINE configs[3] tile: swin_unet/art scale 4, tileSize 256 -> 960 (40 / 20 / 10 windows per side)."""
+    e, model_t, msgs = _engine(swin_models, 4, 256, 1)
+    assert e.output_tile_size == 960
+    x = np.random.default_rng(2).random((1, 3, 256, 256), dtype=np.float32)
+    x = (np.rint(x * 255) / 255).astype(np.float32)
+    y = e.infer(x)
+    assert y is not None, msgs
+    with torch.no_grad():
+        ref = model_t(torch.from_numpy(x)).numpy()
+    err = np.abs(y - ref)
+    assert (err * 255 <= 1.0).mean() >= 0.999 and _psnr(y * 255, ref * 255) > 50, ((err * 255 <= 1.0).mean(), err.max())
+    e.close()
+
+
 def test_swin_render_matches_oracle(built_lib, swin_models):
     """cfg4 in miniature: swin_unet/art scale 4, batch 4 with padding slots, blend 1/16."""
     e, model_t, msgs = _engine(swin_models, 4, 64, 4)
