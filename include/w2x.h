@@ -101,6 +101,11 @@ W2X_API int w2x_render_device(w2x_engine* e, const uint8_t* d_src_bgr, int width
 W2X_API int w2x_submit(w2x_engine* e, const uint8_t* src_bgr, int width, int height, size_t src_stride,
                        uint8_t* dst_bgr, size_t dst_stride);
 W2X_API int w2x_wait(w2x_engine* e, int ticket);
+/* One image sharded over several engines (one per GPU, identically loaded) by contiguous bands of the GLOBAL tile grid's rows;
+ * the seam tile row is exchanged peer-to-peer (cudaMemcpyPeerAsync over NVLink), no collective.  Byte-identical to w2x_render
+ * on one GPU.  Host buffers as in w2x_render. */
+W2X_API int w2x_render_banded(w2x_engine* const* engines, int count, const uint8_t* src_bgr, int width, int height,
+                              size_t src_stride, uint8_t* dst_bgr, size_t dst_stride);
 W2X_API int w2x_sync(w2x_engine* e);
 W2X_API void* w2x_host_alloc(size_t bytes);   /* cudaHostAlloc (pinned) */
 W2X_API void w2x_host_free(void* p);

@@ -79,6 +79,17 @@ int w2x_submit(w2x_engine* e, const uint8_t* src, int width, int height, size_t 
     return e->impl.submit(src, width, height, src_stride, dst, dst_stride);
 }
 
+int w2x_render_banded(w2x_engine* const* engines, int count, const uint8_t* src, int width, int height, size_t src_stride,
+                      uint8_t* dst, size_t dst_stride) {
+    if (!engines || count < 1 || count > 16 || !src || !dst) return 0;
+    Engine* es[16];
+    for (int i = 0; i < count; ++i) {
+        if (!engines[i]) return 0;
+        es[i] = &engines[i]->impl;
+    }
+    return Engine::renderBanded(es, count, src, width, height, src_stride, dst, dst_stride) ? 1 : 0;
+}
+
 int w2x_wait(w2x_engine* e, int ticket) { return e && e->impl.wait(ticket) ? 1 : 0; }
 int w2x_sync(w2x_engine* e) { return e && e->impl.sync() ? 1 : 0; }
 

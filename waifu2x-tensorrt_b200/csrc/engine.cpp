@@ -138,6 +138,9 @@ void Engine::unload() {
     dW.clear(); dBias.clear();
     auto freep = [](auto*& p) { if (p) { cudaFree(p); p = nullptr; } };
     freep(dSlots); freep(dTileOut); freep(dTtaMean); freep(dRampX); freep(dRampY); freep(dFrameIn); freep(dFrameOut);
+    freep(dBandTiles); freep(dBandMap); freep(dBandSlots);
+    bandTilesCap = bandMapCap = bandSlotCap = 0;
+    if (evBandModel) { cudaEventDestroy(evBandModel); evBandModel = nullptr; }
     slotCap = tileOutCap = ttaCap = frameInCap = frameOutCap = 0;
     rampXLen = rampYLen = -1;
     for (auto& s : pipe) {
@@ -291,6 +294,7 @@ bool Engine::load(const std::string& onnxPath, const w2x_render_config& rc) {
         scale = (int)model.scale;
         const char* impl = std::getenv("W2X_CONV_IMPL");
         useDirect = impl && std::string(impl) == "direct";
+        debugSync = std::getenv("W2X_DEBUG_SYNC") != nullptr;
         W2X_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));  // img2img_load.cpp:206
         W2X_CUDA(cudaStreamCreateWithFlags(&h2dStream, cudaStreamNonBlocking));
         W2X_CUDA(cudaStreamCreateWithFlags(&d2hStream, cudaStreamNonBlocking));
@@ -663,6 +667,11 @@ void Engine::runModel(cudaStream_t s, __half* finalOut) {
         if (L.seFused) W2X_CUDA(cudaMemsetAsync(L.sePartial, 0, L.sePartialBytes, s));
         launchLayer(L, s, outp);
         ++launches;
+        if (debugSync) {
+            cudaError_t de = cudaStreamSynchronize(s);
+            if (de == cudaSuccess) de = cudaGetLastError();
+            if (de != cudaSuccess) throw Error("layer '" + L.name + "': " + cudaGetErrorString(de));
+        }
         if (L.seR) {
             if (!L.seFused) { launchSeSqueeze(L.p.out, L.p.gn, L.p.out_h, L.p.out_w, L.p.out_c, L.sePartial, L.seBlocks, s); ++launches; }
             launchSeExcite(L.sePartial, L.seBlocks, L.p.gn, L.p.out_c, L.seR, L.p.out_h * L.p.out_w, L.seW1, L.seB1, L.seW2, L.seB2, L.seScale, s);
@@ -884,6 +893,122 @@ int Engine::submit(const uint8_t* src, int w, int h, size_t srcStride, uint8_t* 
     } catch (const std::exception& ex) {
         ELOG(W2X_ERROR, std::string("Submit failed unexpectedly: ") + ex.what() + ".");
         return -1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Row-band mode ("single large image"): the GLOBAL tile grid is computed once, exactly as for one GPU (bands are
+// unions of the reference's tiles: SE pooling is per tile, so re-tiling would change results), and split into contiguous
+// bands of tile rows, one per engine/GPU.  Every band renders its own tiles; the only exchange is the band's LAST tile row,
+// which the band below needs for the blended seam rows: copied peer-to-peer (cudaMemcpyPeerAsync over NVLink) straight into
+// the neighbour's tile buffer.  Each GPU then stitches and downloads only its own output rows.  No collective, no NCCL; the
+// result is byte-identical to the single-GPU render (same tiles, same fp32 add order).
+// ------------------------------------------------------------------------------------------------
+bool Engine::renderBanded(Engine* const* es, int count, const uint8_t* src, int w, int h, size_t srcStride, uint8_t* dst, size_t dstStride) {
+    if (!es || count < 1 || !es[0]) return false;
+    Engine& e0 = *es[0];
+    try {
+        for (int r = 0; r < count; ++r) {
+            if (!es[r] || !es[r]->isLoaded) throw Error("no engine loaded");
+            if (es[r]->tile != e0.tile || es[r]->outTile != e0.outTile || es[r]->scale != e0.scale || es[r]->batch != e0.batch ||
+                es[r]->cfg.overlapX != e0.cfg.overlapX || es[r]->cfg.overlapY != e0.cfg.overlapY)
+                throw Error("row-band render needs identically configured engines");
+            if (es[r]->cfg.tta) throw Error("row-band render does not support --tta yet");
+        }
+        const int scale = e0.scale, outT = e0.outTile, tile = e0.tile, batch = e0.batch;
+        const TileGrid g = calculateTiles(w, h, w * scale, h * scale, tile, tile, outT, outT, scale, e0.cfg.overlapX, e0.cfg.overlapY);
+        if (g.count <= 0) throw Error("frame is too small for the configured tile overlap");
+        const int bands = std::min(count, g.ny);
+        const size_t tileElems = (size_t)outT * outT * 4;
+        const int sty = outT - g.outOvY;
+        const int cw = w * scale, ch = h * scale;
+        struct Band { int j0, j1, own, slots, yBegin, yEnd; };
+        std::vector<Band> bd(bands);
+        for (int r = 0; r < bands; ++r) {
+            const int base = g.ny / bands, extra = g.ny % bands;
+            bd[r].j0 = r * base + std::min(r, extra);
+            bd[r].j1 = bd[r].j0 + base + (r < extra ? 1 : 0);
+            bd[r].own = (bd[r].j1 - bd[r].j0) * g.nx;
+            bd[r].slots = (bd[r].own + batch - 1) / batch * batch;          // own tiles padded to whole batches
+            bd[r].yBegin = r == 0 ? 0 : bd[r].j0 * sty;
+            bd[r].yEnd = r == bands - 1 ? ch : bd[r].j1 * sty;
+        }
+        // ---- phase 1: every band unpacks + runs the model on its tiles (devices run concurrently) ----
+        for (int r = 0; r < bands; ++r) {
+            Engine& e = *es[r];
+            W2X_CUDA(cudaSetDevice(e.cfg.deviceId));
+            e.ensureFrameBuffers(w, h);  // blend ramps + grid bookkeeping for this frame size
+            const size_t inBytes = (size_t)w * 3 * h, outBytes = (size_t)cw * 3 * ch;
+            if (inBytes > e.frameInCap) { if (e.dFrameIn) cudaFree(e.dFrameIn); W2X_CUDA(cudaMalloc(&e.dFrameIn, inBytes)); e.frameInCap = inBytes; }
+            if (outBytes > e.frameOutCap) { if (e.dFrameOut) cudaFree(e.dFrameOut); W2X_CUDA(cudaMalloc(&e.dFrameOut, outBytes)); e.frameOutCap = outBytes; }
+            const size_t needTiles = (size_t)(bd[r].slots + g.nx) * tileElems;   // own (padded) + the row received from above
+            if (needTiles > e.bandTilesCap) { if (e.dBandTiles) cudaFree(e.dBandTiles); W2X_CUDA(cudaMalloc(&e.dBandTiles, needTiles * sizeof(__half))); e.bandTilesCap = needTiles; }
+            if ((size_t)g.count > e.bandMapCap) { if (e.dBandMap) cudaFree(e.dBandMap); W2X_CUDA(cudaMalloc(&e.dBandMap, sizeof(int) * g.count)); e.bandMapCap = g.count; }
+            if ((size_t)bd[r].slots > e.bandSlotCap) { if (e.dBandSlots) cudaFree(e.dBandSlots); W2X_CUDA(cudaMalloc(&e.dBandSlots, sizeof(TileSlot) * bd[r].slots)); e.bandSlotCap = bd[r].slots; }
+            if (!e.evBandModel) W2X_CUDA(cudaEventCreateWithFlags(&e.evBandModel, cudaEventDisableTiming));
+            // slots in row-major band order (so a tile row is contiguous for the peer copy); map: global tile index -> slot
+            std::vector<TileSlot> slots((size_t)bd[r].slots, TileSlot{0, 0, 0, 0});
+            std::vector<int> map((size_t)g.count, -1);
+            for (int j = bd[r].j0; j < bd[r].j1; ++j)
+                for (int i = 0; i < g.nx; ++i) {
+                    const int s = (j - bd[r].j0) * g.nx + i, t = i * g.ny + j;
+                    slots[s] = {g.inRects[t].x, g.inRects[t].y, 0, 1};
+                    map[t] = s;
+                }
+            if (r > 0)
+                for (int i = 0; i < g.nx; ++i) map[i * g.ny + bd[r].j0 - 1] = bd[r].slots + i;  // received seam row
+            W2X_CUDA(cudaMemcpyAsync(e.dBandSlots, slots.data(), sizeof(TileSlot) * slots.size(), cudaMemcpyHostToDevice, e.stream));
+            W2X_CUDA(cudaMemcpyAsync(e.dBandMap, map.data(), sizeof(int) * map.size(), cudaMemcpyHostToDevice, e.stream));
+            W2X_CUDA(cudaMemcpy2DAsync(e.dFrameIn, (size_t)w * 3, src, srcStride, (size_t)w * 3, h, cudaMemcpyHostToDevice, e.stream));
+            W2X_CUDA(cudaStreamSynchronize(e.stream));  // the staging vectors go out of scope
+            for (int b = 0; b < bd[r].slots / batch; ++b) {
+                launchUnpack(e.dFrameIn, w, h, (size_t)w * 3, e.dBandSlots + (size_t)b * batch, batch, tile, e.actIn.p, e.stream);
+                ++e.launches;
+                W2X_CUDA(cudaGetLastError());
+                e.runModel(e.stream, e.dBandTiles + (size_t)b * batch * tileElems);
+            }
+            W2X_CUDA(cudaEventRecord(e.evBandModel, e.stream));
+        }
+        // ---- phase 2: seam exchange (last tile row of band r-1 -> band r), stitch own rows, download ----
+        for (int r = 0; r < bands; ++r) {
+            Engine& e = *es[r];
+            W2X_CUDA(cudaSetDevice(e.cfg.deviceId));
+            if (r > 0) {
+                Engine& up = *es[r - 1];
+                if (up.cfg.deviceId != e.cfg.deviceId) {
+                    int can = 0;
+                    if (cudaDeviceCanAccessPeer(&can, e.cfg.deviceId, up.cfg.deviceId) == cudaSuccess && can) {
+                        const cudaError_t pe = cudaDeviceEnablePeerAccess(up.cfg.deviceId, 0);  // direct NVLink path for the seam copy
+                        if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) W2X_CUDA(pe);
+                        (void)cudaGetLastError();
+                    }
+                }
+                W2X_CUDA(cudaStreamWaitEvent(e.stream, up.evBandModel, 0));
+                const __half* srcRow = up.dBandTiles + (size_t)(bd[r - 1].j1 - 1 - bd[r - 1].j0) * g.nx * tileElems;
+                W2X_CUDA(cudaMemcpyPeerAsync(e.dBandTiles + (size_t)bd[r].slots * tileElems, e.cfg.deviceId, srcRow, up.cfg.deviceId,
+                                             (size_t)g.nx * tileElems * sizeof(__half), e.stream));
+            }
+            StitchParams sp{};
+            sp.tiles = e.dBandTiles; sp.f32 = 0; sp.tile_map = e.dBandMap;
+            sp.outT = outT; sp.nx = g.nx; sp.ny = g.ny; sp.ovx = g.outOvX; sp.ovy = g.outOvY;
+            sp.cw = cw; sp.ch = ch; sp.rampx = e.dRampX; sp.rampy = e.dRampY;
+            sp.dst = e.dFrameOut; sp.pitch = (size_t)cw * 3;
+            sp.y_begin = bd[r].yBegin; sp.y_end = bd[r].yEnd;
+            launchStitch(sp, e.stream);
+            ++e.launches;
+            const size_t rows = (size_t)(bd[r].yEnd - bd[r].yBegin);
+            if (rows)
+                W2X_CUDA(cudaMemcpy2DAsync(dst + (size_t)bd[r].yBegin * dstStride, dstStride, e.dFrameOut + (size_t)bd[r].yBegin * cw * 3, (size_t)cw * 3,
+                                           (size_t)cw * 3, rows, cudaMemcpyDeviceToHost, e.stream));
+        }
+        for (int r = 0; r < bands; ++r) {
+            W2X_CUDA(cudaSetDevice(es[r]->cfg.deviceId));
+            W2X_CUDA(cudaStreamSynchronize(es[r]->stream));
+        }
+        return true;
+    } catch (const std::exception& ex) {
+        e0.log(W2X_ERROR, std::string("Row-band render failed unexpectedly: ") + ex.what() + ".", __FUNCTION__, __LINE__);
+        return false;
     }
 }
 

@@ -69,6 +69,8 @@ public:
     bool renderDevice(const uint8_t* dSrc, int w, int h, size_t srcStride, uint8_t* dDst, size_t dstStride);
     int submit(const uint8_t* src, int w, int h, size_t srcStride, uint8_t* dst, size_t dstStride);
     bool wait(int ticket);
+    // one image sharded over several engines (one per GPU) by bands of tile rows, seam rows exchanged peer-to-peer
+    static bool renderBanded(Engine* const* engines, int count, const uint8_t* src, int w, int h, size_t srcStride, uint8_t* dst, size_t dstStride);
     bool sync();
     bool infer(const float* inNchw, int n, float* outNchw);
     int profileLayers(int repeats, char (*names)[48], float* ms, double* flops, int cap);
@@ -111,6 +113,7 @@ private:
     PackedModel model;
     int tile = 0, outTile = 0, scale = 1, batch = 1;
     bool useDirect = false;
+    bool debugSync = false;      // W2X_DEBUG_SYNC: synchronise + check after every layer (names the failing kernel)
 
     std::vector<void*> allocs;       // freed in unload()
     std::vector<__half*> dW;         // per layer
@@ -152,6 +155,14 @@ private:
     std::vector<StageSpan> spans;
     cudaEvent_t nextEvent();
     cudaEvent_t timerEv[16] = {};
+    // row-band mode
+    __half* dBandTiles = nullptr;
+    size_t bandTilesCap = 0;
+    int* dBandMap = nullptr;
+    size_t bandMapCap = 0;
+    TileSlot* dBandSlots = nullptr;
+    size_t bandSlotCap = 0;
+    cudaEvent_t evBandModel = nullptr;
 };
 
 // On-device self-check of one implicit-GEMM layer (tcgen05 vs scalar reference); see w2x.h.

@@ -84,7 +84,19 @@ struct TileWalker {
     int tn, tx, ty, img;          // current tile indices
     int sn, sx, sy, simg;         // step decomposition
     int tilesN, tilesX, tilesY;
+    // per-image mode (SE layers): every CTA visits tiles first, first+step, ... of EACH image, so the grouping of an image's
+    // tiles into per-CTA partial sums -- and therefore its SE scale, bit for bit -- does not depend on the image's batch slot
+    int perImage, first_, step_, local;
+    __device__ __forceinline__ void initPerImage(int first, int step, int tilesX_, int tilesY_) {
+        perImage = 1; first_ = first; step_ = step; local = first;
+        tilesN = 1; tilesX = tilesX_; tilesY = tilesY_;
+        tn = 0; img = 0;
+        tx = first % tilesX; ty = first / tilesX;
+        sn = 0; simg = 0;
+        sx = step % tilesX; sy = step / tilesX;
+    }
     __device__ __forceinline__ void init(int first, int step, int tilesN_, int tilesX_, int tilesY_) {
+        perImage = 0; first_ = first; step_ = step; local = 0;
         tilesN = tilesN_; tilesX = tilesX_; tilesY = tilesY_;
         int t = first;
         tn = t % tilesN; t /= tilesN;
@@ -96,6 +108,19 @@ struct TileWalker {
         sy = t % tilesY; simg = t / tilesY;
     }
     __device__ __forceinline__ void next() {
+        if (perImage) {
+            local += step_;
+            if (local >= tilesX * tilesY) {  // next image, same tile subset
+                ++img;
+                local = first_;
+                tx = first_ % tilesX; ty = first_ / tilesX;
+            } else {
+                tx += sx;
+                const int c = tx >= tilesX; tx -= c * tilesX;
+                ty += sy + c;
+            }
+            return;
+        }
         tn += sn;
         int c = tn >= tilesN; tn -= c * tilesN;
         tx += sx + c;
@@ -108,6 +133,15 @@ struct TileWalker {
         return TileCoord{img, ty * bh, tx * bw, nBase + tn * bn};
     }
 };
+
+// number of tiles CTA `first` (of `step`) processes: global round-robin, or the same subset of every image for SE layers
+__device__ __forceinline__ int tilesForCta(const ConvArgs& a, int first, int step) {
+    if (a.p.se_sum) {
+        const int perImg = a.tilesX * a.tilesY;
+        return (perImg > first ? (perImg - 1 - first) / step + 1 : 0) * a.p.gn;
+    }
+    return a.totalTiles > first ? (a.totalTiles - 1 - first) / step + 1 : 0;
+}
 
 // coordinates of 64-channel sub-tile `s` of an N tile in the output / skip tensor-map views
 __device__ __forceinline__ void subTileCoords(const ConvArgs& a, const TileCoord& tc, int s, int& c0, int& cz) {
@@ -146,7 +180,8 @@ __device__ __forceinline__ void epilogueWarps(const ConvArgs& a, uint32_t base, 
     const bool active = split || half == 0;
 
     TileWalker w;
-    w.init(first, step, a.tilesN, a.tilesX, a.tilesY);
+    if (a.p.se_sum) w.initPerImage(first, step, a.tilesX, a.tilesY);
+    else w.init(first, step, a.tilesN, a.tilesX, a.tilesY);
     TileWalker ws = w;  // lookahead walker for skip-tile prefetch (leader only)
     int ksNext = 0;
     auto issueSkip = [&](int k) {
@@ -451,14 +486,15 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
     const uint32_t stageBytes = a.bytesA + a.bytesB;
     const uint32_t barFull = base + kOffFull, barEmpty = base + kOffEmpty, barTFull = base + kOffTFull, barTEmpty = base + kOffTEmpty;
     const int first = blockIdx.x, step = gridDim.x;
-    const int nMine = a.totalTiles > first ? (a.totalTiles - 1 - first) / step + 1 : 0;
+    const int nMine = tilesForCta(a, first, step);
 
     if (warp == 0) {
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
             TileWalker w;
-            w.init(first, step, a.tilesN, a.tilesX, a.tilesY);
+            if (a.p.se_sum) w.initPerImage(first, step, a.tilesX, a.tilesY);
+            else w.init(first, step, a.tilesN, a.tilesX, a.tilesY);
             for (int k = 0; k < nMine; ++k, w.next()) {
                 const TileCoord tc = w.coord(a.bh, a.bw, a.bn, 0);
                 for (int tap = 0; tap < a.p.ntaps; ++tap) {
@@ -531,7 +567,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_patch_kernel(const __grid
     // this CTA owns output-channel slice `slice` and every (gridDim/nSplit)-th pixel tile
     const int slice = blockIdx.x % a.nSplit, first = blockIdx.x / a.nSplit, step = gridDim.x / a.nSplit;
     const int n0 = slice * a.bn;
-    const int nMine = a.totalTiles > first ? (a.totalTiles - 1 - first) / step + 1 : 0;
+    const int nMine = tilesForCta(a, first, step);
     const uint32_t rowBytes = (uint32_t)a.kc * 2u;     // one pixel / one weight row of a K chunk: 128 B (kc=64) or 64 B (kc=32)
     const uint32_t tapBytes = (uint32_t)a.bn * rowBytes;  // one (tap, K chunk) block of B: [bn rows][kc]
 
@@ -545,7 +581,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_patch_kernel(const __grid
             int stage = 0;
             uint32_t phase = 0;
             TileWalker w;
-            w.init(first, step, 1, a.tilesX, a.tilesY);
+            if (a.p.se_sum) w.initPerImage(first, step, a.tilesX, a.tilesY);
+            else w.init(first, step, 1, a.tilesX, a.tilesY);
             for (int k = 0; k < nMine; ++k, w.next()) {
                 const TileCoord tc = w.coord(a.bh, a.bw, a.bn, n0);
                 for (int cc = 0; cc < a.cchunks; ++cc) {
@@ -928,8 +965,11 @@ IgemmPlan* igemmCreatePlan(const ConvParams& p) {
             plan->args.p.se_slots = igemmSeSlots(plan);
             if (plan->args.p.se_slots <= 0) throw Error("igemm: fused SE squeeze is not available for this layer shape");
         }
-        static bool attrSet = false;
-        if (!attrSet) {
+        static bool attrSet[64] = {};  // cudaFuncSetAttribute is per device (one engine per GPU in one process: row-band mode)
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev < 0 || dev >= 64) dev = 0;
+        if (!attrSet[dev]) {
             checkCuda(cudaFuncSetAttribute(igemm_kernel<EPI_K_DIRECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
             checkCuda(cudaFuncSetAttribute(igemm_kernel<EPI_K_TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
             checkCuda(cudaFuncSetAttribute(igemm_kernel<EPI_K_TMA_SKIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
@@ -938,7 +978,7 @@ IgemmPlan* igemmCreatePlan(const ConvParams& p) {
             checkCuda(cudaFuncSetAttribute(conv3x3_patch_kernel<EPI_K_TMA, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
             checkCuda(cudaFuncSetAttribute(conv3x3_patch_kernel<EPI_K_DIRECT, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
             checkCuda(cudaFuncSetAttribute(conv3x3_patch_kernel<EPI_K_TMA, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
-            attrSet = true;
+            attrSet[dev] = true;
         }
     } catch (...) {
         delete plan;

@@ -197,6 +197,10 @@ struct StitchParams {
     const float* rampy;  // [ovy]
     uint8_t* dst;
     size_t pitch;
+    // row-band mode (one image sharded over GPUs by tile rows): only output rows [y_begin, y_end) are produced, and tile
+    // (i, j) lives at slot tile_map[i * ny + j] of `tiles` (nullptr = identity, the reference's column-major order)
+    int y_begin, y_end;
+    const int* tile_map;
 };
 void launchStitch(const StitchParams& p, cudaStream_t s);
 void launchTtaReduce(const __half* outs, int tiles, int outT, float* mean, cudaStream_t s);

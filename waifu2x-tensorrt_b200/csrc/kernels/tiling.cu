@@ -98,8 +98,8 @@ __device__ __forceinline__ void loadTilePx(const void* tiles, size_t idx, float&
 template <bool F32>
 __global__ void __launch_bounds__(256) stitch_kernel(StitchParams p) {
     const int ox = blockIdx.x * 64 + (threadIdx.x & 63);
-    const int oy = blockIdx.y * 4 + (threadIdx.x >> 6);
-    if (ox >= p.cw || oy >= p.ch) return;
+    const int oy = p.y_begin + blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (ox >= p.cw || oy >= p.y_end) return;
     const int stx = p.outT - p.ovx, sty = p.outT - p.ovy;
     int ti[2], tj[2], ni = 0, nj = 0;
     {
@@ -129,7 +129,8 @@ __global__ void __launch_bounds__(256) stitch_kernel(StitchParams p) {
             if (ty0 > 0 && ly < p.ovy) wt = p.rampy[ly];
             if (ty0 + th < p.ch && p.outT - 1 - ly < p.ovy) wb = p.rampy[p.outT - 1 - ly];
             float r, g, b;
-            loadTilePx<F32>(p.tiles, ((size_t)(i * p.ny + j) * p.outT + ly) * p.outT + lx, r, g, b);
+            const int slot = p.tile_map ? __ldg(p.tile_map + i * p.ny + j) : i * p.ny + j;
+            loadTilePx<F32>(p.tiles, ((size_t)slot * p.outT + ly) * p.outT + lx, r, g, b);
             // sequential in-place multiplies in the reference order: left, top, right, bottom (x1.0 is exact)
             r = __fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(r, wl), wt), wr), wb);
             g = __fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(g, wl), wt), wr), wb);
@@ -149,8 +150,11 @@ __global__ void __launch_bounds__(256) stitch_kernel(StitchParams p) {
     d[2] = (uint8_t)ir;
 }
 
-void launchStitch(const StitchParams& p, cudaStream_t s) {
-    dim3 grid((p.cw + 63) / 64, (p.ch + 3) / 4);
+void launchStitch(const StitchParams& pin, cudaStream_t s) {
+    StitchParams p = pin;
+    if (p.y_end <= 0) { p.y_begin = 0; p.y_end = p.ch; }  // whole canvas
+    if (p.y_end <= p.y_begin) return;
+    dim3 grid((p.cw + 63) / 64, (p.y_end - p.y_begin + 3) / 4);
     if (p.f32) stitch_kernel<true><<<grid, 256, 0, s>>>(p);
     else stitch_kernel<false><<<grid, 256, 0, s>>>(p);
 }

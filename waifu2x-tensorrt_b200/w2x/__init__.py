@@ -99,6 +99,7 @@ _SIGNATURES = {
     "w2x_render": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_size_t]),
     "w2x_render_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_size_t]),
     "w2x_submit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_size_t]),
+    "w2x_render_banded": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_size_t]),
     "w2x_wait": (C.c_int, [C.c_void_p, C.c_int]),
     "w2x_sync": (C.c_int, [C.c_void_p]),
     "w2x_host_alloc": (C.c_void_p, [C.c_size_t]),
@@ -358,6 +359,17 @@ class Img2Img:
     def d2h(self, arr: np.ndarray, dptr: int):
         if not self._l.w2x_memcpy_d2h(self._h, _ptr(arr), C.c_void_p(dptr), arr.nbytes):
             raise RuntimeError("d2h failed")
+
+
+def render_banded(engines: List["Img2Img"], src: np.ndarray) -> Optional[np.ndarray]:
+    """One image over several engines (one per GPU): bands of tile rows + P2P seam exchange."""
+    src = np.ascontiguousarray(src, dtype=np.uint8)
+    h, w = src.shape[:2]
+    s = engines[0].scaling
+    dst = np.empty((h * s, w * s, 3), np.uint8)
+    arr = (C.c_void_p * len(engines))(*[e._h for e in engines])
+    ok = lib().w2x_render_banded(arr, len(engines), _ptr(src), w, h, src.strides[0], _ptr(dst), dst.strides[0])
+    return dst if ok else None
 
 
 class PinnedArray:
