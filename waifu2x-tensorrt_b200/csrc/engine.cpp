@@ -347,21 +347,21 @@ void Engine::buildPlanCunet() {
         else if (igemmSupported(p)) {
             E.impl = IMPL_IGEMM;
             if (L.se_r) {
-                // fused squeeze: the conv epilogue writes deterministic per-CTA partial sums (<= 4 slots per CTA)
-                E.sePartialBytes = (size_t)batch * 148 * 8 * L.npad * 4;
-                E.sePartial = (float*)dalloc(E.sePartialBytes);
+                // fused squeeze: the conv epilogue accumulates exact fixed-point channel sums (int64 atomics) per image
+                E.sePartialBytes = (size_t)batch * L.npad * sizeof(long long);
+                E.sePartial = (long long*)dalloc(E.sePartialBytes);
                 E.p.se_sum = E.sePartial;
+                E.seFused = true;
             }
             E.plan = igemmCreatePlan(E.p);
-            if (L.se_r) { E.seBlocks = igemmSeSlots(E.plan); E.seFused = true; E.sePartialBytes = (size_t)batch * E.seBlocks * L.npad * 4; }
         }
         else throw Error("no kernel for layer " + L.name);
         if (L.se_r) {
             E.seR = (int)L.se_r;
             E.seW1 = upload(L.se_w1); E.seB1 = upload(L.se_b1); E.seW2 = upload(L.se_w2); E.seB2 = upload(L.se_b2);
             if (!E.seFused) {
-                E.seBlocks = 32;
-                E.sePartial = (float*)dalloc((size_t)batch * E.seBlocks * L.cout * 4);
+                E.sePartialBytes = (size_t)batch * L.cout * sizeof(long long);
+                E.sePartial = (long long*)dalloc(E.sePartialBytes);
             }
             E.seScale = (float*)dalloc((size_t)batch * L.cout * 4);
         }
@@ -664,7 +664,7 @@ double Engine::flopsPerTile() const {
 void Engine::runModel(cudaStream_t s, __half* finalOut) {
     for (auto& L : layers) {
         __half* outp = (L.isFinal && finalOut) ? finalOut : L.p.out;
-        if (L.seFused) W2X_CUDA(cudaMemsetAsync(L.sePartial, 0, L.sePartialBytes, s));
+        if (L.seR) W2X_CUDA(cudaMemsetAsync(L.sePartial, 0, L.sePartialBytes, s));
         launchLayer(L, s, outp);
         ++launches;
         if (debugSync) {
@@ -673,8 +673,8 @@ void Engine::runModel(cudaStream_t s, __half* finalOut) {
             if (de != cudaSuccess) throw Error("layer '" + L.name + "': " + cudaGetErrorString(de));
         }
         if (L.seR) {
-            if (!L.seFused) { launchSeSqueeze(L.p.out, L.p.gn, L.p.out_h, L.p.out_w, L.p.out_c, L.sePartial, L.seBlocks, s); ++launches; }
-            launchSeExcite(L.sePartial, L.seBlocks, L.p.gn, L.p.out_c, L.seR, L.p.out_h * L.p.out_w, L.seW1, L.seB1, L.seW2, L.seB2, L.seScale, s);
+            if (!L.seFused) { launchSeSqueeze(L.p.out, L.p.gn, L.p.out_h, L.p.out_w, L.p.out_c, L.sePartial, s); ++launches; }
+            launchSeExcite(L.sePartial, L.p.gn, L.p.out_c, L.seR, L.p.out_h * L.p.out_w, L.seW1, L.seB1, L.seW2, L.seB2, L.seScale, s);
             ++launches;
             if (L.foldJobs.empty()) { launchSeScale(L.p.out, L.p.gn, L.p.out_h, L.p.out_w, L.p.out_c, L.seScale, s); ++launches; }
             for (const auto& j : L.foldJobs) { launchScaleWeights(j.w, j.wOut, L.seScale, L.p.gn, j.npad, j.ktot, j.cin, s); ++launches; }
@@ -1088,11 +1088,11 @@ int Engine::profileLayers(int repeats, char (*names)[48], float* ms, double* flo
             if (i >= cap) break;
             W2X_CUDA(cudaEventRecord(e0, stream));
             for (int r = 0; r < repeats; ++r) {
-                if (L.seFused) W2X_CUDA(cudaMemsetAsync(L.sePartial, 0, L.sePartialBytes, stream));
+                if (L.seR) W2X_CUDA(cudaMemsetAsync(L.sePartial, 0, L.sePartialBytes, stream));
                 launchLayer(L, stream, nullptr);
                 if (L.seR) {
-                    if (!L.seFused) launchSeSqueeze(L.p.out, L.p.gn, L.p.out_h, L.p.out_w, L.p.out_c, L.sePartial, L.seBlocks, stream);
-                    launchSeExcite(L.sePartial, L.seBlocks, L.p.gn, L.p.out_c, L.seR, L.p.out_h * L.p.out_w, L.seW1, L.seB1, L.seW2, L.seB2, L.seScale, stream);
+                    if (!L.seFused) launchSeSqueeze(L.p.out, L.p.gn, L.p.out_h, L.p.out_w, L.p.out_c, L.sePartial, stream);
+                    launchSeExcite(L.sePartial, L.p.gn, L.p.out_c, L.seR, L.p.out_h * L.p.out_w, L.seW1, L.seB1, L.seW2, L.seB2, L.seScale, stream);
                     if (L.foldJobs.empty()) launchSeScale(L.p.out, L.p.gn, L.p.out_h, L.p.out_w, L.p.out_c, L.seScale, stream);
                     for (const auto& j : L.foldJobs) launchScaleWeights(j.w, j.wOut, L.seScale, L.p.gn, j.npad, j.ktot, j.cin, stream);
                 }

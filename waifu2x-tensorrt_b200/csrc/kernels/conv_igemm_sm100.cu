@@ -84,19 +84,7 @@ struct TileWalker {
     int tn, tx, ty, img;          // current tile indices
     int sn, sx, sy, simg;         // step decomposition
     int tilesN, tilesX, tilesY;
-    // per-image mode (SE layers): every CTA visits tiles first, first+step, ... of EACH image, so the grouping of an image's
-    // tiles into per-CTA partial sums -- and therefore its SE scale, bit for bit -- does not depend on the image's batch slot
-    int perImage, first_, step_, local;
-    __device__ __forceinline__ void initPerImage(int first, int step, int tilesX_, int tilesY_) {
-        perImage = 1; first_ = first; step_ = step; local = first;
-        tilesN = 1; tilesX = tilesX_; tilesY = tilesY_;
-        tn = 0; img = 0;
-        tx = first % tilesX; ty = first / tilesX;
-        sn = 0; simg = 0;
-        sx = step % tilesX; sy = step / tilesX;
-    }
     __device__ __forceinline__ void init(int first, int step, int tilesN_, int tilesX_, int tilesY_) {
-        perImage = 0; first_ = first; step_ = step; local = 0;
         tilesN = tilesN_; tilesX = tilesX_; tilesY = tilesY_;
         int t = first;
         tn = t % tilesN; t /= tilesN;
@@ -108,19 +96,6 @@ struct TileWalker {
         sy = t % tilesY; simg = t / tilesY;
     }
     __device__ __forceinline__ void next() {
-        if (perImage) {
-            local += step_;
-            if (local >= tilesX * tilesY) {  // next image, same tile subset
-                ++img;
-                local = first_;
-                tx = first_ % tilesX; ty = first_ / tilesX;
-            } else {
-                tx += sx;
-                const int c = tx >= tilesX; tx -= c * tilesX;
-                ty += sy + c;
-            }
-            return;
-        }
         tn += sn;
         int c = tn >= tilesN; tn -= c * tilesN;
         tx += sx + c;
@@ -134,12 +109,8 @@ struct TileWalker {
     }
 };
 
-// number of tiles CTA `first` (of `step`) processes: global round-robin, or the same subset of every image for SE layers
+// number of tiles CTA `first` (of `step`) processes (global round-robin)
 __device__ __forceinline__ int tilesForCta(const ConvArgs& a, int first, int step) {
-    if (a.p.se_sum) {
-        const int perImg = a.tilesX * a.tilesY;
-        return (perImg > first ? (perImg - 1 - first) / step + 1 : 0) * a.p.gn;
-    }
     return a.totalTiles > first ? (a.totalTiles - 1 - first) / step + 1 : 0;
 }
 
@@ -180,8 +151,7 @@ __device__ __forceinline__ void epilogueWarps(const ConvArgs& a, uint32_t base, 
     const bool active = split || half == 0;
 
     TileWalker w;
-    if (a.p.se_sum) w.initPerImage(first, step, a.tilesX, a.tilesY);
-    else w.init(first, step, a.tilesN, a.tilesX, a.tilesY);
+    w.init(first, step, a.tilesN, a.tilesX, a.tilesY);
     TileWalker ws = w;  // lookahead walker for skip-tile prefetch (leader only)
     int ksNext = 0;
     auto issueSkip = [&](int k) {
@@ -207,22 +177,14 @@ __device__ __forceinline__ void epilogueWarps(const ConvArgs& a, uint32_t base, 
     const int seC = et & (a.bn - 1);
     const int seG = et / a.bn;                         // 256 / bn row groups
     const int seRows = (128 * a.bn) / kEpiThreads;     // rows per group
-    const int seGroups = kEpiThreads / a.bn;
-    float seAcc = 0.f;
+    long long seAcc = 0;
     int seImg = -1;
     int skipScaleImg = -1;
-    // image boundary (uniform across the epilogue threads): combine the row groups in a fixed order, one slot per CTA
+    // image boundary: one integer atomic per (thread, image); integer addition is exact, so the total is independent of the
+    // tile -> CTA assignment and of the image's position in the batch (byte-identical results for any sharding)
     auto seFlush = [&]() {
-        if (seImg < 0) return;
-        float* scratch = reinterpret_cast<float*>(__cvta_shared_to_generic((size_t)(base + a.headerBytes - 1024u)));
-        scratch[et] = seAcc;
-        namedBarSync(2, kEpiThreads);
-        if (seG == 0) {
-            float t = 0.f;
-            for (int g = 0; g < seGroups; ++g) t += scratch[g * a.bn + seC];
-            a.p.se_sum[((size_t)seImg * a.p.se_slots + first) * a.p.npad + nBase + seC] = t;
-        }
-        namedBarSync(2, kEpiThreads);
+        if (seImg >= 0 && seAcc != 0)
+            atomicAdd(reinterpret_cast<unsigned long long*>(a.p.se_sum + (size_t)seImg * a.p.npad + nBase + seC), (unsigned long long)seAcc);
     };
 
     int acc = 0;
@@ -415,17 +377,17 @@ __device__ __forceinline__ void epilogueWarps(const ConvArgs& a, uint32_t base, 
                 bulkCommit();
             }
             if (doSe) {
-                if (tc.img != seImg) { seFlush(); seImg = tc.img; seAcc = 0.f; }
+                if (tc.img != seImg) { seFlush(); seImg = tc.img; seAcc = 0; }
                 const uint32_t colOff = (uint32_t)(seC >> 6) * 16384u;
                 const int cc = seC & 63;
-                float sacc = 0.f;
+                long long sacc = 0;
                 for (int i = 0; i < seRows; ++i) {
                     const int mm = seG * seRows + i;
                     const bool ok = (tc.y0 + (mm >> a.bwShift)) < a.p.gy && (tc.x0 + (mm & (a.bw - 1))) < a.p.gx;
                     const uint32_t addr = stg + colOff + (uint32_t)mm * 128u + ((uint32_t)((cc >> 3) ^ (mm & 7)) << 4) + (uint32_t)(cc & 7) * 2u;
                     unsigned short hv;
                     asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hv) : "r"(addr));
-                    if (ok) sacc += __half2float(__ushort_as_half(hv));
+                    if (ok) sacc += (long long)__float2int_rn(__half2float(__ushort_as_half(hv)) * kSeFixedScale);
                 }
                 seAcc += sacc;
             }
@@ -493,8 +455,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
             int stage = 0;
             uint32_t phase = 0;
             TileWalker w;
-            if (a.p.se_sum) w.initPerImage(first, step, a.tilesX, a.tilesY);
-            else w.init(first, step, a.tilesN, a.tilesX, a.tilesY);
+            w.init(first, step, a.tilesN, a.tilesX, a.tilesY);
             for (int k = 0; k < nMine; ++k, w.next()) {
                 const TileCoord tc = w.coord(a.bh, a.bw, a.bn, 0);
                 for (int tap = 0; tap < a.p.ntaps; ++tap) {
@@ -581,8 +542,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_patch_kernel(const __grid
             int stage = 0;
             uint32_t phase = 0;
             TileWalker w;
-            if (a.p.se_sum) w.initPerImage(first, step, a.tilesX, a.tilesY);
-            else w.init(first, step, 1, a.tilesX, a.tilesY);
+            w.init(first, step, 1, a.tilesX, a.tilesY);
             for (int k = 0; k < nMine; ++k, w.next()) {
                 const TileCoord tc = w.coord(a.bh, a.bw, a.bn, n0);
                 for (int cc = 0; cc < a.cchunks; ++cc) {
@@ -961,10 +921,7 @@ IgemmPlan* igemmCreatePlan(const ConvParams& p) {
         static const bool noPatch = [] { const char* e = std::getenv("W2X_NO_PATCH"); return e && *e == '1'; }();
         if (!noPatch && wantsPatchKernel(p)) planPatch(plan);
         else planIgemm(plan);
-        if (p.se_sum) {
-            plan->args.p.se_slots = igemmSeSlots(plan);
-            if (plan->args.p.se_slots <= 0) throw Error("igemm: fused SE squeeze is not available for this layer shape");
-        }
+        if (p.se_sum && !igemmSeFusable(plan)) throw Error("igemm: fused SE squeeze is not available for this layer shape");
         static bool attrSet[64] = {};  // cudaFuncSetAttribute is per device (one engine per GPU in one process: row-band mode)
         int dev = 0;
         cudaGetDevice(&dev);
@@ -989,10 +946,9 @@ IgemmPlan* igemmCreatePlan(const ConvParams& p) {
 
 void igemmDestroyPlan(IgemmPlan* plan) { delete plan; }
 
-int igemmSeSlots(const IgemmPlan* plan) {
+bool igemmSeFusable(const IgemmPlan* plan) {
     const ConvArgs& a = plan->args;
-    if (!a.useTma || a.hasSkip || a.nbuf < 2 || a.tilesN != 1 || a.bn < 64) return 0;
-    return plan->grid / a.nSplit;  // one slot per CTA of an output-channel slice
+    return a.useTma && !a.hasSkip && a.nbuf >= 2 && a.tilesN == 1 && a.bn >= 64;
 }
 
 const char* igemmDescribe(const IgemmPlan* plan, char* buf, int cap) {

@@ -48,9 +48,10 @@ struct ConvParams {
     const __half* skip;
     int skip_h, skip_w, skip_c, skip_off;
     const float* skip_scale;  // optional per-(img, channel) multiplier applied to skip (SE fold), or nullptr
-    float* se_sum;            // optional [gn][se_slots][npad] fp32: deterministic per-CTA partial sums of the stored
-                              // activations (fused SE squeeze); the buffer must be zeroed before the launch
-    int se_slots;             // filled in by igemmCreatePlan
+    long long* se_sum;        // optional [gn][npad] int64: fused SE squeeze = sum over the image of round(activation * 2^14),
+                              // accumulated with integer atomics (exact, so the result does not depend on which CTA saw which
+                              // tile or on the image's batch slot); the buffer must be zeroed before the launch
+    int se_slots;             // unused (kept for ABI stability of the struct inside this library)
 };
 
 #ifdef __CUDACC__
@@ -169,7 +170,7 @@ void igemmDestroyPlan(IgemmPlan* plan);
 void igemmLaunch(const IgemmPlan* plan, cudaStream_t s, __half* outOverride = nullptr);
 bool igemmSupported(const ConvParams& p);
 const char* igemmDescribe(const IgemmPlan* plan, char* buf, int cap);
-int igemmSeSlots(const IgemmPlan* plan);  // partial-sum slots per image when ConvParams::se_sum is set (0 = unsupported)
+bool igemmSeFusable(const IgemmPlan* plan);  // can this layer's epilogue produce ConvParams::se_sum?
 int probeUmma(int mode, int pitch, float* err9);
 
 // SwinUNet token kernels (kernels/swin.cu)
@@ -178,8 +179,9 @@ void launchWindowAttention(const __half* qkv, __half* out, int n, int h, int w, 
                            const float* relpos, cudaStream_t s);
 
 // squeeze/excite
-void launchSeSqueeze(const __half* x, int n, int h, int w, int c, float* partial, int nblk, cudaStream_t s);
-void launchSeExcite(const float* partial, int nblk, int n, int c, int r, int hw, const float* w1, const float* b1,
+constexpr float kSeFixedScale = 16384.f;  // 2^14 fixed-point resolution of the squeeze sums
+void launchSeSqueeze(const __half* x, int n, int h, int w, int c, long long* sums, cudaStream_t s);  // sums must be zeroed
+void launchSeExcite(const long long* sums, int n, int c, int r, int hw, const float* w1, const float* b1,
                     const float* w2, const float* b2, float* scale, cudaStream_t s);
 void launchSeScale(__half* x, int n, int h, int w, int c, const float* scale, cudaStream_t s);
 // W'[img][n][k] = W[n][k] * scale[img][k % cin]: folds an SE channel scale into the CONSUMER's weights (one copy per image)

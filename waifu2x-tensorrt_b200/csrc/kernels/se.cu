@@ -8,44 +8,27 @@
 
 namespace w2x {
 
-// grid (nblk, n), 256 threads.  Thread t owns channel pair (t % (c/2)) of pixels p = t / (c/2) + k * (256 / (c/2)).
-__global__ void __launch_bounds__(256) se_squeeze_kernel(const __half* __restrict__ x, int hw, int c,
-                                                         float* __restrict__ partial, int nblk) {
-    extern __shared__ float red[];  // [256][2]
+// Stand-alone squeeze (only used when the producing conv cannot fuse it, e.g. W2X_CONV_IMPL=direct): same exact
+// fixed-point integer accumulation as the fused epilogue.  grid (nblk, n), 256 threads; thread t owns channel t % c.
+__global__ void __launch_bounds__(256) se_squeeze_kernel(const __half* __restrict__ x, int hw, int c, long long* __restrict__ sums, int nblk) {
     const int img = blockIdx.y, blk = blockIdx.x;
-    const int cp = c >> 1;
-    const int lane_c = threadIdx.x % cp, lane_p = threadIdx.x / cp, pstride = 256 / cp;
+    const int lane_c = threadIdx.x % c, lane_p = threadIdx.x / c, pstride = 256 / c;
     const int per = (hw + nblk - 1) / nblk;
     const int p0 = blk * per, p1 = min(hw, p0 + per);
-    const __half2* base = reinterpret_cast<const __half2*>(x + (size_t)img * hw * c);
-    float s0 = 0.f, s1 = 0.f;
-    for (int p = p0 + lane_p; p < p1; p += pstride) {
-        const float2 v = __half22float2(base[(size_t)p * cp + lane_c]);
-        s0 += v.x;
-        s1 += v.y;
-    }
-    red[threadIdx.x * 2] = s0;
-    red[threadIdx.x * 2 + 1] = s1;
-    __syncthreads();
-    if (threadIdx.x < cp) {
-        float a = 0.f, b = 0.f;
-        for (int k = 0; k < pstride; ++k) {
-            a += red[(k * cp + threadIdx.x) * 2];
-            b += red[(k * cp + threadIdx.x) * 2 + 1];
-        }
-        float* o = partial + ((size_t)img * nblk + blk) * c + 2 * threadIdx.x;
-        o[0] = a;
-        o[1] = b;
-    }
+    const __half* base = x + (size_t)img * hw * c;
+    long long s = 0;
+    if (lane_p < pstride)
+        for (int p = p0 + lane_p; p < p1; p += pstride) s += (long long)__float2int_rn(__half2float(base[(size_t)p * c + lane_c]) * kSeFixedScale);
+    if (s != 0) atomicAdd(reinterpret_cast<unsigned long long*>(sums + (size_t)img * c + lane_c), (unsigned long long)s);
 }
 
-void launchSeSqueeze(const __half* x, int n, int h, int w, int c, float* partial, int nblk, cudaStream_t s) {
-    dim3 grid(nblk, n);
-    se_squeeze_kernel<<<grid, 256, 256 * 2 * sizeof(float), s>>>(x, h * w, c, partial, nblk);
+void launchSeSqueeze(const __half* x, int n, int h, int w, int c, long long* sums, cudaStream_t s) {
+    dim3 grid(64, n);
+    se_squeeze_kernel<<<grid, 256, 0, s>>>(x, h * w, c, sums, 64);
 }
 
 // grid n, block 256.  mean -> relu(W1 mean + b1) -> sigmoid(W2 h + b2)
-__global__ void __launch_bounds__(256) se_excite_kernel(const float* __restrict__ partial, int nblk, int c, int r, float inv_hw,
+__global__ void __launch_bounds__(256) se_excite_kernel(const long long* __restrict__ sums, int c, int r, float inv_hw,
                                                         const float* __restrict__ w1, const float* __restrict__ b1,
                                                         const float* __restrict__ w2, const float* __restrict__ b2,
                                                         float* __restrict__ scale) {
@@ -57,28 +40,8 @@ __global__ void __launch_bounds__(256) se_excite_kernel(const float* __restrict_
     const bool fcInSmem = fcElems <= 2048;
     if (fcInSmem)
         for (int i = threadIdx.x; i < fcElems; i += blockDim.x) { sw1[i] = w1[i]; sw2[i] = w2[i]; }
-    {
-        // all 256 threads reduce the partial sums: (256 / c) slot groups per channel, fixed combination order
-        __shared__ float part[256];
-        const int groups = 256 / c, ch = threadIdx.x % c, g = threadIdx.x / c;
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-        const float* pb = partial + (size_t)img * nblk * c + ch;
-        int b = g;
-        for (; b + 3 * groups < nblk; b += 4 * groups) {
-            s0 += pb[(size_t)b * c];
-            s1 += pb[(size_t)(b + groups) * c];
-            s2 += pb[(size_t)(b + 2 * groups) * c];
-            s3 += pb[(size_t)(b + 3 * groups) * c];
-        }
-        for (; b < nblk; b += groups) s0 += pb[(size_t)b * c];
-        part[threadIdx.x] = (s0 + s1) + (s2 + s3);
-        __syncthreads();
-        if (threadIdx.x < c) {
-            float s = 0.f;
-            for (int q = 0; q < groups; ++q) s += part[q * c + threadIdx.x];
-            mean[threadIdx.x] = s * inv_hw;
-        }
-    }
+    for (int ch = threadIdx.x; ch < c; ch += blockDim.x)
+        mean[ch] = (float)((double)sums[(size_t)img * c + ch] * (1.0 / (double)kSeFixedScale)) * inv_hw;
     __syncthreads();
     const float* W1 = fcInSmem ? sw1 : w1;
     const float* W2 = fcInSmem ? sw2 : w2;
@@ -101,9 +64,9 @@ __global__ void __launch_bounds__(256) se_excite_kernel(const float* __restrict_
     }
 }
 
-void launchSeExcite(const float* partial, int nblk, int n, int c, int r, int hw, const float* w1, const float* b1,
+void launchSeExcite(const long long* sums, int n, int c, int r, int hw, const float* w1, const float* b1,
                     const float* w2, const float* b2, float* scale, cudaStream_t s) {
-    se_excite_kernel<<<n, 256, 0, s>>>(partial, nblk, c, r, 1.0f / (float)hw, w1, b1, w2, b2, scale);
+    se_excite_kernel<<<n, 256, 0, s>>>(sums, c, r, 1.0f / (float)hw, w1, b1, w2, b2, scale);
 }
 
 // in-place x *= scale[img][ch], 8 channels (16 B) per thread
