@@ -168,6 +168,10 @@ W2X_API double w2x_selftest_conv(int device, int kind, int n, int h, int w, int 
  * err9[tap] = max |device - host|.  Returns 0 on success. */
 W2X_API int w2x_probe_umma(int device, int mode, int pitch, float* err9);
 
+/* Development probe: milliseconds for `iters` x 4 back-to-back tcgen05.mma (M=128, N=n, K=16, fp16) issued on every SM
+ * from the same smem operands (A descriptor SBO = sbo_a bytes); cycles per MMA = ms * clock / (4 * iters). */
+W2X_API float w2x_probe_mma_rate(int device, int n, int iters, int sbo_a);
+
 /* Host-only helpers (no GPU needed). */
 /* getConfigHash (img2img_build.cpp:8-27) on an explicit device name: writes 64 hex chars + NUL. */
 W2X_API void w2x_config_hash(const char* device_name, const w2x_build_config* cfg, char out_hex[65]);

@@ -143,6 +143,28 @@ def test_pipelined_submit_equals_sync_render(built_lib, models_dir):
         p.free()
 
 
+def test_reload_and_changing_frame_sizes(built_lib, models_dir):
+    """load may be called repeatedly (img2img_load.cpp:149-163,209-222 tears the engine down and re-allocates); frames of
+    different sizes through one engine must not disturb each other."""
+    import w2x
+    e, model_t, msgs = _engine(models_dir, 2, 64, 2)
+    a = tiling.synthetic_frame(90, 70, 1)
+    b = tiling.synthetic_frame(140, 64, 2)
+    ra, rb = e.render(a).copy(), e.render(b).copy()
+    assert np.array_equal(e.render(a), ra) and np.array_equal(e.render(b), rb)
+    _, per = models_dir
+    path1 = per[1][1]
+    assert e.build(path1, w2x.BuildConfig.fixed(3, 128)), msgs
+    assert e.load(path1, w2x.RenderConfig(batchSize=3, height=128, width=128, scaling=1)), msgs   # different model, tile, batch
+    assert e.output_tile_size == 72
+    r1 = e.render(a)
+    assert r1 is not None and r1.shape == a.shape
+    path2 = per[2][1]
+    assert e.load(path2, w2x.RenderConfig(batchSize=2, height=64, width=64, scaling=2)), msgs      # back to the first config
+    assert np.array_equal(e.render(a), ra)
+    e.close()
+
+
 def test_flops_per_tile_matches_survey(built_lib, models_dir):
     """UpCUNet T=256 = 81.90 GFLOP / tile; T=64 = 2.39 GFLOP."""
     e, _, _ = _engine(models_dir, 2, 64, 1)

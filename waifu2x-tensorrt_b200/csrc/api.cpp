@@ -247,6 +247,11 @@ int w2x_probe_umma(int device, int mode, int pitch, float* err9) {
     }
 }
 
+float w2x_probe_mma_rate(int device, int n, int iters, int sbo_a) {
+    if (cudaSetDevice(device) != cudaSuccess) return -1.f;
+    try { return probeMmaRate(n, iters, sbo_a); } catch (...) { return -3.f; }
+}
+
 void w2x_config_hash(const char* device_name, const w2x_build_config* cfg, char out_hex[65]) {
     if (!out_hex) return;
     out_hex[0] = 0;

@@ -673,6 +673,46 @@ __global__ void __launch_bounds__(128, 1) umma_probe_kernel(const __grid_constan
 }
 
 
+// ------------------------------------------------------------------------------------------------------------
+// UMMA issue-rate probe (development aid, w2x_probe_mma_rate): every SM issues `iters` x 4 back-to-back
+// tcgen05.mma (M = 128, N = n, K = 16) on the same smem operands; cycles per MMA = time * clock / (4 * iters).
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1) umma_rate_kernel(int n, int iters, int sboA) {
+    extern __shared__ uint8_t smemRaw[];
+    const uint32_t rawAddr = smemU32(smemRaw);
+    const uint32_t base = (rawAddr + 1023u) & ~1023u;
+    uint8_t* sm = smemRaw + (base - rawAddr);
+    const uint32_t bar = base;
+    volatile uint32_t* tmemSlot = reinterpret_cast<volatile uint32_t*>(sm + 32);
+    const uint32_t sA = base + 1024, sB = sA + 32768;
+    for (uint32_t i = threadIdx.x; i < (32768u + 32768u) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(sm + 1024)[i] = 0u;
+    const int warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) { mbarInit(bar, 1); mbarInitFence(); }
+    if (warp == 0) tmemAlloc(smemU32((const void*)tmemSlot), 256);
+    fenceProxyAsync();
+    tcFenceBefore();
+    __syncthreads();
+    tcFenceAfter();
+    const uint32_t tmemBase = *tmemSlot;
+    if (warp == 1) {
+        if (electOne()) {
+            const uint32_t idesc = instrDescF16(128, n);
+            const uint32_t hiA = descHi((uint32_t)sboA, 2), hiB = descHi(1024, 2);
+            const uint32_t aLo = descLo(sA), bLo = descLo(sB);
+            for (int it = 0; it < iters; ++it) {
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) ummaLoHi(tmemBase, aLo + 2u * ks, hiA, bLo + 2u * ks, hiB, idesc, 1u);
+            }
+            tcCommit(bar);
+        }
+        __syncwarp();
+    }
+    mbarWait(bar, 0);
+    tcFenceBefore();
+    __syncthreads();
+    if (warp == 0) { tcFenceAfter(); tmemDealloc(tmemBase, 256); }
+}
+
 // ---- host side -------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -1039,4 +1079,21 @@ int probeUmma(int mode, int pitch, float* err9) {
 }
 
 
+
+// ms for `iters` x 4 MMAs per SM (all SMs busy); returns < 0 on error
+float probeMmaRate(int n, int iters, int sboA) {
+    if (n < 16 || n > 256 || n % 16) return -1.f;
+    cudaFuncSetAttribute(umma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    umma_rate_kernel<<<numSMs(), 128, 70 * 1024>>>(n, 16, sboA);  // warm-up
+    cudaEventRecord(e0);
+    umma_rate_kernel<<<numSMs(), 128, 70 * 1024>>>(n, iters, sboA);
+    cudaEventRecord(e1);
+    if (cudaEventSynchronize(e1) != cudaSuccess) return -2.f;
+    float ms = -1.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return ms;
+}
 }  // namespace w2x
