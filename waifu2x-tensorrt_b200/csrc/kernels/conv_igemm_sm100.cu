@@ -338,30 +338,51 @@ __device__ __forceinline__ void epilogueWarps(const ConvArgs& a, uint32_t base, 
             const uint32_t sbuf = staging + (uint32_t)(k & (a.nbuf - 1)) * a.stagedBuf;
             const int chunksPerRow = a.bn >> 3;
             const int et2 = threadIdx.x - 64;
-            for (int idx = et2; idx < 128 * chunksPerRow; idx += kEpiThreads) {
-                const int row = idx / chunksPerRow, cc = idx - row * chunksPerRow;
+            const int total = 128 * chunksPerRow;
+            auto chunkOffset = [&](int row, int cc, bool& ok) -> long long {
                 const int yy2 = tc.y0 + (row >> a.bwShift), xx2 = tc.x0 + (row & (a.bw - 1));
-                if (yy2 < a.p.gy && xx2 < a.p.gx) {
-                    uint4 v = ldsV4(sbuf + (uint32_t)row * a.stagedPitch + (uint32_t)cc * 16u);
-                    long long off;
-                    if (a.p.mode == EPI_D2S) {  // pixel shuffle: column (q*cout + co) -> output pixel (2y + q/2, 2x + q%2), channel co
-                        const int j = tc.n0 + cc * 8;
-                        const int q = j / a.p.cout, co = j - q * a.p.cout;
-                        off = (((long long)tc.img * a.p.out_h + 2 * yy2 + (q >> 1)) * a.p.out_w + 2 * xx2 + (q & 1)) * a.p.out_c + co;
-                    } else {
-                        off = (((long long)tc.img * a.p.out_h + yy2) * a.p.out_w + xx2) * a.p.out_c + tc.n0 + cc * 8;
-                    }
-                    if (a.p.skip) {
-                        const uint4 sv = *reinterpret_cast<const uint4*>(a.p.skip + off);
-                        __half2* vh = reinterpret_cast<__half2*>(&v);
-                        const __half2* sh = reinterpret_cast<const __half2*>(&sv);
+                ok = yy2 < a.p.gy && xx2 < a.p.gx;
+                if (a.p.mode == EPI_D2S) {  // pixel shuffle: column (q*cout + co) -> output pixel (2y + q/2, 2x + q%2), channel co
+                    const int j = tc.n0 + cc * 8;
+                    const int q = j / a.p.cout, co = j - q * a.p.cout;
+                    return (((long long)tc.img * a.p.out_h + 2 * yy2 + (q >> 1)) * a.p.out_w + 2 * xx2 + (q & 1)) * a.p.out_c + co;
+                }
+                return (((long long)tc.img * a.p.out_h + yy2) * a.p.out_w + xx2) * a.p.out_c + tc.n0 + cc * 8;
+            };
+            if (a.p.skip) {
+                // residual layers: two chunks per thread per round, both residual loads in flight before either is consumed
+                for (int idx0 = et2; idx0 < total; idx0 += 2 * kEpiThreads) {
+                    const int idx1 = idx0 + kEpiThreads;
+                    const int row0 = idx0 / chunksPerRow, cc0 = idx0 - row0 * chunksPerRow;
+                    const int row1 = idx1 < total ? idx1 / chunksPerRow : row0, cc1 = idx1 < total ? idx1 - row1 * chunksPerRow : cc0;
+                    bool ok0, ok1;
+                    const long long off0 = chunkOffset(row0, cc0, ok0), off1 = chunkOffset(row1, cc1, ok1);
+                    ok1 = ok1 && idx1 < total;
+                    uint4 s0 = make_uint4(0, 0, 0, 0), s1 = s0;
+                    if (ok0) s0 = *reinterpret_cast<const uint4*>(a.p.skip + off0);
+                    if (ok1) s1 = *reinterpret_cast<const uint4*>(a.p.skip + off1);
+                    uint4 v0 = ldsV4(sbuf + (uint32_t)row0 * a.stagedPitch + (uint32_t)cc0 * 16u);
+                    uint4 v1 = ldsV4(sbuf + (uint32_t)row1 * a.stagedPitch + (uint32_t)cc1 * 16u);
+                    __half2* h0 = reinterpret_cast<__half2*>(&v0);
+                    __half2* h1 = reinterpret_cast<__half2*>(&v1);
+                    const __half2* r0 = reinterpret_cast<const __half2*>(&s0);
+                    const __half2* r1 = reinterpret_cast<const __half2*>(&s1);
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const float2 x0 = __half22float2(vh[i]), x1 = __half22float2(sh[i]);
-                            vh[i] = __floats2half2_rn(x0.x + x1.x, x0.y + x1.y);
-                        }
+                    for (int i = 0; i < 4; ++i) {
+                        const float2 a0 = __half22float2(h0[i]), b0 = __half22float2(r0[i]);
+                        const float2 a1 = __half22float2(h1[i]), b1 = __half22float2(r1[i]);
+                        h0[i] = __floats2half2_rn(a0.x + b0.x, a0.y + b0.y);
+                        h1[i] = __floats2half2_rn(a1.x + b1.x, a1.y + b1.y);
                     }
-                    *reinterpret_cast<uint4*>(a.p.out + off) = v;
+                    if (ok0) *reinterpret_cast<uint4*>(a.p.out + off0) = v0;
+                    if (ok1) *reinterpret_cast<uint4*>(a.p.out + off1) = v1;
+                }
+            } else {
+                for (int idx = et2; idx < total; idx += kEpiThreads) {
+                    const int row = idx / chunksPerRow, cc = idx - row * chunksPerRow;
+                    bool ok;
+                    const long long off = chunkOffset(row, cc, ok);
+                    if (ok) *reinterpret_cast<uint4*>(a.p.out + off) = ldsV4(sbuf + (uint32_t)row * a.stagedPitch + (uint32_t)cc * 16u);
                 }
             }
         }

@@ -57,7 +57,15 @@ struct ConvParams {
 #ifdef __CUDACC__
 
 __device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.f ? v : v * slope; }
-__device__ __forceinline__ float geluErf(float v) { return 0.5f * v * (1.f + erff(v * 0.70710678118654752f)); }  // nn.GELU()
+// nn.GELU() (erf form).  erf by Abramowitz-Stegun 7.1.26 (|abs error| < 1.5e-7, far below the fp16 output resolution):
+// ~4x fewer instructions than erff in the Linear epilogues.
+__device__ __forceinline__ float geluErf(float v) {
+    const float x = fabsf(v) * 0.70710678118654752f;
+    const float t = __fdividef(1.f, fmaf(0.3275911f, x, 1.f));
+    const float poly = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f), 0.254829592f);
+    const float erfAbs = 1.f - poly * __expf(-x * x);
+    return 0.5f * v * (1.f + copysignf(erfAbs, v));
+}
 
 struct alignas(16) Half8 { __half2 a, b, c, d; };
 struct alignas(8) Half4 { __half2 a, b; };
