@@ -450,17 +450,18 @@ void Engine::buildPlanCunet() {
     if (outTile != expect) throw Error("internal: output tile size mismatch");
 }
 
-void Engine::launchLayer(LayerExec& L, cudaStream_t s, __half* outp) {
+void Engine::launchLayer(LayerExec& L, cudaStream_t s, __half* outp, int nImg) {
     switch (L.impl) {
-        case IMPL_IGEMM: igemmLaunch(L.plan, s, outp); break;
+        case IMPL_IGEMM: igemmLaunch(L.plan, s, outp, nImg); break;
         case IMPL_LAYERNORM:
-            launchLayerNorm(L.tokIn, L.tokOut, (long long)L.tokN * L.tokH * L.tokW, L.tokC, L.gamma, L.beta, L.eps, s);
+            launchLayerNorm(L.tokIn, L.tokOut, (long long)nImg * L.tokH * L.tokW, L.tokC, L.gamma, L.beta, L.eps, s);
             break;
         case IMPL_ATTENTION:
-            launchWindowAttention(L.tokIn, L.tokOut, L.tokN, L.tokH, L.tokW, L.tokC, L.heads, L.window, L.shift, L.relpos, s);
+            launchWindowAttention(L.tokIn, L.tokOut, nImg, L.tokH, L.tokW, L.tokC, L.heads, L.window, L.shift, L.relpos, s);
             break;
         default: {
             ConvParams p = L.p;
+            p.gn = nImg;
             if (outp) p.out = outp;
             if (L.impl == IMPL_FIRST) launchConvFirst(p, s);
             else launchConvDirect(p, s);
@@ -661,11 +662,13 @@ double Engine::flopsPerTile() const {
     return f;
 }
 
-void Engine::runModel(cudaStream_t s, __half* finalOut) {
+// nImages < batch: the last, partially filled batch of a frame -- the padding slots (img2img_render.cpp:281) are not computed
+void Engine::runModel(cudaStream_t s, __half* finalOut, int nImages) {
+    const int n = (nImages > 0 && nImages < batch) ? nImages : batch;
     for (auto& L : layers) {
         __half* outp = (L.isFinal && finalOut) ? finalOut : L.p.out;
         if (L.seR) W2X_CUDA(cudaMemsetAsync(L.sePartial, 0, L.sePartialBytes, s));
-        launchLayer(L, s, outp);
+        launchLayer(L, s, outp, n);
         ++launches;
         if (debugSync) {
             cudaError_t de = cudaStreamSynchronize(s);
@@ -673,11 +676,11 @@ void Engine::runModel(cudaStream_t s, __half* finalOut) {
             if (de != cudaSuccess) throw Error("layer '" + L.name + "': " + cudaGetErrorString(de));
         }
         if (L.seR) {
-            if (!L.seFused) { launchSeSqueeze(L.p.out, L.p.gn, L.p.out_h, L.p.out_w, L.p.out_c, L.sePartial, s); ++launches; }
-            launchSeExcite(L.sePartial, L.p.gn, L.p.out_c, L.seR, L.p.out_h * L.p.out_w, L.seW1, L.seB1, L.seW2, L.seB2, L.seScale, s);
+            if (!L.seFused) { launchSeSqueeze(L.p.out, n, L.p.out_h, L.p.out_w, L.p.out_c, L.sePartial, s); ++launches; }
+            launchSeExcite(L.sePartial, n, L.p.out_c, L.seR, L.p.out_h * L.p.out_w, L.seW1, L.seB1, L.seW2, L.seB2, L.seScale, s);
             ++launches;
-            if (L.foldJobs.empty()) { launchSeScale(L.p.out, L.p.gn, L.p.out_h, L.p.out_w, L.p.out_c, L.seScale, s); ++launches; }
-            for (const auto& j : L.foldJobs) { launchScaleWeights(j.w, j.wOut, L.seScale, L.p.gn, j.npad, j.ktot, j.cin, s); ++launches; }
+            if (L.foldJobs.empty()) { launchSeScale(L.p.out, n, L.p.out_h, L.p.out_w, L.p.out_c, L.seScale, s); ++launches; }
+            for (const auto& j : L.foldJobs) { launchScaleWeights(j.w, j.wOut, L.seScale, n, j.npad, j.ktot, j.cin, s); ++launches; }
         }
     }
     W2X_CUDA(cudaGetLastError());
@@ -752,11 +755,15 @@ void Engine::renderOnStream(const uint8_t* dSrc, int w, int h, size_t srcPitch, 
     const size_t tileElems = (size_t)outTile * outTile * 4;
     for (int b = 0; b < batchCount; ++b) {
         const auto t0 = std::chrono::steady_clock::now();
+        // real (non-padding) slots of this batch: the reference computes the zero padding tiles and discards them (:281,:298)
+        const int realSteps = grid.count * (cfg.tta ? 8 : 1);
+        const int nReal = std::min(batch, realSteps - b * batch);
+        if (nReal <= 0) continue;
         span(0, [&] {
-            launchUnpack(dSrc, w, h, srcPitch, dSlots + (size_t)b * batch, batch, tile, actIn.p, s);
+            launchUnpack(dSrc, w, h, srcPitch, dSlots + (size_t)b * batch, nReal, tile, actIn.p, s);
             ++launches;
         });
-        span(1, [&] { runModel(s, dTileOut + (size_t)b * batch * tileElems); });
+        span(1, [&] { runModel(s, dTileOut + (size_t)b * batch * tileElems, nReal); });
         if (progCb) {
             const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
             progCb(b + 1, batchCount, 1000.0 / std::max(ms, 1e-6), progUser);  // render.cpp:336-338
@@ -962,10 +969,11 @@ bool Engine::renderBanded(Engine* const* es, int count, const uint8_t* src, int 
             W2X_CUDA(cudaMemcpy2DAsync(e.dFrameIn, (size_t)w * 3, src, srcStride, (size_t)w * 3, h, cudaMemcpyHostToDevice, e.stream));
             W2X_CUDA(cudaStreamSynchronize(e.stream));  // the staging vectors go out of scope
             for (int b = 0; b < bd[r].slots / batch; ++b) {
-                launchUnpack(e.dFrameIn, w, h, (size_t)w * 3, e.dBandSlots + (size_t)b * batch, batch, tile, e.actIn.p, e.stream);
+                const int nReal = std::min(batch, bd[r].own - b * batch);
+                launchUnpack(e.dFrameIn, w, h, (size_t)w * 3, e.dBandSlots + (size_t)b * batch, nReal, tile, e.actIn.p, e.stream);
                 ++e.launches;
                 W2X_CUDA(cudaGetLastError());
-                e.runModel(e.stream, e.dBandTiles + (size_t)b * batch * tileElems);
+                e.runModel(e.stream, e.dBandTiles + (size_t)b * batch * tileElems, nReal);
             }
             W2X_CUDA(cudaEventRecord(e.evBandModel, e.stream));
         }
@@ -1057,7 +1065,7 @@ bool Engine::infer(const float* inNchw, int n, float* outNchw) {
             W2X_CUDA(cudaMemcpyAsync(dIn, inNchw, inElems * 4, cudaMemcpyHostToDevice, stream));
             W2X_CUDA(cudaMemsetAsync(actIn.p, 0, actIn.elems() * 2, stream));
             launchNchwToNhwc4(dIn, n, tile, actIn.p, stream);
-            runModel(stream, dOutH);
+            runModel(stream, dOutH, n);
             launchNhwc4ToNchw(dOutH, n, outTile, dOut, stream);
             launches += 2;
             W2X_CUDA(cudaMemcpyAsync(outNchw, dOut, outElems * 4, cudaMemcpyDeviceToHost, stream));
@@ -1089,7 +1097,7 @@ int Engine::profileLayers(int repeats, char (*names)[48], float* ms, double* flo
             W2X_CUDA(cudaEventRecord(e0, stream));
             for (int r = 0; r < repeats; ++r) {
                 if (L.seR) W2X_CUDA(cudaMemsetAsync(L.sePartial, 0, L.sePartialBytes, stream));
-                launchLayer(L, stream, nullptr);
+                launchLayer(L, stream, nullptr, batch);
                 if (L.seR) {
                     if (!L.seFused) launchSeSqueeze(L.p.out, L.p.gn, L.p.out_h, L.p.out_w, L.p.out_c, L.sePartial, stream);
                     launchSeExcite(L.sePartial, L.p.gn, L.p.out_c, L.seR, L.p.out_h * L.p.out_w, L.seW1, L.seB1, L.seW2, L.seB2, L.seScale, stream);

@@ -95,8 +95,8 @@ private:
     void buildPlan();
     void buildPlanCunet();
     void buildPlanSwin();
-    void launchLayer(LayerExec& L, cudaStream_t s, __half* outOverride);
-    void runModel(cudaStream_t s, __half* finalOut);
+    void launchLayer(LayerExec& L, cudaStream_t s, __half* outOverride, int nImages);
+    void runModel(cudaStream_t s, __half* finalOut, int nImages = 0);
     void ensureFrameBuffers(int w, int h);
     void renderOnStream(const uint8_t* dSrc, int w, int h, size_t srcPitch, uint8_t* dDst, size_t dstPitch, cudaStream_t s, bool timed);
     void* dalloc(size_t bytes);

@@ -1019,16 +1019,21 @@ const char* igemmDescribe(const IgemmPlan* plan, char* buf, int cap) {
     return buf;
 }
 
-void igemmLaunch(const IgemmPlan* plan, cudaStream_t s, __half* outOverride) {
+void igemmLaunch(const IgemmPlan* plan, cudaStream_t s, __half* outOverride, int nImages) {
     if (plan->grid <= 0) return;
+    const bool fewer = nImages > 0 && nImages < plan->args.p.gn;  // last, partially filled batch: skip the padding slots
     const bool redirect = outOverride && outOverride != plan->args.p.out;
     if (redirect && plan->args.staged) throw Error("igemm: output redirection is not available for staged-epilogue layers");
     if (redirect && plan->args.useTma) throw Error("igemm: output redirection is not available for TMA-store layers");
     ConvArgs local;
     const ConvArgs* a = &plan->args;
-    if (redirect) {
-        local = plan->args;  // only the epilogue's destination changes; the tensor maps stay valid
-        local.p.out = outOverride;
+    if (redirect || fewer) {
+        local = plan->args;  // only the epilogue's destination / the image count change; the tensor maps stay valid
+        if (redirect) local.p.out = outOverride;
+        if (fewer) {
+            local.totalTiles = local.totalTiles / local.p.gn * nImages;
+            local.p.gn = nImages;
+        }
         a = &local;
     }
     if (plan->patch) {

@@ -175,7 +175,7 @@ void launchConvFirst(const ConvParams& p, cudaStream_t s);        // cin=4 -> 32
 struct IgemmPlan;                                                 // opaque: tensor maps + launch geometry
 IgemmPlan* igemmCreatePlan(const ConvParams& p);                  // throws w2x::Error when unsupported
 void igemmDestroyPlan(IgemmPlan* plan);
-void igemmLaunch(const IgemmPlan* plan, cudaStream_t s, __half* outOverride = nullptr);
+void igemmLaunch(const IgemmPlan* plan, cudaStream_t s, __half* outOverride = nullptr, int nImages = 0);
 bool igemmSupported(const ConvParams& p);
 const char* igemmDescribe(const IgemmPlan* plan, char* buf, int cap);
 bool igemmSeFusable(const IgemmPlan* plan);  // can this layer's epilogue produce ConvParams::se_sum?
