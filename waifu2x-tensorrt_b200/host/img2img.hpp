@@ -92,6 +92,12 @@ public:
         w2x_set_progress_callback(h_, prog_ ? &Img2Img::onProgress : nullptr, this);
     }
 
+    // extensions (not in the reference): up to three frames in flight, see w2x_submit / w2x_wait in include/w2x.h
+    int submit(const unsigned char* srcBgr, int width, int height, size_t srcStride, unsigned char* dstBgr, size_t dstStride) {
+        return w2x_submit(h_, srcBgr, width, height, srcStride, dstBgr, dstStride);
+    }
+    bool wait(int ticket) { return w2x_wait(h_, ticket) != 0; }
+
     w2x_engine* handle() const { return h_; }
 
 private:
