@@ -4,7 +4,8 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-# kind: 0 conv3x3, 1 conv2x2s2, 2 convT2x2s2(+skip), 3 convT4x4s2p3 head, 4 conv3x3 image head (+skip, clamp)
+# kind: 0 conv3x3, 1 conv2x2s2, 2 convT2x2s2(+skip), 3 convT4x4s2p3 head, 4 conv3x3 image head (+skip, clamp),
+# 5 the same image head through the dedicated taps-in-N kernel (conv_head.cu)
 CASES = [
     (0, 1, 20, 24, 64, 64),     # one M tile with edges (patch kernel)
     (0, 8, 100, 100, 64, 64),   # > 148 tiles: persistent loop, stage ring wrap, double-buffered staging
@@ -20,6 +21,8 @@ CASES = [
     (2, 1, 17, 17, 128, 128),   # N = 512 -> two N tiles
     (3, 2, 50, 50, 64, 3),      # convT 4x4 s2 p3 head
     (4, 2, 58, 58, 64, 3),      # image head + z1 crop + clamp
+    (5, 2, 58, 58, 64, 3),      # image head kernel: partial tiles on both edges
+    (5, 3, 26, 146, 64, 3),     # image head kernel: exact multiples of the 8 x 16 tile, three images
 ]
 
 

@@ -130,8 +130,10 @@ void Engine::unload() {
     if (stream) cudaStreamSynchronize(stream);
     if (h2dStream) cudaStreamSynchronize(h2dStream);
     if (d2hStream) cudaStreamSynchronize(d2hStream);
-    for (auto& L : layers)
+    for (auto& L : layers) {
         if (L.plan) igemmDestroyPlan(L.plan);
+        if (L.head) convHeadDestroyPlan(L.head);
+    }
     layers.clear();
     for (void* p : allocs) cudaFree(p);
     allocs.clear();
@@ -344,6 +346,7 @@ void Engine::buildPlanCunet() {
         E.isFinal = fin;
         if (useDirect) E.impl = IMPL_DIRECT;
         else if (L.kind == L_CONV3 && L.cin == 4 && L.npad == 32 && p.mode == EPI_STORE) E.impl = IMPL_FIRST;
+        else if (convHeadSupported(p) && !std::getenv("W2X_NO_HEAD_KERNEL")) { E.impl = IMPL_HEAD; E.head = convHeadCreatePlan(p); }
         else if (igemmSupported(p)) {
             E.impl = IMPL_IGEMM;
             if (L.se_r) {
@@ -453,6 +456,7 @@ void Engine::buildPlanCunet() {
 void Engine::launchLayer(LayerExec& L, cudaStream_t s, __half* outp, int nImg) {
     switch (L.impl) {
         case IMPL_IGEMM: igemmLaunch(L.plan, s, outp, nImg); break;
+        case IMPL_HEAD: launchConvHead(L.head, s, outp, nImg); break;
         case IMPL_LAYERNORM:
             launchLayerNorm(L.tokIn, L.tokOut, (long long)nImg * L.tokH * L.tokW, L.tokC, L.gamma, L.beta, L.eps, s);
             break;
@@ -652,7 +656,8 @@ int Engine::layerKernel(int index, char* buf, int cap) const {
     const LayerExec& L = layers[index];
     if (L.plan) igemmDescribe(L.plan, buf, cap);
     else std::snprintf(buf, cap, "%s", L.impl == IMPL_FIRST ? "first-layer mma.sync" : L.impl == IMPL_LAYERNORM ? "layernorm" :
-                                       L.impl == IMPL_ATTENTION ? "window-attention mma.sync" : "direct (reference kernel)");
+                                       L.impl == IMPL_ATTENTION ? "window-attention mma.sync" :
+                                       L.impl == IMPL_HEAD ? "image head, taps-in-N mma.sync" : "direct (reference kernel)");
     return 1;
 }
 
@@ -1113,7 +1118,7 @@ int Engine::profileLayers(int repeats, char (*names)[48], float* ms, double* flo
             if (std::getenv("W2X_VERBOSE")) {
                 char d[256] = "";
                 if (L.plan) igemmDescribe(L.plan, d, sizeof(d));
-                std::fprintf(stderr, "[w2x] %-28s %s\n", L.name.c_str(), L.plan ? d : (L.impl == IMPL_FIRST ? "first-layer cuda-core" : "direct"));
+                std::fprintf(stderr, "[w2x] %-28s %s\n", L.name.c_str(), L.plan ? d : (L.impl == IMPL_FIRST ? "first-layer mma.sync" : L.impl == IMPL_HEAD ? "image head taps-in-N mma.sync" : "direct"));
             }
             ms[i] = t / repeats;
             flops[i] = L.flops * batch;
@@ -1133,6 +1138,8 @@ int Engine::profileLayers(int repeats, char (*names)[48], float* ms, double* flo
 // ------------------------------------------------------------------------------------------------
 double selftestConv(int device, int kind, int n, int h, int w, int cin, int cout, unsigned seed) {
     if (cudaSetDevice(device) != cudaSuccess) return -1.0;
+    const bool headKernel = kind == 5;  // kind 5: the layer of kind 4 through the dedicated image-head kernel
+    if (headKernel) kind = 4;
     std::vector<void*> bufs;
     auto dmal = [&](size_t bytes) { void* p = nullptr; W2X_CUDA(cudaMalloc(&p, bytes + 256)); bufs.push_back(p); return p; };
     double result = -1.0;
@@ -1187,8 +1194,15 @@ double selftestConv(int device, int kind, int n, int h, int w, int cin, int cout
         launchConvDirect(p, nullptr);
         W2X_CUDA(cudaDeviceSynchronize());
         p.out = outB;  // the tensor-core kernel writes its own buffer (TMA-store layers bake the pointer into the tensor map)
-        plan = igemmCreatePlan(p);
-        igemmLaunch(plan, nullptr, nullptr);
+        if (headKernel) {
+            HeadPlan* hp = convHeadCreatePlan(p);
+            launchConvHead(hp, nullptr);
+            W2X_CUDA(cudaDeviceSynchronize());
+            convHeadDestroyPlan(hp);
+        } else {
+            plan = igemmCreatePlan(p);
+            igemmLaunch(plan, nullptr, nullptr);
+        }
         W2X_CUDA(cudaDeviceSynchronize());
         std::vector<uint16_t> ha(out.elems()), hb(out.elems());
         W2X_CUDA(cudaMemcpy(ha.data(), outA, ha.size() * 2, cudaMemcpyDeviceToHost));

@@ -25,13 +25,14 @@ struct Act {
     size_t elems() const { return (size_t)n * h * w * c; }
 };
 
-enum ConvImpl { IMPL_DIRECT = 0, IMPL_FIRST = 1, IMPL_IGEMM = 2, IMPL_LAYERNORM = 3, IMPL_ATTENTION = 4 };
+enum ConvImpl { IMPL_DIRECT = 0, IMPL_FIRST = 1, IMPL_IGEMM = 2, IMPL_LAYERNORM = 3, IMPL_ATTENTION = 4, IMPL_HEAD = 5 };
 
 struct LayerExec {
     std::string name;
     ConvParams p{};
     int impl = IMPL_DIRECT;
     IgemmPlan* plan = nullptr;
+    HeadPlan* head = nullptr;  // IMPL_HEAD
     double flops = 0;  // algorithmic 2*MAC for ONE tile
     bool isFinal = false;
     // squeeze/excite applied to p.out after the conv

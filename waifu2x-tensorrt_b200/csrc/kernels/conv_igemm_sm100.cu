@@ -49,6 +49,7 @@ struct ConvArgs {
     int stages, cchunks, kblocks;
     uint32_t idesc, tmemCols, bytesA, bytesB, descHiA, descHiB;
     int useTma, nsub, nbuf, hasSkip;
+    int dbg;  // timing experiments only (W2X_DBG): 1 = epilogue skips math + staging, 2 = no output store, 4 = no MMAs
     uint32_t stageStride, wBytes, stagingBytes;
     int nSplit;
     int staged;                 // EPI_K_STAGED: generic-proxy staging + coalesced copy-out (any N, residual, GELU)
@@ -73,7 +74,7 @@ constexpr int kPatchW = 10, kPatchH = 18;
 // header layout (byte offsets from the 1024-aligned smem base)
 constexpr uint32_t kOffFull = 0, kOffEmpty = 64, kOffTFull = 128, kOffTEmpty = 144, kOffSkip = 160, kOffW = 184, kOffSlot = 256, kOffBias = 1024;
 
-enum EpiKind { EPI_K_DIRECT = 0, EPI_K_TMA = 1, EPI_K_TMA_SKIP = 2, EPI_K_STAGED = 3 };
+enum EpiKind { EPI_K_DIRECT = 0, EPI_K_TMA = 1, EPI_K_TMA_SKIP = 2, EPI_K_STAGED = 3, EPI_K_TMA_GROUPS = 4 };
 
 struct TileCoord {
     int img, y0, x0, n0;
@@ -171,27 +172,26 @@ __device__ __forceinline__ void epilogueWarps(const ConvArgs& a, uint32_t base, 
         for (int k = 0; k < a.nbuf - 1 && k < nMine; ++k) issueSkip(k);
     }
 
-    // fused SE squeeze: thread (channel seC, row group seG) sums its channel over the valid rows of every tile of one image
+    // fused SE squeeze: while a warp converts its 32 rows x 32 columns of a tile, every column is summed over the 32 rows with one
+    // redux.sync on the 2^10 fixed-point value (|v| <= 65504 cannot overflow the 32-row int32 sum); lane j keeps column j's total
+    // in a 64-bit register and issues one integer atomic per (thread, column chunk, image).  Integer addition is exact, so the
+    // result is independent of the tile -> CTA assignment and of the image's slot in the batch (byte-identical under any sharding).
     const bool doSe = kTma && !kSkip && a.p.se_sum != nullptr;
     const int et = threadIdx.x - 64;
-    const int seC = et & (a.bn - 1);
-    const int seG = et / a.bn;                         // 256 / bn row groups
-    const int seRows = (128 * a.bn) / kEpiThreads;     // rows per group
-    long long seAcc = 0;
+    long long seAcc0 = 0, seAcc1 = 0;
     int seImg = -1;
     int skipScaleImg = -1;
-    // image boundary: one integer atomic per (thread, image); integer addition is exact, so the total is independent of the
-    // tile -> CTA assignment and of the image's position in the batch (byte-identical results for any sharding)
     auto seFlush = [&]() {
-        if (seImg >= 0 && seAcc != 0)
-            atomicAdd(reinterpret_cast<unsigned long long*>(a.p.se_sum + (size_t)seImg * a.p.npad + nBase + seC), (unsigned long long)seAcc);
+        if (seImg < 0) return;
+        unsigned long long* dst = reinterpret_cast<unsigned long long*>(a.p.se_sum + (size_t)seImg * a.p.npad + nBase + colBegin + lane);
+        if (seAcc0 != 0) atomicAdd(dst, (unsigned long long)seAcc0);
+        if (seAcc1 != 0) atomicAdd(dst + 32, (unsigned long long)seAcc1);
     };
 
-    int acc = 0;
-    uint32_t accPhase = 0;
+    int acc = 0, b = 0;
+    uint32_t accPhase = 0, bufPhase = 0;
     for (int k = 0; k < nMine; ++k, w.next()) {
         const TileCoord tc = w.coord(a.bh, a.bw, a.bn, nBase);
-        const int b = k % a.nbuf;
         const uint32_t stg = staging + b * bufBytes;
         if (kTma && !kSkip) {
             if (leader) bulkWaitRead(a.nbuf - 1);  // staging buffer b is no longer being read by the store of tile k - nbuf
@@ -213,13 +213,16 @@ __device__ __forceinline__ void epilogueWarps(const ConvArgs& a, uint32_t base, 
         }
         mbarWait(barTFull + 8u * acc, accPhase);
         tcFenceAfter();
-        if (kSkip) mbarWait(barSkip + 8u * b, (uint32_t)(k / a.nbuf) & 1u);
+        if (kSkip) mbarWait(barSkip + 8u * b, bufPhase);
         const uint32_t taddr = tmemBase + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * a.bn);
         uint32_t r[32];
         if (kTma) {
+            if (doSe && tc.img != seImg) { seFlush(); seImg = tc.img; seAcc0 = seAcc1 = 0; }
+            const float seScale = pvalid ? kSeFixedScale : 0.f;  // rows outside the layer's output do not count
             for (int c0 = colBegin; c0 < colBegin + colsPerWarp; c0 += 32) {
                 tmemLd32(taddr + (uint32_t)c0, r);
                 tmemLdWait();
+                int seMine = 0;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const int j0 = c0 + 8 * q;
@@ -261,6 +264,17 @@ __device__ __forceinline__ void epilogueWarps(const ConvArgs& a, uint32_t base, 
 #pragma unroll
                     for (int i = 0; i < 4; ++i) oh[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
                     stsV4(addr, o);
+                    if (!kSkip && doSe) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int colSum = __reduce_add_sync(0xffffffffu, __float2int_rn(v[i] * seScale));
+                            if (lane == 8 * q + i) seMine = colSum;
+                        }
+                    }
+                }
+                if (!kSkip && doSe) {
+                    if (c0 == colBegin) seAcc0 += seMine;
+                    else seAcc1 += seMine;
                 }
             }
         } else if (kStaged) {
@@ -333,6 +347,7 @@ __device__ __forceinline__ void epilogueWarps(const ConvArgs& a, uint32_t base, 
         __syncwarp();
         if (lane == 0) mbarArrive(barTEmpty + 8u * acc);  // accumulator buffer may be overwritten by the next-but-one tile
         if (++acc == 2) { acc = 0; accPhase ^= 1u; }
+        if (++b == a.nbuf) { b = 0; bufPhase ^= 1u; }
         if (kStaged) {
             namedBarSync(1, kEpiThreads);  // the tile is complete in smem (and, two tiles later, this buffer is free again)
             const uint32_t sbuf = staging + (uint32_t)(k & (a.nbuf - 1)) * a.stagedBuf;
@@ -397,21 +412,6 @@ __device__ __forceinline__ void epilogueWarps(const ConvArgs& a, uint32_t base, 
                 }
                 bulkCommit();
             }
-            if (doSe) {
-                if (tc.img != seImg) { seFlush(); seImg = tc.img; seAcc = 0; }
-                const uint32_t colOff = (uint32_t)(seC >> 6) * 16384u;
-                const int cc = seC & 63;
-                long long sacc = 0;
-                for (int i = 0; i < seRows; ++i) {
-                    const int mm = seG * seRows + i;
-                    const bool ok = (tc.y0 + (mm >> a.bwShift)) < a.p.gy && (tc.x0 + (mm & (a.bw - 1))) < a.p.gx;
-                    const uint32_t addr = stg + colOff + (uint32_t)mm * 128u + ((uint32_t)((cc >> 3) ^ (mm & 7)) << 4) + (uint32_t)(cc & 7) * 2u;
-                    unsigned short hv;
-                    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hv) : "r"(addr));
-                    if (ok) sacc += (long long)__float2int_rn(__half2float(__ushort_as_half(hv)) * kSeFixedScale);
-                }
-                seAcc += sacc;
-            }
             if (leader) {
                 if (kSkip) {
                     const int kn = k + a.nbuf - 1;
@@ -427,7 +427,120 @@ __device__ __forceinline__ void epilogueWarps(const ConvArgs& a, uint32_t base, 
     if (kTma && leader) bulkWaitAll();
 }
 
-__device__ __forceinline__ void setupCommon(const ConvArgs& a, uint32_t base, uint8_t* sm, int warp) {
+// ---- TMA-store epilogue in two independent groups of four warps ------------------------------------------------------------
+// Group g (one warp per TMEM lane quarter) owns accumulator buffer g, staging buffer g and every second tile of the CTA, so one
+// group's barrier / TMEM / store latencies overlap the other group's math, and the per-tile bookkeeping (tile walker, barriers)
+// is paid once per 64 accumulator columns of a thread instead of once per 32.  Requires nbuf == 2, no skip tensor.
+__device__ __forceinline__ void epilogueTmaGroups(const ConvArgs& a, uint32_t base, uint32_t tmemBase, int nMine, int first, int step, int nBase) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int quarter = warp & 3;
+    const int group = (warp - 2) >> 2;
+    const bool leader = ((warp - 2) & 3) == 0 && lane == 0;
+    const int m = quarter * 32 + lane;
+    const int yy = m >> a.bwShift, xx = m & (a.bw - 1);
+    const uint32_t barTFull = base + kOffTFull + 8u * group, barTEmpty = base + kOffTEmpty + 8u * group;
+    const uint32_t stg = base + a.headerBytes + (uint32_t)group * (uint32_t)a.nsub * 16384u;
+    const uint32_t rowAddr = stg + (uint32_t)m * 128u;
+    const uint32_t sw = (uint32_t)(m & 7);
+    const uint32_t biasS = base + kOffBias;
+    const uint32_t taddr = tmemBase + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(group * a.bn);
+    const int nPairs = a.bn >> 6;  // 64 accumulator columns per round
+    const int barId = 1 + group;
+
+    // fused SE squeeze (see epilogueWarps): redux.sync per column over the warp's 32 rows, 64-bit totals per lane, one integer
+    // atomic per (thread, 32-column chunk, image)
+    const bool doSe = a.p.se_sum != nullptr;
+    long long seAcc[4] = {0, 0, 0, 0};
+    int seImg = -1;
+    auto seFlush = [&]() {
+        if (seImg < 0) return;
+        unsigned long long* dst = reinterpret_cast<unsigned long long*>(a.p.se_sum + (size_t)seImg * a.p.npad + nBase + lane);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            if (seAcc[c] != 0) atomicAdd(dst + 32 * c, (unsigned long long)seAcc[c]);
+    };
+
+    const int nGroup = nMine > group ? (nMine - group + 1) >> 1 : 0;  // tiles group, group + 2, ... of this CTA
+    TileWalker w;
+    w.init(first + group * step, 2 * step, a.tilesN, a.tilesX, a.tilesY);
+    uint32_t phase = 0;
+    for (int j = 0; j < nGroup; ++j, w.next(), phase ^= 1u) {
+        const TileCoord tc = w.coord(a.bh, a.bw, a.bn, nBase);
+        if (leader) bulkWaitRead(0);  // this group's previous store (two tiles ago) has finished reading the staging buffer
+        namedBarSync(barId, 128);
+        float seScale = 0.f;
+        if (doSe) {
+            if (tc.img != seImg) {
+                seFlush();
+                seImg = tc.img;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) seAcc[c] = 0;
+            }
+            const bool pvalid = (tc.y0 + yy) < a.p.gy && (tc.x0 + xx) < a.p.gx;  // rows outside the layer's output do not count
+            seScale = pvalid ? kSeFixedScale : 0.f;
+        }
+        mbarWait(barTFull, phase);
+        tcFenceAfter();
+#pragma unroll
+        for (int pr = 0; pr < 2; ++pr) {
+            if (pr < nPairs && !(a.dbg & 1)) {
+                uint32_t rLo[32], rHi[32];
+                tmemLd32(taddr + (uint32_t)(64 * pr), rLo);
+                tmemLd32(taddr + (uint32_t)(64 * pr + 32), rHi);
+                tmemLdWait();
+                const uint32_t subAddr = rowAddr + (uint32_t)pr * 16384u;
+                const uint32_t biasAddr = biasS + (uint32_t)(tc.n0 + 64 * pr) * 4u;
+                int seMine0 = 0, seMine1 = 0;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const uint4 b0 = ldsV4(biasAddr + 32u * q), b1 = ldsV4(biasAddr + 32u * q + 16u);
+                    const float bias[8] = {__uint_as_float(b0.x), __uint_as_float(b0.y), __uint_as_float(b0.z), __uint_as_float(b0.w),
+                                           __uint_as_float(b1.x), __uint_as_float(b1.y), __uint_as_float(b1.z), __uint_as_float(b1.w)};
+                    float v[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float t = __uint_as_float(q < 4 ? rLo[8 * (q & 3) + i] : rHi[8 * (q & 3) + i]) + bias[i];
+                        v[i] = fmaxf(t, t * a.p.slope);  // LeakyReLU for 0 < slope <= 1
+                    }
+                    uint4 o;
+                    __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) oh[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+                    stsV4(subAddr + (((uint32_t)q ^ sw) << 4), o);
+                    if (doSe) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int colSum = __reduce_add_sync(0xffffffffu, __float2int_rn(v[i] * seScale));
+                            if (q < 4) { if (lane == 8 * q + i) seMine0 = colSum; }
+                            else { if (lane == 8 * (q - 4) + i) seMine1 = colSum; }
+                        }
+                    }
+                }
+                if (doSe) {
+                    seAcc[2 * pr] += seMine0;
+                    seAcc[2 * pr + 1] += seMine1;
+                }
+            }
+        }
+        tcFenceBefore();
+        __syncwarp();
+        if (lane == 0) mbarArrive(barTEmpty);  // accumulator buffer `group` may be overwritten by this group's next tile
+        fenceProxyAsync();
+        namedBarSync(barId, 128);
+        if (leader && !(a.dbg & 2)) {
+            for (int sub = 0; sub < a.nsub; ++sub) {
+                int c0, cz;
+                subTileCoords(a, tc, sub, c0, cz);
+                tmaStore5d(&a.tmOut, stg + sub * 16384u, c0, tc.x0, cz, tc.y0, tc.img);
+            }
+            bulkCommit();
+        }
+    }
+    if (doSe) seFlush();
+    if (leader) bulkWaitAll();
+}
+
+__device__ __forceinline__ void setupCommon(const ConvArgs& a, uint32_t base, uint8_t* sm, int warp, int accReaders) {
     if (threadIdx.x == 0) {
         for (int s = 0; s < 8; ++s) {
             mbarInit(base + kOffFull + 8u * s, 1);
@@ -435,7 +548,7 @@ __device__ __forceinline__ void setupCommon(const ConvArgs& a, uint32_t base, ui
         }
         for (int i = 0; i < 2; ++i) {
             mbarInit(base + kOffTFull + 8u * i, 1);
-            mbarInit(base + kOffTEmpty + 8u * i, kEpiWarps);
+            mbarInit(base + kOffTEmpty + 8u * i, accReaders);  // warps that must release an accumulator buffer
         }
         for (int i = 0; i < 3; ++i) mbarInit(base + kOffSkip + 8u * i, 1);
         mbarInit(base + kOffW, 1);
@@ -463,7 +576,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
     const uint32_t base = (rawAddr + 1023u) & ~1023u;
     uint8_t* sm = smemRaw + (base - rawAddr);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    setupCommon(a, base, sm, warp);
+    setupCommon(a, base, sm, warp, kEpi == EPI_K_TMA_GROUPS ? kEpiWarps / 2 : kEpiWarps);
     const uint32_t tmemBase = *reinterpret_cast<volatile uint32_t*>(sm + kOffSlot);
     const uint32_t stage0 = base + a.headerBytes + a.stagingBytes;
     const uint32_t stageBytes = a.bytesA + a.bytesB;
@@ -519,7 +632,8 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
             if (++acc == 2) { acc = 0; accPhase ^= 1u; }
         }
     } else {
-        epilogueWarps<kEpi>(a, base, tmemBase, nMine, first, step, 0);
+        if constexpr (kEpi == EPI_K_TMA_GROUPS) epilogueTmaGroups(a, base, tmemBase, nMine, first, step, 0);
+        else epilogueWarps<kEpi>(a, base, tmemBase, nMine, first, step, 0);
     }
 
     tcFenceBefore();
@@ -540,7 +654,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_patch_kernel(const __grid
     const uint32_t base = (rawAddr + 1023u) & ~1023u;
     uint8_t* sm = smemRaw + (base - rawAddr);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    setupCommon(a, base, sm, warp);
+    setupCommon(a, base, sm, warp, kEpi == EPI_K_TMA_GROUPS ? kEpiWarps / 2 : kEpiWarps);
     const uint32_t tmemBase = *reinterpret_cast<volatile uint32_t*>(sm + kOffSlot);
     const uint32_t wBase = base + a.headerBytes + a.stagingBytes;
     const uint32_t stage0 = wBase + a.wBytes;
@@ -597,7 +711,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_patch_kernel(const __grid
                         const uint32_t aTap = aLo + (uint32_t)(((tap / 3) * kPatchW + (tap % 3)) * kRowBytes >> 4);
 #pragma unroll
                         for (int ks = 0; ks < kKC / 16; ++ks)
-                            ummaLoHi(tmemD, aTap + 2u * ks, a.descHiA, bLo + 2u * ks, a.descHiB, a.idesc, (cc | tap | ks) != 0 ? 1u : 0u);
+                            if (!(a.dbg & 4)) ummaLoHi(tmemD, aTap + 2u * ks, a.descHiA, bLo + 2u * ks, a.descHiB, a.idesc, (cc | tap | ks) != 0 ? 1u : 0u);
                         bLo += bTapStep;
                     }
                     tcCommit(barEmpty + 8u * stage);
@@ -611,7 +725,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_patch_kernel(const __grid
         }
     } else {
         // tilesN == 1 for this kernel: the walker's N index stays 0 and the slice offset comes in as nBase
-        epilogueWarps<kEpi>(a, base, tmemBase, nMine, first, step, n0);
+        if constexpr (kEpi == EPI_K_TMA_GROUPS) epilogueTmaGroups(a, base, tmemBase, nMine, first, step, n0);
+        else epilogueWarps<kEpi>(a, base, tmemBase, nMine, first, step, n0);
     }
 
     tcFenceBefore();
@@ -990,6 +1105,9 @@ IgemmPlan* igemmCreatePlan(const ConvParams& p) {
         if (!attrSet[dev]) {
             checkCuda(cudaFuncSetAttribute(igemm_kernel<EPI_K_DIRECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
             checkCuda(cudaFuncSetAttribute(igemm_kernel<EPI_K_TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+            checkCuda(cudaFuncSetAttribute(igemm_kernel<EPI_K_TMA_GROUPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+            checkCuda(cudaFuncSetAttribute(conv3x3_patch_kernel<EPI_K_TMA_GROUPS, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+            checkCuda(cudaFuncSetAttribute(conv3x3_patch_kernel<EPI_K_TMA_GROUPS, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
             checkCuda(cudaFuncSetAttribute(igemm_kernel<EPI_K_TMA_SKIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
             checkCuda(cudaFuncSetAttribute(igemm_kernel<EPI_K_STAGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
             checkCuda(cudaFuncSetAttribute(conv3x3_patch_kernel<EPI_K_DIRECT, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
@@ -1006,6 +1124,15 @@ IgemmPlan* igemmCreatePlan(const ConvParams& p) {
 }
 
 void igemmDestroyPlan(IgemmPlan* plan) { delete plan; }
+
+// 128B-swizzled tensor map over the layer's input view (c, x, z, y, img) with a (64, boxX, 1, boxY, 1) box, for kernels outside
+// this file that stage activation patches with TMA (tm points at a CUtensorMap)
+void encodeActivationMap5d(void* tm, const ConvParams& p, int boxX, int boxY) {
+    const long long dims[5] = {p.dimc, p.dimx, p.dimz, p.dimy, p.gn};
+    const long long st[4] = {p.sx, p.sz, p.sy, p.sn};
+    const int box[5] = {64, boxX, 1, boxY, 1};
+    encode5d(static_cast<CUtensorMap*>(tm), p.in, dims, st, box, true, "activation patch");
+}
 
 bool igemmSeFusable(const IgemmPlan* plan) {
     const ConvArgs& a = plan->args;
@@ -1036,16 +1163,25 @@ void igemmLaunch(const IgemmPlan* plan, cudaStream_t s, __half* outOverride, int
         }
         a = &local;
     }
+    // TMA-store layers without a skip tensor and with two staging buffers run the two-group epilogue
+    static const bool noGroups = std::getenv("W2X_NO_EPI_GROUPS") != nullptr;
+    static const int dbg = std::getenv("W2X_DBG") ? std::atoi(std::getenv("W2X_DBG")) : 0;
+    ConvArgs dbgLocal;
+    if (dbg) { dbgLocal = *a; dbgLocal.dbg = dbg; a = &dbgLocal; }
+    const bool grouped = a->useTma && !a->hasSkip && a->nbuf == 2 && a->bn <= 128 && !noGroups;
     if (plan->patch) {
         if (a->kc == 64) {
-            if (a->useTma) conv3x3_patch_kernel<EPI_K_TMA, 64><<<plan->grid, kThreads, plan->smem, s>>>(*a);
+            if (grouped) conv3x3_patch_kernel<EPI_K_TMA_GROUPS, 64><<<plan->grid, kThreads, plan->smem, s>>>(*a);
+            else if (a->useTma) conv3x3_patch_kernel<EPI_K_TMA, 64><<<plan->grid, kThreads, plan->smem, s>>>(*a);
             else conv3x3_patch_kernel<EPI_K_DIRECT, 64><<<plan->grid, kThreads, plan->smem, s>>>(*a);
         } else {
-            if (a->useTma) conv3x3_patch_kernel<EPI_K_TMA, 32><<<plan->grid, kThreads, plan->smem, s>>>(*a);
+            if (grouped) conv3x3_patch_kernel<EPI_K_TMA_GROUPS, 32><<<plan->grid, kThreads, plan->smem, s>>>(*a);
+            else if (a->useTma) conv3x3_patch_kernel<EPI_K_TMA, 32><<<plan->grid, kThreads, plan->smem, s>>>(*a);
             else conv3x3_patch_kernel<EPI_K_DIRECT, 32><<<plan->grid, kThreads, plan->smem, s>>>(*a);
         }
     } else {
         if (a->hasSkip) igemm_kernel<EPI_K_TMA_SKIP><<<plan->grid, kThreads, plan->smem, s>>>(*a);
+        else if (grouped) igemm_kernel<EPI_K_TMA_GROUPS><<<plan->grid, kThreads, plan->smem, s>>>(*a);
         else if (a->useTma) igemm_kernel<EPI_K_TMA><<<plan->grid, kThreads, plan->smem, s>>>(*a);
         else if (a->staged) igemm_kernel<EPI_K_STAGED><<<plan->grid, kThreads, plan->smem, s>>>(*a);
         else igemm_kernel<EPI_K_DIRECT><<<plan->grid, kThreads, plan->smem, s>>>(*a);

@@ -171,7 +171,13 @@ __device__ __forceinline__ void conv_epilogue8(const ConvParams& p, int img, int
 
 // host-side launchers (kernels/*.cu)
 void launchConvDirect(const ConvParams& p, cudaStream_t s);       // scalar CUDA-core reference (tests / self-check only)
-void launchConvFirst(const ConvParams& p, cudaStream_t s);        // cin=4 -> 32 first layer (CUDA cores)
+void launchConvFirst(const ConvParams& p, cudaStream_t s);        // cin=4 -> 32 first layer (mma.sync column strips)
+struct HeadPlan;                                                  // image head (kernels/conv_head.cu): params + input tensor map
+bool convHeadSupported(const ConvParams& p);                      // 3x3, 64 -> 3 channels, EPI_FINAL
+HeadPlan* convHeadCreatePlan(const ConvParams& p);
+void convHeadDestroyPlan(HeadPlan* plan);
+void launchConvHead(const HeadPlan* plan, cudaStream_t s, __half* outOverride = nullptr, int nImages = 0);
+void encodeActivationMap5d(void* tensorMap, const ConvParams& p, int boxX, int boxY);  // conv_igemm_sm100.cu
 struct IgemmPlan;                                                 // opaque: tensor maps + launch geometry
 IgemmPlan* igemmCreatePlan(const ConvParams& p);                  // throws w2x::Error when unsupported
 void igemmDestroyPlan(IgemmPlan* plan);
@@ -188,7 +194,7 @@ void launchWindowAttention(const __half* qkv, __half* out, int n, int h, int w, 
                            const float* relpos, cudaStream_t s);
 
 // squeeze/excite
-constexpr float kSeFixedScale = 16384.f;  // 2^14 fixed-point resolution of the squeeze sums
+constexpr float kSeFixedScale = 1024.f;  // 2^10 fixed-point resolution of the squeeze sums: 32 fp16-range values cannot overflow int32
 void launchSeSqueeze(const __half* x, int n, int h, int w, int c, long long* sums, cudaStream_t s);  // sums must be zeroed
 void launchSeExcite(const long long* sums, int n, int c, int r, int hw, const float* w1, const float* b1,
                     const float* w2, const float* b2, float* scale, cudaStream_t s);
