@@ -670,9 +670,11 @@ double Engine::flopsPerTile() const {
 // nImages < batch: the last, partially filled batch of a frame -- the padding slots (img2img_render.cpp:281) are not computed
 void Engine::runModel(cudaStream_t s, __half* finalOut, int nImages) {
     const int n = (nImages > 0 && nImages < batch) ? nImages : batch;
+    // SE accumulators are cleared up front so that the layer chain below is kernel -> kernel only (programmatic dependent launch)
+    for (auto& L : layers)
+        if (L.seR) W2X_CUDA(cudaMemsetAsync(L.sePartial, 0, L.sePartialBytes, s));
     for (auto& L : layers) {
         __half* outp = (L.isFinal && finalOut) ? finalOut : L.p.out;
-        if (L.seR) W2X_CUDA(cudaMemsetAsync(L.sePartial, 0, L.sePartialBytes, s));
         launchLayer(L, s, outp, n);
         ++launches;
         if (debugSync) {

@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 
 #include "conv_params.h"
+#include "launch.h"
 
 namespace w2x {
 
@@ -60,6 +61,7 @@ __global__ void __launch_bounds__(256) conv_first_kernel(ConvParams p, int segsX
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const int warpId = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int warpCount = gridDim.x * (blockDim.x >> 5);
+    pdlLaunchDependents();
     // B fragments: b[ky][j][0..1]; k index kk -> (kx = kk >> 2, ci = kk & 3); kx == 3 is the zero pad tap
     uint32_t bf[3][NT][2];
     float bias[NT][2];
@@ -83,6 +85,7 @@ __global__ void __launch_bounds__(256) conv_first_kernel(ConvParams p, int segsX
         a[2] = *reinterpret_cast<const uint32_t*>(row + 2 * 4);
         a[3] = *reinterpret_cast<const uint32_t*>(row + 10 * 4);
     };
+    pdlWait();  // weights and bias above are constants; the input tiles come from the preceding kernel
     for (int unit = warpId; unit < totalUnits; unit += warpCount) {
         const int sx = unit % segsX;
         const int rest = unit / segsX;
@@ -139,8 +142,8 @@ void launchConvFirst(const ConvParams& p, cudaStream_t s) {
     }
     const int blocksNeeded = (total + 7) / 8;
     const int grid = blocksNeeded < sms * 3 ? blocksNeeded : sms * 3;
-    if (p.npad == 64) conv_first_kernel<8><<<grid, 256, 0, s>>>(p, segsX, chunksY, total);
-    else conv_first_kernel<4><<<grid, 256, 0, s>>>(p, segsX, chunksY, total);
+    if (p.npad == 64) launchPdl(conv_first_kernel<8>, dim3(grid), dim3(256), 0, s, p, segsX, chunksY, total);
+    else launchPdl(conv_first_kernel<4>, dim3(grid), dim3(256), 0, s, p, segsX, chunksY, total);
 }
 
 }  // namespace w2x

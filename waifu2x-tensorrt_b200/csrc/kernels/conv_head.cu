@@ -17,6 +17,7 @@
 
 #include "../hostutil.h"
 #include "conv_params.h"
+#include "launch.h"
 #include "sm100_common.cuh"
 
 namespace w2x {
@@ -72,15 +73,14 @@ __global__ void __launch_bounds__(kHeadThreads, 1) conv_head_kernel(const ConvPa
         mbarExpectTx(bar0 + 8u * slot, kPatchTx);
         tmaLoad5d(patch0 + (uint32_t)slot * kPatchBytes, &tmIn, bar0 + 8u * slot, 0, ht.x0, 0, ht.y0, ht.img);
     };
+    pdlLaunchDependents();
     if (tid == 0) {
         for (int st = 0; st < kStages; ++st) mbarInit(bar0 + 8u * st, 1);
         mbarInitFence();
         tmaPrefetchDesc(&tmIn);
-        for (int st = 0; st < kStages - 1; ++st) loadPatch(tile0 + st * stride, st);
     }
-    __syncthreads();
 
-    // B fragments (overlap the first loads): column n = tap*3 + co of the taps-in-N weight matrix, zero for n >= 27
+    // B fragments (constants, loaded before the dependency wait): column n = tap*3 + co of the taps-in-N weight matrix, zero for n >= 27
     uint32_t bf[4][4][2];
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) {
@@ -98,6 +98,11 @@ __global__ void __launch_bounds__(kHeadThreads, 1) conv_head_kernel(const ConvPa
     int gatherOff[9];
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap) gatherOff[tap] = 3 * tap * kPitch + (oy + p.tap[tap].dy) * kPatchX + ox + p.tap[tap].dx;
+
+    pdlWait();  // everything above touches constants only; the input and residual tensors come from preceding kernels
+    if (tid == 0)
+        for (int st = 0; st < kStages - 1; ++st) loadPatch(tile0 + st * stride, st);
+    __syncthreads();  // barrier init visible to all threads
 
     int stage = 0;
     uint32_t phase = 0;
@@ -202,7 +207,7 @@ void launchConvHead(const HeadPlan* plan, cudaStream_t s, __half* outOverride, i
     if (nImages > 0) p.gn = nImages;
     const int tilesX = (p.gx + kTileX - 1) / kTileX, tilesY = (p.gy + kTileY - 1) / kTileY;
     const int numTiles = tilesX * tilesY * p.gn;
-    conv_head_kernel<<<numTiles < sms[dev] ? numTiles : sms[dev], kHeadThreads, kHeadSmem, s>>>(p, plan->tmIn, tilesX, tilesY, numTiles);
+    launchPdl(conv_head_kernel, dim3(numTiles < sms[dev] ? numTiles : sms[dev]), dim3(kHeadThreads), kHeadSmem, s, p, plan->tmIn, tilesX, tilesY, numTiles);
 }
 
 }  // namespace w2x

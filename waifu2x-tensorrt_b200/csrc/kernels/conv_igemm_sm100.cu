@@ -32,6 +32,7 @@
 #include "../hostutil.h"
 #include "../model_pack.h"
 #include "conv_params.h"
+#include "launch.h"
 #include "sm100_common.cuh"
 
 namespace w2x {
@@ -583,6 +584,8 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
     const uint32_t barFull = base + kOffFull, barEmpty = base + kOffEmpty, barTFull = base + kOffTFull, barTEmpty = base + kOffTEmpty;
     const int first = blockIdx.x, step = gridDim.x;
     const int nMine = tilesForCta(a, first, step);
+    pdlLaunchDependents();
+    pdlWait();  // setup above touched constants only (bias, tensor maps); activations and SE-scaled weights come from earlier kernels
 
     if (warp == 0) {
         if (lane == 0) {
@@ -667,13 +670,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_patch_kernel(const __grid
     const uint32_t rowBytes = (uint32_t)a.kc * 2u;     // one pixel / one weight row of a K chunk: 128 B (kc=64) or 64 B (kc=32)
     const uint32_t tapBytes = (uint32_t)a.bn * rowBytes;  // one (tap, K chunk) block of B: [bn rows][kc]
 
+    pdlLaunchDependents();
+    if (warp == 0 && lane == 0) {
+        // resident weights (constants of the loaded model): 9 * cchunks TMA boxes on one barrier, issued before the dependency wait
+        mbarExpectTx(barW, a.wBytes);
+        for (int tap = 0; tap < 9; ++tap)
+            for (int cc = 0; cc < a.cchunks; ++cc)
+                tmaLoad3d(wBase + (uint32_t)(tap * a.cchunks + cc) * tapBytes, &a.tmB, barW, tap * a.p.cin + cc * a.kc, n0, 0);
+    }
+    pdlWait();  // the input activation (and the output buffer's previous readers) belong to earlier kernels
+
     if (warp == 0) {
         if (lane == 0) {
-            // resident weights: 9 * cchunks TMA boxes, one barrier
-            mbarExpectTx(barW, a.wBytes);
-            for (int tap = 0; tap < 9; ++tap)
-                for (int cc = 0; cc < a.cchunks; ++cc)
-                    tmaLoad3d(wBase + (uint32_t)(tap * a.cchunks + cc) * tapBytes, &a.tmB, barW, tap * a.p.cin + cc * a.kc, n0, 0);
             int stage = 0;
             uint32_t phase = 0;
             TileWalker w;
@@ -1171,20 +1179,20 @@ void igemmLaunch(const IgemmPlan* plan, cudaStream_t s, __half* outOverride, int
     const bool grouped = a->useTma && !a->hasSkip && a->nbuf == 2 && a->bn <= 128 && !noGroups;
     if (plan->patch) {
         if (a->kc == 64) {
-            if (grouped) conv3x3_patch_kernel<EPI_K_TMA_GROUPS, 64><<<plan->grid, kThreads, plan->smem, s>>>(*a);
-            else if (a->useTma) conv3x3_patch_kernel<EPI_K_TMA, 64><<<plan->grid, kThreads, plan->smem, s>>>(*a);
-            else conv3x3_patch_kernel<EPI_K_DIRECT, 64><<<plan->grid, kThreads, plan->smem, s>>>(*a);
+            if (grouped) launchPdl(conv3x3_patch_kernel<EPI_K_TMA_GROUPS, 64>, dim3(plan->grid), dim3(kThreads), plan->smem, s, *a);
+            else if (a->useTma) launchPdl(conv3x3_patch_kernel<EPI_K_TMA, 64>, dim3(plan->grid), dim3(kThreads), plan->smem, s, *a);
+            else launchPdl(conv3x3_patch_kernel<EPI_K_DIRECT, 64>, dim3(plan->grid), dim3(kThreads), plan->smem, s, *a);
         } else {
-            if (grouped) conv3x3_patch_kernel<EPI_K_TMA_GROUPS, 32><<<plan->grid, kThreads, plan->smem, s>>>(*a);
-            else if (a->useTma) conv3x3_patch_kernel<EPI_K_TMA, 32><<<plan->grid, kThreads, plan->smem, s>>>(*a);
-            else conv3x3_patch_kernel<EPI_K_DIRECT, 32><<<plan->grid, kThreads, plan->smem, s>>>(*a);
+            if (grouped) launchPdl(conv3x3_patch_kernel<EPI_K_TMA_GROUPS, 32>, dim3(plan->grid), dim3(kThreads), plan->smem, s, *a);
+            else if (a->useTma) launchPdl(conv3x3_patch_kernel<EPI_K_TMA, 32>, dim3(plan->grid), dim3(kThreads), plan->smem, s, *a);
+            else launchPdl(conv3x3_patch_kernel<EPI_K_DIRECT, 32>, dim3(plan->grid), dim3(kThreads), plan->smem, s, *a);
         }
     } else {
-        if (a->hasSkip) igemm_kernel<EPI_K_TMA_SKIP><<<plan->grid, kThreads, plan->smem, s>>>(*a);
-        else if (grouped) igemm_kernel<EPI_K_TMA_GROUPS><<<plan->grid, kThreads, plan->smem, s>>>(*a);
-        else if (a->useTma) igemm_kernel<EPI_K_TMA><<<plan->grid, kThreads, plan->smem, s>>>(*a);
-        else if (a->staged) igemm_kernel<EPI_K_STAGED><<<plan->grid, kThreads, plan->smem, s>>>(*a);
-        else igemm_kernel<EPI_K_DIRECT><<<plan->grid, kThreads, plan->smem, s>>>(*a);
+        if (a->hasSkip) launchPdl(igemm_kernel<EPI_K_TMA_SKIP>, dim3(plan->grid), dim3(kThreads), plan->smem, s, *a);
+        else if (grouped) launchPdl(igemm_kernel<EPI_K_TMA_GROUPS>, dim3(plan->grid), dim3(kThreads), plan->smem, s, *a);
+        else if (a->useTma) launchPdl(igemm_kernel<EPI_K_TMA>, dim3(plan->grid), dim3(kThreads), plan->smem, s, *a);
+        else if (a->staged) launchPdl(igemm_kernel<EPI_K_STAGED>, dim3(plan->grid), dim3(kThreads), plan->smem, s, *a);
+        else launchPdl(igemm_kernel<EPI_K_DIRECT>, dim3(plan->grid), dim3(kThreads), plan->smem, s, *a);
     }
 }
 

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include "conv_params.h"
+#include "launch.h"
 
 namespace w2x {
 
@@ -38,8 +39,10 @@ __global__ void __launch_bounds__(256) se_excite_kernel(const long long* __restr
     const int img = blockIdx.x;
     const int fcElems = r * c;
     const bool fcInSmem = fcElems <= 2048;
+    pdlLaunchDependents();
     if (fcInSmem)
         for (int i = threadIdx.x; i < fcElems; i += blockDim.x) { sw1[i] = w1[i]; sw2[i] = w2[i]; }
+    pdlWait();  // the FC weights above are constants; the channel sums come from the preceding conv
     for (int ch = threadIdx.x; ch < c; ch += blockDim.x)
         mean[ch] = (float)((double)sums[(size_t)img * c + ch] * (1.0 / (double)kSeFixedScale)) * inv_hw;
     __syncthreads();
@@ -66,7 +69,7 @@ __global__ void __launch_bounds__(256) se_excite_kernel(const long long* __restr
 
 void launchSeExcite(const long long* sums, int n, int c, int r, int hw, const float* w1, const float* b1,
                     const float* w2, const float* b2, float* scale, cudaStream_t s) {
-    se_excite_kernel<<<n, 256, 0, s>>>(sums, c, r, 1.0f / (float)hw, w1, b1, w2, b2, scale);
+    launchPdl(se_excite_kernel, dim3(n), dim3(256), 0, s, sums, c, r, 1.0f / (float)hw, w1, b1, w2, b2, scale);
 }
 
 // in-place x *= scale[img][ch], 8 channels (16 B) per thread
@@ -89,6 +92,8 @@ __global__ void __launch_bounds__(256) se_scale_kernel(__half* __restrict__ x, l
 
 __global__ void __launch_bounds__(256) scale_weights_kernel(const __half* __restrict__ w, __half* __restrict__ wOut, const float* __restrict__ scale,
                                                             int total, int ktot, int cin) {
+    pdlLaunchDependents();
+    pdlWait();
     const int img = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;  // pair index
     if (2 * i >= total) return;
@@ -101,7 +106,7 @@ __global__ void __launch_bounds__(256) scale_weights_kernel(const __half* __rest
 void launchScaleWeights(const __half* w, __half* wOut, const float* scale, int nimg, int npad, int ktot, int cin, cudaStream_t s) {
     const int total = npad * ktot;  // even; k and k+1 share a tap because cin is even
     dim3 grid((total / 2 + 255) / 256, nimg);
-    scale_weights_kernel<<<grid, 256, 0, s>>>(w, wOut, scale, total, ktot, cin);
+    launchPdl(scale_weights_kernel, grid, dim3(256), 0, s, w, wOut, scale, total, ktot, cin);
 }
 
 void launchSeScale(__half* x, int n, int h, int w, int c, const float* scale, cudaStream_t s) {

@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 
 #include "conv_params.h"
+#include "launch.h"
 
 namespace w2x {
 
@@ -18,6 +19,7 @@ template <int LANES>  // lanes per token = c / 8: 12 (c = 96) or 24 (c = 192)
 __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict__ x, __half* __restrict__ y, long long tokens, int c,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta, float eps) {
     constexpr int TPW = 32 / LANES;  // tokens per warp iteration (2 or 1)
+    pdlLaunchDependents();
     const int lane = threadIdx.x & 31;
     const int sub = lane / LANES, li = lane - sub * LANES;
     const bool act = sub < TPW;
@@ -27,6 +29,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict
 #pragma unroll
     for (int i = 0; i < 8; ++i) { gm[i] = act ? gamma[li * 8 + i] : 0.f; bt[i] = act ? beta[li * 8 + i] : 0.f; }
     const float invc = 1.f / (float)c;
+    pdlWait();  // gamma / beta are constants; x comes from the preceding kernel
     for (long long t0 = warpId * TPW; t0 < tokens; t0 += warpCount * TPW) {
         const long long tok = t0 + sub;
         const bool ok = act && tok < tokens;
@@ -76,8 +79,8 @@ void launchLayerNorm(const __half* x, __half* y, long long tokens, int c, const 
     }
     const int grid = sms * 8;
     // contract: c in {96, 192}
-    if (c == 96) layernorm_kernel<12><<<grid, 256, 0, s>>>(x, y, tokens, c, gamma, beta, eps);
-    else layernorm_kernel<24><<<grid, 256, 0, s>>>(x, y, tokens, c, gamma, beta, eps);
+    if (c == 96) launchPdl(layernorm_kernel<12>, dim3(grid), dim3(256), 0, s, x, y, tokens, c, gamma, beta, eps);
+    else launchPdl(layernorm_kernel<24>, dim3(grid), dim3(256), 0, s, x, y, tokens, c, gamma, beta, eps);
 }
 
 // One warp per (window, head); window = 6 (36 tokens).  Both GEMMs of the attention run on warp-level mma.sync
@@ -101,6 +104,8 @@ __global__ void __launch_bounds__(128) window_attention_kernel(const __half* __r
     constexpr int WIN = 6, NT = 36, KS = HD / 16, DT = HD / 8;
     __shared__ int stok[4][48];   // token index of each (padded) window position; padding points at position 0
     __shared__ int sreg[4][48];   // shift-mask region id
+    pdlLaunchDependents();
+    pdlWait();
     const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const long long unit = (long long)blockIdx.x * 4 + wib;
     if (unit >= totalUnits) return;  // whole warp exits together
@@ -241,8 +246,8 @@ void launchWindowAttention(const __half* qkv, __half* out, int n, int h, int w, 
     const int hd = c / heads;
     // torchvision drops the shift when the window covers the whole extent (shifted_window_attention :159-163)
     const int sh = (window >= h || window >= w) ? 0 : shift;
-    if (hd == 16) window_attention_kernel<16><<<blocks, 128, 0, s>>>(qkv, out, n, h, w, c, heads, sh, relpos, units);
-    else window_attention_kernel<32><<<blocks, 128, 0, s>>>(qkv, out, n, h, w, c, heads, sh, relpos, units);
+    if (hd == 16) launchPdl(window_attention_kernel<16>, dim3(blocks), dim3(128), 0, s, qkv, out, n, h, w, c, heads, sh, relpos, units);
+    else launchPdl(window_attention_kernel<32>, dim3(blocks), dim3(128), 0, s, qkv, out, n, h, w, c, heads, sh, relpos, units);
 }
 
 }  // namespace w2x
