@@ -13,16 +13,16 @@
 
 namespace w2x {
 
-// Each lane owns one 16-byte chunk (8 channels) of a token: a warp covers 32 / (c/8) tokens per iteration (c = 96 -> 2 full
-// tokens + idle lanes, c = 192 -> 1 token); the reduction runs over the c/8 lanes of a token with segmented shuffles.
-template <int LANES>  // lanes per token = c / 8: 12 (c = 96) or 24 (c = 192)
+// Each lane owns one 16-byte chunk (8 channels) of a token; a token occupies an aligned segment of SEG lanes (c = 96: 12 of 16
+// lanes, two tokens per warp; c = 192: 24 of 32 lanes), so both reductions are log2(SEG)-step xor butterflies (idle lanes add 0).
+template <int SEG>
 __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict__ x, __half* __restrict__ y, long long tokens, int c,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta, float eps) {
-    constexpr int TPW = 32 / LANES;  // tokens per warp iteration (2 or 1)
+    constexpr int TPW = 32 / SEG;  // tokens per warp iteration (2 or 1)
     pdlLaunchDependents();
     const int lane = threadIdx.x & 31;
-    const int sub = lane / LANES, li = lane - sub * LANES;
-    const bool act = sub < TPW;
+    const int sub = lane / SEG, li = lane - sub * SEG;
+    const bool act = li * 8 < c;
     const long long warpId = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const long long warpCount = (long long)gridDim.x * (blockDim.x >> 5);
     float gm[8], bt[8];
@@ -46,18 +46,17 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict
         float sum = 0.f;
 #pragma unroll
         for (int i = 0; i < 8; ++i) sum += v[i];
-        // all-lanes butterfly over the token's LANES lanes: gather via shuffles from the token's first lane range
-        float tot = 0.f;
 #pragma unroll
-        for (int j = 0; j < LANES; ++j) tot += __shfl_sync(0xffffffffu, sum, sub * LANES + j);
-        const float mean = tot * invc;
+        for (int o = SEG / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float mean = sum * invc;
         float sq = 0.f;
+        if (act) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { const float d = v[i] - mean; sq += d * d; }
-        float vt = 0.f;
+            for (int i = 0; i < 8; ++i) { const float d = v[i] - mean; sq += d * d; }
+        }
 #pragma unroll
-        for (int j = 0; j < LANES; ++j) vt += __shfl_sync(0xffffffffu, sq, sub * LANES + j);
-        const float rstd = rsqrtf(vt * invc + eps);
+        for (int o = SEG / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        const float rstd = rsqrtf(sq * invc + eps);
         if (ok) {
             uint4 o;
             __half2* oh = reinterpret_cast<__half2*>(&o);
@@ -79,15 +78,18 @@ void launchLayerNorm(const __half* x, __half* y, long long tokens, int c, const 
     }
     const int grid = sms * 8;
     // contract: c in {96, 192}
-    if (c == 96) launchPdl(layernorm_kernel<12>, dim3(grid), dim3(256), 0, s, x, y, tokens, c, gamma, beta, eps);
-    else launchPdl(layernorm_kernel<24>, dim3(grid), dim3(256), 0, s, x, y, tokens, c, gamma, beta, eps);
+    if (c == 96) launchPdl(layernorm_kernel<16>, dim3(grid), dim3(256), 0, s, x, y, tokens, c, gamma, beta, eps);
+    else launchPdl(layernorm_kernel<32>, dim3(grid), dim3(256), 0, s, x, y, tokens, c, gamma, beta, eps);
 }
 
 // One warp per (window, head); window = 6 (36 tokens).  Both GEMMs of the attention run on warp-level mma.sync
 // (m16n8k16, fp16 in / fp32 accumulate): S = Q K^T as 3 row tiles x 5 column tiles (36 -> 48 x 40, padding masked), the
 // softmax works on the accumulator layout (quad shuffles), and the probabilities are re-used in registers as the A operand
-// of O = P V (the accumulator layout of two adjacent 8-column tiles IS the A fragment of one k-step).  Q/K/V fragments are
-// loaded straight from the [token][3C] tensor (4-byte loads, L1-resident): no shared-memory staging, no re-layout.
+// of O = P V (the accumulator layout of two adjacent 8-column tiles IS the A fragment of one k-step).
+// The warp's Q, K and V slices (36 tokens x head dim each) are staged in shared memory with 16-byte cp.async copies (the
+// roll + window partition is the gather's address math) and read back as MMA fragments with ldmatrix (.trans for V); rows are
+// padded by 16 bytes so the eight row addresses of an 8x8 matrix fall into distinct banks.  The output tile goes back
+// through the same buffer so that it leaves in 16-byte stores.
 __device__ __forceinline__ void mma16816h(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
@@ -97,13 +99,25 @@ __device__ __forceinline__ uint32_t packHalf2(float a, float b) {
     const __half2 h = __floats2half2_rn(a, b);
     return *reinterpret_cast<const uint32_t*>(&h);
 }
+__device__ __forceinline__ void ldsm4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm2(uint32_t addr, uint32_t& r0, uint32_t& r1) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm4t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
 
 template <int HD>
 __global__ void __launch_bounds__(128) window_attention_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int n, int h, int w, int c,
                                                                int heads, int shift, const float* __restrict__ relpos, long long totalUnits) {
-    constexpr int WIN = 6, NT = 36, KS = HD / 16, DT = HD / 8;
+    constexpr int WIN = 6, NT = 36, KS = HD / 16, DT = HD / 8, CH = HD / 8;
+    constexpr int PITCH = HD * 2 + 16;   // bytes per staged row
+    constexpr int MAT = 48 * PITCH;      // one of Q / K / V (48 rows: 36 tokens + zero padding up to the 3 x 16 row tiles)
     __shared__ int stok[4][48];   // token index of each (padded) window position; padding points at position 0
     __shared__ int sreg[4][48];   // shift-mask region id
+    __shared__ __align__(16) uint8_t stage[4][3 * MAT];
     pdlLaunchDependents();
     pdlWait();
     const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -126,31 +140,46 @@ __global__ void __launch_bounds__(128) window_attention_kernel(const __half* __r
         sreg[wib][p] = hid * 3 + wid;
     }
     __syncwarp();
+    // ---- stage Q | K | V of this (window, head): 36 x 3 x CH chunks of 16 bytes, padding rows zeroed ----
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(&stage[wib][0]);
     const long long rowStride = 3ll * c;
-    const __half* qbase = qkv + head * HD;
+    const __half* hbase = qkv + head * HD;
+    for (int idx = lane; idx < NT * 3 * CH; idx += 32) {
+        const int p = idx / (3 * CH), rem = idx - p * (3 * CH);
+        const int which = rem / CH, ch = rem - which * CH;
+        const __half* src = hbase + (long long)stok[wib][p] * rowStride + which * c + ch * 8;
+        const uint32_t dst = sbase + (uint32_t)(which * MAT + p * PITCH + ch * 16);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    for (int idx = lane; idx < 12 * 3 * CH; idx += 32) {
+        const int p = NT + idx / (3 * CH), rem = idx % (3 * CH);
+        *reinterpret_cast<uint4*>(&stage[wib][(rem / CH) * MAT + p * PITCH + (rem % CH) * 16]) = make_uint4(0, 0, 0, 0);
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    const uint32_t sQ = sbase, sK = sbase + MAT, sV = sbase + 2 * MAT;
     // ---- S = Q K^T ----
     float sacc[3][5][4];
 #pragma unroll
     for (int i = 0; i < 3; ++i)
 #pragma unroll
         for (int j = 0; j < 5; ++j) sacc[i][j][0] = sacc[i][j][1] = sacc[i][j][2] = sacc[i][j][3] = 0.f;
+    uint32_t bk[5][KS][2];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        // 8 key tokens x HD dims: matrix m of the ldmatrix = 16-byte chunk m of the rows -> (b0, b1) of k-step m / 2
+        if (KS == 2) ldsm4(sK + (uint32_t)((8 * j + (lane & 7)) * PITCH + (lane >> 3) * 16), bk[j][0][0], bk[j][0][1], bk[j][KS - 1][0], bk[j][KS - 1][1]);
+        else ldsm2(sK + (uint32_t)((8 * j + (lane & 7)) * PITCH + ((lane >> 3) & 1) * 16), bk[j][0][0], bk[j][0][1]);
+    }
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks) {
-        uint32_t bk[5][2];
-#pragma unroll
-        for (int j = 0; j < 5; ++j) {
-            const __half* kp = qbase + (long long)stok[wib][8 * j + g] * rowStride + c + 16 * ks + 2 * t;
-            bk[j][0] = *reinterpret_cast<const uint32_t*>(kp);
-            bk[j][1] = *reinterpret_cast<const uint32_t*>(kp + 8);
-        }
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-            const __half* q0 = qbase + (long long)stok[wib][16 * i + g] * rowStride + 16 * ks + 2 * t;
-            const __half* q1 = qbase + (long long)stok[wib][16 * i + g + 8] * rowStride + 16 * ks + 2 * t;
-            const uint32_t a0 = *reinterpret_cast<const uint32_t*>(q0), a1 = *reinterpret_cast<const uint32_t*>(q1);
-            const uint32_t a2 = *reinterpret_cast<const uint32_t*>(q0 + 8), a3 = *reinterpret_cast<const uint32_t*>(q1 + 8);
+            uint32_t a0, a1, a2, a3;
+            ldsm4(sQ + (uint32_t)((16 * i + (lane & 7) + ((lane >> 3) & 1) * 8) * PITCH + (2 * ks + (lane >> 4)) * 16), a0, a1, a2, a3);
 #pragma unroll
-            for (int j = 0; j < 5; ++j) mma16816h(sacc[i][j], a0, a1, a2, a3, bk[j][0], bk[j][1]);
+            for (int j = 0; j < 5; ++j) mma16816h(sacc[i][j], a0, a1, a2, a3, bk[j][ks][0], bk[j][ks][1]);
         }
     }
     // ---- scale + relative position bias + shift mask + softmax (rows 16i+g and 16i+g+8; columns 8j+2t, 8j+2t+1) ----
@@ -203,38 +232,39 @@ __global__ void __launch_bounds__(128) window_attention_kernel(const __half* __r
     for (int i = 0; i < 3; ++i)
 #pragma unroll
         for (int jd = 0; jd < DT; ++jd) oacc[i][jd][0] = oacc[i][jd][1] = oacc[i][jd][2] = oacc[i][jd][3] = 0.f;
-    const unsigned short* vbase = reinterpret_cast<const unsigned short*>(qbase + 2 * c);
 #pragma unroll
     for (int s = 0; s < 3; ++s) {
-        // V fragments: b0 = (tokens 16s+2t, +1 ; dim 8jd+g), b1 = (tokens 16s+2t+8, +9); padded tokens carry P = 0
-        const long long r0 = (long long)stok[wib][16 * s + 2 * t] * rowStride, r1 = (long long)stok[wib][16 * s + 2 * t + 1] * rowStride;
-        const long long r2 = (long long)stok[wib][min(16 * s + 2 * t + 8, 47)] * rowStride, r3 = (long long)stok[wib][min(16 * s + 2 * t + 9, 47)] * rowStride;
 #pragma unroll
-        for (int jd = 0; jd < DT; ++jd) {
-            const int d = 8 * jd + g;
-            const uint32_t b0 = (uint32_t)vbase[r0 + d] | ((uint32_t)vbase[r1 + d] << 16);
-            const uint32_t b1 = (uint32_t)vbase[r2 + d] | ((uint32_t)vbase[r3 + d] << 16);
+        for (int jp = 0; jp < DT / 2; ++jp) {
+            // V^T fragments of dims 16jp..16jp+15 for tokens 16s..16s+15 (padded tokens are zero rows and carry P = 0)
+            uint32_t b00, b01, b10, b11;
+            ldsm4t(sV + (uint32_t)((16 * s + (lane & 7) + ((lane >> 3) & 1) * 8) * PITCH + (2 * jp + (lane >> 4)) * 16), b00, b01, b10, b11);
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
                 const uint32_t a0 = pa[i][2 * s][0], a1 = pa[i][2 * s][1];
                 const uint32_t a2 = (2 * s + 1 < 5) ? pa[i][(2 * s + 1 < 5) ? 2 * s + 1 : 0][0] : 0u;
                 const uint32_t a3 = (2 * s + 1 < 5) ? pa[i][(2 * s + 1 < 5) ? 2 * s + 1 : 0][1] : 0u;
-                mma16816h(oacc[i][jd], a0, a1, a2, a3, b0, b1);
+                mma16816h(oacc[i][2 * jp], a0, a1, a2, a3, b00, b01);
+                mma16816h(oacc[i][2 * jp + 1], a0, a1, a2, a3, b10, b11);
             }
         }
     }
+    // ---- O -> the Q buffer (all Q reads are done) -> 16-byte stores ----
+    __syncwarp();
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
             const int r = 16 * i + g + 8 * half;
-            if (r < NT) {
-                __half* op = out + (long long)stok[wib][r] * c + head * HD + 2 * t;
 #pragma unroll
-                for (int jd = 0; jd < DT; ++jd)
-                    *reinterpret_cast<__half2*>(op + 8 * jd) = __floats2half2_rn(oacc[i][jd][2 * half], oacc[i][jd][2 * half + 1]);
-            }
+            for (int jd = 0; jd < DT; ++jd)
+                *reinterpret_cast<__half2*>(&stage[wib][r * PITCH + (8 * jd + 2 * t) * 2]) = __floats2half2_rn(oacc[i][jd][2 * half], oacc[i][jd][2 * half + 1]);
         }
+    }
+    __syncwarp();
+    for (int idx = lane; idx < NT * CH; idx += 32) {
+        const int p = idx / CH, ch = idx - p * CH;
+        *reinterpret_cast<uint4*>(out + (long long)stok[wib][p] * c + head * HD + ch * 8) = *reinterpret_cast<const uint4*>(&stage[wib][p * PITCH + ch * 16]);
     }
 }
 
