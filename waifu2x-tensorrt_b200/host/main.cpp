@@ -2,14 +2,15 @@
 // (/root/reference/src/main.cpp:17-140 options, :156-160 extensions, :201-209 model path + suffix, :211-274 render loop,
 // :275-294 build), over the trt::Img2Img shim (img2img.hpp -> libw2x.so) and the ffmpeg pipes in videoio.hpp.
 //
-// Differences by design: frames are pipelined (w2x_submit/w2x_wait: decode, H2D, compute, D2H and encode of up to three
-// consecutive frames overlap; the reference serialises read -> render -> write, main.cpp:263-269), `--ffmpegDir` and
+// Differences by design: frames are pipelined (reader thread -> pinned ring -> w2x_submit/w2x_wait -> writer thread: decode, H2D,
+// compute, D2H and encode overlap; the reference serialises read -> render -> write on one thread, main.cpp:263-269), `--ffmpegDir` and
 // `--modelsDir` are settable (the reference hard-wires "" and "models/"), and a render failure releases the pipes
 // before returning -1.  No CLI11/spdlog: the parser below accepts the same spellings and value sets.
 //
-// Build: make -C waifu2x-tensorrt_b200/csrc cli   (g++ -std=c++17, links libw2x.so only)
+// Build: make -C waifu2x-tensorrt_b200/csrc cli   (g++ -std=c++17 -pthread, links libw2x.so only)
 #include <algorithm>
 #include <chrono>
+#include <condition_variable>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -18,8 +19,10 @@
 #include <functional>
 #include <iostream>
 #include <map>
+#include <mutex>
 #include <set>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "img2img.hpp"
@@ -254,9 +257,12 @@ int main(int argc, char* argv[]) {
     rc.tta = o.tta;
     if (!engine.load(modelPath, rc)) return -1;
 
-    constexpr int kRing = 3;  // frames in flight == Engine::kSlots
+    // Decode, GPU and encode are decoupled (the reference serialises them on one thread, main.cpp:263-269):
+    // a reader thread fills a ring of pinned input frames from the ffmpeg pipe, this thread submits them to the engine (at most
+    // three in flight, Engine::kSlots) and retires them in order, a writer thread drains finished frames into the encoder pipe.
+    constexpr int kRing = 6, kInFlight = 3;
+    enum SlotState { FREE, FILLED, SUBMITTED, DONE };
     PinnedBuffer in[kRing], out[kRing];
-    int tickets[kRing];
     VideoCapture capture;
     VideoWriter writer;
     capture.setFfmpegDir(o.ffmpegDir);
@@ -280,20 +286,78 @@ int main(int argc, char* argv[]) {
             writer.open();
             for (int s = 0; s < kRing; ++s) { in[s].reserve(inSize.bytes()); out[s].reserve(outSize.bytes()); }
 
-            auto retire = [&](size_t f) {  // frame f's upscaled pixels -> encoder
-                if (!engine.wait(tickets[f % kRing])) throw std::runtime_error("render failed");
-                writer.write(out[f % kRing].p, outSize);
+            std::mutex mu;
+            std::condition_variable cv;
+            SlotState state[kRing];
+            for (auto& st : state) st = FREE;
+            size_t framesRead = frameCount;  // lowered by the reader if the pipe ends early
+            bool abort = false;
+            std::exception_ptr failure;
+            auto fail = [&](std::exception_ptr e) {
+                std::lock_guard<std::mutex> lk(mu);
+                if (!failure) failure = e;
+                abort = true;
+                cv.notify_all();
+            };
+            auto waitFor = [&](size_t f, SlotState want) {  // true when slot f % kRing reached `want`; false on abort / end of input
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return abort || state[f % kRing] == want || (want == FILLED && f >= framesRead); });
+                return !abort && state[f % kRing] == want && f < framesRead;
+            };
+            auto setState = [&](size_t f, SlotState st) {
+                std::lock_guard<std::mutex> lk(mu);
+                state[f % kRing] = st;
+                cv.notify_all();
+            };
+            std::thread reader([&] {
+                try {
+                    for (size_t f = 0; f < frameCount; ++f) {
+                        if (!waitFor(f, FREE)) return;
+                        if (!capture.read(in[f % kRing].p)) {
+                            std::lock_guard<std::mutex> lk(mu);
+                            framesRead = f;
+                            cv.notify_all();
+                            return;
+                        }
+                        setState(f, FILLED);
+                    }
+                } catch (...) { fail(std::current_exception()); }
+            });
+            std::thread sink([&] {
+                try {
+                    for (size_t f = 0; f < frameCount; ++f) {
+                        {
+                            std::unique_lock<std::mutex> lk(mu);
+                            cv.wait(lk, [&] { return abort || state[f % kRing] == DONE || f >= framesRead; });
+                            if (abort || f >= framesRead) return;
+                        }
+                        writer.write(out[f % kRing].p, outSize);
+                        setState(f, FREE);
+                    }
+                } catch (...) { fail(std::current_exception()); }
+            });
+            int tickets[kRing];
+            size_t submitted = 0, retired = 0;
+            auto retire = [&]() {
+                if (!engine.wait(tickets[retired % kRing])) throw std::runtime_error("render failed");
+                setState(retired, DONE);
+                ++retired;
                 frameIndex++;
             };
-            size_t submitted = 0;
-            for (; submitted < frameCount; ++submitted) {
-                if (submitted >= (size_t)kRing) retire(submitted - kRing);
-                const int s = (int)(submitted % kRing);
-                if (!capture.read(in[s].p)) break;
-                tickets[s] = engine.submit(in[s].p, inSize.width, inSize.height, (size_t)inSize.width * 3, out[s].p, (size_t)outSize.width * 3);
-                if (tickets[s] < 0) throw std::runtime_error("render failed");
-            }
-            for (size_t f = submitted > (size_t)kRing ? submitted - kRing : 0; f < submitted; ++f) retire(f);
+            try {
+                while (waitFor(submitted, FILLED)) {
+                    if (submitted - retired >= (size_t)kInFlight) retire();
+                    const int s = (int)(submitted % kRing);
+                    tickets[s] = engine.submit(in[s].p, inSize.width, inSize.height, (size_t)inSize.width * 3, out[s].p, (size_t)outSize.width * 3);
+                    if (tickets[s] < 0) throw std::runtime_error("render failed");
+                    setState(submitted, SUBMITTED);
+                    ++submitted;
+                }
+                while (retired < submitted) retire();
+            } catch (...) { fail(std::current_exception()); }
+            reader.join();
+            sink.join();
+            if (failure) std::rethrow_exception(failure);
             capture.release();
             writer.release();
             fileIndex++;

@@ -15,6 +15,18 @@
 #include <sstream>
 #include <stdexcept>
 #include <string>
+#if defined(__linux__)
+#include <fcntl.h>
+#endif
+
+// 1 MiB kernel pipe buffers (Linux default is 64 KiB): a 4K bgr24 frame is 24.9 MB, so fewer, larger transfers per frame
+inline void growPipe(FILE* p) {
+#if defined(__linux__) && defined(F_SETPIPE_SZ)
+    if (p) (void)fcntl(fileno(p), F_SETPIPE_SZ, 1 << 20);
+#else
+    (void)p;
+#endif
+}
 
 struct FrameSize {  // stands in for cv::Size2i
     int width = -1, height = -1;
@@ -54,6 +66,7 @@ public:
             const std::string cmd = ffmpegDir + "ffmpeg -v error -i \"" + path + "\" -f image2pipe -vcodec rawvideo -pix_fmt bgr24 -";
             pipe = popen(cmd.c_str(), "r");
             if (!pipe) throw std::runtime_error("could not open ffmpeg with command\"" + cmd + "\"");
+            growPipe(pipe);
             opened = true;
             frameIndex = -1;
         } catch (...) {
@@ -146,6 +159,7 @@ public:
                                 " \"" + outputFile + "\"";
         pipe = popen(cmd.c_str(), "w");
         if (!pipe) throw std::runtime_error("could not open ffmpeg pipe");
+        growPipe(pipe);
         opened = true;
     }
 
