@@ -291,7 +291,7 @@ def main():
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
                          "peak_source": f"MEASURED_PEAKS.json bf16_tflops ({peak_kind}, burst: kernel timed alone)",
                          "launch_ms_sum": dom_ms, "flops_sum": dom_fl, "traffic": traffic,
-                         "tensor_pipe_busy": "0.92 on unet2.conv5 (ncu hmma_cycles_active / sm cycles, profiles/r01_ncu_patch_batch.txt)" if args.workload == "cunet" else None,
+                         "tensor_pipe_busy": "0.98 on unet2.conv5 (ncu hmma_cycles_active per TPC / 2 / sm cycles_active, profiles/r01_ncu_patch_batch.txt): the pipe waits on shared-memory operands, see DESIGN 4.1" if args.workload == "cunet" else None,
                          "model_stage": {"achieved": stage_tflops, "peak": float(peaks.get("bf16_tflops_sustained", 1400.0)), "unit": "TFLOP/s",
                                          "frac": stage_tflops / float(peaks.get("bf16_tflops_sustained", 1400.0)) if stage_tflops else None,
                                          "flops_per_frame": flops_frame, "note": "all model kernels of the last timed frame (events inside the timed region) vs the sustained peak"}},
