@@ -356,7 +356,17 @@ void Engine::buildPlanCunet() {
                 E.p.se_sum = E.sePartial;
                 E.seFused = true;
             }
-            E.plan = igemmCreatePlan(E.p);
+            // a UNet's second convolution computes its RGB first layer on the fly (fusedFirstProducer): the 32-channel tensor
+            // between them never touches HBM and the first layer's launch disappears
+            static const bool noFuse = std::getenv("W2X_NO_FUSE_FIRST") != nullptr;
+            if (!noFuse && !layers.empty() && layers.back().impl == IMPL_FIRST && !L.se_r && igemmFusedFirstSupported(E.p, layers.back().p)) {
+                E.plan = igemmCreatePlanFusedFirst(E.p, layers.back().p);
+                layers.back().impl = IMPL_SKIP;
+                E.flops += layers.back().flops;
+                layers.back().flops = 0;
+            } else {
+                E.plan = igemmCreatePlan(E.p);
+            }
         }
         else throw Error("no kernel for layer " + L.name);
         if (L.se_r) {
@@ -455,6 +465,7 @@ void Engine::buildPlanCunet() {
 
 void Engine::launchLayer(LayerExec& L, cudaStream_t s, __half* outp, int nImg) {
     switch (L.impl) {
+        case IMPL_SKIP: break;  // computed inside the next layer's kernel
         case IMPL_IGEMM: igemmLaunch(L.plan, s, outp, nImg); break;
         case IMPL_HEAD: launchConvHead(L.head, s, outp, nImg); break;
         case IMPL_LAYERNORM:
@@ -657,7 +668,7 @@ int Engine::layerKernel(int index, char* buf, int cap) const {
     if (L.plan) igemmDescribe(L.plan, buf, cap);
     else std::snprintf(buf, cap, "%s", L.impl == IMPL_FIRST ? "first-layer mma.sync" : L.impl == IMPL_LAYERNORM ? "layernorm" :
                                        L.impl == IMPL_ATTENTION ? "window-attention mma.sync" :
-                                       L.impl == IMPL_HEAD ? "image head, taps-in-N mma.sync" : "direct (reference kernel)");
+                                       L.impl == IMPL_HEAD ? "image head, taps-in-N mma.sync" : L.impl == IMPL_SKIP ? "fused into the next layer" : "direct (reference kernel)");
     return 1;
 }
 
@@ -676,7 +687,7 @@ void Engine::runModel(cudaStream_t s, __half* finalOut, int nImages) {
     for (auto& L : layers) {
         __half* outp = (L.isFinal && finalOut) ? finalOut : L.p.out;
         launchLayer(L, s, outp, n);
-        ++launches;
+        if (L.impl != IMPL_SKIP) ++launches;
         if (debugSync) {
             cudaError_t de = cudaStreamSynchronize(s);
             if (de == cudaSuccess) de = cudaGetLastError();
@@ -1120,7 +1131,7 @@ int Engine::profileLayers(int repeats, char (*names)[48], float* ms, double* flo
             if (std::getenv("W2X_VERBOSE")) {
                 char d[256] = "";
                 if (L.plan) igemmDescribe(L.plan, d, sizeof(d));
-                std::fprintf(stderr, "[w2x] %-28s %s\n", L.name.c_str(), L.plan ? d : (L.impl == IMPL_FIRST ? "first-layer mma.sync" : L.impl == IMPL_HEAD ? "image head taps-in-N mma.sync" : "direct"));
+                std::fprintf(stderr, "[w2x] %-28s %s\n", L.name.c_str(), L.plan ? d : (L.impl == IMPL_FIRST ? "first-layer mma.sync" : L.impl == IMPL_HEAD ? "image head taps-in-N mma.sync" : L.impl == IMPL_SKIP ? "fused into the next layer" : "direct"));
             }
             ms[i] = t / repeats;
             flops[i] = L.flops * batch;

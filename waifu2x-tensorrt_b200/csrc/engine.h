@@ -25,7 +25,7 @@ struct Act {
     size_t elems() const { return (size_t)n * h * w * c; }
 };
 
-enum ConvImpl { IMPL_DIRECT = 0, IMPL_FIRST = 1, IMPL_IGEMM = 2, IMPL_LAYERNORM = 3, IMPL_ATTENTION = 4, IMPL_HEAD = 5 };
+enum ConvImpl { IMPL_DIRECT = 0, IMPL_FIRST = 1, IMPL_IGEMM = 2, IMPL_LAYERNORM = 3, IMPL_ATTENTION = 4, IMPL_HEAD = 5, IMPL_SKIP = 6 };
 
 struct LayerExec {
     std::string name;

@@ -44,6 +44,7 @@ struct ConvArgs {
     CUtensorMap tmB;     // weights [npad][ktot]
     CUtensorMap tmOut;   // TMA-store view of the output (useTma)
     CUtensorMap tmSkip;  // TMA-load view of the skip tensor (hasSkip)
+    CUtensorMap tmRgb;   // fused first layer: [img][H][W*4] view of the NHWC4 input, 20 x 48-element boxes (no swizzle)
     ConvParams p;
     int kc, bn, bw, bh, bwShift;
     int tilesX, tilesY, tilesN, totalTiles;
@@ -56,6 +57,15 @@ struct ConvArgs {
     int staged;                 // EPI_K_STAGED: generic-proxy staging + coalesced copy-out (any N, residual, GELU)
     uint32_t stagedPitch, stagedBuf;
     uint32_t headerBytes;       // barriers + TMEM slot (1 KB) | bias[npad] fp32 (1 KB multiple) | SE scratch (1 KB)
+    // fused RGB first layer (conv3x3 4 -> 32 + LeakyReLU computed by four extra warps straight into the patch ring): see fusedFirstProducer
+    int fused;
+    const __half* fuseIn;       // NHWC4 fp16 input of the first layer, [gn][fuseH][fuseW][4]
+    const __half* fuseW;        // first-layer weights [32][36], k = (ky*3+kx)*4 + c
+    const float* fuseBias;      // [32]
+    float fuseSlope;
+    int fuseW_px, fuseH_px;
+    long long fuseSn;           // elements between images of fuseIn
+    uint32_t fuseOff;           // byte offset (from the aligned smem base) of the two RGB patch buffers
 };
 
 struct IgemmPlan {
@@ -73,7 +83,10 @@ constexpr int kEpiThreads = 32 * kEpiWarps;
 constexpr int kPatchW = 10, kPatchH = 18;
 
 // header layout (byte offsets from the 1024-aligned smem base)
-constexpr uint32_t kOffFull = 0, kOffEmpty = 64, kOffTFull = 128, kOffTEmpty = 144, kOffSkip = 160, kOffW = 184, kOffSlot = 256, kOffBias = 1024;
+constexpr uint32_t kOffFull = 0, kOffEmpty = 64, kOffTFull = 128, kOffTEmpty = 144, kOffSkip = 160, kOffW = 184, kOffRgbFull = 192, kOffRgbEmpty = 224,
+                   kOffSlot = 256, kOffBias = 1024;
+constexpr int kRgbBufs = 4;        // fused first layer: RGB patches in flight
+constexpr int kFuseWarps = 6;      // fused first layer: producer warps, two 16-pixel blocks each (mma.sync is latency-bound per warp)
 
 enum EpiKind { EPI_K_DIRECT = 0, EPI_K_TMA = 1, EPI_K_TMA_SKIP = 2, EPI_K_STAGED = 3, EPI_K_TMA_GROUPS = 4 };
 
@@ -541,10 +554,117 @@ __device__ __forceinline__ void epilogueTmaGroups(const ConvArgs& a, uint32_t ba
     if (leader) bulkWaitAll();
 }
 
-__device__ __forceinline__ void setupCommon(const ConvArgs& a, uint32_t base, uint8_t* sm, int warp, int accReaders) {
+// ---- fused RGB first layer ---------------------------------------------------------------------------------------------
+// The 32-channel input of the second convolution of a UNet (conv1.conv.2) is itself conv3x3(RGB) + LeakyReLU: 36 MACs per value.
+// Instead of a separate kernel writing that tensor to HBM and TMA reading it back, four extra warps compute each tile's 18x10x32
+// patch from a 20x12 RGB patch (cp.async, double buffered) with mma.sync (M = 16 patch pixels, N = 32, K = 36 -> 48) and store it
+// in the exact layout a SWIZZLE_64B TMA box would have produced (16-byte chunk index ^= (pixel >> 1) & 3), then publish the
+// stage on the same full barrier the MMA warp waits on (generic-proxy writes + fence.proxy.async).  Saves, per output pixel of
+// the first layer, 64 B written + 64 B (x halo) read of HBM traffic and one kernel launch.
+__device__ __forceinline__ void fusedFirstProducer(const ConvArgs& a, uint32_t base, uint32_t stage0, int nMine, int first, int step) {
+    constexpr int kRgbW = kPatchW + 2, kRgbH = kPatchH + 2;  // 12 x 20 input pixels
+    const int tid = threadIdx.x - kThreads;                  // 0 .. 32 * kFuseWarps - 1
+    const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const uint32_t barFull = base + kOffFull, barEmpty = base + kOffEmpty;
+    const uint32_t rgb0 = base + a.fuseOff;
+    // B fragments and bias of the first layer (constants)
+    uint32_t bf[4][3][2];
+    float bias[4][2];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+        const __half* wrow = a.fuseW + (8 * nt + g) * 36;
+#pragma unroll
+        for (int ks = 0; ks < 3; ++ks) {
+            const int k0 = 16 * ks + 2 * t;
+            bf[nt][ks][0] = k0 < 36 ? *reinterpret_cast<const uint32_t*>(wrow + k0) : 0u;
+            bf[nt][ks][1] = k0 + 8 < 36 ? *reinterpret_cast<const uint32_t*>(wrow + k0 + 8) : 0u;
+        }
+        bias[nt][0] = a.fuseBias[8 * nt + 2 * t];
+        bias[nt][1] = a.fuseBias[8 * nt + 2 * t + 1];
+    }
+    // A fragment addressing: k = tap*4 + c; register (ks, h) of a lane holds k = 16ks + 2t + 8h, k + 1 of its pixel row
+    uint32_t aOff[3][2];
+#pragma unroll
+    for (int ks = 0; ks < 3; ++ks)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int k = 16 * ks + 2 * t + 8 * h;
+            const int tap = min(k >> 2, 8);  // taps 9..11 are K padding: their weights are zero, any finite pixel will do
+            aOff[ks][h] = (uint32_t)((((tap / 3) * kRgbW + tap % 3) * 4 + (k & 3)) * 2);
+        }
+    pdlWait();  // weights / bias above are constants; the RGB tiles come from the preceding kernel
+
+    // RGB patches arrive by TMA (issued by warp 0, kRgbBufs tiles deep): nothing of this warp's own is in flight when it fences
+    const uint32_t barRgbFull = base + kOffRgbFull, barRgbEmpty = base + kOffRgbEmpty;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int k = 0; k < nMine; ++k) {
+        const int rb = k % kRgbBufs;
+        mbarWait(barRgbFull + 8u * rb, (uint32_t)(k / kRgbBufs) & 1u);
+        const uint32_t rgb = rgb0 + (uint32_t)rb * 2048u;
+        const uint32_t dst = stage0 + (uint32_t)stage * a.stageStride;
+        mbarWait(barEmpty + 8u * stage, phase ^ 1u);  // the MMAs that read this ring slot have completed
+        constexpr int kBlk = 12 / kFuseWarps;
+        static_assert((kPatchW * kPatchH + 15) / 16 == kBlk * kFuseWarps, "whole 16-pixel blocks per producer warp");
+        // this warp's blocks b = warp, warp + kFuseWarps, ... advance together so that their load -> MMA -> pack chains overlap
+        uint32_t r0[kBlk], r1[kBlk];
+        float d[kBlk][4][4];
+#pragma unroll
+        for (int bi = 0; bi < kBlk; ++bi) {
+            const int p0 = 16 * (warp + kFuseWarps * bi) + g, p1 = p0 + 8;
+            const int q0 = min(p0, kPatchW * kPatchH - 1), q1 = min(p1, kPatchW * kPatchH - 1);
+            r0[bi] = rgb + (uint32_t)(((q0 / kPatchW) * kRgbW + q0 % kPatchW) * 8);
+            r1[bi] = rgb + (uint32_t)(((q1 / kPatchW) * kRgbW + q1 % kPatchW) * 8);
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) { d[bi][nt][0] = bias[nt][0]; d[bi][nt][1] = bias[nt][1]; d[bi][nt][2] = bias[nt][0]; d[bi][nt][3] = bias[nt][1]; }
+        }
+#pragma unroll
+        for (int ks = 0; ks < 3; ++ks) {
+            uint32_t af[kBlk][4];
+#pragma unroll
+            for (int bi = 0; bi < kBlk; ++bi) {
+                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(af[bi][0]) : "r"(r0[bi] + aOff[ks][0]));
+                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(af[bi][1]) : "r"(r1[bi] + aOff[ks][0]));
+                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(af[bi][2]) : "r"(r0[bi] + aOff[ks][1]));
+                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(af[bi][3]) : "r"(r1[bi] + aOff[ks][1]));
+            }
+#pragma unroll
+            for (int bi = 0; bi < kBlk; ++bi)
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt)
+                    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                                 : "+f"(d[bi][nt][0]), "+f"(d[bi][nt][1]), "+f"(d[bi][nt][2]), "+f"(d[bi][nt][3])
+                                 : "r"(af[bi][0]), "r"(af[bi][1]), "r"(af[bi][2]), "r"(af[bi][3]), "r"(bf[nt][ks][0]), "r"(bf[nt][ks][1]));
+        }
+        __syncwarp();
+        if (lane == 0) mbarArrive(barRgbEmpty + 8u * rb);  // this warp has read everything it needs from the RGB patch
+        // LeakyReLU, fp16, SWIZZLE_64B placement: pixel row p is 64 bytes, chunk (8 channels) nt lands at nt ^ ((p >> 1) & 3)
+#pragma unroll
+        for (int bi = 0; bi < kBlk; ++bi) {
+            const int p0 = 16 * (warp + kFuseWarps * bi) + g, p1 = p0 + 8;
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                const __half2 lo = __floats2half2_rn(fmaxf(d[bi][nt][0], d[bi][nt][0] * a.fuseSlope), fmaxf(d[bi][nt][1], d[bi][nt][1] * a.fuseSlope));
+                const __half2 hi = __floats2half2_rn(fmaxf(d[bi][nt][2], d[bi][nt][2] * a.fuseSlope), fmaxf(d[bi][nt][3], d[bi][nt][3] * a.fuseSlope));
+                if (p0 < kPatchW * kPatchH)
+                    asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst + (uint32_t)p0 * 64u + ((uint32_t)(nt ^ ((p0 >> 1) & 3)) << 4) + 4u * t),
+                                 "r"(*reinterpret_cast<const uint32_t*>(&lo)) : "memory");
+                if (p1 < kPatchW * kPatchH)
+                    asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst + (uint32_t)p1 * 64u + ((uint32_t)(nt ^ ((p1 >> 1) & 3)) << 4) + 4u * t),
+                                 "r"(*reinterpret_cast<const uint32_t*>(&hi)) : "memory");
+            }
+        }
+        fenceProxyAsync();  // generic-proxy stores above -> visible to the tensor core's async-proxy reads
+        __syncwarp();
+        if (lane == 0) mbarArrive(barFull + 8u * stage);
+        if (++stage == a.stages) { stage = 0; phase ^= 1u; }
+    }
+}
+
+__device__ __forceinline__ void setupCommon(const ConvArgs& a, uint32_t base, uint8_t* sm, int warp, int accReaders, int fullArrivals = 1) {
     if (threadIdx.x == 0) {
         for (int s = 0; s < 8; ++s) {
-            mbarInit(base + kOffFull + 8u * s, 1);
+            mbarInit(base + kOffFull + 8u * s, fullArrivals);
             mbarInit(base + kOffEmpty + 8u * s, 1);
         }
         for (int i = 0; i < 2; ++i) {
@@ -553,6 +673,10 @@ __device__ __forceinline__ void setupCommon(const ConvArgs& a, uint32_t base, ui
         }
         for (int i = 0; i < 3; ++i) mbarInit(base + kOffSkip + 8u * i, 1);
         mbarInit(base + kOffW, 1);
+        for (int i = 0; i < kRgbBufs; ++i) {
+            mbarInit(base + kOffRgbFull + 8u * i, 1);
+            mbarInit(base + kOffRgbEmpty + 8u * i, kFuseWarps);  // the producer warps of the fused first layer
+        }
         mbarInitFence();
         tmaPrefetchDesc(&a.tmA);
         tmaPrefetchDesc(&a.tmB);
@@ -650,14 +774,14 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
 // ======================================================================================================================
 // 3x3 convolution from one input patch per tile, weights resident in shared memory
 // ======================================================================================================================
-template <int kEpi, int kKC>
-__global__ void __launch_bounds__(kThreads, 1) conv3x3_patch_kernel(const __grid_constant__ ConvArgs a) {
+template <int kEpi, int kKC, bool kFused = false>
+__global__ void __launch_bounds__(kFused ? kThreads + 32 * kFuseWarps : kThreads, 1) conv3x3_patch_kernel(const __grid_constant__ ConvArgs a) {
     extern __shared__ uint8_t smemRaw[];
     const uint32_t rawAddr = smemU32(smemRaw);
     const uint32_t base = (rawAddr + 1023u) & ~1023u;
     uint8_t* sm = smemRaw + (base - rawAddr);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    setupCommon(a, base, sm, warp, kEpi == EPI_K_TMA_GROUPS ? kEpiWarps / 2 : kEpiWarps);
+    setupCommon(a, base, sm, warp, kEpi == EPI_K_TMA_GROUPS ? kEpiWarps / 2 : kEpiWarps, kFused ? kFuseWarps : 1);
     const uint32_t tmemBase = *reinterpret_cast<volatile uint32_t*>(sm + kOffSlot);
     const uint32_t wBase = base + a.headerBytes + a.stagingBytes;
     const uint32_t stage0 = wBase + a.wBytes;
@@ -680,7 +804,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_patch_kernel(const __grid
     }
     pdlWait();  // the input activation (and the output buffer's previous readers) belong to earlier kernels
 
-    if (warp == 0) {
+    if (kFused && warp >= kThreads / 32) {
+        fusedFirstProducer(a, base, stage0, nMine, first, step);
+    } else if (warp == 0 && kFused) {
+        if (lane == 0) {
+            // RGB patch loader: 20 rows x 12 pixels x 4 channels per tile, kRgbBufs tiles ahead of the producer warps
+            const uint32_t rgb0 = base + a.fuseOff;
+            TileWalker w;
+            w.init(first, step, 1, a.tilesX, a.tilesY);
+            for (int k = 0; k < nMine; ++k, w.next()) {
+                const TileCoord tc = w.coord(a.bh, a.bw, a.bn, 0);
+                const int rb = k % kRgbBufs;
+                mbarWait(base + kOffRgbEmpty + 8u * rb, ((uint32_t)(k / kRgbBufs) & 1u) ^ 1u);
+                mbarExpectTx(base + kOffRgbFull + 8u * rb, (uint32_t)((kPatchW + 2) * (kPatchH + 2) * 8));
+                tmaLoad3d(rgb0 + (uint32_t)rb * 2048u, &a.tmRgb, base + kOffRgbFull + 8u * rb, tc.x0 * 4, tc.y0, tc.img);
+            }
+        }
+    } else if (warp == 0) {
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
@@ -1116,6 +1256,7 @@ IgemmPlan* igemmCreatePlan(const ConvParams& p) {
             checkCuda(cudaFuncSetAttribute(igemm_kernel<EPI_K_TMA_GROUPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
             checkCuda(cudaFuncSetAttribute(conv3x3_patch_kernel<EPI_K_TMA_GROUPS, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
             checkCuda(cudaFuncSetAttribute(conv3x3_patch_kernel<EPI_K_TMA_GROUPS, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+            checkCuda(cudaFuncSetAttribute(conv3x3_patch_kernel<EPI_K_TMA_GROUPS, 32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
             checkCuda(cudaFuncSetAttribute(igemm_kernel<EPI_K_TMA_SKIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
             checkCuda(cudaFuncSetAttribute(igemm_kernel<EPI_K_STAGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
             checkCuda(cudaFuncSetAttribute(conv3x3_patch_kernel<EPI_K_DIRECT, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
@@ -1128,6 +1269,51 @@ IgemmPlan* igemmCreatePlan(const ConvParams& p) {
         delete plan;
         throw;
     }
+    return plan;
+}
+
+// conv1.conv.2 of a UNet with its RGB first layer computed inside the kernel (fusedFirstProducer).  `first` is the 4 -> 32 layer
+// whose output tensor `second` would have read; that tensor is never written.
+bool igemmFusedFirstSupported(const ConvParams& second, const ConvParams& first) {
+    return first.is3x3 && first.cin == 4 && first.ktot == 36 && first.npad == 32 && first.mode == EPI_STORE && first.act == ACT_LRELU && !first.skip &&
+           first.w_img_stride == 0 && first.sx == 4 && second.is3x3 && second.cin == 32 && second.in == first.out && second.dimx == first.gx &&
+           second.dimy == first.gy && second.npad == 64 && second.mode == EPI_STORE && tmaEpilogueOk(second) && !second.se_sum && wantsPatchKernel(second);
+}
+
+IgemmPlan* igemmCreatePlanFusedFirst(const ConvParams& second, const ConvParams& first) {
+    if (!igemmFusedFirstSupported(second, first)) throw Error("igemm: layer pair cannot be fused");
+    IgemmPlan* plan = igemmCreatePlan(second);
+    ConvArgs& a = plan->args;
+    if (!plan->patch || a.kc != 32 || !a.useTma || a.nbuf != 2 || plan->smem + 8192 > kSmemLimit) {
+        igemmDestroyPlan(plan);
+        throw Error("igemm: fused first layer does not fit this plan");
+    }
+    a.fused = 1;
+    a.fuseIn = first.in;
+    a.fuseW = first.w;
+    a.fuseBias = first.bias;
+    a.fuseSlope = first.slope;
+    a.fuseW_px = first.dimx;
+    a.fuseH_px = first.dimy;
+    a.fuseSn = first.sn;
+    a.fuseOff = a.headerBytes + a.stagingBytes + a.wBytes + (uint32_t)a.stages * a.stageStride;
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)first.dimx * 4, (cuuint64_t)first.dimy, (cuuint64_t)first.gn};
+        cuuint64_t strides[2] = {(cuuint64_t)first.dimx * 8, (cuuint64_t)first.sn * 2};
+        cuuint32_t box[3] = {(cuuint32_t)(kPatchW + 2) * 4, (cuuint32_t)(kPatchH + 2), 1};
+        cuuint32_t es[3] = {1, 1, 1};
+        if (first.sy != (long long)first.dimx * 4 || (first.dimx & 1) || (reinterpret_cast<uintptr_t>(first.in) & 15)) {
+            igemmDestroyPlan(plan);
+            throw Error("igemm: fused first layer needs a dense, 16-byte aligned NHWC4 input");
+        }
+        const CUresult r = encodeTiled()(&a.tmRgb, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void*)first.in, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            igemmDestroyPlan(plan);
+            throw Error("cuTensorMapEncodeTiled(rgb) failed with code " + std::to_string((int)r));
+        }
+    }
+    plan->smem += 8192;  // four RGB patch buffers
     return plan;
 }
 
@@ -1149,7 +1335,7 @@ bool igemmSeFusable(const IgemmPlan* plan) {
 
 const char* igemmDescribe(const IgemmPlan* plan, char* buf, int cap) {
     const ConvArgs& a = plan->args;
-    std::snprintf(buf, cap, "%s bn=%d kc=%d tile=%dx%d stages=%d nbuf=%d tma=%d skip=%d staged=%d split=%d grid=%d smem=%zu", plan->patch ? "patch3x3" : "igemm",
+    std::snprintf(buf, cap, "%s bn=%d kc=%d tile=%dx%d stages=%d nbuf=%d tma=%d skip=%d staged=%d split=%d grid=%d smem=%zu", a.fused ? "patch3x3+rgb-first-layer" : plan->patch ? "patch3x3" : "igemm",
                   a.bn, a.kc, a.bh, a.bw, a.stages, a.nbuf, a.useTma, a.hasSkip, a.staged, a.nSplit, plan->grid, plan->smem);
     return buf;
 }
@@ -1183,7 +1369,9 @@ void igemmLaunch(const IgemmPlan* plan, cudaStream_t s, __half* outOverride, int
             else if (a->useTma) launchPdl(conv3x3_patch_kernel<EPI_K_TMA, 64>, dim3(plan->grid), dim3(kThreads), plan->smem, s, *a);
             else launchPdl(conv3x3_patch_kernel<EPI_K_DIRECT, 64>, dim3(plan->grid), dim3(kThreads), plan->smem, s, *a);
         } else {
-            if (grouped) launchPdl(conv3x3_patch_kernel<EPI_K_TMA_GROUPS, 32>, dim3(plan->grid), dim3(kThreads), plan->smem, s, *a);
+            if (grouped && a->fused) launchPdl(conv3x3_patch_kernel<EPI_K_TMA_GROUPS, 32, true>, dim3(plan->grid), dim3(kThreads + 32 * kFuseWarps), plan->smem, s, *a);
+            else if (a->fused) throw Error("fused first layer needs the two-group TMA epilogue");
+            else if (grouped) launchPdl(conv3x3_patch_kernel<EPI_K_TMA_GROUPS, 32>, dim3(plan->grid), dim3(kThreads), plan->smem, s, *a);
             else if (a->useTma) launchPdl(conv3x3_patch_kernel<EPI_K_TMA, 32>, dim3(plan->grid), dim3(kThreads), plan->smem, s, *a);
             else launchPdl(conv3x3_patch_kernel<EPI_K_DIRECT, 32>, dim3(plan->grid), dim3(kThreads), plan->smem, s, *a);
         }

@@ -181,6 +181,8 @@ void encodeActivationMap5d(void* tensorMap, const ConvParams& p, int boxX, int b
 struct IgemmPlan;                                                 // opaque: tensor maps + launch geometry
 IgemmPlan* igemmCreatePlan(const ConvParams& p);                  // throws w2x::Error when unsupported
 void igemmDestroyPlan(IgemmPlan* plan);
+bool igemmFusedFirstSupported(const ConvParams& second, const ConvParams& first);  // conv(4->32)+lrelu computed inside conv(32->64)
+IgemmPlan* igemmCreatePlanFusedFirst(const ConvParams& second, const ConvParams& first);
 void igemmLaunch(const IgemmPlan* plan, cudaStream_t s, __half* outOverride = nullptr, int nImages = 0);
 bool igemmSupported(const ConvParams& p);
 const char* igemmDescribe(const IgemmPlan* plan, char* buf, int cap);
