@@ -171,6 +171,9 @@ W2X_API int w2x_probe_umma(int device, int mode, int pitch, float* err9);
 /* Development probe: milliseconds for `iters` x 4 back-to-back tcgen05.mma (M=128, N=n, K=16, fp16) issued on every SM
  * from the same smem operands (A descriptor SBO = sbo_a bytes); cycles per MMA = ms * clock / (4 * iters). */
 W2X_API float w2x_probe_mma_rate(int device, int n, int iters, int sbo_a);
+/* Development probe: milliseconds for `iters` x `chains` (1..8 independent accumulators) mma.sync.m16n8k16 per warp with
+ * `warps` warps per SM on every SM, operands in registers: issue rate of the legacy tensor path (first layer, image head, attention). */
+W2X_API float w2x_probe_hmma_rate(int device, int warps, int chains, int iters);
 
 /* Host-only helpers (no GPU needed). */
 /* getConfigHash (img2img_build.cpp:8-27) on an explicit device name: writes 64 hex chars + NUL. */

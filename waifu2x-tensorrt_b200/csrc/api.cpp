@@ -252,6 +252,11 @@ float w2x_probe_mma_rate(int device, int n, int iters, int sbo_a) {
     try { return probeMmaRate(n, iters, sbo_a); } catch (...) { return -3.f; }
 }
 
+float w2x_probe_hmma_rate(int device, int warps, int chains, int iters) {
+    if (cudaSetDevice(device) != cudaSuccess) return -1.f;
+    try { return probeHmmaRate(warps, chains, iters); } catch (...) { return -3.f; }
+}
+
 void w2x_config_hash(const char* device_name, const w2x_build_config* cfg, char out_hex[65]) {
     if (!out_hex) return;
     out_hex[0] = 0;

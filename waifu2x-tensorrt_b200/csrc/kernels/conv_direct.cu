@@ -146,4 +146,46 @@ void launchConvFirst(const ConvParams& p, cudaStream_t s) {
     else launchPdl(conv_first_kernel<4>, dim3(grid), dim3(256), 0, s, p, segsX, chunksY, total);
 }
 
+// Development probe (w2x_probe_hmma_rate): `iters` rounds of `chains` independent mma.sync.m16n8k16 (fp16 in, fp32 accumulate)
+// per warp, `warps` warps per SM on every SM, operands in registers: the issue rate of the legacy tensor path that the
+// first-layer, image-head and window-attention kernels use.  Returns milliseconds.
+__global__ void hmma_rate_kernel(int iters, int chains, float* sink) {
+    float d[8][4];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) d[c][0] = d[c][1] = d[c][2] = d[c][3] = 0.f;
+    const uint32_t a0 = 0x3c003c00u + threadIdx.x, a1 = 0x38003800u, a2 = 0x34003400u, a3 = 0x3c003800u, b0 = 0x38003c00u, b1 = 0x34003800u;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+            if (c < chains)
+                asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                             : "+f"(d[c][0]), "+f"(d[c][1]), "+f"(d[c][2]), "+f"(d[c][3])
+                             : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) s += d[c][0] + d[c][1] + d[c][2] + d[c][3];
+    if (s == 12345.678f) sink[0] = s;  // keeps the accumulators live
+}
+
+float probeHmmaRate(int warps, int chains, int iters) {
+    if (warps < 1 || warps > 32 || chains < 1 || chains > 8 || iters < 1) return -1.f;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    float* sink = nullptr;
+    if (cudaMalloc(&sink, 4) != cudaSuccess) return -2.f;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    hmma_rate_kernel<<<sms, warps * 32>>>(16, chains, sink);  // warm-up
+    cudaEventRecord(e0);
+    hmma_rate_kernel<<<sms, warps * 32>>>(iters, chains, sink);
+    cudaEventRecord(e1);
+    float ms = -3.f;
+    if (cudaEventSynchronize(e1) == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(sink);
+    return ms;
+}
+
 }  // namespace w2x

@@ -4,13 +4,14 @@
 // Why its own kernel: with 3 output channels the layer is bound by how often each input pixel is read, not by math.  A per-tap
 // GEMM (the generic kernels) streams every pixel through the tensor-core operand path nine times (one shifted view per tap).
 // Here the nine taps sit in the N dimension instead: one pass computes, for every pixel of a 10 x 18 input patch, the 27 partial
-// products P[tap*3 + co][pixel] = sum_c w[co][tap][c] * x[pixel][c] (M = pixels, N = 27 -> 32, K = 64: sixteen m16n8k16 MMAs per
-// 16 pixels), parks them in shared memory and each output pixel then adds its nine shifted partials in fp32.  Every input byte
+// products P[tap*3 + co][pixel] = sum_c w[co][tap][c] * x[pixel][c] (M = 128 pixels, N = 27 -> 32, K = 64: four tcgen05.mma per
+// 128 pixels, fp32 accumulators in TMEM), parks them in shared memory and each output pixel then adds its nine shifted partials.  Every input byte
 // is read from HBM/L2 once and from shared memory once; algorithmic traffic = 128 B/pixel in + 8 B/pixel out (+ 8 B skip).
 //
 // One persistent CTA per SM (256 threads) walks 16 x 16 output tiles with a four-stage TMA ring of 18 x 18 input patches
-// (128B-swizzled, three patch loads = 124 KB in flight per SM, out-of-image pixels zero-filled by TMA); mma.sync is the right tool
-// for the math: N = 32 would use a quarter of a tcgen05 instruction's width and the MMA time is < 10 % of the memory time.
+// (128B-swizzled, three patch loads = 124 KB in flight per SM, out-of-image pixels zero-filled by TMA).  The patch is the A operand
+// as TMA wrote it; the first version used mma.sync (336 HMMA per tile) and was bound by the legacy tensor path's issue rate
+// (profiles/r01_hmma_issue_rate.txt: 5-9 SM cycles per HMMA at 8-16 warps), twelve N = 32 UMMAs per tile replace them.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -35,16 +36,9 @@ constexpr int kStages = 4;
 constexpr int kHeadThreads = 256;
 constexpr int kPatchTx = kPatchPx * 128;                 // bytes one TMA patch load delivers
 constexpr int kPtBytes = kCols * kPitch * 4;             // 38448
-constexpr int kHeadSmem = 1024 + kStages * kPatchBytes + kPtBytes + 64;  // alignment slack + ring + P^T + mbarriers
-
-__device__ __forceinline__ void ldmatrixX4(uint32_t addr, uint32_t (&r)[4]) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
-}
-__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
+constexpr int kWBytes = 32 * 128;                        // taps-in-N weight matrix [32 n][64 k] fp16, K-major, 128B-swizzled
+constexpr int kMBlocks = (kPatchPx + 127) / 128;         // 3 UMMA row blocks of 128 patch pixels (rows 324.. are never gathered)
+constexpr int kHeadSmem = 1024 + kStages * kPatchBytes + kWBytes + kPtBytes + 128;  // alignment slack + ring + W + P^T + mbarriers
 
 struct HeadTile {
     int img, y0, x0;
@@ -62,9 +56,12 @@ __global__ void __launch_bounds__(kHeadThreads, 1) conv_head_kernel(const ConvPa
     const uint32_t rawAddr = smemU32(smemRaw);
     const uint32_t patch0 = (rawAddr + 1023u) & ~1023u;  // 128B-swizzle atoms need a 1024-byte aligned ring
     uint8_t* sm = smemRaw + (patch0 - rawAddr);
-    float* pt = reinterpret_cast<float*>(sm + kStages * kPatchBytes);
-    const uint32_t bar0 = patch0 + kStages * kPatchBytes + kPtBytes;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    const uint32_t wsm = patch0 + kStages * kPatchBytes;  // 1024-aligned: kPatchBytes is a multiple of 1024
+    float* pt = reinterpret_cast<float*>(sm + kStages * kPatchBytes + kWBytes);
+    const uint32_t bar0 = wsm + kWBytes + kPtBytes;       // kStages patch barriers, then the MMA barrier, then the TMEM slot
+    const uint32_t barMma = bar0 + 8u * kStages;
+    volatile uint32_t* tmemSlot = reinterpret_cast<volatile uint32_t*>(sm + kStages * kPatchBytes + kWBytes + kPtBytes + 8 * kStages + 8);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile0 = blockIdx.x, stride = gridDim.x;
 
     auto loadPatch = [&](int tile, int slot) {  // thread 0 only
@@ -76,38 +73,43 @@ __global__ void __launch_bounds__(kHeadThreads, 1) conv_head_kernel(const ConvPa
     pdlLaunchDependents();
     if (tid == 0) {
         for (int st = 0; st < kStages; ++st) mbarInit(bar0 + 8u * st, 1);
+        mbarInit(barMma, 1);
         mbarInitFence();
         tmaPrefetchDesc(&tmIn);
     }
-
-    // B fragments (constants, loaded before the dependency wait): column n = tap*3 + co of the taps-in-N weight matrix, zero for n >= 27
-    uint32_t bf[4][4][2];
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
-        const int n = 8 * nt + g;
-        const int tap = n / 3, co = n - 3 * tap;
-        const __half* wrow = p.w + (long long)co * p.ktot + tap * 64 + 2 * t;
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-            bf[nt][ks][0] = n < kCols ? *reinterpret_cast<const uint32_t*>(wrow + 16 * ks) : 0u;
-            bf[nt][ks][1] = n < kCols ? *reinterpret_cast<const uint32_t*>(wrow + 16 * ks + 8) : 0u;
-        }
+    if (warp == 0) tmemAlloc(smemU32((const void*)tmemSlot), 128);  // 3 row blocks x 32 fp32 columns
+    // B operand (constants): row n = tap*3 + co of the taps-in-N weight matrix, 64 input channels along K, zero rows for n >= 27;
+    // K-major SWIZZLE_128B layout: row n is 128 bytes, 16-byte chunk c of the row sits at chunk c ^ (n & 7)
+    for (int i = tid; i < 32 * 8; i += kHeadThreads) {
+        const int n = i >> 3, c = i & 7;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (n < kCols) v = *reinterpret_cast<const uint4*>(p.w + (long long)(n % 3) * p.ktot + (n / 3) * 64 + c * 8);
+        stsV4(wsm + (uint32_t)n * 128u + ((uint32_t)(c ^ (n & 7)) << 4), v);
     }
+    fenceProxyAsync();  // generic-proxy stores -> visible to the tensor core's operand reads
     const float bias0 = __ldg(p.bias + 0), bias1 = __ldg(p.bias + 1), bias2 = __ldg(p.bias + 2);
     const int oy = tid >> 4, ox = tid & 15;
     int gatherOff[9];
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap) gatherOff[tap] = 3 * tap * kPitch + (oy + p.tap[tap].dy) * kPatchX + ox + p.tap[tap].dx;
+    tcFenceBefore();
+    __syncthreads();  // barriers, TMEM slot and the weight tile are visible to every thread
+    tcFenceAfter();
+    const uint32_t tmemBase = *tmemSlot;
+    const uint32_t idesc = instrDescF16(128, 32);
+    const uint32_t hi = descHi(1024, 2);  // 8-row groups 1024 bytes apart, 128-byte swizzle
+    // this thread's part of the accumulator: TMEM lanes of its warp's quarter, 16 of the 32 columns
+    const int quarter = warp & 3, colHalf = warp >> 2;
+    const uint32_t tRow = tmemBase + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(colHalf * 16);
 
     pdlWait();  // everything above touches constants only; the input and residual tensors come from preceding kernels
     if (tid == 0)
         for (int st = 0; st < kStages - 1; ++st) loadPatch(tile0 + st * stride, st);
-    __syncthreads();  // barrier init visible to all threads
 
     int stage = 0;
-    uint32_t phase = 0;
+    uint32_t phase = 0, mmaPhase = 0;
     for (int tile = tile0; tile < numTiles; tile += stride) {
-        // refill the slot freed by the previous tile (its MMAs finished before that iteration's second barrier)
+        // refill the slot freed by the previous tile (its MMAs completed before that iteration's accumulator read-out)
         if (tid == 0) loadPatch(tile + (kStages - 1) * stride, (stage + kStages - 1) % kStages);
         // this tile's residual pixel (z1 crop): issued now, consumed after the MMAs
         const HeadTile ht = headTile(tile, tilesX, tilesY);
@@ -115,31 +117,42 @@ __global__ void __launch_bounds__(kHeadThreads, 1) conv_head_kernel(const ConvPa
         const bool valid = y < p.gy && x < p.gx;
         Half4 sv{};
         if (valid) sv = *reinterpret_cast<const Half4*>(p.skip + (((long long)ht.img * p.skip_h + y + p.skip_off) * p.skip_w + x + p.skip_off) * p.skip_c);
-        mbarWait(bar0 + 8u * stage, phase);  // patch complete
-        __syncthreads();                     // every thread has finished gathering the previous tile from P^T
-
-        // partial products: 16-pixel blocks round-robin over the warps; P^T[n][pixel] <- C fragments
-        const uint32_t patch = patch0 + (uint32_t)stage * kPatchBytes;
-        for (int b = warp; b < kBlocks; b += kHeadThreads / 32) {
-            float d[4][4] = {};
-            const int row = b * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
-            const uint32_t rowAddr = patch + (uint32_t)row * 128u;
+        if (warp == 0) {
+            mbarWait(bar0 + 8u * stage, phase);  // patch complete
+            tcFenceAfter();
+            if (electOne()) {
+                // P[pixel][tap*3 + co] for 3 x 128 patch pixels: four K = 16 steps over the 64 channels each
+                const uint32_t patch = patch0 + (uint32_t)stage * kPatchBytes;
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-                uint32_t a[4];
-                ldmatrixX4(rowAddr + ((uint32_t)((2 * ks + (lane >> 4)) ^ (row & 7)) << 4), a);
+                for (int mb = 0; mb < kMBlocks; ++mb)
 #pragma unroll
-                for (int nt = 0; nt < 4; ++nt) mma16816(d[nt], a, bf[nt][ks][0], bf[nt][ks][1]);
+                    for (int ks = 0; ks < 4; ++ks)
+                        umma(tmemBase + (uint32_t)(mb * 32), makeDesc(patch + (uint32_t)mb * 16384u + (uint32_t)ks * 32u, hi), makeDesc(wsm + (uint32_t)ks * 32u, hi), idesc,
+                             ks != 0 ? 1u : 0u);
+                tcCommit(barMma);
             }
-            float* dst = pt + b * 16 + g;
+            __syncwarp();
+        }
+        mbarWait(barMma, mmaPhase);
+        tcFenceAfter();
+        __syncthreads();  // every thread has finished gathering the previous tile from P^T
+        // accumulators -> P^T[n][pixel] (fp32): lanes are consecutive pixels, so the stores are conflict-free
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt) {
-                const int n = 8 * nt + 2 * t;
-                if (n < kCols) { dst[n * kPitch] = d[nt][0]; dst[n * kPitch + 8] = d[nt][2]; }
-                if (n + 1 < kCols) { dst[(n + 1) * kPitch] = d[nt][1]; dst[(n + 1) * kPitch + 8] = d[nt][3]; }
+        for (int mb = 0; mb < kMBlocks; ++mb) {
+            uint32_t r[32];
+            tmemLd16(tRow + (uint32_t)(mb * 32), r);
+            tmemLdWait();
+            const int px = mb * 128 + quarter * 32 + lane;
+            if (px < kBlocks * 16) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int n = colHalf * 16 + j;
+                    if (n < kCols) pt[n * kPitch + px] = __uint_as_float(r[j]);
+                }
             }
         }
-        __syncthreads();  // P^T complete; this patch slot may be refilled by the load issued in the next iteration
+        tcFenceBefore();
+        __syncthreads();  // P^T complete; the accumulator and this patch slot may be overwritten
 
         // one output pixel per thread: nine shifted partials per channel + bias + cropped residual, clamp, 8-byte store
         float acc0 = bias0, acc1 = bias1, acc2 = bias2;
@@ -157,6 +170,13 @@ __global__ void __launch_bounds__(kHeadThreads, 1) conv_head_kernel(const ConvPa
             *reinterpret_cast<Half4*>(p.out + (((long long)ht.img * p.out_h + y) * p.out_w + x) * p.out_c) = h;
         }
         if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        mmaPhase ^= 1u;
+    }
+    tcFenceBefore();
+    __syncthreads();
+    if (warp == 0) {
+        tcFenceAfter();
+        tmemDealloc(tmemBase, 128);
     }
 }
 

@@ -189,6 +189,7 @@ const char* igemmDescribe(const IgemmPlan* plan, char* buf, int cap);
 bool igemmSeFusable(const IgemmPlan* plan);  // can this layer's epilogue produce ConvParams::se_sum?
 int probeUmma(int mode, int pitch, float* err9);
 float probeMmaRate(int n, int iters, int sboA);
+float probeHmmaRate(int warps, int chains, int iters);  // legacy mma.sync issue rate (conv_direct.cu)
 
 // SwinUNet token kernels (kernels/swin.cu)
 void launchLayerNorm(const __half* x, __half* y, long long tokens, int c, const float* gamma, const float* beta, float eps, cudaStream_t s);
