@@ -257,6 +257,21 @@ float w2x_probe_hmma_rate(int device, int warps, int chains, int iters) {
     try { return probeHmmaRate(warps, chains, iters); } catch (...) { return -3.f; }
 }
 
+int w2x_probe_mma_rate_stream(int device, int n, int iters, int stream_bytes, float* res) {
+    if (!res || cudaSetDevice(device) != cudaSuccess) return -1;
+    try { return probeMmaRateStream(n, iters, stream_bytes, res); } catch (...) { return -3; }
+}
+
+float w2x_probe_mma_tiles(int device, int tiles, int mode) {
+    if (cudaSetDevice(device) != cudaSuccess) return -1.f;
+    try { return probeMmaTiles(tiles, mode); } catch (...) { return -3.f; }
+}
+
+float w2x_probe_l2_stream(int device, int bytes, int iters) {
+    if (cudaSetDevice(device) != cudaSuccess) return -1.f;
+    try { return probeL2Stream(bytes, iters); } catch (...) { return -3.f; }
+}
+
 void w2x_config_hash(const char* device_name, const w2x_build_config* cfg, char out_hex[65]) {
     if (!out_hex) return;
     out_hex[0] = 0;

@@ -188,4 +188,56 @@ float probeHmmaRate(int warps, int chains, int iters) {
     return ms;
 }
 
+// Development probe (w2x_probe_l2_stream): every SM streams the SAME `bytes`-sized global buffer (L2-resident after the first
+// touch) into a four-slot shared-memory ring with cp.async.bulk, `iters` copies per SM, nothing else running: the L2 -> SM
+// ingest rate available to a kernel that streams its weights instead of keeping them resident.  Returns milliseconds.
+__global__ void l2_stream_kernel(const uint8_t* src, int bytes, int iters) {
+    extern __shared__ __align__(128) uint8_t ring[];
+    __shared__ __align__(8) unsigned long long bars[4];
+    if (threadIdx.x != 0) return;
+    const uint32_t base = (uint32_t)__cvta_generic_to_shared(ring);
+    uint32_t bar[4];
+    for (int i = 0; i < 4; ++i) {
+        bar[i] = (uint32_t)__cvta_generic_to_shared(&bars[i]);
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar[i]));
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int k = 0; k < iters + 4; ++k) {
+        const int s = k & 3;
+        if (k >= 4) {  // wait for the copy issued four iterations ago into this slot
+            const uint32_t parity = (uint32_t)((k - 4) >> 2) & 1u;
+            uint32_t done = 0;
+            while (!done)
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar[s]), "r"(parity) : "memory");
+        }
+        if (k < iters) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar[s]), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(base + (uint32_t)s * (uint32_t)bytes),
+                         "l"(src), "r"(bytes), "r"(bar[s]) : "memory");
+        }
+    }
+}
+
+float probeL2Stream(int bytes, int iters) {
+    if (bytes < 1024 || bytes > 49152 || (bytes & 15) || iters < 1) return -1.f;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    uint8_t* src = nullptr;
+    if (cudaMalloc(&src, bytes) != cudaSuccess) return -2.f;
+    cudaMemset(src, 1, bytes);
+    cudaFuncSetAttribute(l2_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 49152);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    l2_stream_kernel<<<sms, 32, 4 * bytes>>>(src, bytes, 8);  // warm-up
+    cudaEventRecord(e0);
+    l2_stream_kernel<<<sms, 32, 4 * bytes>>>(src, bytes, iters);
+    cudaEventRecord(e1);
+    float ms = -3.f;
+    if (cudaEventSynchronize(e1) == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(src);
+    return ms;
+}
+
 }  // namespace w2x

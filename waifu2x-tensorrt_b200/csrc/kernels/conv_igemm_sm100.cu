@@ -51,7 +51,7 @@ struct ConvArgs {
     int stages, cchunks, kblocks;
     uint32_t idesc, tmemCols, bytesA, bytesB, descHiA, descHiB;
     int useTma, nsub, nbuf, hasSkip;
-    int dbg;  // timing experiments only (W2X_DBG): 1 = epilogue skips math + staging, 2 = no output store, 4 = no MMAs
+    int dbg;  // timing experiments only (W2X_DBG): 1 = epilogue skips math + staging, 2 = no output store, 4 = no MMAs, 16 = no activation loads
     uint32_t stageStride, wBytes, stagingBytes;
     int nSplit;
     int staged;                 // EPI_K_STAGED: generic-proxy staging + coalesced copy-out (any N, residual, GELU)
@@ -831,8 +831,12 @@ __global__ void __launch_bounds__(kFused ? kThreads + 32 * kFuseWarps : kThreads
                 for (int cc = 0; cc < a.cchunks; ++cc) {
                     mbarWait(barEmpty + 8u * stage, phase ^ 1u);
                     const uint32_t full = barFull + 8u * stage;
-                    mbarExpectTx(full, a.bytesA);
-                    tmaLoad5d(stage0 + stage * a.stageStride, &a.tmA, full, cc * a.kc, tc.x0, 0, tc.y0, tc.img);
+                    if (a.dbg & 16) {  // timing experiment: no activation traffic at all, the MMAs run on whatever the slot holds
+                        mbarArrive(full);
+                    } else {
+                        mbarExpectTx(full, a.bytesA);
+                        tmaLoad5d(stage0 + stage * a.stageStride, &a.tmA, full, cc * a.kc, tc.x0, 0, tc.y0, tc.img);
+                    }
                     if (++stage == a.stages) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -850,17 +854,27 @@ __global__ void __launch_bounds__(kFused ? kThreads + 32 * kFuseWarps : kThreads
                 mbarWait(barFull + 8u * stage, phase);
                 tcFenceAfter();
                 if (electOne()) {
-                    const uint32_t aLo = descLo(stage0 + stage * a.stageStride);
-                    uint32_t bLo = descLo(wBase + (uint32_t)cc * tapBytes);
+                    // Nine taps = shifted views of the patch: whole pixel rows (kRowBytes each) into the swizzled tile.  The ky loop stays
+                    // rolled on purpose: fully unrolled, the 36 precomputed descriptor pairs do not fit the uniform register file and the
+                    // issue thread spends ~25 spill/fill instructions per MMA (measured with w2x_probe_mma_tiles: 58.6 vs 48 cycles per MMA).
+                    constexpr uint32_t kRowBytes = kKC * 2;
+                    uint32_t aRow = descLo(stage0 + stage * a.stageStride);
+                    uint32_t b0 = descLo(wBase + (uint32_t)cc * tapBytes);
+                    uint32_t accum = cc != 0 ? 1u : 0u;
+                    const uint32_t descHiA = a.descHiA, descHiB = a.descHiB, idesc = a.idesc;
+                    if (!(a.dbg & 4)) {
+#pragma unroll 1
+                        for (int ky = 0; ky < 3; ++ky) {
+                            const uint32_t b1 = b0 + bTapStep, b2 = b1 + bTapStep;
 #pragma unroll
-                    for (int tap = 0; tap < 9; ++tap) {
-                        // shifted view of the patch: whole pixel rows (kRowBytes each) into the swizzled tile
-                        constexpr uint32_t kRowBytes = kKC * 2;
-                        const uint32_t aTap = aLo + (uint32_t)(((tap / 3) * kPatchW + (tap % 3)) * kRowBytes >> 4);
+                            for (int ks = 0; ks < kKC / 16; ++ks) { ummaLoHi(tmemD, aRow + 2u * ks, descHiA, b0 + 2u * ks, descHiB, idesc, accum); accum = 1u; }
 #pragma unroll
-                        for (int ks = 0; ks < kKC / 16; ++ks)
-                            if (!(a.dbg & 4)) ummaLoHi(tmemD, aTap + 2u * ks, a.descHiA, bLo + 2u * ks, a.descHiB, a.idesc, (cc | tap | ks) != 0 ? 1u : 0u);
-                        bLo += bTapStep;
+                            for (int ks = 0; ks < kKC / 16; ++ks) ummaLoHi(tmemD, aRow + (kRowBytes >> 4) + 2u * ks, descHiA, b1 + 2u * ks, descHiB, idesc, 1u);
+#pragma unroll
+                            for (int ks = 0; ks < kKC / 16; ++ks) ummaLoHi(tmemD, aRow + 2u * (kRowBytes >> 4) + 2u * ks, descHiA, b2 + 2u * ks, descHiB, idesc, 1u);
+                            aRow += (uint32_t)(kPatchW * kRowBytes) >> 4;
+                            b0 = b2 + bTapStep;
+                        }
                     }
                     tcCommit(barEmpty + 8u * stage);
                 }
@@ -961,17 +975,26 @@ __global__ void __launch_bounds__(128, 1) umma_probe_kernel(const __grid_constan
 // UMMA issue-rate probe (development aid, w2x_probe_mma_rate): every SM issues `iters` x 4 back-to-back
 // tcgen05.mma (M = 128, N = n, K = 16) on the same smem operands; cycles per MMA = time * clock / (4 * iters).
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128, 1) umma_rate_kernel(int n, int iters, int sboA) {
+// With streamBytes > 0 a third warp concurrently streams an L2-resident buffer into a separate shared-memory ring with
+// cp.async.bulk (four copies of streamBytes in flight) for as long as the MMAs run: measures how much the tensor core's operand
+// reads and asynchronous shared-memory writes slow each other down.  out[2*cta] = MMA cycles, out[2*cta+1] = bytes streamed.
+__global__ void __launch_bounds__(128, 1) umma_rate_kernel(int n, int iters, int sboA, const uint8_t* streamSrc, int streamBytes, long long* out) {
     extern __shared__ uint8_t smemRaw[];
     const uint32_t rawAddr = smemU32(smemRaw);
     const uint32_t base = (rawAddr + 1023u) & ~1023u;
     uint8_t* sm = smemRaw + (base - rawAddr);
     const uint32_t bar = base;
     volatile uint32_t* tmemSlot = reinterpret_cast<volatile uint32_t*>(sm + 32);
-    const uint32_t sA = base + 1024, sB = sA + 32768;
+    volatile uint32_t* doneFlag = reinterpret_cast<volatile uint32_t*>(sm + 40);
+    const uint32_t sA = base + 1024, sB = sA + 32768, sRing = sB + 32768;
     for (uint32_t i = threadIdx.x; i < (32768u + 32768u) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(sm + 1024)[i] = 0u;
     const int warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) { mbarInit(bar, 1); mbarInitFence(); }
+    if (threadIdx.x == 0) {
+        mbarInit(bar, 1);
+        for (int i = 0; i < 4; ++i) mbarInit(base + 64 + 8u * i, 1);
+        mbarInitFence();
+        *doneFlag = 0;
+    }
     if (warp == 0) tmemAlloc(smemU32((const void*)tmemSlot), 256);
     fenceProxyAsync();
     tcFenceBefore();
@@ -979,10 +1002,12 @@ __global__ void __launch_bounds__(128, 1) umma_rate_kernel(int n, int iters, int
     tcFenceAfter();
     const uint32_t tmemBase = *tmemSlot;
     if (warp == 1) {
+        const long long t0 = clock64();
         if (electOne()) {
             const uint32_t idesc = instrDescF16(128, n);
             const uint32_t hiA = descHi((uint32_t)sboA, 2), hiB = descHi(1024, 2);
-            const uint32_t aLo = descLo(sA), bLo = descLo(sB);
+            // streamBytes < 0: no stream, A operand starts -streamBytes - 1 rows (128 B each) into the tile, like a shifted 3x3 tap view
+            const uint32_t aLo = descLo(sA + (streamBytes < 0 ? (uint32_t)(-streamBytes - 1) * 128u : 0u)), bLo = descLo(sB);
             for (int it = 0; it < iters; ++it) {
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) ummaLoHi(tmemBase, aLo + 2u * ks, hiA, bLo + 2u * ks, hiB, idesc, 1u);
@@ -990,11 +1015,132 @@ __global__ void __launch_bounds__(128, 1) umma_rate_kernel(int n, int iters, int
             tcCommit(bar);
         }
         __syncwarp();
+        mbarWait(bar, 0);
+        if (threadIdx.x == 32) {
+            if (out) out[2 * blockIdx.x] = clock64() - t0;
+            *doneFlag = 1;
+        }
+    } else if (warp == 2 && threadIdx.x == 64 && streamBytes > 0) {
+        long long copied = 0;
+        int k = 0;
+        for (;; ++k) {
+            const int sl = k & 3;
+            const uint32_t b = base + 64 + 8u * sl;
+            if (k >= 4) mbarWait(b, (uint32_t)((k - 4) >> 2) & 1u);
+            if (*doneFlag) break;
+            mbarExpectTx(b, (uint32_t)streamBytes);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sRing + (uint32_t)sl * (uint32_t)streamBytes),
+                         "l"(streamSrc), "r"(streamBytes), "r"(b) : "memory");
+            copied += streamBytes;
+        }
+        // drain the copies still in flight before the CTA (and its shared memory) goes away
+        for (int j = 1; j <= 3 && k - j >= 0; ++j) {
+            const int kk = k - j;
+            if (kk + 4 > k - 0 && kk >= 0) mbarWait(base + 64 + 8u * (kk & 3), (uint32_t)(kk >> 2) & 1u);
+        }
+        if (out) out[2 * blockIdx.x + 1] = copied;
     }
     mbarWait(bar, 0);
     tcFenceBefore();
     __syncthreads();
     if (warp == 0) { tcFenceAfter(); tmemDealloc(tmemBase, 256); }
+}
+
+// Tile-loop probe (w2x_probe_mma_tiles): the patch kernel's MMA schedule without any data movement or epilogue -- per "tile" 36
+// UMMAs (nine tap views of one 18x10 patch x four K steps, N = 64) into alternating TMEM accumulators, one commit per tile.
+// mode bit 0: wait for the commit of tile t-2 before issuing tile t (the accumulator hand-back of the real kernel, with a
+// zero-latency epilogue); bit 1: every tap uses the same B tile; bit 2: every tap uses the unshifted A view;
+// bit 3: commit only once at the end; bit 4: always the same accumulator; bit 5: never overwrite (accumulate = 1 throughout).  out[cta] = cycles from first issue to last completion.
+__global__ void __launch_bounds__(128, 1) umma_tile_probe_kernel(int tiles, int mode, long long* out) {
+    extern __shared__ uint8_t smemRaw[];
+    const uint32_t rawAddr = smemU32(smemRaw);
+    const uint32_t base = (rawAddr + 1023u) & ~1023u;
+    uint8_t* sm = smemRaw + (base - rawAddr);
+    volatile uint32_t* tmemSlot = reinterpret_cast<volatile uint32_t*>(sm + 32);
+    const uint32_t sA = base + 1024, sB = sA + 24576;
+    for (uint32_t i = threadIdx.x; i < (24576u + 73728u) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(sm + 1024)[i] = 0u;
+    const int warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        mbarInit(base, 1);
+        mbarInit(base + 8, 1);
+        mbarInit(base + 16, 1);
+        mbarInit(base + 24, 1);
+        mbarInitFence();
+    }
+    if (warp == 0) tmemAlloc(smemU32((const void*)tmemSlot), 128);
+    fenceProxyAsync();
+    tcFenceBefore();
+    __syncthreads();
+    tcFenceAfter();
+    const uint32_t tmemBase = *tmemSlot;
+    if (warp == 1) {
+        const long long t0 = clock64();
+        const uint32_t idesc = instrDescF16(128, 64);
+        const uint32_t hiA = descHi(kPatchW * 128u, 2), hiB = descHi(1024, 2);
+        const uint32_t aLo = descLo(sA), bLo0 = descLo(sB);
+        uint32_t ph[2] = {0, 0};
+        for (int t = 0; t < tiles; ++t) {
+            const int acc = (mode & 16) ? 0 : (t & 1);
+            if ((mode & 1) && t >= 2) { mbarWait(base + 8u * acc, ph[acc]); ph[acc] ^= 1u; tcFenceAfter(); }
+            if (electOne()) {
+                const uint32_t tmemD = tmemBase + (uint32_t)(acc * 64);
+                uint32_t bLo = bLo0;
+                if (mode & 128) {
+                    // the patch kernel's issue loop: ky rolled, kx and ks unrolled (12 MMAs per iteration)
+                    uint32_t aRow = aLo, b0 = bLo0, accum = 0u;
+                    const uint32_t step = 8192u >> 4;
+#pragma unroll 1
+                    for (int ky = 0; ky < 3; ++ky) {
+                        const uint32_t b1 = b0 + step, b2 = b1 + step;
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) { ummaLoHi(tmemD, aRow + 2u * ks, hiA, b0 + 2u * ks, hiB, idesc, accum); accum = 1u; }
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) ummaLoHi(tmemD, aRow + 8u + 2u * ks, hiA, b1 + 2u * ks, hiB, idesc, 1u);
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) ummaLoHi(tmemD, aRow + 16u + 2u * ks, hiA, b2 + 2u * ks, hiB, idesc, 1u);
+                        aRow += (uint32_t)(kPatchW * 128) >> 4;
+                        b0 = b2 + step;
+                    }
+                } else if (mode & 64) {
+                    // rolled tap loops: a handful of live uniform registers instead of 36 precomputed descriptor pairs
+                    uint32_t aRow = aLo, accum = (mode & 32) ? 1u : 0u;
+#pragma unroll 1
+                    for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll 1
+                        for (int kx = 0; kx < 3; ++kx) {
+                            const uint32_t aTap = (mode & 4) ? aLo : aRow + (uint32_t)kx * (128u >> 4);
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks) {
+                                ummaLoHi(tmemD, aTap + 2u * ks, hiA, bLo + 2u * ks, hiB, idesc, accum);
+                                accum = 1u;
+                            }
+                            if (!(mode & 2)) bLo += 8192u >> 4;
+                        }
+                        aRow += (uint32_t)(kPatchW * 128) >> 4;
+                    }
+                } else {
+#pragma unroll
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const uint32_t aTap = aLo + ((mode & 4) ? 0u : (uint32_t)(((tap / 3) * kPatchW + (tap % 3)) * 128 >> 4));
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) ummaLoHi(tmemD, aTap + 2u * ks, hiA, bLo + 2u * ks, hiB, idesc, ((tap | ks) != 0 || (mode & 32)) ? 1u : 0u);
+                        if (!(mode & 2)) bLo += 8192u >> 4;
+                    }
+                }
+                if (mode & 1) tcCommit(base + 8u * acc);       // accumulator hand-back
+                else if (!(mode & 8)) tcCommit(base + 24);      // a commit per tile that nobody waits for (its cost only)
+            }
+            __syncwarp();
+        }
+        // one more commit on a third barrier: it completes when every MMA issued above has completed
+        if (electOne()) tcCommit(base + 16);
+        __syncwarp();
+        mbarWait(base + 16, 0);
+        if (threadIdx.x == 32 && out) out[blockIdx.x] = clock64() - t0;
+    }
+    tcFenceBefore();
+    __syncthreads();
+    if (warp == 0) { tcFenceAfter(); tmemDealloc(tmemBase, 128); }
 }
 
 // ---- host side -------------------------------------------------------------------------------------------
@@ -1444,14 +1590,60 @@ float probeMmaRate(int n, int iters, int sboA) {
     cudaFuncSetAttribute(umma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
-    umma_rate_kernel<<<numSMs(), 128, 70 * 1024>>>(n, 16, sboA);  // warm-up
+    umma_rate_kernel<<<numSMs(), 128, 70 * 1024>>>(n, 16, sboA, nullptr, 0, nullptr);  // warm-up
     cudaEventRecord(e0);
-    umma_rate_kernel<<<numSMs(), 128, 70 * 1024>>>(n, iters, sboA);
+    umma_rate_kernel<<<numSMs(), 128, 70 * 1024>>>(n, iters, sboA, nullptr, 0, nullptr);
     cudaEventRecord(e1);
     if (cudaEventSynchronize(e1) != cudaSuccess) return -2.f;
     float ms = -1.f;
     cudaEventElapsedTime(&ms, e0, e1);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     return ms;
+}
+
+// cycles per MMA of the tile-loop probe (see umma_tile_probe_kernel); negative on error
+float probeMmaTiles(int tiles, int mode) {
+    if (tiles < 2 || tiles > 100000 || (tiles & 1)) return -1.f;
+    const int sms = numSMs();
+    cudaFuncSetAttribute(umma_tile_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 104 * 1024);
+    long long* out = nullptr;
+    if (cudaMalloc(&out, sizeof(long long) * sms) != cudaSuccess) return -2.f;
+    umma_tile_probe_kernel<<<sms, 128, 102 * 1024>>>(4, mode, nullptr);
+    umma_tile_probe_kernel<<<sms, 128, 102 * 1024>>>(tiles, mode, out);
+    float res = -3.f;
+    if (cudaDeviceSynchronize() == cudaSuccess) {
+        std::vector<long long> h(sms);
+        cudaMemcpy(h.data(), out, sizeof(long long) * sms, cudaMemcpyDeviceToHost);
+        double cyc = 0;
+        for (long long v : h) cyc += (double)v;
+        res = (float)(cyc / sms / (36.0 * tiles));
+    }
+    cudaFree(out);
+    return res;
+}
+
+// UMMA issue rate while a second warp streams `streamBytes`-sized L2-resident copies into shared memory (0 = off).
+// res[0] = average SM cycles per MMA, res[1] = average streamed bytes per SM cycle.  Returns 0 on success.
+int probeMmaRateStream(int n, int iters, int streamBytes, float* res) {
+    if (n < 16 || n > 256 || n % 16 || streamBytes < -64 || streamBytes > 16384 || (streamBytes > 0 && (streamBytes & 15))) return -1;
+    const int sms = numSMs();
+    const size_t smem = 70 * 1024 + 4 * (size_t)(streamBytes > 0 ? streamBytes : 0);
+    cudaFuncSetAttribute(umma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 140 * 1024);
+    uint8_t* src = nullptr;
+    long long* out = nullptr;
+    if (cudaMalloc(&src, 16384) != cudaSuccess || cudaMalloc(&out, sizeof(long long) * 2 * sms) != cudaSuccess) return -2;
+    cudaMemset(src, 0, 16384);
+    cudaMemset(out, 0, sizeof(long long) * 2 * sms);
+    const int sbo = streamBytes < 0 ? 1280 : 1024;  // shifted-view experiment uses the patch kernel's 10-pixel row-group pitch
+    umma_rate_kernel<<<sms, 128, smem>>>(n, 16, sbo, src, streamBytes, nullptr);  // warm-up
+    umma_rate_kernel<<<sms, 128, smem>>>(n, iters, sbo, src, streamBytes, out);
+    int rc = cudaDeviceSynchronize() == cudaSuccess ? 0 : -3;
+    std::vector<long long> h(2 * (size_t)sms);
+    if (rc == 0) cudaMemcpy(h.data(), out, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+    double cyc = 0, by = 0;
+    for (int i = 0; i < sms; ++i) { cyc += (double)h[2 * i]; by += (double)h[2 * i + 1]; }
+    if (rc == 0 && cyc > 0) { res[0] = (float)(cyc / sms / (4.0 * iters)); res[1] = (float)(by / cyc); }
+    cudaFree(src); cudaFree(out);
+    return rc;
 }
 }  // namespace w2x

@@ -189,7 +189,10 @@ const char* igemmDescribe(const IgemmPlan* plan, char* buf, int cap);
 bool igemmSeFusable(const IgemmPlan* plan);  // can this layer's epilogue produce ConvParams::se_sum?
 int probeUmma(int mode, int pitch, float* err9);
 float probeMmaRate(int n, int iters, int sboA);
-float probeHmmaRate(int warps, int chains, int iters);  // legacy mma.sync issue rate (conv_direct.cu)
+float probeMmaTiles(int tiles, int mode);  // the patch kernel's MMA schedule in isolation: cycles per MMA
+int probeMmaRateStream(int n, int iters, int streamBytes, float* res);  // UMMA rate with concurrent async smem writes
+float probeHmmaRate(int warps, int chains, int iters);
+float probeL2Stream(int bytes, int iters);               // L2 -> SM ingest rate of a shared, L2-resident buffer (conv_direct.cu)  // legacy mma.sync issue rate (conv_direct.cu)
 
 // SwinUNet token kernels (kernels/swin.cu)
 void launchLayerNorm(const __half* x, __half* y, long long tokens, int c, const float* gamma, const float* beta, float eps, cudaStream_t s);

@@ -127,6 +127,9 @@ _SIGNATURES = {
     "w2x_probe_umma": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "w2x_probe_mma_rate": (C.c_float, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "w2x_probe_hmma_rate": (C.c_float, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "w2x_probe_mma_tiles": (C.c_float, [C.c_int, C.c_int, C.c_int]),
+    "w2x_probe_mma_rate_stream": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
+    "w2x_probe_l2_stream": (C.c_float, [C.c_int, C.c_int, C.c_int]),
     "w2x_config_hash": (None, [C.c_char_p, C.POINTER(_BuildConfig), C.c_char_p]),
     "w2x_pack_onnx": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, C.c_int]),
     "w2x_pack_info": (C.c_int, [C.c_char_p] + [C.POINTER(C.c_int)] * 4),
