@@ -1056,7 +1056,7 @@ __global__ void __launch_bounds__(128, 1) umma_tile_probe_kernel(int tiles, int 
     const uint32_t rawAddr = smemU32(smemRaw);
     const uint32_t base = (rawAddr + 1023u) & ~1023u;
     uint8_t* sm = smemRaw + (base - rawAddr);
-    volatile uint32_t* tmemSlot = reinterpret_cast<volatile uint32_t*>(sm + 32);
+    volatile uint32_t* tmemSlot = reinterpret_cast<volatile uint32_t*>(sm + 48);
     const uint32_t sA = base + 1024, sB = sA + 24576;
     for (uint32_t i = threadIdx.x; i < (24576u + 73728u) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(sm + 1024)[i] = 0u;
     const int warp = threadIdx.x >> 5;
@@ -1065,6 +1065,7 @@ __global__ void __launch_bounds__(128, 1) umma_tile_probe_kernel(int tiles, int 
         mbarInit(base + 8, 1);
         mbarInit(base + 16, 1);
         mbarInit(base + 24, 1);
+        mbarInit(base + 32, 1);
         mbarInitFence();
     }
     if (warp == 0) tmemAlloc(smemU32((const void*)tmemSlot), 128);
@@ -1073,14 +1074,18 @@ __global__ void __launch_bounds__(128, 1) umma_tile_probe_kernel(int tiles, int 
     __syncthreads();
     tcFenceAfter();
     const uint32_t tmemBase = *tmemSlot;
-    if (warp == 1) {
+    // mode bit 8 (256): two issuing warps, warp 1 takes the even tiles (accumulator 0) and warp 2 the odd ones (accumulator 1)
+    const bool dual = (mode & 256) != 0;
+    if (warp == 1 || (dual && warp == 2)) {
+        const int which = warp - 1;
         const long long t0 = clock64();
         const uint32_t idesc = instrDescF16(128, 64);
         const uint32_t hiA = descHi(kPatchW * 128u, 2), hiB = descHi(1024, 2);
         const uint32_t aLo = descLo(sA), bLo0 = descLo(sB);
         uint32_t ph[2] = {0, 0};
-        for (int t = 0; t < tiles; ++t) {
+        for (int t = dual ? which : 0; t < tiles; t += dual ? 2 : 1) {
             const int acc = (mode & 16) ? 0 : (t & 1);
+            // (dual: each warp owns one accumulator, so the hand-back wait is for its own previous tile)
             if ((mode & 1) && t >= 2) { mbarWait(base + 8u * acc, ph[acc]); ph[acc] ^= 1u; tcFenceAfter(); }
             if (electOne()) {
                 const uint32_t tmemD = tmemBase + (uint32_t)(acc * 64);
@@ -1133,10 +1138,10 @@ __global__ void __launch_bounds__(128, 1) umma_tile_probe_kernel(int tiles, int 
             __syncwarp();
         }
         // one more commit on a third barrier: it completes when every MMA issued above has completed
-        if (electOne()) tcCommit(base + 16);
+        if (electOne()) tcCommit(base + 16 + 16u * which);
         __syncwarp();
-        mbarWait(base + 16, 0);
-        if (threadIdx.x == 32 && out) out[blockIdx.x] = clock64() - t0;
+        mbarWait(base + 16 + 16u * which, 0);
+        if ((threadIdx.x & 31) == 0 && out) out[2 * blockIdx.x + which] = clock64() - t0;
     }
     tcFenceBefore();
     __syncthreads();
@@ -1607,15 +1612,16 @@ float probeMmaTiles(int tiles, int mode) {
     const int sms = numSMs();
     cudaFuncSetAttribute(umma_tile_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 104 * 1024);
     long long* out = nullptr;
-    if (cudaMalloc(&out, sizeof(long long) * sms) != cudaSuccess) return -2.f;
+    if (cudaMalloc(&out, sizeof(long long) * 2 * sms) != cudaSuccess) return -2.f;
+    cudaMemset(out, 0, sizeof(long long) * 2 * sms);
     umma_tile_probe_kernel<<<sms, 128, 102 * 1024>>>(4, mode, nullptr);
     umma_tile_probe_kernel<<<sms, 128, 102 * 1024>>>(tiles, mode, out);
     float res = -3.f;
     if (cudaDeviceSynchronize() == cudaSuccess) {
-        std::vector<long long> h(sms);
-        cudaMemcpy(h.data(), out, sizeof(long long) * sms, cudaMemcpyDeviceToHost);
+        std::vector<long long> h(2 * (size_t)sms);
+        cudaMemcpy(h.data(), out, sizeof(long long) * 2 * sms, cudaMemcpyDeviceToHost);
         double cyc = 0;
-        for (long long v : h) cyc += (double)v;
+        for (int i = 0; i < sms; ++i) cyc += (double)std::max(h[2 * i], h[2 * i + 1]);
         res = (float)(cyc / sms / (36.0 * tiles));
     }
     cudaFree(out);
