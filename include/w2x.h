@@ -160,7 +160,8 @@ W2X_API int w2x_tta_reduce(int device, const uint16_t* outs_f16_nhwc4, int tiles
 W2X_API int w2x_infer(w2x_engine* e, const float* in_nchw, int n, float* out_nchw);
 /* One convolution layer of the implicit-GEMM family on random data, tcgen05 kernel vs the scalar CUDA reference
  * kernel, for on-device self-checks: returns max |diff| (negative on error).  kind: 0 conv3x3, 1 conv2x2s2,
- * 2 convT2x2s2(+skip), 3 convT4x4s2p3->4ch, 4 conv3x3->3ch final(+skip,clamp), 5 = kind 4 through the image-head kernel. */
+ * 2 convT2x2s2(+skip), 3 convT4x4s2p3->4ch, 4 conv3x3->3ch final(+skip,clamp), 5 = kind 4 through the image-head kernel,
+ * 6 = kind 3 through the convT-head kernel. */
 W2X_API double w2x_selftest_conv(int device, int kind, int n, int h, int w, int cin, int cout, unsigned seed);
 
 /* Development probe: which UMMA smem-descriptor base_offset convention lets a 3x3 tap read a SHIFTED view of one

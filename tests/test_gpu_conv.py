@@ -5,7 +5,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 # kind: 0 conv3x3, 1 conv2x2s2, 2 convT2x2s2(+skip), 3 convT4x4s2p3 head, 4 conv3x3 image head (+skip, clamp),
-# 5 the same image head through the dedicated taps-in-N kernel (conv_head.cu)
+# 5 the same image head through the dedicated taps-in-N kernel (conv_head.cu), 6 the convT4x4 head through its taps-in-N kernel
 CASES = [
     (0, 1, 20, 24, 64, 64),     # one M tile with edges (patch kernel)
     (0, 8, 100, 100, 64, 64),   # > 148 tiles: persistent loop, stage ring wrap, double-buffered staging
@@ -23,6 +23,8 @@ CASES = [
     (4, 2, 58, 58, 64, 3),      # image head + z1 crop + clamp
     (5, 2, 58, 58, 64, 3),      # image head kernel: partial tiles on both edges
     (5, 3, 26, 146, 64, 3),     # image head kernel: exact multiples of the 8 x 16 tile, three images
+    (6, 2, 50, 50, 64, 3),      # convT 4x4 head kernel: partial tiles
+    (6, 3, 33, 17, 64, 3),      # convT 4x4 head kernel: exactly 32 x 16 GEMM pixels, three images
 ]
 
 

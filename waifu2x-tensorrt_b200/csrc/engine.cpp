@@ -668,7 +668,7 @@ int Engine::layerKernel(int index, char* buf, int cap) const {
     if (L.plan) igemmDescribe(L.plan, buf, cap);
     else std::snprintf(buf, cap, "%s", L.impl == IMPL_FIRST ? "first-layer mma.sync" : L.impl == IMPL_LAYERNORM ? "layernorm" :
                                        L.impl == IMPL_ATTENTION ? "window-attention mma.sync" :
-                                       L.impl == IMPL_HEAD ? "image head, taps-in-N mma.sync" : L.impl == IMPL_SKIP ? "fused into the next layer" : "direct (reference kernel)");
+                                       L.impl == IMPL_HEAD ? "head kernel, taps in N (tcgen05)" : L.impl == IMPL_SKIP ? "fused into the next layer" : "direct (reference kernel)");
     return 1;
 }
 
@@ -1131,7 +1131,7 @@ int Engine::profileLayers(int repeats, char (*names)[48], float* ms, double* flo
             if (std::getenv("W2X_VERBOSE")) {
                 char d[256] = "";
                 if (L.plan) igemmDescribe(L.plan, d, sizeof(d));
-                std::fprintf(stderr, "[w2x] %-28s %s\n", L.name.c_str(), L.plan ? d : (L.impl == IMPL_FIRST ? "first-layer mma.sync" : L.impl == IMPL_HEAD ? "image head taps-in-N mma.sync" : L.impl == IMPL_SKIP ? "fused into the next layer" : "direct"));
+                std::fprintf(stderr, "[w2x] %-28s %s\n", L.name.c_str(), L.plan ? d : (L.impl == IMPL_FIRST ? "first-layer mma.sync" : L.impl == IMPL_HEAD ? "head kernel, taps in N (tcgen05)" : L.impl == IMPL_SKIP ? "fused into the next layer" : "direct"));
             }
             ms[i] = t / repeats;
             flops[i] = L.flops * batch;
@@ -1151,8 +1151,9 @@ int Engine::profileLayers(int repeats, char (*names)[48], float* ms, double* flo
 // ------------------------------------------------------------------------------------------------
 double selftestConv(int device, int kind, int n, int h, int w, int cin, int cout, unsigned seed) {
     if (cudaSetDevice(device) != cudaSuccess) return -1.0;
-    const bool headKernel = kind == 5;  // kind 5: the layer of kind 4 through the dedicated image-head kernel
-    if (headKernel) kind = 4;
+    const bool headKernel = kind == 5 || kind == 6;  // kinds 5 / 6: the layers of kinds 4 / 3 through the dedicated head kernels
+    if (kind == 5) kind = 4;
+    if (kind == 6) kind = 3;
     std::vector<void*> bufs;
     auto dmal = [&](size_t bytes) { void* p = nullptr; W2X_CUDA(cudaMalloc(&p, bytes + 256)); bufs.push_back(p); return p; };
     double result = -1.0;

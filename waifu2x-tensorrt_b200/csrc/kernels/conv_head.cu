@@ -180,14 +180,160 @@ __global__ void __launch_bounds__(kHeadThreads, 1) conv_head_kernel(const ConvPa
     }
 }
 
+// ---- ConvTranspose 4x4 stride 2 pad 3, 64 -> 3 channels (the head of unet1 in the 2x models) ---------------------------------
+// Same idea as the image head: output pixel (2y-1+py, 2x-1+px) is the sum over the 2x2 input neighbourhood (y+wy, x+wx) of
+// w[wy][wx][py][px] . x, so one pass computes P[pixel][(wy,wx), (py,px), co] for every input pixel of an 18x18 patch (N = 4 taps
+// x 4 phases x 4 channels = 64, K = 64: four N = 64 UMMAs per 128 pixels) and each 2x2 output block gathers its 4 x 4 partials.
+constexpr int kUpStages = 3;
+constexpr int kUpRows = 48;                               // P^T rows kept: (tap, phase, co < 3)
+constexpr int kUpWBytes = 64 * 128;
+constexpr int kUpPtBytes = kUpRows * kPitch * 4;          // 68352
+constexpr int kUpSmem = 1024 + kUpStages * kPatchBytes + kUpWBytes + kUpPtBytes + 128;
+
+__global__ void __launch_bounds__(kHeadThreads, 1) conv_up4_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmIn, int tilesX,
+                                                                   int tilesY, int numTiles) {
+    extern __shared__ uint8_t smemRaw[];
+    const uint32_t rawAddr = smemU32(smemRaw);
+    const uint32_t patch0 = (rawAddr + 1023u) & ~1023u;
+    uint8_t* sm = smemRaw + (patch0 - rawAddr);
+    const uint32_t wsm = patch0 + kUpStages * kPatchBytes;
+    float* pt = reinterpret_cast<float*>(sm + kUpStages * kPatchBytes + kUpWBytes);
+    const uint32_t bar0 = wsm + kUpWBytes + kUpPtBytes;
+    const uint32_t barMma = bar0 + 8u * kUpStages;
+    volatile uint32_t* tmemSlot = reinterpret_cast<volatile uint32_t*>(sm + kUpStages * kPatchBytes + kUpWBytes + kUpPtBytes + 8 * kUpStages + 8);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile0 = blockIdx.x, stride = gridDim.x;
+
+    auto loadPatch = [&](int tile, int slot) {  // thread 0 only
+        if (tile >= numTiles) return;
+        const HeadTile ht = headTile(tile, tilesX, tilesY);
+        mbarExpectTx(bar0 + 8u * slot, kPatchTx);
+        tmaLoad5d(patch0 + (uint32_t)slot * kPatchBytes, &tmIn, bar0 + 8u * slot, 0, ht.x0, 0, ht.y0, ht.img);
+    };
+    pdlLaunchDependents();
+    if (tid == 0) {
+        for (int st = 0; st < kUpStages; ++st) mbarInit(bar0 + 8u * st, 1);
+        mbarInit(barMma, 1);
+        mbarInitFence();
+        tmaPrefetchDesc(&tmIn);
+    }
+    if (warp == 0) tmemAlloc(smemU32((const void*)tmemSlot), 256);  // 3 row blocks x 64 fp32 columns
+    // B operand: row n = tap*16 + phase*4 + co holds w[phase*4 + co][tap*64 .. tap*64 + 64) of the packed [16][256] matrix
+    for (int i = tid; i < 64 * 8; i += kHeadThreads) {
+        const int n = i >> 3, c = i & 7;
+        const uint4 v = *reinterpret_cast<const uint4*>(p.w + (long long)(n & 15) * p.ktot + (n >> 4) * 64 + c * 8);
+        stsV4(wsm + (uint32_t)n * 128u + ((uint32_t)(c ^ (n & 7)) << 4), v);
+    }
+    fenceProxyAsync();
+    float biasQ[4][3];  // packed per (phase, channel) column
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int co = 0; co < 3; ++co) biasQ[q][co] = __ldg(p.bias + q * 4 + co);
+    const int gy_ = tid >> 4, gx_ = tid & 15;  // this thread's GEMM pixel inside the 16 x 16 tile
+    tcFenceBefore();
+    __syncthreads();
+    tcFenceAfter();
+    const uint32_t tmemBase = *tmemSlot;
+    const uint32_t idesc = instrDescF16(128, 64);
+    const uint32_t hi = descHi(1024, 2);
+    const int quarter = warp & 3, colHalf = warp >> 2;
+    const uint32_t tRow = tmemBase + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(colHalf * 32);
+
+    pdlWait();
+    if (tid == 0)
+        for (int st = 0; st < kUpStages - 1; ++st) loadPatch(tile0 + st * stride, st);
+
+    int stage = 0;
+    uint32_t phase = 0, mmaPhase = 0;
+    for (int tile = tile0; tile < numTiles; tile += stride) {
+        if (tid == 0) loadPatch(tile + (kUpStages - 1) * stride, (stage + kUpStages - 1) % kUpStages);
+        const HeadTile ht = headTile(tile, tilesX, tilesY);
+        if (warp == 0) {
+            mbarWait(bar0 + 8u * stage, phase);
+            tcFenceAfter();
+            if (electOne()) {
+                const uint32_t patch = patch0 + (uint32_t)stage * kPatchBytes;
+#pragma unroll
+                for (int mb = 0; mb < kMBlocks; ++mb)
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)
+                        umma(tmemBase + (uint32_t)(mb * 64), makeDesc(patch + (uint32_t)mb * 16384u + (uint32_t)ks * 32u, hi), makeDesc(wsm + (uint32_t)ks * 32u, hi), idesc,
+                             ks != 0 ? 1u : 0u);
+                tcCommit(barMma);
+            }
+            __syncwarp();
+        }
+        mbarWait(barMma, mmaPhase);
+        tcFenceAfter();
+        __syncthreads();  // every thread has finished gathering the previous tile from P^T
+#pragma unroll
+        for (int mb = 0; mb < kMBlocks; ++mb) {
+            uint32_t r[32];
+            tmemLd32(tRow + (uint32_t)(mb * 64), r);
+            tmemLdWait();
+            const int px = mb * 128 + quarter * 32 + lane;
+            if (px < kBlocks * 16) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int n = colHalf * 32 + j;            // tap*16 + phase*4 + co
+                    if ((n & 3) < 3) pt[((n >> 4) * 12 + ((n >> 2) & 3) * 3 + (n & 3)) * kPitch + px] = __uint_as_float(r[j]);
+                }
+            }
+        }
+        tcFenceBefore();
+        __syncthreads();  // P^T complete; the accumulator and this patch slot may be overwritten
+
+        // one GEMM pixel = one 2 x 2 output block per thread
+        const int y = ht.y0 + gy_, x = ht.x0 + gx_;
+        if (y < p.gy && x < p.gx) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int oy = 2 * y - 1 + (q >> 1), ox = 2 * x - 1 + (q & 1);
+                float acc0 = biasQ[q][0], acc1 = biasQ[q][1], acc2 = biasQ[q][2];
+#pragma unroll
+                for (int tap = 0; tap < 4; ++tap) {
+                    const float* src = pt + (tap * 12 + q * 3) * kPitch + (gy_ + (tap >> 1)) * kPatchX + gx_ + (tap & 1);
+                    acc0 += src[0];
+                    acc1 += src[kPitch];
+                    acc2 += src[2 * kPitch];
+                }
+                if (oy >= 0 && ox >= 0 && oy < p.out_h && ox < p.out_w) {
+                    Half4 h{__floats2half2_rn(acc0, acc1), __floats2half2_rn(acc2, 0.f)};
+                    *reinterpret_cast<Half4*>(p.out + (((long long)ht.img * p.out_h + oy) * p.out_w + ox) * p.out_c) = h;
+                }
+            }
+        }
+        if (++stage == kUpStages) { stage = 0; phase ^= 1u; }
+        mmaPhase ^= 1u;
+    }
+    tcFenceBefore();
+    __syncthreads();
+    if (warp == 0) {
+        tcFenceAfter();
+        tmemDealloc(tmemBase, 256);
+    }
+}
+
 }  // namespace
 
 struct HeadPlan {
     ConvParams p;
     CUtensorMap tmIn;
+    bool up4;  // ConvTranspose 4x4 s2 p3 head (conv_up4_kernel) instead of the 3x3 image head
 };
 
+static bool convUp4Supported(const ConvParams& p) {
+    if (!(p.mode == EPI_UP4 && p.ntaps == 4 && p.cin == 64 && p.ktot == 256 && p.npad == 16 && p.out_c == 4 && p.w_img_stride == 0 && p.sx == 64 &&
+          p.dimc == 64 && p.dimz == 1 && p.slope == 1.f))
+        return false;
+    for (int i = 0; i < 4; ++i)
+        if (p.tap[i].c0 != 0 || p.tap[i].dz != 0 || p.tap[i].dx != (i & 1) || p.tap[i].dy != (i >> 1)) return false;
+    return true;
+}
+
 bool convHeadSupported(const ConvParams& p) {
+    if (convUp4Supported(p)) return true;
     if (!(p.mode == EPI_FINAL && p.is3x3 && p.cin == 64 && p.ntaps == 9 && p.ktot == 576 && p.w_img_stride == 0 && p.skip && p.skip_c == 4 &&
           p.out_c == 4 && p.sx == 64 && p.dimc == 64 && p.dimz == 1))
         return false;
@@ -198,7 +344,7 @@ bool convHeadSupported(const ConvParams& p) {
 
 HeadPlan* convHeadCreatePlan(const ConvParams& p) {
     if (!convHeadSupported(p)) throw Error("image-head kernel does not support this layer shape");
-    HeadPlan* plan = new HeadPlan{p, {}};
+    HeadPlan* plan = new HeadPlan{p, {}, convUp4Supported(p)};
     try {
         encodeActivationMap5d(&plan->tmIn, p, kPatchX, kPatchY);
     } catch (...) {
@@ -218,6 +364,7 @@ void launchConvHead(const HeadPlan* plan, cudaStream_t s, __half* outOverride, i
     if (dev < 0 || dev >= 64) dev = 0;
     if (!attrSet[dev]) {
         cudaFuncSetAttribute(conv_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHeadSmem);
+        cudaFuncSetAttribute(conv_up4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kUpSmem);
         cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
         if (sms[dev] <= 0) sms[dev] = 148;
         attrSet[dev] = true;
@@ -227,7 +374,9 @@ void launchConvHead(const HeadPlan* plan, cudaStream_t s, __half* outOverride, i
     if (nImages > 0) p.gn = nImages;
     const int tilesX = (p.gx + kTileX - 1) / kTileX, tilesY = (p.gy + kTileY - 1) / kTileY;
     const int numTiles = tilesX * tilesY * p.gn;
-    launchPdl(conv_head_kernel, dim3(numTiles < sms[dev] ? numTiles : sms[dev]), dim3(kHeadThreads), kHeadSmem, s, p, plan->tmIn, tilesX, tilesY, numTiles);
+    const dim3 grid(numTiles < sms[dev] ? numTiles : sms[dev]);
+    if (plan->up4) launchPdl(conv_up4_kernel, grid, dim3(kHeadThreads), kUpSmem, s, p, plan->tmIn, tilesX, tilesY, numTiles);
+    else launchPdl(conv_head_kernel, grid, dim3(kHeadThreads), kHeadSmem, s, p, plan->tmIn, tilesX, tilesY, numTiles);
 }
 
 }  // namespace w2x
