@@ -12,6 +12,6 @@ timeout 1200 ncu --set full --clock-control none --import-source on -k regex:con
 timeout 600 ncu --set full --clock-control none -k regex:"unpack_kernel|stitch_kernel" -s 10 -c 3 -o gpurun_out/prof_tiling \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/prof_tiling.log 2>&1
 # 4. image head kernel
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_head -s 9 -c 1 -o gpurun_out/prof_head \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"conv_head|conv_up4" -s 18 -c 2 -o gpurun_out/prof_head \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/prof_head.log 2>&1
 ls -la gpurun_out
