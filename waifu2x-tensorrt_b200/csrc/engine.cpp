@@ -511,7 +511,17 @@ void Engine::buildPlanSwin() {
         dW.push_back(w);
         dBias.push_back(b);
         if (L.kind == L_LN) { dAux0[i] = uploadF(L.gamma); dAux1[i] = uploadF(L.beta); }
-        if (L.kind == L_ATTN) dAux0[i] = uploadF(L.relpos);
+        if (L.kind == L_ATTN) {
+            // relative-position bias as the attention kernel reads it: [head][48][40] (score tile padding), pre-multiplied by log2(e)
+            // (the softmax runs on exp2), padded key columns pre-masked with -1e30 so the kernel needs no bounds tests
+            if (L.window != 6 || L.relpos.size() != (size_t)L.heads * 36 * 36) throw Error("swin plan: window attention expects window 6 and a [heads][36][36] bias");
+            std::vector<float> t((size_t)L.heads * 48 * 40, 0.f);
+            for (uint32_t h = 0; h < L.heads; ++h)
+                for (int r = 0; r < 48; ++r)
+                    for (int c = 0; c < 40; ++c)
+                        t[((size_t)h * 48 + r) * 40 + c] = c >= 36 ? -1e30f : (r < 36 ? L.relpos[((size_t)h * 36 + r) * 36 + c] * 1.4426950408889634f : 0.f);
+            dAux0[i] = uploadF(t);
+        }
     }
     size_t li = 0;
     auto next = [&](uint32_t kind) -> size_t {

@@ -99,6 +99,12 @@ __device__ __forceinline__ uint32_t packHalf2(float a, float b) {
     const __half2 h = __floats2half2_rn(a, b);
     return *reinterpret_cast<const uint32_t*>(&h);
 }
+// 2^x, one MUFU (inputs here are <= 0 after the max subtraction; large negative inputs flush to 0)
+__device__ __forceinline__ float ex2Approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ void ldsm4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
 }
@@ -183,45 +189,50 @@ __global__ void __launch_bounds__(128) window_attention_kernel(const __half* __r
         }
     }
     // ---- scale + relative position bias + shift mask + softmax (rows 16i+g and 16i+g+8; columns 8j+2t, 8j+2t+1) ----
-    const float scale = rsqrtf((float)HD);
-    const float* bias = relpos + (long long)head * NT * NT;
+    // Everything is in log2 units: `relpos` arrives as [head][48][40], already multiplied by log2(e) and with the padded key columns
+    // set to -1e30, so an element costs one FFMA, (the mask), a max, a subtract, an ex2 and an add.
+    const float scale2 = rsqrtf((float)HD) * 1.4426950408889634f;
+    const float* bias = relpos + (long long)head * 48 * 40 + 2 * t;
+    int colReg[5][2];  // shift-mask region of this lane's ten key columns
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        colReg[j][0] = sreg[wib][min(8 * j + 2 * t, NT - 1)];
+        colReg[j][1] = sreg[wib][min(8 * j + 2 * t + 1, NT - 1)];
+    }
     uint32_t pa[3][5][2];  // probabilities as half2: [row tile][col tile][row g | row g+8]
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
             const int r = 16 * i + g + 8 * half;
-            const bool rowOk = r < NT;
-            const int rr = rowOk ? r : 0;
-            const int myReg = sreg[wib][rr];
+            const int myReg = sreg[wib][min(r, NT - 1)];
+            const float* brow = bias + r * 40;
             float v[5][2];
             float mx = -1e30f;
 #pragma unroll
             for (int j = 0; j < 5; ++j) {
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int col = 8 * j + 2 * t + e;
-                    float a = -1e30f;
-                    if (col < NT) {
-                        a = sacc[i][j][2 * half + e] * scale + __ldg(bias + rr * NT + col);
-                        if (shift > 0 && sreg[wib][col] != myReg) a += -100.f;
-                    }
-                    v[j][e] = a;
-                    mx = fmaxf(mx, a);
+                const float2 b = __ldg(reinterpret_cast<const float2*>(brow + 8 * j));
+                float a0 = fmaf(sacc[i][j][2 * half], scale2, b.x), a1 = fmaf(sacc[i][j][2 * half + 1], scale2, b.y);
+                if (shift > 0) {
+                    if (colReg[j][0] != myReg) a0 -= 144.26950408889634f;  // -100 in natural-log units
+                    if (colReg[j][1] != myReg) a1 -= 144.26950408889634f;
                 }
+                v[j][0] = a0;
+                v[j][1] = a1;
+                mx = fmaxf(mx, fmaxf(a0, a1));
             }
             mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
             mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
             float den = 0.f;
 #pragma unroll
             for (int j = 0; j < 5; ++j) {
-                v[j][0] = __expf(v[j][0] - mx);
-                v[j][1] = __expf(v[j][1] - mx);
+                v[j][0] = ex2Approx(v[j][0] - mx);
+                v[j][1] = ex2Approx(v[j][1] - mx);
                 den += v[j][0] + v[j][1];
             }
             den += __shfl_xor_sync(0xffffffffu, den, 1);
             den += __shfl_xor_sync(0xffffffffu, den, 2);
-            const float inv = 1.f / den;
+            const float inv = __fdividef(1.f, den);
 #pragma unroll
             for (int j = 0; j < 5; ++j) pa[i][j][half] = packHalf2(v[j][0] * inv, v[j][1] * inv);
         }
