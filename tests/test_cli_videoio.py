@@ -148,8 +148,7 @@ def _cli(*args, cwd=None):
 BASE = ["--model", "cunet/art", "--scale", "2", "--noise", "0", "--batchSize", "2", "--tileSize", "64"]
 
 
-@pytest.mark.skipif(not os.path.exists(CLI), reason="CLI not built (make -C waifu2x-tensorrt_b200/csrc)")
-def test_cli_argument_rules(tmp_path):
+def test_cli_argument_rules(tmp_path, built_lib):  # built_lib: `make` builds bin/waifu2x-b200 next to lib/libw2x.so
     assert _cli("--help").returncode == 0
     assert "REQUIRED" in _cli("-h").stdout
     r = _cli("--model", "cunet/art", "build")
@@ -169,7 +168,7 @@ def test_cli_argument_rules(tmp_path):
 
 
 @pytest.mark.gpu
-def test_cli_build_and_render_video_and_image(tmp_path):
+def test_cli_build_and_render_video_and_image(tmp_path, built_lib):
     import w2x
     from __graft_entry__ import make_synthetic_model
 
