@@ -18,7 +18,7 @@ def pytest_configure(config):
 def built_lib():
     """libw2x.so, built in-tree.  Built on demand so `pytest -m "not gpu"` works on a fresh checkout."""
     import w2x
-    if not os.path.exists(w2x.LIB_PATH):
+    if not os.path.exists(w2x.LIB_PATH) or not os.path.exists(os.path.join(PKG, "bin", "waifu2x-b200")):
         import __graft_entry__
         __graft_entry__.build()
     return w2x.lib()
