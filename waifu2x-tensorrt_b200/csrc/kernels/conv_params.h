@@ -60,11 +60,14 @@ __device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.f ? 
 // nn.GELU() (erf form).  erf by Abramowitz-Stegun 7.1.26 (|abs error| < 1.5e-7, far below the fp16 output resolution):
 // ~4x fewer instructions than erff in the Linear epilogues.
 __device__ __forceinline__ float geluErf(float v) {
-    const float x = fabsf(v) * 0.70710678118654752f;
-    const float t = __fdividef(1.f, fmaf(0.3275911f, x, 1.f));
+    // gelu(v) = 0.5 v (1 + erf(v / sqrt 2)) = 0.5 (v + |v| erf(|v| / sqrt 2)); erf(x) = 1 - poly(t) exp(-x^2), t = 1 / (1 + p x)
+    const float av = fabsf(v);
+    float t, e;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f * 0.70710678118654752f, av, 1.f)));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(av * av * (-0.5f * 1.4426950408889634f)));  // exp(-x^2), x^2 = v^2 / 2
     const float poly = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f), 0.254829592f);
-    const float erfAbs = 1.f - poly * __expf(-x * x);
-    return 0.5f * v * (1.f + copysignf(erfAbs, v));
+    const float erfAbs = fmaf(-poly, e, 1.f);
+    return 0.5f * fmaf(av, erfAbs, v);
 }
 
 struct alignas(16) Half8 { __half2 a, b, c, d; };
