@@ -557,7 +557,7 @@ __device__ __forceinline__ void epilogueTmaGroups(const ConvArgs& a, uint32_t ba
 // ---- fused RGB first layer ---------------------------------------------------------------------------------------------
 // The 32-channel input of the second convolution of a UNet (conv1.conv.2) is itself conv3x3(RGB) + LeakyReLU: 36 MACs per value.
 // Instead of a separate kernel writing that tensor to HBM and TMA reading it back, four extra warps compute each tile's 18x10x32
-// patch from a 20x12 RGB patch (cp.async, double buffered) with mma.sync (M = 16 patch pixels, N = 32, K = 36 -> 48) and store it
+// patch from a 20x12 RGB patch (cp.async, double buffered) with mma.sync (M = 16 patch pixels, N = 32, K = 27 -> 32) and store it
 // in the exact layout a SWIZZLE_64B TMA box would have produced (16-byte chunk index ^= (pixel >> 1) & 3), then publish the
 // stage on the same full barrier the MMA warp waits on (generic-proxy writes + fence.proxy.async).  Saves, per output pixel of
 // the first layer, 64 B written + 64 B (x halo) read of HBM traffic and one kernel launch.
@@ -567,30 +567,44 @@ __device__ __forceinline__ void fusedFirstProducer(const ConvArgs& a, uint32_t b
     const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const uint32_t barFull = base + kOffFull, barEmpty = base + kOffEmpty;
     const uint32_t rgb0 = base + a.fuseOff;
+    // K runs over k' = tap*3 + c (27 real values, padded to 32: two k-steps); the zero fourth channel of the NHWC4 input and of the
+    // packed [32][tap*4 + c] weights is skipped, which saves a third of the HMMAs (the legacy tensor path is this producer's bound)
+    constexpr int kKs = 2;
     // B fragments and bias of the first layer (constants)
-    uint32_t bf[4][3][2];
+    uint32_t bf[4][kKs][2];
     float bias[4][2];
+    auto wHalf = [&](const __half* wrow, int kp) -> uint32_t {
+        return kp < 27 ? (uint32_t)__half_as_ushort(wrow[(kp / 3) * 4 + kp % 3]) : 0u;
+    };
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) {
         const __half* wrow = a.fuseW + (8 * nt + g) * 36;
 #pragma unroll
-        for (int ks = 0; ks < 3; ++ks) {
+        for (int ks = 0; ks < kKs; ++ks) {
             const int k0 = 16 * ks + 2 * t;
-            bf[nt][ks][0] = k0 < 36 ? *reinterpret_cast<const uint32_t*>(wrow + k0) : 0u;
-            bf[nt][ks][1] = k0 + 8 < 36 ? *reinterpret_cast<const uint32_t*>(wrow + k0 + 8) : 0u;
+            bf[nt][ks][0] = wHalf(wrow, k0) | (wHalf(wrow, k0 + 1) << 16);
+            bf[nt][ks][1] = wHalf(wrow, k0 + 8) | (wHalf(wrow, k0 + 9) << 16);
         }
         bias[nt][0] = a.fuseBias[8 * nt + 2 * t];
         bias[nt][1] = a.fuseBias[8 * nt + 2 * t + 1];
     }
-    // A fragment addressing: k = tap*4 + c; register (ks, h) of a lane holds k = 16ks + 2t + 8h, k + 1 of its pixel row
-    uint32_t aOff[3][2];
+    // A fragment addressing: register (ks, h) of a lane holds k' = 16ks + 2t + 8h and k' + 1 of its pixel row.  The two halves are not
+    // adjacent in the NHWC4 patch in general, so each register is a byte permute of two aligned 32-bit loads.
+    uint32_t aOffA[kKs][2], aOffB[kKs][2], aSel[kKs][2];
+    auto halfOff = [&](int kp) -> int {  // offset (in halfs, from the pixel's patch position) of element k'
+        const int tap = kp / 3;
+        return kp < 27 ? ((tap / 3) * kRgbW + tap % 3) * 4 + kp % 3 : 0;
+    };
 #pragma unroll
-    for (int ks = 0; ks < 3; ++ks)
+    for (int ks = 0; ks < kKs; ++ks)
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            const int k = 16 * ks + 2 * t + 8 * h;
-            const int tap = min(k >> 2, 8);  // taps 9..11 are K padding: their weights are zero, any finite pixel will do
-            aOff[ks][h] = (uint32_t)((((tap / 3) * kRgbW + tap % 3) * 4 + (k & 3)) * 2);
+            const int k0 = 16 * ks + 2 * t + 8 * h;
+            const int ha = halfOff(k0), hb = halfOff(k0 + 1);
+            aOffA[ks][h] = (uint32_t)((ha & ~1) * 2);
+            aOffB[ks][h] = (uint32_t)((hb & ~1) * 2);
+            const uint32_t sa = 2u * (uint32_t)(ha & 1), sb = 4u + 2u * (uint32_t)(hb & 1);
+            aSel[ks][h] = sa | ((sa + 1u) << 4) | (sb << 8) | ((sb + 1u) << 12);
         }
     pdlWait();  // weights / bias above are constants; the RGB tiles come from the preceding kernel
 
@@ -619,14 +633,19 @@ __device__ __forceinline__ void fusedFirstProducer(const ConvArgs& a, uint32_t b
             for (int nt = 0; nt < 4; ++nt) { d[bi][nt][0] = bias[nt][0]; d[bi][nt][1] = bias[nt][1]; d[bi][nt][2] = bias[nt][0]; d[bi][nt][3] = bias[nt][1]; }
         }
 #pragma unroll
-        for (int ks = 0; ks < 3; ++ks) {
+        for (int ks = 0; ks < kKs; ++ks) {
             uint32_t af[kBlk][4];
 #pragma unroll
             for (int bi = 0; bi < kBlk; ++bi) {
-                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(af[bi][0]) : "r"(r0[bi] + aOff[ks][0]));
-                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(af[bi][1]) : "r"(r1[bi] + aOff[ks][0]));
-                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(af[bi][2]) : "r"(r0[bi] + aOff[ks][1]));
-                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(af[bi][3]) : "r"(r1[bi] + aOff[ks][1]));
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {  // a0: (row g, k' low), a1: (row g + 8, k' low), a2 / a3: the same rows, k' + 8
+                    const uint32_t rowBase = (q & 1) ? r1[bi] : r0[bi];
+                    const int h = q >> 1;
+                    uint32_t wa, wb;
+                    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(wa) : "r"(rowBase + aOffA[ks][h]));
+                    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(wb) : "r"(rowBase + aOffB[ks][h]));
+                    af[bi][q] = __byte_perm(wa, wb, aSel[ks][h]);
+                }
             }
 #pragma unroll
             for (int bi = 0; bi < kBlk; ++bi)
