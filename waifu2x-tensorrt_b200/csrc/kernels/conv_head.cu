@@ -3,10 +3,10 @@
 //
 // Why its own kernel: with 3 output channels the layer is bound by how often each input pixel is read, not by math.  A per-tap
 // GEMM (the generic kernels) streams every pixel through the tensor-core operand path nine times (one shifted view per tap).
-// Here the nine taps sit in the N dimension instead: one pass computes, for every pixel of a 10 x 18 input patch, the 27 partial
+// Here the nine taps sit in the N dimension instead: one pass computes, for every pixel of an 18 x 18 input patch, the 27 partial
 // products P[tap*3 + co][pixel] = sum_c w[co][tap][c] * x[pixel][c] (M = 128 pixels, N = 27 -> 32, K = 64: four tcgen05.mma per
-// 128 pixels, fp32 accumulators in TMEM), parks them in shared memory and each output pixel then adds its nine shifted partials.  Every input byte
-// is read from HBM/L2 once and from shared memory once; algorithmic traffic = 128 B/pixel in + 8 B/pixel out (+ 8 B skip).
+// 128 pixels, fp32 accumulators in TMEM), parks them in shared memory and each output pixel then adds its nine shifted partials.
+// Every input byte is read from HBM/L2 once and from shared memory once; algorithmic traffic = 128 B/pixel in + 8 B/pixel out (+ 8 B skip).
 //
 // One persistent CTA per SM (256 threads) walks 16 x 16 output tiles with a four-stage TMA ring of 18 x 18 input patches
 // (128B-swizzled, three patch loads = 124 KB in flight per SM, out-of-image pixels zero-filled by TMA).  The patch is the A operand
