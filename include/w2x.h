@@ -192,6 +192,10 @@ W2X_API void w2x_config_hash(const char* device_name, const w2x_build_config* cf
 /* ONNX -> packed kernel-native weights file, no device needed (the cold part of build). Returns 1/0;
  * err (optional, cap bytes) receives the reason. */
 W2X_API int w2x_pack_onnx(const char* onnx_path, const char* out_path, int precision, char* err, int cap);
+/* getEnginePath (img2img_load.cpp:79-114) without a GPU: which "<stem>_<16 hex>.w2x" next to model_path a render with *cfg on a
+ * device called device_name would load (optimized = exact opt shape first, else the first compatible one in name order).
+ * Returns 1 and the path in out_path, or 0 and the reason ("could not satisfy render configuration", ...). */
+W2X_API int w2x_select_engine(const char* model_path, const w2x_render_config* cfg, const char* device_name, char* out_path, size_t cap);
 /* Describe a packed file: arch id (1 CUNet 1x, 2 UpCUNet 2x), scale, border offset, layer count. */
 W2X_API int w2x_pack_info(const char* pack_path, int* arch, int* scale, int* offset, int* layers);
 

@@ -294,6 +294,18 @@ int w2x_pack_onnx(const char* onnx_path, const char* out_path, int precision, ch
     }
 }
 
+int w2x_select_engine(const char* model_path, const w2x_render_config* cfg, const char* device_name, char* out_path, size_t cap) {
+    if (!model_path || !cfg || !device_name || !out_path || cap == 0) return 0;
+    try {
+        const std::string p = selectEngine(model_path, *cfg, device_name);
+        std::snprintf(out_path, cap, "%s", p.c_str());
+        return p.size() < cap ? 1 : 0;
+    } catch (const std::exception& ex) {
+        std::snprintf(out_path, cap, "%s", ex.what());
+        return 0;
+    }
+}
+
 int w2x_pack_info(const char* pack_path, int* arch, int* scale, int* offset, int* layers) {
     try {
         PackedModel pm = deserializePack(readFile(pack_path));

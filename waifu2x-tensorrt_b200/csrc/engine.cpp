@@ -173,16 +173,6 @@ static std::string deviceNameOf(int id) {
     return prop.name;
 }
 
-static int deviceIdOf(const std::string& name) {  // helper.h:47-56
-    int n = 0;
-    if (cudaGetDeviceCount(&n) != cudaSuccess) return -1;
-    for (int i = 0; i < n; ++i) {
-        cudaDeviceProp prop{};
-        if (cudaGetDeviceProperties(&prop, i) == cudaSuccess && name == prop.name) return i;
-    }
-    return -1;
-}
-
 bool Engine::build(const std::string& onnxPath, const w2x_build_config& bc) {
     try {
         cudaError_t e = cudaSetDevice(bc.deviceId);
@@ -218,45 +208,12 @@ bool Engine::build(const std::string& onnxPath, const w2x_build_config& bc) {
     }
 }
 
-// getEnginePath, img2img_load.cpp:79-114.  Deviation: the name must be exactly <stem>_<16 hex>.w2x, and
-// candidates are visited in sorted order so the choice is deterministic.
+// getEnginePath, img2img_load.cpp:79-114: the selection rules live in hostutil.cpp (selectEngine) so they can be tested without a
+// GPU; here only the device name of the requested device is looked up.
 static std::string findEngine(const std::string& modelPath, const w2x_render_config& rc) {
-    if (!fs::exists(modelPath)) throw Error("model file does not exist");
-    const std::string stem = fs::path(modelPath).stem().string();
-    fs::path dir = fs::path(modelPath).parent_path();
-    if (dir.empty()) dir = ".";
-    std::vector<fs::path> cands;
-    for (const auto& entry : fs::directory_iterator(dir)) {
-        if (!entry.is_regular_file()) continue;
-        const fs::path& p = entry.path();
-        const std::string fn = p.filename().string();
-        if (p.extension().string() != ".w2x" || fn.size() != stem.size() + 1 + 16 + 4) continue;
-        if (fn.compare(0, stem.size(), stem) != 0 || fn[stem.size()] != '_') continue;
-        bool hex = true;
-        for (size_t i = stem.size() + 1; i < stem.size() + 17; ++i) hex = hex && std::isxdigit((unsigned char)fn[i]);
-        if (hex) cands.push_back(p);
-    }
-    std::sort(cands.begin(), cands.end());
-    std::string chosen;
-    for (const auto& p : cands) {
-        const std::string cfgPath = fs::path(p).replace_extension("").string() + ".json";
-        if (!fs::exists(cfgPath)) continue;
-        Sidecar sc = readSidecar(cfgPath);
-        // The reference maps the sidecar's device NAME back to the FIRST device with that name (helper.h:47-56), so on a box
-        // of identical GPUs only device 0 can ever load an engine.  Deviation: a plan is compatible with every device that
-        // carries the recorded name (needed for one-engine-per-GPU frame sharding).
-        sc.cfg.deviceId = deviceIdOf(sc.deviceName);
-        {
-            cudaDeviceProp prop{};
-            if (cudaGetDeviceProperties(&prop, rc.deviceId) == cudaSuccess && sc.deviceName == prop.name) sc.cfg.deviceId = rc.deviceId;
-        }
-        if (isCompatible(rc, sc.cfg)) {
-            if (isOptimized(rc, sc.cfg)) return p.string();
-            if (chosen.empty()) chosen = p.string();
-        }
-    }
-    if (chosen.empty()) throw Error("could not satisfy render configuration");
-    return chosen;
+    cudaDeviceProp prop{};
+    const std::string name = cudaGetDeviceProperties(&prop, rc.deviceId) == cudaSuccess ? prop.name : "";
+    return selectEngine(modelPath, rc, name);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -4,6 +4,8 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
+#include <filesystem>
 #include <fstream>
 #include <sstream>
 
@@ -243,6 +245,45 @@ bool isCompatible(const w2x_render_config& r, const w2x_build_config& b) {
 bool isOptimized(const w2x_render_config& r, const w2x_build_config& b) {
     return r.batchSize == b.optBatchSize && r.channels == b.optChannels && r.width == b.optWidth &&
            r.height == b.optHeight;
+}
+
+// getEnginePath, img2img_load.cpp:79-114: among the artefacts "<stem>_<16 hex>.w2x" next to the model that have a json sidecar
+// and are compatible with the render configuration, an optimized one (opt == requested) wins, else the first compatible one.
+// Deviations: the file name must match exactly (the reference's prefix match lets "noise0" pick up
+// "noise0_scale2x_<hash>"), candidates are visited in sorted order so the choice is deterministic, and a plan is compatible
+// with EVERY device that carries the recorded device name -- the reference maps the name back to the first such device
+// (helper.h:47-56), so on a box of identical GPUs only device 0 could ever load an engine.
+std::string selectEngine(const std::string& modelPath, const w2x_render_config& rc, const std::string& rcDeviceName) {
+    namespace fs = std::filesystem;
+    if (!fs::exists(modelPath)) throw Error("model file does not exist");
+    const std::string stem = fs::path(modelPath).stem().string();
+    fs::path dir = fs::path(modelPath).parent_path();
+    if (dir.empty()) dir = ".";
+    std::vector<fs::path> cands;
+    for (const auto& entry : fs::directory_iterator(dir)) {
+        if (!entry.is_regular_file()) continue;
+        const fs::path& p = entry.path();
+        const std::string fn = p.filename().string();
+        if (p.extension().string() != ".w2x" || fn.size() != stem.size() + 1 + 16 + 4) continue;
+        if (fn.compare(0, stem.size(), stem) != 0 || fn[stem.size()] != '_') continue;
+        bool hex = true;
+        for (size_t i = stem.size() + 1; i < stem.size() + 17; ++i) hex = hex && std::isxdigit((unsigned char)fn[i]);
+        if (hex) cands.push_back(p);
+    }
+    std::sort(cands.begin(), cands.end());
+    std::string chosen;
+    for (const auto& p : cands) {
+        const std::string cfgPath = fs::path(p).replace_extension("").string() + ".json";
+        if (!fs::exists(cfgPath)) continue;
+        Sidecar sc = readSidecar(cfgPath);
+        sc.cfg.deviceId = (!rcDeviceName.empty() && sc.deviceName == rcDeviceName) ? rc.deviceId : -1;
+        if (isCompatible(rc, sc.cfg)) {
+            if (isOptimized(rc, sc.cfg)) return p.string();
+            if (chosen.empty()) chosen = p.string();
+        }
+    }
+    if (chosen.empty()) throw Error("could not satisfy render configuration");
+    return chosen;
 }
 
 std::vector<uint8_t> readFile(const std::string& path) {

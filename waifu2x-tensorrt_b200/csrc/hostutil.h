@@ -43,7 +43,9 @@ void writeSidecar(const std::string& path, const Sidecar& s);
 Sidecar readSidecar(const std::string& path);
 
 bool isCompatible(const w2x_render_config& r, const w2x_build_config& b);  // img2img_load.cpp:9-20
-bool isOptimized(const w2x_render_config& r, const w2x_build_config& b);   // img2img_load.cpp:22-27
+bool isOptimized(const w2x_render_config& r, const w2x_build_config& b);
+// engine artefact discovery (img2img_load.cpp:79-114) for a render on a device called rcDeviceName; throws when nothing fits
+std::string selectEngine(const std::string& modelPath, const w2x_render_config& rc, const std::string& rcDeviceName);   // img2img_load.cpp:22-27
 
 std::vector<uint8_t> readFile(const std::string& path);
 void writeFile(const std::string& path, const void* data, size_t n);

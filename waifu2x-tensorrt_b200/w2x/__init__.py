@@ -125,6 +125,7 @@ _SIGNATURES = {
     "w2x_infer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "w2x_selftest_conv": (C.c_double, [C.c_int] * 7 + [C.c_uint]),
     "w2x_probe_umma": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
+    "w2x_select_engine": (C.c_int, [C.c_char_p, C.POINTER(_RenderConfig), C.c_char_p, C.c_char_p, C.c_size_t]),
     "w2x_probe_mma_rate": (C.c_float, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "w2x_probe_hmma_rate": (C.c_float, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "w2x_probe_mma_tiles": (C.c_float, [C.c_int, C.c_int, C.c_int]),
@@ -190,6 +191,14 @@ def pack_onnx(onnx_path: str, out_path: str, precision: int = PRECISION_FP16) ->
     err = C.create_string_buffer(512)
     if not lib().w2x_pack_onnx(onnx_path.encode(), out_path.encode(), precision, err, 512):
         raise RuntimeError(err.value.decode())
+
+
+def select_engine(model_path: str, cfg: "RenderConfig", device_name: str) -> str:
+    """img2img_load.cpp:79-114 without a GPU: the engine artefact `load` would pick on a device called device_name."""
+    buf = C.create_string_buffer(4096)
+    if not lib().w2x_select_engine(model_path.encode(), C.byref(cfg._c()), device_name.encode(), buf, 4096):
+        raise RuntimeError(buf.value.decode())
+    return buf.value.decode()
 
 
 def pack_info(path: str):
