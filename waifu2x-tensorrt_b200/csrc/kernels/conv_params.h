@@ -48,7 +48,7 @@ struct ConvParams {
     const __half* skip;
     int skip_h, skip_w, skip_c, skip_off;
     const float* skip_scale;  // optional per-(img, channel) multiplier applied to skip (SE fold), or nullptr
-    long long* se_sum;        // optional [gn][npad] int64: fused SE squeeze = sum over the image of round(activation * 2^14),
+    long long* se_sum;        // optional [gn][npad] int64: fused SE squeeze = sum over the image of round(activation * 2^10) (kSeFixedScale),
                               // accumulated with integer atomics (exact, so the result does not depend on which CTA saw which
                               // tile or on the image's batch slot); the buffer must be zeroed before the launch
     int se_slots;             // unused (kept for ABI stability of the struct inside this library)
