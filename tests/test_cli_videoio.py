@@ -126,6 +126,28 @@ def test_videoio_pipes_roundtrip(tmp_path):
     assert cmd == f"-v error -y -f rawvideo -vcodec rawvideo -s 20x12 -pix_fmt bgr24 -r {30000 / 1001:.6f} -i - -vcodec libx264 -pix_fmt yuv420p -crf 23 {outp}"
 
 
+def test_videoio_still_image_has_one_frame(tmp_path):
+    """capture.cpp:88-92: ffprobe reports nb_frames=N/A for images; the capture then yields exactly one frame."""
+    d = str(tmp_path)
+    tools = _fake_tools(d)
+    src = os.path.join(d, "prog.cpp")
+    with open(src, "w") as f:
+        f.write(VIDEOIO_PROG)
+    exe = os.path.join(d, "prog")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", os.path.join(PKG, "host"), src, "-o", exe])
+    rng = np.random.default_rng(3)
+    frames = rng.integers(0, 256, (3, 8, 10, 3), dtype=np.uint8)   # the file holds more data than the one frame that is read
+    img = os.path.join(d, "still.png")
+    _fake_video(img, frames, rate="25/1", image=True)
+    outp = os.path.join(d, "out.png")
+    r = subprocess.run([exe, tools, img, outp], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    l0, l1 = r.stdout.strip().splitlines()
+    assert l0.split()[3] == "1" and abs(float(l0.split()[2]) - 25.0) < 1e-9
+    assert l1.split() == ["1", "0"]
+    assert np.array_equal(np.fromfile(outp, np.uint8).reshape(frames[0].shape), 255 - frames[0])
+
+
 def test_videoio_invalid_probe(tmp_path):
     d = str(tmp_path)
     tools = _fake_tools(d)
