@@ -1445,6 +1445,8 @@ IgemmPlan* igemmCreatePlan(const ConvParams& p) {
 // conv1.conv.2 of a UNet with its RGB first layer computed inside the kernel (fusedFirstProducer).  `first` is the 4 -> 32 layer
 // whose output tensor `second` would have read; that tensor is never written.
 bool igemmFusedFirstSupported(const ConvParams& second, const ConvParams& first) {
+    // the RGB patches are TMA boxes over [img][H][W*4]: rows must be a multiple of 16 bytes and the base 16-byte aligned
+    if (first.sy != (long long)first.dimx * 4 || (first.dimx & 1) || (reinterpret_cast<uintptr_t>(first.in) & 15)) return false;
     return first.is3x3 && first.cin == 4 && first.ktot == 36 && first.npad == 32 && first.mode == EPI_STORE && first.act == ACT_LRELU && !first.skip &&
            first.w_img_stride == 0 && first.sx == 4 && second.is3x3 && second.cin == 32 && second.in == first.out && second.dimx == first.gx &&
            second.dimy == first.gy && second.npad == 64 && second.mode == EPI_STORE && tmaEpilogueOk(second) && !second.se_sum && wantsPatchKernel(second);
