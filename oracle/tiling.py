@@ -4,11 +4,13 @@ NumPy restatement of the reference's host/OpenCV-CUDA tiling arithmetic.  Nothin
 on the product path may import this module: only tests/, __graft_entry__.smoke()
 and bench.py's cpu_baseline / --impl reference legs use it, as the checker.
 
-Parity status: "parity unpinned" for values that pass through the model (the
-reference has no tests, golden vectors or runnable engine).  The
-integer tile grid / blend-weight indexing below is a literal restatement of the
-reference source and is pinned by the golden numbers in tests/golden/tile_grid.json
-(derived by hand from the reference formulas, cross-checked by oracle/tiling_c.c).
+Parity status: this restatement is PINNED against the reference's own code: oracle/_ref/libw2xref.so is
+/root/reference/src/tensorrt/*.cpp compiled unmodified against CPU mocks of the absent libraries (oracle/Makefile,
+oracle/ref_shim/), and tests/test_ref_parity.py checks every function below, and the whole render() loop with analytic
+stand-in networks, bit-for-bit against it (live when the library is built, else against tests/golden/ref_goldens.npz and
+tile_grid.json that tests/golden/make_ref_goldens.py generated from it).  Values that pass through the NEURAL NETWORK stay
+"parity unpinned" against the reference (TensorRT engine + nunif ONNX files are unobtainable): they are
+checked against the fp32 PyTorch graphs in oracle/models.py with BASELINE.json's tolerance.
 
 Reference citations are relative to /root/reference/.
 """
@@ -223,10 +225,13 @@ ModelFn = Callable[[np.ndarray], np.ndarray]  # [B,3,T,T] f32 -> [B,3,outT,outT]
 
 def render(src_bgr: np.ndarray, model: ModelFn, tile: int, out_tile: int, scaling: int,
            overlap: float, batch: int = 1, tta: bool = False,
-           model_batch: int | None = None) -> np.ndarray:
-    """trt::Img2Img::render, src/tensorrt/img2img_render.cpp:224-348, with the TTA mean
-    (intent, not the bug).  `batch` only groups model calls; padding slots
-    (:281) are zero tiles whose outputs are discarded (:298-299)."""
+           model_batch: int | None = None, tta_mode: str = "mean") -> np.ndarray:
+    """trt::Img2Img::render, src/tensorrt/img2img_render.cpp:224-348.  `batch` only groups model calls; padding slots
+    (:281) are zero tiles whose outputs are discarded (:298-299).
+
+    tta_mode "mean" (default, what the product implements): the 8-way average the code computes at :305-314.
+    tta_mode "reference_q1": what the reference actually adds to the canvas -- `outputTile = &tmpOutputMat` (:315), i.e.
+    the LAST de-augmented tile, the average being dropped; used to pin this restatement against oracle/_ref."""
     H, W = src_bgr.shape[:2]
     rgb = src_bgr[..., ::-1]                                        # :227
     oh, ow = H * scaling, W * scaling
@@ -266,7 +271,10 @@ def render(src_bgr: np.ndarray, model: ModelFn, tile: int, out_tile: int, scalin
                     acc = acc + reverse_augment(o, aug)             # :310-312
                 if aug != 7:
                     continue
-                o = acc * np.float32(1.0 / 8.0)                     # :314 (mean; q1)
+                if tta_mode == "reference_q1":
+                    o = reverse_augment(o, aug)                     # :315 tmpOutputMat, the last de-augmented tile
+                else:
+                    o = acc * np.float32(1.0 / 8.0)                 # :314 (mean; q1)
             rect = g.out_rects[ti]
             if overlapping:
                 o = apply_weights(o, rect, ow, oh, weights)         # :325-326

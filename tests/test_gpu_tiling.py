@@ -85,3 +85,37 @@ def test_tta_reduce_is_bit_exact(built_lib):
             acc = acc + tiling.reverse_augment(outs[t, k, :, :, :3].astype(np.float32), k)
         ref = acc * np.float32(0.125)
         assert np.array_equal(got[t, :, :, :3], ref), t
+
+
+# ---- against vectors produced by the reference's own code (oracle/_ref, see tests/golden/make_ref_goldens.py) ----------------
+import os  # noqa: E402
+
+import refcases  # noqa: E402
+
+_GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_goldens.npz"))
+
+
+@pytest.mark.parametrize("name", sorted(refcases.UNPACK_CASES))
+def test_unpack_matches_reference_golden(name, built_lib):
+    """unpack kernel == padRoi -> applyAugmentation -> blobFromImages of the reference (f32 result rounded to fp16), bit-exact."""
+    import w2x
+    W, H, T, OT, S, B, seed = refcases.UNPACK_CASES[name]
+    src = refcases.frame(W, H, seed)
+    g = tiling.calculate_tiles(W, H, W * S, H * S, T, T, OT, OT, S, B, B)
+    gold = _GOLD["unpack_" + name]  # [n][3][T][T] fp16, from RGB tiles
+    got = w2x.unpack_tiles(src, g.in_rects, [i % 8 for i in range(g.count)], T)
+    assert got.shape[0] == gold.shape[0]
+    assert np.array_equal(np.ascontiguousarray(got[..., :3].transpose(0, 3, 1, 2)).view(np.uint16), gold.view(np.uint16))
+    assert (got[..., 3] == 0).all()
+
+
+@pytest.mark.parametrize("name", sorted(refcases.STITCH_CASES))
+def test_stitch_matches_reference_golden(name, built_lib):
+    """stitch kernel == the reference's applyWeights + canvas add + convertTo(8U, 255) + RGB2BGR on the same tile values."""
+    import w2x
+    W, H, T, OT, S, B, seed = refcases.STITCH_CASES[name]
+    g = tiling.calculate_tiles(W, H, W * S, H * S, T, T, OT, OT, S, B, B)
+    tiles = np.zeros((g.count, OT, OT, 4), np.float16)
+    tiles[..., :3] = refcases.stitch_tiles(g.count, OT, seed)
+    got = w2x.stitch_tiles(tiles, g.nx, g.ny, g.out_overlap[0], g.out_overlap[1], W * S, H * S)
+    assert np.array_equal(got, _GOLD["stitch_" + name])

@@ -31,8 +31,10 @@ TileGrid calculateTiles(int inW, int inH, int outW, int outH, int tileW, int til
     if (g.scaledInW - g.inOvX <= 0 || g.scaledInH - g.inOvY <= 0) throw Error("calculateTiles: overlap too large");
     g.nx = (int)std::lround(std::ceil((double)(inW - g.inOvX) / (g.scaledInW - g.inOvX)));
     g.ny = (int)std::lround(std::ceil((double)(inH - g.inOvY) / (g.scaledInH - g.inOvY)));
-    if (g.nx < 1) g.nx = g.nx;  // the reference would produce zero tiles for a frame narrower than the overlap; keep
-    g.count = g.nx * g.ny;
+    // A frame no larger than the input overlap makes tiling.x / tiling.y non-positive: the reference's loops (:43-44) then emit no
+    // rects while its tileCount = x * y can even come out positive (both negative) and index past the empty vectors.  Report an
+    // empty grid instead, so that every caller's `count <= 0` guard fires.
+    g.count = (g.nx < 1 || g.ny < 1) ? 0 : g.nx * g.ny;
     g.inRects.reserve(g.count > 0 ? g.count : 0);
     g.outRects.reserve(g.count > 0 ? g.count : 0);
     const int bx = (tileW - g.scaledInW) / 2, by = (tileH - g.scaledInH) / 2;  // C++ truncating division
