@@ -158,34 +158,6 @@ W2X_API int w2x_tta_reduce(int device, const uint16_t* outs_f16_nhwc4, int tiles
 /* Img2Img::infer (img2img_infer.cpp:41-93): [n,3,T,T] f32 NCHW in [0,1] -> [n,3,outT,outT] f32 NCHW, through the
  * loaded model (n <= batchSize).  Host buffers. */
 W2X_API int w2x_infer(w2x_engine* e, const float* in_nchw, int n, float* out_nchw);
-/* One convolution layer of the implicit-GEMM family on random data, tcgen05 kernel vs the scalar CUDA reference
- * kernel, for on-device self-checks: returns max |diff| (negative on error).  kind: 0 conv3x3, 1 conv2x2s2,
- * 2 convT2x2s2(+skip), 3 convT4x4s2p3->4ch, 4 conv3x3->3ch final(+skip,clamp), 5 = kind 4 through the image-head kernel,
- * 6 = kind 3 through the convT-head kernel. */
-W2X_API double w2x_selftest_conv(int device, int kind, int n, int h, int w, int cin, int cout, unsigned seed);
-
-/* Development probe: which UMMA smem-descriptor base_offset convention lets a 3x3 tap read a SHIFTED view of one
- * TMA-loaded 128B-swizzled patch (mode 0: base_offset=(start>>7)&7, mode 1: 0; pitch = patch row pitch in pixels).
- * err9[tap] = max |device - host|.  Returns 0 on success. */
-W2X_API int w2x_probe_umma(int device, int mode, int pitch, float* err9);
-
-/* Development probe: milliseconds for `iters` x 4 back-to-back tcgen05.mma (M=128, N=n, K=16, fp16) issued on every SM
- * from the same smem operands (A descriptor SBO = sbo_a bytes); cycles per MMA = ms * clock / (4 * iters). */
-W2X_API float w2x_probe_mma_rate(int device, int n, int iters, int sbo_a);
-/* Same MMA loop while another warp streams `stream_bytes`-sized L2-resident copies into shared memory (0 = none): res[0] = SM
- * cycles per MMA, res[1] = bytes streamed per SM cycle.  Shows how operand reads and async shared-memory writes interfere. */
-W2X_API int w2x_probe_mma_rate_stream(int device, int n, int iters, int stream_bytes, float* res);
-/* Development probe: milliseconds for `iters` x `chains` (1..8 independent accumulators) mma.sync.m16n8k16 per warp with
- * `warps` warps per SM on every SM, operands in registers: issue rate of the legacy tensor path (first layer, image head, attention). */
-W2X_API float w2x_probe_hmma_rate(int device, int warps, int chains, int iters);
-/* Development probe: SM cycles per MMA of the 3x3 patch kernel's MMA schedule in isolation (36 N=64 UMMAs per tile from nine tap
- * views, alternating TMEM accumulators, one commit per tile; no loads, no epilogue).  mode bits: 1 = wait for tile t-2's commit
- * before issuing tile t, 2 = one B tile for all taps, 4 = unshifted A views, 8 = a single commit at the end. */
-W2X_API float w2x_probe_mma_tiles(int device, int tiles, int mode);
-/* Development probe: milliseconds for every SM to copy the same `bytes` (16-byte multiple, <= 48 KiB) L2-resident buffer into
- * shared memory `iters` times with cp.async.bulk, four copies in flight per SM: the L2 -> SM rate streamed weights would get. */
-W2X_API float w2x_probe_l2_stream(int device, int bytes, int iters);
-
 /* Host-only helpers (no GPU needed). */
 /* getConfigHash (img2img_build.cpp:8-27) on an explicit device name: writes 64 hex chars + NUL. */
 W2X_API void w2x_config_hash(const char* device_name, const w2x_build_config* cfg, char out_hex[65]);

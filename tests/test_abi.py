@@ -1,4 +1,6 @@
-"""The C-ABI library loads without a GPU and exports every symbol include/w2x.h declares."""
+"""The C-ABI libraries load without a GPU and export every symbol include/*.h declares: include/w2x.h (the drop-in boundary) and
+the test hooks of include/w2x_dev.h from the shipped lib/libw2x.so; the w2x_probe_* micro-benchmarks of include/w2x_dev.h from the
+development build lib/libw2x_dev.so only."""
 import ctypes as C
 import os
 import re
@@ -6,8 +8,8 @@ import re
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def declared_symbols():
-    hdr = open(os.path.join(ROOT, "include", "w2x.h")).read()
+def declared_symbols(header="w2x.h"):
+    hdr = open(os.path.join(ROOT, "include", header)).read()
     return sorted(set(re.findall(r"W2X_API[^;]*?\b(w2x_[a-z0-9_]+)\s*\(", hdr, re.S)))
 
 
@@ -15,14 +17,30 @@ def test_header_and_binding_agree(built_lib):
     import w2x
     decl = declared_symbols()
     assert len(decl) >= 30
-    assert decl == w2x.EXPORTED_SYMBOLS
+    dev = declared_symbols("w2x_dev.h")
+    hooks = [n for n in dev if not n.startswith("w2x_probe_")]
+    assert sorted(decl + hooks) == w2x.EXPORTED_SYMBOLS
+    assert sorted(n for n in dev if n.startswith("w2x_probe_")) == sorted(w2x._DEV_SIGNATURES)
 
 
 def test_library_exports_every_declared_symbol(built_lib):
     import w2x
     raw = C.CDLL(w2x.LIB_PATH)
-    for name in declared_symbols():
+    for name in declared_symbols() + [n for n in declared_symbols("w2x_dev.h") if not n.startswith("w2x_probe_")]:
         assert hasattr(raw, name), name
+    # the shipped library carries no micro-benchmarks; the development build carries everything
+    for name in w2x._DEV_SIGNATURES:
+        assert not hasattr(raw, name), name
+    dev = C.CDLL(w2x.DEV_LIB_PATH)
+    for name in declared_symbols() + declared_symbols("w2x_dev.h"):
+        assert hasattr(dev, name), name
+
+
+def test_shipped_library_ignores_work_skipping_switches(built_lib):
+    """W2X_DBG / W2X_CONV_IMPL / W2X_NO_* alter or skip kernel work: they are compiled out of lib/libw2x.so (csrc/hostutil.h devEnv)."""
+    blob = open(__import__("w2x").LIB_PATH, "rb").read()
+    for name in (b"W2X_DBG", b"W2X_CONV_IMPL", b"W2X_NO_PATCH", b"W2X_NO_FUSE_FIRST", b"W2X_NO_EPI_GROUPS", b"W2X_NO_HEAD_KERNEL", b"W2X_NO_PDL"):
+        assert name + b"\0" not in blob, name
 
 
 def test_defaults_match_reference_config(built_lib):

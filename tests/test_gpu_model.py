@@ -214,3 +214,40 @@ def test_full_size_frame_properties(built_lib, models_dir):
     own = 2 * 256 - 72 - 32                                                      # output pixels owned by tile 0 alone: out tile 440 minus the 32-pixel blend band
     assert np.array_equal(a[:own, :own], crop[:own, :own])
     pin_in.free(); pin_out.free()
+
+
+def test_infer_cfg2_tile256_batch8_matches_fp32_oracle(built_lib, models_dir):
+    """BASELINE configs[1] exactly at the model boundary: cunet/art scale 2, tileSize 256, batchSize 8 -- the only size that
+    exercises nSplit = 4, the 256-wide layers and the odd extents 117 / 113.  Eight real image tiles through w2x_infer vs the
+    fp32 PyTorch graph: u8 within +-1 LSB on >= 99.9 % of values, PSNR >= 50 dB (BASELINE.json north_star)."""
+    e, model_t, msgs = _engine(models_dir, 2, 256, 8)
+    assert e.output_tile_size == 440
+    frame = tiling.synthetic_frame(1920, 1080, 7)[..., ::-1]
+    g = tiling.calculate_tiles(1920, 1080, 3840, 2160, 256, 256, 440, 440, 2, 1 / 16, 1 / 16)
+    picks = [0, 5, 6, 17, 29, 41, 54, 59]  # corners (replicate padding), edges and interior tiles of the 10 x 6 grid
+    x = np.stack([tiling.normalize_u8(tiling.pad_roi(frame, g.in_rects[i])).transpose(2, 0, 1) for i in picks]).astype(np.float32)
+    y = e.infer(x)
+    assert y is not None, msgs
+    ref = _model_fn(model_t)(x)
+    assert y.shape == ref.shape == (8, 3, 440, 440)
+    a, b = np.clip(np.rint(y * 255), 0, 255), np.clip(np.rint(ref * 255), 0, 255)
+    frac = (np.abs(a - b) <= 1).mean()
+    assert frac >= 0.999, (frac, np.abs(a - b).max())
+    assert _psnr(a, b) >= 50
+    for i in range(8):  # per tile as well: no slot of the batch may be worse than the bar
+        assert (np.abs(a[i] - b[i]) <= 1).mean() >= 0.999, i
+    e.close()
+
+
+def test_render_cfg3_tile400_tta(built_lib, models_dir):
+    """BASELINE configs[2] exactly: cunet/art scale 1 (denoise only), --tta, tileSize 400 (out tile 344, overlap 25 / 25).
+    Two tiles x 8 augmentations; the product averages the eight de-augmented outputs."""
+    e, model_t, msgs = _engine(models_dir, 1, 400, 4, 1 / 16, tta=True)
+    assert e.output_tile_size == 344
+    src = tiling.synthetic_frame(400, 330, 12)
+    dst = e.render(src)
+    assert dst is not None, msgs
+    ref = tiling.render(src, _model_fn(model_t), 400, 344, 1, 1 / 16, 4, tta=True)
+    diff = np.abs(dst.astype(np.int32) - ref.astype(np.int32))
+    assert (diff <= 1).mean() >= 0.999 and _psnr(dst, ref) >= 50, ((diff <= 1).mean(), diff.max())
+    e.close()

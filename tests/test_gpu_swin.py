@@ -107,3 +107,49 @@ def test_swin_rejects_bad_tile(built_lib, swin_models):
     assert not e.load(path, w2x.RenderConfig(batchSize=1, height=128, width=128, scaling=2))
     assert "not supported by swin_unet" in msgs[-1]
     e.close()
+
+
+def test_swin_photo_stream_cfg5_order_and_parity(built_lib, tmp_path):
+    """BASELINE configs[4] in miniature: swin_unet/photo scale 4, tileSize 256, an ordered stream of 8 distinct frames through
+    the pipelined submit/wait path (pinned buffers, three frames in flight).  Every output must be the render of ITS frame
+    (order check) and match the fp32 oracle of that frame."""
+    import __graft_entry__
+    import w2x
+    model_t, path = __graft_entry__.make_synthetic_model(str(tmp_path), scale=4, noise=3, model="swin_unet/photo")
+    assert "swin_unet" in path and "photo" in path
+    e = w2x.Img2Img()
+    msgs = []
+    e.setMessageCallback(lambda s, m: msgs.append((s, m)))
+    assert e.build(path, w2x.BuildConfig.fixed(4, 256)), msgs
+    assert e.load(path, w2x.RenderConfig(batchSize=4, height=256, width=256, scaling=4)), msgs
+    W, H, n = 250, 200, 8   # 2 x 1 tiles of 256 per frame
+    frames = [tiling.synthetic_frame(W, H, 100 + s) for s in range(n)]
+    pin_in = [w2x.PinnedArray((H, W, 3)) for _ in range(n)]
+    pin_out = [w2x.PinnedArray((H * 4, W * 4, 3)) for _ in range(n)]
+    tickets = []
+    for f, pi, po in zip(frames, pin_in, pin_out):
+        pi.array[...] = f
+        t = e.submit(pi.ptr, W, H, po.ptr)
+        assert t >= 0, msgs
+        tickets.append(t)
+    assert tickets == sorted(tickets)
+    outs = []
+    for t, po in zip(tickets, pin_out):
+        assert e.wait(t)
+        outs.append(po.array.copy())
+    for i in range(n):
+        assert np.array_equal(outs[i], e.render(frames[i])), f"frame {i} came back out of order or differs from the synchronous render"
+    for i in range(n - 1):
+        assert not np.array_equal(outs[i], outs[i + 1])
+
+    def f(x):
+        with torch.no_grad():
+            return model_t(torch.from_numpy(np.ascontiguousarray(x))).numpy()
+
+    for i in (0, n - 1):
+        ref = tiling.render(frames[i], f, 256, 960, 4, 1 / 16, 4)
+        diff = np.abs(outs[i].astype(np.int32) - ref.astype(np.int32))
+        assert (diff <= 1).mean() >= 0.999 and _psnr(outs[i], ref) >= 50, (i, (diff <= 1).mean(), diff.max())
+    e.close()
+    for p in pin_in + pin_out:
+        p.free()

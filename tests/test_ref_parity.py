@@ -51,7 +51,8 @@ def test_oracle_and_product_grid_equal_reference_on_random_frames(W, H, T, S, B,
     g = tiling.calculate_tiles(W, H, W * S, H * S, T, T, OT, OT, S, B, B)
     if g.nx < 1 or g.ny < 1:
         # frame smaller than the input overlap: the reference's tiling.x / tiling.y go non-positive and its loops do not run
-        assert ins == [] and n == g.nx * g.ny
+        # a negative tileCount makes the reference's vector::reserve throw (render() then fails): reported as INT_MIN by the driver
+        assert ins == [] and (n == g.nx * g.ny or (n == -(1 << 31) and g.nx * g.ny < 0))
         n2, _, ir2, _ = w2x.calculate_tiles(W, H, W * S, H * S, T, T, OT, OT, S, B, B)
         assert n2 == 0 and ir2 == []  # the product reports an empty grid (the reference's tileCount may be garbage here)
         return

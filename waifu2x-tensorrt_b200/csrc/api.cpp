@@ -6,6 +6,7 @@
 #include <filesystem>
 
 #include "engine.h"
+#include "../../include/w2x_dev.h"
 
 using namespace w2x;
 
@@ -238,6 +239,18 @@ double w2x_selftest_conv(int device, int kind, int n, int h, int w, int cin, int
     }
 }
 
+int w2x_run_conv_layer(int device, int kind, int head, int n, int h, int w, int cin, int cout, const uint16_t* in_nhwc, const uint16_t* weights,
+                       const float* bias, const uint16_t* skip_nhwc, uint16_t* out_nhwc) {
+    try {
+        runConvLayer(device, kind, head ? 1 : 0, n, h, w, cin, cout, in_nhwc, weights, bias, skip_nhwc, out_nhwc);
+        return 1;
+    } catch (const std::exception& ex) {
+        std::fprintf(stderr, "w2x_run_conv_layer: %s\n", ex.what());
+        return 0;
+    }
+}
+
+#ifdef W2X_DEV
 int w2x_probe_umma(int device, int mode, int pitch, float* err9) {
     try {
         if (!err9 || cudaSetDevice(device) != cudaSuccess) return -1;
@@ -271,6 +284,7 @@ float w2x_probe_l2_stream(int device, int bytes, int iters) {
     if (cudaSetDevice(device) != cudaSuccess) return -1.f;
     try { return probeL2Stream(bytes, iters); } catch (...) { return -3.f; }
 }
+#endif  // W2X_DEV
 
 void w2x_config_hash(const char* device_name, const w2x_build_config* cfg, char out_hex[65]) {
     if (!out_hex) return;

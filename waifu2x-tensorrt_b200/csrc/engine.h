@@ -94,6 +94,7 @@ public:
 private:
     void unload();
     void buildPlan();
+    void uploadAsync(void* dst, const void* src, size_t bytes);
     void buildPlanCunet();
     void buildPlanSwin();
     void launchLayer(LayerExec& L, cudaStream_t s, __half* outOverride, int nImages);
@@ -166,7 +167,9 @@ private:
     cudaEvent_t evBandModel = nullptr;
 };
 
-// On-device self-check of one implicit-GEMM layer (tcgen05 vs scalar reference); see w2x.h.
+// Single-layer test hooks, see include/w2x_dev.h.  impl: 0 = the kernel the planner picks, 1 = head kernel, 2 = scalar reference.
+void runConvLayer(int device, int kind, int impl, int n, int h, int w, int cin, int cout, const uint16_t* in, const uint16_t* wPacked,
+                  const float* bias, const uint16_t* skip, uint16_t* out);
 double selftestConv(int device, int kind, int n, int h, int w, int cin, int cout, unsigned seed);
 
 }  // namespace w2x

@@ -3,6 +3,7 @@
 #pragma once
 #include <cstdint>
 #include <map>
+#include <cstdlib>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -14,6 +15,17 @@ namespace w2x {
 struct Error : std::runtime_error {
     using std::runtime_error::runtime_error;
 };
+
+// Development switches (kernel variants, timing experiments that skip work) exist only in the W2X_DEV build (lib/libw2x_dev.so);
+// the shipped library ignores the environment for them.
+inline const char* devEnv(const char* name) {
+#ifdef W2X_DEV
+    return std::getenv(name);
+#else
+    (void)name;
+    return nullptr;
+#endif
+}
 
 // ---- tile grid (img2img_render.cpp:7-66) ----------------------------------------------------------
 struct TileGrid {

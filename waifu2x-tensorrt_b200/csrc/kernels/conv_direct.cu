@@ -146,6 +146,7 @@ void launchConvFirst(const ConvParams& p, cudaStream_t s) {
     else launchPdl(conv_first_kernel<4>, dim3(grid), dim3(256), 0, s, p, segsX, chunksY, total);
 }
 
+#ifdef W2X_DEV
 // Development probe (w2x_probe_hmma_rate): `iters` rounds of `chains` independent mma.sync.m16n8k16 (fp16 in, fp32 accumulate)
 // per warp, `warps` warps per SM on every SM, operands in registers: the issue rate of the legacy tensor path that the
 // first-layer, image-head and window-attention kernels use.  Returns milliseconds.
@@ -240,4 +241,5 @@ float probeL2Stream(int bytes, int iters) {
     return ms;
 }
 
+#endif  // W2X_DEV
 }  // namespace w2x

@@ -39,6 +39,13 @@ namespace w2x {
 
 using namespace sm100;
 
+// timing experiments that switch parts of a kernel off (W2X_DBG) exist only in the development build
+#ifdef W2X_DEV
+#define W2X_DBG_ON(a, bit) (((a).dbg & (bit)) != 0)
+#else
+#define W2X_DBG_ON(a, bit) false
+#endif
+
 struct ConvArgs {
     CUtensorMap tmA;     // activation loads (igemm: per-tap box; patch kernel: 18x10 patch box)
     CUtensorMap tmB;     // weights [npad][ktot]
@@ -497,7 +504,7 @@ __device__ __forceinline__ void epilogueTmaGroups(const ConvArgs& a, uint32_t ba
         tcFenceAfter();
 #pragma unroll
         for (int pr = 0; pr < 2; ++pr) {
-            if (pr < nPairs && !(a.dbg & 1)) {
+            if (pr < nPairs && !W2X_DBG_ON(a, 1)) {
                 uint32_t rLo[32], rHi[32];
                 tmemLd32(taddr + (uint32_t)(64 * pr), rLo);
                 tmemLd32(taddr + (uint32_t)(64 * pr + 32), rHi);
@@ -541,7 +548,7 @@ __device__ __forceinline__ void epilogueTmaGroups(const ConvArgs& a, uint32_t ba
         if (lane == 0) mbarArrive(barTEmpty);  // accumulator buffer `group` may be overwritten by this group's next tile
         fenceProxyAsync();
         namedBarSync(barId, 128);
-        if (leader && !(a.dbg & 2)) {
+        if (leader && !W2X_DBG_ON(a, 2)) {
             for (int sub = 0; sub < a.nsub; ++sub) {
                 int c0, cz;
                 subTileCoords(a, tc, sub, c0, cz);
@@ -850,7 +857,7 @@ __global__ void __launch_bounds__(kFused ? kThreads + 32 * kFuseWarps : kThreads
                 for (int cc = 0; cc < a.cchunks; ++cc) {
                     mbarWait(barEmpty + 8u * stage, phase ^ 1u);
                     const uint32_t full = barFull + 8u * stage;
-                    if (a.dbg & 16) {  // timing experiment: no activation traffic at all, the MMAs run on whatever the slot holds
+                    if (W2X_DBG_ON(a, 16)) {  // timing experiment: no activation traffic at all, the MMAs run on whatever the slot holds
                         mbarArrive(full);
                     } else {
                         mbarExpectTx(full, a.bytesA);
@@ -881,7 +888,7 @@ __global__ void __launch_bounds__(kFused ? kThreads + 32 * kFuseWarps : kThreads
                     uint32_t b0 = descLo(wBase + (uint32_t)cc * tapBytes);
                     uint32_t accum = cc != 0 ? 1u : 0u;
                     const uint32_t descHiA = a.descHiA, descHiB = a.descHiB, idesc = a.idesc;
-                    if (!(a.dbg & 4)) {
+                    if (!W2X_DBG_ON(a, 4)) {
 #pragma unroll 1
                         for (int ky = 0; ky < 3; ++ky) {
                             const uint32_t b1 = b0 + bTapStep, b2 = b1 + bTapStep;
@@ -918,6 +925,7 @@ __global__ void __launch_bounds__(kFused ? kThreads + 32 * kFuseWarps : kThreads
     }
 }
 
+#ifdef W2X_DEV
 // ------------------------------------------------------------------------------------------------------------
 // UMMA descriptor probe (development aid, reachable through w2x_probe_umma): one TMA-loaded, 128B-swizzled patch of
 // 18 x 16 pixels x 64 channels; for every 3x3 tap the A operand is a SHIFTED VIEW of that patch (start address moved by
@@ -1167,6 +1175,8 @@ __global__ void __launch_bounds__(128, 1) umma_tile_probe_kernel(int tiles, int 
     if (warp == 0) { tcFenceAfter(); tmemDealloc(tmemBase, 128); }
 }
 
+#endif  // W2X_DEV
+
 // ---- host side -------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -1412,7 +1422,7 @@ IgemmPlan* igemmCreatePlan(const ConvParams& p) {
     plan->args = ConvArgs{};
     plan->args.p = p;
     try {
-        static const bool noPatch = [] { const char* e = std::getenv("W2X_NO_PATCH"); return e && *e == '1'; }();
+        static const bool noPatch = [] { const char* e = devEnv("W2X_NO_PATCH"); return e && *e == '1'; }();
         if (!noPatch && wantsPatchKernel(p)) planPatch(plan);
         else planIgemm(plan);
         if (p.se_sum && !igemmSeFusable(plan)) throw Error("igemm: fused SE squeeze is not available for this layer shape");
@@ -1530,8 +1540,8 @@ void igemmLaunch(const IgemmPlan* plan, cudaStream_t s, __half* outOverride, int
         a = &local;
     }
     // TMA-store layers without a skip tensor and with two staging buffers run the two-group epilogue
-    static const bool noGroups = std::getenv("W2X_NO_EPI_GROUPS") != nullptr;
-    static const int dbg = std::getenv("W2X_DBG") ? std::atoi(std::getenv("W2X_DBG")) : 0;
+    static const bool noGroups = devEnv("W2X_NO_EPI_GROUPS") != nullptr;
+    static const int dbg = devEnv("W2X_DBG") ? std::atoi(devEnv("W2X_DBG")) : 0;
     ConvArgs dbgLocal;
     if (dbg) { dbgLocal = *a; dbgLocal.dbg = dbg; a = &dbgLocal; }
     const bool grouped = a->useTma && !a->hasSkip && a->nbuf == 2 && a->bn <= 128 && !noGroups;
@@ -1557,6 +1567,7 @@ void igemmLaunch(const IgemmPlan* plan, cudaStream_t s, __half* outOverride, int
 }
 
 
+#ifdef W2X_DEV
 // returns 0 on success; err9[tap] = max |device - host| for the given base_offset mode
 int probeUmma(int mode, int pitch, float* err9) {
     if (pitch % 8 != 0 && mode < 2) { /* allowed: explores non-1024 SBO */ }
@@ -1673,4 +1684,5 @@ int probeMmaRateStream(int n, int iters, int streamBytes, float* res) {
     cudaFree(src); cudaFree(out);
     return rc;
 }
+#endif  // W2X_DEV
 }  // namespace w2x

@@ -2,12 +2,14 @@
 // while its predecessor in the stream drains (the predecessor calls pdlLaunchDependents() at its start), runs its prologue
 // (barrier init, TMEM allocation, constant loads) and then blocks in pdlWait() until the predecessor has completed and its
 // writes are visible.  Rule for every kernel launched this way: pdlWait() is executed by every thread before the first access
-// to memory that any earlier kernel writes or still reads.  W2X_NO_PDL=1 falls back to plain stream order.
+// to memory that any earlier kernel writes or still reads.  W2X_NO_PDL=1 falls back to plain stream order (W2X_DEV build only).
 #pragma once
 #include <cuda_runtime.h>
 
 #include <cstdlib>
 #include <utility>
+
+#include "../hostutil.h"
 
 namespace w2x {
 
@@ -17,7 +19,7 @@ __device__ __forceinline__ void pdlLaunchDependents() { asm volatile("griddepcon
 #endif
 
 inline bool pdlEnabled() {
-    static const bool on = std::getenv("W2X_NO_PDL") == nullptr;
+    static const bool on = devEnv("W2X_NO_PDL") == nullptr;
     return on;
 }
 

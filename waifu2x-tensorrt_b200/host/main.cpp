@@ -360,6 +360,7 @@ int main(int argc, char* argv[]) {
             if (failure) std::rethrow_exception(failure);
             capture.release();
             writer.release();
+            if (writer.exitStatus() != 0) throw std::runtime_error("ffmpeg failed to encode \"" + file.string() + "\" (exit status " + std::to_string(writer.exitStatus()) + ")");
             fileIndex++;
         }
     } catch (const std::exception& e) {

@@ -36,6 +36,18 @@ struct FrameSize {  // stands in for cv::Size2i
     size_t bytes() const { return (size_t)width * height * 3; }
 };
 
+// A path inside the double quotes of the reference's command lines (capture.cpp:65-68,96-99; writer.cpp:24-33).  The reference pastes
+// the raw path, so a file name containing " $ ` or \ would be interpreted by the shell (the CLI feeds this from recursive directory
+// discovery, i.e. untrusted names); those four characters are backslash-escaped, every other path yields the reference's exact text.
+inline std::string quotedPath(const std::string& path) {
+    std::string q = "\"";
+    for (char c : path) {
+        if (c == '"' || c == '$' || c == '`' || c == '\\') q += '\\';
+        q += c;
+    }
+    return q + "\"";
+}
+
 class VideoCapture {
 public:
     VideoCapture() noexcept = default;
@@ -49,7 +61,7 @@ public:
         try {
             if (!std::filesystem::exists(path)) throw std::runtime_error("input file does not exist");
             const std::string probe = ffmpegDir + "ffprobe -v error -select_streams v:0 -show_entries "
-                                      "stream=width,height,r_frame_rate,nb_frames -of default=noprint_wrappers=1 \"" + path + "\"";
+                                      "stream=width,height,r_frame_rate,nb_frames -of default=noprint_wrappers=1 " + quotedPath(path);
             FILE* p = popen(probe.c_str(), "r");
             if (!p) throw std::runtime_error("could not open ffprobe with command\"" + probe + "\"");
             char buffer[128];
@@ -63,7 +75,7 @@ public:
             frameSize.height = std::stoi(props.at("height"));
             frameRate = fraction(props.at("r_frame_rate"));
             frameCount = props.at("nb_frames") == "n/a" ? 1 : std::stoi(props.at("nb_frames"));  // no frame count => an image
-            const std::string cmd = ffmpegDir + "ffmpeg -v error -i \"" + path + "\" -f image2pipe -vcodec rawvideo -pix_fmt bgr24 -";
+            const std::string cmd = ffmpegDir + "ffmpeg -v error -i " + quotedPath(path) + " -f image2pipe -vcodec rawvideo -pix_fmt bgr24 -";
             pipe = popen(cmd.c_str(), "r");
             if (!pipe) throw std::runtime_error("could not open ffmpeg with command\"" + cmd + "\"");
             growPipe(pipe);
@@ -156,7 +168,7 @@ public:
                                 std::to_string(frameSize.height) + " -pix_fmt bgr24" + (frameRate <= 0 ? "" : " -r " + std::to_string(frameRate)) +
                                 " -i -" + (codec.empty() ? "" : " -vcodec " + codec) + (pixelFormat.empty() ? "" : " -pix_fmt " + pixelFormat) +
                                 (crf < 0 ? "" : " -crf " + std::to_string(crf)) + (quality < 0 ? "" : " -q:v " + std::to_string(quality)) +
-                                " \"" + outputFile + "\"";
+                                " " + quotedPath(outputFile);
         pipe = popen(cmd.c_str(), "w");
         if (!pipe) throw std::runtime_error("could not open ffmpeg pipe");
         growPipe(pipe);
@@ -178,11 +190,15 @@ public:
     }
 #endif
 
+    // Closes the encoder pipe; the exit status of ffmpeg is kept (the reference drops it, writer.cpp:59-66): a failed encode must
+    // not look like success to the caller.
     void release() noexcept {
-        if (pipe) pclose(pipe);
+        if (pipe) lastStatus = pclose(pipe);
         pipe = nullptr;
         opened = false;
     }
+    // 0 when the last closed encoder exited cleanly (or none was opened)
+    [[nodiscard]] int exitStatus() const noexcept { return lastStatus; }
 
     [[nodiscard]] const std::string& getFfmpegDir() const noexcept { return ffmpegDir; }
     [[nodiscard]] const FrameSize& getFrameSize() const noexcept { return frameSize; }
@@ -214,4 +230,5 @@ private:
     double frameRate = -1;
     std::string outputFile, pixelFormat, codec;
     int crf = -1, quality = -1;
+    int lastStatus = 0;
 };

@@ -124,19 +124,40 @@ _SIGNATURES = {
     "w2x_tta_reduce": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "w2x_infer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "w2x_selftest_conv": (C.c_double, [C.c_int] * 7 + [C.c_uint]),
-    "w2x_probe_umma": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
+    "w2x_run_conv_layer": (C.c_int, [C.c_int] * 8 + [C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.c_void_p, C.c_void_p]),
     "w2x_select_engine": (C.c_int, [C.c_char_p, C.POINTER(_RenderConfig), C.c_char_p, C.c_char_p, C.c_size_t]),
-    "w2x_probe_mma_rate": (C.c_float, [C.c_int, C.c_int, C.c_int, C.c_int]),
-    "w2x_probe_hmma_rate": (C.c_float, [C.c_int, C.c_int, C.c_int, C.c_int]),
-    "w2x_probe_mma_tiles": (C.c_float, [C.c_int, C.c_int, C.c_int]),
-    "w2x_probe_mma_rate_stream": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
-    "w2x_probe_l2_stream": (C.c_float, [C.c_int, C.c_int, C.c_int]),
     "w2x_config_hash": (None, [C.c_char_p, C.POINTER(_BuildConfig), C.c_char_p]),
     "w2x_pack_onnx": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, C.c_int]),
     "w2x_pack_info": (C.c_int, [C.c_char_p] + [C.POINTER(C.c_int)] * 4),
 }
 
 EXPORTED_SYMBOLS = sorted(_SIGNATURES)
+
+# development build only (lib/libw2x_dev.so, -DW2X_DEV): micro-benchmarks declared in include/w2x_dev.h
+_DEV_SIGNATURES = {
+    "w2x_probe_umma": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
+    "w2x_probe_mma_rate": (C.c_float, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "w2x_probe_hmma_rate": (C.c_float, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "w2x_probe_mma_tiles": (C.c_float, [C.c_int, C.c_int, C.c_int]),
+    "w2x_probe_mma_rate_stream": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
+    "w2x_probe_l2_stream": (C.c_float, [C.c_int, C.c_int, C.c_int]),
+}
+DEV_LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libw2x_dev.so")
+_dev_lib = None
+
+
+def dev_lib() -> C.CDLL:
+    """lib/libw2x_dev.so: the same sources built with -DW2X_DEV (probes + the W2X_* switches that alter kernel work).
+    Only scripts/ use it; tests and bench.py run the shipped library."""
+    global _dev_lib
+    if _dev_lib is None:
+        l = C.CDLL(DEV_LIB_PATH)
+        for name, (res, args) in {**_SIGNATURES, **_DEV_SIGNATURES}.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        _dev_lib = l
+    return _dev_lib
 
 
 def lib() -> C.CDLL:
@@ -239,6 +260,25 @@ def tta_reduce(outs_f16: np.ndarray, device: int = 0) -> np.ndarray:
     if not lib().w2x_tta_reduce(device, _ptr(t), tiles, ot, _ptr(mean)):
         raise RuntimeError("w2x_tta_reduce failed")
     return mean
+
+
+def run_conv_layer(kind: int, x: np.ndarray, w_packed: np.ndarray, bias: np.ndarray, cout: int, skip: Optional[np.ndarray] = None,
+                   head: bool = False, device: int = 0) -> np.ndarray:
+    """One layer of the dense path on host data (include/w2x_dev.h: w2x_run_conv_layer).  x: fp16 NHWC [n][h][w][cin];
+    w_packed: fp16 [npad][ktot]; bias f32 [npad]; returns fp16 NHWC."""
+    x = np.ascontiguousarray(x, np.float16)
+    n, h, w, cin = x.shape
+    shape = {0: (n, h - 2, w - 2, cout), 1: (n, h // 2, w // 2, cout), 2: (n, 2 * h, 2 * w, cout), 3: (n, 2 * h - 4, 2 * w - 4, 4),
+             4: (n, h - 2, w - 2, 4)}[kind]
+    out = np.zeros(shape, np.float16)
+    wp = np.ascontiguousarray(w_packed, np.float16)
+    b = np.ascontiguousarray(bias, np.float32)
+    sk = np.ascontiguousarray(skip, np.float16) if skip is not None else None
+    ok = lib().w2x_run_conv_layer(device, kind, int(head), n, h, w, cin, cout, _ptr(x), _ptr(wp), b.ctypes.data_as(C.POINTER(C.c_float)),
+                                  _ptr(sk) if sk is not None else None, _ptr(out))
+    if not ok:
+        raise RuntimeError("w2x_run_conv_layer failed")
+    return out
 
 
 def selftest_conv(kind: int, n: int, h: int, w: int, cin: int, cout: int, seed: int = 1, device: int = 0) -> float:
