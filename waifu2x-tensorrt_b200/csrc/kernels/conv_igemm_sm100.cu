@@ -42,8 +42,17 @@ using namespace sm100;
 // timing experiments that switch parts of a kernel off (W2X_DBG) exist only in the development build
 #ifdef W2X_DEV
 #define W2X_DBG_ON(a, bit) (((a).dbg & (bit)) != 0)
+// cycle counters of the patch kernel's roles: 0 MMA warp total, 1 wait accumulator-empty, 2 wait patch-full, 3 issue + commit,
+// 4 producer total, 5 producer wait slot-empty, 6 epilogue group 0 total, 7 wait accumulator-full, 8 TMEM load + math + staging,
+// 9 barriers + store issue, 10 tiles of this CTA, 11 %globaltimer ns of the MMA loop
+#define W2X_PROF_DECL(name) long long name = 0
+#define W2X_PROF_T(var) const long long var = clock64()
+#define W2X_PROF_ADD(acc, t0) acc += clock64() - (t0)
 #else
 #define W2X_DBG_ON(a, bit) false
+#define W2X_PROF_DECL(name)
+#define W2X_PROF_T(var)
+#define W2X_PROF_ADD(acc, t0)
 #endif
 
 struct ConvArgs {
@@ -73,6 +82,7 @@ struct ConvArgs {
     int fuseW_px, fuseH_px;
     long long fuseSn;           // elements between images of fuseIn
     uint32_t fuseOff;           // byte offset (from the aligned smem base) of the two RGB patch buffers
+    long long* prof;            // W2X_DEV only: per-CTA cycle counters [grid][16] (W2X_PROF=1), see profSlot
 };
 
 struct IgemmPlan {
@@ -485,10 +495,14 @@ __device__ __forceinline__ void epilogueTmaGroups(const ConvArgs& a, uint32_t ba
     TileWalker w;
     w.init(first + group * step, 2 * step, a.tilesN, a.tilesX, a.tilesY);
     uint32_t phase = 0;
+    W2X_PROF_DECL(pWaitFull); W2X_PROF_DECL(pMath); W2X_PROF_DECL(pSync);
+    W2X_PROF_T(pT0);
     for (int j = 0; j < nGroup; ++j, w.next(), phase ^= 1u) {
         const TileCoord tc = w.coord(a.bh, a.bw, a.bn, nBase);
+        W2X_PROF_T(ps0);
         if (leader) bulkWaitRead(0);  // this group's previous store (two tiles ago) has finished reading the staging buffer
         namedBarSync(barId, 128);
+        W2X_PROF_ADD(pSync, ps0);
         float seScale = 0.f;
         if (doSe) {
             if (tc.img != seImg) {
@@ -500,8 +514,11 @@ __device__ __forceinline__ void epilogueTmaGroups(const ConvArgs& a, uint32_t ba
             const bool pvalid = (tc.y0 + yy) < a.p.gy && (tc.x0 + xx) < a.p.gx;  // rows outside the layer's output do not count
             seScale = pvalid ? kSeFixedScale : 0.f;
         }
+        W2X_PROF_T(pw0);
         mbarWait(barTFull, phase);
         tcFenceAfter();
+        W2X_PROF_ADD(pWaitFull, pw0);
+        W2X_PROF_T(pm0);
 #pragma unroll
         for (int pr = 0; pr < 2; ++pr) {
             if (pr < nPairs && !W2X_DBG_ON(a, 1)) {
@@ -546,6 +563,8 @@ __device__ __forceinline__ void epilogueTmaGroups(const ConvArgs& a, uint32_t ba
         tcFenceBefore();
         __syncwarp();
         if (lane == 0) mbarArrive(barTEmpty);  // accumulator buffer `group` may be overwritten by this group's next tile
+        W2X_PROF_ADD(pMath, pm0);
+        W2X_PROF_T(ps1);
         fenceProxyAsync();
         namedBarSync(barId, 128);
         if (leader && !W2X_DBG_ON(a, 2)) {
@@ -556,7 +575,14 @@ __device__ __forceinline__ void epilogueTmaGroups(const ConvArgs& a, uint32_t ba
             }
             bulkCommit();
         }
+        W2X_PROF_ADD(pSync, ps1);
     }
+#ifdef W2X_DEV
+    if (a.prof && group == 0 && leader) {
+        long long* pr = a.prof + 16ll * blockIdx.x;
+        pr[6] = clock64() - pT0; pr[7] = pWaitFull; pr[8] = pMath; pr[9] = pSync;
+    }
+#endif
     if (doSe) seFlush();
     if (leader) bulkWaitAll();
 }
@@ -852,10 +878,14 @@ __global__ void __launch_bounds__(kFused ? kThreads + 32 * kFuseWarps : kThreads
             uint32_t phase = 0;
             TileWalker w;
             w.init(first, step, 1, a.tilesX, a.tilesY);
+            W2X_PROF_DECL(pWaitEmpty);
+            W2X_PROF_T(pT0);
             for (int k = 0; k < nMine; ++k, w.next()) {
                 const TileCoord tc = w.coord(a.bh, a.bw, a.bn, n0);
                 for (int cc = 0; cc < a.cchunks; ++cc) {
+                    W2X_PROF_T(pa);
                     mbarWait(barEmpty + 8u * stage, phase ^ 1u);
+                    W2X_PROF_ADD(pWaitEmpty, pa);
                     const uint32_t full = barFull + 8u * stage;
                     if (W2X_DBG_ON(a, 16)) {  // timing experiment: no activation traffic at all, the MMAs run on whatever the slot holds
                         mbarArrive(full);
@@ -866,19 +896,33 @@ __global__ void __launch_bounds__(kFused ? kThreads + 32 * kFuseWarps : kThreads
                     if (++stage == a.stages) { stage = 0; phase ^= 1u; }
                 }
             }
+#ifdef W2X_DEV
+            if (a.prof) { a.prof[16ll * blockIdx.x + 4] = clock64() - pT0; a.prof[16ll * blockIdx.x + 5] = pWaitEmpty; }
+#endif
         }
     } else if (warp == 1) {
         int stage = 0, acc = 0;
         uint32_t phase = 0, accPhase = 0;
         mbarWait(barW, 0);
         const uint32_t bTapStep = ((uint32_t)a.cchunks * tapBytes) >> 4;  // descriptor-lo distance between consecutive taps of B
+        W2X_PROF_DECL(pWaitAcc); W2X_PROF_DECL(pWaitFull); W2X_PROF_DECL(pIssue);
+        W2X_PROF_T(pT0);
+#ifdef W2X_DEV
+        unsigned long long gt0 = 0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt0));
+#endif
         for (int k = 0; k < nMine; ++k) {
+            W2X_PROF_T(pa);
             mbarWait(barTEmpty + 8u * acc, accPhase ^ 1u);
             tcFenceAfter();
+            W2X_PROF_ADD(pWaitAcc, pa);
             const uint32_t tmemD = tmemBase + (uint32_t)(acc * a.bn);
             for (int cc = 0; cc < a.cchunks; ++cc) {
+                W2X_PROF_T(pb);
                 mbarWait(barFull + 8u * stage, phase);
                 tcFenceAfter();
+                W2X_PROF_ADD(pWaitFull, pb);
+                W2X_PROF_T(pc);
                 if (electOne()) {
                     // Nine taps = shifted views of the patch: whole pixel rows (kRowBytes each) into the swizzled tile.  The ky loop stays
                     // rolled on purpose: fully unrolled, the 36 precomputed descriptor pairs do not fit the uniform register file and the
@@ -905,12 +949,21 @@ __global__ void __launch_bounds__(kFused ? kThreads + 32 * kFuseWarps : kThreads
                     tcCommit(barEmpty + 8u * stage);
                 }
                 __syncwarp();
+                W2X_PROF_ADD(pIssue, pc);
                 if (++stage == a.stages) { stage = 0; phase ^= 1u; }
             }
             if (electOne()) tcCommit(barTFull + 8u * acc);
             __syncwarp();
             if (++acc == 2) { acc = 0; accPhase ^= 1u; }
         }
+#ifdef W2X_DEV
+        if (a.prof && lane == 0) {
+            unsigned long long gt1 = 0;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt1));
+            long long* pr = a.prof + 16ll * blockIdx.x;
+            pr[0] = clock64() - pT0; pr[1] = pWaitAcc; pr[2] = pWaitFull; pr[3] = pIssue; pr[10] = nMine; pr[11] = (long long)(gt1 - gt0);
+        }
+#endif
     } else {
         // tilesN == 1 for this kernel: the walker's N index stays 0 and the slice offset comes in as nBase
         if constexpr (kEpi == EPI_K_TMA_GROUPS) epilogueTmaGroups(a, base, tmemBase, nMine, first, step, n0);
@@ -1159,6 +1212,7 @@ __global__ void __launch_bounds__(128, 1) umma_tile_probe_kernel(int tiles, int 
                         if (!(mode & 2)) bLo += 8192u >> 4;
                     }
                 }
+                if (mode & 512) tcCommit(base + 32);            // a second commit per tile, like the kernel's slot-empty + accumulator-full pair
                 if (mode & 1) tcCommit(base + 8u * acc);       // accumulator hand-back
                 else if (!(mode & 8)) tcCommit(base + 24);      // a commit per tile that nobody waits for (its cost only)
             }
@@ -1544,6 +1598,17 @@ void igemmLaunch(const IgemmPlan* plan, cudaStream_t s, __half* outOverride, int
     static const int dbg = devEnv("W2X_DBG") ? std::atoi(devEnv("W2X_DBG")) : 0;
     ConvArgs dbgLocal;
     if (dbg) { dbgLocal = *a; dbgLocal.dbg = dbg; a = &dbgLocal; }
+#ifdef W2X_DEV
+    // W2X_PROF=1: per-role cycle counters of the patch kernel, averaged over the CTAs and printed after a synchronising launch
+    static const bool profOn = devEnv("W2X_PROF") != nullptr;
+    long long* profBuf = nullptr;
+    ConvArgs profLocal;
+    if (profOn && plan->patch && !a->fused) {
+        checkCuda(cudaMalloc(&profBuf, sizeof(long long) * 16 * plan->grid));
+        checkCuda(cudaMemsetAsync(profBuf, 0, sizeof(long long) * 16 * plan->grid, s));
+        profLocal = *a; profLocal.prof = profBuf; a = &profLocal;
+    }
+#endif
     const bool grouped = a->useTma && !a->hasSkip && a->nbuf == 2 && a->bn <= 128 && !noGroups;
     if (plan->patch) {
         if (a->kc == 64) {
@@ -1564,6 +1629,26 @@ void igemmLaunch(const IgemmPlan* plan, cudaStream_t s, __half* outOverride, int
         else if (a->staged) launchPdl(igemm_kernel<EPI_K_STAGED>, dim3(plan->grid), dim3(kThreads), plan->smem, s, *a);
         else launchPdl(igemm_kernel<EPI_K_DIRECT>, dim3(plan->grid), dim3(kThreads), plan->smem, s, *a);
     }
+#ifdef W2X_DEV
+    if (profBuf) {
+        checkCuda(cudaStreamSynchronize(s));
+        std::vector<long long> h(16 * (size_t)plan->grid);
+        checkCuda(cudaMemcpy(h.data(), profBuf, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        cudaFree(profBuf);
+        double sum[16] = {0};
+        long long maxTotal = 0;
+        for (int c = 0; c < plan->grid; ++c) {
+            for (int i = 0; i < 16; ++i) sum[i] += (double)h[16 * c + i];
+            maxTotal = std::max(maxTotal, h[16 * c]);
+        }
+        const double g = plan->grid, tiles = sum[10] / g, mmas = tiles * a->cchunks * 9 * (a->kc / 16);
+        std::fprintf(stderr,
+                     "[w2x prof] cin=%d cout=%d %dx%d n=%d | tiles/CTA %.1f | MMA warp: total %.0f (max %lld) = waitAcc %.0f + waitFull %.0f + issue %.0f ; %.1f cyc/MMA, clock %.3f GHz | "
+                     "producer: total %.0f waitEmpty %.0f | epi g0: total %.0f waitTFull %.0f math %.0f sync+store %.0f\n",
+                     a->p.cin, a->p.npad, a->p.gx, a->p.gy, a->p.gn, tiles, sum[0] / g, maxTotal, sum[1] / g, sum[2] / g, sum[3] / g, sum[0] / g / std::max(mmas, 1.0),
+                     sum[11] > 0 ? sum[0] / sum[11] : 0.0, sum[4] / g, sum[5] / g, sum[6] / g, sum[7] / g, sum[8] / g, sum[9] / g);
+    }
+#endif
 }
 
 

@@ -160,6 +160,12 @@ def dev_lib() -> C.CDLL:
     return _dev_lib
 
 
+def use_dev_lib() -> None:
+    """Route this process's w2x calls through lib/libw2x_dev.so (scripts/ only: kernel timing experiments)."""
+    global _lib
+    _lib = dev_lib()
+
+
 def lib() -> C.CDLL:
     """Load libw2x.so (built in-tree by `make -C waifu2x-tensorrt_b200/csrc` / __graft_entry__.build())."""
     global _lib
