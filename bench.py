@@ -1,18 +1,26 @@
 #!/usr/bin/env python
-"""bench.py — output Mpx/s of the tile -> model -> stitch hot path (BASELINE.json metric).
+"""bench.py -- output Mpx/s of the tile -> model -> stitch hot path (BASELINE.json metric: "output Mpx/s, cunet/art 2x &
+swin_unet 4x, tile 256").
 
-Default workload (config.workload): BASELINE configs[1] = cunet/art scale 2 noise 3, tileSize 256, batchSize 8, fp16,
-synthetic 1920x1080 BGR frames -> 3840x2160 (60 tiles + 4 padding slots per frame).  One "step" = one frame.
-`--workload swin` runs BASELINE configs[3] instead (swin_unet/art scale 4 noise 3, tile 256, batch 4: 45 tiles + 3 padding
-slots, 1920x1080 -> 7680x4320); it is an extra measurement, the driver's line is the default workload.
+The top-level line is BASELINE configs[1] (config.workload): cunet/art scale 2 noise 3, tileSize 256, batchSize 8, fp16, synthetic
+1920x1080 BGR frames -> 3840x2160 (60 tiles + 4 padding slots per frame); one "step" = one frame.  The same run also measures, at N = 1
+on rank 0, the other half of the metric and the TTA configuration, reported under `workloads`:
+  workloads.swin       BASELINE configs[3]: swin_unet/art scale 4 noise 3, tile 256, batch 4 (45 tiles + 3 padding slots, -> 7680x4320)
+  workloads.cunet_tta  BASELINE configs[2]: cunet/art scale 1 noise 3, tile 400, --tta (24 tiles x 8 augmentations, -> 1920x1080)
+(`--workload swin|cunet_tta` makes one of them the top-level line instead; `--only` skips the extra workloads.)
 
-  value : whole-job output Mpx/s with the input frames already resident in HBM (w2x_render_device), CUDA events on the
-          engine's stream, max over ranks.
-  e2e   : the same metric through the reference-facing call path with HOST buffers: pinned host frame -> H2D ->
-          render -> D2H into a pinned host frame, pipelined (w2x_submit / w2x_wait), copies inside the timed region.
-  roofline : the model stage (tcgen05 implicit-GEMM convolutions dominate it) against the measured dense bf16 peak.
-  cpu_baseline / --impl reference : the reference has no CPU path and cannot be built here; this arm times
-          the oracle port (PyTorch fp32 on the host cores + NumPy tiling restatement) on a bounded sample.
+  value     whole-job output Mpx/s, input frames already resident in HBM (w2x_render_device), CUDA events on the engine's stream,
+            max over ranks.
+  e2e       the same metric through the public API with HOST buffers, copies inside the timed region: pinned host frame -> H2D ->
+            render -> D2H into a pinned host frame, pipelined (w2x_submit / w2x_wait, three frames in flight).
+  e2e_sync  the literal drop-in call: synchronous w2x_render (== trt::Img2Img::render) with pageable host buffers, one frame at a time.
+  roofline  dominant kernel family (conv3x3_patch_kernel for cunet, igemm_kernel for swin): algorithmic 2*MAC FLOPs of those launches
+            / their CUDA-event time (per-layer pass on the engine stream), against MEASURED_PEAKS.json bf16_tflops (burst).
+  roofline_tiling  the memory-bound kernels (unpack, stitch, tta_reduce): SURVEY 8d algorithmic bytes / CUDA-event time of the last
+            timed frame, against MEASURED_PEAKS.json hbm_gbs.
+  cpu_baseline / --impl reference  the reference has no CPU path and its TensorRT/OpenCV-CUDA engine cannot be built here;
+            this arm times the oracle port (PyTorch fp32 on the host cores + NumPy tiling restatement) on a bounded sample.
+Before timing, the run refuses work-skipping development switches and checks one rendered frame against a fresh synchronous render.
 """
 from __future__ import annotations
 
@@ -34,25 +42,34 @@ for p in (ROOT, PKG):
 
 FRAME_W, FRAME_H, BLEND = 1920, 1080, 1.0 / 16.0
 WORKLOADS = {
-    "cunet": dict(model="cunet/art", family="cunet", scale=2, noise=3, tile=256, batch=8, tiles=60,
+    "cunet": dict(model="cunet/art", family="cunet", scale=2, noise=3, tile=256, batch=8, tiles=60, tta=False, dom="patch3x3",
+                  dom_name="conv3x3_patch_kernel (tcgen05)",
                   name="cunet/art scale2 noise3 tile256 batch8 fp16, synthetic 1920x1080 -> 3840x2160 frames (BASELINE configs[1])",
                   cpu_crop=(640, 360), cpu_note="640x360 crop (8 tiles of 256 -> 1280x720)"),
-    "swin": dict(model="swin_unet/art", family="swin_unet", scale=4, noise=3, tile=256, batch=4, tiles=45,
+    "swin": dict(model="swin_unet/art", family="swin_unet", scale=4, noise=3, tile=256, batch=4, tiles=45, tta=False, dom="igemm",
+                 dom_name="igemm_kernel (tcgen05)",
                  name="swin_unet/art scale4 noise3 tile256 batch4 fp16, synthetic 1920x1080 -> 7680x4320 frames (BASELINE configs[3])",
                  cpu_crop=(464, 240), cpu_note="464x240 crop (2 tiles of 256 -> 1856x960)"),
+    "cunet_tta": dict(model="cunet/art", family="cunet", scale=1, noise=3, tile=400, batch=8, tiles=24, tta=True, dom="patch3x3",
+                      dom_name="conv3x3_patch_kernel (tcgen05)",
+                      name="cunet/art scale1 noise3 tile400 batch8 --tta fp16, synthetic 1920x1080 -> 1920x1080 frames (BASELINE configs[2])",
+                      cpu_crop=(344, 344), cpu_note="344x344 crop (1 tile of 400 x 8 augmentations)"),
 }
 METRIC, UNIT = "output Mpx/s", "Mpx/s"
+# switches of the development build that alter or skip kernel work (the shipped library ignores them; refuse anyway)
+FORBIDDEN_ENV = ("W2X_DBG", "W2X_CONV_IMPL", "W2X_NO_PATCH", "W2X_NO_FUSE_FIRST", "W2X_NO_EPI_GROUPS", "W2X_NO_HEAD_KERNEL", "W2X_NO_PDL",
+                 "W2X_PROF", "W2X_REPEAT", "W2X_DEBUG_SYNC")
 
 
 def _peaks():
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
     except Exception:
-        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback (B200_PROFILING.md)"
 
 
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    Q = ("clocks.sm,clocks.max.sm,power.draw.instant,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
@@ -60,7 +77,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -68,9 +85,17 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def mark(self):
+        self.t0 = time.perf_counter()
 
     def stop(self):
+        t1 = time.perf_counter()
+        rows = [r for t, r in self.rows if getattr(self, "t0", 0.0) <= t <= t1]
+        if len(rows) < 2:  # very short window: fall back to everything sampled since start (includes the warm-up)
+            rows = [r for _, r in self.rows]
+        self.rows = rows
         if self.proc:
             self.proc.terminate()
             try:
@@ -88,7 +113,8 @@ class ClockSampler:
                     reasons.add(name)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(pw), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": statistics.median(sm), "sm_min_mhz": min(sm), "sm_max_mhz": max(mx), "power_w_median": statistics.median(pw), "power_w_max": max(pw),
+                "reasons": sorted(reasons), "samples": len(sm)}
 
 
 def cpu_oracle_sample(wl, threads: int, repeats: int = 1):
@@ -110,9 +136,17 @@ def cpu_oracle_sample(wl, threads: int, repeats: int = 1):
     times = []
     for _ in range(repeats):
         t0 = time.perf_counter()
-        out = tiling.render(frame, fn, wl["tile"], out_tile, wl["scale"], BLEND, batch=1)
+        out = tiling.render(frame, fn, wl["tile"], out_tile, wl["scale"], BLEND, batch=1, tta=wl["tta"])
         times.append(time.perf_counter() - t0)
     return out.shape[0] * out.shape[1] / 1e6, times
+
+
+def cpu_baseline_block(wl, passes: int = 3):
+    threads = len(os.sched_getaffinity(0))
+    mpx, times = cpu_oracle_sample(wl, threads, repeats=passes)
+    return {"value": mpx / statistics.median(times), "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"one {wl['cpu_note']}, PyTorch fp32 CPU oracle + NumPy tiling, median of {passes} passes",
+            "pass_seconds": [round(t, 3) for t in times]}
 
 
 def run_reference(args, wl):
@@ -137,40 +171,36 @@ def run_reference(args, wl):
     print(json.dumps(line), flush=True)
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=24)
-    ap.add_argument("--warmup", type=int, default=4)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cunet", choices=sorted(WORKLOADS))
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--layers", action="store_true", help="also print a per-layer profile to stderr")
-    args = ap.parse_args()
-    wl = WORKLOADS[args.workload]
-    if args.impl == "reference":
-        return run_reference(args, wl)
+def tiling_roofline(wl, stage, hbm_gbs, peak_kind):
+    """HBM fraction of the memory-bound kernels from the stage times of the last timed frame.  Algorithmic bytes per SURVEY 8d:
+    unpack = 3*T^2 read + 2*3*T^2 written per tile; stitch = 2*3*outT^2 read per tile + 3 B per output pixel written;
+    tta_reduce = 8*2*3*outT^2 read + 2*3*outT^2 written per tile."""
+    T, S = wl["tile"], wl["scale"]
+    out_t = {"cunet": (2 * T - 72 if S == 2 else T - 56), "swin_unet": (T - 16) * S}[wl["family"]]
+    steps = wl["tiles"] * (8 if wl["tta"] else 1)
+    out_px = FRAME_W * S * FRAME_H * S
+    rows = {"unpack": (steps * 9 * T * T, stage.get("unpack", 0.0)),
+            "stitch": (wl["tiles"] * 6 * out_t * out_t + 3 * out_px, stage.get("stitch", 0.0))}
+    if wl["tta"]:
+        rows["tta_reduce"] = (wl["tiles"] * (8 * 6 + 6) * out_t * out_t, stage.get("tta_reduce", 0.0))
+    out = {"bound": "hbm", "peak": hbm_gbs, "unit": "GB/s", "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})",
+           "note": "algorithmic bytes (SURVEY 8d) / CUDA-event time inside the timed region, last frame; unpack is summed over the frame's batches"}
+    for k, (nbytes, ms) in rows.items():
+        gbs = nbytes / (ms / 1e3) / 1e9 if ms > 0 else None
+        out[k] = {"bytes": nbytes, "ms": ms, "achieved": gbs, "frac": gbs / hbm_gbs if gbs else None}
+    return out
 
+
+def measure(wl, args, rank, world, local, dist, heavy=True):
+    """One workload on this rank's GPU -> dict of measurements (the caller assembles the JSON line)."""
     import numpy as np
     import torch
-    import torch.distributed as dist
 
     import __graft_entry__
     import w2x
     from oracle import tiling  # synthetic frame generator only; never on the measured path
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    w2x.lib()
     TILE, BATCH, SCALE = wl["tile"], wl["batch"], wl["scale"]
-
-    # ---- build + load through the reference-shaped API ----
     tmp = tempfile.mkdtemp(prefix=f"w2x_bench_r{rank}_")
     _, onnx_path = __graft_entry__.make_synthetic_model(tmp, scale=SCALE, noise=wl["noise"], model=wl["model"])
     eng = w2x.Img2Img()
@@ -178,8 +208,9 @@ def main():
     eng.setMessageCallback(lambda sev, m: msgs.append((sev, m)))
     if not eng.build(onnx_path, w2x.BuildConfig.fixed(BATCH, TILE, device=local)):
         raise SystemExit(f"build failed: {msgs}")
-    if not eng.load(onnx_path, w2x.RenderConfig(deviceId=local, batchSize=BATCH, height=TILE, width=TILE, scaling=SCALE, overlap=(BLEND, BLEND))):
+    if not eng.load(onnx_path, w2x.RenderConfig(deviceId=local, batchSize=BATCH, height=TILE, width=TILE, scaling=SCALE, overlap=(BLEND, BLEND), tta=wl["tta"])):
         raise SystemExit(f"load failed: {msgs}")
+    steps, warmup = (args.steps, args.warmup) if heavy else (max(8, args.steps // 3), max(3, args.warmup // 2))
 
     n_in = 4  # distinct input frames, rotated
     frames = [tiling.synthetic_frame(FRAME_W, FRAME_H, rank * 1000 + s) for s in range(n_in)]
@@ -193,20 +224,27 @@ def main():
     def barrier():
         eng.sync()
         torch.cuda.synchronize()
-        if world > 1:
+        if world > 1 and heavy:
             dist.barrier()
         eng.sync()
 
+    def allmax(x):
+        if world > 1 and heavy:
+            t = torch.tensor([x], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return x
+
     # ---- device-resident throughput (`value`) ----
-    for i in range(args.warmup):
+    sampler = ClockSampler(local)
+    sampler.start()  # nvidia-smi needs a few hundred ms to start: begin before the warm-up, keep the samples of the timed window
+    for i in range(warmup):
         assert eng.render_device(d_in[i % n_in], FRAME_W, FRAME_H, d_out), eng.last_error
     barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler.mark()
     launches0 = eng.launch_count
     eng.timer_mark(0)
-    model_ms_sum = 0.0
-    for i in range(args.steps):
+    for i in range(steps):
         assert eng.render_device(d_in[i % n_in], FRAME_W, FRAME_H, d_out), eng.last_error
     eng.timer_mark(1)
     eng.sync()
@@ -215,15 +253,16 @@ def main():
     launches = eng.launch_count - launches0
     stage = eng.last_stage_ms()  # stage split of the last timed frame (events recorded inside the timed region)
     clocks = sampler.stop()
-    if world > 1:
-        t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_max = float(t.item())
-    else:
-        ms_max = ms_total
-    value = world * args.steps * out_mpx / (ms_max / 1e3)
+    ms_max = allmax(ms_total)
+    value = (world if heavy else 1) * steps * out_mpx / (ms_max / 1e3)
+    # the last timed frame, read back, must equal a fresh synchronous render of the same input through the drop-in call
+    last = np.empty((FRAME_H * SCALE, FRAME_W * SCALE, 3), np.uint8)
+    eng.d2h(last, d_out)
+    fresh = eng.render(frames[(steps - 1) % n_in])
+    if fresh is None or not np.array_equal(fresh, last):
+        raise SystemExit("bench: the last timed frame differs from a fresh render() of the same input")
 
-    # ---- end-to-end through host buffers (`e2e`) ----
+    # ---- end to end through host buffers, pipelined (`e2e`) ----
     ring = 4
     pin_in = [w2x.PinnedArray((FRAME_H, FRAME_W, 3)) for _ in range(ring)]
     pin_out = [w2x.PinnedArray((FRAME_H * SCALE, FRAME_W * SCALE, 3)) for _ in range(ring)]
@@ -242,77 +281,147 @@ def main():
         for t in tickets[-ring:]:
             assert eng.wait(t)
 
-    e2e_pass(max(args.warmup, ring))  # every ring slot has been through one H2D / D2H before the timed pass
+    e2e_pass(max(warmup, ring))  # every ring slot has been through one H2D / D2H before the timed pass
     barrier()
     eng.timer_mark(2, 1)
     t0 = time.perf_counter()
-    e2e_pass(args.steps)
+    e2e_pass(steps)
     eng.timer_mark(3, 2)
     eng.sync()
     e2e_wall_ms = (time.perf_counter() - t0) * 1e3
     e2e_ms = eng.timer_elapsed_ms(2, 3)
     if e2e_ms <= 0:
         e2e_ms = e2e_wall_ms
-    if world > 1:
-        t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
-    e2e_value = world * args.steps * out_mpx / (e2e_ms / 1e3)
-    checksum = int(pin_out[(args.steps - 1) % ring].array[::97, ::89].astype(np.uint64).sum())  # result read on the host
+    e2e_ms = allmax(e2e_ms)
+    e2e_value = (world if heavy else 1) * steps * out_mpx / (e2e_ms / 1e3)
+    if not np.array_equal(pin_out[(steps - 1) % ring].array, eng.render(frames[(steps - 1) % ring % n_in])):
+        raise SystemExit("bench: the last pipelined frame differs from a fresh render() of the same input")
+    checksum = int(pin_out[(steps - 1) % ring].array[::97, ::89].astype(np.uint64).sum())  # result read on the host
 
+    # ---- the literal drop-in call: synchronous render(), pageable host buffers (`e2e_sync`) ----
+    sync_steps = max(4, steps // 4)
+    page_in = [np.array(f, copy=True) for f in frames]
+    page_out = np.empty((FRAME_H * SCALE, FRAME_W * SCALE, 3), np.uint8)
+    for i in range(2):
+        assert eng.render_into(page_in[i % n_in], page_out), eng.last_error
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(sync_steps):
+        assert eng.render_into(page_in[i % n_in], page_out), eng.last_error
+    sync_ms = allmax((time.perf_counter() - t0) * 1e3)
+    sync_value = (world if heavy else 1) * sync_steps * out_mpx / (sync_ms / 1e3)
+
+    res = dict(value=value, ms_per_step=ms_max / steps, steps=steps, warmup=warmup, stage=stage, clocks=clocks, launches=int(launches),
+               e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=in_bytes, d2h_bytes_per_step=out_bytes, ms_per_step=e2e_ms / steps,
+                        wall_ms_per_step=e2e_wall_ms / steps, host_checksum=checksum, path="w2x_submit / w2x_wait, pinned host buffers, 3 frames in flight"),
+               e2e_sync=dict(value=sync_value, unit=UNIT, ms_per_step=sync_ms / sync_steps, steps=sync_steps,
+                             path="w2x_render (trt::Img2Img::render drop-in), pageable host buffers, synchronous, wall clock"),
+               fps=(world if heavy else 1) * steps / (ms_max / 1e3), out_mpx=out_mpx)
     if rank == 0:
         peaks, peak_kind = _peaks()
-        flops_frame = eng.flops_per_tile * wl["tiles"]  # real tiles per 1080p frame (padding slots excluded)
+        flops_frame = eng.flops_per_tile * wl["tiles"] * (8 if wl["tta"] else 1)  # real tiles per 1080p frame (padding slots excluded)
         model_ms = stage.get("model", 0.0)
         stage_tflops = flops_frame / (model_ms / 1e3) / 1e12 if model_ms > 0 else None
         # dominant kernel family, each launch timed with CUDA events on the engine stream (3 back-to-back repeats per layer,
         # inputs of a batch of tiles exceed L2): algorithmic FLOPs of those launches / their summed duration
         prof = eng.profile_layers(3)
-        dom_key = "patch3x3" if args.workload == "cunet" else "igemm"
-        dom = [(ms, fl) for i, (name, ms, fl) in enumerate(prof) if (eng.layer_kernel(i) or "").startswith(dom_key)]
+        dom = [(ms, fl) for i, (name, ms, fl) in enumerate(prof) if (eng.layer_kernel(i) or "").startswith(wl["dom"])]
         dom_ms, dom_fl = sum(m for m, _ in dom), sum(f for _, f in dom)
         achieved = dom_fl / (dom_ms / 1e3) / 1e12 if dom_ms > 0 else None
         peak = float(peaks.get("bf16_tflops", 1600.0))  # burst figure: these launches are timed alone
-        traffic = None
+        sustained = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        traffic, traffic_src = None, None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(args.workload)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+            traffic, traffic_src = tj.get(wl.get("traffic_key", args.workload)), tj.get(wl.get("traffic_key", args.workload) + "_note")
         except Exception:
             pass
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "fp16 (fp32 accumulate)", "data": "synthetic",
-            "config": {"workload": wl["name"], "frames_per_rank": args.steps, "sharding": "frames round-robin, one engine per GPU, no collective",
-                       "l2": "each step streams >1 GB of activations + 4 rotating input frames (> 126 MB L2)", "weights": "seeded synthetic (seed 1234)"},
-            "fps": world * args.steps / (ms_max / 1e3),
-            "stage_ms_last_frame": {k: stage.get(k, 0.0) for k in ("unpack", "model", "stitch")},
-            "roofline": {"bound": "tensor", "kernel": ("conv3x3_patch_kernel (tcgen05)" if args.workload == "cunet" else "igemm_kernel (tcgen05)")
-                         + f": {len(dom)} launches per batch, algorithmic 2*MAC FLOPs / CUDA-event time",
-                         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
-                         "peak_source": f"MEASURED_PEAKS.json bf16_tflops ({peak_kind}, burst: kernel timed alone)",
-                         "launch_ms_sum": dom_ms, "flops_sum": dom_fl, "traffic": traffic,
-                         "tensor_pipe_busy": "0.98 on unet2.conv5 (ncu hmma_cycles_active per TPC / 2 / sm cycles_active, profiles/r01_ncu_patch_batch.txt): the pipe waits on shared-memory operands, see DESIGN 4.1" if args.workload == "cunet" else None,
-                         "model_stage": {"achieved": stage_tflops, "peak": float(peaks.get("bf16_tflops_sustained", 1400.0)), "unit": "TFLOP/s",
-                                         "frac": stage_tflops / float(peaks.get("bf16_tflops_sustained", 1400.0)) if stage_tflops else None,
-                                         "flops_per_frame": flops_frame, "note": "all model kernels of the last timed frame (events inside the timed region) vs the sustained peak"}},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
-                    "ms_per_step": e2e_ms / args.steps, "wall_ms_per_step": e2e_wall_ms / args.steps, "host_checksum": checksum},
-            "gpu_launches": int(launches),
-            "clocks": clocks,
-        }
-        if not args.no_cpu_baseline:
-            threads = len(os.sched_getaffinity(0))
-            mpx, times = cpu_oracle_sample(wl, threads, repeats=1)
-            line["cpu_baseline"] = {"value": mpx / times[0], "unit": UNIT, "cores": threads, "kind": "port",
-                                    "sample": f"one {wl['cpu_note']}, PyTorch fp32 CPU oracle + NumPy tiling, 1 pass"}
+        res["roofline"] = {
+            "bound": "tensor", "kernel": wl["dom_name"] + f": {len(dom)} launches per batch, algorithmic 2*MAC FLOPs / CUDA-event time",
+            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
+            "peak_source": f"MEASURED_PEAKS.json bf16_tflops ({peak_kind}, burst: kernel timed alone)",
+            "launch_ms_sum": dom_ms, "flops_sum": dom_fl, "traffic": traffic, "traffic_source": traffic_src,
+            "model_stage": {"achieved": stage_tflops, "peak": sustained, "unit": "TFLOP/s", "frac": stage_tflops / sustained if stage_tflops else None,
+                            "flops_per_frame": flops_frame, "note": "all model kernels of the last timed frame (events inside the timed region) vs the sustained peak"}}
+        res["roofline_tiling"] = tiling_roofline(wl, stage, float(peaks.get("hbm_gbs", 6650.0)), peak_kind)
         if args.layers:
-            for name, ms, fl in prof:
-                print(f"  {name:44s} {ms:8.3f} ms  {fl / ms / 1e9 if ms > 0 else 0:9.1f} TFLOP/s", file=sys.stderr)
+            print(f"# per-layer profile, {wl['name']}", file=sys.stderr)
+            for i, (name, ms, fl) in enumerate(prof):
+                print(f"  {name:44s} {ms:8.3f} ms  {fl / ms / 1e9 if ms > 0 else 0:9.1f} TFLOP/s   {eng.layer_kernel(i) or ''}", file=sys.stderr)
+    eng.close()
+    for pbuf in pin_in + pin_out:
+        pbuf.free()
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=32)
+    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cunet", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--only", action="store_true", help="skip the extra workloads (workloads.*) of the default line")
+    ap.add_argument("--batch", type=int, default=0, help="experiment: override the workload's batchSize (the driver line uses the default)")
+    ap.add_argument("--layers", action="store_true", help="also print a per-layer profile to stderr")
+    args = ap.parse_args()
+    wl = dict(WORKLOADS[args.workload])
+    if args.batch > 0:
+        wl["batch"] = args.batch
+        wl["name"] += f" [batch override {args.batch}]"
+    if args.impl == "reference":
+        return run_reference(args, wl)
+    bad = [k for k in FORBIDDEN_ENV if os.environ.get(k)]
+    if bad:
+        raise SystemExit(f"bench.py refuses to run with development switches set: {bad}")
+
+    import torch
+    import torch.distributed as dist
+
+    import w2x
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    w2x.lib()  # the shipped library (lib/libw2x.so); raises if it is missing
+
+    r = measure(wl, args, rank, world, local, dist, heavy=True)
+    extra = {}
+    if rank == 0 and world == 1 and not args.only and args.batch == 0:
+        for key in ("swin", "cunet_tta", "cunet"):
+            if key == args.workload or (key == "cunet" and args.workload != "cunet"):
+                continue
+            w2 = dict(WORKLOADS[key])
+            x = measure(w2, args, rank, world, local, dist, heavy=False)
+            extra[key] = {"workload": w2["name"], "value": x["value"], "unit": UNIT, "ms_per_step": x["ms_per_step"], "steps": x["steps"], "warmup": x["warmup"],
+                          "fps": x["fps"], "e2e": x["e2e"], "e2e_sync": x["e2e_sync"], "stage_ms_last_frame": x["stage"], "roofline": x.get("roofline"),
+                          "roofline_tiling": x.get("roofline_tiling"), "gpu_launches": x["launches"], "clocks": x["clocks"]}
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": world, "steps": r["steps"], "warmup": r["warmup"],
+            "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "fp16 (fp32 accumulate)", "data": "synthetic",
+            "config": {"workload": wl["name"], "frames_per_rank": r["steps"], "sharding": "frames round-robin, one engine per GPU, no collective",
+                       "l2": "each step streams >1 GB of activations + 4 rotating input frames (> 126 MB L2)", "weights": "seeded synthetic (seed 1234)",
+                       "checked": "last timed frame == fresh synchronous render() of the same input (byte-exact), device-resident and pipelined paths"},
+            "fps": r["fps"], "stage_ms_last_frame": r["stage"],
+            "roofline": r.get("roofline"), "roofline_tiling": r.get("roofline_tiling"),
+            "e2e": r["e2e"], "e2e_sync": r["e2e_sync"], "gpu_launches": r["launches"], "clocks": r["clocks"],
+        }
+        if extra:
+            line["workloads"] = extra
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_block(wl, passes=3)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    eng.close()
 
 
 if __name__ == "__main__":

@@ -107,6 +107,24 @@ W2X_API int w2x_wait(w2x_engine* e, int ticket);
 W2X_API int w2x_render_banded(w2x_engine* const* engines, int count, const uint8_t* src_bgr, int width, int height,
                               size_t src_stride, uint8_t* dst_bgr, size_t dst_stride);
 W2X_API int w2x_sync(w2x_engine* e);
+
+/* Frame-parallel multi-GPU rendering in one process (the "device list" the reference's single `--device`, main.cpp:70-74, lacks):
+ * one engine + weight replica + pinned-copy pipeline + host worker thread per listed device; frame f (the ticket, counted from 0 in
+ * submission order) goes to device f mod count; no collective, no peer traffic.  w2x_pool_wait retires frames in whatever order
+ * the caller asks (a writer asks in ticket order, which restores frame order).  A device id may be listed more than once.
+ * build: cfg->deviceId is ignored, one artefact is built per distinct device NAME in the pool (the name is what the file name
+ * hashes, img2img_build.cpp:8-27); load: cfg->deviceId is replaced by each engine's own device.  Buffers as for w2x_submit. */
+typedef struct w2x_pool w2x_pool;
+W2X_API w2x_pool* w2x_pool_create(const int* device_ids, int count);
+W2X_API void w2x_pool_destroy(w2x_pool* p);
+W2X_API int w2x_pool_size(w2x_pool* p);
+W2X_API w2x_engine* w2x_pool_engine(w2x_pool* p, int index);   /* borrowed: introspection, w2x_render_banded */
+W2X_API void w2x_pool_set_message_callback(w2x_pool* p, w2x_message_cb cb, void* user);
+W2X_API int w2x_pool_build(w2x_pool* p, const char* onnx_path, const w2x_build_config* cfg);
+W2X_API int w2x_pool_load(w2x_pool* p, const char* onnx_path, const w2x_render_config* cfg);
+W2X_API int w2x_pool_submit(w2x_pool* p, const uint8_t* src_bgr, int width, int height, size_t src_stride, uint8_t* dst_bgr, size_t dst_stride);
+W2X_API int w2x_pool_wait(w2x_pool* p, int ticket);
+W2X_API int w2x_pool_sync(w2x_pool* p);
 W2X_API void* w2x_host_alloc(size_t bytes);   /* cudaHostAlloc (pinned) */
 W2X_API void w2x_host_free(void* p);
 W2X_API void* w2x_device_alloc(w2x_engine* e, size_t bytes);
@@ -120,7 +138,7 @@ W2X_API int w2x_output_tile_size(w2x_engine* e);          /* outputTensorShape.d
 W2X_API long long w2x_launch_count(w2x_engine* e);        /* kernels launched by this engine so far */
 W2X_API double w2x_model_flops_per_tile(w2x_engine* e);   /* algorithmic 2*MAC of the dense layers */
 /* Per-stage device time of the LAST completed render, from CUDA events on the engine's stream:
- * out[0]=unpack ms, out[1]=model ms, out[2]=stitch/pack ms, out[3]=total ms; returns count written. */
+ * out[0]=unpack ms, out[1]=model ms, out[2]=stitch/pack ms, out[3]=total ms, out[4]=tta_reduce ms (0 without --tta); returns count written (<= n). */
 W2X_API int w2x_last_stage_ms(w2x_engine* e, float* out, int n);
 /* CUDA-event timer on the engine's streams (which: 0 compute, 1 H2D copy, 2 D2H copy): mark idx in [0,16), then
  * w2x_timer_elapsed_ms synchronises both events and returns milliseconds between them (negative on error). */

@@ -226,6 +226,19 @@ def test_cli_build_and_render_video_and_image(tmp_path, built_lib):
     cmd = open(img_out + ".cmd").read()
     assert "-r 1.000000 -i - -crf 23" in cmd                               # image: codec/pix_fmt cleared (main.cpp:246-249)
 
+    # extension: --device with a list shards the frames over an engine pool (the same GPU twice here) -- same bytes, same order
+    os.makedirs(os.path.join(d, "out2"))
+    r = _cli(*BASE, "--device", "0,0", "render", "-i", os.path.join(d, "in", "clip.mkv"), "-o", os.path.join(d, "out2"), "--ffmpegDir", tools, cwd=d)
+    assert r.returncode == 0, r.stdout + r.stderr
+    got2 = np.fromfile(os.path.join(d, "out2", "clip(cunet_art)(noise0)(scale2).mp4"), np.uint8).reshape(want.shape)
+    assert np.array_equal(got2, want)
+    # a file name with shell metacharacters is passed through intact (the reference would let the shell expand it)
+    weird = os.path.join(d, "in", 'we$(ird)`x`".mkv')
+    _fake_video(weird, frames[:2], rate="24/1")
+    r = _cli(*BASE, "render", "-i", weird, "-o", os.path.join(d, "out2"), "--ffmpegDir", tools, cwd=d)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert os.path.exists(os.path.join(d, "out2", 'we$(ird)`x`"(cunet_art)(noise0)(scale2).mp4'))
+
     # --nosuffix without -o writes next to the input with the new extension; missing engine => -1
     r = _cli(*BASE, "render", "-i", os.path.join(d, "in", "clip.mkv"), "--nosuffix", "--ffmpegDir", tools, "--tta", cwd=d)
     assert r.returncode == 0, r.stdout + r.stderr

@@ -251,3 +251,40 @@ def test_render_cfg3_tile400_tta(built_lib, models_dir):
     diff = np.abs(dst.astype(np.int32) - ref.astype(np.int32))
     assert (diff <= 1).mean() >= 0.999 and _psnr(dst, ref) >= 50, ((diff <= 1).mean(), diff.max())
     e.close()
+
+
+def test_pool_round_robin_keeps_frame_order(built_lib, models_dir):
+    """w2x_pool_*: frames sharded round-robin over the pool's engines (here the same GPU listed twice, so it runs on a one-GPU box;
+    tests/test_gpu_banded.py-style multi-GPU runs use distinct ids) and retired by ticket == frame number."""
+    import w2x
+    _, per = models_dir
+    _, path = per[2]
+    pool = w2x.Img2ImgPool([0, 0])
+    msgs = []
+    pool.setMessageCallback(lambda s, m: msgs.append((s, m)))
+    assert pool.build(path, w2x.BuildConfig.fixed(4, 64)), msgs
+    assert pool.load(path, w2x.RenderConfig(batchSize=4, height=64, width=64, scaling=2)), msgs
+    single, _, _ = _engine(models_dir, 2, 64, 4)
+    n, W, H = 11, 120, 80
+    frames = [tiling.synthetic_frame(W, H, 50 + s) for s in range(n)]
+    want = [single.render(f).copy() for f in frames]
+    pin_in = [w2x.PinnedArray((H, W, 3)) for _ in range(n)]
+    pin_out = [w2x.PinnedArray((2 * H, 2 * W, 3)) for _ in range(n)]
+    tickets = []
+    for f, pi, po in zip(frames, pin_in, pin_out):
+        pi.array[...] = f
+        tickets.append(pool.submit(pi.ptr, W, H, po.ptr))
+    assert tickets == list(range(n)), (tickets, msgs)
+    for t in reversed(tickets[:3]):      # any order is allowed ...
+        assert pool.wait(t)
+    for t in tickets[3:]:                # ... a writer asks in frame order
+        assert pool.wait(t)
+    for i in range(n):
+        assert np.array_equal(pin_out[i].array, want[i]), i
+    counts = pool.launch_counts()
+    assert len(counts) == 2 and all(c > 0 for c in counts)     # both engines took part: frames 0,2,4,.. and 1,3,5,..
+    assert not pool.wait(0)                                      # a ticket can be retired once
+    pool.close()
+    single.close()
+    for p in pin_in + pin_out:
+        p.free()

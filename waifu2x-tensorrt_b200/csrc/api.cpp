@@ -6,12 +6,14 @@
 #include <filesystem>
 
 #include "engine.h"
+#include "pool.h"
 #include "../../include/w2x_dev.h"
 
 using namespace w2x;
 
-struct w2x_engine {
-    Engine impl;
+struct w2x_pool {
+    EnginePool impl;
+    w2x_pool(const int* d, int n) : impl(d, n) {}
 };
 
 namespace {
@@ -91,12 +93,36 @@ int w2x_render_banded(w2x_engine* const* engines, int count, const uint8_t* src,
     return Engine::renderBanded(es, count, src, width, height, src_stride, dst, dst_stride) ? 1 : 0;
 }
 
+w2x_pool* w2x_pool_create(const int* device_ids, int count) {
+    try { return new w2x_pool(device_ids, count); } catch (...) { return nullptr; }
+}
+void w2x_pool_destroy(w2x_pool* p) { delete p; }
+int w2x_pool_size(w2x_pool* p) { return p ? p->impl.size() : 0; }
+w2x_engine* w2x_pool_engine(w2x_pool* p, int index) { return p ? p->impl.engine(index) : nullptr; }
+void w2x_pool_set_message_callback(w2x_pool* p, w2x_message_cb cb, void* user) { if (p) p->impl.setMessageCallback(cb, user); }
+int w2x_pool_build(w2x_pool* p, const char* onnx_path, const w2x_build_config* cfg) {
+    try { return p && onnx_path && cfg && p->impl.build(onnx_path, *cfg) ? 1 : 0; } catch (...) { return 0; }
+}
+int w2x_pool_load(w2x_pool* p, const char* onnx_path, const w2x_render_config* cfg) {
+    try { return p && onnx_path && cfg && p->impl.load(onnx_path, *cfg) ? 1 : 0; } catch (...) { return 0; }
+}
+int w2x_pool_submit(w2x_pool* p, const uint8_t* src, int width, int height, size_t src_stride, uint8_t* dst, size_t dst_stride) {
+    if (!p || !src || !dst) return -1;
+    try { return p->impl.submit(src, width, height, src_stride, dst, dst_stride); } catch (...) { return -1; }
+}
+int w2x_pool_wait(w2x_pool* p, int ticket) {
+    try { return p && p->impl.wait(ticket) ? 1 : 0; } catch (...) { return 0; }
+}
+int w2x_pool_sync(w2x_pool* p) {
+    try { return p && p->impl.sync() ? 1 : 0; } catch (...) { return 0; }
+}
+
 int w2x_wait(w2x_engine* e, int ticket) { return e && e->impl.wait(ticket) ? 1 : 0; }
 int w2x_sync(w2x_engine* e) { return e && e->impl.sync() ? 1 : 0; }
 
 void* w2x_host_alloc(size_t bytes) {
     void* p = nullptr;
-    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) return nullptr;
     return p;
 }
 void w2x_host_free(void* p) { if (p) cudaFreeHost(p); }

@@ -775,19 +775,19 @@ void Engine::renderOnStream(const uint8_t* dSrc, int w, int h, size_t srcPitch, 
             progCb(b + 1, batchCount, 1000.0 / std::max(ms, 1e-6), progUser);  // render.cpp:336-338
         }
     }
+    if (cfg.tta)
+        span(4, [&] {
+            launchTtaReduce(dTileOut, grid.count, outTile, dTtaMean, s);
+            ++launches;
+        });
     span(2, [&] {
         StitchParams sp{};
         sp.outT = outTile; sp.nx = grid.nx; sp.ny = grid.ny; sp.ovx = grid.outOvX; sp.ovy = grid.outOvY;
         sp.cw = w * scale; sp.ch = h * scale;
         sp.rampx = dRampX; sp.rampy = dRampY;
         sp.dst = dDst; sp.pitch = dstPitch;
-        if (cfg.tta) {
-            launchTtaReduce(dTileOut, grid.count, outTile, dTtaMean, s);
-            ++launches;
-            sp.tiles = dTtaMean; sp.f32 = 1;
-        } else {
-            sp.tiles = dTileOut; sp.f32 = 0;
-        }
+        sp.tiles = cfg.tta ? (const void*)dTtaMean : (const void*)dTileOut;
+        sp.f32 = cfg.tta ? 1 : 0;
         launchStitch(sp, s);
         ++launches;
     });
@@ -797,7 +797,7 @@ void Engine::renderOnStream(const uint8_t* dSrc, int w, int h, size_t srcPitch, 
 int Engine::lastStageMs(float* out, int n) {
     if (!stream) return 0;
     cudaStreamSynchronize(stream);
-    float acc[4] = {0, 0, 0, 0};
+    float acc[5] = {0, 0, 0, 0, 0};  // unpack, model, stitch, total, tta_reduce
     for (const auto& sp : spans) {
         float ms = 0;
         if (cudaEventElapsedTime(&ms, evPool[sp.e0], evPool[sp.e1]) == cudaSuccess) acc[sp.kind] += ms;
@@ -806,7 +806,7 @@ int Engine::lastStageMs(float* out, int n) {
         float ms = 0;
         if (cudaEventElapsedTime(&ms, evPool[spans.front().e0], evPool[spans.back().e1]) == cudaSuccess) acc[3] = ms;
     }
-    const int k = std::min(n, 4);
+    const int k = std::min(n, 5);
     for (int i = 0; i < k; ++i) out[i] = acc[i];
     return k;
 }
@@ -1191,7 +1191,9 @@ void runConvLayer(int device, int kind, int impl, int n, int h, int w, int cin, 
             launchConvHead(hp, nullptr);
         } else {
             plan = igemmCreatePlan(p);
-            igemmLaunch(plan, nullptr, nullptr);
+            // W2X_REPEAT (development build only): back-to-back launches, for steady-state clock / power readings of one layer
+            const int reps = devEnv("W2X_REPEAT") ? std::max(1, std::atoi(devEnv("W2X_REPEAT"))) : 1;
+            for (int r = 0; r < reps; ++r) igemmLaunch(plan, nullptr, nullptr);
         }
         W2X_CUDA(cudaDeviceSynchronize());
         W2X_CUDA(cudaGetLastError());

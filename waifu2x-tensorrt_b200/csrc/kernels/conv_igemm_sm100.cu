@@ -67,6 +67,7 @@ struct ConvArgs {
     int stages, cchunks, kblocks;
     uint32_t idesc, tmemCols, bytesA, bytesB, descHiA, descHiB;
     int useTma, nsub, nbuf, hasSkip;
+    int nAcc;  // TMEM accumulator buffers: 2, or 4 for the two-group epilogue (each group alternates between two of its own)
     int dbg;  // timing experiments only (W2X_DBG): 1 = epilogue skips math + staging, 2 = no output store, 4 = no MMAs, 16 = no activation loads
     uint32_t stageStride, wBytes, stagingBytes;
     int nSplit;
@@ -100,8 +101,9 @@ constexpr int kEpiThreads = 32 * kEpiWarps;
 constexpr int kPatchW = 10, kPatchH = 18;
 
 // header layout (byte offsets from the 1024-aligned smem base)
-constexpr uint32_t kOffFull = 0, kOffEmpty = 64, kOffTFull = 128, kOffTEmpty = 144, kOffSkip = 160, kOffW = 184, kOffRgbFull = 192, kOffRgbEmpty = 224,
-                   kOffSlot = 256, kOffBias = 1024;
+constexpr uint32_t kOffFull = 0, kOffEmpty = 64, kOffTFull = 128, kOffTEmpty = 160, kOffSkip = 192, kOffW = 216, kOffRgbFull = 224, kOffRgbEmpty = 256,
+                   kOffSlot = 288, kOffBias = 1024;
+constexpr int kMaxAcc = 4;         // TMEM accumulator buffers (barriers for four; nAcc = 2 or 4 per plan)
 constexpr int kRgbBufs = 4;        // fused first layer: RGB patches in flight
 constexpr int kFuseWarps = 6;      // fused first layer: producer warps, two 16-pixel blocks each (mma.sync is latency-bound per warp)
 
@@ -469,12 +471,12 @@ __device__ __forceinline__ void epilogueTmaGroups(const ConvArgs& a, uint32_t ba
     const bool leader = ((warp - 2) & 3) == 0 && lane == 0;
     const int m = quarter * 32 + lane;
     const int yy = m >> a.bwShift, xx = m & (a.bw - 1);
-    const uint32_t barTFull = base + kOffTFull + 8u * group, barTEmpty = base + kOffTEmpty + 8u * group;
     const uint32_t stg = base + a.headerBytes + (uint32_t)group * (uint32_t)a.nsub * 16384u;
     const uint32_t rowAddr = stg + (uint32_t)m * 128u;
     const uint32_t sw = (uint32_t)(m & 7);
     const uint32_t biasS = base + kOffBias;
-    const uint32_t taddr = tmemBase + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(group * a.bn);
+    const uint32_t taddrLane = tmemBase + ((uint32_t)(quarter * 32) << 16);
+    const bool fourAcc = a.nAcc == 4;  // tile k of the CTA uses accumulator k % nAcc: this group's j-th tile (k = 2j + group) -> group + 2 * (j & 1)
     const int nPairs = a.bn >> 6;  // 64 accumulator columns per round
     const int barId = 1 + group;
 
@@ -494,11 +496,14 @@ __device__ __forceinline__ void epilogueTmaGroups(const ConvArgs& a, uint32_t ba
     const int nGroup = nMine > group ? (nMine - group + 1) >> 1 : 0;  // tiles group, group + 2, ... of this CTA
     TileWalker w;
     w.init(first + group * step, 2 * step, a.tilesN, a.tilesX, a.tilesY);
-    uint32_t phase = 0;
     W2X_PROF_DECL(pWaitFull); W2X_PROF_DECL(pMath); W2X_PROF_DECL(pSync);
     W2X_PROF_T(pT0);
-    for (int j = 0; j < nGroup; ++j, w.next(), phase ^= 1u) {
+    for (int j = 0; j < nGroup; ++j, w.next()) {
         const TileCoord tc = w.coord(a.bh, a.bw, a.bn, nBase);
+        const int accIdx = fourAcc ? group + 2 * (j & 1) : group;
+        const uint32_t phase = (uint32_t)(fourAcc ? (j >> 1) : j) & 1u;
+        const uint32_t barTFull = base + kOffTFull + 8u * accIdx, barTEmpty = base + kOffTEmpty + 8u * accIdx;
+        const uint32_t taddr = taddrLane + (uint32_t)(accIdx * a.bn);
         W2X_PROF_T(ps0);
         if (leader) bulkWaitRead(0);  // this group's previous store (two tiles ago) has finished reading the staging buffer
         namedBarSync(barId, 128);
@@ -719,7 +724,7 @@ __device__ __forceinline__ void setupCommon(const ConvArgs& a, uint32_t base, ui
             mbarInit(base + kOffFull + 8u * s, fullArrivals);
             mbarInit(base + kOffEmpty + 8u * s, 1);
         }
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < kMaxAcc; ++i) {
             mbarInit(base + kOffTFull + 8u * i, 1);
             mbarInit(base + kOffTEmpty + 8u * i, accReaders);  // warps that must release an accumulator buffer
         }
@@ -787,27 +792,33 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
         }
     } else if (warp == 1) {
         // whole warp converged; one elected lane issues the MMAs and commits (keeps the issue loop on the uniform datapath)
+        // The issue thread's time between two MMAs is a bubble in the tensor pipe (its queue is shallow: measured, W2X_PROF), so the
+        // loop keeps everything but the MMAs themselves off that path: the NEXT K block's full barrier is probed (non-blocking)
+        // before this block's MMAs are queued, and the accumulator-full commit rides in the same elected section as the last MMAs.
         int stage = 0, acc = 0;
         uint32_t phase = 0, accPhase = 0;
         const int kSteps = a.kc / 16;
+        uint32_t fullOk = 0;
         for (int k = 0; k < nMine; ++k) {
             mbarWait(barTEmpty + 8u * acc, accPhase ^ 1u);
-            tcFenceAfter();
             const uint32_t tmemD = tmemBase + (uint32_t)(acc * a.bn);
             for (int kb = 0; kb < a.kblocks; ++kb) {
-                mbarWait(barFull + 8u * stage, phase);
+                if (!fullOk) mbarWait(barFull + 8u * stage, phase);
                 tcFenceAfter();
+                int nstage = stage + 1;
+                uint32_t nphase = phase;
+                if (nstage == a.stages) { nstage = 0; nphase ^= 1u; }
+                fullOk = mbarTest(barFull + 8u * nstage, nphase);
                 if (electOne()) {
                     const uint32_t aLo = descLo(stage0 + stage * stageBytes), bLo = descLo(stage0 + stage * stageBytes + a.bytesA);
                     for (int ks = 0; ks < kSteps; ++ks)
                         ummaLoHi(tmemD, aLo + 2u * ks, a.descHiA, bLo + 2u * ks, a.descHiB, a.idesc, (kb | ks) != 0 ? 1u : 0u);
                     tcCommit(barEmpty + 8u * stage);
+                    if (kb == a.kblocks - 1) tcCommit(barTFull + 8u * acc);
                 }
                 __syncwarp();
-                if (++stage == a.stages) { stage = 0; phase ^= 1u; }
+                stage = nstage; phase = nphase;
             }
-            if (electOne()) tcCommit(barTFull + 8u * acc);
-            __syncwarp();
             if (++acc == 2) { acc = 0; accPhase ^= 1u; }
         }
     } else {
@@ -901,10 +912,16 @@ __global__ void __launch_bounds__(kFused ? kThreads + 32 * kFuseWarps : kThreads
 #endif
         }
     } else if (warp == 1) {
+        // MMA issuer.  The tensor pipe's queue is shallow, so every cycle this thread spends between two MMAs is a bubble (measured
+        // with W2X_PROF: ~400 cycles per tile in the first version of this loop = 15 % of the layer).  Hence: the barriers of the NEXT
+        // patch / tile are probed with non-blocking test_wait while the current MMAs are being queued (the blocking waits then fall
+        // through), four accumulators make the accumulator-empty wait trivially true, and both commits ride in the elected section.
         int stage = 0, acc = 0;
         uint32_t phase = 0, accPhase = 0;
         mbarWait(barW, 0);
         const uint32_t bTapStep = ((uint32_t)a.cchunks * tapBytes) >> 4;  // descriptor-lo distance between consecutive taps of B
+        const int nAcc = a.nAcc;
+        uint32_t fullOk = 0, accOk = 0;
         W2X_PROF_DECL(pWaitAcc); W2X_PROF_DECL(pWaitFull); W2X_PROF_DECL(pIssue);
         W2X_PROF_T(pT0);
 #ifdef W2X_DEV
@@ -913,16 +930,24 @@ __global__ void __launch_bounds__(kFused ? kThreads + 32 * kFuseWarps : kThreads
 #endif
         for (int k = 0; k < nMine; ++k) {
             W2X_PROF_T(pa);
-            mbarWait(barTEmpty + 8u * acc, accPhase ^ 1u);
-            tcFenceAfter();
+            if (!accOk) mbarWait(barTEmpty + 8u * acc, accPhase ^ 1u);
             W2X_PROF_ADD(pWaitAcc, pa);
             const uint32_t tmemD = tmemBase + (uint32_t)(acc * a.bn);
+            int nacc = acc + 1;
+            uint32_t naccPhase = accPhase;
+            if (nacc == nAcc) { nacc = 0; naccPhase ^= 1u; }
             for (int cc = 0; cc < a.cchunks; ++cc) {
                 W2X_PROF_T(pb);
-                mbarWait(barFull + 8u * stage, phase);
+                if (!fullOk) mbarWait(barFull + 8u * stage, phase);
                 tcFenceAfter();
                 W2X_PROF_ADD(pWaitFull, pb);
                 W2X_PROF_T(pc);
+                int nstage = stage + 1;
+                uint32_t nphase = phase;
+                if (nstage == a.stages) { nstage = 0; nphase ^= 1u; }
+                fullOk = mbarTest(barFull + 8u * nstage, nphase);
+                const bool last = cc == a.cchunks - 1;
+                if (last) accOk = mbarTest(barTEmpty + 8u * nacc, naccPhase ^ 1u);
                 if (electOne()) {
                     // Nine taps = shifted views of the patch: whole pixel rows (kRowBytes each) into the swizzled tile.  The ky loop stays
                     // rolled on purpose: fully unrolled, the 36 precomputed descriptor pairs do not fit the uniform register file and the
@@ -947,14 +972,13 @@ __global__ void __launch_bounds__(kFused ? kThreads + 32 * kFuseWarps : kThreads
                         }
                     }
                     tcCommit(barEmpty + 8u * stage);
+                    if (last) tcCommit(barTFull + 8u * acc);
                 }
                 __syncwarp();
                 W2X_PROF_ADD(pIssue, pc);
-                if (++stage == a.stages) { stage = 0; phase ^= 1u; }
+                stage = nstage; phase = nphase;
             }
-            if (electOne()) tcCommit(barTFull + 8u * acc);
-            __syncwarp();
-            if (++acc == 2) { acc = 0; accPhase ^= 1u; }
+            acc = nacc; accPhase = naccPhase;
         }
 #ifdef W2X_DEV
         if (a.prof && lane == 0) {
@@ -1366,8 +1390,10 @@ void planPatch(IgemmPlan* plan) {
     const size_t fixed = 1024 + a.headerBytes + a.stagingBytes + a.wBytes;
     if (fixed + 2 * (size_t)a.stageStride > kSmemLimit) throw Error("conv3x3 patch kernel: weights do not fit in shared memory");
     a.stages = (int)std::min<size_t>(8, (kSmemLimit - fixed) / a.stageStride);
+    // the two-group epilogue (TMA store, two staging buffers) alternates between two accumulators per group: four in all
+    a.nAcc = (a.useTma && a.nbuf == 2 && 4 * a.bn <= 512) ? 4 : 2;
     uint32_t cols = 32;
-    while (cols < (uint32_t)(2 * a.bn)) cols *= 2;
+    while (cols < (uint32_t)(a.nAcc * a.bn)) cols *= 2;
     a.tmemCols = cols;
     a.idesc = instrDescF16(128, a.bn);
     const uint32_t rowBytes = a.kc * 2u, layout = sw128 ? 2u : 4u;
@@ -1442,6 +1468,7 @@ void planIgemm(IgemmPlan* plan) {
     }
     if (avail < a.stagingBytes + 2 * stageBytes) throw Error("igemm: tile does not fit in shared memory");
     a.stages = (int)std::min<size_t>(8, (avail - a.stagingBytes) / stageBytes);
+    a.nAcc = 2;
     uint32_t cols = 32;
     while (cols < (uint32_t)(2 * a.bn)) cols *= 2;
     a.tmemCols = cols;
@@ -1610,6 +1637,8 @@ void igemmLaunch(const IgemmPlan* plan, cudaStream_t s, __half* outOverride, int
     }
 #endif
     const bool grouped = a->useTma && !a->hasSkip && a->nbuf == 2 && a->bn <= 128 && !noGroups;
+    ConvArgs accLocal;
+    if (!grouped && a->nAcc != 2) { accLocal = *a; accLocal.nAcc = 2; a = &accLocal; }  // only the two-group epilogue handles four accumulators
     if (plan->patch) {
         if (a->kc == 64) {
             if (grouped) launchPdl(conv3x3_patch_kernel<EPI_K_TMA_GROUPS, 64>, dim3(plan->grid), dim3(kThreads), plan->smem, s, *a);

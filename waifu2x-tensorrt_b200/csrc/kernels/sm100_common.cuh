@@ -39,6 +39,22 @@ __device__ __forceinline__ void mbarWait(uint32_t bar, uint32_t parity) {
     } while (!done);
 }
 
+// non-blocking probe of a phase (mbarrier.test_wait never suspends): lets the MMA issuer look at the NEXT tile's barriers while
+// the current tile's MMAs are still being queued, so that the blocking wait at the top of the next tile normally falls through
+__device__ __forceinline__ uint32_t mbarTest(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return done;
+}
+
 // ---- TMA ----
 __device__ __forceinline__ void tmaPrefetchDesc(const CUtensorMap* tm) { asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory"); }
 __device__ __forceinline__ void tmaLoad5d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {

@@ -9,6 +9,7 @@
 #include <functional>
 #include <string>
 #include <utility>
+#include <vector>
 
 #include "../../include/w2x.h"
 
@@ -107,6 +108,41 @@ private:
     int scaling_ = 1;
     MessageCallback msg_;
     ProgressCallback prog_;
+};
+
+// Frame-parallel multi-GPU extension (w2x_pool_*, include/w2x.h): same build / load / submit / wait shape as Img2Img, one engine per
+// listed device, frame f -> devices[f % n].  The message callback may fire on the pool's worker threads.
+class Img2ImgPool {
+public:
+    explicit Img2ImgPool(const std::vector<int>& devices) : h_(w2x_pool_create(devices.data(), (int)devices.size())) {}
+    ~Img2ImgPool() { w2x_pool_destroy(h_); }
+    Img2ImgPool(const Img2ImgPool&) = delete;
+    Img2ImgPool& operator=(const Img2ImgPool&) = delete;
+    bool valid() const { return h_ != nullptr; }
+    bool build(const std::string& path, const BuildConfig& c) {
+        w2x_build_config b{c.deviceId, c.precision == Precision::FP16 ? W2X_PRECISION_FP16 : W2X_PRECISION_TF32,
+                           c.minBatchSize, c.optBatchSize, c.maxBatchSize, c.minChannels, c.optChannels, c.maxChannels,
+                           c.minWidth, c.optWidth, c.maxWidth, c.minHeight, c.optHeight, c.maxHeight};
+        return w2x_pool_build(h_, path.c_str(), &b) != 0;
+    }
+    bool load(const std::string& path, const RenderConfig& c) {
+        w2x_render_config r{c.deviceId, c.precision == Precision::FP16 ? W2X_PRECISION_FP16 : W2X_PRECISION_TF32,
+                            c.batchSize, c.channels, c.height, c.width, c.scaling, c.overlap.x, c.overlap.y, c.tta ? 1 : 0};
+        return w2x_pool_load(h_, path.c_str(), &r) != 0;
+    }
+    int submit(const unsigned char* srcBgr, int width, int height, size_t srcStride, unsigned char* dstBgr, size_t dstStride) {
+        return w2x_pool_submit(h_, srcBgr, width, height, srcStride, dstBgr, dstStride);
+    }
+    bool wait(int ticket) { return w2x_pool_wait(h_, ticket) != 0; }
+    void setMessageCallback(MessageCallback cb) {
+        msg_ = std::move(cb);
+        w2x_pool_set_message_callback(h_, msg_ ? &Img2ImgPool::onMessage : nullptr, this);
+    }
+
+private:
+    static void onMessage(int sev, const char* m, void* self) { static_cast<Img2ImgPool*>(self)->msg_(static_cast<Severity>(sev), m); }
+    w2x_pool* h_;
+    MessageCallback msg_;
 };
 
 }  // namespace trt

@@ -19,6 +19,7 @@
 #include <functional>
 #include <iostream>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <set>
 #include <string>
@@ -35,6 +36,7 @@ namespace {
 struct Options {
     std::string model;
     int scale = 0, noise = 0, batchSize = 0, tileSize = 0, deviceId = 0;
+    std::vector<int> deviceIds;  // extension: --device 0,1,2,... shards the frames of a render over several GPUs
     trt::Precision precision = trt::Precision::FP16;
     std::string command;  // "render" | "build"
     std::vector<fs::path> inputPaths;
@@ -60,7 +62,7 @@ const char* kUsage =
     "  --noise INT:{-1,0,1,2,3} REQUIRED\n"
     "  --batchSize INT:POSITIVE REQUIRED\n"
     "  --tileSize INT:{64,128,256,400,640} REQUIRED\n"
-    "  --device INT:NONNEGATIVE=0    Set the GPU device ID\n"
+    "  --device INT:NONNEGATIVE=0    Set the GPU device ID (extension: a comma-separated list shards frames over several GPUs)\n"
     "  --precision ENUM:{fp16,tf32}=fp16\n"
     "  --modelsDir TEXT=models       Directory holding <model>/[noiseN_][scaleSx].onnx\n\n"
     "Subcommands:\n"
@@ -116,7 +118,20 @@ Options parse(int argc, char** argv) {
         else if (a == "--noise") { o.noise = toInt(a, value()); requireMember(a, o.noise, {-1, 0, 1, 2, 3}); }
         else if (a == "--batchSize") { o.batchSize = toInt(a, value()); if (o.batchSize <= 0) throw ParseError(a + ": must be positive"); }
         else if (a == "--tileSize") { o.tileSize = toInt(a, value()); requireMember(a, o.tileSize, {64, 128, 256, 400, 640}); }
-        else if (a == "--device") { o.deviceId = toInt(a, value()); if (o.deviceId < 0) throw ParseError(a + ": must be non-negative"); }
+        else if (a == "--device") {
+            // the reference takes one id (main.cpp:70-74); a comma-separated list renders frame f on the (f mod n)-th listed GPU
+            std::string list = value();
+            o.deviceIds.clear();
+            size_t pos = 0;
+            while (pos <= list.size()) {
+                const size_t comma = std::min(list.find(',', pos), list.size());
+                const int id = toInt(a, list.substr(pos, comma - pos));
+                if (id < 0) throw ParseError(a + ": must be non-negative");
+                o.deviceIds.push_back(id);
+                pos = comma + 1;
+            }
+            o.deviceId = o.deviceIds.front();
+        }
         else if (a == "--precision") {
             std::string v = value();
             std::transform(v.begin(), v.end(), v.begin(), ::tolower);
@@ -255,14 +270,27 @@ int main(int argc, char* argv[]) {
     rc.scaling = o.scale;
     rc.overlap = {o.blend, o.blend};
     rc.tta = o.tta;
-    if (!engine.load(modelPath, rc)) return -1;
+    std::unique_ptr<trt::Img2ImgPool> pool;
+    if (o.deviceIds.size() > 1) {
+        pool = std::make_unique<trt::Img2ImgPool>(o.deviceIds);
+        if (!pool->valid()) { logLine(trt::Severity::error, "could not create the engine pool for --device list"); return -1; }
+        pool->setMessageCallback(logLine);
+        if (!pool->load(modelPath, rc)) return -1;
+    } else if (!engine.load(modelPath, rc)) {
+        return -1;
+    }
+    auto submitFrame = [&](const unsigned char* src, int w, int h, size_t ss, unsigned char* dst, size_t ds) {
+        return pool ? pool->submit(src, w, h, ss, dst, ds) : engine.submit(src, w, h, ss, dst, ds);
+    };
+    auto waitFrame = [&](int ticket) { return pool ? pool->wait(ticket) : engine.wait(ticket); };
 
     // Decode, GPU and encode are decoupled (the reference serialises them on one thread, main.cpp:263-269):
     // a reader thread fills a ring of pinned input frames from the ffmpeg pipe, this thread submits them to the engine (at most
     // three in flight, Engine::kSlots) and retires them in order, a writer thread drains finished frames into the encoder pipe.
-    constexpr int kRing = 6, kInFlight = 3;
+    const int nDev = (int)std::max<size_t>(o.deviceIds.size(), 1);
+    const int kInFlight = 3 * nDev, kRing = kInFlight + 3;  // three frames in flight per GPU + slack for the reader / writer threads
     enum SlotState { FREE, FILLED, SUBMITTED, DONE };
-    PinnedBuffer in[kRing], out[kRing];
+    std::vector<PinnedBuffer> in(kRing), out(kRing);
     VideoCapture capture;
     VideoWriter writer;
     capture.setFfmpegDir(o.ffmpegDir);
@@ -288,8 +316,7 @@ int main(int argc, char* argv[]) {
 
             std::mutex mu;
             std::condition_variable cv;
-            SlotState state[kRing];
-            for (auto& st : state) st = FREE;
+            std::vector<SlotState> state(kRing, FREE);
             size_t framesRead = frameCount;  // lowered by the reader if the pipe ends early
             bool abort = false;
             std::exception_ptr failure;
@@ -336,10 +363,10 @@ int main(int argc, char* argv[]) {
                     }
                 } catch (...) { fail(std::current_exception()); }
             });
-            int tickets[kRing];
+            std::vector<int> tickets(kRing);
             size_t submitted = 0, retired = 0;
             auto retire = [&]() {
-                if (!engine.wait(tickets[retired % kRing])) throw std::runtime_error("render failed");
+                if (!waitFrame(tickets[retired % kRing])) throw std::runtime_error("render failed");
                 setState(retired, DONE);
                 ++retired;
                 frameIndex++;
@@ -348,7 +375,7 @@ int main(int argc, char* argv[]) {
                 while (waitFor(submitted, FILLED)) {
                     if (submitted - retired >= (size_t)kInFlight) retire();
                     const int s = (int)(submitted % kRing);
-                    tickets[s] = engine.submit(in[s].p, inSize.width, inSize.height, (size_t)inSize.width * 3, out[s].p, (size_t)outSize.width * 3);
+                    tickets[s] = submitFrame(in[s].p, inSize.width, inSize.height, (size_t)inSize.width * 3, out[s].p, (size_t)outSize.width * 3);
                     if (tickets[s] < 0) throw std::runtime_error("render failed");
                     setState(submitted, SUBMITTED);
                     ++submitted;

@@ -101,6 +101,16 @@ _SIGNATURES = {
     "w2x_submit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_size_t]),
     "w2x_render_banded": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_size_t]),
     "w2x_wait": (C.c_int, [C.c_void_p, C.c_int]),
+    "w2x_pool_create": (C.c_void_p, [C.POINTER(C.c_int), C.c_int]),
+    "w2x_pool_destroy": (None, [C.c_void_p]),
+    "w2x_pool_size": (C.c_int, [C.c_void_p]),
+    "w2x_pool_engine": (C.c_void_p, [C.c_void_p, C.c_int]),
+    "w2x_pool_set_message_callback": (None, [C.c_void_p, MESSAGE_CB, C.c_void_p]),
+    "w2x_pool_build": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(_BuildConfig)]),
+    "w2x_pool_load": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(_RenderConfig)]),
+    "w2x_pool_submit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_size_t]),
+    "w2x_pool_wait": (C.c_int, [C.c_void_p, C.c_int]),
+    "w2x_pool_sync": (C.c_int, [C.c_void_p]),
     "w2x_sync": (C.c_int, [C.c_void_p]),
     "w2x_host_alloc": (C.c_void_p, [C.c_size_t]),
     "w2x_host_free": (None, [C.c_void_p]),
@@ -366,9 +376,14 @@ class Img2Img:
         return (self._l.w2x_last_error(self._h) or b"").decode(errors="replace")
 
     def last_stage_ms(self):
-        buf = (C.c_float * 4)()
-        n = self._l.w2x_last_stage_ms(self._h, buf, 4)
-        return dict(zip(["unpack", "model", "stitch", "total"], list(buf)[:n]))
+        buf = (C.c_float * 5)()
+        n = self._l.w2x_last_stage_ms(self._h, buf, 5)
+        return dict(zip(["unpack", "model", "stitch", "total", "tta_reduce"], list(buf)[:n]))
+
+    def render_into(self, src: np.ndarray, dst: np.ndarray) -> bool:
+        """w2x_render on caller-owned (pageable) arrays, no allocation: the literal drop-in call, used for timing."""
+        h, w = src.shape[:2]
+        return bool(self._l.w2x_render(self._h, _ptr(src), w, h, src.strides[0], _ptr(dst), dst.strides[0]))
 
     def timer_mark(self, idx: int, which: int = 0) -> bool:
         return bool(self._l.w2x_timer_mark(self._h, idx, which))
@@ -453,3 +468,55 @@ class PinnedArray:
 def model_path(models_dir: str, model: str, noise: int, scale: int) -> str:
     """models/<model>/[noiseN_][scaleSx].onnx, src/main.cpp:201-204 (trailing underscore for scale 1 kept)."""
     return os.path.join(models_dir, model, ("" if noise == -1 else f"noise{noise}_") + ("" if scale == 1 else f"scale{scale}x") + ".onnx")
+
+
+class Img2ImgPool:
+    """Frame-parallel multi-GPU rendering in one process (w2x_pool_*, include/w2x.h): frame f -> devices[f % len(devices)], one
+    worker thread + engine + weight replica per device, frames retired by ticket."""
+
+    def __init__(self, devices):
+        self._l = lib()
+        ids = (C.c_int * len(devices))(*devices)
+        self._h = self._l.w2x_pool_create(ids, len(devices))
+        if not self._h:
+            raise RuntimeError("w2x_pool_create failed")
+        self.devices = list(devices)
+        self.scaling = 1
+        self._msg_cb = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._l.w2x_pool_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def setMessageCallback(self, cb):
+        """cb may be called from the pool's worker threads."""
+        self._msg_cb = MESSAGE_CB(lambda sev, msg, user: cb(sev, msg.decode(errors="replace"))) if cb else MESSAGE_CB()
+        self._l.w2x_pool_set_message_callback(self._h, self._msg_cb, None)
+
+    def build(self, path: str, config: BuildConfig) -> bool:
+        return bool(self._l.w2x_pool_build(self._h, path.encode(), C.byref(config._c())))
+
+    def load(self, path: str, config: RenderConfig) -> bool:
+        ok = bool(self._l.w2x_pool_load(self._h, path.encode(), C.byref(config._c())))
+        if ok:
+            self.scaling = config.scaling
+        return ok
+
+    def submit(self, src_ptr: int, w: int, h: int, dst_ptr: int) -> int:
+        return int(self._l.w2x_pool_submit(self._h, C.c_void_p(src_ptr), w, h, w * 3, C.c_void_p(dst_ptr), w * self.scaling * 3))
+
+    def wait(self, ticket: int) -> bool:
+        return bool(self._l.w2x_pool_wait(self._h, ticket))
+
+    def sync(self) -> bool:
+        return bool(self._l.w2x_pool_sync(self._h))
+
+    def launch_counts(self):
+        return [int(self._l.w2x_launch_count(self._l.w2x_pool_engine(self._h, i))) for i in range(len(self.devices))]
