@@ -48,7 +48,11 @@ using namespace sm100;
 #define W2X_PROF_DECL(name) long long name = 0
 #define W2X_PROF_T(var) const long long var = clock64()
 #define W2X_PROF_ADD(acc, t0) acc += clock64() - (t0)
+// event trace of CTA 0 (first kTraceTiles tiles): prof[16 * grid + tile * 8 + slot] = clock64()
+constexpr int kTraceTiles = 24;
+#define W2X_TRACE(a, tile, slot) do { if ((a).prof && blockIdx.x == 0 && (tile) < kTraceTiles) (a).prof[16ll * gridDim.x + (tile) * 8 + (slot)] = clock64(); } while (0)
 #else
+#define W2X_TRACE(a, tile, slot)
 #define W2X_DBG_ON(a, bit) false
 #define W2X_PROF_DECL(name)
 #define W2X_PROF_T(var)
@@ -102,10 +106,13 @@ constexpr int kPatchW = 10, kPatchH = 18;
 
 // header layout (byte offsets from the 1024-aligned smem base)
 constexpr uint32_t kOffFull = 0, kOffEmpty = 64, kOffTFull = 128, kOffTEmpty = 160, kOffSkip = 192, kOffW = 216, kOffRgbFull = 224, kOffRgbEmpty = 256,
-                   kOffSlot = 288, kOffBias = 1024;
+                   kOffP1 = 288, kOffImFull = 312, kOffSlot = 336, kOffBias = 1024;
 constexpr int kMaxAcc = 4;         // TMEM accumulator buffers (barriers for four; nAcc = 2 or 4 per plan)
 constexpr int kRgbBufs = 4;        // fused first layer: RGB patches in flight
-constexpr int kFuseWarps = 6;      // fused first layer: producer warps, two 16-pixel blocks each (mma.sync is latency-bound per warp)
+constexpr int kFuseWarps = 4;      // fused first layer: producer warps, one per TMEM lane quarter
+constexpr int kFuseBufs = 3;       // fused first layer: im2col tiles / TMEM regions in flight.  The first-layer MMAs of tile k + 2 are queued
+                                   // before the main MMAs of tile k: the tensor pipe's queue holds about one tile of main MMAs, so a lead of
+                                   // one tile leaves the producer waiting for its accumulators (measured: 2080 instead of ~1330 cycles per tile)
 
 enum EpiKind { EPI_K_DIRECT = 0, EPI_K_TMA = 1, EPI_K_TMA_SKIP = 2, EPI_K_STAGED = 3, EPI_K_TMA_GROUPS = 4 };
 
@@ -522,6 +529,7 @@ __device__ __forceinline__ void epilogueTmaGroups(const ConvArgs& a, uint32_t ba
         W2X_PROF_T(pw0);
         mbarWait(barTFull, phase);
         tcFenceAfter();
+        if (leader) W2X_TRACE(a, 2 * j + group, 6);   // accumulator of tile 2j + group complete
         W2X_PROF_ADD(pWaitFull, pw0);
         W2X_PROF_T(pm0);
 #pragma unroll
@@ -593,129 +601,169 @@ __device__ __forceinline__ void epilogueTmaGroups(const ConvArgs& a, uint32_t ba
 }
 
 // ---- fused RGB first layer ---------------------------------------------------------------------------------------------
-// The 32-channel input of the second convolution of a UNet (conv1.conv.2) is itself conv3x3(RGB) + LeakyReLU: 36 MACs per value.
+// The 32-channel input of the second convolution of a UNet (conv1.conv.2) is itself conv3x3(RGB) + LeakyReLU: 27 MACs per value.
 // Instead of a separate kernel writing that tensor to HBM and TMA reading it back, four extra warps compute each tile's 18x10x32
-// patch from a 20x12 RGB patch (cp.async, double buffered) with mma.sync (M = 16 patch pixels, N = 32, K = 27 -> 32) and store it
-// in the exact layout a SWIZZLE_64B TMA box would have produced (16-byte chunk index ^= (pixel >> 1) & 3), then publish the
-// stage on the same full barrier the MMA warp waits on (generic-proxy writes + fence.proxy.async).  Saves, per output pixel of
-// the first layer, 64 B written + 64 B (x halo) read of HBM traffic and one kernel launch.
-__device__ __forceinline__ void fusedFirstProducer(const ConvArgs& a, uint32_t base, uint32_t stage0, int nMine, int first, int step) {
-    constexpr int kRgbW = kPatchW + 2, kRgbH = kPatchH + 2;  // 12 x 20 input pixels
-    const int tid = threadIdx.x - kThreads;                  // 0 .. 32 * kFuseWarps - 1
-    const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+// patch on the tensor cores as well: they gather a [180 (-> 2 x 128) patch pixels] x [K = 27 -> 32] im2col matrix from the 20x12
+// RGB patch (TMA-loaded, four deep) into shared memory in the SWIZZLE_64B operand layout, one elected thread issues four
+// tcgen05.mma (M = 128, N = 32, K = 16) into a private TMEM region, and the same warps read the accumulators back (tcgen05.ld),
+// add the bias, apply LeakyReLU and store fp16 into the patch ring slot in exactly the layout a SWIZZLE_64B TMA box would have
+// produced, then publish the slot on the full barrier the main MMA warp waits on (generic-proxy writes + fence.proxy.async).
+// Everything is double buffered (im2col tile, TMEM region) and software pipelined: the im2col + MMAs of tile k+1 are issued before
+// tile k is converted.  (The first version of this producer used mma.sync: 1475 cycles per tile, latency-bound and sharing the
+// tensor pipe with the main MMAs; this one costs ~4 x 43 pipe cycles per tile.)  Saves, per output pixel of the first layer, 64 B
+// written + 64 B (x halo) read of HBM traffic and one kernel launch.
+constexpr uint32_t kIm2colBytes = 2 * 128 * 64;   // two M = 128 blocks of 64-byte rows
+constexpr uint32_t kFuseExtraBytes = kRgbBufs * 2048u + kFuseBufs * kIm2colBytes + 2048u + 1024u;  // RGB ring | im2col tiles | W1 | bias1 (+ pad)
+constexpr int kFuseN = 32;         // first-layer output channels = N of its MMAs
+
+// half `i` (0..26) of a patch pixel's im2col row lives in source word (ky, 2 * kx + (c >> 1)), 16-bit half (c & 1)
+__device__ __forceinline__ constexpr int im2colWord(int i) { return (i / 9) * 6 + 2 * ((i % 9) / 3) + (((i % 9) % 3) >> 1); }
+__device__ __forceinline__ constexpr int im2colHalf(int i) { return ((i % 9) % 3) & 1; }
+
+__device__ __forceinline__ void fusedFirstProducer(const ConvArgs& a, uint32_t base, uint32_t stage0, uint32_t tmemBase, int nMine) {
+    constexpr int kRgbW = kPatchW + 2;                       // 12 x 20 input pixels per tile
+    constexpr int kRows = kPatchW * kPatchH;                 // 180 patch pixels
+    constexpr int kProdThreads = 32 * kFuseWarps;
+    const int tid = threadIdx.x - kThreads;                  // 0 .. 127
+    const int warp = tid >> 5, lane = tid & 31;
     const uint32_t barFull = base + kOffFull, barEmpty = base + kOffEmpty;
+    const uint32_t barRgbFull = base + kOffRgbFull, barRgbEmpty = base + kOffRgbEmpty, barP1 = base + kOffP1;
     const uint32_t rgb0 = base + a.fuseOff;
-    // K runs over k' = tap*3 + c (27 real values, padded to 32: two k-steps); the zero fourth channel of the NHWC4 input and of the
-    // packed [32][tap*4 + c] weights is skipped, which saves a third of the HMMAs (the legacy tensor path is this producer's bound)
-    constexpr int kKs = 2;
-    // B fragments and bias of the first layer (constants)
-    uint32_t bf[4][kKs][2];
-    float bias[4][2];
-    auto wHalf = [&](const __half* wrow, int kp) -> uint32_t {
-        return kp < 27 ? (uint32_t)__half_as_ushort(wrow[(kp / 3) * 4 + kp % 3]) : 0u;
-    };
+    const uint32_t im0 = rgb0 + kRgbBufs * 2048u;
+    const uint32_t w1s = im0 + kFuseBufs * kIm2colBytes;
+    const uint32_t bias1s = w1s + 2048u;
+    const uint32_t tmemP = tmemBase + (uint32_t)(a.nAcc * a.bn);   // kFuseBufs regions of 2 x 32 columns behind the main accumulators
+
+    // ---- constants of the loaded model: W1 as the B operand [32 rows n][32 halfs k'] (k' = tap * 3 + c, zero beyond 27), bias
+    {
+        const int n = tid >> 2, q = tid & 3;                 // one 16-byte chunk (8 halfs) per thread
+        const __half* wrow = a.fuseW + n * 36;               // packed [32][tap * 4 + c]
+        uint32_t wv[4];
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
-        const __half* wrow = a.fuseW + (8 * nt + g) * 36;
-#pragma unroll
-        for (int ks = 0; ks < kKs; ++ks) {
-            const int k0 = 16 * ks + 2 * t;
-            bf[nt][ks][0] = wHalf(wrow, k0) | (wHalf(wrow, k0 + 1) << 16);
-            bf[nt][ks][1] = wHalf(wrow, k0 + 8) | (wHalf(wrow, k0 + 9) << 16);
+        for (int j = 0; j < 4; ++j) {
+            const int k0 = 8 * q + 2 * j, k1 = k0 + 1;
+            const uint32_t lo = k0 < 27 ? (uint32_t)__half_as_ushort(wrow[(k0 / 3) * 4 + k0 % 3]) : 0u;
+            const uint32_t hi = k1 < 27 ? (uint32_t)__half_as_ushort(wrow[(k1 / 3) * 4 + k1 % 3]) : 0u;
+            wv[j] = lo | (hi << 16);
         }
-        bias[nt][0] = a.fuseBias[8 * nt + 2 * t];
-        bias[nt][1] = a.fuseBias[8 * nt + 2 * t + 1];
+        stsV4(w1s + (uint32_t)n * 64u + ((uint32_t)(q ^ ((n >> 1) & 3)) << 4), make_uint4(wv[0], wv[1], wv[2], wv[3]));
+        if (tid < 32) {
+            const float bv = a.fuseBias[tid];
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias1s + 4u * tid), "f"(bv) : "memory");
+        }
+        fenceProxyAsync();
     }
-    // A fragment addressing: register (ks, h) of a lane holds k' = 16ks + 2t + 8h and k' + 1 of its pixel row.  The two halves are not
-    // adjacent in the NHWC4 patch in general, so each register is a byte permute of two aligned 32-bit loads.
-    uint32_t aOffA[kKs][2], aOffB[kKs][2], aSel[kKs][2];
-    auto halfOff = [&](int kp) -> int {  // offset (in halfs, from the pixel's patch position) of element k'
-        const int tap = kp / 3;
-        return kp < 27 ? ((tap / 3) * kRgbW + tap % 3) * 4 + kp % 3 : 0;
-    };
-#pragma unroll
-    for (int ks = 0; ks < kKs; ++ks)
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int k0 = 16 * ks + 2 * t + 8 * h;
-            const int ha = halfOff(k0), hb = halfOff(k0 + 1);
-            aOffA[ks][h] = (uint32_t)((ha & ~1) * 2);
-            aOffB[ks][h] = (uint32_t)((hb & ~1) * 2);
-            const uint32_t sa = 2u * (uint32_t)(ha & 1), sb = 4u + 2u * (uint32_t)(hb & 1);
-            aSel[ks][h] = sa | ((sa + 1u) << 4) | (sb << 8) | ((sb + 1u) << 12);
-        }
     pdlWait();  // weights / bias above are constants; the RGB tiles come from the preceding kernel
 
-    // RGB patches arrive by TMA (issued by warp 0, kRgbBufs tiles deep): nothing of this warp's own is in flight when it fences
-    const uint32_t barRgbFull = base + kOffRgbFull, barRgbEmpty = base + kOffRgbEmpty;
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int k = 0; k < nMine; ++k) {
+    const int quarter = (threadIdx.x >> 5) & 3;              // TMEM lane quarter this warp may read: its index in the CTA modulo 4
+
+    // im2col of tile k into buffer k % kFuseBufs (the main MMA warp issues its MMAs: fusedFirstIssue)
+    auto stageTile = [&](int k) {
         const int rb = k % kRgbBufs;
         mbarWait(barRgbFull + 8u * rb, (uint32_t)(k / kRgbBufs) & 1u);
         const uint32_t rgb = rgb0 + (uint32_t)rb * 2048u;
-        const uint32_t dst = stage0 + (uint32_t)stage * a.stageStride;
-        mbarWait(barEmpty + 8u * stage, phase ^ 1u);  // the MMAs that read this ring slot have completed
-        constexpr int kBlk = 12 / kFuseWarps;
-        static_assert((kPatchW * kPatchH + 15) / 16 == kBlk * kFuseWarps, "whole 16-pixel blocks per producer warp");
-        // this warp's blocks b = warp, warp + kFuseWarps, ... advance together so that their load -> MMA -> pack chains overlap
-        uint32_t r0[kBlk], r1[kBlk];
-        float d[kBlk][4][4];
+        const uint32_t im = im0 + (uint32_t)(k % kFuseBufs) * kIm2colBytes;
 #pragma unroll
-        for (int bi = 0; bi < kBlk; ++bi) {
-            const int p0 = 16 * (warp + kFuseWarps * bi) + g, p1 = p0 + 8;
-            const int q0 = min(p0, kPatchW * kPatchH - 1), q1 = min(p1, kPatchW * kPatchH - 1);
-            r0[bi] = rgb + (uint32_t)(((q0 / kPatchW) * kRgbW + q0 % kPatchW) * 8);
-            r1[bi] = rgb + (uint32_t)(((q1 / kPatchW) * kRgbW + q1 % kPatchW) * 8);
+        for (int rr = 0; rr < 2; ++rr) {
+            const int prow = tid + rr * kProdThreads;
+            if (prow < kRows) {
+                const int py = prow / kPatchW, px = prow - py * kPatchW;
+                uint32_t w[18];
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt) { d[bi][nt][0] = bias[nt][0]; d[bi][nt][1] = bias[nt][1]; d[bi][nt][2] = bias[nt][0]; d[bi][nt][3] = bias[nt][1]; }
+                for (int ky = 0; ky < 3; ++ky) {
+                    const uint32_t src = rgb + (uint32_t)(((py + ky) * kRgbW + px) * 8);
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx)
+                        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(w[ky * 6 + 2 * kx]), "=r"(w[ky * 6 + 2 * kx + 1]) : "r"(src + 8u * kx));
+                }
+                uint32_t o[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int i0 = 2 * j, i1 = 2 * j + 1;
+                    if (i0 >= 27) { o[j] = 0u; continue; }
+                    const uint32_t wa = w[im2colWord(i0)];
+                    const uint32_t wb = i1 < 27 ? w[im2colWord(i1 < 27 ? i1 : 0)] : 0u;
+                    const uint32_t sel = (im2colHalf(i0) ? 0x32u : 0x10u) | ((i1 < 27 ? (im2colHalf(i1 < 27 ? i1 : 0) ? 0x76u : 0x54u) : 0x54u) << 8);
+                    o[j] = __byte_perm(wa, wb, sel);
+                }
+                const uint32_t rowAddr = im + (uint32_t)prow * 64u;
+                const uint32_t sw = (uint32_t)(prow >> 1) & 3u;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) stsV4(rowAddr + (((uint32_t)q ^ sw) << 4), make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]));
+            }
         }
+        fenceProxyAsync();   // generic-proxy stores -> visible to the tensor core's async-proxy operand reads
+        tcFenceBefore();     // this thread's earlier tcgen05.ld of the TMEM buffer that the MMAs of this tile will overwrite
+        __syncwarp();
+        if (lane == 0) {
+            mbarArrive(barRgbEmpty + 8u * rb);                 // this warp has read everything it needs from the RGB patch
+            mbarArrive(base + kOffImFull + 8u * (k % kFuseBufs));  // the main MMA warp issues this tile's four first-layer MMAs
+        }
+    };
+
+    int stage = 0;
+    uint32_t phase = 0;
+    W2X_PROF_DECL(pStage); W2X_PROF_DECL(pWaitP1); W2X_PROF_DECL(pWaitSlot); W2X_PROF_DECL(pConv);
+    W2X_PROF_T(pT0);
+    for (int k = 0; k < kFuseBufs - 1 && k < nMine; ++k) stageTile(k);
+    for (int k = 0; k < nMine; ++k) {
+        W2X_PROF_T(pq0);
+        if (k + kFuseBufs - 1 < nMine) stageTile(k + kFuseBufs - 1);   // its buffer was tile k - 1's: those MMAs completed before convert(k - 1)
+        W2X_PROF_ADD(pStage, pq0);
+        const int fb = k % kFuseBufs;
+        const uint32_t fphase = (uint32_t)(k / kFuseBufs) & 1u;
+        // ---- convert tile k: TMEM -> bias + LeakyReLU -> fp16 -> ring slot (SWIZZLE_64B placement: chunk c of pixel row p at c ^ ((p >> 1) & 3))
+        W2X_PROF_T(pq1);
+        if (tid == 0) W2X_TRACE(a, k, 3);       // producer starts waiting for the first-layer accumulators of tile k
+        mbarWait(barP1 + 8u * fb, fphase);
+        tcFenceAfter();
+        if (tid == 0) W2X_TRACE(a, k, 4);       // ... has them
+        W2X_PROF_ADD(pWaitP1, pq1);
+        W2X_PROF_T(pq2);
+        mbarWait(barEmpty + 8u * stage, phase ^ 1u);  // the MMAs that read this ring slot have completed
+        W2X_PROF_ADD(pWaitSlot, pq2);
+        W2X_PROF_T(pq3);
+        const uint32_t dst = stage0 + (uint32_t)stage * a.stageStride;
 #pragma unroll
-        for (int ks = 0; ks < kKs; ++ks) {
-            uint32_t af[kBlk][4];
+        for (int mb = 0; mb < 2; ++mb) {
+            if (mb == 1 && quarter >= 2) break;       // rows 192.. do not exist (180 patch pixels): the whole warp skips
+            const int prow = mb * 128 + quarter * 32 + lane;
+            uint32_t r[32];
+            tmemLd32(tmemP + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(fb * 2 * kFuseN + mb * kFuseN), r);
+            tmemLdWait();
+            if (prow < kRows) {
+                const uint32_t rowAddr = dst + (uint32_t)prow * 64u;
+                const uint32_t sw = (uint32_t)(prow >> 1) & 3u;
 #pragma unroll
-            for (int bi = 0; bi < kBlk; ++bi) {
+                for (int q = 0; q < 4; ++q) {
+                    const uint4 b0 = ldsV4(bias1s + 32u * q), b1 = ldsV4(bias1s + 32u * q + 16u);
+                    const float bias[8] = {__uint_as_float(b0.x), __uint_as_float(b0.y), __uint_as_float(b0.z), __uint_as_float(b0.w),
+                                           __uint_as_float(b1.x), __uint_as_float(b1.y), __uint_as_float(b1.z), __uint_as_float(b1.w)};
+                    uint4 ov;
+                    __half2* oh = reinterpret_cast<__half2*>(&ov);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {  // a0: (row g, k' low), a1: (row g + 8, k' low), a2 / a3: the same rows, k' + 8
-                    const uint32_t rowBase = (q & 1) ? r1[bi] : r0[bi];
-                    const int h = q >> 1;
-                    uint32_t wa, wb;
-                    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(wa) : "r"(rowBase + aOffA[ks][h]));
-                    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(wb) : "r"(rowBase + aOffB[ks][h]));
-                    af[bi][q] = __byte_perm(wa, wb, aSel[ks][h]);
+                    for (int i = 0; i < 4; ++i) {
+                        const float t0 = __uint_as_float(r[8 * q + 2 * i]) + bias[2 * i], t1 = __uint_as_float(r[8 * q + 2 * i + 1]) + bias[2 * i + 1];
+                        oh[i] = __floats2half2_rn(fmaxf(t0, t0 * a.fuseSlope), fmaxf(t1, t1 * a.fuseSlope));
+                    }
+                    stsV4(rowAddr + (((uint32_t)q ^ sw) << 4), ov);
                 }
             }
-#pragma unroll
-            for (int bi = 0; bi < kBlk; ++bi)
-#pragma unroll
-                for (int nt = 0; nt < 4; ++nt)
-                    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                                 : "+f"(d[bi][nt][0]), "+f"(d[bi][nt][1]), "+f"(d[bi][nt][2]), "+f"(d[bi][nt][3])
-                                 : "r"(af[bi][0]), "r"(af[bi][1]), "r"(af[bi][2]), "r"(af[bi][3]), "r"(bf[nt][ks][0]), "r"(bf[nt][ks][1]));
         }
-        __syncwarp();
-        if (lane == 0) mbarArrive(barRgbEmpty + 8u * rb);  // this warp has read everything it needs from the RGB patch
-        // LeakyReLU, fp16, SWIZZLE_64B placement: pixel row p is 64 bytes, chunk (8 channels) nt lands at nt ^ ((p >> 1) & 3)
-#pragma unroll
-        for (int bi = 0; bi < kBlk; ++bi) {
-            const int p0 = 16 * (warp + kFuseWarps * bi) + g, p1 = p0 + 8;
-#pragma unroll
-            for (int nt = 0; nt < 4; ++nt) {
-                const __half2 lo = __floats2half2_rn(fmaxf(d[bi][nt][0], d[bi][nt][0] * a.fuseSlope), fmaxf(d[bi][nt][1], d[bi][nt][1] * a.fuseSlope));
-                const __half2 hi = __floats2half2_rn(fmaxf(d[bi][nt][2], d[bi][nt][2] * a.fuseSlope), fmaxf(d[bi][nt][3], d[bi][nt][3] * a.fuseSlope));
-                if (p0 < kPatchW * kPatchH)
-                    asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst + (uint32_t)p0 * 64u + ((uint32_t)(nt ^ ((p0 >> 1) & 3)) << 4) + 4u * t),
-                                 "r"(*reinterpret_cast<const uint32_t*>(&lo)) : "memory");
-                if (p1 < kPatchW * kPatchH)
-                    asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst + (uint32_t)p1 * 64u + ((uint32_t)(nt ^ ((p1 >> 1) & 3)) << 4) + 4u * t),
-                                 "r"(*reinterpret_cast<const uint32_t*>(&hi)) : "memory");
-            }
-        }
+        tcFenceBefore();
         fenceProxyAsync();  // generic-proxy stores above -> visible to the tensor core's async-proxy reads
         __syncwarp();
         if (lane == 0) mbarArrive(barFull + 8u * stage);
+        if (tid == 0) W2X_TRACE(a, k, 5);       // patch of tile k published
+        W2X_PROF_ADD(pConv, pq3);
         if (++stage == a.stages) { stage = 0; phase ^= 1u; }
     }
+#ifdef W2X_DEV
+    if (a.prof && tid == 0) {
+        long long* pr = a.prof + 16ll * blockIdx.x;
+        pr[12] = clock64() - pT0; pr[13] = pStage; pr[14] = pWaitP1; pr[15] = pConv; pr[5] = pWaitSlot;
+    }
+#endif
 }
 
 __device__ __forceinline__ void setupCommon(const ConvArgs& a, uint32_t base, uint8_t* sm, int warp, int accReaders, int fullArrivals = 1) {
@@ -733,6 +781,10 @@ __device__ __forceinline__ void setupCommon(const ConvArgs& a, uint32_t base, ui
         for (int i = 0; i < kRgbBufs; ++i) {
             mbarInit(base + kOffRgbFull + 8u * i, 1);
             mbarInit(base + kOffRgbEmpty + 8u * i, kFuseWarps);  // the producer warps of the fused first layer
+        }
+        for (int i = 0; i < kFuseBufs; ++i) {
+            mbarInit(base + kOffP1 + 8u * i, 1);              // fused first layer: its MMAs into TMEM buffer i have completed
+            mbarInit(base + kOffImFull + 8u * i, kFuseWarps);  // fused first layer: im2col tile i is written (one arrival per producer warp)
         }
         mbarInitFence();
         tmaPrefetchDesc(&a.tmA);
@@ -868,7 +920,7 @@ __global__ void __launch_bounds__(kFused ? kThreads + 32 * kFuseWarps : kThreads
     pdlWait();  // the input activation (and the output buffer's previous readers) belong to earlier kernels
 
     if (kFused && warp >= kThreads / 32) {
-        fusedFirstProducer(a, base, stage0, nMine, first, step);
+        fusedFirstProducer(a, base, stage0, tmemBase, nMine);
     } else if (warp == 0 && kFused) {
         if (lane == 0) {
             // RGB patch loader: 20 rows x 12 pixels x 4 channels per tile, kRgbBufs tiles ahead of the producer warps
@@ -922,6 +974,33 @@ __global__ void __launch_bounds__(kFused ? kThreads + 32 * kFuseWarps : kThreads
         const uint32_t bTapStep = ((uint32_t)a.cchunks * tapBytes) >> 4;  // descriptor-lo distance between consecutive taps of B
         const int nAcc = a.nAcc;
         uint32_t fullOk = 0, accOk = 0;
+        // fused first layer: this warp also issues the producer's four M = 128, N = 32 MMAs per tile, one tile ahead of the main MMAs
+        // (a second issuing thread would only queue behind this one: the pipe is shared)
+        auto fusedFirstIssue = [&](int k) {
+            const int fb = k % kFuseBufs;
+            const uint32_t im = base + a.fuseOff + kRgbBufs * 2048u + (uint32_t)fb * kIm2colBytes;
+            mbarWait(base + kOffImFull + 8u * fb, (uint32_t)(k / kFuseBufs) & 1u);
+            tcFenceAfter();
+            if (lane == 0) W2X_TRACE(a, k, 0);   // first-layer MMAs of tile k issued
+            if (electOne()) {
+                const uint32_t tD = tmemBase + (uint32_t)(a.nAcc * a.bn) + (uint32_t)(fb * 2 * kFuseN);
+                const uint32_t bLo = descLo(base + a.fuseOff + kRgbBufs * 2048u + kFuseBufs * kIm2colBytes);
+                const uint32_t hi64 = descHi(512u, 4u);       // SWIZZLE_64B, 8-row groups 512 bytes apart
+                const uint32_t idesc1 = instrDescF16(128, kFuseN);
+#pragma unroll
+                for (int mb = 0; mb < 2; ++mb) {
+                    const uint32_t aLo = descLo(im + (uint32_t)mb * 8192u);
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks)
+                        if (!W2X_DBG_ON(a, 32)) ummaLoHi(tD + (uint32_t)kFuseN * mb, aLo + 2u * ks, hi64, bLo + 2u * ks, hi64, idesc1, ks ? 1u : 0u);
+                }
+                tcCommit(base + kOffP1 + 8u * fb);
+            }
+            __syncwarp();
+            if (lane == 0) W2X_TRACE(a, k, 7);   // first-layer MMAs of tile k: issue done
+        };
+        if (kFused)
+            for (int k = 0; k < kFuseBufs - 1 && k < nMine; ++k) fusedFirstIssue(k);
         W2X_PROF_DECL(pWaitAcc); W2X_PROF_DECL(pWaitFull); W2X_PROF_DECL(pIssue);
         W2X_PROF_T(pT0);
 #ifdef W2X_DEV
@@ -929,6 +1008,7 @@ __global__ void __launch_bounds__(kFused ? kThreads + 32 * kFuseWarps : kThreads
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt0));
 #endif
         for (int k = 0; k < nMine; ++k) {
+            if (kFused && k + kFuseBufs - 1 < nMine) fusedFirstIssue(k + kFuseBufs - 1);
             W2X_PROF_T(pa);
             if (!accOk) mbarWait(barTEmpty + 8u * acc, accPhase ^ 1u);
             W2X_PROF_ADD(pWaitAcc, pa);
@@ -942,6 +1022,7 @@ __global__ void __launch_bounds__(kFused ? kThreads + 32 * kFuseWarps : kThreads
                 tcFenceAfter();
                 W2X_PROF_ADD(pWaitFull, pb);
                 W2X_PROF_T(pc);
+                if (lane == 0) W2X_TRACE(a, k, 1);   // main MMAs of tile k: issue starts
                 int nstage = stage + 1;
                 uint32_t nphase = phase;
                 if (nstage == a.stages) { nstage = 0; nphase ^= 1u; }
@@ -976,6 +1057,7 @@ __global__ void __launch_bounds__(kFused ? kThreads + 32 * kFuseWarps : kThreads
                 }
                 __syncwarp();
                 W2X_PROF_ADD(pIssue, pc);
+                if (lane == 0) W2X_TRACE(a, k, 2);   // main MMAs of tile k: issue done
                 stage = nstage; phase = nphase;
             }
             acc = nacc; accPhase = naccPhase;
@@ -1547,11 +1629,17 @@ IgemmPlan* igemmCreatePlanFusedFirst(const ConvParams& second, const ConvParams&
     if (!igemmFusedFirstSupported(second, first)) throw Error("igemm: layer pair cannot be fused");
     IgemmPlan* plan = igemmCreatePlan(second);
     ConvArgs& a = plan->args;
-    if (!plan->patch || a.kc != 32 || !a.useTma || a.nbuf != 2 || plan->smem + 8192 > kSmemLimit) {
+    while (a.stages > 3 && (a.stages > 6 || plan->smem + kFuseExtraBytes > kSmemLimit)) {  // the producer stays two tiles ahead: six ring slots are plenty
+        --a.stages;
+        plan->smem -= a.stageStride;
+    }
+    if (!plan->patch || a.kc != 32 || !a.useTma || a.nbuf != 2 || plan->smem + kFuseExtraBytes > kSmemLimit) {
         igemmDestroyPlan(plan);
         throw Error("igemm: fused first layer does not fit this plan");
     }
     a.fused = 1;
+    a.nAcc = 2;                                        // TMEM: 2 x 64 accumulator columns + kFuseBufs x 64 for the producer's first-layer tiles
+    a.tmemCols = 512;
     a.fuseIn = first.in;
     a.fuseW = first.w;
     a.fuseBias = first.bias;
@@ -1576,7 +1664,7 @@ IgemmPlan* igemmCreatePlanFusedFirst(const ConvParams& second, const ConvParams&
             throw Error("cuTensorMapEncodeTiled(rgb) failed with code " + std::to_string((int)r));
         }
     }
-    plan->smem += 8192;  // four RGB patch buffers
+    plan->smem += kFuseExtraBytes;  // RGB patch ring, two im2col tiles, first-layer weights + bias
     return plan;
 }
 
@@ -1630,9 +1718,9 @@ void igemmLaunch(const IgemmPlan* plan, cudaStream_t s, __half* outOverride, int
     static const bool profOn = devEnv("W2X_PROF") != nullptr;
     long long* profBuf = nullptr;
     ConvArgs profLocal;
-    if (profOn && plan->patch && !a->fused) {
-        checkCuda(cudaMalloc(&profBuf, sizeof(long long) * 16 * plan->grid));
-        checkCuda(cudaMemsetAsync(profBuf, 0, sizeof(long long) * 16 * plan->grid, s));
+    if (profOn && plan->patch) {
+        checkCuda(cudaMalloc(&profBuf, sizeof(long long) * (16 * plan->grid + 8 * kTraceTiles)));
+        checkCuda(cudaMemsetAsync(profBuf, 0, sizeof(long long) * (16 * plan->grid + 8 * kTraceTiles), s));
         profLocal = *a; profLocal.prof = profBuf; a = &profLocal;
     }
 #endif
@@ -1661,7 +1749,7 @@ void igemmLaunch(const IgemmPlan* plan, cudaStream_t s, __half* outOverride, int
 #ifdef W2X_DEV
     if (profBuf) {
         checkCuda(cudaStreamSynchronize(s));
-        std::vector<long long> h(16 * (size_t)plan->grid);
+        std::vector<long long> h(16 * (size_t)plan->grid + 8 * kTraceTiles);
         checkCuda(cudaMemcpy(h.data(), profBuf, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
         cudaFree(profBuf);
         double sum[16] = {0};
@@ -1676,6 +1764,17 @@ void igemmLaunch(const IgemmPlan* plan, cudaStream_t s, __half* outOverride, int
                      "producer: total %.0f waitEmpty %.0f | epi g0: total %.0f waitTFull %.0f math %.0f sync+store %.0f\n",
                      a->p.cin, a->p.npad, a->p.gx, a->p.gy, a->p.gn, tiles, sum[0] / g, maxTotal, sum[1] / g, sum[2] / g, sum[3] / g, sum[0] / g / std::max(mmas, 1.0),
                      sum[11] > 0 ? sum[0] / sum[11] : 0.0, sum[4] / g, sum[5] / g, sum[6] / g, sum[7] / g, sum[8] / g, sum[9] / g);
+        if (a->fused && devEnv("W2X_TRACE")) {
+            const long long* tr = h.data() + 16 * (size_t)plan->grid;
+            long long t0 = tr[0];
+            std::fprintf(stderr, "[w2x trace] CTA 0, cycles since the first event: tile | L1 issued | main issue start | main issue end | producer waits P1 | has P1 | patch published | acc complete\n");
+            for (int t = 0; t < kTraceTiles; ++t)
+                std::fprintf(stderr, "[w2x trace] %2d | %7lld (done %7lld) | %7lld | %7lld | %7lld | %7lld | %7lld | %7lld\n", t, tr[t * 8 + 0] - t0, tr[t * 8 + 7] - t0, tr[t * 8 + 1] - t0, tr[t * 8 + 2] - t0,
+                             tr[t * 8 + 3] - t0, tr[t * 8 + 4] - t0, tr[t * 8 + 5] - t0, tr[t * 8 + 6] - t0);
+        }
+        if (a->fused)
+            std::fprintf(stderr, "[w2x prof]   first-layer producer: total %.0f = im2col %.0f + wait P1 %.0f + wait slot %.0f + convert %.0f  (per tile %.0f / %.0f / %.0f / %.0f)\n", sum[12] / g,
+                         sum[13] / g, sum[14] / g, sum[5] / g, sum[15] / g, sum[13] / g / std::max(tiles, 1.0), sum[14] / g / std::max(tiles, 1.0), sum[5] / g / std::max(tiles, 1.0), sum[15] / g / std::max(tiles, 1.0));
     }
 #endif
 }

@@ -55,6 +55,12 @@ __device__ __forceinline__ uint32_t mbarTest(uint32_t bar, uint32_t parity) {
     return done;
 }
 
+// spin on test_wait: for short hand-offs between two roles that are nearly in step (try_wait may park the thread and its wake-up
+// latency then dominates the hand-off)
+__device__ __forceinline__ void mbarSpin(uint32_t bar, uint32_t parity) {
+    while (!mbarTest(bar, parity)) {}
+}
+
 // ---- TMA ----
 __device__ __forceinline__ void tmaPrefetchDesc(const CUtensorMap* tm) { asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory"); }
 __device__ __forceinline__ void tmaLoad5d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {

@@ -222,27 +222,16 @@ __global__ void __launch_bounds__(kSW) stitch_kernel(StitchParams p, int vecOk) 
     // a pixel covered by one tile with unit weights (85 % of the canvas at blend 1/16): x 1.0 and 0 + x are exact, so the
     // multiplies and the accumulate can be skipped without changing a bit
     const bool plainX = ni == 1 && wls[0] == 1.f && wrs[0] == 1.f;
-    // pass 1: the single-tile pixels of this column (the common case) issue all their loads back to back -- kSR independent
-    // 8 / 16-byte reads in flight per thread instead of one at a time (the kernel is latency-bound otherwise)
-    float vr[kSR], vg[kSR], vb[kSR];
-    unsigned plainMask = 0;
-#pragma unroll
+#pragma unroll 2
     for (int row = 0; row < kSR; ++row) {
         const StitchRow& ri = rowInfo[row];   // shared-memory broadcast reads
-        vr[row] = vg[row] = vb[row] = 0.f;
-        if (live && plainX && ri.n == 1 && ri.wt[0] == 1.f && ri.wb[0] == 1.f) {
-            const int slot = p.tile_map ? __ldg(p.tile_map + ti[0] * p.ny + ri.j[0]) : ti[0] * p.ny + ri.j[0];
-            loadTilePx<F32>(p.tiles, ((size_t)slot * p.outT + ri.ly[0]) * p.outT + lxs[0], vr[row], vg[row], vb[row]);
-            plainMask |= 1u << row;
-        }
-    }
-#pragma unroll
-    for (int row = 0; row < kSR; ++row) {
-        const StitchRow& ri = rowInfo[row];
         const int rn = ri.n;
         if (!live || rn == 0) continue;
-        float accr = vr[row], accg = vg[row], accb = vb[row];
-        if (!((plainMask >> row) & 1u)) {
+        float accr = 0.f, accg = 0.f, accb = 0.f;
+        if (plainX && rn == 1 && ri.wt[0] == 1.f && ri.wb[0] == 1.f) {
+            const int slot = p.tile_map ? __ldg(p.tile_map + ti[0] * p.ny + ri.j[0]) : ti[0] * p.ny + ri.j[0];
+            loadTilePx<F32>(p.tiles, ((size_t)slot * p.outT + ri.ly[0]) * p.outT + lxs[0], accr, accg, accb);
+        } else {
 #pragma unroll
             for (int a = 0; a < 2; ++a) {       // tile order of the reference: x outer, y inner (render.cpp:43-44)
                 if (a >= ni) break;
