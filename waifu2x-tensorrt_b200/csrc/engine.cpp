@@ -140,8 +140,8 @@ void Engine::unload() {
     dW.clear(); dBias.clear();
     auto freep = [](auto*& p) { if (p) { cudaFree(p); p = nullptr; } };
     freep(dSlots); freep(dTileOut); freep(dTtaMean); freep(dRampX); freep(dRampY); freep(dFrameIn); freep(dFrameOut);
-    freep(dBandTiles); freep(dBandMap); freep(dBandSlots);
-    bandTilesCap = bandMapCap = bandSlotCap = 0;
+    freep(dBandTiles); freep(dBandMap); freep(dBandSlots); freep(dBandMean);
+    bandTilesCap = bandMapCap = bandSlotCap = bandMeanCap = 0;
     if (evBandModel) { cudaEventDestroy(evBandModel); evBandModel = nullptr; }
     slotCap = tileOutCap = ttaCap = frameInCap = frameOutCap = 0;
     rampXLen = rampYLen = -1;
@@ -912,10 +912,12 @@ int Engine::submit(const uint8_t* src, int w, int h, size_t srcStride, uint8_t* 
 // ------------------------------------------------------------------------------------------------
 // Row-band mode ("single large image"): the GLOBAL tile grid is computed once, exactly as for one GPU (bands are
 // unions of the reference's tiles: SE pooling is per tile, so re-tiling would change results), and split into contiguous
-// bands of tile rows, one per engine/GPU.  Every band renders its own tiles; the only exchange is the band's LAST tile row,
-// which the band below needs for the blended seam rows: copied peer-to-peer (cudaMemcpyPeerAsync over NVLink) straight into
-// the neighbour's tile buffer.  Each GPU then stitches and downloads only its own output rows.  No collective, no NCCL; the
-// result is byte-identical to the single-GPU render (same tiles, same fp32 add order).
+// bands of tile rows, one per engine/GPU.  Each GPU receives only the input rows its tiles read (band rows + halo; replicate
+// padding can then only trigger at the true image edges), renders its tiles (with --tta: eight augmentations + the mean), and
+// stitches and downloads only its own output rows.  The one exchange is the blended seam: the bottom `oov` rows of the upper
+// band's last tile row (cfg4: 9 x 64 x 960 x 8 B = 4.4 MB), copied peer-to-peer over NVLink into the lower neighbour's tile
+// buffer.  No collective, no NCCL, no host synchronisation between the devices until the final wait; the result is
+// byte-identical to the single-GPU render (same tiles, same fp32 add order).
 // ------------------------------------------------------------------------------------------------
 bool Engine::renderBanded(Engine* const* es, int count, const uint8_t* src, int w, int h, size_t srcStride, uint8_t* dst, size_t dstStride) {
     if (!es || count < 1 || !es[0]) return false;
@@ -924,70 +926,94 @@ bool Engine::renderBanded(Engine* const* es, int count, const uint8_t* src, int 
         for (int r = 0; r < count; ++r) {
             if (!es[r] || !es[r]->isLoaded) throw Error("no engine loaded");
             if (es[r]->tile != e0.tile || es[r]->outTile != e0.outTile || es[r]->scale != e0.scale || es[r]->batch != e0.batch ||
-                es[r]->cfg.overlapX != e0.cfg.overlapX || es[r]->cfg.overlapY != e0.cfg.overlapY)
+                es[r]->cfg.overlapX != e0.cfg.overlapX || es[r]->cfg.overlapY != e0.cfg.overlapY || es[r]->cfg.tta != e0.cfg.tta)
                 throw Error("row-band render needs identically configured engines");
-            if (es[r]->cfg.tta) throw Error("row-band render does not support --tta yet");
         }
         const int scale = e0.scale, outT = e0.outTile, tile = e0.tile, batch = e0.batch;
+        const bool tta = e0.cfg.tta != 0;
+        const int spt = tta ? 8 : 1;  // model runs per tile
         const TileGrid g = calculateTiles(w, h, w * scale, h * scale, tile, tile, outT, outT, scale, e0.cfg.overlapX, e0.cfg.overlapY);
         if (g.count <= 0) throw Error("frame is too small for the configured tile overlap");
         const int bands = std::min(count, g.ny);
         const size_t tileElems = (size_t)outT * outT * 4;
+        const size_t elemBytes = tta ? sizeof(float) : sizeof(__half);  // stitched tiles: the fp16 model outputs, or the f32 TTA means
         const int sty = outT - g.outOvY;
         const int cw = w * scale, ch = h * scale;
-        struct Band { int j0, j1, own, slots, yBegin, yEnd; };
+        struct Band { int j0, j1, own, steps, yBegin, yEnd, inY0, inY1; };
         std::vector<Band> bd(bands);
         for (int r = 0; r < bands; ++r) {
             const int base = g.ny / bands, extra = g.ny % bands;
             bd[r].j0 = r * base + std::min(r, extra);
             bd[r].j1 = bd[r].j0 + base + (r < extra ? 1 : 0);
             bd[r].own = (bd[r].j1 - bd[r].j0) * g.nx;
-            bd[r].slots = (bd[r].own + batch - 1) / batch * batch;          // own tiles padded to whole batches
+            bd[r].steps = (bd[r].own * spt + batch - 1) / batch * batch;       // own model runs padded to whole batches
             bd[r].yBegin = r == 0 ? 0 : bd[r].j0 * sty;
             bd[r].yEnd = r == bands - 1 ? ch : bd[r].j1 * sty;
+            // input rows read by this band's tiles (tile rows are the inner index of the column-major grid: tile (0, j) is rect j)
+            bd[r].inY0 = std::max(0, g.inRects[bd[r].j0].y);
+            bd[r].inY1 = std::min(h, g.inRects[bd[r].j1 - 1].y + tile);
+            if (bd[r].inY1 <= bd[r].inY0) { bd[r].inY0 = std::min(std::max(bd[r].inY0, 0), h - 1); bd[r].inY1 = bd[r].inY0 + 1; }
         }
-        // ---- phase 1: every band unpacks + runs the model on its tiles (devices run concurrently) ----
+        auto grow = [](auto*& p, size_t& cap, size_t need, size_t elem) {
+            if (need <= cap) return;
+            if (p) cudaFree(p);
+            p = nullptr;
+            W2X_CUDA(cudaMalloc((void**)&p, need * elem));
+            cap = need;
+        };
+        // ---- phase 1: every band uploads its rows, unpacks and runs the model on its tiles; nothing here waits for a device ----
         for (int r = 0; r < bands; ++r) {
             Engine& e = *es[r];
+            const Band& b = bd[r];
             W2X_CUDA(cudaSetDevice(e.cfg.deviceId));
-            e.ensureFrameBuffers(w, h);  // blend ramps + grid bookkeeping for this frame size
-            const size_t inBytes = (size_t)w * 3 * h, outBytes = (size_t)cw * 3 * ch;
-            if (inBytes > e.frameInCap) { if (e.dFrameIn) cudaFree(e.dFrameIn); W2X_CUDA(cudaMalloc(&e.dFrameIn, inBytes)); e.frameInCap = inBytes; }
-            if (outBytes > e.frameOutCap) { if (e.dFrameOut) cudaFree(e.dFrameOut); W2X_CUDA(cudaMalloc(&e.dFrameOut, outBytes)); e.frameOutCap = outBytes; }
-            const size_t needTiles = (size_t)(bd[r].slots + g.nx) * tileElems;   // own (padded) + the row received from above
-            if (needTiles > e.bandTilesCap) { if (e.dBandTiles) cudaFree(e.dBandTiles); W2X_CUDA(cudaMalloc(&e.dBandTiles, needTiles * sizeof(__half))); e.bandTilesCap = needTiles; }
-            if ((size_t)g.count > e.bandMapCap) { if (e.dBandMap) cudaFree(e.dBandMap); W2X_CUDA(cudaMalloc(&e.dBandMap, sizeof(int) * g.count)); e.bandMapCap = g.count; }
-            if ((size_t)bd[r].slots > e.bandSlotCap) { if (e.dBandSlots) cudaFree(e.dBandSlots); W2X_CUDA(cudaMalloc(&e.dBandSlots, sizeof(TileSlot) * bd[r].slots)); e.bandSlotCap = bd[r].slots; }
+            e.ensureFrameBuffers(w, h);  // blend ramps for this frame size
+            const int bandH = b.inY1 - b.inY0;
+            grow(e.dFrameIn, e.frameInCap, (size_t)w * 3 * bandH, 1);
+            grow(e.dFrameOut, e.frameOutCap, (size_t)cw * 3 * (size_t)(b.yEnd - b.yBegin), 1);
+            grow(e.dBandTiles, e.bandTilesCap, (size_t)b.steps * tileElems + (tta ? 0 : (size_t)g.nx * tileElems), sizeof(__half));
+            if (tta) grow(e.dBandMean, e.bandMeanCap, (size_t)(b.own + g.nx) * tileElems, sizeof(float));
+            grow(e.dBandMap, e.bandMapCap, (size_t)g.count, sizeof(int));
+            grow(e.dBandSlots, e.bandSlotCap, (size_t)b.steps, sizeof(TileSlot));
             if (!e.evBandModel) W2X_CUDA(cudaEventCreateWithFlags(&e.evBandModel, cudaEventDisableTiming));
-            // slots in row-major band order (so a tile row is contiguous for the peer copy); map: global tile index -> slot
-            std::vector<TileSlot> slots((size_t)bd[r].slots, TileSlot{0, 0, 0, 0});
-            std::vector<int> map((size_t)g.count, -1);
-            for (int j = bd[r].j0; j < bd[r].j1; ++j)
+            // model runs in row-major band order (a tile row is contiguous for the seam copy), eight consecutive augmentations per
+            // tile with --tta; map: global tile index -> slot of the stitched tile buffer.  The staging vectors live in the engine
+            // so that the asynchronous copies below never outlive them.
+            e.bandSlotsHost.assign((size_t)b.steps, TileSlot{0, 0, 0, 0});
+            e.bandMapHost.assign((size_t)g.count, -1);
+            for (int j = b.j0; j < b.j1; ++j)
                 for (int i = 0; i < g.nx; ++i) {
-                    const int s = (j - bd[r].j0) * g.nx + i, t = i * g.ny + j;
-                    slots[s] = {g.inRects[t].x, g.inRects[t].y, 0, 1};
-                    map[t] = s;
+                    const int s = (j - b.j0) * g.nx + i, t = i * g.ny + j;
+                    for (int a = 0; a < spt; ++a) e.bandSlotsHost[(size_t)s * spt + a] = {g.inRects[t].x, g.inRects[t].y - b.inY0, a, 1};
+                    e.bandMapHost[t] = s;
                 }
+            const int recvSlot = tta ? b.own : b.steps;  // where the seam row received from the band above lands
             if (r > 0)
-                for (int i = 0; i < g.nx; ++i) map[i * g.ny + bd[r].j0 - 1] = bd[r].slots + i;  // received seam row
-            W2X_CUDA(cudaMemcpyAsync(e.dBandSlots, slots.data(), sizeof(TileSlot) * slots.size(), cudaMemcpyHostToDevice, e.stream));
-            W2X_CUDA(cudaMemcpyAsync(e.dBandMap, map.data(), sizeof(int) * map.size(), cudaMemcpyHostToDevice, e.stream));
-            W2X_CUDA(cudaMemcpy2DAsync(e.dFrameIn, (size_t)w * 3, src, srcStride, (size_t)w * 3, h, cudaMemcpyHostToDevice, e.stream));
-            W2X_CUDA(cudaStreamSynchronize(e.stream));  // the staging vectors go out of scope
-            for (int b = 0; b < bd[r].slots / batch; ++b) {
-                const int nReal = std::min(batch, bd[r].own - b * batch);
-                launchUnpack(e.dFrameIn, w, h, (size_t)w * 3, e.dBandSlots + (size_t)b * batch, nReal, tile, e.actIn.p, e.stream);
+                for (int i = 0; i < g.nx; ++i) e.bandMapHost[i * g.ny + b.j0 - 1] = recvSlot + i;
+            W2X_CUDA(cudaMemcpyAsync(e.dBandSlots, e.bandSlotsHost.data(), sizeof(TileSlot) * e.bandSlotsHost.size(), cudaMemcpyHostToDevice, e.stream));
+            W2X_CUDA(cudaMemcpyAsync(e.dBandMap, e.bandMapHost.data(), sizeof(int) * e.bandMapHost.size(), cudaMemcpyHostToDevice, e.stream));
+            W2X_CUDA(cudaMemcpy2DAsync(e.dFrameIn, (size_t)w * 3, src + (size_t)b.inY0 * srcStride, srcStride, (size_t)w * 3, bandH, cudaMemcpyHostToDevice, e.stream));
+            const int realSteps = b.own * spt;
+            for (int bi = 0; bi < b.steps / batch; ++bi) {
+                const int nReal = std::min(batch, realSteps - bi * batch);
+                if (nReal <= 0) break;
+                launchUnpack(e.dFrameIn, w, bandH, (size_t)w * 3, e.dBandSlots + (size_t)bi * batch, nReal, tile, e.actIn.p, e.stream);
                 ++e.launches;
                 W2X_CUDA(cudaGetLastError());
-                e.runModel(e.stream, e.dBandTiles + (size_t)b * batch * tileElems, nReal);
+                e.runModel(e.stream, e.dBandTiles + (size_t)bi * batch * tileElems, nReal);
+            }
+            if (tta) {
+                launchTtaReduce(e.dBandTiles, b.own, outT, e.dBandMean, e.stream);
+                ++e.launches;
             }
             W2X_CUDA(cudaEventRecord(e.evBandModel, e.stream));
         }
-        // ---- phase 2: seam exchange (last tile row of band r-1 -> band r), stitch own rows, download ----
+        // ---- phase 2: seam exchange (bottom overlap rows of band r-1's last tile row -> band r), stitch own rows, download ----
         for (int r = 0; r < bands; ++r) {
             Engine& e = *es[r];
+            const Band& b = bd[r];
             W2X_CUDA(cudaSetDevice(e.cfg.deviceId));
-            if (r > 0) {
+            uint8_t* tilesBase = tta ? reinterpret_cast<uint8_t*>(e.dBandMean) : reinterpret_cast<uint8_t*>(e.dBandTiles);
+            if (r > 0 && g.outOvY > 0) {
                 Engine& up = *es[r - 1];
                 if (up.cfg.deviceId != e.cfg.deviceId) {
                     int can = 0;
@@ -998,22 +1024,27 @@ bool Engine::renderBanded(Engine* const* es, int count, const uint8_t* src, int 
                     }
                 }
                 W2X_CUDA(cudaStreamWaitEvent(e.stream, up.evBandModel, 0));
-                const __half* srcRow = up.dBandTiles + (size_t)(bd[r - 1].j1 - 1 - bd[r - 1].j0) * g.nx * tileElems;
-                W2X_CUDA(cudaMemcpyPeerAsync(e.dBandTiles + (size_t)bd[r].slots * tileElems, e.cfg.deviceId, srcRow, up.cfg.deviceId,
-                                             (size_t)g.nx * tileElems * sizeof(__half), e.stream));
+                const uint8_t* upBase = tta ? reinterpret_cast<const uint8_t*>(up.dBandMean) : reinterpret_cast<const uint8_t*>(up.dBandTiles);
+                const size_t tileBytes = tileElems * elemBytes;
+                const size_t rowOff = (size_t)(outT - g.outOvY) * outT * 4 * elemBytes;      // first blended row inside a tile
+                const size_t stripBytes = (size_t)g.outOvY * outT * 4 * elemBytes;           // the overlap rows of one tile: contiguous
+                const uint8_t* srcRow = upBase + (size_t)(bd[r - 1].j1 - 1 - bd[r - 1].j0) * g.nx * tileBytes + rowOff;
+                uint8_t* dstRow = tilesBase + (size_t)(tta ? b.own : b.steps) * tileBytes + rowOff;
+                W2X_CUDA(cudaMemcpy2DAsync(dstRow, tileBytes, srcRow, tileBytes, stripBytes, (size_t)g.nx, cudaMemcpyDefault, e.stream));
             }
             StitchParams sp{};
-            sp.tiles = e.dBandTiles; sp.f32 = 0; sp.tile_map = e.dBandMap;
+            sp.tiles = tilesBase; sp.f32 = tta ? 1 : 0; sp.tile_map = e.dBandMap;
             sp.outT = outT; sp.nx = g.nx; sp.ny = g.ny; sp.ovx = g.outOvX; sp.ovy = g.outOvY;
             sp.cw = cw; sp.ch = ch; sp.rampx = e.dRampX; sp.rampy = e.dRampY;
-            sp.dst = e.dFrameOut; sp.pitch = (size_t)cw * 3;
-            sp.y_begin = bd[r].yBegin; sp.y_end = bd[r].yEnd;
+            // the band's output rows land at the top of its (band-sized) output buffer
+            sp.dst = e.dFrameOut - (size_t)b.yBegin * cw * 3; sp.pitch = (size_t)cw * 3;
+            sp.y_begin = b.yBegin; sp.y_end = b.yEnd;
             launchStitch(sp, e.stream);
             ++e.launches;
-            const size_t rows = (size_t)(bd[r].yEnd - bd[r].yBegin);
+            const size_t rows = (size_t)(b.yEnd - b.yBegin);
             if (rows)
-                W2X_CUDA(cudaMemcpy2DAsync(dst + (size_t)bd[r].yBegin * dstStride, dstStride, e.dFrameOut + (size_t)bd[r].yBegin * cw * 3, (size_t)cw * 3,
-                                           (size_t)cw * 3, rows, cudaMemcpyDeviceToHost, e.stream));
+                W2X_CUDA(cudaMemcpy2DAsync(dst + (size_t)b.yBegin * dstStride, dstStride, e.dFrameOut, (size_t)cw * 3, (size_t)cw * 3, rows,
+                                           cudaMemcpyDeviceToHost, e.stream));
         }
         for (int r = 0; r < bands; ++r) {
             W2X_CUDA(cudaSetDevice(es[r]->cfg.deviceId));

@@ -165,6 +165,10 @@ private:
     TileSlot* dBandSlots = nullptr;
     size_t bandSlotCap = 0;
     cudaEvent_t evBandModel = nullptr;
+    float* dBandMean = nullptr;                  // --tta in row-band mode: [own tiles + received seam row][outT][outT][4] f32
+    size_t bandMeanCap = 0;
+    std::vector<TileSlot> bandSlotsHost;         // staging of the asynchronous uploads (must outlive them)
+    std::vector<int> bandMapHost;
 };
 
 // Single-layer test hooks, see include/w2x_dev.h.  impl: 0 = the kernel the planner picks, 1 = head kernel, 2 = scalar reference.
