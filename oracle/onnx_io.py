@@ -147,6 +147,9 @@ class GraphBuilder:
         return y
 
     def lrelu(self, x: str, alpha: float = 0.1) -> str:
+        if getattr(self, "mutate", "") == "alpha" and not getattr(self, "_alpha_done", False) and self.n > 40:
+            self._alpha_done = True
+            alpha = 0.2
         return self.unary("LeakyRelu", x, [attr_f("alpha", alpha)])
 
     def binary(self, op: str, a: str, b: str) -> str:
@@ -156,6 +159,13 @@ class GraphBuilder:
 
     def crop(self, x: str, p: int) -> str:
         """F.pad(x, (-p,)*4) as Slice over axes 2,3."""
+        if getattr(self, "mutate", "") == "crop" and p == 16:
+            p = 5
+        if getattr(self, "mutate", "") == "pad":
+            pads = self.init(self._new("pads"), np.array([0, 0, -p, -p, 0, 0, -p, -p], np.int64))
+            y = self._new("pad")
+            self.nodes.append(node("Pad", [x, pads], [y]))
+            return y
         big = 2 ** 31 - 1
         s = self.init(self._new("starts"), np.array([p, p], np.int64))
         e = self.init(self._new("ends"), np.array([-p, -p], np.int64))
@@ -188,9 +198,12 @@ def _emit_bottom(g: GraphBuilder, x: str, m, name: str) -> str:
     return g.conv_transpose(x, m, name) if isinstance(m, nn.ConvTranspose2d) else g.conv(x, m, name)
 
 
-def export_cunet(model_t, path: str | None = None) -> bytes:
-    """Emit oracle.models.CUNet / UpCUNet as ONNX (NCHW, dynamic batch/H/W)."""
+def export_cunet(model_t, path: str | None = None, mutate: str = "") -> bytes:
+    """Emit oracle.models.CUNet / UpCUNet as ONNX (NCHW, dynamic batch/H/W).  `mutate` writes a deliberately different graph with
+    the same weight shapes (tests of the importer's topology checks): "alpha" (LeakyReLU slope 0.2 once), "crop" (a skip cropped
+    by 5), "noclip", "pad" (crops as negative Pad nodes, which is also valid), "shuffle" (initializers in another order)."""
     g = GraphBuilder()
+    g.mutate = mutate
     u1, u2 = model_t.unet1, model_t.unet2
     x = "x"
     # unet1
@@ -214,8 +227,13 @@ def export_cunet(model_t, path: str | None = None) -> bytes:
     x1 = g.crop(x1, 16)
     x5 = g.lrelu(g.conv(g.binary("Add", x1, x4), u2.conv5, "unet2.conv5"))
     z2 = _emit_bottom(g, x5, u2.conv_bottom, "unet2.conv_bottom")
-    y = g.clip01(g.binary("Add", g.crop(z1, 20), z2))
+    y = g.binary("Add", g.crop(z1, 20), z2)
+    if mutate != "noclip":
+        y = g.clip01(y)
     g.nodes.append(node("Identity", [y], ["y"]))
+    if mutate == "shuffle":
+        import random
+        random.Random(1).shuffle(g.inits)
     blob = model(g.nodes, g.inits,
                  [value_info("x", ["batch", 3, "height", "width"])],
                  [value_info("y", ["batch", 3, "out_height", "out_width"])])
@@ -325,6 +343,15 @@ def read_model(blob: bytes):
 # best-effort Reshape/Transpose/Softmax skeleton: the real nunif exports are unobtainable here, no generic ONNX
 # runtime in the image can execute window attention graphs, and the product's importer keys on the weight-bearing nodes only.
 def _emit_linear(g: GraphBuilder, x: str, m, name: str) -> str:
+    if getattr(g, "variant", "") == "decomposed":
+        # older / un-folded exports: Linear as Gemm with the torch [out, in] weight and transB = 1
+        w = g.init(name + ".weight", m.weight.detach().numpy())
+        ins = [x, w]
+        if m.bias is not None:
+            ins.append(g.init(name + ".bias", m.bias.detach().numpy()))
+        y = g._new("gemm")
+        g.nodes.append(node("Gemm", ins, [y], name + ".matmul", [attr_f("alpha", 1.0), attr_f("beta", 1.0), attr_i("transB", 1)]))
+        return y
     w = g.init(name + ".weight_t", m.weight.detach().numpy().T.copy())  # [in, out]
     y = g._new("matmul")
     g.nodes.append(node("MatMul", [x, w], [y], name + ".matmul"))
@@ -339,6 +366,17 @@ def _emit_linear(g: GraphBuilder, x: str, m, name: str) -> str:
 def _emit_layernorm(g: GraphBuilder, x: str, m, name: str) -> str:
     s = g.init(name + ".weight", m.weight.detach().numpy())
     b = g.init(name + ".bias", m.bias.detach().numpy())
+    if getattr(g, "variant", "") == "decomposed":
+        # opset < 17: ReduceMean -> Sub -> Pow -> ReduceMean -> Add(eps) -> Sqrt -> Div -> Mul(gamma) -> Add(beta)
+        ax = [attr_ints("axes", [-1]), attr_i("keepdims", 1)]
+        mean = g.unary("ReduceMean", x, ax)
+        d = g.binary("Sub", x, mean)
+        sq = g.binary("Pow", d, g.init(g._new("two"), np.array(2.0, np.float32)))
+        var = g.unary("ReduceMean", sq, ax)
+        std = g.unary("Sqrt", g.binary("Add", var, g.init(g._new("eps"), np.array(float(m.eps), np.float32))))
+        y = g._new("ln")
+        g.nodes.append(node("Add", [g.binary("Mul", g.binary("Div", d, std), s), b], [y], name))  # carries the LayerNorm's name
+        return y
     y = g._new("ln")
     g.nodes.append(node("LayerNormalization", [x, s, b], [y], name, [attr_i("axis", -1), attr_f("epsilon", float(m.eps))]))
     return y
@@ -351,7 +389,9 @@ def _emit_swin_block(g: GraphBuilder, x: str, blk, name: str) -> str:
     scores = g.binary("MatMul", q, q)
     bias = blk.attn.get_relative_position_bias().detach().numpy()  # [1, heads, N, N]
     bname = g.init(name + ".attn.relative_position_bias", bias)
-    scores = g.binary("Add", scores, bname)
+    sb = g._new("add")
+    g.nodes.append(node("Add", [scores, bname], [sb], name + ".attn.bias_add"))
+    scores = sb
     p = g.unary("Softmax", scores, [attr_i("axis", -1)])
     o = g.unary("Reshape", g.unary("Transpose", g.binary("MatMul", p, q)))
     o = _emit_linear(g, o, blk.attn.proj, name + ".attn.proj")
@@ -363,9 +403,11 @@ def _emit_swin_block(g: GraphBuilder, x: str, blk, name: str) -> str:
     return g.binary("Add", x, h)
 
 
-def export_swin(model_t, path: str | None = None) -> bytes:
-    """Emit oracle.models.SwinUNet as ONNX (see the note above about the skeleton nodes)."""
+def export_swin(model_t, path: str | None = None, variant: str = "") -> bytes:
+    """Emit oracle.models.SwinUNet as ONNX (see the note above about the skeleton nodes).  variant "decomposed" writes what an
+    older exporter would: LayerNorm as its primitive ops, Linear as Gemm(transB = 1), initializers in shuffled order, opset 13."""
     g = GraphBuilder()
+    g.variant = variant
     x = g.lrelu(g.conv("x", model_t.patch[0], "patch.0"))
     x = g.lrelu(g.conv(x, model_t.patch[2], "patch.2"))
     x = g.unary("Transpose", g.crop(x, 6), [attr_ints("perm", [0, 2, 3, 1])])
@@ -398,8 +440,11 @@ def export_swin(model_t, path: str | None = None) -> bytes:
         x = g.unary("DepthToSpace", x, [attr_i("blocksize", model_t.to_image.scale)])
     y = g.clip01(x)
     g.nodes.append(node("Identity", [y], ["y"]))
+    if variant == "decomposed":
+        import random
+        random.Random(0).shuffle(g.inits)
     blob = model(g.nodes, g.inits, [value_info("x", ["batch", 3, "height", "width"])],
-                 [value_info("y", ["batch", 3, "out_height", "out_width"])], name="w2x_swin_unet", opset=17)
+                 [value_info("y", ["batch", 3, "out_height", "out_width"])], name="w2x_swin_unet", opset=13 if variant == "decomposed" else 17)
     if path:
         with open(path, "wb") as f:
             f.write(blob)

@@ -25,7 +25,10 @@ CASES = [("cunet/art", 2, 256, 8, 7680, 4320), ("swin_unet/art", 4, 256, 4, 3840
 for model, scale, tile, batch, W, H in CASES:
     tmp = tempfile.mkdtemp()
     _, onnx = __graft_entry__.make_synthetic_model(tmp, scale=scale, noise=3, model=model)
-    src = tiling.synthetic_frame(W, H, 1)
+    src_pin = w2x.PinnedArray((H, W, 3))        # pinned host buffers: the per-band copies of all GPUs then run concurrently
+    dst_pin = w2x.PinnedArray((H * scale, W * scale, 3))
+    src_pin.array[...] = tiling.synthetic_frame(W, H, 1)
+    src = src_pin.array
     engines = []
     for d in range(ngpu):
         e = w2x.Img2Img()
@@ -34,7 +37,7 @@ for model, scale, tile, batch, W, H in CASES:
     ref = None
     n = 1
     while n <= ngpu:
-        out = w2x.render_banded(engines[:n], src)  # warm-up, allocations
+        out = w2x.render_banded(engines[:n], src, dst_pin.array)  # warm-up, allocations
         if ref is None:
             ref = out.copy()
         same = bool(np.array_equal(out, ref))
@@ -43,7 +46,7 @@ for model, scale, tile, batch, W, H in CASES:
         times = []
         for _ in range(5):
             t0 = time.perf_counter()
-            out = w2x.render_banded(engines[:n], src)
+            out = w2x.render_banded(engines[:n], src, dst_pin.array)
             times.append(time.perf_counter() - t0)
         clocks = sampler.stop()
         ms = statistics.median(times) * 1e3

@@ -96,3 +96,66 @@ def test_model_path_rule():
     assert w2x.model_path("models", "cunet/art", 3, 2) == "models/cunet/art/noise3_scale2x.onnx"
     assert w2x.model_path("models", "cunet/art", -1, 2) == "models/cunet/art/scale2x.onnx"
     assert w2x.model_path("models", "swin_unet/photo", 0, 1) == "models/swin_unet/photo/noise0_.onnx"
+
+
+# ---- importer tolerance / strictness (ADVICE: "same conv shapes, different topology packs silently") ----------
+def test_pack_accepts_equivalent_cunet_exports(built_lib, tmp_path):
+    """Crops written as negative Pad nodes and initializers in another order describe the same network: identical pack."""
+    import w2x
+    from oracle import onnx_io
+    from oracle.models import make_model
+    m = make_model("cunet", 2, 7)
+    blobs = {}
+    for mut in ("", "pad", "shuffle"):
+        p, q = str(tmp_path / f"m_{mut}.onnx"), str(tmp_path / f"m_{mut}.w2x")
+        onnx_io.export_cunet(m, p, mutate=mut)
+        w2x.pack_onnx(p, q)
+        blobs[mut] = open(q, "rb").read()
+    assert blobs[""] == blobs["pad"] == blobs["shuffle"]
+
+
+@pytest.mark.parametrize("mut,needle", [("alpha", "alpha"), ("crop", "crops"), ("noclip", "Clip")])
+def test_pack_rejects_cunet_with_different_topology(mut, needle, built_lib, tmp_path):
+    """Same weight shapes, different network (LeakyReLU slope, a skip crop, the final clamp): the build must fail loudly."""
+    import w2x
+    from oracle import onnx_io
+    from oracle.models import make_model
+    p = str(tmp_path / "m.onnx")
+    onnx_io.export_cunet(make_model("cunet", 2, 7), p, mutate=mut)
+    with pytest.raises(RuntimeError) as ei:
+        w2x.pack_onnx(p, str(tmp_path / "m.w2x"))
+    assert needle in str(ei.value), str(ei.value)
+
+
+def test_pack_rejects_grouped_and_dilated_convs(built_lib, tmp_path):
+    import w2x
+    from oracle import onnx_io
+    from oracle.models import make_model
+    m = make_model("cunet", 1, 3)
+    blob = onnx_io.export_cunet(m)
+    # flip `group` 1 -> 2 in the first Conv node: attribute "group" is written as name(field 1) + i(field 3) + type(field 20)
+    needle = b"\x0a\x05group\x18\x01"
+    assert needle in blob
+    bad = blob.replace(needle, b"\x0a\x05group\x18\x02", 1)
+    p = str(tmp_path / "g.onnx")
+    open(p, "wb").write(bad)
+    with pytest.raises(RuntimeError) as ei:
+        w2x.pack_onnx(p, str(tmp_path / "g.w2x"))
+    assert "group" in str(ei.value)
+
+
+@pytest.mark.parametrize("scale", [2, 4])
+def test_pack_swin_decomposed_export_equals_fused_export(scale, built_lib, tmp_path):
+    """LayerNorm as primitive ops, Linear as Gemm(transB=1), shuffled initializers, opset 13 -> byte-identical packed weights."""
+    import w2x
+    from oracle import onnx_io
+    from oracle.models import make_model
+    m = make_model("swin_unet", scale, 5)
+    out = {}
+    for variant in ("", "decomposed"):
+        p, q = str(tmp_path / f"s_{variant}.onnx"), str(tmp_path / f"s_{variant}.w2x")
+        onnx_io.export_swin(m, p, variant=variant)
+        w2x.pack_onnx(p, q)
+        out[variant] = open(q, "rb").read()
+    assert w2x.pack_info(str(tmp_path / "s_.w2x")) == w2x.pack_info(str(tmp_path / "s_decomposed.w2x"))
+    assert out[""] == out["decomposed"]

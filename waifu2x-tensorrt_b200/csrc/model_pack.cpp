@@ -1,7 +1,9 @@
 #include "model_pack.h"
 
 #include <cmath>
+#include <algorithm>
 #include <cstring>
+#include <deque>
 
 #include "hostutil.h"
 
@@ -177,21 +179,33 @@ OnnxNode parseNode(Span s, std::vector<OnnxTensor>& constants) {
         }
     }
     for (Span a : attrs) {
-        std::string an;
+        std::string an, sval;
         std::vector<int64_t> ints;
         Span tens{nullptr, 0};
         float fval = 0.f;
+        int64_t ival = 0;
         Reader ar(a);
         while (!ar.done()) {
             Field f = ar.next();
             if (f.id == 1) an = str(f.bytes);
             else if (f.id == 2 && f.wt == 5) { uint32_t u = (uint32_t)f.v; std::memcpy(&fval, &u, 4); }
+            else if (f.id == 3 && f.wt == 0) ival = (int64_t)f.v;
+            else if (f.id == 4 && f.wt == 2) sval = str(f.bytes);
             else if (f.id == 8) readInts(f, ints);
             else if (f.id == 5 && f.wt == 2) tens = f.bytes;
         }
         if (an == "kernel_shape") n.kernel_shape = ints;
         else if (an == "strides") n.strides = ints;
         else if (an == "pads") n.pads = ints;
+        else if (an == "dilations") n.dilations = ints;
+        else if (an == "axes") n.axes = ints;
+        else if (an == "group") n.group = ival;
+        else if (an == "transA") n.transA = ival;
+        else if (an == "transB") n.transB = ival;
+        else if (an == "auto_pad") n.auto_pad = sval;
+        else if (an == "alpha") n.alpha = fval;
+        else if (an == "min") { n.hasMin = true; n.minv = fval; }
+        else if (an == "max") { n.hasMax = true; n.maxv = fval; }
         else if (an == "epsilon") n.epsilon = fval;
         else if (an == "value" && n.op == "Constant" && tens.p && !n.outputs.empty()) {
             OnnxTensor t = parseTensor(tens);
@@ -239,7 +253,76 @@ struct ConvNode {
     int cout = 0, cin = 0, kh = 0, kw = 0, stride = 1, pad = 0;
     const OnnxTensor* w = nullptr;
     const OnnxTensor* b = nullptr;
+    const OnnxNode* node = nullptr;
 };
+
+// ---- topology checks: the kernels hard-wire what the weight shapes cannot tell (activation slope, crops, clamp) ---------------
+struct GraphIndex {
+    const OnnxGraph& g;
+    explicit GraphIndex(const OnnxGraph& g_) : g(g_) {}
+    // nodes that read tensor `name`, looking through Identity / Cast
+    std::vector<const OnnxNode*> consumers(const std::string& name) const {
+        std::vector<const OnnxNode*> out;
+        for (const auto& n : g.nodes)
+            for (const auto& in : n.inputs)
+                if (in == name) {
+                    if ((n.op == "Identity" || n.op == "Cast") && !n.outputs.empty()) {
+                        auto more = consumers(n.outputs[0]);
+                        out.insert(out.end(), more.begin(), more.end());
+                    } else {
+                        out.push_back(&n);
+                    }
+                }
+        return out;
+    }
+    const OnnxNode* producer(const std::string& name) const {
+        for (const auto& n : g.nodes)
+            for (const auto& o : n.outputs)
+                if (o == name) return &n;
+        return nullptr;
+    }
+    const OnnxNode* consumerOp(const std::string& name, const char* op) const {
+        for (const OnnxNode* n : consumers(name))
+            if (n->op == op) return n;
+        return nullptr;
+    }
+};
+
+// symmetric spatial crop amount of a Slice (starts [p,p], ends [-p,-p] over axes 2,3) or a negative Pad; -1 if the node is neither
+int cropAmount(const OnnxGraph& g, const OnnxNode& n) {
+    if (n.op == "Slice" && n.inputs.size() >= 3) {
+        const OnnxTensor *s = g.find(n.inputs[1]), *e = g.find(n.inputs[2]);
+        const OnnxTensor* ax = n.inputs.size() > 3 ? g.find(n.inputs[3]) : nullptr;
+        if (!s || !e || s->idata.size() != 2 || e->idata.size() != 2) return -1;
+        if (ax && (ax->idata.size() != 2 || !((ax->idata[0] == 2 && ax->idata[1] == 3) || (ax->idata[0] == -2 && ax->idata[1] == -1)))) return -1;
+        if (s->idata[0] != s->idata[1] || e->idata[0] != e->idata[1] || s->idata[0] <= 0 || e->idata[0] != -s->idata[0]) return -1;
+        return (int)s->idata[0];
+    }
+    if (n.op == "Pad") {
+        std::vector<int64_t> pads = n.pads;
+        if (pads.empty() && n.inputs.size() >= 2)
+            if (const OnnxTensor* p = g.find(n.inputs[1])) pads = p->idata;
+        if (pads.size() != 8 || pads[0] || pads[1] || pads[4] || pads[5]) return -1;
+        if (pads[2] >= 0 || pads[2] != pads[3] || pads[2] != pads[6] || pads[2] != pads[7]) return -1;
+        return (int)-pads[2];
+    }
+    return -1;
+}
+
+void verifyClip01(const OnnxGraph& g, const char* what) {
+    for (const auto& n : g.nodes) {
+        if (n.op != "Clip") continue;
+        float lo = n.minv, hi = n.maxv;
+        bool haveLo = n.hasMin, haveHi = n.hasMax;
+        if (n.inputs.size() > 1 && !n.inputs[1].empty())
+            if (const OnnxTensor* t = g.find(n.inputs[1])) { if (!t->data.empty()) { lo = t->data[0]; haveLo = true; } }
+        if (n.inputs.size() > 2 && !n.inputs[2].empty())
+            if (const OnnxTensor* t = g.find(n.inputs[2])) { if (!t->data.empty()) { hi = t->data[0]; haveHi = true; } }
+        if (haveLo && haveHi && lo == 0.f && hi == 1.f) return;
+        throw Error(std::string("pack: ") + what + " clamps its output to something other than [0, 1]");
+    }
+    throw Error(std::string("pack: ") + what + " has no Clip(0, 1) on its output (the image head kernels clamp unconditionally)");
+}
 
 std::vector<ConvNode> collectConvs(const OnnxGraph& g) {
     std::vector<ConvNode> out;
@@ -259,6 +342,16 @@ std::vector<ConvNode> collectConvs(const OnnxGraph& g) {
         c.kw = (int)d[3];
         c.stride = n.strides.empty() ? 1 : (int)n.strides[0];
         c.pad = n.pads.empty() ? 0 : (int)n.pads[0];
+        // the kernels implement plain dense convolutions only: anything else must fail the build, not run wrong
+        if (n.group != 1) throw Error("onnx: conv '" + n.name + "' has group " + std::to_string(n.group) + " (only 1 is supported)");
+        for (int64_t d : n.dilations)
+            if (d != 1) throw Error("onnx: conv '" + n.name + "' is dilated (unsupported)");
+        for (int64_t s : n.strides)
+            if (s != c.stride) throw Error("onnx: conv '" + n.name + "' has anisotropic strides (unsupported)");
+        for (int64_t p : n.pads)
+            if (p != c.pad) throw Error("onnx: conv '" + n.name + "' has asymmetric padding (unsupported)");
+        if (!n.auto_pad.empty() && n.auto_pad != "NOTSET") throw Error("onnx: conv '" + n.name + "' uses auto_pad " + n.auto_pad + " (unsupported)");
+        c.node = &n;
         if ((size_t)(d[0] * d[1] * d[2] * d[3]) != c.w->data.size()) throw Error("onnx: conv weight '" + c.w->name + "' has no float data");
         out.push_back(c);
     }
@@ -405,6 +498,12 @@ PackedModel packSwin(const OnnxGraph& g, int precision) {
     size_t ci = 0;
     int pendingLin = -1;
     std::string pendingOut;
+    const GraphIndex gi(g);
+    std::deque<OnnxTensor> synth;  // Gemm weights stored [N, K] (transB = 1), transposed into the MatMul convention
+    // decomposed LayerNorm (exporters below opset 17): ... -> Div(x - mean, Sqrt(var + eps)) -> Mul(gamma) -> Add(beta)
+    struct PendingLn { std::string mulOut; const OnnxTensor* gamma; float eps; };
+    std::vector<PendingLn> pendingLn;
+    auto isVec = [](const OnnxTensor* t) { return t && t->dims.size() == 1 && !t->data.empty(); };
     for (const auto& n : g.nodes) {
         if (n.op == "Conv" || n.op == "ConvTranspose") {
             Rec r; r.type = R_CONV; r.conv = convs.at(ci++); r.name = n.name;
@@ -414,6 +513,44 @@ PackedModel packSwin(const OnnxGraph& g, int precision) {
             Rec r; r.type = R_LN; r.a = g.find(n.inputs[1]); r.b = g.find(n.inputs[2]); r.name = n.name; r.eps = n.epsilon;
             if (!r.a || !r.b) throw Error("pack: LayerNormalization parameters are not initializers");
             recs.push_back(r);
+        } else if (n.op == "Gemm" && n.inputs.size() >= 2) {
+            const OnnxTensor* w = g.find(n.inputs[1]);
+            if (w && w->dims.size() == 2 && !n.transA) {
+                const OnnxTensor* wt = w;
+                if (n.transB) {
+                    const int N = (int)w->dims[0], K = (int)w->dims[1];
+                    if ((size_t)N * K != w->data.size()) throw Error("pack: Gemm weight of '" + n.name + "' has no float data");
+                    synth.emplace_back();
+                    OnnxTensor& t = synth.back();
+                    t.name = w->name + "^T";
+                    t.dims = {K, N};
+                    t.data.resize((size_t)K * N);
+                    for (int nn = 0; nn < N; ++nn)
+                        for (int k = 0; k < K; ++k) t.data[(size_t)k * N + nn] = w->data[(size_t)nn * K + k];
+                    wt = &t;
+                }
+                Rec r; r.type = R_LIN; r.a = wt; r.name = n.name;
+                r.b = n.inputs.size() > 2 && !n.inputs[2].empty() ? g.find(n.inputs[2]) : nullptr;
+                recs.push_back(r);
+                pendingLin = -1;
+            }
+        } else if (n.op == "Mul" && n.inputs.size() == 2) {
+            // Mul(Div(...), gamma): second half of a decomposed LayerNorm
+            for (int side = 0; side < 2; ++side) {
+                const OnnxTensor* gamma = g.find(n.inputs[1 - side]);
+                const OnnxNode* div = gi.producer(n.inputs[side]);
+                if (!isVec(gamma) || !div || div->op != "Div" || div->inputs.size() != 2) continue;
+                const OnnxNode* sq = gi.producer(div->inputs[1]);
+                if (!sq || sq->op != "Sqrt") continue;
+                float eps = 1e-5f;
+                if (const OnnxNode* addEps = gi.producer(sq->inputs[0]))
+                    if (addEps->op == "Add")
+                        for (const auto& in : addEps->inputs)
+                            if (const OnnxTensor* e = g.find(in))
+                                if (e->data.size() == 1) eps = e->data[0];
+                pendingLn.push_back({n.outputs.empty() ? std::string() : n.outputs[0], gamma, eps});
+                break;
+            }
         } else if (n.op == "MatMul" && n.inputs.size() == 2) {
             const OnnxTensor* w = g.find(n.inputs[1]);
             if (w && w->dims.size() == 2) {
@@ -427,6 +564,16 @@ PackedModel packSwin(const OnnxGraph& g, int precision) {
             const std::string other = n.inputs[0];
             if (!t) { t = g.find(n.inputs[0]); }
             if (!t) continue;
+            bool wasLn = false;
+            for (size_t k = 0; k < pendingLn.size(); ++k)
+                if (isVec(t) && (n.inputs[0] == pendingLn[k].mulOut || n.inputs[1] == pendingLn[k].mulOut)) {
+                    Rec r; r.type = R_LN; r.a = pendingLn[k].gamma; r.b = t; r.name = n.name; r.eps = pendingLn[k].eps;
+                    recs.push_back(r);
+                    pendingLn.erase(pendingLn.begin() + (long)k);
+                    wasLn = true;
+                    break;
+                }
+            if (wasLn) continue;
             if (t->dims.size() == 1 && pendingLin >= 0 && (n.inputs[0] == pendingOut || n.inputs[1] == pendingOut)) {
                 recs[pendingLin].b = t;  // bias of the preceding MatMul
                 pendingLin = -1;
@@ -526,13 +673,21 @@ PackedModel packSwin(const OnnxGraph& g, int precision) {
         throw Error("pack: swin_unet template mismatch at the image head");
     }
     m.offset = 8 * m.scale;
+    // what the shapes cannot tell: LeakyReLU(0.1) after both patch-embedding convs, the final clamp
+    for (const Rec* r : {&c0, &c1}) {
+        const OnnxNode* act = r->conv.node && !r->conv.node->outputs.empty() ? gi.consumerOp(r->conv.node->outputs[0], "LeakyRelu") : nullptr;
+        if (!act || std::fabs(act->alpha - 0.1f) > 1e-6f) throw Error("pack: swin_unet patch embedding conv '" + r->name + "' is not followed by LeakyRelu(0.1)");
+    }
+    verifyClip01(g, "the swin_unet graph");
     return m;
 }
 }  // namespace
 
 PackedModel packFromOnnx(const OnnxGraph& g, int precision) {
+    // SwinUNet exports carry LayerNorm (fused, or decomposed into ... Sqrt -> Div -> Mul -> Add below opset 17) and an Erf GELU / Softmax;
+    // the cunet family has none of these
     for (const auto& n : g.nodes)
-        if (n.op == "LayerNormalization") return packSwin(g, precision);
+        if (n.op == "LayerNormalization" || n.op == "Softmax" || n.op == "Erf") return packSwin(g, precision);
     std::vector<ConvNode> convs = collectConvs(g);
     PackedModel m;
     m.precision = (uint32_t)precision;
@@ -573,6 +728,50 @@ PackedModel packFromOnnx(const OnnxGraph& g, int precision) {
         const PackedLayer& L = m.layers[i];
         if (L.kind != tmpl[i].kind || (int)L.cin != tmpl[i].cin || (int)L.cout != tmpl[i].cout || (L.se_r != 0) != tmpl[i].se)
             throw Error("pack: layer " + std::to_string(i) + " ('" + L.name + "') does not match the cunet template");
+    }
+    // ---- what the shapes cannot tell: activation slopes, skip crops, SE wiring, the final clamp ----
+    {
+        const GraphIndex gi(g);
+        size_t li = 0;
+        for (size_t i = 0; i < convs.size(); ++i) {
+            const ConvNode& c = convs[i];
+            const std::string out = c.node->outputs.empty() ? std::string() : c.node->outputs[0];
+            if (!c.transpose && c.kh == 1 && c.kw == 1) {
+                // SE: GlobalAveragePool -> 1x1 -> Relu -> 1x1 -> Sigmoid -> Mul
+                const ConvNode& c2 = convs[i + 1];
+                const OnnxNode* pool = gi.producer(c.node->inputs[0]);
+                const bool pooled = pool && (pool->op == "GlobalAveragePool" || (pool->op == "ReduceMean" && pool->axes.size() == 2));
+                if (!pooled) throw Error("pack: squeeze/excite '" + c.name + "' is not fed by a global average pool");
+                if (!gi.consumerOp(out, "Relu")) throw Error("pack: squeeze/excite '" + c.name + "' is not followed by Relu");
+                const OnnxNode* sg = gi.consumerOp(c2.node->outputs.empty() ? std::string() : c2.node->outputs[0], "Sigmoid");
+                if (!sg || !gi.consumerOp(sg->outputs[0], "Mul")) throw Error("pack: squeeze/excite '" + c2.name + "' is not followed by Sigmoid -> Mul");
+                ++i;
+                continue;
+            }
+            const bool head = li == 7 || li == 21;
+            const OnnxNode* act = gi.consumerOp(out, "LeakyRelu");
+            if (head) {
+                if (act) throw Error("pack: image head '" + c.name + "' has an activation (the kernels apply none)");
+            } else {
+                if (!act) throw Error("pack: conv '" + c.name + "' is not followed by LeakyRelu (the kernels fuse LeakyReLU(0.1))");
+                if (std::fabs(act->alpha - 0.1f) > 1e-6f)
+                    throw Error("pack: LeakyRelu after '" + c.name + "' has alpha " + std::to_string(act->alpha) + " (the kernels fuse 0.1)");
+            }
+            ++li;
+        }
+        std::vector<int> crops;
+        for (const auto& n : g.nodes) {
+            const int a = cropAmount(g, n);
+            if (a > 0) crops.push_back(a);
+        }
+        std::sort(crops.begin(), crops.end());
+        if (crops != std::vector<int>{4, 4, 16, 20})
+            throw Error("pack: the skip-connection crops of the graph are not the cunet ones (4, 4, 16, 20)");
+        int skipAdds = 0;
+        for (const auto& n : g.nodes)
+            if (n.op == "Add" && n.inputs.size() == 2 && !g.find(n.inputs[0]) && !g.find(n.inputs[1])) ++skipAdds;
+        if (skipAdds != 4) throw Error("pack: expected 4 skip / residual additions in a cunet graph, found " + std::to_string(skipAdds));
+        verifyClip01(g, "the cunet graph");
     }
     m.arch = up ? ARCH_UPCUNET : ARCH_CUNET;
     m.scale = up ? 2 : 1;

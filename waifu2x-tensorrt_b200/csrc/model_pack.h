@@ -19,8 +19,13 @@ struct OnnxTensor {
 struct OnnxNode {
     std::string op, name;
     std::vector<std::string> inputs, outputs;
-    std::vector<int64_t> kernel_shape, strides, pads;
+    std::vector<int64_t> kernel_shape, strides, pads, dilations, axes;
+    int64_t group = 1, transA = 0, transB = 0;
+    std::string auto_pad;
     float epsilon = 1e-5f;  // LayerNormalization
+    float alpha = 0.01f;    // LeakyRelu (ONNX default) / Gemm
+    bool hasMin = false, hasMax = false;  // Clip (opset < 11 carries the bounds as attributes)
+    float minv = 0.f, maxv = 0.f;
 };
 struct OnnxGraph {
     std::vector<OnnxNode> nodes;

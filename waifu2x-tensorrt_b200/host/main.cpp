@@ -246,7 +246,12 @@ int main(int argc, char* argv[]) {
 
     const std::string noiseTag = o.noise == -1 ? "" : "noise" + std::to_string(o.noise);
     const std::string scaleTag = o.scale == 1 ? "" : "scale" + std::to_string(o.scale);
-    const std::string modelPath = o.modelsDir + "/" + o.model + "/" + (noiseTag.empty() ? "" : noiseTag + "_") + (scaleTag.empty() ? "" : scaleTag + "x") + ".onnx";
+    std::string modelPath = o.modelsDir + "/" + o.model + "/" + (noiseTag.empty() ? "" : noiseTag + "_") + (scaleTag.empty() ? "" : scaleTag + "x") + ".onnx";
+    // main.cpp:201-204 yields "noiseN_.onnx" (trailing underscore) for scale 1; the released archives name that file "noiseN.onnx"
+    if (scaleTag.empty() && !noiseTag.empty() && !fs::exists(modelPath)) {
+        const std::string alt = o.modelsDir + "/" + o.model + "/" + noiseTag + ".onnx";
+        if (fs::exists(alt)) modelPath = alt;
+    }
     std::string flatModel = o.model;
     std::replace(flatModel.begin(), flatModel.end(), '/', '_');
     const std::string suffix = "(" + flatModel + ")" + (noiseTag.empty() ? "" : "(" + noiseTag + ")") + (scaleTag.empty() ? "" : "(" + scaleTag + ")") + (o.tta ? "(tta)" : "");

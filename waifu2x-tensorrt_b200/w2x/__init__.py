@@ -436,12 +436,14 @@ class Img2Img:
             raise RuntimeError("d2h failed")
 
 
-def render_banded(engines: List["Img2Img"], src: np.ndarray) -> Optional[np.ndarray]:
-    """One image over several engines (one per GPU): bands of tile rows + P2P seam exchange."""
+def render_banded(engines: List["Img2Img"], src: np.ndarray, dst: Optional[np.ndarray] = None) -> Optional[np.ndarray]:
+    """One image over several engines (one per GPU): bands of tile rows + P2P seam exchange.  Pass pinned arrays
+    (PinnedArray.array) for src / dst to let the per-band copies of all GPUs overlap."""
     src = np.ascontiguousarray(src, dtype=np.uint8)
     h, w = src.shape[:2]
     s = engines[0].scaling
-    dst = np.empty((h * s, w * s, 3), np.uint8)
+    if dst is None:
+        dst = np.empty((h * s, w * s, 3), np.uint8)
     arr = (C.c_void_p * len(engines))(*[e._h for e in engines])
     ok = lib().w2x_render_banded(arr, len(engines), _ptr(src), w, h, src.strides[0], _ptr(dst), dst.strides[0])
     return dst if ok else None
