@@ -12,6 +12,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+from bench import ClockSampler  # noqa: E402
 from oracle.models import make_model  # noqa: E402
 
 
@@ -41,16 +42,23 @@ def main():
         frame()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    iters = 10
+    iters = 30
+    sampler = ClockSampler(0)
+    sampler.start()
+    for _ in range(5):  # nvidia-smi needs a few hundred ms to start
+        frame()
+    torch.cuda.synchronize()
+    sampler.mark()
     e0.record()
     for _ in range(iters):
         frame()
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
+    clocks = sampler.stop()
     print(json.dumps({"impl": "library baseline (PyTorch-CUDA fp16, cuDNN/cuBLAS; not TensorRT)", "workload": which, "model_stage_ms_per_frame": ms,
                       "equivalent_output_mpx_s": out_mpx / (ms / 1e3), "tiles": tiles, "batch": batch, "torch": torch.__version__,
-                      "cudnn": torch.backends.cudnn.version(), "note": "model stage only (no unpack / stitch / copies); padding slots skipped like the product"}))
+                      "cudnn": torch.backends.cudnn.version(), "clocks": clocks, "note": "model stage only (no unpack / stitch / copies); padding slots skipped like the product"}))
 
 
 if __name__ == "__main__":

@@ -2,7 +2,7 @@ mkdir -p gpurun_out
 python - <<'PY' 2>&1 | tee gpurun_out/hmma_rate.log
 import sys; sys.path.insert(0, "waifu2x-tensorrt_b200")
 import w2x
-l = w2x.lib()
+l = w2x.dev_lib()  # probes live in lib/libw2x_dev.so (-DW2X_DEV)
 iters = 20000
 print("# legacy mma.sync.m16n8k16 (fp16 -> fp32) issue-rate probe: operands in registers, 148 SMs; clock assumed 1.965 GHz")
 for warps in (1, 4, 8, 16):

@@ -1,7 +1,7 @@
 python - <<'PY' 2>&1 | tee gpurun_out/mma_rate.log
 import sys; sys.path.insert(0, "waifu2x-tensorrt_b200")
 import w2x
-l = w2x.lib()
+l = w2x.dev_lib()  # probes live in lib/libw2x_dev.so (-DW2X_DEV)
 iters = 20000
 print("# UMMA issue-rate probe: M=128, K=16 fp16, 148 SMs, 4*iters MMAs per SM; clock assumed 1.965 GHz (boost, short run)")
 for sbo in (1024, 1280):

@@ -2,7 +2,7 @@ mkdir -p gpurun_out
 python - <<'PY' 2>&1 | tee gpurun_out/mma_stream.log
 import sys, ctypes as C; sys.path.insert(0, "waifu2x-tensorrt_b200")
 import w2x
-l = w2x.lib()
+l = w2x.dev_lib()  # probes live in lib/libw2x_dev.so (-DW2X_DEV)
 print("# UMMA (M=128, K=16, fp16, operands resident in smem) issue rate with a concurrent cp.async.bulk stream into another smem region")
 print("# columns: N, stream copy size, SM cycles per MMA, streamed bytes per SM cycle, operand bytes per cycle (A 4 KB + B N*32 B per MMA)")
 res = (C.c_float * 2)()

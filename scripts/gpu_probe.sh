@@ -3,7 +3,7 @@ timeout 120 python - <<'PY' 2>&1 | tee gpurun_out/probe.log
 import sys, ctypes as C
 sys.path.insert(0, "waifu2x-tensorrt_b200")
 import w2x
-l = w2x.lib()
+l = w2x.dev_lib()  # probes live in lib/libw2x_dev.so (-DW2X_DEV)
 for pitch in (16, 10, 24):
     for mode in (0, 1):
         err = (C.c_float * 9)()
