@@ -251,6 +251,25 @@ __device__ __forceinline__ void epilogueWarps(const ConvArgs& a, uint32_t base, 
             namedBarSync(2, kEpiThreads);
             skipScaleImg = tc.img;
         }
+        // token-wise Linear with a residual: the first round of residual chunks is fetched BEFORE blocking on the accumulator, so that
+        // its global-memory latency hides behind the MMAs (the copy-out below was three dependent load round trips per tile)
+        constexpr int kPre = 4;
+        uint4 preRes[kPre];
+        const bool prefetched = kStaged && a.p.skip && a.p.mode == EPI_STORE;  // (the pixel-shuffle layers address their residual differently)
+        if (prefetched) {
+            const int chunksPerRow = a.bn >> 3, total = 128 * chunksPerRow;
+#pragma unroll
+            for (int i = 0; i < kPre; ++i) {
+                preRes[i] = make_uint4(0, 0, 0, 0);
+                const int idx = et + i * kEpiThreads;
+                if (idx < total) {
+                    const int row = idx / chunksPerRow, cc = idx - row * chunksPerRow;
+                    const int yy2 = tc.y0 + (row >> a.bwShift), xx2 = tc.x0 + (row & (a.bw - 1));
+                    if (yy2 < a.p.gy && xx2 < a.p.gx)
+                        preRes[i] = *reinterpret_cast<const uint4*>(a.p.skip + (((long long)tc.img * a.p.out_h + yy2) * a.p.out_w + xx2) * a.p.out_c + tc.n0 + cc * 8);
+                }
+            }
+        }
         mbarWait(barTFull + 8u * acc, accPhase);
         tcFenceAfter();
         if (kSkip) mbarWait(barSkip + 8u * b, bufPhase);
@@ -405,32 +424,40 @@ __device__ __forceinline__ void epilogueWarps(const ConvArgs& a, uint32_t base, 
                 return (((long long)tc.img * a.p.out_h + yy2) * a.p.out_w + xx2) * a.p.out_c + tc.n0 + cc * 8;
             };
             if (a.p.skip) {
-                // residual layers: two chunks per thread per round, both residual loads in flight before either is consumed
-                for (int idx0 = et2; idx0 < total; idx0 += 2 * kEpiThreads) {
-                    const int idx1 = idx0 + kEpiThreads;
-                    const int row0 = idx0 / chunksPerRow, cc0 = idx0 - row0 * chunksPerRow;
-                    const int row1 = idx1 < total ? idx1 / chunksPerRow : row0, cc1 = idx1 < total ? idx1 - row1 * chunksPerRow : cc0;
-                    bool ok0, ok1;
-                    const long long off0 = chunkOffset(row0, cc0, ok0), off1 = chunkOffset(row1, cc1, ok1);
-                    ok1 = ok1 && idx1 < total;
-                    uint4 s0 = make_uint4(0, 0, 0, 0), s1 = s0;
-                    if (ok0) s0 = *reinterpret_cast<const uint4*>(a.p.skip + off0);
-                    if (ok1) s1 = *reinterpret_cast<const uint4*>(a.p.skip + off1);
-                    uint4 v0 = ldsV4(sbuf + (uint32_t)row0 * a.stagedPitch + (uint32_t)cc0 * 16u);
-                    uint4 v1 = ldsV4(sbuf + (uint32_t)row1 * a.stagedPitch + (uint32_t)cc1 * 16u);
-                    __half2* h0 = reinterpret_cast<__half2*>(&v0);
-                    __half2* h1 = reinterpret_cast<__half2*>(&v1);
-                    const __half2* r0 = reinterpret_cast<const __half2*>(&s0);
-                    const __half2* r1 = reinterpret_cast<const __half2*>(&s1);
+                // residual layers (same geometry as the output: the residual stream is updated in place): kPre chunks per thread per
+                // round, all residual loads of a round in flight before any is consumed; round 0 was prefetched above
+                for (int base0 = et2, round = 0; base0 < total; base0 += kPre * kEpiThreads, ++round) {
+                    uint4 res[kPre];
+                    long long offs[kPre];
+                    bool oks[kPre];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float2 a0 = __half22float2(h0[i]), b0 = __half22float2(r0[i]);
-                        const float2 a1 = __half22float2(h1[i]), b1 = __half22float2(r1[i]);
-                        h0[i] = __floats2half2_rn(a0.x + b0.x, a0.y + b0.y);
-                        h1[i] = __floats2half2_rn(a1.x + b1.x, a1.y + b1.y);
+                    for (int i = 0; i < kPre; ++i) {
+                        const int idx = base0 + i * kEpiThreads;
+                        oks[i] = false;
+                        offs[i] = 0;
+                        res[i] = make_uint4(0, 0, 0, 0);
+                        if (idx < total) {
+                            const int row = idx / chunksPerRow, cc = idx - row * chunksPerRow;
+                            offs[i] = chunkOffset(row, cc, oks[i]);
+                            if (round == 0 && prefetched) res[i] = preRes[i];
+                            else if (oks[i]) res[i] = *reinterpret_cast<const uint4*>(a.p.skip + offs[i]);
+                        }
                     }
-                    if (ok0) *reinterpret_cast<uint4*>(a.p.out + off0) = v0;
-                    if (ok1) *reinterpret_cast<uint4*>(a.p.out + off1) = v1;
+#pragma unroll
+                    for (int i = 0; i < kPre; ++i) {
+                        const int idx = base0 + i * kEpiThreads;
+                        if (idx >= total || !oks[i]) continue;
+                        const int row = idx / chunksPerRow, cc = idx - row * chunksPerRow;
+                        uint4 v = ldsV4(sbuf + (uint32_t)row * a.stagedPitch + (uint32_t)cc * 16u);
+                        __half2* h = reinterpret_cast<__half2*>(&v);
+                        const __half2* r = reinterpret_cast<const __half2*>(&res[i]);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float2 x0 = __half22float2(h[j]), x1 = __half22float2(r[j]);
+                            h[j] = __floats2half2_rn(x0.x + x1.x, x0.y + x1.y);
+                        }
+                        *reinterpret_cast<uint4*>(a.p.out + offs[i]) = v;
+                    }
                 }
             } else {
                 for (int idx = et2; idx < total; idx += kEpiThreads) {
@@ -803,8 +830,10 @@ __device__ __forceinline__ void setupCommon(const ConvArgs& a, uint32_t base, ui
 // ======================================================================================================================
 // generic implicit GEMM (per-tap A loads)
 // ======================================================================================================================
+// Token-wise layers (EPI_K_STAGED: K <= 384, a few MMAs per tile) are latency-bound, not tensor-bound: two CTAs share an SM there
+// (half the shared memory and TMEM each), so one CTA's epilogue / copy-out overlaps the other's loads and MMAs.
 template <int kEpi>
-__global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constant__ ConvArgs a) {
+__global__ void __launch_bounds__(kThreads, kEpi == EPI_K_STAGED ? 2 : 1) igemm_kernel(const __grid_constant__ ConvArgs a) {
     extern __shared__ uint8_t smemRaw[];
     const uint32_t rawAddr = smemU32(smemRaw);
     const uint32_t base = (rawAddr + 1023u) & ~1023u;
@@ -1550,6 +1579,10 @@ void planIgemm(IgemmPlan* plan) {
     }
     if (avail < a.stagingBytes + 2 * stageBytes) throw Error("igemm: tile does not fit in shared memory");
     a.stages = (int)std::min<size_t>(8, (avail - a.stagingBytes) / stageBytes);
+    // staged (token-wise) layers: two CTAs per SM when a four-deep ring fits in half the shared memory and both accumulator sets in TMEM
+    const size_t halfAvail = kSmemLimit / 2 - 2048 - 1024 - a.headerBytes;
+    const bool twoPerSm = a.staged && 2 * a.bn <= 256 && halfAvail >= a.stagingBytes + 3 * stageBytes;
+    if (twoPerSm) a.stages = (int)std::min<size_t>(6, (halfAvail - a.stagingBytes) / stageBytes);
     a.nAcc = 2;
     uint32_t cols = 32;
     while (cols < (uint32_t)(2 * a.bn)) cols *= 2;
@@ -1566,7 +1599,7 @@ void planIgemm(IgemmPlan* plan) {
     }
     encodeWeights(&a.tmB, p, a.kc, a.bn, sw128);
     if (a.useTma) encodeOutMaps(a);
-    plan->grid = std::min(a.totalTiles, numSMs());
+    plan->grid = std::min(a.totalTiles, (twoPerSm ? 2 : 1) * numSMs());
     plan->smem = 1024 + a.headerBytes + a.stagingBytes + (size_t)a.stages * stageBytes;
 }
 
