@@ -71,6 +71,7 @@ struct ConvArgs {
     int stages, cchunks, kblocks;
     uint32_t idesc, tmemCols, bytesA, bytesB, descHiA, descHiB;
     int useTma, nsub, nbuf, hasSkip;
+    int twoPerSm;  // staged token-wise layer planned for two CTAs per SM (EPI_K_STAGED2)
     int nAcc;  // TMEM accumulator buffers: 2, or 4 for the two-group epilogue (each group alternates between two of its own)
     int dbg;  // timing experiments only (W2X_DBG): 1 = epilogue skips math + staging, 2 = no output store, 4 = no MMAs, 16 = no activation loads
     uint32_t stageStride, wBytes, stagingBytes;
@@ -114,7 +115,8 @@ constexpr int kFuseBufs = 3;       // fused first layer: im2col tiles / TMEM reg
                                    // before the main MMAs of tile k: the tensor pipe's queue holds about one tile of main MMAs, so a lead of
                                    // one tile leaves the producer waiting for its accumulators (measured: 2080 instead of ~1330 cycles per tile)
 
-enum EpiKind { EPI_K_DIRECT = 0, EPI_K_TMA = 1, EPI_K_TMA_SKIP = 2, EPI_K_STAGED = 3, EPI_K_TMA_GROUPS = 4 };
+enum EpiKind { EPI_K_DIRECT = 0, EPI_K_TMA = 1, EPI_K_TMA_SKIP = 2, EPI_K_STAGED = 3, EPI_K_TMA_GROUPS = 4,
+               EPI_K_STAGED2 = 5 };  // STAGED2: the same code compiled for two CTAs per SM (register cap 102)
 
 struct TileCoord {
     int img, y0, x0, n0;
@@ -174,7 +176,7 @@ template <int kEpi>
 __device__ __forceinline__ void epilogueWarps(const ConvArgs& a, uint32_t base, uint32_t tmemBase, int nMine, int first, int step, int nBase) {
     constexpr bool kTma = kEpi == EPI_K_TMA || kEpi == EPI_K_TMA_SKIP;
     constexpr bool kSkip = kEpi == EPI_K_TMA_SKIP;
-    constexpr bool kStaged = kEpi == EPI_K_STAGED;
+    constexpr bool kStaged = kEpi == EPI_K_STAGED || kEpi == EPI_K_STAGED2;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int quarter = warp & 3;
     const int half = (warp - 2) >> 2;
@@ -830,10 +832,10 @@ __device__ __forceinline__ void setupCommon(const ConvArgs& a, uint32_t base, ui
 // ======================================================================================================================
 // generic implicit GEMM (per-tap A loads)
 // ======================================================================================================================
-// Token-wise layers (EPI_K_STAGED: K <= 384, a few MMAs per tile) are latency-bound, not tensor-bound: two CTAs share an SM there
-// (half the shared memory and TMEM each), so one CTA's epilogue / copy-out overlaps the other's loads and MMAs.
+// Token-wise layers (staged epilogue: K <= 768, a few MMAs per tile) are latency-bound, not tensor-bound: the EPI_K_STAGED2 variant
+// runs two CTAs per SM (half the shared memory and TMEM each), so one CTA's epilogue / copy-out overlaps the other's loads and MMAs.
 template <int kEpi>
-__global__ void __launch_bounds__(kThreads, kEpi == EPI_K_STAGED ? 2 : 1) igemm_kernel(const __grid_constant__ ConvArgs a) {
+__global__ void __launch_bounds__(kThreads, kEpi == EPI_K_STAGED2 ? 2 : 1) igemm_kernel(const __grid_constant__ ConvArgs a) {
     extern __shared__ uint8_t smemRaw[];
     const uint32_t rawAddr = smemU32(smemRaw);
     const uint32_t base = (rawAddr + 1023u) & ~1023u;
@@ -1536,6 +1538,25 @@ void planIgemm(IgemmPlan* plan) {
     a.hasSkip = (a.useTma && p.mode == EPI_D2S && p.skip) ? 1 : 0;
     a.bn = pickBn(p.npad);
     if (p.mode == EPI_D2S && a.useTma) a.bn = (p.cout % 128 == 0 || 128 % p.cout == 0) ? 128 : 64;  // whole 64-channel sub-tiles of one phase
+    // token-wise layers whose shape rules out the TMA epilogue: coalescing staged epilogue
+    const bool skipSameGeom = !p.skip || (p.skip_off == 0 && p.skip_c == p.out_c && p.skip_h == p.out_h && p.skip_w == p.out_w && !p.skip_scale);
+    a.staged = (!a.useTma && a.bn >= 32 && skipSameGeom &&
+                ((p.mode == EPI_STORE && p.cout == p.npad && p.out_c == p.npad) ||
+                 (p.mode == EPI_D2S && p.cout % 8 == 0 && p.out_c == p.cout && p.npad == 4 * p.cout && p.act == ACT_LRELU))) ? 1 : 0;
+    a.twoPerSm = 0;
+    if (a.staged && p.ntaps == 1) {
+        // two CTAs per SM: N tiles of at most 128 columns (2 x 2 x 128 accumulator columns fit the SM's 512), and a K chunk whose
+        // three-deep ring + staging fits half the shared memory
+        const size_t halfAvail = kSmemLimit / 2 - 2048 - 1024 - a.headerBytes;
+        for (int bn2 = 128; bn2 >= 32 && !a.twoPerSm; bn2 -= 32) {
+            if (p.npad % bn2) continue;
+            for (int kc : {a.kc, 32}) {
+                if (p.cin % kc) continue;
+                const size_t stageB = (size_t)(128 + bn2) * kc * 2, staging = 2 * (((size_t)128 * (bn2 * 2 + 16) + 1023) & ~(size_t)1023);
+                if (halfAvail >= staging + 3 * stageB) { a.twoPerSm = 1; a.bn = bn2; a.kc = kc; break; }
+            }
+        }
+    }
     a.nSplit = 1;
     a.cchunks = p.cin / a.kc;
     a.kblocks = p.ntaps * a.cchunks;
@@ -1558,11 +1579,6 @@ void planIgemm(IgemmPlan* plan) {
     const size_t avail = kSmemLimit - 1024 - a.headerBytes;
     a.nbuf = 1;
     a.stagingBytes = 0;
-    // token-wise layers whose shape rules out the TMA epilogue: coalescing staged epilogue
-    const bool skipSameGeom = !p.skip || (p.skip_off == 0 && p.skip_c == p.out_c && p.skip_h == p.out_h && p.skip_w == p.out_w && !p.skip_scale);
-    a.staged = (!a.useTma && a.bn >= 32 && skipSameGeom &&
-                ((p.mode == EPI_STORE && p.cout == p.npad && p.out_c == p.npad) ||
-                 (p.mode == EPI_D2S && p.cout % 8 == 0 && p.out_c == p.cout && p.npad == 4 * p.cout && p.act == ACT_LRELU))) ? 1 : 0;
     if (a.staged) {
         a.stagedPitch = (uint32_t)a.bn * 2u + 16u;
         a.stagedBuf = (128u * a.stagedPitch + 1023u) & ~1023u;
@@ -1579,10 +1595,8 @@ void planIgemm(IgemmPlan* plan) {
     }
     if (avail < a.stagingBytes + 2 * stageBytes) throw Error("igemm: tile does not fit in shared memory");
     a.stages = (int)std::min<size_t>(8, (avail - a.stagingBytes) / stageBytes);
-    // staged (token-wise) layers: two CTAs per SM when a four-deep ring fits in half the shared memory and both accumulator sets in TMEM
-    const size_t halfAvail = kSmemLimit / 2 - 2048 - 1024 - a.headerBytes;
-    const bool twoPerSm = a.staged && 2 * a.bn <= 256 && halfAvail >= a.stagingBytes + 3 * stageBytes;
-    if (twoPerSm) a.stages = (int)std::min<size_t>(6, (halfAvail - a.stagingBytes) / stageBytes);
+    const bool twoPerSm = a.twoPerSm != 0;
+    if (twoPerSm) a.stages = (int)std::min<size_t>(6, (kSmemLimit / 2 - 2048 - 1024 - a.headerBytes - a.stagingBytes) / stageBytes);
     a.nAcc = 2;
     uint32_t cols = 32;
     while (cols < (uint32_t)(2 * a.bn)) cols *= 2;
@@ -1635,6 +1649,7 @@ IgemmPlan* igemmCreatePlan(const ConvParams& p) {
             checkCuda(cudaFuncSetAttribute(conv3x3_patch_kernel<EPI_K_TMA_GROUPS, 32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
             checkCuda(cudaFuncSetAttribute(igemm_kernel<EPI_K_TMA_SKIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
             checkCuda(cudaFuncSetAttribute(igemm_kernel<EPI_K_STAGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+            checkCuda(cudaFuncSetAttribute(igemm_kernel<EPI_K_STAGED2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
             checkCuda(cudaFuncSetAttribute(conv3x3_patch_kernel<EPI_K_DIRECT, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
             checkCuda(cudaFuncSetAttribute(conv3x3_patch_kernel<EPI_K_TMA, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
             checkCuda(cudaFuncSetAttribute(conv3x3_patch_kernel<EPI_K_DIRECT, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
@@ -1776,6 +1791,7 @@ void igemmLaunch(const IgemmPlan* plan, cudaStream_t s, __half* outOverride, int
         if (a->hasSkip) launchPdl(igemm_kernel<EPI_K_TMA_SKIP>, dim3(plan->grid), dim3(kThreads), plan->smem, s, *a);
         else if (grouped) launchPdl(igemm_kernel<EPI_K_TMA_GROUPS>, dim3(plan->grid), dim3(kThreads), plan->smem, s, *a);
         else if (a->useTma) launchPdl(igemm_kernel<EPI_K_TMA>, dim3(plan->grid), dim3(kThreads), plan->smem, s, *a);
+        else if (a->staged && a->twoPerSm) launchPdl(igemm_kernel<EPI_K_STAGED2>, dim3(plan->grid), dim3(kThreads), plan->smem, s, *a);
         else if (a->staged) launchPdl(igemm_kernel<EPI_K_STAGED>, dim3(plan->grid), dim3(kThreads), plan->smem, s, *a);
         else launchPdl(igemm_kernel<EPI_K_DIRECT>, dim3(plan->grid), dim3(kThreads), plan->smem, s, *a);
     }

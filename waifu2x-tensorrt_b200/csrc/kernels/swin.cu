@@ -30,40 +30,48 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict
     for (int i = 0; i < 8; ++i) { gm[i] = act ? gamma[li * 8 + i] : 0.f; bt[i] = act ? beta[li * 8 + i] : 0.f; }
     const float invc = 1.f / (float)c;
     pdlWait();  // gamma / beta are constants; x comes from the preceding kernel
-    for (long long t0 = warpId * TPW; t0 < tokens; t0 += warpCount * TPW) {
-        const long long tok = t0 + sub;
-        const bool ok = act && tok < tokens;
-        float v[8];
-        if (ok) {
-            const uint4 raw = *reinterpret_cast<const uint4*>(x + tok * c + li * 8);
-            const __half2* h = reinterpret_cast<const __half2*>(&raw);
+    // two independent token groups per iteration: both 16-byte loads are in flight before either is reduced (one load per lane per
+    // iteration left the kernel latency-bound at half the HBM rate)
+    constexpr int U = 2;
+    for (long long t0 = warpId * TPW * U; t0 < tokens; t0 += warpCount * TPW * U) {
+        uint4 raw[U];
+        bool ok[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long tok = t0 + u * TPW + sub;
+            ok[u] = act && tok < tokens;
+            raw[u] = make_uint4(0, 0, 0, 0);
+            if (ok[u]) raw[u] = *reinterpret_cast<const uint4*>(x + tok * c + li * 8);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long tok = t0 + u * TPW + sub;
+            float v[8];
+            const __half2* h = reinterpret_cast<const __half2*>(&raw[u]);
 #pragma unroll
             for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
-        } else {
+            float sum = 0.f;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = 0.f;
-        }
-        float sum = 0.f;
+            for (int i = 0; i < 8; ++i) sum += v[i];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) sum += v[i];
+            for (int o = SEG / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            const float mean = sum * invc;
+            float sq = 0.f;
+            if (act) {
 #pragma unroll
-        for (int o = SEG / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        const float mean = sum * invc;
-        float sq = 0.f;
-        if (act) {
+                for (int i = 0; i < 8; ++i) { const float d = v[i] - mean; sq += d * d; }
+            }
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { const float d = v[i] - mean; sq += d * d; }
-        }
+            for (int o = SEG / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+            const float rstd = rsqrtf(sq * invc + eps);
+            if (ok[u]) {
+                uint4 o;
+                __half2* oh = reinterpret_cast<__half2*>(&o);
 #pragma unroll
-        for (int o = SEG / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-        const float rstd = rsqrtf(sq * invc + eps);
-        if (ok) {
-            uint4 o;
-            __half2* oh = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-                oh[i] = __floats2half2_rn((v[2 * i] - mean) * rstd * gm[2 * i] + bt[2 * i], (v[2 * i + 1] - mean) * rstd * gm[2 * i + 1] + bt[2 * i + 1]);
-            *reinterpret_cast<uint4*>(y + tok * c + li * 8) = o;
+                for (int i = 0; i < 4; ++i)
+                    oh[i] = __floats2half2_rn((v[2 * i] - mean) * rstd * gm[2 * i] + bt[2 * i], (v[2 * i + 1] - mean) * rstd * gm[2 * i + 1] + bt[2 * i + 1]);
+                *reinterpret_cast<uint4*>(y + tok * c + li * 8) = o;
+            }
         }
     }
 }
