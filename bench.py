@@ -184,7 +184,7 @@ def tiling_roofline(wl, stage, hbm_gbs, peak_kind):
     if wl["tta"]:
         rows["tta_reduce"] = (wl["tiles"] * (8 * 6 + 6) * out_t * out_t, stage.get("tta_reduce", 0.0))
     out = {"bound": "hbm", "peak": hbm_gbs, "unit": "GB/s", "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})",
-           "note": "algorithmic bytes (SURVEY 8d) / CUDA-event time inside the timed region, last frame; unpack is summed over the frame's batches"}
+           "note": "algorithmic bytes (SURVEY 8d) / CUDA-event time inside the timed region, last frame; one unpack launch per frame"}
     for k, (nbytes, ms) in rows.items():
         gbs = nbytes / (ms / 1e3) / 1e9 if ms > 0 else None
         out[k] = {"bytes": nbytes, "ms": ms, "achieved": gbs, "frac": gbs / hbm_gbs if gbs else None}

@@ -139,7 +139,8 @@ void Engine::unload() {
     allocs.clear();
     dW.clear(); dBias.clear();
     auto freep = [](auto*& p) { if (p) { cudaFree(p); p = nullptr; } };
-    freep(dSlots); freep(dTileOut); freep(dTtaMean); freep(dRampX); freep(dRampY); freep(dFrameIn); freep(dFrameOut);
+    freep(dSlots); freep(dTileOut); freep(dTtaMean); freep(dRampX); freep(dRampY); freep(dFrameIn); freep(dFrameOut); freep(dUnpacked);
+    unpackedCap = 0;
     freep(dBandTiles); freep(dBandMap); freep(dBandSlots); freep(dBandMean);
     bandTilesCap = bandMapCap = bandSlotCap = bandMeanCap = 0;
     if (evBandModel) { cudaEventDestroy(evBandModel); evBandModel = nullptr; }
@@ -439,10 +440,10 @@ void Engine::buildPlanCunet() {
     if (outTile != expect) throw Error("internal: output tile size mismatch");
 }
 
-void Engine::launchLayer(LayerExec& L, cudaStream_t s, __half* outp, int nImg) {
+void Engine::launchLayer(LayerExec& L, cudaStream_t s, __half* outp, int nImg, const __half* inOverride) {
     switch (L.impl) {
         case IMPL_SKIP: break;  // computed inside the next layer's kernel
-        case IMPL_IGEMM: igemmLaunch(L.plan, s, outp, nImg); break;
+        case IMPL_IGEMM: igemmLaunch(L.plan, s, outp, nImg, inOverride); break;
         case IMPL_HEAD: launchConvHead(L.head, s, outp, nImg); break;
         case IMPL_LAYERNORM:
             launchLayerNorm(L.tokIn, L.tokOut, (long long)nImg * L.tokH * L.tokW, L.tokC, L.gamma, L.beta, L.eps, s);
@@ -454,6 +455,7 @@ void Engine::launchLayer(LayerExec& L, cudaStream_t s, __half* outp, int nImg) {
             ConvParams p = L.p;
             p.gn = nImg;
             if (outp) p.out = outp;
+            if (inOverride) p.in = inOverride;
             if (L.impl == IMPL_FIRST) launchConvFirst(p, s);
             else launchConvDirect(p, s);
         }
@@ -665,14 +667,26 @@ double Engine::flopsPerTile() const {
 }
 
 // nImages < batch: the last, partially filled batch of a frame -- the padding slots (img2img_render.cpp:281) are not computed
-void Engine::runModel(cudaStream_t s, __half* finalOut, int nImages) {
+// The layer that reads the model input can be pointed at another buffer when it is a direct / first-layer kernel (plain pointer) or
+// the fused first layer (second tensor map); a first layer on the generic igemm path keeps the per-batch input tensor.
+bool Engine::frameWideUnpack() const {
+    if (layers.size() < 2) return false;
+    const int impl = layers[0].impl;
+    return impl == IMPL_FIRST || impl == IMPL_DIRECT || (impl == IMPL_SKIP && layers[1].plan != nullptr);
+}
+
+// inTiles: this batch's unpacked tiles inside the frame-wide buffer (nullptr: the per-batch input tensor actIn)
+void Engine::runModel(cudaStream_t s, __half* finalOut, int nImages, const __half* inTiles) {
     const int n = (nImages > 0 && nImages < batch) ? nImages : batch;
     // SE accumulators are cleared up front so that the layer chain below is kernel -> kernel only (programmatic dependent launch)
     for (auto& L : layers)
         if (L.seR) W2X_CUDA(cudaMemsetAsync(L.sePartial, 0, L.sePartialBytes, s));
-    for (auto& L : layers) {
+    for (size_t li = 0; li < layers.size(); ++li) {
+        LayerExec& L = layers[li];
         __half* outp = (L.isFinal && finalOut) ? finalOut : L.p.out;
-        launchLayer(L, s, outp, n);
+        // the layer that reads the model input: layer 0, or its fused consumer (layer 1) when layer 0 runs inside it
+        const bool readsInput = inTiles && (li == 0 || (li == 1 && layers[0].impl == IMPL_SKIP));
+        launchLayer(L, s, outp, n, readsInput ? inTiles : nullptr);
         if (L.impl != IMPL_SKIP) ++launches;
         if (debugSync) {
             cudaError_t de = cudaStreamSynchronize(s);
@@ -714,6 +728,17 @@ void Engine::ensureFrameBuffers(int w, int h) {
         slotCap = stepCount;
     }
     uploadAsync(dSlots, slots.data(), sizeof(TileSlot) * stepCount);
+    if (frameWideUnpack()) {
+        const size_t need = (size_t)stepCount * tile * tile * 4;
+        if (need > unpackedCap) {
+            if (dUnpacked) cudaFree(dUnpacked);
+            dUnpacked = nullptr;
+            W2X_CUDA(cudaMalloc(&dUnpacked, need * sizeof(__half)));
+            unpackedCap = need;
+            // a fused RGB first layer reads the buffer through a tensor map of its own
+            if (layers[0].impl == IMPL_SKIP) igemmSetFusedFrameInput(layers[1].plan, dUnpacked, stepCount);
+        }
+    }
     const size_t tileElems = (size_t)outTile * outTile * 4;
     if ((size_t)stepCount * tileElems > tileOutCap) {
         if (dTileOut) cudaFree(dTileOut);
@@ -759,17 +784,26 @@ void Engine::renderOnStream(const uint8_t* dSrc, int w, int h, size_t srcPitch, 
         spans.push_back({kind, i0, evUsed - 1});
     };
     const size_t tileElems = (size_t)outTile * outTile * 4;
-    for (int b = 0; b < batchCount; ++b) {
-        const auto t0 = std::chrono::steady_clock::now();
-        // real (non-padding) slots of this batch: the reference computes the zero padding tiles and discards them (:281,:298)
-        const int realSteps = grid.count * (cfg.tta ? 8 : 1);
-        const int nReal = std::min(batch, realSteps - b * batch);
-        if (nReal <= 0) continue;
+    const size_t inElems = (size_t)tile * tile * 4;
+    // real (non-padding) slots: the reference computes the zero padding tiles of the last batch and discards them (:281,:298)
+    const int realSteps = grid.count * (cfg.tta ? 8 : 1);
+    // all tiles of the frame are unpacked by ONE launch into a frame-wide buffer; the batches then chain kernel -> kernel
+    const bool frameWide = frameWideUnpack();
+    if (frameWide)
         span(0, [&] {
-            launchUnpack(dSrc, w, h, srcPitch, dSlots + (size_t)b * batch, nReal, tile, actIn.p, s);
+            launchUnpack(dSrc, w, h, srcPitch, dSlots, realSteps, tile, dUnpacked, s);
             ++launches;
         });
-        span(1, [&] { runModel(s, dTileOut + (size_t)b * batch * tileElems, nReal); });
+    for (int b = 0; b < batchCount; ++b) {
+        const auto t0 = std::chrono::steady_clock::now();
+        const int nReal = std::min(batch, realSteps - b * batch);
+        if (nReal <= 0) continue;
+        if (!frameWide)
+            span(0, [&] {
+                launchUnpack(dSrc, w, h, srcPitch, dSlots + (size_t)b * batch, nReal, tile, actIn.p, s);
+                ++launches;
+            });
+        span(1, [&] { runModel(s, dTileOut + (size_t)b * batch * tileElems, nReal, frameWide ? dUnpacked + (size_t)b * batch * inElems : nullptr); });
         if (progCb) {
             const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
             progCb(b + 1, batchCount, 1000.0 / std::max(ms, 1e-6), progUser);  // render.cpp:336-338

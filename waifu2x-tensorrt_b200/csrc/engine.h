@@ -97,8 +97,9 @@ private:
     void uploadAsync(void* dst, const void* src, size_t bytes);
     void buildPlanCunet();
     void buildPlanSwin();
-    void launchLayer(LayerExec& L, cudaStream_t s, __half* outOverride, int nImages);
-    void runModel(cudaStream_t s, __half* finalOut, int nImages = 0);
+    void launchLayer(LayerExec& L, cudaStream_t s, __half* outOverride, int nImages, const __half* inOverride = nullptr);
+    void runModel(cudaStream_t s, __half* finalOut, int nImages = 0, const __half* inTiles = nullptr);
+    bool frameWideUnpack() const;
     void ensureFrameBuffers(int w, int h);
     void renderOnStream(const uint8_t* dSrc, int w, int h, size_t srcPitch, uint8_t* dDst, size_t dstPitch, cudaStream_t s, bool timed);
     void* dalloc(size_t bytes);
@@ -132,6 +133,8 @@ private:
     int stepCount = 0, batchCount = 0;
     TileSlot* dSlots = nullptr;
     size_t slotCap = 0;
+    __half* dUnpacked = nullptr;     // [steps][tile][tile][4] fp16: every tile of the frame, unpacked by one launch
+    size_t unpackedCap = 0;
     __half* dTileOut = nullptr;      // [steps][outT][outT][4] fp16
     size_t tileOutCap = 0;
     float* dTtaMean = nullptr;       // [tiles][outT][outT][4] f32 (TTA only)

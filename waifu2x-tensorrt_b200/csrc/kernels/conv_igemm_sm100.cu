@@ -88,6 +88,7 @@ struct ConvArgs {
     int fuseW_px, fuseH_px;
     long long fuseSn;           // elements between images of fuseIn
     uint32_t fuseOff;           // byte offset (from the aligned smem base) of the two RGB patch buffers
+    int fuseImgBase;            // fused first layer reading a frame-wide tile buffer: index of this batch's first image in it
     long long* prof;            // W2X_DEV only: per-CTA cycle counters [grid][16] (W2X_PROF=1), see profSlot
 };
 
@@ -96,6 +97,10 @@ struct IgemmPlan {
     int grid = 0;
     size_t smem = 0;
     bool patch = false;
+    // fused first layer: a second RGB tensor map over the frame-wide unpacked-tile buffer (igemmSetFusedFrameInput)
+    CUtensorMap tmRgbFrame;
+    const __half* frameBase = nullptr;
+    long long frameImages = 0;
 };
 
 namespace {
@@ -654,7 +659,7 @@ __device__ __forceinline__ void fusedFirstProducer(const ConvArgs& a, uint32_t b
     constexpr int kRows = kPatchW * kPatchH;                 // 180 patch pixels
     constexpr int kProdThreads = 32 * kFuseWarps;
     const int tid = threadIdx.x - kThreads;                  // 0 .. 127
-    const int warp = tid >> 5, lane = tid & 31;
+    const int lane = tid & 31;
     const uint32_t barFull = base + kOffFull, barEmpty = base + kOffEmpty;
     const uint32_t barRgbFull = base + kOffRgbFull, barRgbEmpty = base + kOffRgbEmpty, barP1 = base + kOffP1;
     const uint32_t rgb0 = base + a.fuseOff;
@@ -963,7 +968,7 @@ __global__ void __launch_bounds__(kFused ? kThreads + 32 * kFuseWarps : kThreads
                 const int rb = k % kRgbBufs;
                 mbarWait(base + kOffRgbEmpty + 8u * rb, ((uint32_t)(k / kRgbBufs) & 1u) ^ 1u);
                 mbarExpectTx(base + kOffRgbFull + 8u * rb, (uint32_t)((kPatchW + 2) * (kPatchH + 2) * 8));
-                tmaLoad3d(rgb0 + (uint32_t)rb * 2048u, &a.tmRgb, base + kOffRgbFull + 8u * rb, tc.x0 * 4, tc.y0, tc.img);
+                tmaLoad3d(rgb0 + (uint32_t)rb * 2048u, &a.tmRgb, base + kOffRgbFull + 8u * rb, tc.x0 * 4, tc.y0, tc.img + a.fuseImgBase);
             }
         }
     } else if (warp == 0) {
@@ -1718,6 +1723,23 @@ IgemmPlan* igemmCreatePlanFusedFirst(const ConvParams& second, const ConvParams&
 
 void igemmDestroyPlan(IgemmPlan* plan) { delete plan; }
 
+// Fused first layer: let the plan read its RGB tiles from a frame-wide buffer [images][H][W][4] (all tiles of a frame unpacked by
+// one launch) instead of the per-batch input tensor; igemmLaunch(..., inOverride) then selects the batch inside it.
+void igemmSetFusedFrameInput(IgemmPlan* plan, const __half* base, long long images) {
+    ConvArgs& a = plan->args;
+    if (!a.fused) throw Error("igemm: not a fused first-layer plan");
+    if ((reinterpret_cast<uintptr_t>(base) & 15) || images < 1) throw Error("igemm: frame input must be 16-byte aligned");
+    cuuint64_t dims[3] = {(cuuint64_t)a.fuseW_px * 4, (cuuint64_t)a.fuseH_px, (cuuint64_t)images};
+    cuuint64_t strides[2] = {(cuuint64_t)a.fuseW_px * 8, (cuuint64_t)a.fuseSn * 2};
+    cuuint32_t box[3] = {(cuuint32_t)(kPatchW + 2) * 4, (cuuint32_t)(kPatchH + 2), 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    const CUresult r = encodeTiled()(&plan->tmRgbFrame, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw Error("cuTensorMapEncodeTiled(rgb frame) failed with code " + std::to_string((int)r));
+    plan->frameBase = base;
+    plan->frameImages = images;
+}
+
 // 128B-swizzled tensor map over the layer's input view (c, x, z, y, img) with a (64, boxX, 1, boxY, 1) box, for kernels outside
 // this file that stage activation patches with TMA (tm points at a CUtensorMap)
 void encodeActivationMap5d(void* tm, const ConvParams& p, int boxX, int boxY) {
@@ -1739,7 +1761,7 @@ const char* igemmDescribe(const IgemmPlan* plan, char* buf, int cap) {
     return buf;
 }
 
-void igemmLaunch(const IgemmPlan* plan, cudaStream_t s, __half* outOverride, int nImages) {
+void igemmLaunch(const IgemmPlan* plan, cudaStream_t s, __half* outOverride, int nImages, const __half* inOverride) {
     if (plan->grid <= 0) return;
     const bool fewer = nImages > 0 && nImages < plan->args.p.gn;  // last, partially filled batch: skip the padding slots
     const bool redirect = outOverride && outOverride != plan->args.p.out;
@@ -1747,9 +1769,20 @@ void igemmLaunch(const IgemmPlan* plan, cudaStream_t s, __half* outOverride, int
     if (redirect && plan->args.useTma) throw Error("igemm: output redirection is not available for TMA-store layers");
     ConvArgs local;
     const ConvArgs* a = &plan->args;
-    if (redirect || fewer) {
+    const bool frameIn = inOverride && plan->args.fused && inOverride != plan->args.fuseIn;
+    if (inOverride && !plan->args.fused && inOverride != plan->args.p.in) throw Error("igemm: input redirection is only available for the fused first layer");
+    if (frameIn) {
+        const long long off = inOverride - plan->frameBase;
+        if (!plan->frameBase || off < 0 || off % plan->args.fuseSn || off / plan->args.fuseSn + (nImages > 0 ? nImages : plan->args.p.gn) > plan->frameImages)
+            throw Error("igemm: input override lies outside the registered frame buffer");
+    }
+    if (redirect || fewer || frameIn) {
         local = plan->args;  // only the epilogue's destination / the image count change; the tensor maps stay valid
         if (redirect) local.p.out = outOverride;
+        if (frameIn) {
+            local.tmRgb = plan->tmRgbFrame;
+            local.fuseImgBase = (int)((inOverride - plan->frameBase) / plan->args.fuseSn);
+        }
         if (fewer) {
             local.totalTiles = local.totalTiles / local.p.gn * nImages;
             local.p.gn = nImages;

@@ -186,7 +186,8 @@ IgemmPlan* igemmCreatePlan(const ConvParams& p);                  // throws w2x:
 void igemmDestroyPlan(IgemmPlan* plan);
 bool igemmFusedFirstSupported(const ConvParams& second, const ConvParams& first);  // conv(4->32)+lrelu computed inside conv(32->64)
 IgemmPlan* igemmCreatePlanFusedFirst(const ConvParams& second, const ConvParams& first);
-void igemmLaunch(const IgemmPlan* plan, cudaStream_t s, __half* outOverride = nullptr, int nImages = 0);
+void igemmLaunch(const IgemmPlan* plan, cudaStream_t s, __half* outOverride = nullptr, int nImages = 0, const __half* inOverride = nullptr);
+void igemmSetFusedFrameInput(IgemmPlan* plan, const __half* base, long long images);
 bool igemmSupported(const ConvParams& p);
 const char* igemmDescribe(const IgemmPlan* plan, char* buf, int cap);
 bool igemmSeFusable(const IgemmPlan* plan);  // can this layer's epilogue produce ConvParams::se_sum?
