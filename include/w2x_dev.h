@@ -30,6 +30,13 @@ extern "C" {
 W2X_API int w2x_run_conv_layer(int device, int kind, int head, int n, int h, int w, int cin, int cout, const uint16_t* in_nhwc,
                                const uint16_t* weights, const float* bias, const uint16_t* skip_nhwc, uint16_t* out_nhwc);
 
+/* The fused MLP half of a SwinUNet block (kernels/swin_mlp_sm100.cu; replaces a slice of the engine enqueued at img2img_infer.cpp:80):
+ * x[tokens][96] (NHWC fp16 bits, updated in place) += fc2(GELU(fc1(LayerNorm(x)))), w1 = [192][96], w2 = [96][192] fp16 bits (K-major),
+ * gamma / beta [96], b1 [192], b2 [96].  ms_out (optional) receives the average device time of `reps` further launches on the same
+ * buffer.  Returns 1 on success. */
+W2X_API int w2x_run_swin_mlp(int device, long long tokens, uint16_t* x, const float* gamma, const float* beta, float eps, const uint16_t* w1,
+                             const float* b1, const uint16_t* w2, const float* b2, int reps, float* ms_out);
+
 /* One convolution layer of the implicit-GEMM family on random data, tcgen05 kernel vs the scalar CUDA reference
  * kernel, for on-device self-checks: returns max |diff| (negative on error).  kind: 0 conv3x3, 1 conv2x2s2,
  * 2 convT2x2s2(+skip), 3 convT4x4s2p3->4ch, 4 conv3x3->3ch final(+skip,clamp), 5 = kind 4 through the image-head kernel,

@@ -276,6 +276,48 @@ int w2x_run_conv_layer(int device, int kind, int head, int n, int h, int w, int 
     }
 }
 
+int w2x_run_swin_mlp(int device, long long tokens, uint16_t* x, const float* gamma, const float* beta, float eps, const uint16_t* w1, const float* b1,
+                     const uint16_t* w2, const float* b2, int reps, float* ms_out) {
+    void* bufs[7] = {};
+    SwinMlpPlan* plan = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    int ok = 0;
+    try {
+        if (tokens < 1 || !x || !gamma || !beta || !w1 || !b1 || !w2 || !b2) throw Error("invalid argument");
+        W2X_CUDA(cudaSetDevice(device));
+        const size_t sizes[7] = {(size_t)tokens * 96 * 2, 96 * 4, 96 * 4, 192 * 96 * 2, 192 * 4, 96 * 192 * 2, 96 * 4};
+        const void* host[7] = {x, gamma, beta, w1, b1, w2, b2};
+        for (int i = 0; i < 7; ++i) {
+            W2X_CUDA(cudaMalloc(&bufs[i], sizes[i]));
+            W2X_CUDA(cudaMemcpy(bufs[i], host[i], sizes[i], cudaMemcpyHostToDevice));
+        }
+        plan = swinMlpCreatePlan((__half*)bufs[0], (const float*)bufs[1], (const float*)bufs[2], eps, (const __half*)bufs[3], (const float*)bufs[4],
+                                 (const __half*)bufs[5], (const float*)bufs[6]);
+        swinMlpLaunch(plan, nullptr, tokens);
+        W2X_CUDA(cudaDeviceSynchronize());
+        W2X_CUDA(cudaMemcpy(x, bufs[0], sizes[0], cudaMemcpyDeviceToHost));
+        if (ms_out && reps > 0) {
+            W2X_CUDA(cudaEventCreate(&e0));
+            W2X_CUDA(cudaEventCreate(&e1));
+            W2X_CUDA(cudaEventRecord(e0, nullptr));
+            for (int i = 0; i < reps; ++i) swinMlpLaunch(plan, nullptr, tokens);
+            W2X_CUDA(cudaEventRecord(e1, nullptr));
+            W2X_CUDA(cudaEventSynchronize(e1));
+            W2X_CUDA(cudaEventElapsedTime(ms_out, e0, e1));
+            *ms_out /= (float)reps;
+        }
+        ok = 1;
+    } catch (const std::exception& ex) {
+        std::fprintf(stderr, "w2x_run_swin_mlp: %s\n", ex.what());
+    }
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (plan) swinMlpDestroyPlan(plan);
+    for (void* b : bufs)
+        if (b) cudaFree(b);
+    return ok;
+}
+
 #ifdef W2X_DEV
 int w2x_probe_umma(int device, int mode, int pitch, float* err9) {
     try {

@@ -133,6 +133,7 @@ void Engine::unload() {
     for (auto& L : layers) {
         if (L.plan) igemmDestroyPlan(L.plan);
         if (L.head) convHeadDestroyPlan(L.head);
+        if (L.mlp) swinMlpDestroyPlan(L.mlp);
     }
     layers.clear();
     for (void* p : allocs) cudaFree(p);
@@ -445,6 +446,7 @@ void Engine::launchLayer(LayerExec& L, cudaStream_t s, __half* outp, int nImg, c
         case IMPL_SKIP: break;  // computed inside the next layer's kernel
         case IMPL_IGEMM: igemmLaunch(L.plan, s, outp, nImg, inOverride); break;
         case IMPL_HEAD: launchConvHead(L.head, s, outp, nImg); break;
+        case IMPL_SWIN_MLP: swinMlpLaunch(L.mlp, s, (long long)nImg * L.tokH * L.tokW); break;
         case IMPL_LAYERNORM:
             launchLayerNorm(L.tokIn, L.tokOut, (long long)nImg * L.tokH * L.tokW, L.tokC, L.gamma, L.beta, L.eps, s);
             break;
@@ -588,9 +590,27 @@ void Engine::buildPlanSwin() {
             layers.push_back(E);
         }
         linear(pj, att, x, ACT_LRELU, &x);   // x += proj(attn)
-        pushLn(n2);
-        linear(f1, ln, hid, ACT_GELU, nullptr);
-        linear(f2, hid, x, ACT_LRELU, &x);   // x += fc2(gelu(fc1(ln)))
+        const PackedLayer &F1 = model.layers[f1], &F2 = model.layers[f2];
+        if (!useDirect && !devEnv("W2X_NO_MLP_FUSE") && swinMlpSupported(c, (int)F1.npad) && (int)F1.ktot == c && (int)F2.npad == c && F2.ktot == F1.npad) {
+            // x += fc2(gelu(fc1(LayerNorm(x)))) in ONE kernel: the normalised rows and the hidden tensor stay in shared memory
+            for (size_t i : {n2, f1}) {
+                LayerExec S;
+                S.name = model.layers[i].name;
+                S.impl = IMPL_SKIP;
+                layers.push_back(S);
+            }
+            LayerExec E;
+            E.name = F2.name;
+            E.impl = IMPL_SWIN_MLP;
+            E.tokN = x.n; E.tokH = h; E.tokW = w; E.tokC = c;
+            E.flops = 2.0 * h * w * ((double)F1.npad * F1.ktot + (double)F2.npad * F2.ktot);
+            E.mlp = swinMlpCreatePlan(x.p, dAux0[n2], dAux1[n2], model.layers[n2].eps, dW[f1], dBias[f1], dW[f2], dBias[f2]);
+            layers.push_back(E);
+        } else {
+            pushLn(n2);
+            linear(f1, ln, hid, ACT_GELU, nullptr);
+            linear(f2, hid, x, ACT_LRELU, &x);   // x += fc2(gelu(fc1(ln)))
+        }
         ++blockIndex;
     };
     auto stage = [&](Act& x) {
@@ -654,6 +674,7 @@ int Engine::layerKernel(int index, char* buf, int cap) const {
     if (index < 0 || index >= (int)layers.size()) return 0;
     const LayerExec& L = layers[index];
     if (L.plan) igemmDescribe(L.plan, buf, cap);
+    else if (L.mlp) swinMlpDescribe(buf, cap);
     else std::snprintf(buf, cap, "%s", L.impl == IMPL_FIRST ? "first-layer mma.sync" : L.impl == IMPL_LAYERNORM ? "layernorm" :
                                        L.impl == IMPL_ATTENTION ? "window-attention mma.sync" :
                                        L.impl == IMPL_HEAD ? "head kernel, taps in N (tcgen05)" : L.impl == IMPL_SKIP ? "fused into the next layer" : "direct (reference kernel)");

@@ -1749,6 +1749,19 @@ void encodeActivationMap5d(void* tm, const ConvParams& p, int boxX, int boxY) {
     encode5d(static_cast<CUtensorMap*>(tm), p.in, dims, st, box, true, "activation patch");
 }
 
+// swizzled 2-D tensor map over a K-major fp16 matrix [rows][k] with a (boxK, boxRows) box (64-byte swizzle for boxK = 32, 128-byte for
+// boxK = 64), for kernels outside this file that keep weight matrices resident in shared memory as UMMA operands
+void encodeMatrixMap2d(void* tm, const void* ptr, long long k, long long rows, int boxK, int boxRows, bool sw128) {
+    cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)k * 2};
+    cuuint32_t box[2] = {(cuuint32_t)boxK, (cuuint32_t)boxRows};
+    cuuint32_t es[2] = {1, 1};
+    const CUresult r = encodeTiled()(static_cast<CUtensorMap*>(tm), CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, es,
+                                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw Error("cuTensorMapEncodeTiled(matrix) failed with code " + std::to_string((int)r));
+}
+
 bool igemmSeFusable(const IgemmPlan* plan) {
     const ConvArgs& a = plan->args;
     return a.useTma && !a.hasSkip && a.nbuf >= 2 && a.tilesN == 1 && a.bn >= 64;

@@ -181,6 +181,13 @@ HeadPlan* convHeadCreatePlan(const ConvParams& p);
 void convHeadDestroyPlan(HeadPlan* plan);
 void launchConvHead(const HeadPlan* plan, cudaStream_t s, __half* outOverride = nullptr, int nImages = 0);
 void encodeActivationMap5d(void* tensorMap, const ConvParams& p, int boxX, int boxY);  // conv_igemm_sm100.cu
+void encodeMatrixMap2d(void* tensorMap, const void* ptr, long long k, long long rows, int boxK, int boxRows, bool sw128);  // conv_igemm_sm100.cu
+struct SwinMlpPlan;                                               // fused LN + fc1 + GELU + fc2 + residual (kernels/swin_mlp_sm100.cu)
+bool swinMlpSupported(int c, int hidden);
+SwinMlpPlan* swinMlpCreatePlan(__half* x, const float* gamma, const float* beta, float eps, const __half* w1, const float* b1, const __half* w2, const float* b2);
+void swinMlpDestroyPlan(SwinMlpPlan* plan);
+void swinMlpLaunch(const SwinMlpPlan* plan, cudaStream_t s, long long tokens);
+const char* swinMlpDescribe(char* buf, int cap);
 struct IgemmPlan;                                                 // opaque: tensor maps + launch geometry
 IgemmPlan* igemmCreatePlan(const ConvParams& p);                  // throws w2x::Error when unsupported
 void igemmDestroyPlan(IgemmPlan* plan);

@@ -1,0 +1,385 @@
+// Fused MLP half of a SwinUNet block (torchvision SwinTransformerBlock: x = x + fc2(GELU(fc1(LayerNorm(x))))), one kernel
+// instead of layernorm_kernel + two igemm_kernel launches.  Per 128-token tile the token rows are read from HBM once and written
+// once; the normalised rows, the hidden tensor (2C wide) and both weight matrices never leave the SM:
+//
+//   warps 0-3   producers: one token row per thread (192 B, twelve 16-byte loads in flight), LayerNorm in registers (two-pass, fp32),
+//               fp16 rows written into shared memory in the SWIZZLE_64B K-major layout of a UMMA A operand (three 32-channel chunks)
+//   warp  4     MMA issuer (one elected lane): fc1 = 6 x tcgen05.mma M128 N192 K16 into a double-buffered TMEM accumulator,
+//               fc2 = 12 x M128 N96 K16 whose A operand is the hidden tile the epilogue warps wrote; fc1 of tile k+1 is queued
+//               before fc2 of tile k, so the tensor pipe works while the CUDA cores evaluate GELU
+//   warps 5-12  epilogue (two warps per TMEM lane quarter, splitting the columns): phase 1 = tcgen05.ld, + bias, erf-GELU, fp16,
+//               written as the SWIZZLE_128B A operand of fc2; phase 2 = tcgen05.ld, + bias + residual (prefetched from x), 16-byte
+//               stores to x in place.  Phase 1 of tile k+1 runs before phase 2 of tile k (fc2 of tile k executes meanwhile).
+//
+// Both weight matrices (2 x 36 KB for C = 96) are TMA-loaded once per CTA and stay resident.  The kernel is bound by the GELU
+// evaluation on the CUDA cores (128 x 192 values per tile), not by HBM or the tensor pipe.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <string>
+
+#include "conv_params.h"
+#include "launch.h"
+#include "sm100_common.cuh"
+
+namespace w2x {
+using namespace sm100;
+namespace {
+
+constexpr int kC = 96;             // token width
+constexpr int kHid = 192;          // hidden width (mlp_ratio 2)
+constexpr int kRows = 128;         // tokens per tile = UMMA M
+constexpr int kProdWarps = 4;
+constexpr int kMmaWarp = 4;
+constexpr int kEpiWarp0 = 5;
+constexpr int kEpiWarps = 8;
+constexpr int kMlpThreads = 32 * (kEpiWarp0 + kEpiWarps);   // 416
+
+// shared-memory map (byte offsets from the 1024-aligned base)
+constexpr uint32_t kBarW = 0, kBarAFull = 8, kBarAEmpty = 24, kBarD1Full = 40, kBarD1Empty = 56, kBarHFull = 72, kBarHEmpty = 88, kBarD2Full = 104,
+                   kBarD2Empty = 112, kTmemSlot = 120;
+constexpr uint32_t kOffB1 = 256, kOffB2 = kOffB1 + kHid * 4, kOffGamma = kOffB2 + kC * 4, kOffBeta = kOffGamma + kC * 4;
+constexpr uint32_t kW1Chunk = kHid * 64;          // [192 rows][32 k] fp16, SWIZZLE_64B
+constexpr uint32_t kW2Chunk = kC * 128;           // [96 rows][64 k] fp16, SWIZZLE_128B
+constexpr uint32_t kAChunk = kRows * 64;          // [128 rows][32 k]
+constexpr uint32_t kHChunk = kRows * 128;         // [128 rows][64 k]
+constexpr uint32_t kOffW1 = 4096;
+constexpr uint32_t kOffW2 = kOffW1 + 3 * kW1Chunk;
+constexpr uint32_t kOffA = kOffW2 + 3 * kW2Chunk;
+constexpr uint32_t kOffH = kOffA + 2 * 3 * kAChunk;
+constexpr uint32_t kMlpSmem = kOffH + 2 * 3 * kHChunk + 1024;   // + alignment slack
+static_assert(kOffBeta + kC * 4 <= kOffW1, "constants overflow the header");
+static_assert(kOffW2 % 1024 == 0 && kOffA % 1024 == 0 && kOffH % 1024 == 0, "swizzled operands need 1024-byte alignment");
+static_assert(kMlpSmem <= 227 * 1024, "shared memory budget");
+constexpr uint32_t kTmemD2 = 2 * kHid;            // columns: D1 buffers at 0 and 192, D2 at 384
+constexpr uint32_t kTmemCols = 512;
+
+struct MlpArgs {
+    CUtensorMap tmW1, tmW2;
+    __half* x;                 // [tokens][96] fp16, updated in place
+    const float* b1;           // [192]
+    const float* b2;           // [96]
+    const float* gamma;        // [96]
+    const float* beta;         // [96]
+    float eps;
+    long long tokens;
+};
+
+__device__ __forceinline__ void stsF32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+__device__ __forceinline__ void unpack8(const uint4& raw, float (&v)[8]) {
+    const __half2* h = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 f = __half22float2(h[i]);
+        v[2 * i] = f.x;
+        v[2 * i + 1] = f.y;
+    }
+}
+__device__ __forceinline__ void loadF8(uint32_t addr, float (&v)[8]) {
+    const uint4 a = ldsV4(addr), b = ldsV4(addr + 16u);
+    v[0] = __uint_as_float(a.x); v[1] = __uint_as_float(a.y); v[2] = __uint_as_float(a.z); v[3] = __uint_as_float(a.w);
+    v[4] = __uint_as_float(b.x); v[5] = __uint_as_float(b.y); v[6] = __uint_as_float(b.z); v[7] = __uint_as_float(b.w);
+}
+
+__global__ void __launch_bounds__(kMlpThreads, 1) swin_mlp_kernel(const __grid_constant__ MlpArgs a) {
+    extern __shared__ uint8_t smemRaw[];
+    const uint32_t base = (smemU32(smemRaw) + 1023u) & ~1023u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    pdlLaunchDependents();
+
+    // ---- prologue: constants only (weights, biases, LayerNorm parameters) ----
+    if (threadIdx.x == 0) {
+        mbarInit(base + kBarW, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbarInit(base + kBarAFull + 8u * i, kProdWarps);
+            mbarInit(base + kBarAEmpty + 8u * i, 1);
+            mbarInit(base + kBarD1Full + 8u * i, 1);
+            mbarInit(base + kBarD1Empty + 8u * i, kEpiWarps);
+            mbarInit(base + kBarHFull + 8u * i, kEpiWarps);
+            mbarInit(base + kBarHEmpty + 8u * i, 1);
+        }
+        mbarInit(base + kBarD2Full, 1);
+        mbarInit(base + kBarD2Empty, kEpiWarps);
+        mbarInitFence();
+        tmaPrefetchDesc(&a.tmW1);
+        tmaPrefetchDesc(&a.tmW2);
+    }
+    for (int i = threadIdx.x; i < kHid; i += kMlpThreads) stsF32(base + kOffB1 + 4u * i, a.b1[i]);
+    for (int i = threadIdx.x; i < kC; i += kMlpThreads) {
+        stsF32(base + kOffB2 + 4u * i, a.b2[i]);
+        stsF32(base + kOffGamma + 4u * i, a.gamma[i]);
+        stsF32(base + kOffBeta + 4u * i, a.beta[i]);
+    }
+    if (warp == kMmaWarp) tmemAlloc(base + kTmemSlot, kTmemCols);
+    tcFenceBefore();
+    __syncthreads();
+    tcFenceAfter();
+    uint32_t tmemBase;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmemBase) : "r"(base + kTmemSlot));
+    if (warp == kMmaWarp && lane == 0) {
+        mbarExpectTx(base + kBarW, 3 * kW1Chunk + 3 * kW2Chunk);
+        for (int kc = 0; kc < 3; ++kc) {
+            tmaLoad2d(base + kOffW1 + kc * kW1Chunk, &a.tmW1, base + kBarW, kc * 32, 0);
+            tmaLoad2d(base + kOffW2 + kc * kW2Chunk, &a.tmW2, base + kBarW, kc * 64, 0);
+        }
+    }
+    const long long tiles = (a.tokens + kRows - 1) / kRows;
+    const int first = blockIdx.x, step = gridDim.x;
+    const int nMine = first < tiles ? (int)((tiles - first + step - 1) / step) : 0;
+    pdlWait();  // x is written by the preceding kernel
+
+    if (warp < kProdWarps) {
+        // ---- LayerNorm producers: thread = token row ----
+        const int t = threadIdx.x;
+        const uint32_t sw = (uint32_t)(t >> 1) & 3u;
+        for (int k = 0; k < nMine; ++k) {
+            const long long g = ((long long)first + (long long)k * step) * kRows + t;
+            const bool valid = g < a.tokens;
+            uint4 raw[12];
+#pragma unroll
+            for (int j = 0; j < 12; ++j) raw[j] = make_uint4(0, 0, 0, 0);
+            if (valid) {
+                const uint4* src = reinterpret_cast<const uint4*>(a.x + g * kC);
+#pragma unroll
+                for (int j = 0; j < 12; ++j) raw[j] = src[j];
+            }
+            float sum = 0.f;
+#pragma unroll
+            for (int j = 0; j < 12; ++j) {
+                float v[8];
+                unpack8(raw[j], v);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) sum += v[i];
+            }
+            const float mean = sum * (1.f / kC);
+            float sq = 0.f;
+#pragma unroll
+            for (int j = 0; j < 12; ++j) {
+                float v[8];
+                unpack8(raw[j], v);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { const float d = v[i] - mean; sq += d * d; }
+            }
+            const float rstd = rsqrtf(sq * (1.f / kC) + a.eps);
+            const int buf = k & 1;
+            mbarWait(base + kBarAEmpty + 8u * buf, (uint32_t)((k >> 1) & 1) ^ 1u);   // fc1 of tile k-2 has consumed this buffer
+            const uint32_t rowAddr = base + kOffA + (uint32_t)buf * 3u * kAChunk + (uint32_t)t * 64u;
+#pragma unroll
+            for (int j = 0; j < 12; ++j) {
+                float v[8], gm[8], bt[8];
+                unpack8(raw[j], v);
+                loadF8(base + kOffGamma + 32u * j, gm);
+                loadF8(base + kOffBeta + 32u * j, bt);
+                uint4 o;
+                __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    oh[i] = __floats2half2_rn((v[2 * i] - mean) * rstd * gm[2 * i] + bt[2 * i], (v[2 * i + 1] - mean) * rstd * gm[2 * i + 1] + bt[2 * i + 1]);
+                if (!valid) o = make_uint4(0, 0, 0, 0);
+                stsV4(rowAddr + (uint32_t)(j >> 2) * kAChunk + ((((uint32_t)j & 3u) ^ sw) << 4), o);
+            }
+            fenceProxyAsync();  // generic-proxy stores -> visible to the tensor core's operand reads
+            __syncwarp();
+            if (lane == 0) mbarArrive(base + kBarAFull + 8u * buf);
+        }
+    } else if (warp == kMmaWarp) {
+        // ---- MMA issuer: whole warp converged, one elected lane issues ----
+        const uint32_t hi64 = descHi(512u, 4u), hi128 = descHi(1024u, 2u);
+        const uint32_t idesc1 = instrDescF16(kRows, kHid), idesc2 = instrDescF16(kRows, kC);
+        auto fc1 = [&](int t) {
+            const int buf = t & 1;
+            const uint32_t ph = (uint32_t)(t >> 1) & 1u;
+            mbarWait(base + kBarAFull + 8u * buf, ph);
+            mbarWait(base + kBarD1Empty + 8u * buf, ph ^ 1u);
+            tcFenceAfter();
+            if (electOne()) {
+                const uint32_t aBase = base + kOffA + (uint32_t)buf * 3u * kAChunk;
+#pragma unroll
+                for (int kc = 0; kc < 3; ++kc)
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks)
+                        ummaLoHi(tmemBase + (uint32_t)buf * kHid, descLo(aBase + kc * kAChunk + ks * 32u), hi64, descLo(base + kOffW1 + kc * kW1Chunk + ks * 32u), hi64,
+                                 idesc1, (kc | ks) != 0 ? 1u : 0u);
+                tcCommit(base + kBarD1Full + 8u * buf);
+                tcCommit(base + kBarAEmpty + 8u * buf);
+            }
+            __syncwarp();
+        };
+        auto fc2 = [&](int t) {
+            const int buf = t & 1;
+            mbarWait(base + kBarHFull + 8u * buf, (uint32_t)(t >> 1) & 1u);
+            mbarWait(base + kBarD2Empty, ((uint32_t)t & 1u) ^ 1u);
+            tcFenceAfter();
+            if (electOne()) {
+                const uint32_t hBase = base + kOffH + (uint32_t)buf * 3u * kHChunk;
+#pragma unroll
+                for (int kc = 0; kc < 3; ++kc)
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)
+                        ummaLoHi(tmemBase + kTmemD2, descLo(hBase + kc * kHChunk + ks * 32u), hi128, descLo(base + kOffW2 + kc * kW2Chunk + ks * 32u), hi128, idesc2,
+                                 (kc | ks) != 0 ? 1u : 0u);
+                tcCommit(base + kBarD2Full);
+                tcCommit(base + kBarHEmpty + 8u * buf);
+            }
+            __syncwarp();
+        };
+        mbarWait(base + kBarW, 0);
+        if (nMine > 0) fc1(0);
+        for (int k = 0; k < nMine; ++k) {
+            if (k + 1 < nMine) fc1(k + 1);
+            fc2(k);
+        }
+    } else {
+        // ---- epilogue warps ----
+        const int quarter = warp & 3;                // TMEM lane quarter this warp may read: its index in the CTA modulo 4
+        const int half = (warp - kEpiWarp0) >> 2;    // which half of the accumulator columns
+        const int row = quarter * 32 + lane;
+        const uint32_t taddrLane = tmemBase + ((uint32_t)(quarter * 32) << 16);
+        const uint32_t sw = (uint32_t)row & 7u;
+        uint32_t r[32];
+        auto phase1 = [&](int t) {   // hidden = GELU(fc1 + b1) -> shared memory (A operand of fc2)
+            const int buf = t & 1;
+            const uint32_t ph = (uint32_t)(t >> 1) & 1u;
+            mbarWait(base + kBarD1Full + 8u * buf, ph);
+            tcFenceAfter();
+            mbarWait(base + kBarHEmpty + 8u * buf, ph ^ 1u);   // fc2 of tile t-2 has consumed this hidden buffer
+            const uint32_t hRow = base + kOffH + (uint32_t)buf * 3u * kHChunk + (uint32_t)row * 128u;
+#pragma unroll 1
+            for (int c = 0; c < 3; ++c) {
+                const int col0 = half * (kHid / 2) + c * 32;
+                tmemLd32(taddrLane + (uint32_t)(buf * kHid + col0), r);
+                tmemLdWait();
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int h0 = col0 + 8 * q;
+                    float bias[8];
+                    loadF8(base + kOffB1 + 4u * h0, bias);
+                    uint4 o;
+                    __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        oh[i] = __floats2half2_rn(geluErf(__uint_as_float(r[8 * q + 2 * i]) + bias[2 * i]), geluErf(__uint_as_float(r[8 * q + 2 * i + 1]) + bias[2 * i + 1]));
+                    stsV4(hRow + (uint32_t)(h0 >> 6) * kHChunk + (((uint32_t)((h0 & 63) >> 3) ^ sw) << 4), o);
+                }
+            }
+            fenceProxyAsync();
+            tcFenceBefore();
+            __syncwarp();
+            if (lane == 0) {
+                mbarArrive(base + kBarHFull + 8u * buf);
+                mbarArrive(base + kBarD1Empty + 8u * buf);
+            }
+        };
+        auto phase2 = [&](int t) {   // x += fc2 + b2
+            const long long g = ((long long)first + (long long)t * step) * kRows + row;
+            const bool valid = g < a.tokens;
+            const int col0 = half * (kC / 2);
+            __half* xrow = a.x + g * kC + col0;
+            uint4 res[6];
+#pragma unroll
+            for (int j = 0; j < 6; ++j) res[j] = make_uint4(0, 0, 0, 0);
+            if (valid) {
+#pragma unroll
+                for (int j = 0; j < 6; ++j) res[j] = reinterpret_cast<const uint4*>(xrow)[j];   // residual in flight while fc2 finishes
+            }
+            mbarWait(base + kBarD2Full, (uint32_t)t & 1u);
+            tcFenceAfter();
+            uint32_t r2[32];
+            tmemLd32(taddrLane + kTmemD2 + (uint32_t)col0, r);
+            tmemLd16(taddrLane + kTmemD2 + (uint32_t)col0 + 32u, r2);
+            tmemLdWait();
+            tcFenceBefore();
+            __syncwarp();
+            if (lane == 0) mbarArrive(base + kBarD2Empty);
+            if (valid) {
+#pragma unroll
+                for (int j = 0; j < 6; ++j) {
+                    float bias[8], rv[8];
+                    loadF8(base + kOffB2 + 4u * (col0 + 8 * j), bias);
+                    unpack8(res[j], rv);
+                    uint4 o;
+                    __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float a0 = __uint_as_float(j < 4 ? r[8 * j + 2 * i] : r2[8 * (j - 4) + 2 * i]);
+                        const float a1 = __uint_as_float(j < 4 ? r[8 * j + 2 * i + 1] : r2[8 * (j - 4) + 2 * i + 1]);
+                        oh[i] = __floats2half2_rn(a0 + bias[2 * i] + rv[2 * i], a1 + bias[2 * i + 1] + rv[2 * i + 1]);
+                    }
+                    reinterpret_cast<uint4*>(xrow)[j] = o;
+                }
+            }
+        };
+        if (nMine > 0) phase1(0);
+        for (int k = 0; k < nMine; ++k) {
+            if (k + 1 < nMine) phase1(k + 1);
+            phase2(k);
+        }
+    }
+
+    tcFenceBefore();
+    __syncthreads();
+    if (warp == kMmaWarp) {
+        tcFenceAfter();
+        tmemDealloc(tmemBase, kTmemCols);
+    }
+}
+
+}  // namespace
+
+struct SwinMlpPlan {
+    MlpArgs args;
+};
+
+bool swinMlpSupported(int c, int hidden) { return c == kC && hidden == kHid; }
+
+SwinMlpPlan* swinMlpCreatePlan(__half* x, const float* gamma, const float* beta, float eps, const __half* w1, const float* b1, const __half* w2, const float* b2) {
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w1) | reinterpret_cast<uintptr_t>(w2)) & 15) throw Error("swin mlp: operands must be 16-byte aligned");
+    SwinMlpPlan* plan = new SwinMlpPlan{};
+    try {
+        encodeMatrixMap2d(&plan->args.tmW1, w1, kC, kHid, 32, kHid, false);     // fc1 weights [192][96], K-major
+        encodeMatrixMap2d(&plan->args.tmW2, w2, kHid, kC, 64, kC, true);        // fc2 weights [96][192]
+    } catch (...) {
+        delete plan;
+        throw;
+    }
+    plan->args.x = x;
+    plan->args.b1 = b1;
+    plan->args.b2 = b2;
+    plan->args.gamma = gamma;
+    plan->args.beta = beta;
+    plan->args.eps = eps;
+    plan->args.tokens = 0;
+    return plan;
+}
+
+void swinMlpDestroyPlan(SwinMlpPlan* plan) { delete plan; }
+
+const char* swinMlpDescribe(char* buf, int cap) {
+    std::snprintf(buf, cap, "swin-mlp fused LN+fc1+GELU+fc2+residual (tcgen05) c=%d hidden=%d rows=%d smem=%u", kC, kHid, kRows, kMlpSmem);
+    return buf;
+}
+
+void swinMlpLaunch(const SwinMlpPlan* plan, cudaStream_t s, long long tokens) {
+    static bool attrSet[64] = {};
+    static int sms[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (!attrSet[dev]) {
+        cudaFuncSetAttribute(swin_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMlpSmem);
+        cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+        if (sms[dev] <= 0) sms[dev] = 148;
+        attrSet[dev] = true;
+    }
+    if (tokens <= 0) return;
+    MlpArgs a = plan->args;
+    a.tokens = tokens;
+    const long long tiles = (tokens + kRows - 1) / kRows;
+    const dim3 grid((unsigned)(tiles < sms[dev] ? tiles : sms[dev]));
+    const cudaError_t e = launchPdl(swin_mlp_kernel, grid, dim3(kMlpThreads), kMlpSmem, s, a);
+    if (e != cudaSuccess) throw Error(std::string("swin mlp launch: ") + cudaGetErrorString(e));
+}
+
+}  // namespace w2x
