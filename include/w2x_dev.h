@@ -31,11 +31,12 @@ W2X_API int w2x_run_conv_layer(int device, int kind, int head, int n, int h, int
                                const uint16_t* weights, const float* bias, const uint16_t* skip_nhwc, uint16_t* out_nhwc);
 
 /* The fused MLP half of a SwinUNet block (kernels/swin_mlp_sm100.cu; replaces a slice of the engine enqueued at img2img_infer.cpp:80):
- * x[tokens][96] (NHWC fp16 bits, updated in place) += fc2(GELU(fc1(LayerNorm(x)))), w1 = [192][96], w2 = [96][192] fp16 bits (K-major),
- * gamma / beta [96], b1 [192], b2 [96].  ms_out (optional) receives the average device time of `reps` further launches on the same
- * buffer.  Returns 1 on success. */
-W2X_API int w2x_run_swin_mlp(int device, long long tokens, uint16_t* x, const float* gamma, const float* beta, float eps, const uint16_t* w1,
-                             const float* b1, const uint16_t* w2, const float* b2, int reps, float* ms_out);
+ * x[tokens][c] (NHWC fp16 bits, updated in place) += fc2(GELU(fc1(LayerNorm(x)))), c = 96 or 192, w1 = [2c][c], w2 = [c][2c] fp16 bits
+ * (K-major), gamma / beta [c], b1 [2c], b2 [c].  variant 0 = the kernel the planner picks (weights resident for c = 96, streamed per
+ * hidden chunk for c = 192), 1 = streamed weights.  ms_out (optional) receives the average device time of `reps` further launches on
+ * the same buffer.  Returns 1 on success. */
+W2X_API int w2x_run_swin_mlp(int device, long long tokens, int c, int variant, uint16_t* x, const float* gamma, const float* beta, float eps,
+                             const uint16_t* w1, const float* b1, const uint16_t* w2, const float* b2, int reps, float* ms_out);
 
 /* One convolution layer of the implicit-GEMM family on random data, tcgen05 kernel vs the scalar CUDA reference
  * kernel, for on-device self-checks: returns max |diff| (negative on error).  kind: 0 conv3x3, 1 conv2x2s2,

@@ -276,23 +276,24 @@ int w2x_run_conv_layer(int device, int kind, int head, int n, int h, int w, int 
     }
 }
 
-int w2x_run_swin_mlp(int device, long long tokens, uint16_t* x, const float* gamma, const float* beta, float eps, const uint16_t* w1, const float* b1,
-                     const uint16_t* w2, const float* b2, int reps, float* ms_out) {
+int w2x_run_swin_mlp(int device, long long tokens, int c, int variant, uint16_t* x, const float* gamma, const float* beta, float eps, const uint16_t* w1,
+                     const float* b1, const uint16_t* w2, const float* b2, int reps, float* ms_out) {
     void* bufs[7] = {};
     SwinMlpPlan* plan = nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     int ok = 0;
     try {
-        if (tokens < 1 || !x || !gamma || !beta || !w1 || !b1 || !w2 || !b2) throw Error("invalid argument");
+        if (tokens < 1 || !x || !gamma || !beta || !w1 || !b1 || !w2 || !b2 || !swinMlpSupported(c, 2 * c)) throw Error("invalid argument");
         W2X_CUDA(cudaSetDevice(device));
-        const size_t sizes[7] = {(size_t)tokens * 96 * 2, 96 * 4, 96 * 4, 192 * 96 * 2, 192 * 4, 96 * 192 * 2, 96 * 4};
+        const size_t C = (size_t)c;
+        const size_t sizes[7] = {(size_t)tokens * C * 2, C * 4, C * 4, 2 * C * C * 2, 2 * C * 4, 2 * C * C * 2, C * 4};
         const void* host[7] = {x, gamma, beta, w1, b1, w2, b2};
         for (int i = 0; i < 7; ++i) {
             W2X_CUDA(cudaMalloc(&bufs[i], sizes[i]));
             W2X_CUDA(cudaMemcpy(bufs[i], host[i], sizes[i], cudaMemcpyHostToDevice));
         }
-        plan = swinMlpCreatePlan((__half*)bufs[0], (const float*)bufs[1], (const float*)bufs[2], eps, (const __half*)bufs[3], (const float*)bufs[4],
-                                 (const __half*)bufs[5], (const float*)bufs[6]);
+        plan = swinMlpCreatePlan((__half*)bufs[0], c, (const float*)bufs[1], (const float*)bufs[2], eps, (const __half*)bufs[3], (const float*)bufs[4],
+                                 (const __half*)bufs[5], (const float*)bufs[6], variant);
         swinMlpLaunch(plan, nullptr, tokens);
         W2X_CUDA(cudaDeviceSynchronize());
         W2X_CUDA(cudaMemcpy(x, bufs[0], sizes[0], cudaMemcpyDeviceToHost));

@@ -604,7 +604,7 @@ void Engine::buildPlanSwin() {
             E.impl = IMPL_SWIN_MLP;
             E.tokN = x.n; E.tokH = h; E.tokW = w; E.tokC = c;
             E.flops = 2.0 * h * w * ((double)F1.npad * F1.ktot + (double)F2.npad * F2.ktot);
-            E.mlp = swinMlpCreatePlan(x.p, dAux0[n2], dAux1[n2], model.layers[n2].eps, dW[f1], dBias[f1], dW[f2], dBias[f2]);
+            E.mlp = swinMlpCreatePlan(x.p, c, dAux0[n2], dAux1[n2], model.layers[n2].eps, dW[f1], dBias[f1], dW[f2], dBias[f2]);
             layers.push_back(E);
         } else {
             pushLn(n2);
@@ -674,7 +674,7 @@ int Engine::layerKernel(int index, char* buf, int cap) const {
     if (index < 0 || index >= (int)layers.size()) return 0;
     const LayerExec& L = layers[index];
     if (L.plan) igemmDescribe(L.plan, buf, cap);
-    else if (L.mlp) swinMlpDescribe(buf, cap);
+    else if (L.mlp) swinMlpDescribe(L.mlp, buf, cap);
     else std::snprintf(buf, cap, "%s", L.impl == IMPL_FIRST ? "first-layer mma.sync" : L.impl == IMPL_LAYERNORM ? "layernorm" :
                                        L.impl == IMPL_ATTENTION ? "window-attention mma.sync" :
                                        L.impl == IMPL_HEAD ? "head kernel, taps in N (tcgen05)" : L.impl == IMPL_SKIP ? "fused into the next layer" : "direct (reference kernel)");

@@ -184,10 +184,11 @@ void encodeActivationMap5d(void* tensorMap, const ConvParams& p, int boxX, int b
 void encodeMatrixMap2d(void* tensorMap, const void* ptr, long long k, long long rows, int boxK, int boxRows, bool sw128);  // conv_igemm_sm100.cu
 struct SwinMlpPlan;                                               // fused LN + fc1 + GELU + fc2 + residual (kernels/swin_mlp_sm100.cu)
 bool swinMlpSupported(int c, int hidden);
-SwinMlpPlan* swinMlpCreatePlan(__half* x, const float* gamma, const float* beta, float eps, const __half* w1, const float* b1, const __half* w2, const float* b2);
+SwinMlpPlan* swinMlpCreatePlan(__half* x, int c, const float* gamma, const float* beta, float eps, const __half* w1, const float* b1, const __half* w2, const float* b2,
+                               int variant = 0);  // variant 1: stream the weights even where they would fit
 void swinMlpDestroyPlan(SwinMlpPlan* plan);
 void swinMlpLaunch(const SwinMlpPlan* plan, cudaStream_t s, long long tokens);
-const char* swinMlpDescribe(char* buf, int cap);
+const char* swinMlpDescribe(const SwinMlpPlan* plan, char* buf, int cap);
 struct IgemmPlan;                                                 // opaque: tensor maps + launch geometry
 IgemmPlan* igemmCreatePlan(const ConvParams& p);                  // throws w2x::Error when unsupported
 void igemmDestroyPlan(IgemmPlan* plan);

@@ -58,11 +58,11 @@ constexpr uint32_t kTmemCols = 512;
 
 struct MlpArgs {
     CUtensorMap tmW1, tmW2;
-    __half* x;                 // [tokens][96] fp16, updated in place
-    const float* b1;           // [192]
-    const float* b2;           // [96]
-    const float* gamma;        // [96]
-    const float* beta;         // [96]
+    __half* x;                 // [tokens][C] fp16, updated in place
+    const float* b1;           // [2C]
+    const float* b2;           // [C]
+    const float* gamma;        // [C]
+    const float* beta;         // [C]
     float eps;
     long long tokens;
 };
@@ -326,20 +326,399 @@ __global__ void __launch_bounds__(kMlpThreads, 1) swin_mlp_kernel(const __grid_c
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------------------
+// Streaming variant for wider levels (C = 192: the two weight matrices are 288 KB and cannot stay resident).  Same roles, but the
+// hidden dimension is processed in chunks of 64 units: a TMA warp streams, per chunk, the 64 fc1 rows W1[c*64 .. +64][C] and the 64
+// fc2 columns W2[C][c*64 .. +64] from L2 through a two-stage ring; fc1(chunk) -> D1 (64 TMEM columns, double-buffered) -> GELU ->
+// hidden chunk in shared memory (double-buffered) -> fc2 accumulates the chunk into D2[128][C].  fc1 of chunk g+1 is queued before
+// fc2 of chunk g.  With C = 192 a row is normalised by two producer threads (96 channels each, statistics exchanged by shuffle).
+// ------------------------------------------------------------------------------------------------------------------------------
+template <int C>
+struct StreamCfg {
+    static constexpr int kHidden = 2 * C;
+    static constexpr int kChunk = 64;                         // hidden units per chunk
+    static constexpr int kChunks = kHidden / kChunk;
+    static constexpr int kKA = C / 32;                        // 32-channel K chunks of the A operand (SWIZZLE_64B)
+    static constexpr int kPieces = C / 8;                     // 16-byte pieces of a token row
+    static constexpr int kProd = 4;                           // producer warps: one token row per thread
+    static constexpr int kTmaW = kProd, kMmaW = kProd + 1, kEpi0 = kProd + 2;
+    static constexpr int kThreadsS = 32 * (kEpi0 + kEpiWarps);
+    static constexpr int kABufs = C == 96 ? 2 : 1;
+    static constexpr uint32_t kW1Bytes = kKA * kChunk * 64;   // kKA boxes [64 rows][32 k]
+    static constexpr uint32_t kW2Bytes = C * 128;             // one box [C rows][64 k], SWIZZLE_128B
+    static constexpr uint32_t kStage = kW1Bytes + kW2Bytes;
+    static constexpr uint32_t kABytes = kKA * kAChunk;
+    static constexpr uint32_t kOffRing = 4096;
+    static constexpr uint32_t kOffAS = kOffRing + 2 * kStage;
+    static constexpr uint32_t kOffHS = kOffAS + kABufs * kABytes;
+    static constexpr uint32_t kSmem = kOffHS + 2 * kHChunk + 1024;
+    static constexpr uint32_t kD2Col = 2 * kChunk;
+    static constexpr uint32_t kTmem = C == 96 ? 256 : 512;
+    // header: barriers, then b1[2C], b2[C], gamma[C], beta[C] as f32
+    static constexpr uint32_t kB1 = 256, kB2 = kB1 + 4 * kHidden, kGamma = kB2 + 4 * C, kBeta = kGamma + 4 * C;
+    static_assert(kBeta + 4 * C <= kOffRing, "constants overflow the header");
+    static_assert(kStage % 1024 == 0 && kW1Bytes % 1024 == 0 && kABytes % 1024 == 0, "swizzled operands need 1024-byte alignment");
+    static_assert(kSmem <= 227 * 1024, "shared memory budget");
+};
+// barriers of the streaming kernel (byte offsets)
+constexpr uint32_t sBarWFull = 0, sBarWEmpty = 16, sBarAFull = 32, sBarAEmpty = 48, sBarD1Full = 64, sBarD1Empty = 80, sBarHFull = 96, sBarHEmpty = 112,
+                   sBarD2Full = 128, sBarD2Empty = 136, sTmemSlot = 144, sBarW2Full = 152, sBarW2Empty = 168;   // sBarW*: the fc1 half of a ring stage
+
+template <int C>
+__global__ void __launch_bounds__(StreamCfg<C>::kThreadsS, 1) swin_mlp_stream_kernel(const __grid_constant__ MlpArgs a) {
+    using Cfg = StreamCfg<C>;
+    extern __shared__ uint8_t smemRaw[];
+    const uint32_t base = (smemU32(smemRaw) + 1023u) & ~1023u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    pdlLaunchDependents();
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbarInit(base + sBarWFull + 8u * i, 1);
+            mbarInit(base + sBarWEmpty + 8u * i, 1);
+            mbarInit(base + sBarW2Full + 8u * i, 1);
+            mbarInit(base + sBarW2Empty + 8u * i, 1);
+            mbarInit(base + sBarAFull + 8u * i, Cfg::kProd);
+            mbarInit(base + sBarAEmpty + 8u * i, 1);
+            mbarInit(base + sBarD1Full + 8u * i, 1);
+            mbarInit(base + sBarD1Empty + 8u * i, kEpiWarps);
+            mbarInit(base + sBarHFull + 8u * i, kEpiWarps);
+            mbarInit(base + sBarHEmpty + 8u * i, 1);
+        }
+        mbarInit(base + sBarD2Full, 1);
+        mbarInit(base + sBarD2Empty, kEpiWarps);
+        mbarInitFence();
+        tmaPrefetchDesc(&a.tmW1);
+        tmaPrefetchDesc(&a.tmW2);
+    }
+    for (int i = threadIdx.x; i < Cfg::kHidden; i += Cfg::kThreadsS) stsF32(base + Cfg::kB1 + 4u * i, a.b1[i]);
+    for (int i = threadIdx.x; i < C; i += Cfg::kThreadsS) {
+        stsF32(base + Cfg::kB2 + 4u * i, a.b2[i]);
+        stsF32(base + Cfg::kGamma + 4u * i, a.gamma[i]);
+        stsF32(base + Cfg::kBeta + 4u * i, a.beta[i]);
+    }
+    if (warp == Cfg::kMmaW) tmemAlloc(base + sTmemSlot, Cfg::kTmem);
+    tcFenceBefore();
+    __syncthreads();
+    tcFenceAfter();
+    uint32_t tmemBase;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmemBase) : "r"(base + sTmemSlot));
+    const long long tiles = (a.tokens + kRows - 1) / kRows;
+    const int first = blockIdx.x, step = gridDim.x;
+    const int nMine = first < tiles ? (int)((tiles - first + step - 1) / step) : 0;
+    const int nChunksMine = nMine * Cfg::kChunks;
+
+    if (warp == Cfg::kTmaW) {
+        // ---- weight stream (constants: starts before the predecessor kernel has finished) ----
+        if (lane == 0) {
+            for (int g = 0; g < nChunksMine; ++g) {
+                // the two halves of a stage are released separately: the fc1 rows of chunk g can be fetched as soon as fc1 of chunk
+                // g-2 has completed, one GELU period before the fc2 columns of chunk g-2 are done with
+                const int st = g & 1, c = g % Cfg::kChunks;
+                const uint32_t par = (uint32_t)((g >> 1) & 1) ^ 1u, dst = base + Cfg::kOffRing + (uint32_t)st * Cfg::kStage;
+                mbarWait(base + sBarWEmpty + 8u * st, par);
+                const uint32_t full1 = base + sBarWFull + 8u * st, full2 = base + sBarW2Full + 8u * st;
+                mbarExpectTx(full1, Cfg::kW1Bytes);
+                for (int ka = 0; ka < Cfg::kKA; ++ka) tmaLoad2d(dst + (uint32_t)ka * (Cfg::kChunk * 64u), &a.tmW1, full1, ka * 32, c * Cfg::kChunk);
+                mbarWait(base + sBarW2Empty + 8u * st, par);
+                mbarExpectTx(full2, Cfg::kW2Bytes);
+                tmaLoad2d(dst + Cfg::kW1Bytes, &a.tmW2, full2, c * Cfg::kChunk, 0);
+            }
+        }
+    } else if (warp < Cfg::kProd) {
+        // ---- LayerNorm producers: one token row per thread ----
+        pdlWait();  // x is written by the preceding kernel
+        const int row = threadIdx.x;
+        const uint32_t sw = (uint32_t)(row >> 1) & 3u;
+        // normalise 12 pieces (96 channels) held in registers and store them as A-operand rows; J0 = index of the first piece
+        auto emit = [&](const uint4 (&raw)[12], int J0, float mean, float rstd, bool valid, uint32_t rowAddr) {
+#pragma unroll
+            for (int j = 0; j < 12; ++j) {
+                const int J = J0 + j;
+                float v[8], gm[8], bt[8];
+                unpack8(raw[j], v);
+                loadF8(base + Cfg::kGamma + 32u * J, gm);
+                loadF8(base + Cfg::kBeta + 32u * J, bt);
+                uint4 o;
+                __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    oh[i] = __floats2half2_rn((v[2 * i] - mean) * rstd * gm[2 * i] + bt[2 * i], (v[2 * i + 1] - mean) * rstd * gm[2 * i + 1] + bt[2 * i + 1]);
+                if (!valid) o = make_uint4(0, 0, 0, 0);
+                stsV4(rowAddr + (uint32_t)(J >> 2) * kAChunk + ((((uint32_t)J & 3u) ^ sw) << 4), o);
+            }
+        };
+        for (int k = 0; k < nMine; ++k) {
+            const long long g = ((long long)first + (long long)k * step) * kRows + row;
+            const bool valid = g < a.tokens;
+            const uint4* src = reinterpret_cast<const uint4*>(a.x + g * C);
+            const int buf = Cfg::kABufs == 2 ? (k & 1) : 0;
+            const uint32_t use = Cfg::kABufs == 2 ? (uint32_t)(k >> 1) : (uint32_t)k;
+            const uint32_t rowAddr = base + Cfg::kOffAS + (uint32_t)buf * Cfg::kABytes + (uint32_t)row * 64u;
+            uint4 raw[12];
+            if constexpr (C == 96) {
+                // the whole row stays in registers: two-pass statistics
+#pragma unroll
+                for (int j = 0; j < 12; ++j) raw[j] = make_uint4(0, 0, 0, 0);
+                if (valid) {
+#pragma unroll
+                    for (int j = 0; j < 12; ++j) raw[j] = src[j];
+                }
+                float sum = 0.f;
+#pragma unroll
+                for (int j = 0; j < 12; ++j) {
+                    float v[8];
+                    unpack8(raw[j], v);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) sum += v[i];
+                }
+                const float mean = sum * (1.f / C);
+                float sq = 0.f;
+#pragma unroll
+                for (int j = 0; j < 12; ++j) {
+                    float v[8];
+                    unpack8(raw[j], v);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { const float d = v[i] - mean; sq += d * d; }
+                }
+                const float rstd = rsqrtf(sq * (1.f / C) + a.eps);
+                mbarWait(base + sBarAEmpty + 8u * buf, (use & 1u) ^ 1u);   // the last fc1 chunk that read this buffer has completed
+                emit(raw, 0, mean, rstd, valid, rowAddr);
+            } else {
+                // 384-byte rows do not fit the register budget next to the epilogue warps: statistics in one streaming pass (sums of
+                // x - x0 and (x - x0)^2 with x0 = the row's first element, so a large common offset cannot cancel), then the row
+                // is read again (an L2 hit) 96 channels at a time for the normalisation
+                float x0 = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                for (int h = 0; h < Cfg::kPieces / 12; ++h) {
+#pragma unroll
+                    for (int j = 0; j < 12; ++j) raw[j] = make_uint4(0, 0, 0, 0);
+                    if (valid) {
+#pragma unroll
+                        for (int j = 0; j < 12; ++j) raw[j] = src[12 * h + j];
+                    }
+                    if (h == 0) x0 = __low2float(*reinterpret_cast<const __half2*>(&raw[0]));
+#pragma unroll
+                    for (int j = 0; j < 12; ++j) {
+                        float v[8];
+                        unpack8(raw[j], v);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) { const float d = v[i] - x0; s1 += d; s2 = fmaf(d, d, s2); }
+                    }
+                }
+                const float m1 = s1 * (1.f / C);
+                const float mean = x0 + m1;
+                const float rstd = rsqrtf(fmaxf(s2 * (1.f / C) - m1 * m1, 0.f) + a.eps);
+                if (valid) {
+#pragma unroll
+                    for (int j = 0; j < 12; ++j) raw[j] = src[j];   // in flight while the buffer is still being read by fc1
+                }
+                mbarWait(base + sBarAEmpty + 8u * buf, (use & 1u) ^ 1u);
+#pragma unroll
+                for (int h = 0; h < Cfg::kPieces / 12; ++h) {
+                    uint4 nxt[12];
+                    if (h + 1 < Cfg::kPieces / 12 && valid) {
+#pragma unroll
+                        for (int j = 0; j < 12; ++j) nxt[j] = src[12 * (h + 1) + j];
+                    }
+                    emit(raw, 12 * h, mean, rstd, valid, rowAddr);
+                    if (h + 1 < Cfg::kPieces / 12) {
+#pragma unroll
+                        for (int j = 0; j < 12; ++j) raw[j] = nxt[j];
+                    }
+                }
+            }
+            fenceProxyAsync();
+            __syncwarp();
+            if (lane == 0) mbarArrive(base + sBarAFull + 8u * buf);
+        }
+    } else if (warp == Cfg::kMmaW) {
+        const uint32_t hi64 = descHi(512u, 4u), hi128 = descHi(1024u, 2u);
+        const uint32_t idesc1 = instrDescF16(kRows, Cfg::kChunk), idesc2 = instrDescF16(kRows, C);
+        auto fc1 = [&](int g) {   // D1[g & 1] = A(tile) x W1 chunk^T
+            const int k = g / Cfg::kChunks, c = g - k * Cfg::kChunks, st = g & 1;
+            const int buf = Cfg::kABufs == 2 ? (k & 1) : 0;
+            const uint32_t use = Cfg::kABufs == 2 ? (uint32_t)(k >> 1) : (uint32_t)k;
+            if (c == 0) mbarWait(base + sBarAFull + 8u * buf, use & 1u);
+            mbarWait(base + sBarWFull + 8u * st, (uint32_t)(g >> 1) & 1u);
+            mbarWait(base + sBarD1Empty + 8u * st, ((uint32_t)(g >> 1) & 1u) ^ 1u);
+            tcFenceAfter();
+            if (electOne()) {
+                const uint32_t aBase = base + Cfg::kOffAS + (uint32_t)buf * Cfg::kABytes, wBase = base + Cfg::kOffRing + (uint32_t)st * Cfg::kStage;
+#pragma unroll
+                for (int ka = 0; ka < Cfg::kKA; ++ka)
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks)
+                        ummaLoHi(tmemBase + (uint32_t)st * Cfg::kChunk, descLo(aBase + ka * kAChunk + ks * 32u), hi64, descLo(wBase + ka * (Cfg::kChunk * 64u) + ks * 32u), hi64,
+                                 idesc1, (ka | ks) != 0 ? 1u : 0u);
+                tcCommit(base + sBarD1Full + 8u * st);
+                tcCommit(base + sBarWEmpty + 8u * st);
+                if (c == Cfg::kChunks - 1) tcCommit(base + sBarAEmpty + 8u * buf);   // the tile's normalised rows are no longer needed
+            }
+            __syncwarp();
+        };
+        auto fc2 = [&](int g) {   // D2 += hidden chunk x W2 chunk^T
+            const int k = g / Cfg::kChunks, c = g - k * Cfg::kChunks, st = g & 1;
+            mbarWait(base + sBarHFull + 8u * st, (uint32_t)(g >> 1) & 1u);
+            mbarWait(base + sBarW2Full + 8u * st, (uint32_t)(g >> 1) & 1u);
+            if (c == 0) mbarWait(base + sBarD2Empty, ((uint32_t)k & 1u) ^ 1u);
+            tcFenceAfter();
+            if (electOne()) {
+                const uint32_t hBase = base + Cfg::kOffHS + (uint32_t)st * kHChunk, wBase = base + Cfg::kOffRing + (uint32_t)st * Cfg::kStage + Cfg::kW1Bytes;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                    ummaLoHi(tmemBase + Cfg::kD2Col, descLo(hBase + ks * 32u), hi128, descLo(wBase + ks * 32u), hi128, idesc2, (c | ks) != 0 ? 1u : 0u);
+                tcCommit(base + sBarHEmpty + 8u * st);
+                tcCommit(base + sBarW2Empty + 8u * st);
+                if (c == Cfg::kChunks - 1) tcCommit(base + sBarD2Full);
+            }
+            __syncwarp();
+        };
+        if (nChunksMine > 0) fc1(0);
+        for (int g = 0; g < nChunksMine; ++g) {
+            if (g + 1 < nChunksMine) fc1(g + 1);
+            fc2(g);
+        }
+    } else {
+        // ---- epilogue warps ----
+        pdlWait();  // the residual rows come from the preceding kernel
+        const int quarter = warp & 3;
+        const int half = (warp - Cfg::kEpi0) >> 2;
+        const int row = quarter * 32 + lane;
+        const uint32_t taddrLane = tmemBase + ((uint32_t)(quarter * 32) << 16);
+        const uint32_t sw = (uint32_t)row & 7u;
+        uint32_t r[32];
+        auto phase1 = [&](int g) {   // GELU(fc1 chunk + b1) -> hidden chunk buffer g & 1
+            const int c = g % Cfg::kChunks, st = g & 1;
+            const uint32_t ph = (uint32_t)(g >> 1) & 1u;
+            mbarWait(base + sBarD1Full + 8u * st, ph);
+            tcFenceAfter();
+            tmemLd32(taddrLane + (uint32_t)(st * Cfg::kChunk + half * 32), r);
+            tmemLdWait();
+            tcFenceBefore();
+            __syncwarp();
+            if (lane == 0) mbarArrive(base + sBarD1Empty + 8u * st);   // the accumulator is in registers: fc1 of chunk g+2 may overwrite it
+            mbarWait(base + sBarHEmpty + 8u * st, ph ^ 1u);   // fc2 of chunk g-2 has consumed this buffer
+            const uint32_t hRow = base + Cfg::kOffHS + (uint32_t)st * kHChunk + (uint32_t)row * 128u;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float bias[8];
+                loadF8(base + Cfg::kB1 + 4u * (uint32_t)(c * Cfg::kChunk + half * 32 + 8 * q), bias);
+                uint4 o;
+                __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    oh[i] = __floats2half2_rn(geluErf(__uint_as_float(r[8 * q + 2 * i]) + bias[2 * i]), geluErf(__uint_as_float(r[8 * q + 2 * i + 1]) + bias[2 * i + 1]));
+                stsV4(hRow + (((uint32_t)(half * 4 + q) ^ sw) << 4), o);
+            }
+            fenceProxyAsync();
+            __syncwarp();
+            if (lane == 0) mbarArrive(base + sBarHFull + 8u * st);
+        };
+        auto phase2 = [&](int k) {   // x += fc2 + b2 for tile k
+            const long long g = ((long long)first + (long long)k * step) * kRows + row;
+            const bool valid = g < a.tokens;
+            const int col0 = half * (C / 2);
+            __half* xrow = a.x + g * C + col0;
+            mbarWait(base + sBarD2Full, (uint32_t)k & 1u);
+            tcFenceAfter();
+#pragma unroll 1
+            for (int p = 0; p < C / 64; ++p) {   // 32 columns per round
+                uint4 res[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) res[j] = make_uint4(0, 0, 0, 0);
+                if (valid) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) res[j] = reinterpret_cast<const uint4*>(xrow)[4 * p + j];
+                }
+                tmemLd32(taddrLane + Cfg::kD2Col + (uint32_t)(col0 + 32 * p), r);
+                tmemLdWait();
+                if (valid) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float bias[8], rv[8];
+                        loadF8(base + Cfg::kB2 + 4u * (uint32_t)(col0 + 32 * p + 8 * j), bias);
+                        unpack8(res[j], rv);
+                        uint4 o;
+                        __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            oh[i] = __floats2half2_rn(__uint_as_float(r[8 * j + 2 * i]) + bias[2 * i] + rv[2 * i], __uint_as_float(r[8 * j + 2 * i + 1]) + bias[2 * i + 1] + rv[2 * i + 1]);
+                        reinterpret_cast<uint4*>(xrow)[4 * p + j] = o;
+                    }
+                }
+            }
+            if (C % 64) {   // 16-column tail (C = 96: 48 columns per thread)
+                constexpr int p16 = (C / 64) * 32;
+                uint4 res[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+                if (valid) {
+                    res[0] = reinterpret_cast<const uint4*>(xrow)[p16 / 8];
+                    res[1] = reinterpret_cast<const uint4*>(xrow)[p16 / 8 + 1];
+                }
+                tmemLd16(taddrLane + Cfg::kD2Col + (uint32_t)(col0 + p16), r);
+                tmemLdWait();
+                if (valid) {
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        float bias[8], rv[8];
+                        loadF8(base + Cfg::kB2 + 4u * (uint32_t)(col0 + p16 + 8 * j), bias);
+                        unpack8(res[j], rv);
+                        uint4 o;
+                        __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            oh[i] = __floats2half2_rn(__uint_as_float(r[8 * j + 2 * i]) + bias[2 * i] + rv[2 * i], __uint_as_float(r[8 * j + 2 * i + 1]) + bias[2 * i + 1] + rv[2 * i + 1]);
+                        reinterpret_cast<uint4*>(xrow)[p16 / 8 + j] = o;
+                    }
+                }
+            }
+            tcFenceBefore();
+            __syncwarp();
+            if (lane == 0) mbarArrive(base + sBarD2Empty);
+        };
+        // chunk g+1 is converted before the finished tile of chunk g is written back (its fc2 runs meanwhile)
+        if (nChunksMine > 0) phase1(0);
+        for (int g = 0; g < nChunksMine; ++g) {
+            if (g + 1 < nChunksMine) phase1(g + 1);
+            if (g % Cfg::kChunks == Cfg::kChunks - 1) phase2(g / Cfg::kChunks);
+        }
+    }
+
+    tcFenceBefore();
+    __syncthreads();
+    if (warp == Cfg::kMmaW) {
+        tcFenceAfter();
+        tmemDealloc(tmemBase, Cfg::kTmem);
+    }
+}
+
 }  // namespace
 
 struct SwinMlpPlan {
     MlpArgs args;
+    int c = 0;
+    bool stream = false;   // weights streamed per hidden chunk (swin_mlp_stream_kernel) instead of resident
 };
 
-bool swinMlpSupported(int c, int hidden) { return c == kC && hidden == kHid; }
+bool swinMlpSupported(int c, int hidden) { return (c == 96 || c == 192) && hidden == 2 * c; }
 
-SwinMlpPlan* swinMlpCreatePlan(__half* x, const float* gamma, const float* beta, float eps, const __half* w1, const float* b1, const __half* w2, const float* b2) {
+// variant: 0 = resident weights where they fit (C = 96), streamed otherwise; 1 = always streamed
+SwinMlpPlan* swinMlpCreatePlan(__half* x, int c, const float* gamma, const float* beta, float eps, const __half* w1, const float* b1, const __half* w2, const float* b2,
+                               int variant) {
+    if (!swinMlpSupported(c, 2 * c)) throw Error("swin mlp: unsupported width");
     if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w1) | reinterpret_cast<uintptr_t>(w2)) & 15) throw Error("swin mlp: operands must be 16-byte aligned");
     SwinMlpPlan* plan = new SwinMlpPlan{};
+    plan->c = c;
+    plan->stream = variant == 1 || c != kC;
     try {
-        encodeMatrixMap2d(&plan->args.tmW1, w1, kC, kHid, 32, kHid, false);     // fc1 weights [192][96], K-major
-        encodeMatrixMap2d(&plan->args.tmW2, w2, kHid, kC, 64, kC, true);        // fc2 weights [96][192]
+        // fc1 weights [2C][C] and fc2 weights [C][2C], both K-major
+        if (plan->stream) {
+            encodeMatrixMap2d(&plan->args.tmW1, w1, c, 2 * c, 32, 64, false);
+            encodeMatrixMap2d(&plan->args.tmW2, w2, 2 * c, c, 64, c, true);
+        } else {
+            encodeMatrixMap2d(&plan->args.tmW1, w1, kC, kHid, 32, kHid, false);
+            encodeMatrixMap2d(&plan->args.tmW2, w2, kHid, kC, 64, kC, true);
+        }
     } catch (...) {
         delete plan;
         throw;
@@ -356,8 +735,10 @@ SwinMlpPlan* swinMlpCreatePlan(__half* x, const float* gamma, const float* beta,
 
 void swinMlpDestroyPlan(SwinMlpPlan* plan) { delete plan; }
 
-const char* swinMlpDescribe(char* buf, int cap) {
-    std::snprintf(buf, cap, "swin-mlp fused LN+fc1+GELU+fc2+residual (tcgen05) c=%d hidden=%d rows=%d smem=%u", kC, kHid, kRows, kMlpSmem);
+const char* swinMlpDescribe(const SwinMlpPlan* plan, char* buf, int cap) {
+    const unsigned smem = !plan->stream ? kMlpSmem : plan->c == 96 ? StreamCfg<96>::kSmem : StreamCfg<192>::kSmem;
+    std::snprintf(buf, cap, "swin-mlp fused LN+fc1+GELU+fc2+residual (tcgen05) c=%d hidden=%d rows=%d weights=%s smem=%u", plan->c, 2 * plan->c, kRows,
+                  plan->stream ? "streamed" : "resident", smem);
     return buf;
 }
 
@@ -369,6 +750,8 @@ void swinMlpLaunch(const SwinMlpPlan* plan, cudaStream_t s, long long tokens) {
     if (dev < 0 || dev >= 64) dev = 0;
     if (!attrSet[dev]) {
         cudaFuncSetAttribute(swin_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMlpSmem);
+        cudaFuncSetAttribute(swin_mlp_stream_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, StreamCfg<96>::kSmem);
+        cudaFuncSetAttribute(swin_mlp_stream_kernel<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, StreamCfg<192>::kSmem);
         cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
         if (sms[dev] <= 0) sms[dev] = 148;
         attrSet[dev] = true;
@@ -378,7 +761,10 @@ void swinMlpLaunch(const SwinMlpPlan* plan, cudaStream_t s, long long tokens) {
     a.tokens = tokens;
     const long long tiles = (tokens + kRows - 1) / kRows;
     const dim3 grid((unsigned)(tiles < sms[dev] ? tiles : sms[dev]));
-    const cudaError_t e = launchPdl(swin_mlp_kernel, grid, dim3(kMlpThreads), kMlpSmem, s, a);
+    cudaError_t e;
+    if (!plan->stream) e = launchPdl(swin_mlp_kernel, grid, dim3(kMlpThreads), kMlpSmem, s, a);
+    else if (plan->c == 96) e = launchPdl(swin_mlp_stream_kernel<96>, grid, dim3(StreamCfg<96>::kThreadsS), StreamCfg<96>::kSmem, s, a);
+    else e = launchPdl(swin_mlp_stream_kernel<192>, grid, dim3(StreamCfg<192>::kThreadsS), StreamCfg<192>::kSmem, s, a);
     if (e != cudaSuccess) throw Error(std::string("swin mlp launch: ") + cudaGetErrorString(e));
 }
 

@@ -135,7 +135,7 @@ _SIGNATURES = {
     "w2x_infer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "w2x_selftest_conv": (C.c_double, [C.c_int] * 7 + [C.c_uint]),
     "w2x_run_conv_layer": (C.c_int, [C.c_int] * 8 + [C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.c_void_p, C.c_void_p]),
-    "w2x_run_swin_mlp": (C.c_int, [C.c_int, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+    "w2x_run_swin_mlp": (C.c_int, [C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_int, C.POINTER(C.c_float)]),
     "w2x_select_engine": (C.c_int, [C.c_char_p, C.POINTER(_RenderConfig), C.c_char_p, C.c_char_p, C.c_size_t]),
     "w2x_config_hash": (None, [C.c_char_p, C.POINTER(_BuildConfig), C.c_char_p]),
@@ -300,16 +300,17 @@ def run_conv_layer(kind: int, x: np.ndarray, w_packed: np.ndarray, bias: np.ndar
 
 
 def run_swin_mlp(x: np.ndarray, gamma: np.ndarray, beta: np.ndarray, eps: float, w1: np.ndarray, b1: np.ndarray, w2: np.ndarray, b2: np.ndarray,
-                 reps: int = 0, device: int = 0):
-    """x + fc2(GELU(fc1(LayerNorm(x)))) through the fused MLP kernel (include/w2x_dev.h: w2x_run_swin_mlp).  x: fp16 [tokens][96];
-    w1 fp16 [192][96], w2 fp16 [96][192].  Returns (fp16 [tokens][96], average ms of `reps` extra launches or None)."""
+                 reps: int = 0, device: int = 0, variant: int = 0):
+    """x + fc2(GELU(fc1(LayerNorm(x)))) through the fused MLP kernel (include/w2x_dev.h: w2x_run_swin_mlp).  x: fp16 [tokens][c],
+    c = 96 or 192; w1 fp16 [2c][c], w2 fp16 [c][2c].  Returns (fp16 [tokens][c], average ms of `reps` extra launches or None)."""
     out = np.ascontiguousarray(x, np.float16).copy()
-    assert out.ndim == 2 and out.shape[1] == 96
+    assert out.ndim == 2 and out.shape[1] in (96, 192)
+    c = out.shape[1]
     f32 = [np.ascontiguousarray(a, np.float32) for a in (gamma, beta, b1, b2)]
     f16 = [np.ascontiguousarray(a, np.float16) for a in (w1, w2)]
-    assert f16[0].shape == (192, 96) and f16[1].shape == (96, 192)
+    assert f16[0].shape == (2 * c, c) and f16[1].shape == (c, 2 * c)
     ms = C.c_float(0)
-    ok = lib().w2x_run_swin_mlp(device, out.shape[0], _ptr(out), _ptr(f32[0]), _ptr(f32[1]), float(eps), _ptr(f16[0]), _ptr(f32[2]), _ptr(f16[1]), _ptr(f32[3]),
+    ok = lib().w2x_run_swin_mlp(device, out.shape[0], c, int(variant), _ptr(out), _ptr(f32[0]), _ptr(f32[1]), float(eps), _ptr(f16[0]), _ptr(f32[2]), _ptr(f16[1]), _ptr(f32[3]),
                                 int(reps), C.byref(ms))
     if not ok:
         raise RuntimeError("w2x_run_swin_mlp failed")
