@@ -38,6 +38,11 @@ W2X_API int w2x_run_conv_layer(int device, int kind, int head, int n, int h, int
 W2X_API int w2x_run_swin_mlp(int device, long long tokens, int c, int variant, uint16_t* x, const float* gamma, const float* beta, float eps,
                              const uint16_t* w1, const float* b1, const uint16_t* w2, const float* b2, int reps, float* ms_out);
 
+/* The fused LayerNorm + QKV projection of a SwinUNet block (kernels/swin_mlp_sm100.cu): out[tokens][3c] = LayerNorm(x[tokens][c]) w^T + bias,
+ * c = 96 or 192, w = [3c][c] fp16 bits (K-major).  ms_out as above.  Returns 1 on success. */
+W2X_API int w2x_run_swin_lnlinear(int device, long long tokens, int c, const uint16_t* x, const float* gamma, const float* beta, float eps,
+                                  const uint16_t* w, const float* bias, uint16_t* out, int reps, float* ms_out);
+
 /* One convolution layer of the implicit-GEMM family on random data, tcgen05 kernel vs the scalar CUDA reference
  * kernel, for on-device self-checks: returns max |diff| (negative on error).  kind: 0 conv3x3, 1 conv2x2s2,
  * 2 convT2x2s2(+skip), 3 convT4x4s2p3->4ch, 4 conv3x3->3ch final(+skip,clamp), 5 = kind 4 through the image-head kernel,

@@ -57,17 +57,26 @@ struct ConvParams {
 #ifdef __CUDACC__
 
 __device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.f ? v : v * slope; }
-// nn.GELU() (erf form).  erf by Abramowitz-Stegun 7.1.26 (|abs error| < 1.5e-7, far below the fp16 output resolution):
-// ~4x fewer instructions than erff in the Linear epilogues.
+// nn.GELU() (erf form): gelu(v) = v * Phi(v).  Phi(v) - 1/2 = v * Q(v^2) with a degree-9 polynomial Q fitted on |v| <= 4 (Chebyshev
+// nodes; |error of gelu| <= 1.3e-5 there, fp32 Horner included); outside, v * Phi(+-4) -- a relative error of 3.3e-5 for v > 4 and an
+// absolute error <= 1.3e-4 where the true value is within 1.3e-4 of zero -- all far below the fp16 resolution of the stored result.
+// No MUFU: the rcp + ex2 of the Abramowitz-Stegun form made the Linear epilogues and the fused MLP kernel bound by the XU pipe
+// (99.8 % busy in profiles/r02_ncu_swin_mlp.txt); this form is 14 FMA-pipe instructions.
 __device__ __forceinline__ float geluErf(float v) {
-    // gelu(v) = 0.5 v (1 + erf(v / sqrt 2)) = 0.5 (v + |v| erf(|v| / sqrt 2)); erf(x) = 1 - poly(t) exp(-x^2), t = 1 / (1 + p x)
-    const float av = fabsf(v);
-    float t, e;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f * 0.70710678118654752f, av, 1.f)));
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(av * av * (-0.5f * 1.4426950408889634f)));  // exp(-x^2), x^2 = v^2 / 2
-    const float poly = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f), 0.254829592f);
-    const float erfAbs = fmaf(-poly, e, 1.f);
-    return 0.5f * fmaf(av, erfAbs, v);
+    const float vn = fmaxf(v, -4.f);
+    const float vc = fminf(vn, 4.f);
+    const float u = vc * vc;
+    float q = -4.407132645e-12f;
+    q = fmaf(q, u, 4.129891984e-10f);
+    q = fmaf(q, u, -1.754582968e-08f);
+    q = fmaf(q, u, 4.542657450e-07f);
+    q = fmaf(q, u, -8.172721209e-06f);
+    q = fmaf(q, u, 1.105528936e-04f);
+    q = fmaf(q, u, -1.176239806e-03f);
+    q = fmaf(q, u, 9.960514493e-03f);
+    q = fmaf(q, u, -6.648434699e-02f);
+    q = fmaf(q, u, 3.989418149e-01f);
+    return vn * fmaf(vc, q, 0.5f);
 }
 
 struct alignas(16) Half8 { __half2 a, b, c, d; };
@@ -186,6 +195,8 @@ struct SwinMlpPlan;                                               // fused LN + 
 bool swinMlpSupported(int c, int hidden);
 SwinMlpPlan* swinMlpCreatePlan(__half* x, int c, const float* gamma, const float* beta, float eps, const __half* w1, const float* b1, const __half* w2, const float* b2,
                                int variant = 0);  // variant 1: stream the weights even where they would fit
+bool swinLnLinearSupported(int c, int n);                         // LayerNorm + Linear (QKV projection) in one kernel, same plan type
+SwinMlpPlan* swinLnLinearCreatePlan(const __half* x, int c, const float* gamma, const float* beta, float eps, const __half* w, const float* bias, __half* out);
 void swinMlpDestroyPlan(SwinMlpPlan* plan);
 void swinMlpLaunch(const SwinMlpPlan* plan, cudaStream_t s, long long tokens);
 const char* swinMlpDescribe(const SwinMlpPlan* plan, char* buf, int cap);

@@ -65,6 +65,7 @@ struct MlpArgs {
     const float* beta;         // [C]
     float eps;
     long long tokens;
+    __half* out;               // LN + Linear kernel only: [tokens][3C]
 };
 
 __device__ __forceinline__ void stsF32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
@@ -83,6 +84,122 @@ __device__ __forceinline__ void loadF8(uint32_t addr, float (&v)[8]) {
     v[4] = __uint_as_float(b.x); v[5] = __uint_as_float(b.y); v[6] = __uint_as_float(b.z); v[7] = __uint_as_float(b.w);
 }
 
+// LayerNorm producer warps (groups of 4 warps, one token row per thread): rows of tile k -> fp16 A-operand rows (SWIZZLE_64B,
+// 32-channel K chunks of kAChunk bytes) in buffer k % kABufs at offA; barAFull / barAEmpty are the shared-memory addresses of buffer
+// 0's barriers.  kFirst / kStep let several groups of four warps share the tiles (measured: a second group does not pay, the 96
+// registers per thread it leaves cost more than the overlap gains).
+template <int C, int kABufs>
+__device__ __forceinline__ void lnProducerLoop(const MlpArgs& a, uint32_t base, uint32_t offA, uint32_t offGamma, uint32_t offBeta, uint32_t barAFull, uint32_t barAEmpty,
+                                               int first, int step, int nMine, int kFirst = 0, int kStep = 1) {
+    const int lane = threadIdx.x & 31;
+    pdlWait();  // x is written by the preceding kernel
+    const int row = threadIdx.x & 127;
+    const uint32_t sw = (uint32_t)(row >> 1) & 3u;
+    // normalise 12 pieces (96 channels) held in registers and store them as A-operand rows; J0 = index of the first piece
+    auto emit = [&](const uint4 (&raw)[12], int J0, float mean, float rstd, bool valid, uint32_t rowAddr) {
+#pragma unroll
+        for (int j = 0; j < 12; ++j) {
+            const int J = J0 + j;
+            float v[8], gm[8], bt[8];
+            unpack8(raw[j], v);
+            loadF8(base + offGamma + 32u * J, gm);
+            loadF8(base + offBeta + 32u * J, bt);
+            uint4 o;
+            __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                oh[i] = __floats2half2_rn((v[2 * i] - mean) * rstd * gm[2 * i] + bt[2 * i], (v[2 * i + 1] - mean) * rstd * gm[2 * i + 1] + bt[2 * i + 1]);
+            if (!valid) o = make_uint4(0, 0, 0, 0);
+            stsV4(rowAddr + (uint32_t)(J >> 2) * kAChunk + ((((uint32_t)J & 3u) ^ sw) << 4), o);
+        }
+    };
+    for (int k = kFirst; k < nMine; k += kStep) {
+        const long long g = ((long long)first + (long long)k * step) * kRows + row;
+        const bool valid = g < a.tokens;
+        const uint4* src = reinterpret_cast<const uint4*>(a.x + g * C);
+        const int buf = kABufs == 2 ? (k & 1) : 0;
+        const uint32_t use = kABufs == 2 ? (uint32_t)(k >> 1) : (uint32_t)k;
+        const uint32_t rowAddr = base + offA + (uint32_t)buf * (uint32_t)(C / 32) * kAChunk + (uint32_t)row * 64u;
+        uint4 raw[12];
+        if constexpr (C == 96) {
+            // the whole row stays in registers: two-pass statistics
+#pragma unroll
+            for (int j = 0; j < 12; ++j) raw[j] = make_uint4(0, 0, 0, 0);
+            if (valid) {
+#pragma unroll
+                for (int j = 0; j < 12; ++j) raw[j] = src[j];
+            }
+            float ps[4] = {0.f, 0.f, 0.f, 0.f};   // four partial sums: the reductions are not one 96-long dependent chain
+#pragma unroll
+            for (int j = 0; j < 12; ++j) {
+                float v[8];
+                unpack8(raw[j], v);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) ps[i & 3] += v[i];
+            }
+            const float mean = ((ps[0] + ps[1]) + (ps[2] + ps[3])) * (1.f / C);
+            float pq[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int j = 0; j < 12; ++j) {
+                float v[8];
+                unpack8(raw[j], v);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { const float d = v[i] - mean; pq[i & 3] = fmaf(d, d, pq[i & 3]); }
+            }
+            const float rstd = rsqrtf(((pq[0] + pq[1]) + (pq[2] + pq[3])) * (1.f / C) + a.eps);
+            mbarWait(barAEmpty + 8u * buf, (use & 1u) ^ 1u);   // the last fc1 chunk that read this buffer has completed
+            emit(raw, 0, mean, rstd, valid, rowAddr);
+        } else {
+            // 384-byte rows do not fit the register budget next to the epilogue warps: statistics in one streaming pass (sums of
+            // x - x0 and (x - x0)^2 with x0 = the row's first element, so a large common offset cannot cancel), then the row
+            // is read again (an L2 hit) 96 channels at a time for the normalisation
+            float x0 = 0.f, p1[4] = {0.f, 0.f, 0.f, 0.f}, p2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int h = 0; h < (C / 8) / 12; ++h) {
+#pragma unroll
+                for (int j = 0; j < 12; ++j) raw[j] = make_uint4(0, 0, 0, 0);
+                if (valid) {
+#pragma unroll
+                    for (int j = 0; j < 12; ++j) raw[j] = src[12 * h + j];
+                }
+                if (h == 0) x0 = __low2float(*reinterpret_cast<const __half2*>(&raw[0]));
+#pragma unroll
+                for (int j = 0; j < 12; ++j) {
+                    float v[8];
+                    unpack8(raw[j], v);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { const float d = v[i] - x0; p1[i & 3] += d; p2[i & 3] = fmaf(d, d, p2[i & 3]); }
+                }
+            }
+            const float s1 = (p1[0] + p1[1]) + (p1[2] + p1[3]), s2 = (p2[0] + p2[1]) + (p2[2] + p2[3]);
+            const float m1 = s1 * (1.f / C);
+            const float mean = x0 + m1;
+            const float rstd = rsqrtf(fmaxf(s2 * (1.f / C) - m1 * m1, 0.f) + a.eps);
+            if (valid) {
+#pragma unroll
+                for (int j = 0; j < 12; ++j) raw[j] = src[j];   // in flight while the buffer is still being read by fc1
+            }
+            mbarWait(barAEmpty + 8u * buf, (use & 1u) ^ 1u);
+#pragma unroll
+            for (int h = 0; h < (C / 8) / 12; ++h) {
+                uint4 nxt[12];
+                if (h + 1 < (C / 8) / 12 && valid) {
+#pragma unroll
+                    for (int j = 0; j < 12; ++j) nxt[j] = src[12 * (h + 1) + j];
+                }
+                emit(raw, 12 * h, mean, rstd, valid, rowAddr);
+                if (h + 1 < (C / 8) / 12) {
+#pragma unroll
+                    for (int j = 0; j < 12; ++j) raw[j] = nxt[j];
+                }
+            }
+        }
+        fenceProxyAsync();
+        __syncwarp();
+        if (lane == 0) mbarArrive(barAFull + 8u * buf);
+    }
+}
+
 __global__ void __launch_bounds__(kMlpThreads, 1) swin_mlp_kernel(const __grid_constant__ MlpArgs a) {
     extern __shared__ uint8_t smemRaw[];
     const uint32_t base = (smemU32(smemRaw) + 1023u) & ~1023u;
@@ -93,7 +210,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) swin_mlp_kernel(const __grid_c
     if (threadIdx.x == 0) {
         mbarInit(base + kBarW, 1);
         for (int i = 0; i < 2; ++i) {
-            mbarInit(base + kBarAFull + 8u * i, kProdWarps);
+            mbarInit(base + kBarAFull + 8u * i, 4);
             mbarInit(base + kBarAEmpty + 8u * i, 1);
             mbarInit(base + kBarD1Full + 8u * i, 1);
             mbarInit(base + kBarD1Empty + 8u * i, kEpiWarps);
@@ -132,58 +249,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) swin_mlp_kernel(const __grid_c
 
     if (warp < kProdWarps) {
         // ---- LayerNorm producers: thread = token row ----
-        const int t = threadIdx.x;
-        const uint32_t sw = (uint32_t)(t >> 1) & 3u;
-        for (int k = 0; k < nMine; ++k) {
-            const long long g = ((long long)first + (long long)k * step) * kRows + t;
-            const bool valid = g < a.tokens;
-            uint4 raw[12];
-#pragma unroll
-            for (int j = 0; j < 12; ++j) raw[j] = make_uint4(0, 0, 0, 0);
-            if (valid) {
-                const uint4* src = reinterpret_cast<const uint4*>(a.x + g * kC);
-#pragma unroll
-                for (int j = 0; j < 12; ++j) raw[j] = src[j];
-            }
-            float sum = 0.f;
-#pragma unroll
-            for (int j = 0; j < 12; ++j) {
-                float v[8];
-                unpack8(raw[j], v);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) sum += v[i];
-            }
-            const float mean = sum * (1.f / kC);
-            float sq = 0.f;
-#pragma unroll
-            for (int j = 0; j < 12; ++j) {
-                float v[8];
-                unpack8(raw[j], v);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) { const float d = v[i] - mean; sq += d * d; }
-            }
-            const float rstd = rsqrtf(sq * (1.f / kC) + a.eps);
-            const int buf = k & 1;
-            mbarWait(base + kBarAEmpty + 8u * buf, (uint32_t)((k >> 1) & 1) ^ 1u);   // fc1 of tile k-2 has consumed this buffer
-            const uint32_t rowAddr = base + kOffA + (uint32_t)buf * 3u * kAChunk + (uint32_t)t * 64u;
-#pragma unroll
-            for (int j = 0; j < 12; ++j) {
-                float v[8], gm[8], bt[8];
-                unpack8(raw[j], v);
-                loadF8(base + kOffGamma + 32u * j, gm);
-                loadF8(base + kOffBeta + 32u * j, bt);
-                uint4 o;
-                __half2* oh = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    oh[i] = __floats2half2_rn((v[2 * i] - mean) * rstd * gm[2 * i] + bt[2 * i], (v[2 * i + 1] - mean) * rstd * gm[2 * i + 1] + bt[2 * i + 1]);
-                if (!valid) o = make_uint4(0, 0, 0, 0);
-                stsV4(rowAddr + (uint32_t)(j >> 2) * kAChunk + ((((uint32_t)j & 3u) ^ sw) << 4), o);
-            }
-            fenceProxyAsync();  // generic-proxy stores -> visible to the tensor core's operand reads
-            __syncwarp();
-            if (lane == 0) mbarArrive(base + kBarAFull + 8u * buf);
-        }
+        lnProducerLoop<kC, 2>(a, base, kOffA, kOffGamma, kOffBeta, base + kBarAFull, base + kBarAEmpty, first, step, nMine);
     } else if (warp == kMmaWarp) {
         // ---- MMA issuer: whole warp converged, one elected lane issues ----
         const uint32_t hi64 = descHi(512u, 4u), hi128 = descHi(1024u, 2u);
@@ -272,18 +338,22 @@ __global__ void __launch_bounds__(kMlpThreads, 1) swin_mlp_kernel(const __grid_c
                 mbarArrive(base + kBarD1Empty + 8u * buf);
             }
         };
+        uint4 res[6];
+        auto prefetchResidual = [&](int t) {   // issued one GELU phase ahead of its use: the L2 latency is hidden behind phase 1
+            const long long g = ((long long)first + (long long)t * step) * kRows + row;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) res[j] = make_uint4(0, 0, 0, 0);
+            if (g < a.tokens) {
+                const uint4* xr = reinterpret_cast<const uint4*>(a.x + g * kC + half * (kC / 2));
+#pragma unroll
+                for (int j = 0; j < 6; ++j) res[j] = xr[j];
+            }
+        };
         auto phase2 = [&](int t) {   // x += fc2 + b2
             const long long g = ((long long)first + (long long)t * step) * kRows + row;
             const bool valid = g < a.tokens;
             const int col0 = half * (kC / 2);
             __half* xrow = a.x + g * kC + col0;
-            uint4 res[6];
-#pragma unroll
-            for (int j = 0; j < 6; ++j) res[j] = make_uint4(0, 0, 0, 0);
-            if (valid) {
-#pragma unroll
-                for (int j = 0; j < 6; ++j) res[j] = reinterpret_cast<const uint4*>(xrow)[j];   // residual in flight while fc2 finishes
-            }
             mbarWait(base + kBarD2Full, (uint32_t)t & 1u);
             tcFenceAfter();
             uint32_t r2[32];
@@ -313,6 +383,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) swin_mlp_kernel(const __grid_c
         };
         if (nMine > 0) phase1(0);
         for (int k = 0; k < nMine; ++k) {
+            prefetchResidual(k);
             if (k + 1 < nMine) phase1(k + 1);
             phase2(k);
         }
@@ -378,7 +449,7 @@ __global__ void __launch_bounds__(StreamCfg<C>::kThreadsS, 1) swin_mlp_stream_ke
             mbarInit(base + sBarWEmpty + 8u * i, 1);
             mbarInit(base + sBarW2Full + 8u * i, 1);
             mbarInit(base + sBarW2Empty + 8u * i, 1);
-            mbarInit(base + sBarAFull + 8u * i, Cfg::kProd);
+            mbarInit(base + sBarAFull + 8u * i, 4);
             mbarInit(base + sBarAEmpty + 8u * i, 1);
             mbarInit(base + sBarD1Full + 8u * i, 1);
             mbarInit(base + sBarD1Empty + 8u * i, kEpiWarps);
@@ -427,111 +498,7 @@ __global__ void __launch_bounds__(StreamCfg<C>::kThreadsS, 1) swin_mlp_stream_ke
         }
     } else if (warp < Cfg::kProd) {
         // ---- LayerNorm producers: one token row per thread ----
-        pdlWait();  // x is written by the preceding kernel
-        const int row = threadIdx.x;
-        const uint32_t sw = (uint32_t)(row >> 1) & 3u;
-        // normalise 12 pieces (96 channels) held in registers and store them as A-operand rows; J0 = index of the first piece
-        auto emit = [&](const uint4 (&raw)[12], int J0, float mean, float rstd, bool valid, uint32_t rowAddr) {
-#pragma unroll
-            for (int j = 0; j < 12; ++j) {
-                const int J = J0 + j;
-                float v[8], gm[8], bt[8];
-                unpack8(raw[j], v);
-                loadF8(base + Cfg::kGamma + 32u * J, gm);
-                loadF8(base + Cfg::kBeta + 32u * J, bt);
-                uint4 o;
-                __half2* oh = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    oh[i] = __floats2half2_rn((v[2 * i] - mean) * rstd * gm[2 * i] + bt[2 * i], (v[2 * i + 1] - mean) * rstd * gm[2 * i + 1] + bt[2 * i + 1]);
-                if (!valid) o = make_uint4(0, 0, 0, 0);
-                stsV4(rowAddr + (uint32_t)(J >> 2) * kAChunk + ((((uint32_t)J & 3u) ^ sw) << 4), o);
-            }
-        };
-        for (int k = 0; k < nMine; ++k) {
-            const long long g = ((long long)first + (long long)k * step) * kRows + row;
-            const bool valid = g < a.tokens;
-            const uint4* src = reinterpret_cast<const uint4*>(a.x + g * C);
-            const int buf = Cfg::kABufs == 2 ? (k & 1) : 0;
-            const uint32_t use = Cfg::kABufs == 2 ? (uint32_t)(k >> 1) : (uint32_t)k;
-            const uint32_t rowAddr = base + Cfg::kOffAS + (uint32_t)buf * Cfg::kABytes + (uint32_t)row * 64u;
-            uint4 raw[12];
-            if constexpr (C == 96) {
-                // the whole row stays in registers: two-pass statistics
-#pragma unroll
-                for (int j = 0; j < 12; ++j) raw[j] = make_uint4(0, 0, 0, 0);
-                if (valid) {
-#pragma unroll
-                    for (int j = 0; j < 12; ++j) raw[j] = src[j];
-                }
-                float sum = 0.f;
-#pragma unroll
-                for (int j = 0; j < 12; ++j) {
-                    float v[8];
-                    unpack8(raw[j], v);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) sum += v[i];
-                }
-                const float mean = sum * (1.f / C);
-                float sq = 0.f;
-#pragma unroll
-                for (int j = 0; j < 12; ++j) {
-                    float v[8];
-                    unpack8(raw[j], v);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) { const float d = v[i] - mean; sq += d * d; }
-                }
-                const float rstd = rsqrtf(sq * (1.f / C) + a.eps);
-                mbarWait(base + sBarAEmpty + 8u * buf, (use & 1u) ^ 1u);   // the last fc1 chunk that read this buffer has completed
-                emit(raw, 0, mean, rstd, valid, rowAddr);
-            } else {
-                // 384-byte rows do not fit the register budget next to the epilogue warps: statistics in one streaming pass (sums of
-                // x - x0 and (x - x0)^2 with x0 = the row's first element, so a large common offset cannot cancel), then the row
-                // is read again (an L2 hit) 96 channels at a time for the normalisation
-                float x0 = 0.f, s1 = 0.f, s2 = 0.f;
-#pragma unroll
-                for (int h = 0; h < Cfg::kPieces / 12; ++h) {
-#pragma unroll
-                    for (int j = 0; j < 12; ++j) raw[j] = make_uint4(0, 0, 0, 0);
-                    if (valid) {
-#pragma unroll
-                        for (int j = 0; j < 12; ++j) raw[j] = src[12 * h + j];
-                    }
-                    if (h == 0) x0 = __low2float(*reinterpret_cast<const __half2*>(&raw[0]));
-#pragma unroll
-                    for (int j = 0; j < 12; ++j) {
-                        float v[8];
-                        unpack8(raw[j], v);
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) { const float d = v[i] - x0; s1 += d; s2 = fmaf(d, d, s2); }
-                    }
-                }
-                const float m1 = s1 * (1.f / C);
-                const float mean = x0 + m1;
-                const float rstd = rsqrtf(fmaxf(s2 * (1.f / C) - m1 * m1, 0.f) + a.eps);
-                if (valid) {
-#pragma unroll
-                    for (int j = 0; j < 12; ++j) raw[j] = src[j];   // in flight while the buffer is still being read by fc1
-                }
-                mbarWait(base + sBarAEmpty + 8u * buf, (use & 1u) ^ 1u);
-#pragma unroll
-                for (int h = 0; h < Cfg::kPieces / 12; ++h) {
-                    uint4 nxt[12];
-                    if (h + 1 < Cfg::kPieces / 12 && valid) {
-#pragma unroll
-                        for (int j = 0; j < 12; ++j) nxt[j] = src[12 * (h + 1) + j];
-                    }
-                    emit(raw, 12 * h, mean, rstd, valid, rowAddr);
-                    if (h + 1 < Cfg::kPieces / 12) {
-#pragma unroll
-                        for (int j = 0; j < 12; ++j) raw[j] = nxt[j];
-                    }
-                }
-            }
-            fenceProxyAsync();
-            __syncwarp();
-            if (lane == 0) mbarArrive(base + sBarAFull + 8u * buf);
-        }
+        lnProducerLoop<C, Cfg::kABufs>(a, base, Cfg::kOffAS, Cfg::kGamma, Cfg::kBeta, base + sBarAFull, base + sBarAEmpty, first, step, nMine);
     } else if (warp == Cfg::kMmaW) {
         const uint32_t hi64 = descHi(512u, 4u), hi128 = descHi(1024u, 2u);
         const uint32_t idesc1 = instrDescF16(kRows, Cfg::kChunk), idesc2 = instrDescF16(kRows, C);
@@ -692,12 +659,166 @@ __global__ void __launch_bounds__(StreamCfg<C>::kThreadsS, 1) swin_mlp_stream_ke
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------------------
+// LayerNorm + Linear (the QKV projection of a block: out[tokens][3C] = LayerNorm(x) W^T + b), same producer / MMA / epilogue roles.
+// The output is produced in chunks of 96 columns: the chunk's weight rows W[c*96 .. +96][C] stream through a three-stage TMA ring,
+// fc(chunk) -> D (96 TMEM columns, double-buffered) -> + bias -> fp16 -> 16-byte stores.  The normalised rows never touch HBM.
+// ------------------------------------------------------------------------------------------------------------------------------
+template <int C>
+struct LinCfg {
+    static constexpr int kN = 3 * C;
+    static constexpr int kNC = 96;                            // output columns per chunk
+    static constexpr int kChunks = kN / kNC;
+    static constexpr int kKA = C / 32;
+    static constexpr int kProd = 4, kTmaW = 4, kMmaW = 5, kEpi0 = 6;
+    static constexpr int kThreadsL = 32 * (kEpi0 + kEpiWarps);
+    static constexpr int kStages = 3;
+    static constexpr uint32_t kStage = kKA * kNC * 64;        // kKA boxes [96 rows][32 k]
+    static constexpr uint32_t kABytes = kKA * kAChunk;
+    static constexpr uint32_t kOffRing = 4096;
+    static constexpr uint32_t kOffAS = kOffRing + kStages * kStage;
+    static constexpr uint32_t kSmem = kOffAS + 2 * kABytes + 1024;
+    static constexpr uint32_t kTmem = 256;
+    static constexpr uint32_t kBias = 256, kGamma = kBias + 4 * kN, kBeta = kGamma + 4 * C;
+    static_assert(kBeta + 4 * C <= kOffRing, "constants overflow the header");
+    static_assert(kStage % 1024 == 0 && kABytes % 1024 == 0, "swizzled operands need 1024-byte alignment");
+    static_assert(kSmem <= 227 * 1024, "shared memory budget");
+};
+constexpr uint32_t lBarWFull = 0, lBarWEmpty = 32, lBarAFull = 64, lBarAEmpty = 80, lBarDFull = 96, lBarDEmpty = 112, lTmemSlot = 128;
+
+template <int C>
+__global__ void __launch_bounds__(LinCfg<C>::kThreadsL, 1) swin_lnlinear_kernel(const __grid_constant__ MlpArgs a) {
+    using Cfg = LinCfg<C>;
+    extern __shared__ uint8_t smemRaw[];
+    const uint32_t base = (smemU32(smemRaw) + 1023u) & ~1023u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    pdlLaunchDependents();
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < Cfg::kStages; ++i) {
+            mbarInit(base + lBarWFull + 8u * i, 1);
+            mbarInit(base + lBarWEmpty + 8u * i, 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbarInit(base + lBarAFull + 8u * i, 4);
+            mbarInit(base + lBarAEmpty + 8u * i, 1);
+            mbarInit(base + lBarDFull + 8u * i, 1);
+            mbarInit(base + lBarDEmpty + 8u * i, kEpiWarps);
+        }
+        mbarInitFence();
+        tmaPrefetchDesc(&a.tmW1);
+    }
+    for (int i = threadIdx.x; i < Cfg::kN; i += Cfg::kThreadsL) stsF32(base + Cfg::kBias + 4u * i, a.b1[i]);
+    for (int i = threadIdx.x; i < C; i += Cfg::kThreadsL) {
+        stsF32(base + Cfg::kGamma + 4u * i, a.gamma[i]);
+        stsF32(base + Cfg::kBeta + 4u * i, a.beta[i]);
+    }
+    if (warp == Cfg::kMmaW) tmemAlloc(base + lTmemSlot, Cfg::kTmem);
+    tcFenceBefore();
+    __syncthreads();
+    tcFenceAfter();
+    uint32_t tmemBase;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmemBase) : "r"(base + lTmemSlot));
+    const long long tiles = (a.tokens + kRows - 1) / kRows;
+    const int first = blockIdx.x, step = gridDim.x;
+    const int nMine = first < tiles ? (int)((tiles - first + step - 1) / step) : 0;
+    const int nChunksMine = nMine * Cfg::kChunks;
+
+    if (warp == Cfg::kTmaW) {
+        if (lane == 0) {
+            int st = 0;
+            uint32_t ph = 0;
+            for (int g = 0; g < nChunksMine; ++g) {
+                const int c = g % Cfg::kChunks;
+                mbarWait(base + lBarWEmpty + 8u * st, ph ^ 1u);
+                const uint32_t full = base + lBarWFull + 8u * st, dst = base + Cfg::kOffRing + (uint32_t)st * Cfg::kStage;
+                mbarExpectTx(full, Cfg::kStage);
+                for (int ka = 0; ka < Cfg::kKA; ++ka) tmaLoad2d(dst + (uint32_t)ka * (Cfg::kNC * 64u), &a.tmW1, full, ka * 32, c * Cfg::kNC);
+                if (++st == Cfg::kStages) { st = 0; ph ^= 1u; }
+            }
+        }
+    } else if (warp < Cfg::kProd) {
+        lnProducerLoop<C, 2>(a, base, Cfg::kOffAS, Cfg::kGamma, Cfg::kBeta, base + lBarAFull, base + lBarAEmpty, first, step, nMine);
+    } else if (warp == Cfg::kMmaW) {
+        const uint32_t hi64 = descHi(512u, 4u);
+        const uint32_t idesc = instrDescF16(kRows, Cfg::kNC);
+        int st = 0;
+        uint32_t ph = 0;
+        for (int g = 0; g < nChunksMine; ++g) {
+            const int k = g / Cfg::kChunks, c = g - k * Cfg::kChunks, buf = k & 1, d = g & 1;
+            if (c == 0) mbarWait(base + lBarAFull + 8u * buf, (uint32_t)(k >> 1) & 1u);
+            mbarWait(base + lBarWFull + 8u * st, ph);
+            mbarWait(base + lBarDEmpty + 8u * d, ((uint32_t)(g >> 1) & 1u) ^ 1u);
+            tcFenceAfter();
+            if (electOne()) {
+                const uint32_t aBase = base + Cfg::kOffAS + (uint32_t)buf * Cfg::kABytes, wBase = base + Cfg::kOffRing + (uint32_t)st * Cfg::kStage;
+#pragma unroll
+                for (int ka = 0; ka < Cfg::kKA; ++ka)
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks)
+                        ummaLoHi(tmemBase + (uint32_t)d * 128u, descLo(aBase + ka * kAChunk + ks * 32u), hi64, descLo(wBase + ka * (Cfg::kNC * 64u) + ks * 32u), hi64, idesc,
+                                 (ka | ks) != 0 ? 1u : 0u);
+                tcCommit(base + lBarDFull + 8u * d);
+                tcCommit(base + lBarWEmpty + 8u * st);
+                if (c == Cfg::kChunks - 1) tcCommit(base + lBarAEmpty + 8u * buf);
+            }
+            __syncwarp();
+            if (++st == Cfg::kStages) { st = 0; ph ^= 1u; }
+        }
+    } else {
+        pdlWait();  // the output buffer may still be read by the preceding kernels
+        const int quarter = warp & 3;
+        const int half = (warp - Cfg::kEpi0) >> 2;
+        const int row = quarter * 32 + lane;
+        const uint32_t taddrLane = tmemBase + ((uint32_t)(quarter * 32) << 16);
+        uint32_t r[32], r2[32];
+        for (int g = 0; g < nChunksMine; ++g) {
+            const int k = g / Cfg::kChunks, c = g - k * Cfg::kChunks, d = g & 1;
+            const long long tok = ((long long)first + (long long)k * step) * kRows + row;
+            mbarWait(base + lBarDFull + 8u * d, (uint32_t)(g >> 1) & 1u);
+            tcFenceAfter();
+            const int col0 = half * 48;
+            tmemLd32(taddrLane + (uint32_t)(d * 128 + col0), r);
+            tmemLd16(taddrLane + (uint32_t)(d * 128 + col0 + 32), r2);
+            tmemLdWait();
+            tcFenceBefore();
+            __syncwarp();
+            if (lane == 0) mbarArrive(base + lBarDEmpty + 8u * d);
+            if (tok < a.tokens) {
+                uint4* dst = reinterpret_cast<uint4*>(a.out + tok * Cfg::kN + c * Cfg::kNC + col0);
+#pragma unroll
+                for (int j = 0; j < 6; ++j) {
+                    float bias[8];
+                    loadF8(base + Cfg::kBias + 4u * (uint32_t)(c * Cfg::kNC + col0 + 8 * j), bias);
+                    uint4 o;
+                    __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float a0 = __uint_as_float(j < 4 ? r[8 * j + 2 * i] : r2[8 * (j - 4) + 2 * i]);
+                        const float a1 = __uint_as_float(j < 4 ? r[8 * j + 2 * i + 1] : r2[8 * (j - 4) + 2 * i + 1]);
+                        oh[i] = __floats2half2_rn(a0 + bias[2 * i], a1 + bias[2 * i + 1]);
+                    }
+                    dst[j] = o;
+                }
+            }
+        }
+    }
+
+    tcFenceBefore();
+    __syncthreads();
+    if (warp == Cfg::kMmaW) {
+        tcFenceAfter();
+        tmemDealloc(tmemBase, Cfg::kTmem);
+    }
+}
+
 }  // namespace
 
 struct SwinMlpPlan {
     MlpArgs args;
     int c = 0;
     bool stream = false;   // weights streamed per hidden chunk (swin_mlp_stream_kernel) instead of resident
+    bool linear = false;   // LayerNorm + Linear (swin_lnlinear_kernel) instead of the MLP
 };
 
 bool swinMlpSupported(int c, int hidden) { return (c == 96 || c == 192) && hidden == 2 * c; }
@@ -733,9 +854,40 @@ SwinMlpPlan* swinMlpCreatePlan(__half* x, int c, const float* gamma, const float
     return plan;
 }
 
+bool swinLnLinearSupported(int c, int n) { return (c == 96 || c == 192) && n == 3 * c; }
+
+// out[tokens][3c] = LayerNorm(x) w^T + bias, w = [3c][c] fp16 K-major
+SwinMlpPlan* swinLnLinearCreatePlan(const __half* x, int c, const float* gamma, const float* beta, float eps, const __half* w, const float* bias, __half* out) {
+    if (!swinLnLinearSupported(c, 3 * c)) throw Error("swin ln+linear: unsupported width");
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(out)) & 15) throw Error("swin ln+linear: operands must be 16-byte aligned");
+    SwinMlpPlan* plan = new SwinMlpPlan{};
+    plan->c = c;
+    plan->linear = true;
+    try {
+        encodeMatrixMap2d(&plan->args.tmW1, w, c, 3 * c, 32, 96, false);
+        plan->args.tmW2 = plan->args.tmW1;
+    } catch (...) {
+        delete plan;
+        throw;
+    }
+    plan->args.x = const_cast<__half*>(x);
+    plan->args.out = out;
+    plan->args.b1 = bias;
+    plan->args.b2 = bias;
+    plan->args.gamma = gamma;
+    plan->args.beta = beta;
+    plan->args.eps = eps;
+    return plan;
+}
+
 void swinMlpDestroyPlan(SwinMlpPlan* plan) { delete plan; }
 
 const char* swinMlpDescribe(const SwinMlpPlan* plan, char* buf, int cap) {
+    if (plan->linear) {
+        std::snprintf(buf, cap, "swin-lnlinear fused LN+Linear (tcgen05) c=%d n=%d rows=%d weights=streamed smem=%u", plan->c, 3 * plan->c, kRows,
+                      plan->c == 96 ? LinCfg<96>::kSmem : LinCfg<192>::kSmem);
+        return buf;
+    }
     const unsigned smem = !plan->stream ? kMlpSmem : plan->c == 96 ? StreamCfg<96>::kSmem : StreamCfg<192>::kSmem;
     std::snprintf(buf, cap, "swin-mlp fused LN+fc1+GELU+fc2+residual (tcgen05) c=%d hidden=%d rows=%d weights=%s smem=%u", plan->c, 2 * plan->c, kRows,
                   plan->stream ? "streamed" : "resident", smem);
@@ -752,6 +904,8 @@ void swinMlpLaunch(const SwinMlpPlan* plan, cudaStream_t s, long long tokens) {
         cudaFuncSetAttribute(swin_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMlpSmem);
         cudaFuncSetAttribute(swin_mlp_stream_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, StreamCfg<96>::kSmem);
         cudaFuncSetAttribute(swin_mlp_stream_kernel<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, StreamCfg<192>::kSmem);
+        cudaFuncSetAttribute(swin_lnlinear_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, LinCfg<96>::kSmem);
+        cudaFuncSetAttribute(swin_lnlinear_kernel<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, LinCfg<192>::kSmem);
         cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
         if (sms[dev] <= 0) sms[dev] = 148;
         attrSet[dev] = true;
@@ -762,7 +916,9 @@ void swinMlpLaunch(const SwinMlpPlan* plan, cudaStream_t s, long long tokens) {
     const long long tiles = (tokens + kRows - 1) / kRows;
     const dim3 grid((unsigned)(tiles < sms[dev] ? tiles : sms[dev]));
     cudaError_t e;
-    if (!plan->stream) e = launchPdl(swin_mlp_kernel, grid, dim3(kMlpThreads), kMlpSmem, s, a);
+    if (plan->linear && plan->c == 96) e = launchPdl(swin_lnlinear_kernel<96>, grid, dim3(LinCfg<96>::kThreadsL), LinCfg<96>::kSmem, s, a);
+    else if (plan->linear) e = launchPdl(swin_lnlinear_kernel<192>, grid, dim3(LinCfg<192>::kThreadsL), LinCfg<192>::kSmem, s, a);
+    else if (!plan->stream) e = launchPdl(swin_mlp_kernel, grid, dim3(kMlpThreads), kMlpSmem, s, a);
     else if (plan->c == 96) e = launchPdl(swin_mlp_stream_kernel<96>, grid, dim3(StreamCfg<96>::kThreadsS), StreamCfg<96>::kSmem, s, a);
     else e = launchPdl(swin_mlp_stream_kernel<192>, grid, dim3(StreamCfg<192>::kThreadsS), StreamCfg<192>::kSmem, s, a);
     if (e != cudaSuccess) throw Error(std::string("swin mlp launch: ") + cudaGetErrorString(e));
