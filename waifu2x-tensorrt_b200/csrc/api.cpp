@@ -362,6 +362,53 @@ int w2x_run_swin_lnlinear(int device, long long tokens, int c, const uint16_t* x
     return ok;
 }
 
+int w2x_run_swin_attn(int device, int n, int h, int w, int c, int heads, int shift, uint16_t* x, const float* gamma, const float* beta, float eps, const uint16_t* wqkv,
+                      const float* bqkv, const uint16_t* wproj, const float* bproj, const float* relpos, int reps, float* ms_out) {
+    void* bufs[8] = {};
+    SwinAttnPlan* plan = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    int ok = 0;
+    try {
+        if (n < 1 || !x || !gamma || !beta || !wqkv || !bqkv || !wproj || !bproj || !relpos || !swinAttnSupported(c, heads, 6, h, w)) throw Error("invalid argument");
+        W2X_CUDA(cudaSetDevice(device));
+        std::vector<uint16_t> wR;
+        std::vector<float> bR, relR;
+        swinAttnPrepare(wqkv, bqkv, relpos, c, heads, wR, bR, relR);
+        const size_t C = (size_t)c;
+        const size_t sizes[8] = {(size_t)n * h * w * C * 2, C * 4, C * 4, wR.size() * 2, bR.size() * 4, C * C * 2, C * 4, relR.size() * 4};
+        const void* host[8] = {x, gamma, beta, wR.data(), bR.data(), wproj, bproj, relR.data()};
+        for (int i = 0; i < 8; ++i) {
+            W2X_CUDA(cudaMalloc(&bufs[i], sizes[i]));
+            W2X_CUDA(cudaMemcpy(bufs[i], host[i], sizes[i], cudaMemcpyHostToDevice));
+        }
+        W2X_CUDA(cudaDeviceSynchronize());
+        plan = swinAttnCreatePlan((__half*)bufs[0], n, h, w, c, heads, 6, shift, (const float*)bufs[1], (const float*)bufs[2], eps, (const __half*)bufs[3],
+                                  (const float*)bufs[4], (const __half*)bufs[5], (const float*)bufs[6], (const float*)bufs[7]);
+        swinAttnLaunch(plan, nullptr, n);
+        W2X_CUDA(cudaDeviceSynchronize());
+        W2X_CUDA(cudaMemcpy(x, bufs[0], sizes[0], cudaMemcpyDeviceToHost));
+        if (ms_out && reps > 0) {
+            W2X_CUDA(cudaEventCreate(&e0));
+            W2X_CUDA(cudaEventCreate(&e1));
+            W2X_CUDA(cudaEventRecord(e0, nullptr));
+            for (int i = 0; i < reps; ++i) swinAttnLaunch(plan, nullptr, n);
+            W2X_CUDA(cudaEventRecord(e1, nullptr));
+            W2X_CUDA(cudaEventSynchronize(e1));
+            W2X_CUDA(cudaEventElapsedTime(ms_out, e0, e1));
+            *ms_out /= (float)reps;
+        }
+        ok = 1;
+    } catch (const std::exception& ex) {
+        std::fprintf(stderr, "w2x_run_swin_attn: %s\n", ex.what());
+    }
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (plan) swinAttnDestroyPlan(plan);
+    for (void* b : bufs)
+        if (b) cudaFree(b);
+    return ok;
+}
+
 #ifdef W2X_DEV
 int w2x_probe_umma(int device, int mode, int pitch, float* err9) {
     try {

@@ -134,6 +134,7 @@ void Engine::unload() {
         if (L.plan) igemmDestroyPlan(L.plan);
         if (L.head) convHeadDestroyPlan(L.head);
         if (L.mlp) swinMlpDestroyPlan(L.mlp);
+        if (L.attn) swinAttnDestroyPlan(L.attn);
     }
     layers.clear();
     for (void* p : allocs) cudaFree(p);
@@ -447,6 +448,7 @@ void Engine::launchLayer(LayerExec& L, cudaStream_t s, __half* outp, int nImg, c
         case IMPL_IGEMM: igemmLaunch(L.plan, s, outp, nImg, inOverride); break;
         case IMPL_HEAD: launchConvHead(L.head, s, outp, nImg); break;
         case IMPL_SWIN_MLP: swinMlpLaunch(L.mlp, s, (long long)nImg * L.tokH * L.tokW); break;
+        case IMPL_SWIN_ATTN: swinAttnLaunch(L.attn, s, nImg); break;
         case IMPL_LAYERNORM:
             launchLayerNorm(L.tokIn, L.tokOut, (long long)nImg * L.tokH * L.tokW, L.tokC, L.gamma, L.beta, L.eps, s);
             break;
@@ -567,6 +569,9 @@ void Engine::buildPlanSwin() {
         if (residual) { p.skip = residual->p; p.skip_h = residual->h; p.skip_w = residual->w; p.skip_c = residual->c; p.skip_off = 0; }
         pushConv(i, p, 2.0 * in.h * in.w * (double)L.npad * L.ktot);
     };
+    // regrouped / pre-scaled attention operands of the fused kernel: the host copies stay alive until the uploads have landed
+    std::vector<std::vector<uint16_t>> keepW;
+    std::vector<std::vector<float>> keepF;
     int blockIndex = 0;
     auto block = [&](Act& x) {
         const int h = x.h, w = x.w, c = x.c;
@@ -580,7 +585,38 @@ void Engine::buildPlanSwin() {
             layers.push_back(E);
         };
         const PackedLayer& QK = model.layers[qk];
-        if (kFuseLnQkv && !useDirect && !devEnv("W2X_NO_MLP_FUSE") && swinLnLinearSupported(c, (int)QK.npad) && (int)QK.ktot == c) {
+        const PackedLayer &AT = model.layers[at], &PJ = model.layers[pj];
+        const int blockShift = (blockIndex % 2) ? (int)AT.window / 2 : 0;
+        const bool fuseAttn = !useDirect && !devEnv("W2X_NO_ATTN_FUSE") && swinAttnSupported(c, (int)AT.heads, (int)AT.window, h, w) && (int)QK.npad == 3 * c &&
+                              (int)QK.ktot == c && (int)PJ.npad == c && (int)PJ.ktot == c && AT.relpos.size() == (size_t)AT.heads * 36 * 36;
+        if (fuseAttn) {
+            // x += proj(window attention(LayerNorm(x))) in ONE kernel: normalised rows, Q / K / V, scores and probabilities stay on the SM
+            keepW.emplace_back();
+            keepF.emplace_back();
+            keepF.emplace_back();
+            std::vector<uint16_t>& wR = keepW.back();
+            std::vector<float>&bR = keepF[keepF.size() - 2], &relR = keepF.back();
+            swinAttnPrepare(QK.w.data(), QK.bias.data(), AT.relpos.data(), c, (int)AT.heads, wR, bR, relR);
+            __half* dWr = (__half*)dalloc(wR.size() * 2);
+            uploadAsync(dWr, wR.data(), wR.size() * 2);
+            float* dBr = uploadF(bR);
+            float* dRel = uploadF(relR);
+            for (size_t i : {n1, qk, at}) {
+                LayerExec S;
+                S.name = model.layers[i].name;
+                S.impl = IMPL_SKIP;
+                layers.push_back(S);
+            }
+            LayerExec E;
+            E.name = PJ.name;
+            E.impl = IMPL_SWIN_ATTN;
+            E.tokN = x.n; E.tokH = h; E.tokW = w; E.tokC = c;
+            E.heads = (int)AT.heads; E.window = (int)AT.window; E.shift = blockShift;
+            E.flops = 2.0 * h * w * ((double)QK.npad * QK.ktot + (double)PJ.npad * PJ.ktot) + 4.0 * (h / 6) * (w / 6) * 36.0 * 36.0 * c;
+            E.attn = swinAttnCreatePlan(x.p, x.n, h, w, c, (int)AT.heads, (int)AT.window, blockShift, dAux0[n1], dAux1[n1], model.layers[n1].eps, dWr, dBr, dW[pj],
+                                        dBias[pj], dRel);
+            layers.push_back(E);
+        } else if (kFuseLnQkv && !useDirect && !devEnv("W2X_NO_MLP_FUSE") && swinLnLinearSupported(c, (int)QK.npad) && (int)QK.ktot == c) {
             // qkv = LayerNorm(x) Wqkv^T + b in ONE kernel: the normalised rows stay in shared memory
             LayerExec S;
             S.name = model.layers[n1].name;
@@ -597,7 +633,7 @@ void Engine::buildPlanSwin() {
             pushLn(n1);
             linear(qk, ln, qkv, ACT_LRELU, nullptr);
         }
-        {
+        if (!fuseAttn) {
             const PackedLayer& L = model.layers[at];
             if (L.window != 6 || (c / (int)L.heads != 16 && c / (int)L.heads != 32) || h % 6 || w % 6)
                 throw Error("swin plan: unsupported attention geometry (window 6, head dim 16/32 only)");
@@ -608,8 +644,8 @@ void Engine::buildPlanSwin() {
             E.relpos = dAux0[at];
             E.flops = 4.0 * (h / 6) * (w / 6) * 36.0 * 36.0 * c;
             layers.push_back(E);
+            linear(pj, att, x, ACT_LRELU, &x);   // x += proj(attn)
         }
-        linear(pj, att, x, ACT_LRELU, &x);   // x += proj(attn)
         const PackedLayer &F1 = model.layers[f1], &F2 = model.layers[f2];
         if (!useDirect && !devEnv("W2X_NO_MLP_FUSE") && swinMlpSupported(c, (int)F1.npad) && (int)F1.ktot == c && (int)F2.npad == c && F2.ktot == F1.npad) {
             // x += fc2(gelu(fc1(LayerNorm(x)))) in ONE kernel: the normalised rows and the hidden tensor stay in shared memory
@@ -688,6 +724,7 @@ void Engine::buildPlanSwin() {
     if (li != model.layers.size()) throw Error("swin plan: trailing layers in pack file");
     outTile = actOut.h;
     if (outTile != (tile - 16) * S) throw Error("internal: swin output tile size mismatch");
+    W2X_CUDA(cudaStreamSynchronize(stream));  // keepW / keepF are read by the uploads above
 }
 
 int Engine::layerKernel(int index, char* buf, int cap) const {
@@ -695,6 +732,7 @@ int Engine::layerKernel(int index, char* buf, int cap) const {
     const LayerExec& L = layers[index];
     if (L.plan) igemmDescribe(L.plan, buf, cap);
     else if (L.mlp) swinMlpDescribe(L.mlp, buf, cap);
+    else if (L.attn) swinAttnDescribe(L.attn, buf, cap);
     else std::snprintf(buf, cap, "%s", L.impl == IMPL_FIRST ? "first-layer mma.sync" : L.impl == IMPL_LAYERNORM ? "layernorm" :
                                        L.impl == IMPL_ATTENTION ? "window-attention mma.sync" :
                                        L.impl == IMPL_HEAD ? "head kernel, taps in N (tcgen05)" : L.impl == IMPL_SKIP ? "fused into the next layer" : "direct (reference kernel)");

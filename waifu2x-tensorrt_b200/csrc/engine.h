@@ -25,7 +25,7 @@ struct Act {
     size_t elems() const { return (size_t)n * h * w * c; }
 };
 
-enum ConvImpl { IMPL_DIRECT = 0, IMPL_FIRST = 1, IMPL_IGEMM = 2, IMPL_LAYERNORM = 3, IMPL_ATTENTION = 4, IMPL_HEAD = 5, IMPL_SKIP = 6, IMPL_SWIN_MLP = 7 };
+enum ConvImpl { IMPL_DIRECT = 0, IMPL_FIRST = 1, IMPL_IGEMM = 2, IMPL_LAYERNORM = 3, IMPL_ATTENTION = 4, IMPL_HEAD = 5, IMPL_SKIP = 6, IMPL_SWIN_MLP = 7, IMPL_SWIN_ATTN = 8 };
 
 struct LayerExec {
     std::string name;
@@ -34,6 +34,7 @@ struct LayerExec {
     IgemmPlan* plan = nullptr;
     HeadPlan* head = nullptr;  // IMPL_HEAD
     SwinMlpPlan* mlp = nullptr;  // IMPL_SWIN_MLP: LayerNorm + fc1 + GELU + fc2 + residual in one kernel (the two preceding layers are IMPL_SKIP)
+    SwinAttnPlan* attn = nullptr;  // IMPL_SWIN_ATTN: LayerNorm + QKV + window attention + proj + residual in one kernel (three preceding layers are IMPL_SKIP)
     double flops = 0;  // algorithmic 2*MAC for ONE tile
     bool isFinal = false;
     // squeeze/excite applied to p.out after the conv

@@ -7,6 +7,7 @@
 #pragma once
 #include <cuda_fp16.h>
 #include <cstdint>
+#include <vector>
 
 namespace w2x {
 
@@ -200,6 +201,15 @@ SwinMlpPlan* swinLnLinearCreatePlan(const __half* x, int c, const float* gamma, 
 void swinMlpDestroyPlan(SwinMlpPlan* plan);
 void swinMlpLaunch(const SwinMlpPlan* plan, cudaStream_t s, long long tokens);
 const char* swinMlpDescribe(const SwinMlpPlan* plan, char* buf, int cap);
+struct SwinAttnPlan;                                              // fused LN + QKV + window attention + proj + residual (kernels/swin_attn_sm100.cu)
+bool swinAttnSupported(int c, int heads, int window, int h, int w);
+void swinAttnPrepare(const uint16_t* wqkv, const float* bqkv, const float* relpos, int c, int heads, std::vector<uint16_t>& wOut, std::vector<float>& bOut,
+                     std::vector<float>& relOut);
+SwinAttnPlan* swinAttnCreatePlan(__half* x, int n, int h, int w, int c, int heads, int window, int shift, const float* gamma, const float* beta, float eps,
+                                 const __half* wqkvR, const float* bqkvR, const __half* wproj, const float* bproj, const float* relposR);
+void swinAttnDestroyPlan(SwinAttnPlan* plan);
+void swinAttnLaunch(const SwinAttnPlan* plan, cudaStream_t s, int nImages);
+const char* swinAttnDescribe(const SwinAttnPlan* plan, char* buf, int cap);
 struct IgemmPlan;                                                 // opaque: tensor maps + launch geometry
 IgemmPlan* igemmCreatePlan(const ConvParams& p);                  // throws w2x::Error when unsupported
 void igemmDestroyPlan(IgemmPlan* plan);

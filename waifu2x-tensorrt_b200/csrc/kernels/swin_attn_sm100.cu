@@ -1,0 +1,640 @@
+// Fused attention half of a SwinUNet block (torchvision SwinTransformerBlock: x = x + proj(W-MSA / SW-MSA(LayerNorm(x)))), one
+// kernel instead of layernorm_kernel + QKV igemm + window_attention_kernel (mma.sync) + proj igemm.  The token rows are read from HBM
+// once and written once; the normalised rows, Q, K, V, the scores, the probabilities and the attention output never leave the SM.
+//
+// A tile is three 6x6 windows (108 tokens, rows 108..127 of the M = 128 UMMA tile are padding).  Row r holds position r % 36 of window
+// r / 36; the cyclic shift (torch.roll) and the window partition are the address math of the gather / scatter.  Per tile and per
+// 32-channel chunk c of Q / K / V (C = 96: a pair of 16-wide heads):
+//
+//   QKV(c)   D1[128][96]  = LN(x)[128][C] . W'[c]^T          6 x tcgen05.mma M128 N96 K16   (W' = rows of Wqkv regrouped per chunk,
+//                                                                                           q rows pre-multiplied by d^-1/2 log2 e)
+//   E1(c)    D1 + bias -> fp16 -> Q[128][32], K[key][32] (K-major SWIZZLE_64B operands), V^T[32][key] (SWIZZLE_128B); the key index of
+//            row r is 40 (r / 36) + r % 36, so a window's keys start at a 16-byte chunk of a probability row
+//   S(h)     S_h[128][128] = Q_h K_h^T                       1 x M128 N128 K16 per head (block-diagonal: only the 36 columns of a row's
+//                                                            own window are ever read back)
+//   SM(h)    thread = query row: tcgen05.ld of its window's 40 columns, + relative-position bias (+ shift mask), exp2 softmax,
+//            probabilities -> fp16 -> P[128][128] (SWIZZLE_128B A operand; off-diagonal blocks stay zero from the prologue)
+//   PV(h)    O[128][16 h .. +16] = P V_h                     8 x M128 N16 K16
+//   E2(c)    O -> fp16 -> Oc[128][32] (A operand)
+//   proj(c)  D2[128][C] += Oc . Wproj[:, 32 c .. +32]^T      2 x M128 N96 K16
+//   E3       D2 + bias + residual -> x (in place, scattered back to the tokens' positions)
+//
+// Roles: warps 0-3 LayerNorm producers (swin_token.cuh, one token row per thread), warp 4 MMA issuer (one elected lane), warps 5-12
+// epilogue / softmax (two warps per TMEM lane quarter).  The epilogue warps run SM(2g), E1(g+1), E2(g-1), SM(2g+1), E3 in that order
+// over the CTA's chunk sequence g, so every tensor-core hand-off is covered by CUDA-core work of a neighbouring chunk; the MMA warp
+// issues in the matching order.  All weights (Wqkv' 54 KB, Wproj 18 KB) and the bias tables (6 heads x [36][44] fp32) stay resident.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "conv_params.h"
+#include "launch.h"
+#include "sm100_common.cuh"
+#include "swin_token.cuh"
+
+namespace w2x {
+using namespace sm100;
+using namespace swintok;
+namespace {
+
+constexpr int kC = 96;                 // token width
+constexpr int kHeads = 6, kHD = 16;    // head dim 16: a 32-channel chunk is a pair of heads
+constexpr int kChunks = kC / 32;
+constexpr int kWin = 6, kNT = 36;      // window side, tokens per window
+constexpr int kWinTile = 3;            // windows per tile
+constexpr int kKeyStride = 40;         // key index of window w, position p: 40 w + p (a window starts at a 16-byte chunk of a P row)
+constexpr int kBiasPitch = 44;         // floats per bias-table row: 16-byte loads of 8 consecutive rows hit distinct banks
+constexpr uint32_t kBiasHead = kNT * kBiasPitch * 4;
+constexpr int kMmaWarp = 4, kEpiWarp0 = 5, kEpiWarps = 8;
+constexpr int kAttnThreads = 32 * (kEpiWarp0 + kEpiWarps);   // 416
+
+// barriers (byte offsets from the 1024-aligned base)
+constexpr uint32_t bW = 0, bAFull = 8, bAEmpty = 16, bD1Full = 24, bQKFull = 32, bQKEmpty = 40, bVEmpty = 48, bSFull = 64, bSEmpty = 80, bPFull = 96, bPEmpty = 104,
+                   bOFull = 112, bOEmpty = 128, bOcFull = 144, bOcEmpty = 152, bD2Full = 160, bD2Empty = 168, kTmemSlot = 176;
+constexpr uint32_t kOffBqkv = 256, kOffBproj = kOffBqkv + 3 * kC * 4, kOffGamma = kOffBproj + kC * 4, kOffBeta = kOffGamma + kC * 4;
+constexpr uint32_t kWqkvKa = 3 * kC * 64;              // one 32-wide K chunk of W': [288 rows][32 k] fp16, SWIZZLE_64B
+constexpr uint32_t kWqkvChunk = 96 * 64;               // the 96 rows (q32 | k32 | v32) of one channel chunk inside it
+constexpr uint32_t kWprojKa = kC * 64;                 // [96 rows][32 k]
+constexpr uint32_t kOffWqkv = 4096;
+constexpr uint32_t kOffWproj = kOffWqkv + kChunks * kWqkvKa;
+constexpr uint32_t kOffBias = kOffWproj + kChunks * kWprojKa;
+constexpr uint32_t kBiasBytes = kHeads * kBiasHead;
+constexpr uint32_t kOffA = (kOffBias + kBiasBytes + 1023u) & ~1023u;
+constexpr uint32_t kOffQ = kOffA + kChunks * kAChunk;
+constexpr uint32_t kOffK = kOffQ + kAChunk;
+constexpr uint32_t kVBuf = 2 * 32 * 128;               // V^T: two 64-key chunks of [32 dims][64 keys] fp16, SWIZZLE_128B
+constexpr uint32_t kOffV = kOffK + kAChunk;
+constexpr uint32_t kPChunk = kRows * 128;              // [128 rows][64 keys]
+constexpr uint32_t kOffP = kOffV + 2 * kVBuf;
+constexpr uint32_t kOffOc = kOffP + 2 * kPChunk;
+constexpr uint32_t kAttnSmem = kOffOc + kAChunk + 1024;   // + alignment slack
+static_assert(kOffBeta + kC * 4 <= kOffWqkv, "constants overflow the header");
+static_assert(kOffWproj % 1024 == 0 && kOffA % 1024 == 0 && kOffV % 1024 == 0 && kOffP % 1024 == 0 && kOffOc % 1024 == 0, "swizzled operands need 1024-byte alignment");
+static_assert(kBiasBytes % 16 == 0 && kOffBias % 16 == 0, "bulk copy granularity");
+static_assert(kAttnSmem <= 227 * 1024, "shared memory budget");
+// TMEM columns
+constexpr uint32_t tD1 = 0, tD2 = 96, tS = 192, tO = 448, kTmemCols = 512;
+
+struct AttnArgs {
+    CUtensorMap tmWqkv, tmWproj;
+    __half* x;               // [n][h][w][C] fp16, updated in place
+    const float* bqkv;       // [3C] regrouped like W' (q part pre-scaled)
+    const float* bproj;      // [C]
+    const float* gamma;      // [C]
+    const float* beta;       // [C]
+    const float* relpos;     // [heads][36][kBiasPitch] fp32, multiplied by log2 e
+    float eps;
+    int h, w, shiftY, shiftX;   // cyclic shift per dimension (torchvision drops it in a dimension the window covers)
+    int nwx, nwy;            // windows per row / column of an image
+    long long windows;       // n * nwy * nwx
+};
+
+__device__ __forceinline__ void bulkLoad1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmemLd8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void stsU16(uint32_t addr, unsigned short v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory"); }
+__device__ __forceinline__ float ex2f(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ uint32_t packH2(float a, float b) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+// token held by row `row` of tile `tile` (window-ordered gather; < 0 for padding rows and windows past the end)
+struct WindowTokens {
+    int h, w, shiftY, shiftX, nwx, nwy;
+    long long windows;
+    int first, step;
+    __device__ __forceinline__ long long tokenOfTile(long long tile, int row) const {
+        if (row >= kWinTile * kNT) return -1;
+        const int wi = row / kNT, p = row - wi * kNT;
+        long long win = tile * kWinTile + wi;
+        if (win >= windows) return -1;
+        const int wx = (int)(win % nwx);
+        win /= nwx;
+        const int wy = (int)(win % nwy);
+        const long long img = win / nwy;
+        int y = wy * kWin + p / kWin + shiftY, x = wx * kWin + p % kWin + shiftX;   // torch.roll(x, -shift): rolled[p] = x[p + shift]
+        if (y >= h) y -= h;
+        if (x >= w) x -= w;
+        return (img * h + y) * (long long)w + x;
+    }
+    __device__ __forceinline__ long long operator()(int k, int row) const { return tokenOfTile((long long)first + (long long)k * step, row); }
+};
+
+__global__ void __launch_bounds__(kAttnThreads, 1) swin_attn_kernel(const __grid_constant__ AttnArgs a) {
+    extern __shared__ uint8_t smemRaw[];
+    const uint32_t base = (smemU32(smemRaw) + 1023u) & ~1023u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    pdlLaunchDependents();
+
+    // ---- prologue: constants only (weights, biases, LayerNorm parameters, bias tables) ----
+    if (threadIdx.x == 0) {
+        mbarInit(base + bW, 1);
+        mbarInit(base + bAFull, 4);
+        mbarInit(base + bAEmpty, 1);
+        mbarInit(base + bD1Full, 1);
+        mbarInit(base + bQKFull, kEpiWarps);
+        mbarInit(base + bQKEmpty, 1);
+        mbarInit(base + bPFull, kEpiWarps);
+        mbarInit(base + bPEmpty, 1);
+        mbarInit(base + bOcFull, kEpiWarps);
+        mbarInit(base + bOcEmpty, 1);
+        mbarInit(base + bD2Full, 1);
+        mbarInit(base + bD2Empty, kEpiWarps);
+        for (int i = 0; i < 2; ++i) {
+            mbarInit(base + bVEmpty + 8u * i, 1);
+            mbarInit(base + bSFull + 8u * i, 1);
+            mbarInit(base + bSEmpty + 8u * i, kEpiWarps);
+            mbarInit(base + bOFull + 8u * i, 1);
+            mbarInit(base + bOEmpty + 8u * i, kEpiWarps);
+        }
+        mbarInitFence();
+        tmaPrefetchDesc(&a.tmWqkv);
+        tmaPrefetchDesc(&a.tmWproj);
+    }
+    for (int i = threadIdx.x; i < 3 * kC; i += kAttnThreads) stsF32(base + kOffBqkv + 4u * i, a.bqkv[i]);
+    for (int i = threadIdx.x; i < kC; i += kAttnThreads) {
+        stsF32(base + kOffBproj + 4u * i, a.bproj[i]);
+        stsF32(base + kOffGamma + 4u * i, a.gamma[i]);
+        stsF32(base + kOffBeta + 4u * i, a.beta[i]);
+    }
+    // Q / K / V / P / Oc start as zeros: padding keys (K rows and V^T columns nobody writes) must be finite, and the off-diagonal
+    // blocks of P (rows of one window x keys of another) are never written
+    for (uint32_t o = (uint32_t)threadIdx.x * 16u; o < kOffOc + kAChunk - kOffQ; o += (uint32_t)kAttnThreads * 16u) stsV4(base + kOffQ + o, make_uint4(0, 0, 0, 0));
+    fenceProxyAsync();
+    if (warp == kMmaWarp) tmemAlloc(base + kTmemSlot, kTmemCols);
+    tcFenceBefore();
+    __syncthreads();
+    tcFenceAfter();
+    uint32_t tmemBase;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmemBase) : "r"(base + kTmemSlot));
+    if (warp == kMmaWarp && lane == 0) {
+        mbarExpectTx(base + bW, kChunks * kWqkvKa + kChunks * kWprojKa + kBiasBytes);
+        for (int ka = 0; ka < kChunks; ++ka) {
+            for (int c = 0; c < kChunks; ++c) tmaLoad2d(base + kOffWqkv + ka * kWqkvKa + c * kWqkvChunk, &a.tmWqkv, base + bW, ka * 32, c * 96);
+            tmaLoad2d(base + kOffWproj + ka * kWprojKa, &a.tmWproj, base + bW, ka * 32, 0);
+        }
+        bulkLoad1d(base + kOffBias, a.relpos, kBiasBytes, base + bW);
+    }
+    const long long tiles = (a.windows + kWinTile - 1) / kWinTile;
+    const int first = blockIdx.x, step = gridDim.x;
+    const int nMine = first < tiles ? (int)((tiles - first + step - 1) / step) : 0;
+    const int G = nMine * kChunks;   // this CTA's chunk sequence: g = 3 k + c; heads j = 2 g, 2 g + 1
+    const WindowTokens tokens{a.h, a.w, a.shiftY, a.shiftX, a.nwx, a.nwy, a.windows, first, step};
+
+    if (warp < kMmaWarp) {
+        // ---- LayerNorm producers: thread = tile row, gathers its token through the window map ----
+        lnProducerLoop<kC, 1>(a.x, a.eps, tokens, base, kOffA, kOffGamma, kOffBeta, base + bAFull, base + bAEmpty, nMine);
+    } else if (warp == kMmaWarp) {
+        // ---- MMA issuer: whole warp converged, one elected lane issues ----
+        const uint32_t hi64 = descHi(512u, 4u), hi128 = descHi(1024u, 2u);
+        const uint32_t idQkv = instrDescF16(kRows, 96), idS = instrDescF16(kRows, 128), idPv = instrDescF16(kRows, kHD), idProj = instrDescF16(kRows, kC);
+        auto qkv = [&](int g) {   // D1 = LN rows x W'[chunk]^T; the caller has seen QKFull(g - 1): E1 of the previous chunk has drained D1
+            const int k = g / kChunks, c = g - k * kChunks;
+            if (c == 0) mbarWait(base + bAFull, (uint32_t)k & 1u);
+            tcFenceAfter();
+            if (electOne()) {
+#pragma unroll
+                for (int ka = 0; ka < kChunks; ++ka)
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks)
+                        ummaLoHi(tmemBase + tD1, descLo(base + kOffA + ka * kAChunk + ks * 32u), hi64, descLo(base + kOffWqkv + ka * kWqkvKa + c * kWqkvChunk + ks * 32u), hi64,
+                                 idQkv, (ka | ks) != 0 ? 1u : 0u);
+                tcCommit(base + bD1Full);
+                if (c == kChunks - 1) tcCommit(base + bAEmpty);   // the tile's normalised rows are no longer needed
+            }
+            __syncwarp();
+        };
+        auto scores = [&](int j) {   // S[j & 1] = Q_h K_h^T for head j & 1 of the pair in the Q / K buffers
+            const int b = j & 1, g = j >> 1;
+            mbarWait(base + bSEmpty + 8u * b, ((uint32_t)g & 1u) ^ 1u);
+            tcFenceAfter();
+            if (electOne()) {
+                ummaLoHi(tmemBase + tS + 128u * b, descLo(base + kOffQ + 32u * b), hi64, descLo(base + kOffK + 32u * b), hi64, idS, 0u);
+                tcCommit(base + bSFull + 8u * b);
+                if (b == 1) tcCommit(base + bQKEmpty);
+            }
+            __syncwarp();
+        };
+        auto pv = [&](int j) {   // O[g & 1][16 b .. +16] = P V_h
+            const int b = j & 1, g = j >> 1, ob = g & 1;
+            mbarWait(base + bPFull, (uint32_t)j & 1u);
+            if (b == 0) mbarWait(base + bOEmpty + 8u * ob, ((uint32_t)(g >> 1) & 1u) ^ 1u);
+            tcFenceAfter();
+            if (electOne()) {
+#pragma unroll
+                for (int kc = 0; kc < 2; ++kc)
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)
+                        ummaLoHi(tmemBase + tO + 32u * ob + 16u * b, descLo(base + kOffP + kc * kPChunk + ks * 32u), hi128,
+                                 descLo(base + kOffV + ob * kVBuf + kc * 4096u + b * 2048u + ks * 32u), hi128, idPv, (kc | ks) != 0 ? 1u : 0u);
+                tcCommit(base + bPEmpty);
+                if (b == 1) {
+                    tcCommit(base + bOFull + 8u * ob);
+                    tcCommit(base + bVEmpty + 8u * ob);
+                }
+            }
+            __syncwarp();
+        };
+        auto proj = [&](int g) {   // D2 += Oc x Wproj[:, chunk]^T
+            const int k = g / kChunks, c = g - k * kChunks;
+            mbarWait(base + bOcFull, (uint32_t)g & 1u);
+            if (c == 0) mbarWait(base + bD2Empty, ((uint32_t)k & 1u) ^ 1u);
+            tcFenceAfter();
+            if (electOne()) {
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks)
+                    ummaLoHi(tmemBase + tD2, descLo(base + kOffOc + ks * 32u), hi64, descLo(base + kOffWproj + c * kWprojKa + ks * 32u), hi64, idProj, (c | ks) != 0 ? 1u : 0u);
+                tcCommit(base + bOcEmpty);
+                if (c == kChunks - 1) tcCommit(base + bD2Full);
+            }
+            __syncwarp();
+        };
+        mbarWait(base + bW, 0);
+        if (G > 0) {
+            qkv(0);
+            mbarWait(base + bQKFull, 0);
+            scores(0);
+            scores(1);
+            if (1 < G) qkv(1);
+        }
+        for (int g = 0; g <= G; ++g) {   // the order of the epilogue warps' iteration g
+            if (g < G) pv(2 * g);
+            if (g + 1 < G) {
+                mbarWait(base + bQKFull, (uint32_t)(g + 1) & 1u);
+                scores(2 * g + 2);
+                if (g + 2 < G) qkv(g + 2);
+            }
+            if (g >= 1) proj(g - 1);
+            if (g + 1 < G) scores(2 * g + 3);
+            if (g < G) pv(2 * g + 1);
+        }
+    } else {
+        // ---- epilogue / softmax warps ----
+        pdlWait();  // the residual rows come from the preceding kernel
+        const int quarter = warp & 3;                // TMEM lane quarter this warp may read: its index in the CTA modulo 4
+        const int sub = (warp - kEpiWarp0) >> 2;     // the two warps of a quarter
+        const int row = quarter * 32 + lane;
+        const uint32_t taddrLane = tmemBase + ((uint32_t)(quarter * 32) << 16);
+        const bool rowValid = row < kWinTile * kNT;
+        const int rw = rowValid ? row / kNT : 0, rp = rowValid ? row - rw * kNT : 0;
+        const int kidx = kKeyStride * rw + rp;       // this row's key slot
+        // softmax passes: quarters 0 / 3 hold rows of one window (the two warps alternate heads), quarters 1 / 2 straddle two windows
+        // (each warp takes one of them, every head)
+        const bool single = quarter == 0 || quarter == 3;
+        const int passWin = quarter == 0 ? 0 : quarter == 3 ? 2 : quarter - 1 + sub;
+        const bool active = rowValid && rw == passWin;
+        const int pq = active ? rp : 0;
+        const uint32_t swQ = ((uint32_t)row >> 1) & 3u, swKey = ((uint32_t)kidx >> 1) & 3u, swP = (uint32_t)row & 7u;
+        uint32_t r[32], r2[32];
+
+        auto e1 = [&](int g) {   // D1 (+ bias) -> Q / K / V^T operands
+            const int c = g % kChunks, vb = g & 1;
+            mbarWait(base + bD1Full, (uint32_t)g & 1u);
+            tcFenceAfter();
+            tmemLd32(taddrLane + tD1 + 32u * sub, r);            // sub 0: Q columns, sub 1: K columns
+            tmemLd16(taddrLane + tD1 + 64u + 16u * sub, r2);     // V dims 16 sub .. +16
+            tmemLdWait();
+            mbarWait(base + bQKEmpty, ((uint32_t)g & 1u) ^ 1u);            // both S MMAs of the previous chunk have read Q / K
+            mbarWait(base + bVEmpty + 8u * vb, ((uint32_t)(g >> 1) & 1u) ^ 1u);   // both PV MMAs of chunk g - 2 have read this V buffer
+            const uint32_t bOff = base + kOffBqkv + 4u * (uint32_t)(c * 96);
+            if (sub == 0 || rowValid) {
+                const uint32_t dst = sub == 0 ? base + kOffQ + (uint32_t)row * 64u : base + kOffK + (uint32_t)kidx * 64u;
+                const uint32_t sw = sub == 0 ? swQ : swKey;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float bias[8];
+                    loadF8(bOff + 4u * (uint32_t)(32 * sub + 8 * q), bias);
+                    uint4 o;
+                    o.x = packH2(__uint_as_float(r[8 * q]) + bias[0], __uint_as_float(r[8 * q + 1]) + bias[1]);
+                    o.y = packH2(__uint_as_float(r[8 * q + 2]) + bias[2], __uint_as_float(r[8 * q + 3]) + bias[3]);
+                    o.z = packH2(__uint_as_float(r[8 * q + 4]) + bias[4], __uint_as_float(r[8 * q + 5]) + bias[5]);
+                    o.w = packH2(__uint_as_float(r[8 * q + 6]) + bias[6], __uint_as_float(r[8 * q + 7]) + bias[7]);
+                    stsV4(dst + (((uint32_t)q ^ sw) << 4), o);
+                }
+            }
+            if (rowValid) {
+                // V^T[dim][key]: 2-byte stores; the lanes of a warp hold consecutive keys, so a store instruction covers 64 contiguous bytes
+                const uint32_t vDst = base + kOffV + (uint32_t)vb * kVBuf + ((uint32_t)kidx >> 6) * 4096u + ((uint32_t)kidx & 7u) * 2u;
+                const uint32_t kc16 = ((uint32_t)kidx & 63u) >> 3;
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    float bias[8];
+                    loadF8(bOff + 4u * (uint32_t)(64 + 16 * sub + 8 * q), bias);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const uint32_t dd = (uint32_t)(16 * sub + 8 * q + i);
+                        stsU16(vDst + dd * 128u + ((kc16 ^ (dd & 7u)) << 4), __half_as_ushort(__float2half_rn(__uint_as_float(r2[8 * q + i]) + bias[i])));
+                    }
+                }
+            }
+            fenceProxyAsync();
+            tcFenceBefore();
+            __syncwarp();
+            if (lane == 0) mbarArrive(base + bQKFull);
+        };
+
+        // keys a query may attend to in a shifted block (torchvision's attn_mask: tokens of the last window row / column that were rolled
+        // in from the opposite image edge form their own regions); bit j = key position j of the pass's window
+        const bool shifted = (a.shiftY | a.shiftX) > 0;
+        uint32_t allowLo = 0xffffffffu, allowHi = 0xfu;
+        auto setMask = [&](long long tile) {
+            allowLo = 0xffffffffu;
+            allowHi = 0xfu;
+            if (shifted) {
+                long long win = tile * kWinTile + passWin;
+                const int wx = (int)(win % a.nwx);
+                win /= a.nwx;
+                const int wy = (int)(win % a.nwy);
+                constexpr unsigned long long yLo = 0x3ffffull;        // key rows 0..2
+                constexpr unsigned long long xLo = 0x1c71c71c7ull;    // key columns 0..2 of every row
+                unsigned long long m = 0xfffffffffull;
+                if (a.shiftY > 0 && wy == a.nwy - 1) m &= (pq / kWin < kWin / 2) ? yLo : ~yLo;
+                if (a.shiftX > 0 && wx == a.nwx - 1) m &= (pq % kWin < kWin / 2) ? xLo : ~xLo;
+                allowLo = (uint32_t)m;
+                allowHi = (uint32_t)(m >> 32) & 0xfu;
+            }
+        };
+
+        auto sm = [&](int j) {   // softmax of head j for this warp's pass -> P
+            const int b = j & 1, g = j >> 1;
+            const bool mine = !single || b == sub;
+            mbarWait(base + bSFull + 8u * b, (uint32_t)g & 1u);
+            tcFenceAfter();
+            uint32_t s2[8];
+            bool waited = false;
+            if (mine) {
+                tmemLd32(taddrLane + tS + 128u * b + (uint32_t)(kKeyStride * passWin), r);
+                tmemLd8(taddrLane + tS + 128u * b + (uint32_t)(kKeyStride * passWin) + 32u, s2);
+                tmemLdWait();
+            }
+            tcFenceBefore();
+            __syncwarp();
+            if (lane == 0) mbarArrive(base + bSEmpty + 8u * b);   // the scores are in registers: the next head of this parity may overwrite them
+            if (mine) {
+                const int head = 2 * (g % kChunks) + b;
+                const uint32_t bRow = base + kOffBias + (uint32_t)head * kBiasHead + (uint32_t)pq * (kBiasPitch * 4u);
+                float v[kNT];
+#pragma unroll
+                for (int q = 0; q < kNT / 4; ++q) {
+                    const uint4 bb = ldsV4(bRow + 16u * q);
+                    const uint32_t* src = q < 8 ? &r[4 * q] : &s2[4 * q - 32];
+                    v[4 * q] = __uint_as_float(src[0]) + __uint_as_float(bb.x);
+                    v[4 * q + 1] = __uint_as_float(src[1]) + __uint_as_float(bb.y);
+                    v[4 * q + 2] = __uint_as_float(src[2]) + __uint_as_float(bb.z);
+                    v[4 * q + 3] = __uint_as_float(src[3]) + __uint_as_float(bb.w);
+                }
+                if (shifted) {
+#pragma unroll
+                    for (int i = 0; i < kNT; ++i) {
+                        const uint32_t bit = i < 32 ? (allowLo >> i) & 1u : (allowHi >> (i - 32)) & 1u;
+                        v[i] = bit ? v[i] : v[i] - 144.26950408889634f;   // -100 in natural-log units
+                    }
+                }
+                float mx = v[0];
+#pragma unroll
+                for (int i = 1; i < kNT; ++i) mx = fmaxf(mx, v[i]);
+                float den = 0.f;
+#pragma unroll
+                for (int i = 0; i < kNT; ++i) {
+                    v[i] = ex2f(v[i] - mx);
+                    den += v[i];
+                }
+                const float inv = __fdividef(1.f, den);
+                mbarWait(base + bPEmpty, ((uint32_t)j & 1u) ^ 1u);   // PV of the previous head has read P
+                waited = true;
+                if (active) {
+                    const uint32_t pRow = base + kOffP + (uint32_t)row * 128u;
+#pragma unroll
+                    for (int q = 0; q < 5; ++q) {
+                        uint4 o;
+                        o.x = packH2(v[8 * q] * inv, v[8 * q + 1] * inv);
+                        o.y = packH2(v[8 * q + 2] * inv, v[8 * q + 3] * inv);
+                        if (q < 4) {
+                            o.z = packH2(v[8 * q + 4] * inv, v[8 * q + 5] * inv);
+                            o.w = packH2(v[8 * q + 6] * inv, v[8 * q + 7] * inv);
+                        } else {
+                            o.z = 0u;   // keys 36..39 of the window's slot: padding
+                            o.w = 0u;
+                        }
+                        const uint32_t ci = (uint32_t)(5 * passWin + q);
+                        stsV4(pRow + (ci >> 3) * kPChunk + (((ci & 7u) ^ swP) << 4), o);
+                    }
+                }
+            }
+            // a warp that sat this head out must not arrive early: its arrival would be counted in the phase of the PREVIOUS head while
+            // slower warps are still writing that head's probabilities
+            if (!waited) mbarWait(base + bPEmpty, ((uint32_t)j & 1u) ^ 1u);
+            fenceProxyAsync();
+            __syncwarp();
+            if (lane == 0) mbarArrive(base + bPFull);
+        };
+
+        auto e2 = [&](int g) {   // O -> fp16 -> Oc (A operand of proj)
+            const int ob = g & 1;
+            mbarWait(base + bOFull + 8u * ob, (uint32_t)(g >> 1) & 1u);
+            tcFenceAfter();
+            tmemLd16(taddrLane + tO + 32u * ob + 16u * sub, r2);
+            tmemLdWait();
+            tcFenceBefore();
+            __syncwarp();
+            if (lane == 0) mbarArrive(base + bOEmpty + 8u * ob);
+            mbarWait(base + bOcEmpty, ((uint32_t)g & 1u) ^ 1u);   // proj of the previous chunk has read Oc
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                uint4 o;
+                o.x = packH2(__uint_as_float(r2[8 * q]), __uint_as_float(r2[8 * q + 1]));
+                o.y = packH2(__uint_as_float(r2[8 * q + 2]), __uint_as_float(r2[8 * q + 3]));
+                o.z = packH2(__uint_as_float(r2[8 * q + 4]), __uint_as_float(r2[8 * q + 5]));
+                o.w = packH2(__uint_as_float(r2[8 * q + 6]), __uint_as_float(r2[8 * q + 7]));
+                stsV4(base + kOffOc + (uint32_t)row * 64u + (((uint32_t)(2 * sub + q) ^ swQ) << 4), o);
+            }
+            fenceProxyAsync();
+            __syncwarp();
+            if (lane == 0) mbarArrive(base + bOcFull);
+        };
+
+        uint4 res[6];
+        long long resTok = -1;
+        auto prefetchResidual = [&](int k) {   // issued one softmax pass ahead of its use
+            resTok = tokens(k, row);
+#pragma unroll
+            for (int q = 0; q < 6; ++q) res[q] = make_uint4(0, 0, 0, 0);
+            if (resTok >= 0) {
+                const uint4* xr = reinterpret_cast<const uint4*>(a.x + resTok * kC + sub * (kC / 2));
+#pragma unroll
+                for (int q = 0; q < 6; ++q) res[q] = xr[q];
+            }
+        };
+        auto e3 = [&](int k) {   // x += D2 + bproj
+            const int col0 = sub * (kC / 2);
+            mbarWait(base + bD2Full, (uint32_t)k & 1u);
+            tcFenceAfter();
+            tmemLd32(taddrLane + tD2 + (uint32_t)col0, r);
+            tmemLd16(taddrLane + tD2 + (uint32_t)col0 + 32u, r2);
+            tmemLdWait();
+            tcFenceBefore();
+            __syncwarp();
+            if (lane == 0) mbarArrive(base + bD2Empty);
+            if (resTok >= 0) {
+                uint4* xrow = reinterpret_cast<uint4*>(a.x + resTok * kC + col0);
+#pragma unroll
+                for (int q = 0; q < 6; ++q) {
+                    float bias[8], rv[8];
+                    loadF8(base + kOffBproj + 4u * (uint32_t)(col0 + 8 * q), bias);
+                    unpack8(res[q], rv);
+                    uint4 o;
+                    __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float a0 = __uint_as_float(q < 4 ? r[8 * q + 2 * i] : r2[8 * (q - 4) + 2 * i]);
+                        const float a1 = __uint_as_float(q < 4 ? r[8 * q + 2 * i + 1] : r2[8 * (q - 4) + 2 * i + 1]);
+                        oh[i] = __floats2half2_rn(a0 + bias[2 * i] + rv[2 * i], a1 + bias[2 * i + 1] + rv[2 * i + 1]);
+                    }
+                    xrow[q] = o;
+                }
+            }
+        };
+
+        mbarWait(base + bW, 0);   // bias tables
+        if (G > 0) e1(0);
+        for (int g = 0; g <= G; ++g) {
+            if (g < G) {
+                if (g % kChunks == 0) setMask((long long)first + (long long)(g / kChunks) * step);
+                sm(2 * g);
+            }
+            if (g + 1 < G) e1(g + 1);
+            if (g >= 1) e2(g - 1);
+            const bool fin = g >= 1 && (g - 1) % kChunks == kChunks - 1;   // chunk g - 1 closed a tile
+            if (fin) prefetchResidual((g - 1) / kChunks);
+            if (g < G) sm(2 * g + 1);
+            if (fin) e3((g - 1) / kChunks);
+        }
+    }
+
+    tcFenceBefore();
+    __syncthreads();
+    if (warp == kMmaWarp) {
+        tcFenceAfter();
+        tmemDealloc(tmemBase, kTmemCols);
+    }
+}
+
+}  // namespace
+
+struct SwinAttnPlan {
+    AttnArgs args;
+    int n = 0;
+};
+
+bool swinAttnSupported(int c, int heads, int window, int h, int w) {
+    return c == kC && heads == kHeads && window == kWin && h > 0 && w > 0 && h % kWin == 0 && w % kWin == 0;
+}
+
+// Host-side operand preparation (done once per block at plan time):
+//   wOut [3C][C] fp16 bits: the rows of Wqkv regrouped per 32-channel chunk (q32 | k32 | v32), q rows multiplied by d^-1/2 log2(e);
+//   bOut [3C]: the bias in the same order and scale;  relOut [heads][36][44]: relative-position bias times log2(e), rows padded.
+void swinAttnPrepare(const uint16_t* wqkv, const float* bqkv, const float* relpos, int c, int heads, std::vector<uint16_t>& wOut, std::vector<float>& bOut,
+                     std::vector<float>& relOut) {
+    if (c != kC || heads != kHeads) throw Error("swin attention: unsupported width");
+    const float log2e = 1.4426950408889634f;
+    const float qScale = log2e / std::sqrt((float)(c / heads));
+    wOut.assign((size_t)3 * c * c, 0);
+    bOut.assign((size_t)3 * c, 0.f);
+    for (int ch = 0; ch < c / 32; ++ch)
+        for (int t = 0; t < 3; ++t)
+            for (int i = 0; i < 32; ++i) {
+                const int src = t * c + 32 * ch + i, dst = ch * 96 + t * 32 + i;
+                const float s = t == 0 ? qScale : 1.f;
+                for (int k = 0; k < c; ++k) {
+                    __half_raw in;
+                    in.x = wqkv[(size_t)src * c + k];
+                    const __half_raw o = __float2half_rn(__half2float(__half(in)) * s);
+                    wOut[(size_t)dst * c + k] = o.x;
+                }
+                bOut[dst] = bqkv[src] * s;
+            }
+    relOut.assign((size_t)heads * kNT * kBiasPitch, 0.f);
+    for (int hd = 0; hd < heads; ++hd)
+        for (int p = 0; p < kNT; ++p)
+            for (int j = 0; j < kNT; ++j) relOut[((size_t)hd * kNT + p) * kBiasPitch + j] = relpos[((size_t)hd * kNT + p) * kNT + j] * log2e;
+}
+
+// All pointers are device memory: wqkvR / bqkvR / relposR as produced by swinAttnPrepare, wproj [C][C] fp16 K-major.
+SwinAttnPlan* swinAttnCreatePlan(__half* x, int n, int h, int w, int c, int heads, int window, int shift, const float* gamma, const float* beta, float eps,
+                                 const __half* wqkvR, const float* bqkvR, const __half* wproj, const float* bproj, const float* relposR) {
+    if (!swinAttnSupported(c, heads, window, h, w)) throw Error("swin attention: unsupported geometry");
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(wqkvR) | reinterpret_cast<uintptr_t>(wproj) | reinterpret_cast<uintptr_t>(relposR)) & 15)
+        throw Error("swin attention: operands must be 16-byte aligned");
+    SwinAttnPlan* plan = new SwinAttnPlan{};
+    try {
+        encodeMatrixMap2d(&plan->args.tmWqkv, wqkvR, c, 3 * c, 32, 96, false);
+        encodeMatrixMap2d(&plan->args.tmWproj, wproj, c, c, 32, c, false);
+    } catch (...) {
+        delete plan;
+        throw;
+    }
+    AttnArgs& a = plan->args;
+    a.x = x;
+    a.bqkv = bqkvR;
+    a.bproj = bproj;
+    a.gamma = gamma;
+    a.beta = beta;
+    a.relpos = relposR;
+    a.eps = eps;
+    a.h = h;
+    a.w = w;
+    // torchvision drops the shift in a dimension the window covers (shifted_window_attention)
+    a.shiftY = window >= h ? 0 : shift;
+    a.shiftX = window >= w ? 0 : shift;
+    a.nwx = w / window;
+    a.nwy = h / window;
+    a.windows = 0;
+    plan->n = n;
+    return plan;
+}
+
+void swinAttnDestroyPlan(SwinAttnPlan* plan) { delete plan; }
+
+const char* swinAttnDescribe(const SwinAttnPlan* plan, char* buf, int cap) {
+    std::snprintf(buf, cap, "swin-attn fused LN+QKV+window-attention+proj+residual (tcgen05) c=%d heads=%d window=%d shift=%d rows=%d windows/tile=%d smem=%u", kC, kHeads,
+                  kWin, plan->args.shiftY > plan->args.shiftX ? plan->args.shiftY : plan->args.shiftX, kRows, kWinTile, kAttnSmem);
+    return buf;
+}
+
+void swinAttnLaunch(const SwinAttnPlan* plan, cudaStream_t s, int nImages) {
+    static bool attrSet[64] = {};
+    static int sms[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (!attrSet[dev]) {
+        cudaFuncSetAttribute(swin_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
+        cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+        if (sms[dev] <= 0) sms[dev] = 148;
+        attrSet[dev] = true;
+    }
+    if (nImages <= 0) return;
+    AttnArgs a = plan->args;
+    a.windows = (long long)nImages * a.nwx * a.nwy;
+    const long long tiles = (a.windows + kWinTile - 1) / kWinTile;
+    const dim3 grid((unsigned)(tiles < sms[dev] ? tiles : sms[dev]));
+    const cudaError_t e = launchPdl(swin_attn_kernel, grid, dim3(kAttnThreads), kAttnSmem, s, a);
+    if (e != cudaSuccess) throw Error(std::string("swin attention launch: ") + cudaGetErrorString(e));
+}
+
+}  // namespace w2x

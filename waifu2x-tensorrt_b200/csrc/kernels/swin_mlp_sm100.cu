@@ -23,14 +23,15 @@
 #include "conv_params.h"
 #include "launch.h"
 #include "sm100_common.cuh"
+#include "swin_token.cuh"
 
 namespace w2x {
 using namespace sm100;
+using namespace swintok;
 namespace {
 
 constexpr int kC = 96;             // token width
 constexpr int kHid = 192;          // hidden width (mlp_ratio 2)
-constexpr int kRows = 128;         // tokens per tile = UMMA M
 constexpr int kProdWarps = 4;
 constexpr int kMmaWarp = 4;
 constexpr int kEpiWarp0 = 5;
@@ -43,7 +44,6 @@ constexpr uint32_t kBarW = 0, kBarAFull = 8, kBarAEmpty = 24, kBarD1Full = 40, k
 constexpr uint32_t kOffB1 = 256, kOffB2 = kOffB1 + kHid * 4, kOffGamma = kOffB2 + kC * 4, kOffBeta = kOffGamma + kC * 4;
 constexpr uint32_t kW1Chunk = kHid * 64;          // [192 rows][32 k] fp16, SWIZZLE_64B
 constexpr uint32_t kW2Chunk = kC * 128;           // [96 rows][64 k] fp16, SWIZZLE_128B
-constexpr uint32_t kAChunk = kRows * 64;          // [128 rows][32 k]
 constexpr uint32_t kHChunk = kRows * 128;         // [128 rows][64 k]
 constexpr uint32_t kOffW1 = 4096;
 constexpr uint32_t kOffW2 = kOffW1 + 3 * kW1Chunk;
@@ -68,137 +68,16 @@ struct MlpArgs {
     __half* out;               // LN + Linear kernel only: [tokens][3C]
 };
 
-__device__ __forceinline__ void stsF32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
-__device__ __forceinline__ void unpack8(const uint4& raw, float (&v)[8]) {
-    const __half2* h = reinterpret_cast<const __half2*>(&raw);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float2 f = __half22float2(h[i]);
-        v[2 * i] = f.x;
-        v[2 * i + 1] = f.y;
-    }
-}
-__device__ __forceinline__ void loadF8(uint32_t addr, float (&v)[8]) {
-    const uint4 a = ldsV4(addr), b = ldsV4(addr + 16u);
-    v[0] = __uint_as_float(a.x); v[1] = __uint_as_float(a.y); v[2] = __uint_as_float(a.z); v[3] = __uint_as_float(a.w);
-    v[4] = __uint_as_float(b.x); v[5] = __uint_as_float(b.y); v[6] = __uint_as_float(b.z); v[7] = __uint_as_float(b.w);
-}
-
-// LayerNorm producer warps (groups of 4 warps, one token row per thread): rows of tile k -> fp16 A-operand rows (SWIZZLE_64B,
-// 32-channel K chunks of kAChunk bytes) in buffer k % kABufs at offA; barAFull / barAEmpty are the shared-memory addresses of buffer
-// 0's barriers.  kFirst / kStep let several groups of four warps share the tiles (measured: a second group does not pay, the 96
-// registers per thread it leaves cost more than the overlap gains).
-template <int C, int kABufs>
-__device__ __forceinline__ void lnProducerLoop(const MlpArgs& a, uint32_t base, uint32_t offA, uint32_t offGamma, uint32_t offBeta, uint32_t barAFull, uint32_t barAEmpty,
-                                               int first, int step, int nMine, int kFirst = 0, int kStep = 1) {
-    const int lane = threadIdx.x & 31;
-    pdlWait();  // x is written by the preceding kernel
-    const int row = threadIdx.x & 127;
-    const uint32_t sw = (uint32_t)(row >> 1) & 3u;
-    // normalise 12 pieces (96 channels) held in registers and store them as A-operand rows; J0 = index of the first piece
-    auto emit = [&](const uint4 (&raw)[12], int J0, float mean, float rstd, bool valid, uint32_t rowAddr) {
-#pragma unroll
-        for (int j = 0; j < 12; ++j) {
-            const int J = J0 + j;
-            float v[8], gm[8], bt[8];
-            unpack8(raw[j], v);
-            loadF8(base + offGamma + 32u * J, gm);
-            loadF8(base + offBeta + 32u * J, bt);
-            uint4 o;
-            __half2* oh = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-                oh[i] = __floats2half2_rn((v[2 * i] - mean) * rstd * gm[2 * i] + bt[2 * i], (v[2 * i + 1] - mean) * rstd * gm[2 * i + 1] + bt[2 * i + 1]);
-            if (!valid) o = make_uint4(0, 0, 0, 0);
-            stsV4(rowAddr + (uint32_t)(J >> 2) * kAChunk + ((((uint32_t)J & 3u) ^ sw) << 4), o);
-        }
-    };
-    for (int k = kFirst; k < nMine; k += kStep) {
+// tiles are consecutive runs of 128 tokens, dealt round-robin to the CTAs
+struct LinearTokens {
+    long long tokens;
+    int first, step;
+    __device__ __forceinline__ long long operator()(int k, int row) const {
         const long long g = ((long long)first + (long long)k * step) * kRows + row;
-        const bool valid = g < a.tokens;
-        const uint4* src = reinterpret_cast<const uint4*>(a.x + g * C);
-        const int buf = kABufs == 2 ? (k & 1) : 0;
-        const uint32_t use = kABufs == 2 ? (uint32_t)(k >> 1) : (uint32_t)k;
-        const uint32_t rowAddr = base + offA + (uint32_t)buf * (uint32_t)(C / 32) * kAChunk + (uint32_t)row * 64u;
-        uint4 raw[12];
-        if constexpr (C == 96) {
-            // the whole row stays in registers: two-pass statistics
-#pragma unroll
-            for (int j = 0; j < 12; ++j) raw[j] = make_uint4(0, 0, 0, 0);
-            if (valid) {
-#pragma unroll
-                for (int j = 0; j < 12; ++j) raw[j] = src[j];
-            }
-            float ps[4] = {0.f, 0.f, 0.f, 0.f};   // four partial sums: the reductions are not one 96-long dependent chain
-#pragma unroll
-            for (int j = 0; j < 12; ++j) {
-                float v[8];
-                unpack8(raw[j], v);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) ps[i & 3] += v[i];
-            }
-            const float mean = ((ps[0] + ps[1]) + (ps[2] + ps[3])) * (1.f / C);
-            float pq[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int j = 0; j < 12; ++j) {
-                float v[8];
-                unpack8(raw[j], v);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) { const float d = v[i] - mean; pq[i & 3] = fmaf(d, d, pq[i & 3]); }
-            }
-            const float rstd = rsqrtf(((pq[0] + pq[1]) + (pq[2] + pq[3])) * (1.f / C) + a.eps);
-            mbarWait(barAEmpty + 8u * buf, (use & 1u) ^ 1u);   // the last fc1 chunk that read this buffer has completed
-            emit(raw, 0, mean, rstd, valid, rowAddr);
-        } else {
-            // 384-byte rows do not fit the register budget next to the epilogue warps: statistics in one streaming pass (sums of
-            // x - x0 and (x - x0)^2 with x0 = the row's first element, so a large common offset cannot cancel), then the row
-            // is read again (an L2 hit) 96 channels at a time for the normalisation
-            float x0 = 0.f, p1[4] = {0.f, 0.f, 0.f, 0.f}, p2[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int h = 0; h < (C / 8) / 12; ++h) {
-#pragma unroll
-                for (int j = 0; j < 12; ++j) raw[j] = make_uint4(0, 0, 0, 0);
-                if (valid) {
-#pragma unroll
-                    for (int j = 0; j < 12; ++j) raw[j] = src[12 * h + j];
-                }
-                if (h == 0) x0 = __low2float(*reinterpret_cast<const __half2*>(&raw[0]));
-#pragma unroll
-                for (int j = 0; j < 12; ++j) {
-                    float v[8];
-                    unpack8(raw[j], v);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) { const float d = v[i] - x0; p1[i & 3] += d; p2[i & 3] = fmaf(d, d, p2[i & 3]); }
-                }
-            }
-            const float s1 = (p1[0] + p1[1]) + (p1[2] + p1[3]), s2 = (p2[0] + p2[1]) + (p2[2] + p2[3]);
-            const float m1 = s1 * (1.f / C);
-            const float mean = x0 + m1;
-            const float rstd = rsqrtf(fmaxf(s2 * (1.f / C) - m1 * m1, 0.f) + a.eps);
-            if (valid) {
-#pragma unroll
-                for (int j = 0; j < 12; ++j) raw[j] = src[j];   // in flight while the buffer is still being read by fc1
-            }
-            mbarWait(barAEmpty + 8u * buf, (use & 1u) ^ 1u);
-#pragma unroll
-            for (int h = 0; h < (C / 8) / 12; ++h) {
-                uint4 nxt[12];
-                if (h + 1 < (C / 8) / 12 && valid) {
-#pragma unroll
-                    for (int j = 0; j < 12; ++j) nxt[j] = src[12 * (h + 1) + j];
-                }
-                emit(raw, 12 * h, mean, rstd, valid, rowAddr);
-                if (h + 1 < (C / 8) / 12) {
-#pragma unroll
-                    for (int j = 0; j < 12; ++j) raw[j] = nxt[j];
-                }
-            }
-        }
-        fenceProxyAsync();
-        __syncwarp();
-        if (lane == 0) mbarArrive(barAFull + 8u * buf);
+        return g < tokens ? g : -1;
     }
-}
+};
+__device__ __forceinline__ LinearTokens linearTokens(long long tokens, int first, int step) { return LinearTokens{tokens, first, step}; }
 
 __global__ void __launch_bounds__(kMlpThreads, 1) swin_mlp_kernel(const __grid_constant__ MlpArgs a) {
     extern __shared__ uint8_t smemRaw[];
@@ -249,7 +128,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) swin_mlp_kernel(const __grid_c
 
     if (warp < kProdWarps) {
         // ---- LayerNorm producers: thread = token row ----
-        lnProducerLoop<kC, 2>(a, base, kOffA, kOffGamma, kOffBeta, base + kBarAFull, base + kBarAEmpty, first, step, nMine);
+        lnProducerLoop<kC, 2>(a.x, a.eps, linearTokens(a.tokens, first, step), base, kOffA, kOffGamma, kOffBeta, base + kBarAFull, base + kBarAEmpty, nMine);
     } else if (warp == kMmaWarp) {
         // ---- MMA issuer: whole warp converged, one elected lane issues ----
         const uint32_t hi64 = descHi(512u, 4u), hi128 = descHi(1024u, 2u);
@@ -498,7 +377,7 @@ __global__ void __launch_bounds__(StreamCfg<C>::kThreadsS, 1) swin_mlp_stream_ke
         }
     } else if (warp < Cfg::kProd) {
         // ---- LayerNorm producers: one token row per thread ----
-        lnProducerLoop<C, Cfg::kABufs>(a, base, Cfg::kOffAS, Cfg::kGamma, Cfg::kBeta, base + sBarAFull, base + sBarAEmpty, first, step, nMine);
+        lnProducerLoop<C, Cfg::kABufs>(a.x, a.eps, linearTokens(a.tokens, first, step), base, Cfg::kOffAS, Cfg::kGamma, Cfg::kBeta, base + sBarAFull, base + sBarAEmpty, nMine);
     } else if (warp == Cfg::kMmaW) {
         const uint32_t hi64 = descHi(512u, 4u), hi128 = descHi(1024u, 2u);
         const uint32_t idesc1 = instrDescF16(kRows, Cfg::kChunk), idesc2 = instrDescF16(kRows, C);
@@ -738,7 +617,7 @@ __global__ void __launch_bounds__(LinCfg<C>::kThreadsL, 1) swin_lnlinear_kernel(
             }
         }
     } else if (warp < Cfg::kProd) {
-        lnProducerLoop<C, 2>(a, base, Cfg::kOffAS, Cfg::kGamma, Cfg::kBeta, base + lBarAFull, base + lBarAEmpty, first, step, nMine);
+        lnProducerLoop<C, 2>(a.x, a.eps, linearTokens(a.tokens, first, step), base, Cfg::kOffAS, Cfg::kGamma, Cfg::kBeta, base + lBarAFull, base + lBarAEmpty, nMine);
     } else if (warp == Cfg::kMmaW) {
         const uint32_t hi64 = descHi(512u, 4u);
         const uint32_t idesc = instrDescF16(kRows, Cfg::kNC);

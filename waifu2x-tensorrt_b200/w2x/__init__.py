@@ -137,6 +137,8 @@ _SIGNATURES = {
     "w2x_run_conv_layer": (C.c_int, [C.c_int] * 8 + [C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.c_void_p, C.c_void_p]),
     "w2x_run_swin_lnlinear": (C.c_int, [C.c_int, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_int, C.POINTER(C.c_float)]),
+    "w2x_run_swin_attn": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_float)]),
     "w2x_run_swin_mlp": (C.c_int, [C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_int, C.POINTER(C.c_float)]),
     "w2x_select_engine": (C.c_int, [C.c_char_p, C.POINTER(_RenderConfig), C.c_char_p, C.c_char_p, C.c_size_t]),
@@ -316,6 +318,24 @@ def run_swin_mlp(x: np.ndarray, gamma: np.ndarray, beta: np.ndarray, eps: float,
                                 int(reps), C.byref(ms))
     if not ok:
         raise RuntimeError("w2x_run_swin_mlp failed")
+    return out, (ms.value if reps > 0 else None)
+
+
+def run_swin_attn(x: np.ndarray, gamma: np.ndarray, beta: np.ndarray, eps: float, wqkv: np.ndarray, bqkv: np.ndarray, wproj: np.ndarray, bproj: np.ndarray,
+                  relpos: np.ndarray, heads: int = 6, shift: int = 0, reps: int = 0, device: int = 0):
+    """x + proj(window attention(LayerNorm(x))) through the fused attention kernel (include/w2x_dev.h: w2x_run_swin_attn).  x: fp16
+    [n][h][w][c]; wqkv [3c][c], wproj [c][c] fp16; relpos [heads][36][36] f32.  Returns (result fp16 [n][h][w][c], ms per launch or None)."""
+    out = np.ascontiguousarray(x, dtype=np.float16).copy()
+    n, h, w, c = out.shape
+    f16 = [np.ascontiguousarray(a, dtype=np.float16) for a in (wqkv, wproj)]
+    f32 = [np.ascontiguousarray(a, dtype=np.float32) for a in (gamma, beta, bqkv, bproj, relpos)]
+    if f16[0].shape != (3 * c, c) or f16[1].shape != (c, c) or f32[4].shape != (heads, 36, 36):
+        raise ValueError("run_swin_attn: operand shapes")
+    ms = C.c_float(0.0)
+    ok = lib().w2x_run_swin_attn(device, n, h, w, c, int(heads), int(shift), _ptr(out), _ptr(f32[0]), _ptr(f32[1]), float(eps), _ptr(f16[0]), _ptr(f32[2]),
+                                 _ptr(f16[1]), _ptr(f32[3]), _ptr(f32[4]), int(reps), C.byref(ms))
+    if not ok:
+        raise RuntimeError("w2x_run_swin_attn failed")
     return out, (ms.value if reps > 0 else None)
 
 
