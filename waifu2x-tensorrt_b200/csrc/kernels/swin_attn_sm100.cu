@@ -19,10 +19,16 @@
 //   proj(c)  D2[128][C] += Oc . Wproj[:, 32 c .. +32]^T      2 x M128 N96 K16
 //   E3       D2 + bias + residual -> x (in place, scattered back to the tokens' positions)
 //
-// Roles: warps 0-3 LayerNorm producers (swin_token.cuh, one token row per thread), warp 4 MMA issuer (one elected lane), warps 5-12
-// epilogue / softmax (two warps per TMEM lane quarter).  The epilogue warps run SM(2g), E1(g+1), E2(g-1), SM(2g+1), E3 in that order
-// over the CTA's chunk sequence g, so every tensor-core hand-off is covered by CUDA-core work of a neighbouring chunk; the MMA warp
-// issues in the matching order.  All weights (Wqkv' 54 KB, Wproj 18 KB) and the bias tables (6 heads x [36][44] fp32) stay resident.
+// Roles (16 warps, four per scheduler; a warp reads the TMEM lane quarter given by its index modulo 4):
+//   warps 0-3    LayerNorm producers (swin_token.cuh, one token row per thread)
+//   warps 4-7    row warps: E1, E2 and E3 for the 32 rows of their quarter
+//   warp  12     issuer A: QKV and proj MMAs          warp 15   issuer B: S and PV MMAs (one elected lane each)
+//   warps 8-11, 13, 14   softmax: quarters 0 / 3 hold rows of one window (one warp), quarters 1 / 2 straddle two windows (one warp per
+//                window); every softmax warp runs one pass per head
+// Each hand-off (tcgen05.commit -> mbarrier -> waiting warp) then sits between DIFFERENT warps, so the row warps convert chunk g + 1 and
+// the issuers queue its MMAs while the softmax warps are still on chunk g.  (The first version ran SM, E1, E2, E3 in sequence on eight
+// epilogue warps: 0.18 ms per level-1 block, every warp latency-bound on its own chain of waits; profiles/r02_ncu_swin_attn_v1.txt.)
+// All weights (Wqkv' 54 KB, Wproj 18 KB) and the bias tables (6 heads x [36][44] fp32) stay resident.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -50,8 +56,8 @@ constexpr int kWinTile = 3;            // windows per tile
 constexpr int kKeyStride = 40;         // key index of window w, position p: 40 w + p (a window starts at a 16-byte chunk of a P row)
 constexpr int kBiasPitch = 44;         // floats per bias-table row: 16-byte loads of 8 consecutive rows hit distinct banks
 constexpr uint32_t kBiasHead = kNT * kBiasPitch * 4;
-constexpr int kMmaWarp = 4, kEpiWarp0 = 5, kEpiWarps = 8;
-constexpr int kAttnThreads = 32 * (kEpiWarp0 + kEpiWarps);   // 416
+constexpr int kRowWarp0 = 4, kRowWarps = 4, kSmWarps = 6, kIssuerA = 12, kIssuerB = 15;
+constexpr int kAttnThreads = 32 * 16;
 
 // barriers (byte offsets from the 1024-aligned base)
 constexpr uint32_t bW = 0, bAFull = 8, bAEmpty = 16, bD1Full = 24, bQKFull = 32, bQKEmpty = 40, bVEmpty = 48, bSFull = 64, bSEmpty = 80, bPFull = 96, bPEmpty = 104,
@@ -135,6 +141,7 @@ struct WindowTokens {
     __device__ __forceinline__ long long operator()(int k, int row) const { return tokenOfTile((long long)first + (long long)k * step, row); }
 };
 
+// 16 warps x 128 registers: the whole register file
 __global__ void __launch_bounds__(kAttnThreads, 1) swin_attn_kernel(const __grid_constant__ AttnArgs a) {
     extern __shared__ uint8_t smemRaw[];
     const uint32_t base = (smemU32(smemRaw) + 1023u) & ~1023u;
@@ -147,20 +154,20 @@ __global__ void __launch_bounds__(kAttnThreads, 1) swin_attn_kernel(const __grid
         mbarInit(base + bAFull, 4);
         mbarInit(base + bAEmpty, 1);
         mbarInit(base + bD1Full, 1);
-        mbarInit(base + bQKFull, kEpiWarps);
+        mbarInit(base + bQKFull, kRowWarps);
         mbarInit(base + bQKEmpty, 1);
-        mbarInit(base + bPFull, kEpiWarps);
+        mbarInit(base + bPFull, kSmWarps);
         mbarInit(base + bPEmpty, 1);
-        mbarInit(base + bOcFull, kEpiWarps);
+        mbarInit(base + bOcFull, kRowWarps);
         mbarInit(base + bOcEmpty, 1);
         mbarInit(base + bD2Full, 1);
-        mbarInit(base + bD2Empty, kEpiWarps);
+        mbarInit(base + bD2Empty, kRowWarps);
         for (int i = 0; i < 2; ++i) {
             mbarInit(base + bVEmpty + 8u * i, 1);
             mbarInit(base + bSFull + 8u * i, 1);
-            mbarInit(base + bSEmpty + 8u * i, kEpiWarps);
+            mbarInit(base + bSEmpty + 8u * i, kSmWarps);
             mbarInit(base + bOFull + 8u * i, 1);
-            mbarInit(base + bOEmpty + 8u * i, kEpiWarps);
+            mbarInit(base + bOEmpty + 8u * i, kRowWarps);
         }
         mbarInitFence();
         tmaPrefetchDesc(&a.tmWqkv);
@@ -176,13 +183,13 @@ __global__ void __launch_bounds__(kAttnThreads, 1) swin_attn_kernel(const __grid
     // blocks of P (rows of one window x keys of another) are never written
     for (uint32_t o = (uint32_t)threadIdx.x * 16u; o < kOffOc + kAChunk - kOffQ; o += (uint32_t)kAttnThreads * 16u) stsV4(base + kOffQ + o, make_uint4(0, 0, 0, 0));
     fenceProxyAsync();
-    if (warp == kMmaWarp) tmemAlloc(base + kTmemSlot, kTmemCols);
+    if (warp == kIssuerA) tmemAlloc(base + kTmemSlot, kTmemCols);
     tcFenceBefore();
     __syncthreads();
     tcFenceAfter();
     uint32_t tmemBase;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmemBase) : "r"(base + kTmemSlot));
-    if (warp == kMmaWarp && lane == 0) {
+    if (warp == kIssuerA && lane == 0) {
         mbarExpectTx(base + bW, kChunks * kWqkvKa + kChunks * kWprojKa + kBiasBytes);
         for (int ka = 0; ka < kChunks; ++ka) {
             for (int c = 0; c < kChunks; ++c) tmaLoad2d(base + kOffWqkv + ka * kWqkvKa + c * kWqkvChunk, &a.tmWqkv, base + bW, ka * 32, c * 96);
@@ -196,15 +203,31 @@ __global__ void __launch_bounds__(kAttnThreads, 1) swin_attn_kernel(const __grid
     const int G = nMine * kChunks;   // this CTA's chunk sequence: g = 3 k + c; heads j = 2 g, 2 g + 1
     const WindowTokens tokens{a.h, a.w, a.shiftY, a.shiftX, a.nwx, a.nwy, a.windows, first, step};
 
-    if (warp < kMmaWarp) {
+    const uint32_t hi64 = descHi(512u, 4u), hi128 = descHi(1024u, 2u);
+    if (warp < kRowWarp0) {
         // ---- LayerNorm producers: thread = tile row, gathers its token through the window map ----
         lnProducerLoop<kC, 1>(a.x, a.eps, tokens, base, kOffA, kOffGamma, kOffBeta, base + bAFull, base + bAEmpty, nMine);
-    } else if (warp == kMmaWarp) {
-        // ---- MMA issuer: whole warp converged, one elected lane issues ----
-        const uint32_t hi64 = descHi(512u, 4u), hi128 = descHi(1024u, 2u);
-        const uint32_t idQkv = instrDescF16(kRows, 96), idS = instrDescF16(kRows, 128), idPv = instrDescF16(kRows, kHD), idProj = instrDescF16(kRows, kC);
-        auto qkv = [&](int g) {   // D1 = LN rows x W'[chunk]^T; the caller has seen QKFull(g - 1): E1 of the previous chunk has drained D1
+    } else if (warp == kIssuerA) {
+        // ---- issuer A: QKV(g) and proj(g - 2), in the order the row warps produce their inputs ----
+        const uint32_t idQkv = instrDescF16(kRows, 96), idProj = instrDescF16(kRows, kC);
+        auto proj = [&](int g) {   // D2 += Oc x Wproj[:, chunk]^T
             const int k = g / kChunks, c = g - k * kChunks;
+            mbarWait(base + bOcFull, (uint32_t)g & 1u);
+            if (c == 0) mbarWait(base + bD2Empty, ((uint32_t)k & 1u) ^ 1u);
+            tcFenceAfter();
+            if (electOne()) {
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks)
+                    ummaLoHi(tmemBase + tD2, descLo(base + kOffOc + ks * 32u), hi64, descLo(base + kOffWproj + c * kWprojKa + ks * 32u), hi64, idProj, (c | ks) != 0 ? 1u : 0u);
+                tcCommit(base + bOcEmpty);
+                if (c == kChunks - 1) tcCommit(base + bD2Full);
+            }
+            __syncwarp();
+        };
+        mbarWait(base + bW, 0);
+        for (int g = 0; g < G; ++g) {
+            const int k = g / kChunks, c = g - k * kChunks;
+            if (g >= 1) mbarWait(base + bQKFull, (uint32_t)(g - 1) & 1u);   // E1 of the previous chunk has drained D1
             if (c == 0) mbarWait(base + bAFull, (uint32_t)k & 1u);
             tcFenceAfter();
             if (electOne()) {
@@ -218,7 +241,13 @@ __global__ void __launch_bounds__(kAttnThreads, 1) swin_attn_kernel(const __grid
                 if (c == kChunks - 1) tcCommit(base + bAEmpty);   // the tile's normalised rows are no longer needed
             }
             __syncwarp();
-        };
+            if (g >= 2) proj(g - 2);
+        }
+        if (G >= 2) proj(G - 2);
+        if (G >= 1) proj(G - 1);
+    } else if (warp == kIssuerB) {
+        // ---- issuer B: S(2g), S(2g + 1) of the chunk the row warps just converted, interleaved with PV of the previous chunk ----
+        const uint32_t idS = instrDescF16(kRows, 128), idPv = instrDescF16(kRows, kHD);
         auto scores = [&](int j) {   // S[j & 1] = Q_h K_h^T for head j & 1 of the pair in the Q / K buffers
             const int b = j & 1, g = j >> 1;
             mbarWait(base + bSEmpty + 8u * b, ((uint32_t)g & 1u) ^ 1u);
@@ -250,95 +279,66 @@ __global__ void __launch_bounds__(kAttnThreads, 1) swin_attn_kernel(const __grid
             }
             __syncwarp();
         };
-        auto proj = [&](int g) {   // D2 += Oc x Wproj[:, chunk]^T
-            const int k = g / kChunks, c = g - k * kChunks;
-            mbarWait(base + bOcFull, (uint32_t)g & 1u);
-            if (c == 0) mbarWait(base + bD2Empty, ((uint32_t)k & 1u) ^ 1u);
-            tcFenceAfter();
-            if (electOne()) {
-#pragma unroll
-                for (int ks = 0; ks < 2; ++ks)
-                    ummaLoHi(tmemBase + tD2, descLo(base + kOffOc + ks * 32u), hi64, descLo(base + kOffWproj + c * kWprojKa + ks * 32u), hi64, idProj, (c | ks) != 0 ? 1u : 0u);
-                tcCommit(base + bOcEmpty);
-                if (c == kChunks - 1) tcCommit(base + bD2Full);
+        for (int g = 0; g <= G; ++g) {
+            if (g >= 1) pv(2 * g - 2);
+            if (g < G) {
+                mbarWait(base + bQKFull, (uint32_t)g & 1u);
+                scores(2 * g);
             }
-            __syncwarp();
-        };
-        mbarWait(base + bW, 0);
-        if (G > 0) {
-            qkv(0);
-            mbarWait(base + bQKFull, 0);
-            scores(0);
-            scores(1);
-            if (1 < G) qkv(1);
+            if (g >= 1) pv(2 * g - 1);
+            if (g < G) scores(2 * g + 1);
         }
-        for (int g = 0; g <= G; ++g) {   // the order of the epilogue warps' iteration g
-            if (g < G) pv(2 * g);
-            if (g + 1 < G) {
-                mbarWait(base + bQKFull, (uint32_t)(g + 1) & 1u);
-                scores(2 * g + 2);
-                if (g + 2 < G) qkv(g + 2);
-            }
-            if (g >= 1) proj(g - 1);
-            if (g + 1 < G) scores(2 * g + 3);
-            if (g < G) pv(2 * g + 1);
-        }
-    } else {
-        // ---- epilogue / softmax warps ----
+    } else if (warp < kRowWarp0 + kRowWarps) {
+        // ---- row warps: thread = tile row ----
         pdlWait();  // the residual rows come from the preceding kernel
-        const int quarter = warp & 3;                // TMEM lane quarter this warp may read: its index in the CTA modulo 4
-        const int sub = (warp - kEpiWarp0) >> 2;     // the two warps of a quarter
+        const int quarter = warp & 3;                // = warp - kRowWarp0: the TMEM lane quarter this warp may read
         const int row = quarter * 32 + lane;
         const uint32_t taddrLane = tmemBase + ((uint32_t)(quarter * 32) << 16);
         const bool rowValid = row < kWinTile * kNT;
         const int rw = rowValid ? row / kNT : 0, rp = rowValid ? row - rw * kNT : 0;
         const int kidx = kKeyStride * rw + rp;       // this row's key slot
-        // softmax passes: quarters 0 / 3 hold rows of one window (the two warps alternate heads), quarters 1 / 2 straddle two windows
-        // (each warp takes one of them, every head)
-        const bool single = quarter == 0 || quarter == 3;
-        const int passWin = quarter == 0 ? 0 : quarter == 3 ? 2 : quarter - 1 + sub;
-        const bool active = rowValid && rw == passWin;
-        const int pq = active ? rp : 0;
-        const uint32_t swQ = ((uint32_t)row >> 1) & 3u, swKey = ((uint32_t)kidx >> 1) & 3u, swP = (uint32_t)row & 7u;
+        const uint32_t swQ = ((uint32_t)row >> 1) & 3u, swKey = ((uint32_t)kidx >> 1) & 3u;
         uint32_t r[32], r2[32];
-
+        auto cvt8 = [&](const uint32_t* acc, uint32_t biasAddr) {
+            float bias[8];
+            loadF8(biasAddr, bias);
+            uint4 o;
+            o.x = packH2(__uint_as_float(acc[0]) + bias[0], __uint_as_float(acc[1]) + bias[1]);
+            o.y = packH2(__uint_as_float(acc[2]) + bias[2], __uint_as_float(acc[3]) + bias[3]);
+            o.z = packH2(__uint_as_float(acc[4]) + bias[4], __uint_as_float(acc[5]) + bias[5]);
+            o.w = packH2(__uint_as_float(acc[6]) + bias[6], __uint_as_float(acc[7]) + bias[7]);
+            return o;
+        };
         auto e1 = [&](int g) {   // D1 (+ bias) -> Q / K / V^T operands
             const int c = g % kChunks, vb = g & 1;
+            const uint32_t bOff = base + kOffBqkv + 4u * (uint32_t)(c * 96);
             mbarWait(base + bD1Full, (uint32_t)g & 1u);
             tcFenceAfter();
-            tmemLd32(taddrLane + tD1 + 32u * sub, r);            // sub 0: Q columns, sub 1: K columns
-            tmemLd16(taddrLane + tD1 + 64u + 16u * sub, r2);     // V dims 16 sub .. +16
+            tmemLd32(taddrLane + tD1, r);          // Q columns
+            tmemLd32(taddrLane + tD1 + 32u, r2);   // K columns
             tmemLdWait();
-            mbarWait(base + bQKEmpty, ((uint32_t)g & 1u) ^ 1u);            // both S MMAs of the previous chunk have read Q / K
-            mbarWait(base + bVEmpty + 8u * vb, ((uint32_t)(g >> 1) & 1u) ^ 1u);   // both PV MMAs of chunk g - 2 have read this V buffer
-            const uint32_t bOff = base + kOffBqkv + 4u * (uint32_t)(c * 96);
-            if (sub == 0 || rowValid) {
-                const uint32_t dst = sub == 0 ? base + kOffQ + (uint32_t)row * 64u : base + kOffK + (uint32_t)kidx * 64u;
-                const uint32_t sw = sub == 0 ? swQ : swKey;
+            mbarWait(base + bQKEmpty, ((uint32_t)g & 1u) ^ 1u);   // both S MMAs of the previous chunk have read Q / K
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    float bias[8];
-                    loadF8(bOff + 4u * (uint32_t)(32 * sub + 8 * q), bias);
-                    uint4 o;
-                    o.x = packH2(__uint_as_float(r[8 * q]) + bias[0], __uint_as_float(r[8 * q + 1]) + bias[1]);
-                    o.y = packH2(__uint_as_float(r[8 * q + 2]) + bias[2], __uint_as_float(r[8 * q + 3]) + bias[3]);
-                    o.z = packH2(__uint_as_float(r[8 * q + 4]) + bias[4], __uint_as_float(r[8 * q + 5]) + bias[5]);
-                    o.w = packH2(__uint_as_float(r[8 * q + 6]) + bias[6], __uint_as_float(r[8 * q + 7]) + bias[7]);
-                    stsV4(dst + (((uint32_t)q ^ sw) << 4), o);
-                }
+            for (int q = 0; q < 4; ++q) stsV4(base + kOffQ + (uint32_t)row * 64u + (((uint32_t)q ^ swQ) << 4), cvt8(&r[8 * q], bOff + 32u * q));
+            if (rowValid) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) stsV4(base + kOffK + (uint32_t)kidx * 64u + (((uint32_t)q ^ swKey) << 4), cvt8(&r2[8 * q], bOff + 128u + 32u * q));
             }
+            tmemLd32(taddrLane + tD1 + 64u, r);    // V columns (both heads)
+            tmemLdWait();
+            mbarWait(base + bVEmpty + 8u * vb, ((uint32_t)(g >> 1) & 1u) ^ 1u);   // both PV MMAs of chunk g - 2 have read this V buffer
             if (rowValid) {
                 // V^T[dim][key]: 2-byte stores; the lanes of a warp hold consecutive keys, so a store instruction covers 64 contiguous bytes
                 const uint32_t vDst = base + kOffV + (uint32_t)vb * kVBuf + ((uint32_t)kidx >> 6) * 4096u + ((uint32_t)kidx & 7u) * 2u;
                 const uint32_t kc16 = ((uint32_t)kidx & 63u) >> 3;
 #pragma unroll
-                for (int q = 0; q < 2; ++q) {
+                for (int q = 0; q < 4; ++q) {
                     float bias[8];
-                    loadF8(bOff + 4u * (uint32_t)(64 + 16 * sub + 8 * q), bias);
+                    loadF8(bOff + 4u * (uint32_t)(64 + 8 * q), bias);
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        const uint32_t dd = (uint32_t)(16 * sub + 8 * q + i);
-                        stsU16(vDst + dd * 128u + ((kc16 ^ (dd & 7u)) << 4), __half_as_ushort(__float2half_rn(__uint_as_float(r2[8 * q + i]) + bias[i])));
+                        const uint32_t dd = (uint32_t)(8 * q + i);
+                        stsU16(vDst + dd * 128u + ((kc16 ^ (dd & 7u)) << 4), __half_as_ushort(__float2half_rn(__uint_as_float(r[8 * q + i]) + bias[i])));
                     }
                 }
             }
@@ -347,14 +347,107 @@ __global__ void __launch_bounds__(kAttnThreads, 1) swin_attn_kernel(const __grid
             __syncwarp();
             if (lane == 0) mbarArrive(base + bQKFull);
         };
-
+        auto e2 = [&](int g) {   // O -> fp16 -> Oc (A operand of proj); the probabilities were normalised by the softmax warps
+            const int ob = g & 1;
+            mbarWait(base + bOFull + 8u * ob, (uint32_t)(g >> 1) & 1u);
+            tcFenceAfter();
+            tmemLd32(taddrLane + tO + 32u * ob, r2);
+            tmemLdWait();
+            tcFenceBefore();
+            __syncwarp();
+            if (lane == 0) mbarArrive(base + bOEmpty + 8u * ob);
+            mbarWait(base + bOcEmpty, ((uint32_t)g & 1u) ^ 1u);   // proj of the previous chunk has read Oc
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                uint4 o;
+                o.x = packH2(__uint_as_float(r2[8 * q]), __uint_as_float(r2[8 * q + 1]));
+                o.y = packH2(__uint_as_float(r2[8 * q + 2]), __uint_as_float(r2[8 * q + 3]));
+                o.z = packH2(__uint_as_float(r2[8 * q + 4]), __uint_as_float(r2[8 * q + 5]));
+                o.w = packH2(__uint_as_float(r2[8 * q + 6]), __uint_as_float(r2[8 * q + 7]));
+                stsV4(base + kOffOc + (uint32_t)row * 64u + (((uint32_t)q ^ swQ) << 4), o);
+            }
+            fenceProxyAsync();
+            __syncwarp();
+            if (lane == 0) mbarArrive(base + bOcFull);
+        };
+        auto e3 = [&](int k) {   // x += D2 + bproj, 48 columns at a time
+            const long long tok = tokens(k, row);
+            __half* xrow = a.x + (tok >= 0 ? tok : 0) * kC;
+            uint4 res[6];
+#pragma unroll
+            for (int q = 0; q < 6; ++q) res[q] = make_uint4(0, 0, 0, 0);
+            if (tok >= 0) {   // issued before the accumulator wait (an L2 hit: the producers read these rows one tile ago)
+#pragma unroll
+                for (int q = 0; q < 6; ++q) res[q] = reinterpret_cast<const uint4*>(xrow)[q];
+            }
+            mbarWait(base + bD2Full, (uint32_t)k & 1u);
+            tcFenceAfter();
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                const int col0 = half * (kC / 2);
+                tmemLd32(taddrLane + tD2 + (uint32_t)col0, r);
+                tmemLd16(taddrLane + tD2 + (uint32_t)col0 + 32u, r2);
+                tmemLdWait();
+                if (half == 1) {
+                    tcFenceBefore();
+                    __syncwarp();
+                    if (lane == 0) mbarArrive(base + bD2Empty);
+                }
+                uint4 nxt[6];
+                if (half == 0 && tok >= 0) {
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) nxt[q] = reinterpret_cast<const uint4*>(xrow)[6 + q];
+                }
+                if (tok >= 0) {
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) {
+                        float bias[8], rv[8];
+                        loadF8(base + kOffBproj + 4u * (uint32_t)(col0 + 8 * q), bias);
+                        unpack8(res[q], rv);
+                        uint4 o;
+                        __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float a0 = __uint_as_float(q < 4 ? r[8 * q + 2 * i] : r2[8 * (q - 4) + 2 * i]);
+                            const float a1 = __uint_as_float(q < 4 ? r[8 * q + 2 * i + 1] : r2[8 * (q - 4) + 2 * i + 1]);
+                            oh[i] = __floats2half2_rn(a0 + bias[2 * i] + rv[2 * i], a1 + bias[2 * i + 1] + rv[2 * i + 1]);
+                        }
+                        reinterpret_cast<uint4*>(xrow)[6 * half + q] = o;
+                    }
+                }
+                if (half == 0) {
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) res[q] = nxt[q];
+                }
+            }
+        };
+        for (int g = 0; g <= G + 2; ++g) {
+            if (g < G) e1(g);
+            if (g >= 2 && g - 2 < G) e2(g - 2);
+            if (g >= 3 && (g - 3) % kChunks == kChunks - 1) e3((g - 3) / kChunks);   // proj of the tile's last chunk was queued an iteration ago
+        }
+    } else {
+        // ---- softmax warps: thread = query row, one pass (one window's 36 keys) per head ----
+        const int quarter = warp & 3;
+        const int sub = warp >= 12 ? 1 : 0;          // second warp of quarters 1 / 2
+        const int row = quarter * 32 + lane;
+        const uint32_t taddrLane = tmemBase + ((uint32_t)(quarter * 32) << 16);
+        const bool rowValid = row < kWinTile * kNT;
+        const int rw = rowValid ? row / kNT : 0, rp = rowValid ? row - rw * kNT : 0;
+        const int passWin = quarter == 0 ? 0 : quarter == 3 ? 2 : quarter - 1 + sub;
+        const bool active = rowValid && rw == passWin;
+        const int pq = active ? rp : 0;
+        const uint32_t swP = (uint32_t)row & 7u;
+        uint32_t r[32], s2[8];
         // keys a query may attend to in a shifted block (torchvision's attn_mask: tokens of the last window row / column that were rolled
         // in from the opposite image edge form their own regions); bit j = key position j of the pass's window
         const bool shifted = (a.shiftY | a.shiftX) > 0;
         uint32_t allowLo = 0xffffffffu, allowHi = 0xfu;
+        bool maskedWin = false;   // warp-uniform: the pass's window lies on the last window row / column of a shifted block
         auto setMask = [&](long long tile) {
             allowLo = 0xffffffffu;
             allowHi = 0xfu;
+            maskedWin = false;
             if (shifted) {
                 long long win = tile * kWinTile + passWin;
                 const int wx = (int)(win % a.nwx);
@@ -367,168 +460,79 @@ __global__ void __launch_bounds__(kAttnThreads, 1) swin_attn_kernel(const __grid
                 if (a.shiftX > 0 && wx == a.nwx - 1) m &= (pq % kWin < kWin / 2) ? xLo : ~xLo;
                 allowLo = (uint32_t)m;
                 allowHi = (uint32_t)(m >> 32) & 0xfu;
+                maskedWin = (a.shiftY > 0 && wy == a.nwy - 1) || (a.shiftX > 0 && wx == a.nwx - 1);
             }
         };
-
-        auto sm = [&](int j) {   // softmax of head j for this warp's pass -> P
+        mbarWait(base + bW, 0);   // bias tables
+        for (int j = 0; j < 2 * G; ++j) {
             const int b = j & 1, g = j >> 1;
-            const bool mine = !single || b == sub;
+            if (b == 0 && g % kChunks == 0) setMask((long long)first + (long long)(g / kChunks) * step);
             mbarWait(base + bSFull + 8u * b, (uint32_t)g & 1u);
             tcFenceAfter();
-            uint32_t s2[8];
-            bool waited = false;
-            if (mine) {
-                tmemLd32(taddrLane + tS + 128u * b + (uint32_t)(kKeyStride * passWin), r);
-                tmemLd8(taddrLane + tS + 128u * b + (uint32_t)(kKeyStride * passWin) + 32u, s2);
-                tmemLdWait();
-            }
+            tmemLd32(taddrLane + tS + 128u * b + (uint32_t)(kKeyStride * passWin), r);
+            tmemLd8(taddrLane + tS + 128u * b + (uint32_t)(kKeyStride * passWin) + 32u, s2);
+            tmemLdWait();
             tcFenceBefore();
             __syncwarp();
             if (lane == 0) mbarArrive(base + bSEmpty + 8u * b);   // the scores are in registers: the next head of this parity may overwrite them
-            if (mine) {
-                const int head = 2 * (g % kChunks) + b;
-                const uint32_t bRow = base + kOffBias + (uint32_t)head * kBiasHead + (uint32_t)pq * (kBiasPitch * 4u);
-                float v[kNT];
+            const int head = 2 * (g % kChunks) + b;
+            const uint32_t bRow = base + kOffBias + (uint32_t)head * kBiasHead + (uint32_t)pq * (kBiasPitch * 4u);
+            float v[kNT];
 #pragma unroll
-                for (int q = 0; q < kNT / 4; ++q) {
-                    const uint4 bb = ldsV4(bRow + 16u * q);
-                    const uint32_t* src = q < 8 ? &r[4 * q] : &s2[4 * q - 32];
-                    v[4 * q] = __uint_as_float(src[0]) + __uint_as_float(bb.x);
-                    v[4 * q + 1] = __uint_as_float(src[1]) + __uint_as_float(bb.y);
-                    v[4 * q + 2] = __uint_as_float(src[2]) + __uint_as_float(bb.z);
-                    v[4 * q + 3] = __uint_as_float(src[3]) + __uint_as_float(bb.w);
-                }
-                if (shifted) {
-#pragma unroll
-                    for (int i = 0; i < kNT; ++i) {
-                        const uint32_t bit = i < 32 ? (allowLo >> i) & 1u : (allowHi >> (i - 32)) & 1u;
-                        v[i] = bit ? v[i] : v[i] - 144.26950408889634f;   // -100 in natural-log units
-                    }
-                }
-                float mx = v[0];
-#pragma unroll
-                for (int i = 1; i < kNT; ++i) mx = fmaxf(mx, v[i]);
-                float den = 0.f;
+            for (int q = 0; q < kNT / 4; ++q) {
+                const uint4 bb = ldsV4(bRow + 16u * q);
+                const uint32_t* src = q < 8 ? &r[4 * q] : &s2[4 * q - 32];
+                v[4 * q] = __uint_as_float(src[0]) + __uint_as_float(bb.x);
+                v[4 * q + 1] = __uint_as_float(src[1]) + __uint_as_float(bb.y);
+                v[4 * q + 2] = __uint_as_float(src[2]) + __uint_as_float(bb.z);
+                v[4 * q + 3] = __uint_as_float(src[3]) + __uint_as_float(bb.w);
+            }
+            if (maskedWin) {
 #pragma unroll
                 for (int i = 0; i < kNT; ++i) {
-                    v[i] = ex2f(v[i] - mx);
-                    den += v[i];
-                }
-                const float inv = __fdividef(1.f, den);
-                mbarWait(base + bPEmpty, ((uint32_t)j & 1u) ^ 1u);   // PV of the previous head has read P
-                waited = true;
-                if (active) {
-                    const uint32_t pRow = base + kOffP + (uint32_t)row * 128u;
-#pragma unroll
-                    for (int q = 0; q < 5; ++q) {
-                        uint4 o;
-                        o.x = packH2(v[8 * q] * inv, v[8 * q + 1] * inv);
-                        o.y = packH2(v[8 * q + 2] * inv, v[8 * q + 3] * inv);
-                        if (q < 4) {
-                            o.z = packH2(v[8 * q + 4] * inv, v[8 * q + 5] * inv);
-                            o.w = packH2(v[8 * q + 6] * inv, v[8 * q + 7] * inv);
-                        } else {
-                            o.z = 0u;   // keys 36..39 of the window's slot: padding
-                            o.w = 0u;
-                        }
-                        const uint32_t ci = (uint32_t)(5 * passWin + q);
-                        stsV4(pRow + (ci >> 3) * kPChunk + (((ci & 7u) ^ swP) << 4), o);
-                    }
+                    const uint32_t bit = i < 32 ? (allowLo >> i) & 1u : (allowHi >> (i - 32)) & 1u;
+                    v[i] = bit ? v[i] : v[i] - 144.26950408889634f;   // -100 in natural-log units
                 }
             }
-            // a warp that sat this head out must not arrive early: its arrival would be counted in the phase of the PREVIOUS head while
-            // slower warps are still writing that head's probabilities
-            if (!waited) mbarWait(base + bPEmpty, ((uint32_t)j & 1u) ^ 1u);
+            float m4[4] = {v[0], v[1], v[2], v[3]};
+#pragma unroll
+            for (int i = 4; i < kNT; ++i) m4[i & 3] = fmaxf(m4[i & 3], v[i]);
+            const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+            float d4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int i = 0; i < kNT; ++i) {
+                v[i] = ex2f(v[i] - mx);
+                d4[i & 3] += v[i];
+            }
+            const float inv = __fdividef(1.f, (d4[0] + d4[1]) + (d4[2] + d4[3]));
+            mbarWait(base + bPEmpty, ((uint32_t)j & 1u) ^ 1u);   // PV of the previous head has read P
+            if (active) {
+                const uint32_t pRow = base + kOffP + (uint32_t)row * 128u;
+#pragma unroll
+                for (int q = 0; q < 5; ++q) {
+                    uint4 o;
+                    o.x = packH2(v[8 * q] * inv, v[8 * q + 1] * inv);
+                    o.y = packH2(v[8 * q + 2] * inv, v[8 * q + 3] * inv);
+                    if (q < 4) {
+                        o.z = packH2(v[8 * q + 4] * inv, v[8 * q + 5] * inv);
+                        o.w = packH2(v[8 * q + 6] * inv, v[8 * q + 7] * inv);
+                    } else {
+                        o.z = 0u;   // keys 36..39 of the window's slot: padding
+                        o.w = 0u;
+                    }
+                    const uint32_t ci = (uint32_t)(5 * passWin + q);
+                    stsV4(pRow + (ci >> 3) * kPChunk + (((ci & 7u) ^ swP) << 4), o);
+                }
+            }
             fenceProxyAsync();
             __syncwarp();
             if (lane == 0) mbarArrive(base + bPFull);
-        };
-
-        auto e2 = [&](int g) {   // O -> fp16 -> Oc (A operand of proj)
-            const int ob = g & 1;
-            mbarWait(base + bOFull + 8u * ob, (uint32_t)(g >> 1) & 1u);
-            tcFenceAfter();
-            tmemLd16(taddrLane + tO + 32u * ob + 16u * sub, r2);
-            tmemLdWait();
-            tcFenceBefore();
-            __syncwarp();
-            if (lane == 0) mbarArrive(base + bOEmpty + 8u * ob);
-            mbarWait(base + bOcEmpty, ((uint32_t)g & 1u) ^ 1u);   // proj of the previous chunk has read Oc
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                uint4 o;
-                o.x = packH2(__uint_as_float(r2[8 * q]), __uint_as_float(r2[8 * q + 1]));
-                o.y = packH2(__uint_as_float(r2[8 * q + 2]), __uint_as_float(r2[8 * q + 3]));
-                o.z = packH2(__uint_as_float(r2[8 * q + 4]), __uint_as_float(r2[8 * q + 5]));
-                o.w = packH2(__uint_as_float(r2[8 * q + 6]), __uint_as_float(r2[8 * q + 7]));
-                stsV4(base + kOffOc + (uint32_t)row * 64u + (((uint32_t)(2 * sub + q) ^ swQ) << 4), o);
-            }
-            fenceProxyAsync();
-            __syncwarp();
-            if (lane == 0) mbarArrive(base + bOcFull);
-        };
-
-        uint4 res[6];
-        long long resTok = -1;
-        auto prefetchResidual = [&](int k) {   // issued one softmax pass ahead of its use
-            resTok = tokens(k, row);
-#pragma unroll
-            for (int q = 0; q < 6; ++q) res[q] = make_uint4(0, 0, 0, 0);
-            if (resTok >= 0) {
-                const uint4* xr = reinterpret_cast<const uint4*>(a.x + resTok * kC + sub * (kC / 2));
-#pragma unroll
-                for (int q = 0; q < 6; ++q) res[q] = xr[q];
-            }
-        };
-        auto e3 = [&](int k) {   // x += D2 + bproj
-            const int col0 = sub * (kC / 2);
-            mbarWait(base + bD2Full, (uint32_t)k & 1u);
-            tcFenceAfter();
-            tmemLd32(taddrLane + tD2 + (uint32_t)col0, r);
-            tmemLd16(taddrLane + tD2 + (uint32_t)col0 + 32u, r2);
-            tmemLdWait();
-            tcFenceBefore();
-            __syncwarp();
-            if (lane == 0) mbarArrive(base + bD2Empty);
-            if (resTok >= 0) {
-                uint4* xrow = reinterpret_cast<uint4*>(a.x + resTok * kC + col0);
-#pragma unroll
-                for (int q = 0; q < 6; ++q) {
-                    float bias[8], rv[8];
-                    loadF8(base + kOffBproj + 4u * (uint32_t)(col0 + 8 * q), bias);
-                    unpack8(res[q], rv);
-                    uint4 o;
-                    __half2* oh = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float a0 = __uint_as_float(q < 4 ? r[8 * q + 2 * i] : r2[8 * (q - 4) + 2 * i]);
-                        const float a1 = __uint_as_float(q < 4 ? r[8 * q + 2 * i + 1] : r2[8 * (q - 4) + 2 * i + 1]);
-                        oh[i] = __floats2half2_rn(a0 + bias[2 * i] + rv[2 * i], a1 + bias[2 * i + 1] + rv[2 * i + 1]);
-                    }
-                    xrow[q] = o;
-                }
-            }
-        };
-
-        mbarWait(base + bW, 0);   // bias tables
-        if (G > 0) e1(0);
-        for (int g = 0; g <= G; ++g) {
-            if (g < G) {
-                if (g % kChunks == 0) setMask((long long)first + (long long)(g / kChunks) * step);
-                sm(2 * g);
-            }
-            if (g + 1 < G) e1(g + 1);
-            if (g >= 1) e2(g - 1);
-            const bool fin = g >= 1 && (g - 1) % kChunks == kChunks - 1;   // chunk g - 1 closed a tile
-            if (fin) prefetchResidual((g - 1) / kChunks);
-            if (g < G) sm(2 * g + 1);
-            if (fin) e3((g - 1) / kChunks);
         }
     }
 
     tcFenceBefore();
     __syncthreads();
-    if (warp == kMmaWarp) {
+    if (warp == kIssuerA) {
         tcFenceAfter();
         tmemDealloc(tmemBase, kTmemCols);
     }
