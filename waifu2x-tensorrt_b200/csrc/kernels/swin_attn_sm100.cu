@@ -205,10 +205,72 @@ __global__ void __launch_bounds__(kAttnThreads, 1) swin_attn_kernel(const __grid
 
     const uint32_t hi64 = descHi(512u, 4u), hi128 = descHi(1024u, 2u);
     if (warp < kRowWarp0) {
-        // ---- LayerNorm producers: thread = tile row, gathers its token through the window map ----
-        lnProducerLoop<kC, 1>(a.x, a.eps, tokens, base, kOffA, kOffGamma, kOffBeta, base + bAFull, base + bAEmpty, nMine);
+        // ---- LayerNorm producers: thread = tile row, gathers its token through the window map; after handing tile k + 1 to the tensor
+        // core they write back tile k (E3: their warp index is also the TMEM lane quarter of their rows) ----
+        const int quarter = warp;
+        const int row = quarter * 32 + lane;
+        const uint32_t taddrLane = tmemBase + ((uint32_t)(quarter * 32) << 16);
+        uint32_t r[32], r2[32];
+        auto e3 = [&](int k) {   // x += D2 + bproj, 48 columns at a time
+            const long long tok = tokens(k, row);
+            __half* xrow = a.x + (tok >= 0 ? tok : 0) * kC;
+            uint4 res[6];
+#pragma unroll
+            for (int q = 0; q < 6; ++q) res[q] = make_uint4(0, 0, 0, 0);
+            if (tok >= 0) {   // issued before the accumulator wait (an L2 hit: the producers read these rows one tile ago)
+#pragma unroll
+                for (int q = 0; q < 6; ++q) res[q] = reinterpret_cast<const uint4*>(xrow)[q];
+            }
+            mbarWait(base + bD2Full, (uint32_t)k & 1u);
+            tcFenceAfter();
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                const int col0 = half * (kC / 2);
+                tmemLd32(taddrLane + tD2 + (uint32_t)col0, r);
+                tmemLd16(taddrLane + tD2 + (uint32_t)col0 + 32u, r2);
+                tmemLdWait();
+                if (half == 1) {
+                    tcFenceBefore();
+                    __syncwarp();
+                    if (lane == 0) mbarArrive(base + bD2Empty);
+                }
+                uint4 nxt[6];
+                if (half == 0 && tok >= 0) {
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) nxt[q] = reinterpret_cast<const uint4*>(xrow)[6 + q];
+                }
+                if (tok >= 0) {
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) {
+                        float bias[8], rv[8];
+                        loadF8(base + kOffBproj + 4u * (uint32_t)(col0 + 8 * q), bias);
+                        unpack8(res[q], rv);
+                        uint4 o;
+                        __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float a0 = __uint_as_float(q < 4 ? r[8 * q + 2 * i] : r2[8 * (q - 4) + 2 * i]);
+                            const float a1 = __uint_as_float(q < 4 ? r[8 * q + 2 * i + 1] : r2[8 * (q - 4) + 2 * i + 1]);
+                            oh[i] = __floats2half2_rn(a0 + bias[2 * i] + rv[2 * i], a1 + bias[2 * i + 1] + rv[2 * i + 1]);
+                        }
+                        reinterpret_cast<uint4*>(xrow)[6 * half + q] = o;
+                    }
+                }
+                if (half == 0) {
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) res[q] = nxt[q];
+                }
+            }
+        };
+        // tile k's rows are handed over while tile k - 1 is being processed; tile k - 2's accumulator is complete (or about to be) by then,
+        // so the write-back never holds up the next tile's loads
+        lnProducerLoop<kC, 1>(a.x, a.eps, tokens, base, kOffA, kOffGamma, kOffBeta, base + bAFull, base + bAEmpty, nMine, 0, 1, [&](int k) {
+            if (k >= 2) e3(k - 2);
+        });
+        if (nMine >= 2) e3(nMine - 2);
+        if (nMine >= 1) e3(nMine - 1);
     } else if (warp == kIssuerA) {
-        // ---- issuer A: QKV(g) and proj(g - 2), in the order the row warps produce their inputs ----
+        // ---- issuer A: QKV(g) and proj(g - 3), in the order the row warps produce their inputs ----
         const uint32_t idQkv = instrDescF16(kRows, 96), idProj = instrDescF16(kRows, kC);
         auto proj = [&](int g) {   // D2 += Oc x Wproj[:, chunk]^T
             const int k = g / kChunks, c = g - k * kChunks;
@@ -241,10 +303,9 @@ __global__ void __launch_bounds__(kAttnThreads, 1) swin_attn_kernel(const __grid
                 if (c == kChunks - 1) tcCommit(base + bAEmpty);   // the tile's normalised rows are no longer needed
             }
             __syncwarp();
-            if (g >= 2) proj(g - 2);
+            if (g >= 3) proj(g - 3);   // its Oc tile was written an iteration ago: never blocks the next QKV
         }
-        if (G >= 2) proj(G - 2);
-        if (G >= 1) proj(G - 1);
+        for (int g = G > 3 ? G - 3 : 0; g < G; ++g) proj(g);
     } else if (warp == kIssuerB) {
         // ---- issuer B: S(2g), S(2g + 1) of the chunk the row warps just converted, interleaved with PV of the previous chunk ----
         const uint32_t idS = instrDescF16(kRows, 128), idPv = instrDescF16(kRows, kHD);
@@ -284,9 +345,9 @@ __global__ void __launch_bounds__(kAttnThreads, 1) swin_attn_kernel(const __grid
             if (g < G) {
                 mbarWait(base + bQKFull, (uint32_t)g & 1u);
                 scores(2 * g);
+                scores(2 * g + 1);   // waits only until the softmax warps have LOADED the previous head of this parity: frees Q / K early
             }
             if (g >= 1) pv(2 * g - 1);
-            if (g < G) scores(2 * g + 1);
         }
     } else if (warp < kRowWarp0 + kRowWarps) {
         // ---- row warps: thread = tile row ----
@@ -370,61 +431,9 @@ __global__ void __launch_bounds__(kAttnThreads, 1) swin_attn_kernel(const __grid
             __syncwarp();
             if (lane == 0) mbarArrive(base + bOcFull);
         };
-        auto e3 = [&](int k) {   // x += D2 + bproj, 48 columns at a time
-            const long long tok = tokens(k, row);
-            __half* xrow = a.x + (tok >= 0 ? tok : 0) * kC;
-            uint4 res[6];
-#pragma unroll
-            for (int q = 0; q < 6; ++q) res[q] = make_uint4(0, 0, 0, 0);
-            if (tok >= 0) {   // issued before the accumulator wait (an L2 hit: the producers read these rows one tile ago)
-#pragma unroll
-                for (int q = 0; q < 6; ++q) res[q] = reinterpret_cast<const uint4*>(xrow)[q];
-            }
-            mbarWait(base + bD2Full, (uint32_t)k & 1u);
-            tcFenceAfter();
-#pragma unroll 1
-            for (int half = 0; half < 2; ++half) {
-                const int col0 = half * (kC / 2);
-                tmemLd32(taddrLane + tD2 + (uint32_t)col0, r);
-                tmemLd16(taddrLane + tD2 + (uint32_t)col0 + 32u, r2);
-                tmemLdWait();
-                if (half == 1) {
-                    tcFenceBefore();
-                    __syncwarp();
-                    if (lane == 0) mbarArrive(base + bD2Empty);
-                }
-                uint4 nxt[6];
-                if (half == 0 && tok >= 0) {
-#pragma unroll
-                    for (int q = 0; q < 6; ++q) nxt[q] = reinterpret_cast<const uint4*>(xrow)[6 + q];
-                }
-                if (tok >= 0) {
-#pragma unroll
-                    for (int q = 0; q < 6; ++q) {
-                        float bias[8], rv[8];
-                        loadF8(base + kOffBproj + 4u * (uint32_t)(col0 + 8 * q), bias);
-                        unpack8(res[q], rv);
-                        uint4 o;
-                        __half2* oh = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const float a0 = __uint_as_float(q < 4 ? r[8 * q + 2 * i] : r2[8 * (q - 4) + 2 * i]);
-                            const float a1 = __uint_as_float(q < 4 ? r[8 * q + 2 * i + 1] : r2[8 * (q - 4) + 2 * i + 1]);
-                            oh[i] = __floats2half2_rn(a0 + bias[2 * i] + rv[2 * i], a1 + bias[2 * i + 1] + rv[2 * i + 1]);
-                        }
-                        reinterpret_cast<uint4*>(xrow)[6 * half + q] = o;
-                    }
-                }
-                if (half == 0) {
-#pragma unroll
-                    for (int q = 0; q < 6; ++q) res[q] = nxt[q];
-                }
-            }
-        };
-        for (int g = 0; g <= G + 2; ++g) {
+        for (int g = 0; g <= G + 1; ++g) {
             if (g < G) e1(g);
-            if (g >= 2 && g - 2 < G) e2(g - 2);
-            if (g >= 3 && (g - 3) % kChunks == kChunks - 1) e3((g - 3) / kChunks);   // proj of the tile's last chunk was queued an iteration ago
+            if (g >= 2) e2(g - 2);
         }
     } else {
         // ---- softmax warps: thread = query row, one pass (one window's 36 keys) per head ----
