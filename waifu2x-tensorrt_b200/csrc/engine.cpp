@@ -701,11 +701,57 @@ void Engine::buildPlanSwin() {
     Act y1 = up(y2, &x1);
     stage(y1);
     Act top = y1;
-    if (S == 4) top = up(y1, nullptr);
+    // 4x models end in PatchUp (Linear 96 -> 4 x 96, pixel shuffle 2) followed by ToImage (Linear 96 -> 4 x 3, pixel shuffle 2) with nothing in
+    // between: one linear map 96 -> 16 x 3 with a pixel shuffle of 4.  Composed here in fp32 from the packed weights (then rounded to
+    // fp16 once), the 4 x 96-wide intermediate tensor (177 MB per batch of four tiles) is neither written nor read.
+    const bool composeHead = S == 4 && !useDirect && !devEnv("W2X_NO_HEAD_COMPOSE") && li + 2 == model.layers.size() && model.layers[li].kind == L_UPLIN &&
+                             model.layers[li + 1].kind == L_TOIMG && model.layers[li + 1].upscale == 2 && model.layers[li + 1].ktot == model.layers[li].cout &&
+                             model.layers[li].npad == 4 * model.layers[li].cout;
+    if (S == 4 && !composeHead) top = up(y1, nullptr);
     {
+        const size_t iu = composeHead ? next(L_UPLIN) : 0;
         const size_t i = next(L_TOIMG);
         const PackedLayer& L = model.layers[i];
-        const int s = (int)L.upscale;
+        int s = (int)L.upscale, npad = 16;
+        const __half* dWeights = dW[i];
+        const float* dBiases = dBias[i];
+        double flops = 2.0 * top.h * top.w * 3.0 * s * s * L.ktot;
+        if (composeHead) {
+            const PackedLayer& U = model.layers[iu];   // rows q0 * cout + c (q0 = dy * 2 + dx), K = cin
+            const int cmid = (int)U.cout, K = (int)U.ktot;
+            keepW.emplace_back((size_t)64 * K, (uint16_t)0);
+            keepF.emplace_back(64, 0.f);
+            std::vector<uint16_t>& wc = keepW.back();
+            std::vector<float>& bc = keepF.back();
+            std::vector<double> acc((size_t)K);
+            for (int q0 = 0; q0 < 4; ++q0)
+                for (int q1 = 0; q1 < 4; ++q1)
+                    for (int c3 = 0; c3 < 3; ++c3) {
+                        const int oy = 2 * (q0 >> 1) + (q1 >> 1), ox = 2 * (q0 & 1) + (q1 & 1);
+                        const int dst = (oy * 4 + ox) * 4 + c3, rowI = q1 * 4 + c3;
+                        std::fill(acc.begin(), acc.end(), 0.0);
+                        double b = L.bias[rowI];
+                        for (int c = 0; c < cmid; ++c) {
+                            const double wi = halfBitsToFloat(L.w[(size_t)rowI * cmid + c]);
+                            const uint16_t* urow = &U.w[(size_t)(q0 * cmid + c) * K];
+                            for (int k = 0; k < K; ++k) acc[k] += wi * halfBitsToFloat(urow[k]);
+                            b += wi * U.bias[q0 * cmid + c];
+                        }
+                        for (int k = 0; k < K; ++k) wc[(size_t)dst * K + k] = floatToHalfBits((float)acc[k]);
+                        bc[dst] = (float)b;
+                    }
+            __half* dWc = (__half*)dalloc(wc.size() * 2);
+            uploadAsync(dWc, wc.data(), wc.size() * 2);
+            dWeights = dWc;
+            dBiases = uploadF(bc);
+            s = 4;
+            npad = 64;
+            flops = 2.0 * top.h * top.w * 3.0 * s * s * K;
+            LayerExec Sk;
+            Sk.name = U.name;
+            Sk.impl = IMPL_SKIP;
+            layers.push_back(Sk);
+        }
         Act out = allocAct(top.h * s, top.w * s, 4);
         ConvParams p{};
         p.in = top.p;
@@ -714,11 +760,11 @@ void Engine::buildPlanSwin() {
         p.cin = top.c; p.gn = top.n;
         p.ntaps = 1; p.tap[0] = {0, 0, 0, 0};
         p.gx = top.w; p.gy = top.h;
-        p.npad = 16; p.ktot = (int)L.ktot;
-        p.w = dW[i]; p.bias = dBias[i];
+        p.npad = npad; p.ktot = composeHead ? (int)model.layers[iu].ktot : (int)L.ktot;
+        p.w = dWeights; p.bias = dBiases;
         p.mode = EPI_TOIMG; p.slope = 1.f; p.cout = s;
         p.out = out.p; p.out_h = out.h; p.out_w = out.w; p.out_c = 4;
-        pushConv(i, p, 2.0 * top.h * top.w * 3.0 * s * s * L.ktot, true);
+        pushConv(i, p, flops, true);
         actOut = out;
     }
     if (li != model.layers.size()) throw Error("swin plan: trailing layers in pack file");

@@ -16,7 +16,7 @@ enum EpiMode : int {
     EPI_D2S = 1,    // ConvTranspose 2x2 s2: column (q*cout+co) -> out[img][2y+q/2][2x+q%2][co] = lrelu(acc+bias) + skip
     EPI_UP4 = 2,    // ConvTranspose 4x4 s2 p3 head: column (q*4+co) -> out[img][2y-1+q/2][2x-1+q%2][co] = acc + bias
     EPI_FINAL = 3,  // image head: out[img][y][x][0..4) = clamp(acc + bias + skip[img][y+off][x+off], 0, 1)
-    EPI_TOIMG = 4,  // SwinUNet ToImage: column (q*4+c) -> out[img][s*y+q/2][s*x+q%2][c] = clamp(acc + bias, 0, 1), s = cout (1|2)
+    EPI_TOIMG = 4,  // SwinUNet ToImage: column (q*4+c) -> out[img][s*y+q/s][s*x+q%s][c] = clamp(acc + bias, 0, 1), s = cout (1|2|4)
 };
 enum ActKind : int { ACT_LRELU = 0, ACT_GELU = 1 };  // ACT_LRELU with slope 1 == identity
 
@@ -159,7 +159,7 @@ __device__ __forceinline__ void conv_epilogue8(const ConvParams& p, int img, int
         for (int hsel = 0; hsel < 2; ++hsel) {
             const int q = (j0 >> 2) + hsel;
             if (q >= s * s) continue;
-            const int oy = s * y + (q >> 1), ox = s * x + (q & 1);
+            const int oy = s * y + q / s, ox = s * x + q % s;
             const float* vv = v + 4 * hsel;
             const float* bb = p.bias + j0 + 4 * hsel;
             Half4 h{__floats2half2_rn(fminf(fmaxf(vv[0] + __ldg(bb + 0), 0.f), 1.f), fminf(fmaxf(vv[1] + __ldg(bb + 1), 0.f), 1.f)),
