@@ -44,10 +44,11 @@ W2X_API int w2x_run_swin_lnlinear(int device, long long tokens, int c, const uin
                                   const uint16_t* w, const float* bias, uint16_t* out, int reps, float* ms_out);
 
 /* The fused attention half of a SwinUNet block (kernels/swin_attn_sm100.cu; replaces a slice of the engine enqueued at img2img_infer.cpp:80):
- * x[n][h][w][c] (NHWC fp16 bits, updated in place) += proj(window attention(LayerNorm(x))) with 6x6 windows, cyclic shift `shift` (0 or 3),
- * relative-position bias relpos[heads][36][36] and torchvision's shift mask; c = 96, heads = 6, h and w multiples of 6.  wqkv = [3c][c]
- * (rows q | k | v, head-major), wproj = [c][c] fp16 bits (K-major), bqkv [3c], bproj [c], gamma / beta [c].  ms_out (optional) receives the
- * average device time of `reps` further launches on the same buffer.  Returns 1 on success. */
+ * 6x6 windows, cyclic shift `shift` (0 or 3), relative-position bias relpos[heads][36][36] and torchvision's shift mask; heads = 6, h and w
+ * multiples of 6.  c = 96: x[n][h][w][c] (NHWC fp16 bits, updated in place) += proj(window attention(LayerNorm(x))); c = 192: x receives
+ * window attention(LayerNorm(x)), the kernel's output before the projection (wproj / bproj may be NULL).  wqkv = [3c][c] (rows q | k | v,
+ * head-major), wproj = [c][c] fp16 bits (K-major), bqkv [3c], bproj [c], gamma / beta [c].  ms_out (optional) receives the average device
+ * time of `reps` further launches on the same buffers.  Returns 1 on success. */
 W2X_API int w2x_run_swin_attn(int device, int n, int h, int w, int c, int heads, int shift, uint16_t* x, const float* gamma, const float* beta, float eps,
                               const uint16_t* wqkv, const float* bqkv, const uint16_t* wproj, const float* bproj, const float* relpos, int reps, float* ms_out);
 

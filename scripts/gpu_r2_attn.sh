@@ -7,9 +7,9 @@ import sys
 sys.path.insert(0, 'waifu2x-tensorrt_b200'); sys.path.insert(0, 'tests')
 import w2x
 from test_gpu_swin_attn import make_case
-for n, h, w in [(4, 240, 240), (4, 120, 120)]:
-    case = make_case(n, h, w, 3)
+for c, n, h, w in [(96, 4, 240, 240), (192, 4, 120, 120), (192, 4, 60, 60)]:
+    case = make_case(n, h, w, 3, c)
     for shift in (0, 3):
         out, ms = w2x.run_swin_attn(*case, shift=shift, reps=50)
-        print('fused attention c=96 shift=%d, %d tokens: %.4f ms per launch' % (shift, n * h * w, ms), flush=True)
+        print('fused attention c=%d shift=%d, %d tokens: %.4f ms per launch' % (c, shift, n * h * w, ms), flush=True)
 PY

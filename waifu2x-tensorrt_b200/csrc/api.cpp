@@ -364,12 +364,14 @@ int w2x_run_swin_lnlinear(int device, long long tokens, int c, const uint16_t* x
 
 int w2x_run_swin_attn(int device, int n, int h, int w, int c, int heads, int shift, uint16_t* x, const float* gamma, const float* beta, float eps, const uint16_t* wqkv,
                       const float* bqkv, const uint16_t* wproj, const float* bproj, const float* relpos, int reps, float* ms_out) {
-    void* bufs[8] = {};
+    void* bufs[9] = {};
     SwinAttnPlan* plan = nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     int ok = 0;
     try {
-        if (n < 1 || !x || !gamma || !beta || !wqkv || !bqkv || !wproj || !bproj || !relpos || !swinAttnSupported(c, heads, 6, h, w)) throw Error("invalid argument");
+        if (n < 1 || !x || !gamma || !beta || !wqkv || !bqkv || !relpos || !swinAttnSupported(c, heads, 6, h, w)) throw Error("invalid argument");
+        const bool fuseProj = swinAttnFusesProj(c);
+        if (fuseProj && (!wproj || !bproj)) throw Error("invalid argument");
         W2X_CUDA(cudaSetDevice(device));
         std::vector<uint16_t> wR;
         std::vector<float> bR, relR;
@@ -378,15 +380,20 @@ int w2x_run_swin_attn(int device, int n, int h, int w, int c, int heads, int shi
         const size_t sizes[8] = {(size_t)n * h * w * C * 2, C * 4, C * 4, wR.size() * 2, bR.size() * 4, C * C * 2, C * 4, relR.size() * 4};
         const void* host[8] = {x, gamma, beta, wR.data(), bR.data(), wproj, bproj, relR.data()};
         for (int i = 0; i < 8; ++i) {
+            if (!host[i]) continue;   // wproj / bproj of the variant that stops at the attention output
             W2X_CUDA(cudaMalloc(&bufs[i], sizes[i]));
             W2X_CUDA(cudaMemcpy(bufs[i], host[i], sizes[i], cudaMemcpyHostToDevice));
         }
+        if (!fuseProj) {
+            W2X_CUDA(cudaMalloc(&bufs[8], sizes[0]));
+            W2X_CUDA(cudaMemset(bufs[8], 0, sizes[0]));
+        }
         W2X_CUDA(cudaDeviceSynchronize());
         plan = swinAttnCreatePlan((__half*)bufs[0], n, h, w, c, heads, 6, shift, (const float*)bufs[1], (const float*)bufs[2], eps, (const __half*)bufs[3],
-                                  (const float*)bufs[4], (const __half*)bufs[5], (const float*)bufs[6], (const float*)bufs[7]);
+                                  (const float*)bufs[4], (const __half*)bufs[5], (const float*)bufs[6], (const float*)bufs[7], (__half*)bufs[8]);
         swinAttnLaunch(plan, nullptr, n);
         W2X_CUDA(cudaDeviceSynchronize());
-        W2X_CUDA(cudaMemcpy(x, bufs[0], sizes[0], cudaMemcpyDeviceToHost));
+        W2X_CUDA(cudaMemcpy(x, fuseProj ? bufs[0] : bufs[8], sizes[0], cudaMemcpyDeviceToHost));
         if (ms_out && reps > 0) {
             W2X_CUDA(cudaEventCreate(&e0));
             W2X_CUDA(cudaEventCreate(&e1));

@@ -590,7 +590,9 @@ void Engine::buildPlanSwin() {
         const bool fuseAttn = !useDirect && !devEnv("W2X_NO_ATTN_FUSE") && swinAttnSupported(c, (int)AT.heads, (int)AT.window, h, w) && (int)QK.npad == 3 * c &&
                               (int)QK.ktot == c && (int)PJ.npad == c && (int)PJ.ktot == c && AT.relpos.size() == (size_t)AT.heads * 36 * 36;
         if (fuseAttn) {
-            // x += proj(window attention(LayerNorm(x))) in ONE kernel: normalised rows, Q / K / V, scores and probabilities stay on the SM
+            // c = 96: x += proj(window attention(LayerNorm(x))) in ONE kernel (normalised rows, Q / K / V, scores and probabilities stay on the
+            // SM); c = 192: the same kernel up to the attention output, then the Linear kernel for proj + residual
+            const bool fuseProj = swinAttnFusesProj(c);
             keepW.emplace_back();
             keepF.emplace_back();
             keepF.emplace_back();
@@ -601,21 +603,33 @@ void Engine::buildPlanSwin() {
             uploadAsync(dWr, wR.data(), wR.size() * 2);
             float* dBr = uploadF(bR);
             float* dRel = uploadF(relR);
-            for (size_t i : {n1, qk, at}) {
+            for (size_t i : {n1, qk}) {
                 LayerExec S;
                 S.name = model.layers[i].name;
                 S.impl = IMPL_SKIP;
                 layers.push_back(S);
             }
             LayerExec E;
-            E.name = PJ.name;
             E.impl = IMPL_SWIN_ATTN;
             E.tokN = x.n; E.tokH = h; E.tokW = w; E.tokC = c;
             E.heads = (int)AT.heads; E.window = (int)AT.window; E.shift = blockShift;
-            E.flops = 2.0 * h * w * ((double)QK.npad * QK.ktot + (double)PJ.npad * PJ.ktot) + 4.0 * (h / 6) * (w / 6) * 36.0 * 36.0 * c;
-            E.attn = swinAttnCreatePlan(x.p, x.n, h, w, c, (int)AT.heads, (int)AT.window, blockShift, dAux0[n1], dAux1[n1], model.layers[n1].eps, dWr, dBr, dW[pj],
-                                        dBias[pj], dRel);
-            layers.push_back(E);
+            const double flopsQkvAttn = 2.0 * h * w * (double)QK.npad * QK.ktot + 4.0 * (h / 6) * (w / 6) * 36.0 * 36.0 * c;
+            E.attn = swinAttnCreatePlan(x.p, x.n, h, w, c, (int)AT.heads, (int)AT.window, blockShift, dAux0[n1], dAux1[n1], model.layers[n1].eps, dWr, dBr,
+                                        fuseProj ? dW[pj] : nullptr, fuseProj ? dBias[pj] : nullptr, dRel, fuseProj ? nullptr : att.p);
+            if (fuseProj) {
+                LayerExec S;
+                S.name = AT.name;
+                S.impl = IMPL_SKIP;
+                layers.push_back(S);
+                E.name = PJ.name;
+                E.flops = flopsQkvAttn + 2.0 * h * w * (double)PJ.npad * PJ.ktot;
+                layers.push_back(E);
+            } else {
+                E.name = AT.name;
+                E.flops = flopsQkvAttn;
+                layers.push_back(E);
+                linear(pj, att, x, ACT_LRELU, &x);   // x += proj(attn)
+            }
         } else if (kFuseLnQkv && !useDirect && !devEnv("W2X_NO_MLP_FUSE") && swinLnLinearSupported(c, (int)QK.npad) && (int)QK.ktot == c) {
             // qkv = LayerNorm(x) Wqkv^T + b in ONE kernel: the normalised rows stay in shared memory
             LayerExec S;

@@ -205,8 +205,9 @@ struct SwinAttnPlan;                                              // fused LN + 
 bool swinAttnSupported(int c, int heads, int window, int h, int w);
 void swinAttnPrepare(const uint16_t* wqkv, const float* bqkv, const float* relpos, int c, int heads, std::vector<uint16_t>& wOut, std::vector<float>& bOut,
                      std::vector<float>& relOut);
+bool swinAttnFusesProj(int c);                                    // c = 96: proj + residual inside the kernel (x in place); c = 192: attention output to `out`
 SwinAttnPlan* swinAttnCreatePlan(__half* x, int n, int h, int w, int c, int heads, int window, int shift, const float* gamma, const float* beta, float eps,
-                                 const __half* wqkvR, const float* bqkvR, const __half* wproj, const float* bproj, const float* relposR);
+                                 const __half* wqkvR, const float* bqkvR, const __half* wproj, const float* bproj, const float* relposR, __half* out);
 void swinAttnDestroyPlan(SwinAttnPlan* plan);
 void swinAttnLaunch(const SwinAttnPlan* plan, cudaStream_t s, int nImages);
 const char* swinAttnDescribe(const SwinAttnPlan* plan, char* buf, int cap);

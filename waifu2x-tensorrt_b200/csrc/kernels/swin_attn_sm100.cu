@@ -48,43 +48,60 @@ using namespace sm100;
 using namespace swintok;
 namespace {
 
-constexpr int kC = 96;                 // token width
-constexpr int kHeads = 6, kHD = 16;    // head dim 16: a 32-channel chunk is a pair of heads
-constexpr int kChunks = kC / 32;
+constexpr int kHeads = 6;
 constexpr int kWin = 6, kNT = 36;      // window side, tokens per window
 constexpr int kWinTile = 3;            // windows per tile
 constexpr int kKeyStride = 40;         // key index of window w, position p: 40 w + p (a window starts at a 16-byte chunk of a P row)
 constexpr int kBiasPitch = 44;         // floats per bias-table row: 16-byte loads of 8 consecutive rows hit distinct banks
 constexpr uint32_t kBiasHead = kNT * kBiasPitch * 4;
+constexpr uint32_t kBiasBytes = kHeads * kBiasHead;
 constexpr int kRowWarp0 = 4, kRowWarps = 4, kSmWarps = 6, kIssuerA = 12, kIssuerB = 15;
 constexpr int kAttnThreads = 32 * 16;
+constexpr uint32_t kWqkvChunk = 96 * 64;               // the 96 rows (q32 | k32 | v32) of one channel chunk, one 32-wide K chunk: [96][32 k] fp16
+constexpr uint32_t kVBuf = 2 * 32 * 128;               // V^T: two 64-key chunks of [32 dims][64 keys] fp16, SWIZZLE_128B
+constexpr uint32_t kPChunk = kRows * 128;              // [128 rows][64 keys]
 
 // barriers (byte offsets from the 1024-aligned base)
 constexpr uint32_t bW = 0, bAFull = 8, bAEmpty = 16, bD1Full = 24, bQKFull = 32, bQKEmpty = 40, bVEmpty = 48, bSFull = 64, bSEmpty = 80, bPFull = 96, bPEmpty = 104,
-                   bOFull = 112, bOEmpty = 128, bOcFull = 144, bOcEmpty = 152, bD2Full = 160, bD2Empty = 168, kTmemSlot = 176;
-constexpr uint32_t kOffBqkv = 256, kOffBproj = kOffBqkv + 3 * kC * 4, kOffGamma = kOffBproj + kC * 4, kOffBeta = kOffGamma + kC * 4;
-constexpr uint32_t kWqkvKa = 3 * kC * 64;              // one 32-wide K chunk of W': [288 rows][32 k] fp16, SWIZZLE_64B
-constexpr uint32_t kWqkvChunk = 96 * 64;               // the 96 rows (q32 | k32 | v32) of one channel chunk inside it
-constexpr uint32_t kWprojKa = kC * 64;                 // [96 rows][32 k]
-constexpr uint32_t kOffWqkv = 4096;
-constexpr uint32_t kOffWproj = kOffWqkv + kChunks * kWqkvKa;
-constexpr uint32_t kOffBias = kOffWproj + kChunks * kWprojKa;
-constexpr uint32_t kBiasBytes = kHeads * kBiasHead;
-constexpr uint32_t kOffA = (kOffBias + kBiasBytes + 1023u) & ~1023u;
-constexpr uint32_t kOffQ = kOffA + kChunks * kAChunk;
-constexpr uint32_t kOffK = kOffQ + kAChunk;
-constexpr uint32_t kVBuf = 2 * 32 * 128;               // V^T: two 64-key chunks of [32 dims][64 keys] fp16, SWIZZLE_128B
-constexpr uint32_t kOffV = kOffK + kAChunk;
-constexpr uint32_t kPChunk = kRows * 128;              // [128 rows][64 keys]
-constexpr uint32_t kOffP = kOffV + 2 * kVBuf;
-constexpr uint32_t kOffOc = kOffP + 2 * kPChunk;
-constexpr uint32_t kAttnSmem = kOffOc + kAChunk + 1024;   // + alignment slack
-static_assert(kOffBeta + kC * 4 <= kOffWqkv, "constants overflow the header");
-static_assert(kOffWproj % 1024 == 0 && kOffA % 1024 == 0 && kOffV % 1024 == 0 && kOffP % 1024 == 0 && kOffOc % 1024 == 0, "swizzled operands need 1024-byte alignment");
-static_assert(kBiasBytes % 16 == 0 && kOffBias % 16 == 0, "bulk copy granularity");
-static_assert(kAttnSmem <= 227 * 1024, "shared memory budget");
-// TMEM columns
-constexpr uint32_t tD1 = 0, tD2 = 96, tS = 192, tO = 448, kTmemCols = 512;
+                   bOFull = 112, bOEmpty = 128, bOcFull = 144, bOcEmpty = 152, bD2Full = 160, bD2Empty = 168, kTmemSlot = 176, bWFull = 184, bWEmpty = 200, bD1Full2 = 216, bD1Empty = 224;
+
+// Two instantiations:
+//   C = 96  (levels 1 / 5, head dim 16: a 32-channel chunk is a PAIR of heads): everything above, all weights resident;
+//   C = 192 (levels 2 - 4, head dim 32: a chunk is one head): the 221 KB of Wqkv' stream through a two-stage TMA ring (one 36 KB chunk per
+//           stage, issued by issuer A one chunk ahead), and the kernel ends at the attention output (fp16, written to `out` by the row
+//           warps): Wproj and a 192-column accumulator do not fit next to the ring, the output projection stays on the Linear kernel.
+template <int C>
+struct ACfg {
+    static constexpr int kC = C;
+    static constexpr int kHD = C / kHeads;            // 16 | 32
+    static constexpr int kHPC = 32 / kHD;             // heads per 32-channel chunk
+    static constexpr int kChunks = C / 32;            // channel chunks of Q / K / V = K chunks of the LayerNorm rows
+    static constexpr bool kProj = C == 96;            // output projection + residual inside the kernel
+    static constexpr bool kResident = C == 96;        // Wqkv' resident (else streamed per chunk)
+    static constexpr uint32_t kOffBqkv = 256, kOffBproj = kOffBqkv + 3 * C * 4, kOffGamma = kOffBproj + (kProj ? C * 4 : 0), kOffBeta = kOffGamma + C * 4;
+    static constexpr uint32_t kWqkvKa = 3 * C * 64;           // resident: one 32-wide K chunk of W': [3C rows][32 k] fp16, SWIZZLE_64B
+    static constexpr uint32_t kStage = kChunks * kWqkvChunk;  // streamed: the chunk's 96 rows, all K chunks
+    static constexpr uint32_t kWprojKa = C * 64;              // [C rows][32 k]
+    static constexpr uint32_t kOffWqkv = 4096;
+    static constexpr uint32_t kOffWproj = kOffWqkv + (kResident ? kChunks * kWqkvKa : 2 * kStage);
+    static constexpr uint32_t kOffBias = kOffWproj + (kProj ? kChunks * kWprojKa : 0);
+    static constexpr uint32_t kOffA = (kOffBias + kBiasBytes + 1023u) & ~1023u;
+    static constexpr uint32_t kOffQ = kOffA + kChunks * kAChunk;
+    static constexpr uint32_t kOffK = kOffQ + kAChunk;
+    static constexpr uint32_t kOffV = kOffK + kAChunk;
+    static constexpr uint32_t kOffP = kOffV + 2 * kVBuf;
+    static constexpr uint32_t kOffOc = kOffP + 2 * kPChunk;
+    static constexpr uint32_t kZeroEnd = kOffOc + (kProj ? kAChunk : 0);
+    static constexpr uint32_t kSmem = kZeroEnd + 1024;   // + alignment slack
+    // TMEM columns
+    static constexpr int kD1Bufs = kProj ? 1 : 2;     // QKV accumulators: the second one takes the columns of the proj accumulator
+    static constexpr uint32_t tD1 = 0, tD2 = 96, tS = 192, tO = tS + 256, kTmemCols = 512;
+    static_assert(kOffBeta + C * 4 <= kOffWqkv, "constants overflow the header");
+    static_assert(kOffWproj % 1024 == 0 && kOffA % 1024 == 0 && kOffV % 1024 == 0 && kOffP % 1024 == 0 && kOffOc % 1024 == 0, "swizzled operands need 1024-byte alignment");
+    static_assert(kBiasBytes % 16 == 0 && kOffBias % 16 == 0, "bulk copy granularity");
+    static_assert(kSmem <= 227 * 1024, "shared memory budget");
+    static_assert(tO + 64 <= kTmemCols, "tensor memory budget");
+};
 
 struct AttnArgs {
     CUtensorMap tmWqkv, tmWproj;
@@ -94,6 +111,7 @@ struct AttnArgs {
     const float* gamma;      // [C]
     const float* beta;       // [C]
     const float* relpos;     // [heads][36][kBiasPitch] fp32, multiplied by log2 e
+    __half* out;             // C = 192 only: attention output [n][h][w][C] (before the output projection)
     float eps;
     int h, w, shiftY, shiftX;   // cyclic shift per dimension (torchvision drops it in a dimension the window covers)
     int nwx, nwy;            // windows per row / column of an image
@@ -142,7 +160,14 @@ struct WindowTokens {
 };
 
 // 16 warps x 128 registers: the whole register file
+template <int C>
 __global__ void __launch_bounds__(kAttnThreads, 1) swin_attn_kernel(const __grid_constant__ AttnArgs a) {
+    using F = ACfg<C>;
+    constexpr int kC = F::kC, kHD = F::kHD, kHPC = F::kHPC, kChunks = F::kChunks;
+    constexpr uint32_t kOffBqkv = F::kOffBqkv, kOffBproj = F::kOffBproj, kOffGamma = F::kOffGamma, kOffBeta = F::kOffBeta, kWqkvKa = F::kWqkvKa, kWprojKa = F::kWprojKa,
+                       kOffWqkv = F::kOffWqkv, kOffWproj = F::kOffWproj, kOffBias = F::kOffBias, kOffA = F::kOffA, kOffQ = F::kOffQ, kOffK = F::kOffK, kOffV = F::kOffV,
+                       kOffP = F::kOffP, kOffOc = F::kOffOc, tD1 = F::tD1, tD2 = F::tD2, tS = F::tS, tO = F::tO, kTmemCols = F::kTmemCols, kStage = F::kStage;
+    (void)kOffBproj; (void)kWqkvKa; (void)kWprojKa; (void)kOffWproj; (void)kOffOc; (void)tD2; (void)kStage; (void)kHPC;
     extern __shared__ uint8_t smemRaw[];
     const uint32_t base = (smemU32(smemRaw) + 1023u) & ~1023u;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -154,6 +179,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) swin_attn_kernel(const __grid
         mbarInit(base + bAFull, 4);
         mbarInit(base + bAEmpty, 1);
         mbarInit(base + bD1Full, 1);
+        mbarInit(base + bD1Full2, 1);
         mbarInit(base + bQKFull, kRowWarps);
         mbarInit(base + bQKEmpty, 1);
         mbarInit(base + bPFull, kSmWarps);
@@ -168,20 +194,23 @@ __global__ void __launch_bounds__(kAttnThreads, 1) swin_attn_kernel(const __grid
             mbarInit(base + bSEmpty + 8u * i, kSmWarps);
             mbarInit(base + bOFull + 8u * i, 1);
             mbarInit(base + bOEmpty + 8u * i, kRowWarps);
+            mbarInit(base + bWFull + 8u * i, 1);
+            mbarInit(base + bWEmpty + 8u * i, 1);
+            mbarInit(base + bD1Empty + 8u * i, kRowWarps);
         }
         mbarInitFence();
         tmaPrefetchDesc(&a.tmWqkv);
-        tmaPrefetchDesc(&a.tmWproj);
+        if constexpr (F::kProj) tmaPrefetchDesc(&a.tmWproj);
     }
     for (int i = threadIdx.x; i < 3 * kC; i += kAttnThreads) stsF32(base + kOffBqkv + 4u * i, a.bqkv[i]);
     for (int i = threadIdx.x; i < kC; i += kAttnThreads) {
-        stsF32(base + kOffBproj + 4u * i, a.bproj[i]);
+        if constexpr (F::kProj) stsF32(base + kOffBproj + 4u * i, a.bproj[i]);
         stsF32(base + kOffGamma + 4u * i, a.gamma[i]);
         stsF32(base + kOffBeta + 4u * i, a.beta[i]);
     }
     // Q / K / V / P / Oc start as zeros: padding keys (K rows and V^T columns nobody writes) must be finite, and the off-diagonal
     // blocks of P (rows of one window x keys of another) are never written
-    for (uint32_t o = (uint32_t)threadIdx.x * 16u; o < kOffOc + kAChunk - kOffQ; o += (uint32_t)kAttnThreads * 16u) stsV4(base + kOffQ + o, make_uint4(0, 0, 0, 0));
+    for (uint32_t o = (uint32_t)threadIdx.x * 16u; o < F::kZeroEnd - kOffQ; o += (uint32_t)kAttnThreads * 16u) stsV4(base + kOffQ + o, make_uint4(0, 0, 0, 0));
     fenceProxyAsync();
     if (warp == kIssuerA) tmemAlloc(base + kTmemSlot, kTmemCols);
     tcFenceBefore();
@@ -190,17 +219,21 @@ __global__ void __launch_bounds__(kAttnThreads, 1) swin_attn_kernel(const __grid
     uint32_t tmemBase;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmemBase) : "r"(base + kTmemSlot));
     if (warp == kIssuerA && lane == 0) {
-        mbarExpectTx(base + bW, kChunks * kWqkvKa + kChunks * kWprojKa + kBiasBytes);
-        for (int ka = 0; ka < kChunks; ++ka) {
-            for (int c = 0; c < kChunks; ++c) tmaLoad2d(base + kOffWqkv + ka * kWqkvKa + c * kWqkvChunk, &a.tmWqkv, base + bW, ka * 32, c * 96);
-            tmaLoad2d(base + kOffWproj + ka * kWprojKa, &a.tmWproj, base + bW, ka * 32, 0);
+        if constexpr (F::kResident) {
+            mbarExpectTx(base + bW, kChunks * kWqkvKa + kChunks * kWprojKa + kBiasBytes);
+            for (int ka = 0; ka < kChunks; ++ka) {
+                for (int c = 0; c < kChunks; ++c) tmaLoad2d(base + kOffWqkv + ka * kWqkvKa + c * kWqkvChunk, &a.tmWqkv, base + bW, ka * 32, c * 96);
+                tmaLoad2d(base + kOffWproj + ka * kWprojKa, &a.tmWproj, base + bW, ka * 32, 0);
+            }
+        } else {
+            mbarExpectTx(base + bW, kBiasBytes);
         }
         bulkLoad1d(base + kOffBias, a.relpos, kBiasBytes, base + bW);
     }
     const long long tiles = (a.windows + kWinTile - 1) / kWinTile;
     const int first = blockIdx.x, step = gridDim.x;
     const int nMine = first < tiles ? (int)((tiles - first + step - 1) / step) : 0;
-    const int G = nMine * kChunks;   // this CTA's chunk sequence: g = 3 k + c; heads j = 2 g, 2 g + 1
+    const int G = nMine * kChunks;   // this CTA's chunk sequence: g = kChunks k + c; heads j = kHPC g + h
     const WindowTokens tokens{a.h, a.w, a.shiftY, a.shiftX, a.nwx, a.nwy, a.windows, first, step};
 
     const uint32_t hi64 = descHi(512u, 4u), hi128 = descHi(1024u, 2u);
@@ -211,7 +244,8 @@ __global__ void __launch_bounds__(kAttnThreads, 1) swin_attn_kernel(const __grid
         const int row = quarter * 32 + lane;
         const uint32_t taddrLane = tmemBase + ((uint32_t)(quarter * 32) << 16);
         uint32_t r[32], r2[32];
-        auto e3 = [&](int k) {   // x += D2 + bproj, 48 columns at a time
+        (void)row; (void)taddrLane; (void)r; (void)r2;
+        [[maybe_unused]] auto e3 = [&](int k) {   // x += D2 + bproj, 48 columns at a time
             const long long tok = tokens(k, row);
             __half* xrow = a.x + (tok >= 0 ? tok : 0) * kC;
             uint4 res[6];
@@ -264,15 +298,19 @@ __global__ void __launch_bounds__(kAttnThreads, 1) swin_attn_kernel(const __grid
         };
         // tile k's rows are handed over while tile k - 1 is being processed; tile k - 2's accumulator is complete (or about to be) by then,
         // so the write-back never holds up the next tile's loads
-        lnProducerLoop<kC, 1>(a.x, a.eps, tokens, base, kOffA, kOffGamma, kOffBeta, base + bAFull, base + bAEmpty, nMine, 0, 1, [&](int k) {
-            if (k >= 2) e3(k - 2);
-        });
-        if (nMine >= 2) e3(nMine - 2);
-        if (nMine >= 1) e3(nMine - 1);
+        if constexpr (F::kProj) {
+            lnProducerLoop<kC, 1>(a.x, a.eps, tokens, base, kOffA, kOffGamma, kOffBeta, base + bAFull, base + bAEmpty, nMine, 0, 1, [&](int k) {
+                if (k >= 2) e3(k - 2);
+            });
+            if (nMine >= 2) e3(nMine - 2);
+            if (nMine >= 1) e3(nMine - 1);
+        } else {
+            lnProducerLoop<kC, 1>(a.x, a.eps, tokens, base, kOffA, kOffGamma, kOffBeta, base + bAFull, base + bAEmpty, nMine);
+        }
     } else if (warp == kIssuerA) {
         // ---- issuer A: QKV(g) and proj(g - 3), in the order the row warps produce their inputs ----
         const uint32_t idQkv = instrDescF16(kRows, 96), idProj = instrDescF16(kRows, kC);
-        auto proj = [&](int g) {   // D2 += Oc x Wproj[:, chunk]^T
+        [[maybe_unused]] auto proj = [&](int g) {   // D2 += Oc x Wproj[:, chunk]^T
             const int k = g / kChunks, c = g - k * kChunks;
             mbarWait(base + bOcFull, (uint32_t)g & 1u);
             if (c == 0) mbarWait(base + bD2Empty, ((uint32_t)k & 1u) ^ 1u);
@@ -286,68 +324,102 @@ __global__ void __launch_bounds__(kAttnThreads, 1) swin_attn_kernel(const __grid
             }
             __syncwarp();
         };
-        mbarWait(base + bW, 0);
+        // streamed weights: the chunk's rows [96][C] of W' (kChunks boxes of 32 k) into ring stage g & 1; the stage was last read by QKV(g - 2)
+        auto loadChunk = [&](int g) {
+            const int st = g & 1, c = g % kChunks;
+            mbarWait(base + bWEmpty + 8u * st, ((uint32_t)(g >> 1) & 1u) ^ 1u);
+            if (lane == 0) {
+                const uint32_t full = base + bWFull + 8u * st, dst = base + kOffWqkv + (uint32_t)st * kStage;
+                mbarExpectTx(full, kStage);
+                for (int ka = 0; ka < kChunks; ++ka) tmaLoad2d(dst + (uint32_t)ka * kWqkvChunk, &a.tmWqkv, full, ka * 32, c * 96);
+            }
+            __syncwarp();
+        };
+        if constexpr (F::kResident) mbarWait(base + bW, 0);
+        else if (G > 0) loadChunk(0);
         for (int g = 0; g < G; ++g) {
             const int k = g / kChunks, c = g - k * kChunks;
-            if (g >= 1) mbarWait(base + bQKFull, (uint32_t)(g - 1) & 1u);   // E1 of the previous chunk has drained D1
+            const int d = g % F::kD1Bufs;   // accumulator buffer
+            if constexpr (F::kD1Bufs == 1) {
+                if (g >= 1) mbarWait(base + bQKFull, (uint32_t)(g - 1) & 1u);   // E1 of the previous chunk has drained D1
+            } else {
+                mbarWait(base + bD1Empty + 8u * d, ((uint32_t)(g >> 1) & 1u) ^ 1u);   // E1 of chunk g - 2 has drained this accumulator
+            }
+            if constexpr (!F::kResident) mbarWait(base + bWFull + 8u * (g & 1), (uint32_t)(g >> 1) & 1u);
             if (c == 0) mbarWait(base + bAFull, (uint32_t)k & 1u);
             tcFenceAfter();
             if (electOne()) {
+                const uint32_t wBase = F::kResident ? base + kOffWqkv + c * kWqkvChunk : base + kOffWqkv + (uint32_t)(g & 1) * kStage;
+                const uint32_t wKa = F::kResident ? kWqkvKa : kWqkvChunk;
 #pragma unroll
                 for (int ka = 0; ka < kChunks; ++ka)
 #pragma unroll
                     for (int ks = 0; ks < 2; ++ks)
-                        ummaLoHi(tmemBase + tD1, descLo(base + kOffA + ka * kAChunk + ks * 32u), hi64, descLo(base + kOffWqkv + ka * kWqkvKa + c * kWqkvChunk + ks * 32u), hi64,
-                                 idQkv, (ka | ks) != 0 ? 1u : 0u);
-                tcCommit(base + bD1Full);
+                        ummaLoHi(tmemBase + tD1 + 96u * d, descLo(base + kOffA + ka * kAChunk + ks * 32u), hi64, descLo(wBase + ka * wKa + ks * 32u), hi64, idQkv,
+                                 (ka | ks) != 0 ? 1u : 0u);
+                tcCommit(base + (d == 0 ? bD1Full : bD1Full2));
+                if constexpr (!F::kResident) tcCommit(base + bWEmpty + 8u * (g & 1));
                 if (c == kChunks - 1) tcCommit(base + bAEmpty);   // the tile's normalised rows are no longer needed
             }
             __syncwarp();
-            if (g >= 3) proj(g - 3);   // its Oc tile was written an iteration ago: never blocks the next QKV
+            if constexpr (!F::kResident) {
+                if (g + 1 < G) loadChunk(g + 1);   // waits for QKV(g - 1), queued one iteration ago, to release the other ring stage
+            }
+            if constexpr (F::kProj) {
+                if (g >= 3) proj(g - 3);   // its Oc tile was written an iteration ago: never blocks the next QKV
+            }
         }
-        for (int g = G > 3 ? G - 3 : 0; g < G; ++g) proj(g);
+        if constexpr (F::kProj) {
+            for (int g = G > 3 ? G - 3 : 0; g < G; ++g) proj(g);
+        }
     } else if (warp == kIssuerB) {
         // ---- issuer B: S(2g), S(2g + 1) of the chunk the row warps just converted, interleaved with PV of the previous chunk ----
         const uint32_t idS = instrDescF16(kRows, 128), idPv = instrDescF16(kRows, kHD);
-        auto scores = [&](int j) {   // S[j & 1] = Q_h K_h^T for head j & 1 of the pair in the Q / K buffers
-            const int b = j & 1, g = j >> 1;
-            mbarWait(base + bSEmpty + 8u * b, ((uint32_t)g & 1u) ^ 1u);
+        auto scores = [&](int j) {   // S[j & 1] = Q_h K_h^T for head j (head j % kHPC of the chunk in the Q / K buffers)
+            const int sb = j & 1, hh = j % kHPC;
+            mbarWait(base + bSEmpty + 8u * sb, ((uint32_t)(j >> 1) & 1u) ^ 1u);
             tcFenceAfter();
             if (electOne()) {
-                ummaLoHi(tmemBase + tS + 128u * b, descLo(base + kOffQ + 32u * b), hi64, descLo(base + kOffK + 32u * b), hi64, idS, 0u);
-                tcCommit(base + bSFull + 8u * b);
-                if (b == 1) tcCommit(base + bQKEmpty);
+#pragma unroll
+                for (int ks = 0; ks < kHD / 16; ++ks)
+                    ummaLoHi(tmemBase + tS + 128u * sb, descLo(base + kOffQ + 32u * (hh + ks)), hi64, descLo(base + kOffK + 32u * (hh + ks)), hi64, idS, ks != 0 ? 1u : 0u);
+                tcCommit(base + bSFull + 8u * sb);
+                if (hh == kHPC - 1) tcCommit(base + bQKEmpty);
             }
             __syncwarp();
         };
-        auto pv = [&](int j) {   // O[g & 1][16 b .. +16] = P V_h
-            const int b = j & 1, g = j >> 1, ob = g & 1;
+        auto pv = [&](int j) {   // O[g & 1][kHD hh .. +kHD] = P V_h
+            const int g = j / kHPC, hh = j - g * kHPC, ob = g & 1;
             mbarWait(base + bPFull, (uint32_t)j & 1u);
-            if (b == 0) mbarWait(base + bOEmpty + 8u * ob, ((uint32_t)(g >> 1) & 1u) ^ 1u);
+            if (hh == 0) mbarWait(base + bOEmpty + 8u * ob, ((uint32_t)(g >> 1) & 1u) ^ 1u);
             tcFenceAfter();
             if (electOne()) {
 #pragma unroll
                 for (int kc = 0; kc < 2; ++kc)
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks)
-                        ummaLoHi(tmemBase + tO + 32u * ob + 16u * b, descLo(base + kOffP + kc * kPChunk + ks * 32u), hi128,
-                                 descLo(base + kOffV + ob * kVBuf + kc * 4096u + b * 2048u + ks * 32u), hi128, idPv, (kc | ks) != 0 ? 1u : 0u);
+                        ummaLoHi(tmemBase + tO + 32u * ob + (uint32_t)(kHD * hh), descLo(base + kOffP + kc * kPChunk + ks * 32u), hi128,
+                                 descLo(base + kOffV + ob * kVBuf + kc * 4096u + (uint32_t)hh * (kHD * 128u) + ks * 32u), hi128, idPv, (kc | ks) != 0 ? 1u : 0u);
                 tcCommit(base + bPEmpty);
-                if (b == 1) {
+                if (hh == kHPC - 1) {
                     tcCommit(base + bOFull + 8u * ob);
                     tcCommit(base + bVEmpty + 8u * ob);
                 }
             }
             __syncwarp();
         };
+        // the scores of chunk g are queued BEFORE the PV MMAs of chunk g - 1: a softmax warp that finishes a head finds the next one ready
+        // instead of waiting for PV + S + two hand-offs (each scores() waits only until the previous head of its parity has been LOADED)
         for (int g = 0; g <= G; ++g) {
-            if (g >= 1) pv(2 * g - 2);
             if (g < G) {
                 mbarWait(base + bQKFull, (uint32_t)g & 1u);
-                scores(2 * g);
-                scores(2 * g + 1);   // waits only until the softmax warps have LOADED the previous head of this parity: frees Q / K early
+#pragma unroll
+                for (int hh = 0; hh < kHPC; ++hh) scores(g * kHPC + hh);
             }
-            if (g >= 1) pv(2 * g - 1);
+            if (g >= 1) {
+#pragma unroll
+                for (int hh = 0; hh < kHPC; ++hh) pv((g - 1) * kHPC + hh);
+            }
         }
     } else if (warp < kRowWarp0 + kRowWarps) {
         // ---- row warps: thread = tile row ----
@@ -373,10 +445,12 @@ __global__ void __launch_bounds__(kAttnThreads, 1) swin_attn_kernel(const __grid
         auto e1 = [&](int g) {   // D1 (+ bias) -> Q / K / V^T operands
             const int c = g % kChunks, vb = g & 1;
             const uint32_t bOff = base + kOffBqkv + 4u * (uint32_t)(c * 96);
-            mbarWait(base + bD1Full, (uint32_t)g & 1u);
+            const int d = g % F::kD1Bufs;
+            const uint32_t tAcc = taddrLane + tD1 + 96u * (uint32_t)d;
+            mbarWait(base + (d == 0 ? bD1Full : bD1Full2), (uint32_t)(g / F::kD1Bufs) & 1u);
             tcFenceAfter();
-            tmemLd32(taddrLane + tD1, r);          // Q columns
-            tmemLd32(taddrLane + tD1 + 32u, r2);   // K columns
+            tmemLd32(tAcc, r);          // Q columns
+            tmemLd32(tAcc + 32u, r2);   // K columns
             tmemLdWait();
             mbarWait(base + bQKEmpty, ((uint32_t)g & 1u) ^ 1u);   // both S MMAs of the previous chunk have read Q / K
 #pragma unroll
@@ -385,8 +459,13 @@ __global__ void __launch_bounds__(kAttnThreads, 1) swin_attn_kernel(const __grid
 #pragma unroll
                 for (int q = 0; q < 4; ++q) stsV4(base + kOffK + (uint32_t)kidx * 64u + (((uint32_t)q ^ swKey) << 4), cvt8(&r2[8 * q], bOff + 128u + 32u * q));
             }
-            tmemLd32(taddrLane + tD1 + 64u, r);    // V columns (both heads)
+            tmemLd32(tAcc + 64u, r);    // V columns (both heads)
             tmemLdWait();
+            if constexpr (F::kD1Bufs == 2) {
+                tcFenceBefore();
+                __syncwarp();
+                if (lane == 0) mbarArrive(base + bD1Empty + 8u * d);   // the accumulator is in registers
+            }
             mbarWait(base + bVEmpty + 8u * vb, ((uint32_t)(g >> 1) & 1u) ^ 1u);   // both PV MMAs of chunk g - 2 have read this V buffer
             if (rowValid) {
                 // V^T[dim][key]: 2-byte stores; the lanes of a warp hold consecutive keys, so a store instruction covers 64 contiguous bytes
@@ -408,7 +487,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) swin_attn_kernel(const __grid
             __syncwarp();
             if (lane == 0) mbarArrive(base + bQKFull);
         };
-        auto e2 = [&](int g) {   // O -> fp16 -> Oc (A operand of proj); the probabilities were normalised by the softmax warps
+        auto e2 = [&](int g) {   // O -> fp16 -> Oc (A operand of proj) or `out`; the probabilities were normalised by the softmax warps
             const int ob = g & 1;
             mbarWait(base + bOFull + 8u * ob, (uint32_t)(g >> 1) & 1u);
             tcFenceAfter();
@@ -417,6 +496,23 @@ __global__ void __launch_bounds__(kAttnThreads, 1) swin_attn_kernel(const __grid
             tcFenceBefore();
             __syncwarp();
             if (lane == 0) mbarArrive(base + bOEmpty + 8u * ob);
+            if constexpr (!F::kProj) {
+                const int k = g / kChunks, c = g - k * kChunks;
+                const long long tok = tokens(k, row);
+                if (tok >= 0) {
+                    uint4* dst = reinterpret_cast<uint4*>(a.out + tok * kC + 32 * c);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        uint4 o;
+                        o.x = packH2(__uint_as_float(r2[8 * q]), __uint_as_float(r2[8 * q + 1]));
+                        o.y = packH2(__uint_as_float(r2[8 * q + 2]), __uint_as_float(r2[8 * q + 3]));
+                        o.z = packH2(__uint_as_float(r2[8 * q + 4]), __uint_as_float(r2[8 * q + 5]));
+                        o.w = packH2(__uint_as_float(r2[8 * q + 6]), __uint_as_float(r2[8 * q + 7]));
+                        dst[q] = o;
+                    }
+                }
+                return;
+            }
             mbarWait(base + bOcEmpty, ((uint32_t)g & 1u) ^ 1u);   // proj of the previous chunk has read Oc
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -473,10 +569,10 @@ __global__ void __launch_bounds__(kAttnThreads, 1) swin_attn_kernel(const __grid
             }
         };
         mbarWait(base + bW, 0);   // bias tables
-        for (int j = 0; j < 2 * G; ++j) {
-            const int b = j & 1, g = j >> 1;
-            if (b == 0 && g % kChunks == 0) setMask((long long)first + (long long)(g / kChunks) * step);
-            mbarWait(base + bSFull + 8u * b, (uint32_t)g & 1u);
+        for (int j = 0; j < kHPC * G; ++j) {
+            const int b = j & 1;   // score buffer
+            if (j % kHeads == 0) setMask((long long)first + (long long)(j / kHeads) * step);
+            mbarWait(base + bSFull + 8u * b, (uint32_t)(j >> 1) & 1u);
             tcFenceAfter();
             tmemLd32(taddrLane + tS + 128u * b + (uint32_t)(kKeyStride * passWin), r);
             tmemLd8(taddrLane + tS + 128u * b + (uint32_t)(kKeyStride * passWin) + 32u, s2);
@@ -484,7 +580,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) swin_attn_kernel(const __grid
             tcFenceBefore();
             __syncwarp();
             if (lane == 0) mbarArrive(base + bSEmpty + 8u * b);   // the scores are in registers: the next head of this parity may overwrite them
-            const int head = 2 * (g % kChunks) + b;
+            const int head = j % kHeads;
             const uint32_t bRow = base + kOffBias + (uint32_t)head * kBiasHead + (uint32_t)pq * (kBiasPitch * 4u);
             float v[kNT];
 #pragma unroll
@@ -551,11 +647,11 @@ __global__ void __launch_bounds__(kAttnThreads, 1) swin_attn_kernel(const __grid
 
 struct SwinAttnPlan {
     AttnArgs args;
-    int n = 0;
+    int n = 0, c = 0;
 };
 
 bool swinAttnSupported(int c, int heads, int window, int h, int w) {
-    return c == kC && heads == kHeads && window == kWin && h > 0 && w > 0 && h % kWin == 0 && w % kWin == 0;
+    return (c == 96 || c == 192) && heads == kHeads && window == kWin && h > 0 && w > 0 && h % kWin == 0 && w % kWin == 0;
 }
 
 // Host-side operand preparation (done once per block at plan time):
@@ -563,7 +659,7 @@ bool swinAttnSupported(int c, int heads, int window, int h, int w) {
 //   bOut [3C]: the bias in the same order and scale;  relOut [heads][36][44]: relative-position bias times log2(e), rows padded.
 void swinAttnPrepare(const uint16_t* wqkv, const float* bqkv, const float* relpos, int c, int heads, std::vector<uint16_t>& wOut, std::vector<float>& bOut,
                      std::vector<float>& relOut) {
-    if (c != kC || heads != kHeads) throw Error("swin attention: unsupported width");
+    if ((c != 96 && c != 192) || heads != kHeads) throw Error("swin attention: unsupported width");
     const float log2e = 1.4426950408889634f;
     const float qScale = log2e / std::sqrt((float)(c / heads));
     wOut.assign((size_t)3 * c * c, 0);
@@ -587,16 +683,24 @@ void swinAttnPrepare(const uint16_t* wqkv, const float* bqkv, const float* relpo
             for (int j = 0; j < kNT; ++j) relOut[((size_t)hd * kNT + p) * kBiasPitch + j] = relpos[((size_t)hd * kNT + p) * kNT + j] * log2e;
 }
 
-// All pointers are device memory: wqkvR / bqkvR / relposR as produced by swinAttnPrepare, wproj [C][C] fp16 K-major.
+// All pointers are device memory: wqkvR / bqkvR / relposR as produced by swinAttnPrepare.  c = 96: wproj [C][C] fp16 K-major and bproj, x is
+// updated in place (out unused); c = 192: the attention output goes to out [n][h][w][C] (wproj / bproj unused: swinAttnFusesProj).
+bool swinAttnFusesProj(int c) { return c == 96; }
+
 SwinAttnPlan* swinAttnCreatePlan(__half* x, int n, int h, int w, int c, int heads, int window, int shift, const float* gamma, const float* beta, float eps,
-                                 const __half* wqkvR, const float* bqkvR, const __half* wproj, const float* bproj, const float* relposR) {
+                                 const __half* wqkvR, const float* bqkvR, const __half* wproj, const float* bproj, const float* relposR, __half* out) {
     if (!swinAttnSupported(c, heads, window, h, w)) throw Error("swin attention: unsupported geometry");
-    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(wqkvR) | reinterpret_cast<uintptr_t>(wproj) | reinterpret_cast<uintptr_t>(relposR)) & 15)
+    const bool fuseProj = swinAttnFusesProj(c);
+    if (fuseProj ? (!wproj || !bproj) : !out) throw Error("swin attention: missing operand");
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(wqkvR) | reinterpret_cast<uintptr_t>(wproj) | reinterpret_cast<uintptr_t>(relposR) |
+         reinterpret_cast<uintptr_t>(out)) & 15)
         throw Error("swin attention: operands must be 16-byte aligned");
     SwinAttnPlan* plan = new SwinAttnPlan{};
+    plan->c = c;
     try {
         encodeMatrixMap2d(&plan->args.tmWqkv, wqkvR, c, 3 * c, 32, 96, false);
-        encodeMatrixMap2d(&plan->args.tmWproj, wproj, c, c, 32, c, false);
+        if (fuseProj) encodeMatrixMap2d(&plan->args.tmWproj, wproj, c, c, 32, c, false);
+        else plan->args.tmWproj = plan->args.tmWqkv;
     } catch (...) {
         delete plan;
         throw;
@@ -608,6 +712,7 @@ SwinAttnPlan* swinAttnCreatePlan(__half* x, int n, int h, int w, int c, int head
     a.gamma = gamma;
     a.beta = beta;
     a.relpos = relposR;
+    a.out = out;
     a.eps = eps;
     a.h = h;
     a.w = w;
@@ -624,8 +729,9 @@ SwinAttnPlan* swinAttnCreatePlan(__half* x, int n, int h, int w, int c, int head
 void swinAttnDestroyPlan(SwinAttnPlan* plan) { delete plan; }
 
 const char* swinAttnDescribe(const SwinAttnPlan* plan, char* buf, int cap) {
-    std::snprintf(buf, cap, "swin-attn fused LN+QKV+window-attention+proj+residual (tcgen05) c=%d heads=%d window=%d shift=%d rows=%d windows/tile=%d smem=%u", kC, kHeads,
-                  kWin, plan->args.shiftY > plan->args.shiftX ? plan->args.shiftY : plan->args.shiftX, kRows, kWinTile, kAttnSmem);
+    std::snprintf(buf, cap, "swin-attn fused LN+QKV+window-attention%s (tcgen05) c=%d heads=%d window=%d shift=%d rows=%d windows/tile=%d weights=%s smem=%u",
+                  plan->c == 96 ? "+proj+residual" : "", plan->c, kHeads, kWin, plan->args.shiftY > plan->args.shiftX ? plan->args.shiftY : plan->args.shiftX, kRows, kWinTile,
+                  plan->c == 96 ? "resident" : "streamed", plan->c == 96 ? ACfg<96>::kSmem : ACfg<192>::kSmem);
     return buf;
 }
 
@@ -636,7 +742,8 @@ void swinAttnLaunch(const SwinAttnPlan* plan, cudaStream_t s, int nImages) {
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64) dev = 0;
     if (!attrSet[dev]) {
-        cudaFuncSetAttribute(swin_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
+        cudaFuncSetAttribute(swin_attn_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, ACfg<96>::kSmem);
+        cudaFuncSetAttribute(swin_attn_kernel<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, ACfg<192>::kSmem);
         cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
         if (sms[dev] <= 0) sms[dev] = 148;
         attrSet[dev] = true;
@@ -646,7 +753,8 @@ void swinAttnLaunch(const SwinAttnPlan* plan, cudaStream_t s, int nImages) {
     a.windows = (long long)nImages * a.nwx * a.nwy;
     const long long tiles = (a.windows + kWinTile - 1) / kWinTile;
     const dim3 grid((unsigned)(tiles < sms[dev] ? tiles : sms[dev]));
-    const cudaError_t e = launchPdl(swin_attn_kernel, grid, dim3(kAttnThreads), kAttnSmem, s, a);
+    const cudaError_t e = plan->c == 96 ? launchPdl(swin_attn_kernel<96>, grid, dim3(kAttnThreads), ACfg<96>::kSmem, s, a)
+                                        : launchPdl(swin_attn_kernel<192>, grid, dim3(kAttnThreads), ACfg<192>::kSmem, s, a);
     if (e != cudaSuccess) throw Error(std::string("swin attention launch: ") + cudaGetErrorString(e));
 }
 

@@ -321,19 +321,25 @@ def run_swin_mlp(x: np.ndarray, gamma: np.ndarray, beta: np.ndarray, eps: float,
     return out, (ms.value if reps > 0 else None)
 
 
-def run_swin_attn(x: np.ndarray, gamma: np.ndarray, beta: np.ndarray, eps: float, wqkv: np.ndarray, bqkv: np.ndarray, wproj: np.ndarray, bproj: np.ndarray,
+def run_swin_attn(x: np.ndarray, gamma: np.ndarray, beta: np.ndarray, eps: float, wqkv: np.ndarray, bqkv: np.ndarray, wproj, bproj,
                   relpos: np.ndarray, heads: int = 6, shift: int = 0, reps: int = 0, device: int = 0):
-    """x + proj(window attention(LayerNorm(x))) through the fused attention kernel (include/w2x_dev.h: w2x_run_swin_attn).  x: fp16
-    [n][h][w][c]; wqkv [3c][c], wproj [c][c] fp16; relpos [heads][36][36] f32.  Returns (result fp16 [n][h][w][c], ms per launch or None)."""
+    """The fused attention kernel (include/w2x_dev.h: w2x_run_swin_attn).  x: fp16 [n][h][w][c]; wqkv [3c][c] fp16; relpos [heads][36][36] f32.
+    c = 96: returns x + proj(window attention(LayerNorm(x))) (wproj [c][c] fp16, bproj [c]); c = 192: returns window attention(LayerNorm(x)),
+    the kernel's output before the projection (wproj / bproj ignored).  Second value: ms per launch over `reps` extra launches, or None."""
     out = np.ascontiguousarray(x, dtype=np.float16).copy()
     n, h, w, c = out.shape
-    f16 = [np.ascontiguousarray(a, dtype=np.float16) for a in (wqkv, wproj)]
-    f32 = [np.ascontiguousarray(a, dtype=np.float32) for a in (gamma, beta, bqkv, bproj, relpos)]
-    if f16[0].shape != (3 * c, c) or f16[1].shape != (c, c) or f32[4].shape != (heads, 36, 36):
+    wq = np.ascontiguousarray(wqkv, dtype=np.float16)
+    f32 = [np.ascontiguousarray(a, dtype=np.float32) for a in (gamma, beta, bqkv, relpos)]
+    if wq.shape != (3 * c, c) or f32[3].shape != (heads, 36, 36):
         raise ValueError("run_swin_attn: operand shapes")
+    wp = bp = None
+    if c == 96:
+        wp, bp = np.ascontiguousarray(wproj, dtype=np.float16), np.ascontiguousarray(bproj, dtype=np.float32)
+        if wp.shape != (c, c) or bp.shape != (c,):
+            raise ValueError("run_swin_attn: operand shapes")
     ms = C.c_float(0.0)
-    ok = lib().w2x_run_swin_attn(device, n, h, w, c, int(heads), int(shift), _ptr(out), _ptr(f32[0]), _ptr(f32[1]), float(eps), _ptr(f16[0]), _ptr(f32[2]),
-                                 _ptr(f16[1]), _ptr(f32[3]), _ptr(f32[4]), int(reps), C.byref(ms))
+    ok = lib().w2x_run_swin_attn(device, n, h, w, c, int(heads), int(shift), _ptr(out), _ptr(f32[0]), _ptr(f32[1]), float(eps), _ptr(wq), _ptr(f32[2]),
+                                 _ptr(wp) if wp is not None else None, _ptr(bp) if bp is not None else None, _ptr(f32[3]), int(reps), C.byref(ms))
     if not ok:
         raise RuntimeError("w2x_run_swin_attn failed")
     return out, (ms.value if reps > 0 else None)
