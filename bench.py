@@ -14,7 +14,7 @@ on rank 0, the other half of the metric and the TTA configuration, reported unde
   e2e       the same metric through the public API with HOST buffers, copies inside the timed region: pinned host frame -> H2D ->
             render -> D2H into a pinned host frame, pipelined (w2x_submit / w2x_wait, three frames in flight).
   e2e_sync  the literal drop-in call: synchronous w2x_render (== trt::Img2Img::render) with pageable host buffers, one frame at a time.
-  roofline  dominant kernel family (conv3x3_patch_kernel for cunet, igemm_kernel for swin): algorithmic 2*MAC FLOPs of those launches
+  roofline  dominant kernel family (conv3x3_patch_kernel for cunet, the fused token kernels swin_attn_kernel / swin_mlp_kernel for swin): algorithmic 2*MAC FLOPs of those launches
             / their CUDA-event time (per-layer pass on the engine stream), against MEASURED_PEAKS.json bf16_tflops (burst).
   roofline_tiling  the memory-bound kernels (unpack, stitch, tta_reduce): SURVEY 8d algorithmic bytes / CUDA-event time of the last
             timed frame, against MEASURED_PEAKS.json hbm_gbs.
@@ -46,8 +46,8 @@ WORKLOADS = {
                   dom_name="conv3x3_patch_kernel (tcgen05)",
                   name="cunet/art scale2 noise3 tile256 batch8 fp16, synthetic 1920x1080 -> 3840x2160 frames (BASELINE configs[1])",
                   cpu_crop=(640, 360), cpu_note="640x360 crop (8 tiles of 256 -> 1280x720)"),
-    "swin": dict(model="swin_unet/art", family="swin_unet", scale=4, noise=3, tile=256, batch=4, tiles=45, tta=False, dom="igemm",
-                 dom_name="igemm_kernel (tcgen05)",
+    "swin": dict(model="swin_unet/art", family="swin_unet", scale=4, noise=3, tile=256, batch=4, tiles=45, tta=False, dom="swin-",
+                 dom_name="swin_attn_kernel + swin_mlp_kernel (fused token kernels, tcgen05)",
                  name="swin_unet/art scale4 noise3 tile256 batch4 fp16, synthetic 1920x1080 -> 7680x4320 frames (BASELINE configs[3])",
                  cpu_crop=(464, 240), cpu_note="464x240 crop (2 tiles of 256 -> 1856x960)"),
     "cunet_tta": dict(model="cunet/art", family="cunet", scale=1, noise=3, tile=400, batch=8, tiles=24, tta=True, dom="patch3x3",

@@ -35,14 +35,15 @@ __device__ __forceinline__ void loadF8(uint32_t addr, float (&v)[8]) {
 // LayerNorm producer warps (groups of 4 warps, one token row per thread): rows of tile k -> fp16 A-operand rows (SWIZZLE_64B,
 // 32-channel K chunks of kAChunk bytes) in buffer k % kABufs at offA; tokenOf(k, row) names the token a row holds (the fused attention
 // kernel gathers window-ordered tokens this way: roll + window partition are its address math); barAFull / barAEmpty are the shared-memory addresses of buffer
-// 0's barriers.  afterTile(k) runs after tile k has been handed over; kFirst / kStep let several groups of four warps share the tiles (measured: a second group does not pay, the 96
+// 0's barriers.  beforeTile(k) / afterTile(k) run before tile k's rows are loaded / after they have been handed over; kFirst / kStep let several groups of four warps share the tiles (measured: a second group does not pay, the 96
 // registers per thread it leaves cost more than the overlap gains).
 struct NoTileHook {
     __device__ __forceinline__ void operator()(int) const {}
 };
-template <int C, int kABufs, typename TokenOf, typename AfterTile = NoTileHook>
+template <int C, int kABufs, typename TokenOf, typename AfterTile = NoTileHook, typename BeforeTile = NoTileHook>
 __device__ __forceinline__ void lnProducerLoop(const __half* x, float eps, TokenOf tokenOf, uint32_t base, uint32_t offA, uint32_t offGamma, uint32_t offBeta,
-                                               uint32_t barAFull, uint32_t barAEmpty, int nMine, int kFirst = 0, int kStep = 1, AfterTile afterTile = AfterTile()) {
+                                               uint32_t barAFull, uint32_t barAEmpty, int nMine, int kFirst = 0, int kStep = 1, AfterTile afterTile = AfterTile(),
+                                               BeforeTile beforeTile = BeforeTile()) {
     const int lane = threadIdx.x & 31;
     pdlWait();  // x is written by the preceding kernel
     const int row = threadIdx.x & 127;
@@ -66,6 +67,7 @@ __device__ __forceinline__ void lnProducerLoop(const __half* x, float eps, Token
         }
     };
     for (int k = kFirst; k < nMine; k += kStep) {
+        beforeTile(k);   // per-tile work that must not sit behind this tile's wait for a free A buffer
         const long long g = tokenOf(k, row);   // token index of row `row` of this CTA's k-th tile, or < 0 for a padding row
         const bool valid = g >= 0;
         const uint4* src = reinterpret_cast<const uint4*>(x + (valid ? g : 0) * C);
