@@ -333,7 +333,7 @@ def measure(wl, args, rank, world, local, dist, heavy=True):
         traffic, traffic_src = None, None
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
-            traffic, traffic_src = tj.get(wl.get("traffic_key", args.workload)), tj.get(wl.get("traffic_key", args.workload) + "_note")
+            traffic, traffic_src = tj.get(wl["key"]), tj.get(wl["key"] + "_note")
         except Exception:
             pass
         res["roofline"] = {
@@ -366,7 +366,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="experiment: override the workload's batchSize (the driver line uses the default)")
     ap.add_argument("--layers", action="store_true", help="also print a per-layer profile to stderr")
     args = ap.parse_args()
-    wl = dict(WORKLOADS[args.workload])
+    wl = dict(WORKLOADS[args.workload], key=args.workload)
     if args.batch > 0:
         wl["batch"] = args.batch
         wl["name"] += f" [batch override {args.batch}]"
@@ -397,7 +397,7 @@ def main():
         for key in ("swin", "cunet_tta", "cunet"):
             if key == args.workload or (key == "cunet" and args.workload != "cunet"):
                 continue
-            w2 = dict(WORKLOADS[key])
+            w2 = dict(WORKLOADS[key], key=key)
             x = measure(w2, args, rank, world, local, dist, heavy=False)
             extra[key] = {"workload": w2["name"], "value": x["value"], "unit": UNIT, "ms_per_step": x["ms_per_step"], "steps": x["steps"], "warmup": x["warmup"],
                           "fps": x["fps"], "e2e": x["e2e"], "e2e_sync": x["e2e_sync"], "stage_ms_last_frame": x["stage"], "roofline": x.get("roofline"),
