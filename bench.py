@@ -58,7 +58,7 @@ WORKLOADS = {
 METRIC, UNIT = "output Mpx/s", "Mpx/s"
 # switches of the development build that alter or skip kernel work (the shipped library ignores them; refuse anyway)
 FORBIDDEN_ENV = ("W2X_DBG", "W2X_CONV_IMPL", "W2X_NO_PATCH", "W2X_NO_FUSE_FIRST", "W2X_NO_EPI_GROUPS", "W2X_NO_HEAD_KERNEL", "W2X_NO_PDL",
-                 "W2X_PROF", "W2X_REPEAT", "W2X_DEBUG_SYNC")
+                 "W2X_PROF", "W2X_REPEAT", "W2X_DEBUG_SYNC", "W2X_NO_MLP_FUSE", "W2X_NO_ATTN_FUSE", "W2X_NO_HEAD_COMPOSE")
 
 
 def _peaks():
