@@ -141,6 +141,9 @@ void Engine::unload() {
     allocs.clear();
     dW.clear(); dBias.clear();
     auto freep = [](auto*& p) { if (p) { cudaFree(p); p = nullptr; } };
+    freep(dTileMap); tileMapCap = 0;
+    for (cudaEvent_t e : bandEv) cudaEventDestroy(e);
+    bandEv.clear();
     freep(dSlots); freep(dTileOut); freep(dTtaMean); freep(dRampX); freep(dRampY); freep(dFrameIn); freep(dFrameOut); freep(dUnpacked);
     unpackedCap = 0;
     freep(dBandTiles); freep(dBandMap); freep(dBandSlots); freep(dBandMean);
@@ -855,11 +858,37 @@ void Engine::ensureFrameBuffers(int w, int h) {
     const int stepsPerTile = cfg.tta ? 8 : 1;
     batchCount = (int)std::lround(std::ceil((double)(grid.count * stepsPerTile) / batch));  // render.cpp:249
     stepCount = batchCount * batch;
+    // Tile order.  The reference walks its column-major tile list (render.cpp:264-265).  A tile's result does not depend on its batch
+    // or slot (exact integer SE sums), so without TTA the tiles are processed ROW by row instead: the output rows above the next tile row
+    // are then final as soon as a tile row is done, which lets render() stitch and download them while later batches still compute.
+    // rowBands[j] = {first output row, end row, batch after which they are final}; tileMapHost[ti] = slot of reference tile ti.
+    rowBands.clear();
+    std::vector<int> tileMapHost;
     std::vector<TileSlot> slots((size_t)stepCount);
-    for (int step = 0; step < stepCount; ++step) {
-        const int ti = step / stepsPerTile, aug = step % stepsPerTile;  // render.cpp:264-265
-        if (ti < grid.count) slots[step] = {grid.inRects[ti].x, grid.inRects[ti].y, aug, 1};
-        else slots[step] = {0, 0, 0, 0};  // zero dummy tile, render.cpp:281
+    if (!cfg.tta) {
+        tileMapHost.assign((size_t)grid.count, 0);
+        for (int step = 0; step < stepCount; ++step) {
+            if (step < grid.count) {
+                const int j = step / grid.nx, i = step - j * grid.nx, ti = i * grid.ny + j;
+                slots[step] = {grid.inRects[ti].x, grid.inRects[ti].y, 0, 1};
+                tileMapHost[ti] = step;
+            } else {
+                slots[step] = {0, 0, 0, 0};  // zero dummy tile, render.cpp:281
+            }
+        }
+        int y0 = 0;
+        for (int j = 0; j < grid.ny; ++j) {
+            const int y1 = j + 1 < grid.ny ? grid.outRects[j + 1].y : h * scale;   // tile (0, j + 1): top of the next tile row
+            if (y1 > y0) rowBands.push_back({y0, y1, ((j + 1) * grid.nx - 1) / batch});
+            else if (!rowBands.empty()) rowBands.back().batch = ((j + 1) * grid.nx - 1) / batch;
+            y0 = std::max(y0, y1);
+        }
+    } else {
+        for (int step = 0; step < stepCount; ++step) {
+            const int ti = step / stepsPerTile, aug = step % stepsPerTile;  // render.cpp:264-265
+            if (ti < grid.count) slots[step] = {grid.inRects[ti].x, grid.inRects[ti].y, aug, 1};
+            else slots[step] = {0, 0, 0, 0};  // zero dummy tile, render.cpp:281
+        }
     }
     if ((size_t)stepCount > slotCap) {
         if (dSlots) cudaFree(dSlots);
@@ -867,6 +896,15 @@ void Engine::ensureFrameBuffers(int w, int h) {
         slotCap = stepCount;
     }
     uploadAsync(dSlots, slots.data(), sizeof(TileSlot) * stepCount);
+    if (!tileMapHost.empty()) {
+        if (tileMapHost.size() > tileMapCap) {
+            if (dTileMap) cudaFree(dTileMap);
+            dTileMap = nullptr;
+            W2X_CUDA(cudaMalloc(&dTileMap, sizeof(int) * tileMapHost.size()));
+            tileMapCap = tileMapHost.size();
+        }
+        uploadAsync(dTileMap, tileMapHost.data(), sizeof(int) * tileMapHost.size());
+    }
     if (frameWideUnpack()) {
         const size_t need = (size_t)stepCount * tile * tile * 4;
         if (need > unpackedCap) {
@@ -909,8 +947,24 @@ void Engine::ensureFrameBuffers(int w, int h) {
     frameH = h;
 }
 
-void Engine::renderOnStream(const uint8_t* dSrc, int w, int h, size_t srcPitch, uint8_t* dDst, size_t dstPitch, cudaStream_t s, bool timed) {
+void Engine::renderOnStream(const uint8_t* dSrc, int w, int h, size_t srcPitch, uint8_t* dDst, size_t dstPitch, cudaStream_t s, bool timed,
+                            std::vector<BandDone>* bands) {
     ensureFrameBuffers(w, h);
+    const bool progressive = bands != nullptr && !cfg.tta && !rowBands.empty();
+    if (bands) bands->clear();
+    auto stitchRows = [&](int yBegin, int yEnd) {
+        StitchParams sp{};
+        sp.outT = outTile; sp.nx = grid.nx; sp.ny = grid.ny; sp.ovx = grid.outOvX; sp.ovy = grid.outOvY;
+        sp.cw = w * scale; sp.ch = h * scale;
+        sp.rampx = dRampX; sp.rampy = dRampY;
+        sp.dst = dDst; sp.pitch = dstPitch;
+        sp.tiles = cfg.tta ? (const void*)dTtaMean : (const void*)dTileOut;
+        sp.f32 = cfg.tta ? 1 : 0;
+        sp.tile_map = cfg.tta ? nullptr : dTileMap;
+        sp.y_begin = yBegin; sp.y_end = yEnd;
+        launchStitch(sp, s);
+        ++launches;
+    };
     if (timed) { evUsed = 0; spans.clear(); }
     auto span = [&](int kind, auto&& fn) {
         if (!timed) { fn(); return; }
@@ -943,27 +997,36 @@ void Engine::renderOnStream(const uint8_t* dSrc, int w, int h, size_t srcPitch, 
                 ++launches;
             });
         span(1, [&] { runModel(s, dTileOut + (size_t)b * batch * tileElems, nReal, frameWide ? dUnpacked + (size_t)b * batch * inElems : nullptr); });
+        if (progressive) {
+            // output rows that only depend on tile rows finished with this batch: stitch them now, hand the caller an event to copy after
+            for (const RowBand& rb : rowBands) {
+                if (rb.batch != b) continue;
+                span(2, [&] { stitchRows(rb.y0, rb.y1); });
+                if (bandEv.size() <= bands->size()) {
+                    cudaEvent_t e;
+                    W2X_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                    bandEv.push_back(e);
+                }
+                cudaEvent_t e = bandEv[bands->size()];
+                W2X_CUDA(cudaEventRecord(e, s));
+                bands->push_back({rb.y0, rb.y1, e});
+            }
+        }
         if (progCb) {
             const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
             progCb(b + 1, batchCount, 1000.0 / std::max(ms, 1e-6), progUser);  // render.cpp:336-338
         }
+    }
+    if (progressive) {
+        W2X_CUDA(cudaGetLastError());
+        return;
     }
     if (cfg.tta)
         span(4, [&] {
             launchTtaReduce(dTileOut, grid.count, outTile, dTtaMean, s);
             ++launches;
         });
-    span(2, [&] {
-        StitchParams sp{};
-        sp.outT = outTile; sp.nx = grid.nx; sp.ny = grid.ny; sp.ovx = grid.outOvX; sp.ovy = grid.outOvY;
-        sp.cw = w * scale; sp.ch = h * scale;
-        sp.rampx = dRampX; sp.rampy = dRampY;
-        sp.dst = dDst; sp.pitch = dstPitch;
-        sp.tiles = cfg.tta ? (const void*)dTtaMean : (const void*)dTileOut;
-        sp.f32 = cfg.tta ? 1 : 0;
-        launchStitch(sp, s);
-        ++launches;
-    });
+    span(2, [&] { stitchRows(0, h * scale); });
     W2X_CUDA(cudaGetLastError());
 }
 
@@ -1028,9 +1091,22 @@ bool Engine::render(const uint8_t* src, int w, int h, size_t srcStride, uint8_t*
             frameOutCap = outBytes;
         }
         W2X_CUDA(cudaMemcpy2DAsync(dFrameIn, (size_t)w * 3, src, srcStride, (size_t)w * 3, h, cudaMemcpyHostToDevice, stream));  // render.cpp:226
-        renderOnStream(dFrameIn, w, h, (size_t)w * 3, dFrameOut, (size_t)w * scale * 3, stream, true);
-        W2X_CUDA(cudaMemcpy2DAsync(dst, dstStride, dFrameOut, (size_t)w * scale * 3, (size_t)w * scale * 3, (size_t)h * scale,
-                                   cudaMemcpyDeviceToHost, stream));  // render.cpp:344
+        // every kernel of the frame is queued first; the output then leaves band by band (rows that are final after a tile row), each copy
+        // ordered behind its band's stitch only, so the download of a band overlaps the batches still computing (the reference downloads
+        // the whole canvas after the last batch, render.cpp:344).  With --tta there is one band: the whole frame after the reduce.
+        std::vector<BandDone> bands;
+        const size_t opitch = (size_t)w * scale * 3;
+        renderOnStream(dFrameIn, w, h, (size_t)w * 3, dFrameOut, opitch, stream, true, &bands);
+        if (bands.empty()) {
+            W2X_CUDA(cudaMemcpy2DAsync(dst, dstStride, dFrameOut, opitch, opitch, (size_t)h * scale, cudaMemcpyDeviceToHost, stream));  // render.cpp:344
+        } else {
+            for (const BandDone& bd : bands) {
+                W2X_CUDA(cudaStreamWaitEvent(d2hStream, bd.ev, 0));
+                W2X_CUDA(cudaMemcpy2DAsync(dst + (size_t)bd.y0 * dstStride, dstStride, dFrameOut + (size_t)bd.y0 * opitch, opitch, opitch, (size_t)(bd.y1 - bd.y0),
+                                           cudaMemcpyDeviceToHost, d2hStream));
+            }
+            W2X_CUDA(cudaStreamSynchronize(d2hStream));
+        }
         W2X_CUDA(cudaStreamSynchronize(stream));  // the sync the reference leaves commented out (render.cpp:345)
         return true;
     } catch (const std::exception& ex) {

@@ -103,7 +103,11 @@ private:
     void runModel(cudaStream_t s, __half* finalOut, int nImages = 0, const __half* inTiles = nullptr);
     bool frameWideUnpack() const;
     void ensureFrameBuffers(int w, int h);
-    void renderOnStream(const uint8_t* dSrc, int w, int h, size_t srcPitch, uint8_t* dDst, size_t dstPitch, cudaStream_t s, bool timed);
+    struct RowBand { int y0, y1, batch; };             // output rows [y0, y1) are final once batch `batch` has run (row-major tile order)
+    struct BandDone { int y0, y1; cudaEvent_t ev; };   // ... and have been stitched when `ev` fires
+    // bands != nullptr (and no TTA): stitch progressively, one launch per finished tile row, and report the bands instead of one stitch at the end
+    void renderOnStream(const uint8_t* dSrc, int w, int h, size_t srcPitch, uint8_t* dDst, size_t dstPitch, cudaStream_t s, bool timed,
+                        std::vector<BandDone>* bands = nullptr);
     void* dalloc(size_t bytes);
     Act allocAct(int h, int w, int c);
 
@@ -134,6 +138,10 @@ private:
     TileGrid grid;
     int stepCount = 0, batchCount = 0;
     TileSlot* dSlots = nullptr;
+    int* dTileMap = nullptr;                     // slot of reference tile ti (row-major processing order without TTA)
+    size_t tileMapCap = 0;
+    std::vector<RowBand> rowBands;
+    std::vector<cudaEvent_t> bandEv;
     size_t slotCap = 0;
     __half* dUnpacked = nullptr;     // [steps][tile][tile][4] fp16: every tile of the frame, unpacked by one launch
     size_t unpackedCap = 0;
