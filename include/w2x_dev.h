@@ -38,11 +38,6 @@ W2X_API int w2x_run_conv_layer(int device, int kind, int head, int n, int h, int
 W2X_API int w2x_run_swin_mlp(int device, long long tokens, int c, int variant, uint16_t* x, const float* gamma, const float* beta, float eps,
                              const uint16_t* w1, const float* b1, const uint16_t* w2, const float* b2, int reps, float* ms_out);
 
-/* The fused LayerNorm + QKV projection of a SwinUNet block (kernels/swin_mlp_sm100.cu): out[tokens][3c] = LayerNorm(x[tokens][c]) w^T + bias,
- * c = 96 or 192, w = [3c][c] fp16 bits (K-major).  ms_out as above.  Returns 1 on success. */
-W2X_API int w2x_run_swin_lnlinear(int device, long long tokens, int c, const uint16_t* x, const float* gamma, const float* beta, float eps,
-                                  const uint16_t* w, const float* bias, uint16_t* out, int reps, float* ms_out);
-
 /* The fused attention half of a SwinUNet block (kernels/swin_attn_sm100.cu; replaces a slice of the engine enqueued at img2img_infer.cpp:80):
  * 6x6 windows, cyclic shift `shift` (0 or 3), relative-position bias relpos[heads][36][36] and torchvision's shift mask; heads = 6, h and w
  * multiples of 6.  c = 96: x[n][h][w][c] (NHWC fp16 bits, updated in place) += proj(window attention(LayerNorm(x))); c = 192: x receives

@@ -12,13 +12,6 @@ for c, tokens, variant in [(96, 4 * 240 * 240, 0), (96, 4 * 240 * 240, 1), (192,
     for _ in range(2):
         out, ms = w2x.run_swin_mlp(*case, reps=50, variant=variant)
         print('fused mlp c=%d variant=%d, %d tokens: %.4f ms per launch' % (c, variant, tokens, ms))
-import numpy as np
-for c, tokens in [(96, 4 * 240 * 240), (192, 4 * 120 * 120)]:
-    rng = np.random.default_rng(1)
-    x = rng.standard_normal((tokens, c)).astype(np.float16)
-    w = (rng.standard_normal((3 * c, c)) / 10).astype(np.float16)
-    out, ms = w2x.run_swin_lnlinear(x, np.ones(c, np.float32), np.zeros(c, np.float32), 1e-5, w, np.zeros(3 * c, np.float32), reps=50)
-    print('fused ln+qkv c=%d, %d tokens: %.4f ms per launch' % (c, tokens, ms))
 PY
 timeout 600 python -m pytest tests/test_gpu_swin.py tests/test_gpu_banded.py -x -q -m gpu 2>&1 | tail -5
 timeout 300 python bench.py --only --workload swin --no-cpu-baseline --steps 16 2>/dev/null | tee gpurun_out/bench_swin_mlp.json | python -c "

@@ -15,7 +15,4 @@ for c in (96, 192):
         tokens = 148 * 128 * tiles_per_cta
         case = make_case(tokens, 3, c)
         _, ms = w2x.run_swin_mlp(*case, reps=30)
-        rng = np.random.default_rng(1)
-        w = (rng.standard_normal((3 * c, c)) / 10).astype(np.float16)
-        _, ms2 = w2x.run_swin_lnlinear(case[0], case[1], case[2], 1e-5, w, np.zeros(3 * c, np.float32), reps=30)
-        print("c=%d tiles/CTA=%2d tokens=%7d  mlp %.4f ms  ln+qkv %.4f ms" % (c, tiles_per_cta, tokens, ms, ms2), flush=True)
+        print("c=%d tiles/CTA=%2d tokens=%7d  mlp %.4f ms" % (c, tiles_per_cta, tokens, ms), flush=True)

@@ -319,49 +319,6 @@ int w2x_run_swin_mlp(int device, long long tokens, int c, int variant, uint16_t*
     return ok;
 }
 
-int w2x_run_swin_lnlinear(int device, long long tokens, int c, const uint16_t* x, const float* gamma, const float* beta, float eps, const uint16_t* w,
-                          const float* bias, uint16_t* out, int reps, float* ms_out) {
-    void* bufs[6] = {};
-    SwinMlpPlan* plan = nullptr;
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    int ok = 0;
-    try {
-        if (tokens < 1 || !x || !gamma || !beta || !w || !bias || !out || !swinLnLinearSupported(c, 3 * c)) throw Error("invalid argument");
-        W2X_CUDA(cudaSetDevice(device));
-        const size_t C = (size_t)c;
-        const size_t sizes[6] = {(size_t)tokens * C * 2, C * 4, C * 4, 3 * C * C * 2, 3 * C * 4, (size_t)tokens * 3 * C * 2};
-        const void* host[5] = {x, gamma, beta, w, bias};
-        for (int i = 0; i < 6; ++i) {
-            W2X_CUDA(cudaMalloc(&bufs[i], sizes[i]));
-            if (i < 5) W2X_CUDA(cudaMemcpy(bufs[i], host[i], sizes[i], cudaMemcpyHostToDevice));
-        }
-        plan = swinLnLinearCreatePlan((const __half*)bufs[0], c, (const float*)bufs[1], (const float*)bufs[2], eps, (const __half*)bufs[3], (const float*)bufs[4],
-                                      (__half*)bufs[5]);
-        swinMlpLaunch(plan, nullptr, tokens);
-        W2X_CUDA(cudaDeviceSynchronize());
-        W2X_CUDA(cudaMemcpy(out, bufs[5], sizes[5], cudaMemcpyDeviceToHost));
-        if (ms_out && reps > 0) {
-            W2X_CUDA(cudaEventCreate(&e0));
-            W2X_CUDA(cudaEventCreate(&e1));
-            W2X_CUDA(cudaEventRecord(e0, nullptr));
-            for (int i = 0; i < reps; ++i) swinMlpLaunch(plan, nullptr, tokens);
-            W2X_CUDA(cudaEventRecord(e1, nullptr));
-            W2X_CUDA(cudaEventSynchronize(e1));
-            W2X_CUDA(cudaEventElapsedTime(ms_out, e0, e1));
-            *ms_out /= (float)reps;
-        }
-        ok = 1;
-    } catch (const std::exception& ex) {
-        std::fprintf(stderr, "w2x_run_swin_lnlinear: %s\n", ex.what());
-    }
-    if (e0) cudaEventDestroy(e0);
-    if (e1) cudaEventDestroy(e1);
-    if (plan) swinMlpDestroyPlan(plan);
-    for (void* b : bufs)
-        if (b) cudaFree(b);
-    return ok;
-}
-
 int w2x_run_swin_attn(int device, int n, int h, int w, int c, int heads, int shift, uint16_t* x, const float* gamma, const float* beta, float eps, const uint16_t* wqkv,
                       const float* bqkv, const uint16_t* wproj, const float* bproj, const float* relpos, int reps, float* ms_out) {
     void* bufs[9] = {};

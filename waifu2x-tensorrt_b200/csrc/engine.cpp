@@ -473,10 +473,6 @@ void Engine::launchLayer(LayerExec& L, cudaStream_t s, __half* outp, int nImg, c
 // SwinUNet execution plan: token tensors are NHWC fp16 [batch][h][w][C]; the residual stream is updated in
 // place by the proj / fc2 epilogues (each thread reads exactly the element it then overwrites).
 // ------------------------------------------------------------------------------------------------
-// LayerNorm + QKV in one kernel: measured slower than layernorm_kernel + igemm_kernel while its token rows are read and its output
-// written one row per thread (LSU-wavefront bound); off until those go through TMA
-static constexpr bool kFuseLnQkv = false;
-
 void Engine::buildPlanSwin() {
     const int C = (int)model.dim, S = (int)model.scale;
     if (C != 96) throw Error("swin plan: only base_dim 96 (the released swin_unet models) is supported by the LayerNorm/attention kernels");
@@ -633,19 +629,6 @@ void Engine::buildPlanSwin() {
                 layers.push_back(E);
                 linear(pj, att, x, ACT_LRELU, &x);   // x += proj(attn)
             }
-        } else if (kFuseLnQkv && !useDirect && !devEnv("W2X_NO_MLP_FUSE") && swinLnLinearSupported(c, (int)QK.npad) && (int)QK.ktot == c) {
-            // qkv = LayerNorm(x) Wqkv^T + b in ONE kernel: the normalised rows stay in shared memory
-            LayerExec S;
-            S.name = model.layers[n1].name;
-            S.impl = IMPL_SKIP;
-            layers.push_back(S);
-            LayerExec E;
-            E.name = QK.name;
-            E.impl = IMPL_SWIN_MLP;
-            E.tokN = x.n; E.tokH = h; E.tokW = w; E.tokC = c;
-            E.flops = 2.0 * h * w * (double)QK.npad * QK.ktot;
-            E.mlp = swinLnLinearCreatePlan(x.p, c, dAux0[n1], dAux1[n1], model.layers[n1].eps, dW[qk], dBias[qk], qkv.p);
-            layers.push_back(E);
         } else {
             pushLn(n1);
             linear(qk, ln, qkv, ACT_LRELU, nullptr);

@@ -196,8 +196,6 @@ struct SwinMlpPlan;                                               // fused LN + 
 bool swinMlpSupported(int c, int hidden);
 SwinMlpPlan* swinMlpCreatePlan(__half* x, int c, const float* gamma, const float* beta, float eps, const __half* w1, const float* b1, const __half* w2, const float* b2,
                                int variant = 0);  // variant 1: stream the weights even where they would fit
-bool swinLnLinearSupported(int c, int n);                         // LayerNorm + Linear (QKV projection) in one kernel, same plan type
-SwinMlpPlan* swinLnLinearCreatePlan(const __half* x, int c, const float* gamma, const float* beta, float eps, const __half* w, const float* bias, __half* out);
 void swinMlpDestroyPlan(SwinMlpPlan* plan);
 void swinMlpLaunch(const SwinMlpPlan* plan, cudaStream_t s, long long tokens);
 const char* swinMlpDescribe(const SwinMlpPlan* plan, char* buf, int cap);

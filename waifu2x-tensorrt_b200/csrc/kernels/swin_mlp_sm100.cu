@@ -65,7 +65,6 @@ struct MlpArgs {
     const float* beta;         // [C]
     float eps;
     long long tokens;
-    __half* out;               // LN + Linear kernel only: [tokens][3C]
 };
 
 // tiles are consecutive runs of 128 tokens, dealt round-robin to the CTAs
@@ -539,165 +538,12 @@ __global__ void __launch_bounds__(StreamCfg<C>::kThreadsS, 1) swin_mlp_stream_ke
 }
 
 
-// ------------------------------------------------------------------------------------------------------------------------------
-// LayerNorm + Linear (the QKV projection of a block: out[tokens][3C] = LayerNorm(x) W^T + b), same producer / MMA / epilogue roles.
-// The output is produced in chunks of 96 columns: the chunk's weight rows W[c*96 .. +96][C] stream through a three-stage TMA ring,
-// fc(chunk) -> D (96 TMEM columns, double-buffered) -> + bias -> fp16 -> 16-byte stores.  The normalised rows never touch HBM.
-// ------------------------------------------------------------------------------------------------------------------------------
-template <int C>
-struct LinCfg {
-    static constexpr int kN = 3 * C;
-    static constexpr int kNC = 96;                            // output columns per chunk
-    static constexpr int kChunks = kN / kNC;
-    static constexpr int kKA = C / 32;
-    static constexpr int kProd = 4, kTmaW = 4, kMmaW = 5, kEpi0 = 6;
-    static constexpr int kThreadsL = 32 * (kEpi0 + kEpiWarps);
-    static constexpr int kStages = 3;
-    static constexpr uint32_t kStage = kKA * kNC * 64;        // kKA boxes [96 rows][32 k]
-    static constexpr uint32_t kABytes = kKA * kAChunk;
-    static constexpr uint32_t kOffRing = 4096;
-    static constexpr uint32_t kOffAS = kOffRing + kStages * kStage;
-    static constexpr uint32_t kSmem = kOffAS + 2 * kABytes + 1024;
-    static constexpr uint32_t kTmem = 256;
-    static constexpr uint32_t kBias = 256, kGamma = kBias + 4 * kN, kBeta = kGamma + 4 * C;
-    static_assert(kBeta + 4 * C <= kOffRing, "constants overflow the header");
-    static_assert(kStage % 1024 == 0 && kABytes % 1024 == 0, "swizzled operands need 1024-byte alignment");
-    static_assert(kSmem <= 227 * 1024, "shared memory budget");
-};
-constexpr uint32_t lBarWFull = 0, lBarWEmpty = 32, lBarAFull = 64, lBarAEmpty = 80, lBarDFull = 96, lBarDEmpty = 112, lTmemSlot = 128;
-
-template <int C>
-__global__ void __launch_bounds__(LinCfg<C>::kThreadsL, 1) swin_lnlinear_kernel(const __grid_constant__ MlpArgs a) {
-    using Cfg = LinCfg<C>;
-    extern __shared__ uint8_t smemRaw[];
-    const uint32_t base = (smemU32(smemRaw) + 1023u) & ~1023u;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    pdlLaunchDependents();
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < Cfg::kStages; ++i) {
-            mbarInit(base + lBarWFull + 8u * i, 1);
-            mbarInit(base + lBarWEmpty + 8u * i, 1);
-        }
-        for (int i = 0; i < 2; ++i) {
-            mbarInit(base + lBarAFull + 8u * i, 4);
-            mbarInit(base + lBarAEmpty + 8u * i, 1);
-            mbarInit(base + lBarDFull + 8u * i, 1);
-            mbarInit(base + lBarDEmpty + 8u * i, kEpiWarps);
-        }
-        mbarInitFence();
-        tmaPrefetchDesc(&a.tmW1);
-    }
-    for (int i = threadIdx.x; i < Cfg::kN; i += Cfg::kThreadsL) stsF32(base + Cfg::kBias + 4u * i, a.b1[i]);
-    for (int i = threadIdx.x; i < C; i += Cfg::kThreadsL) {
-        stsF32(base + Cfg::kGamma + 4u * i, a.gamma[i]);
-        stsF32(base + Cfg::kBeta + 4u * i, a.beta[i]);
-    }
-    if (warp == Cfg::kMmaW) tmemAlloc(base + lTmemSlot, Cfg::kTmem);
-    tcFenceBefore();
-    __syncthreads();
-    tcFenceAfter();
-    uint32_t tmemBase;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmemBase) : "r"(base + lTmemSlot));
-    const long long tiles = (a.tokens + kRows - 1) / kRows;
-    const int first = blockIdx.x, step = gridDim.x;
-    const int nMine = first < tiles ? (int)((tiles - first + step - 1) / step) : 0;
-    const int nChunksMine = nMine * Cfg::kChunks;
-
-    if (warp == Cfg::kTmaW) {
-        if (lane == 0) {
-            int st = 0;
-            uint32_t ph = 0;
-            for (int g = 0; g < nChunksMine; ++g) {
-                const int c = g % Cfg::kChunks;
-                mbarWait(base + lBarWEmpty + 8u * st, ph ^ 1u);
-                const uint32_t full = base + lBarWFull + 8u * st, dst = base + Cfg::kOffRing + (uint32_t)st * Cfg::kStage;
-                mbarExpectTx(full, Cfg::kStage);
-                for (int ka = 0; ka < Cfg::kKA; ++ka) tmaLoad2d(dst + (uint32_t)ka * (Cfg::kNC * 64u), &a.tmW1, full, ka * 32, c * Cfg::kNC);
-                if (++st == Cfg::kStages) { st = 0; ph ^= 1u; }
-            }
-        }
-    } else if (warp < Cfg::kProd) {
-        lnProducerLoop<C, 2>(a.x, a.eps, linearTokens(a.tokens, first, step), base, Cfg::kOffAS, Cfg::kGamma, Cfg::kBeta, base + lBarAFull, base + lBarAEmpty, nMine);
-    } else if (warp == Cfg::kMmaW) {
-        const uint32_t hi64 = descHi(512u, 4u);
-        const uint32_t idesc = instrDescF16(kRows, Cfg::kNC);
-        int st = 0;
-        uint32_t ph = 0;
-        for (int g = 0; g < nChunksMine; ++g) {
-            const int k = g / Cfg::kChunks, c = g - k * Cfg::kChunks, buf = k & 1, d = g & 1;
-            if (c == 0) mbarWait(base + lBarAFull + 8u * buf, (uint32_t)(k >> 1) & 1u);
-            mbarWait(base + lBarWFull + 8u * st, ph);
-            mbarWait(base + lBarDEmpty + 8u * d, ((uint32_t)(g >> 1) & 1u) ^ 1u);
-            tcFenceAfter();
-            if (electOne()) {
-                const uint32_t aBase = base + Cfg::kOffAS + (uint32_t)buf * Cfg::kABytes, wBase = base + Cfg::kOffRing + (uint32_t)st * Cfg::kStage;
-#pragma unroll
-                for (int ka = 0; ka < Cfg::kKA; ++ka)
-#pragma unroll
-                    for (int ks = 0; ks < 2; ++ks)
-                        ummaLoHi(tmemBase + (uint32_t)d * 128u, descLo(aBase + ka * kAChunk + ks * 32u), hi64, descLo(wBase + ka * (Cfg::kNC * 64u) + ks * 32u), hi64, idesc,
-                                 (ka | ks) != 0 ? 1u : 0u);
-                tcCommit(base + lBarDFull + 8u * d);
-                tcCommit(base + lBarWEmpty + 8u * st);
-                if (c == Cfg::kChunks - 1) tcCommit(base + lBarAEmpty + 8u * buf);
-            }
-            __syncwarp();
-            if (++st == Cfg::kStages) { st = 0; ph ^= 1u; }
-        }
-    } else {
-        pdlWait();  // the output buffer may still be read by the preceding kernels
-        const int quarter = warp & 3;
-        const int half = (warp - Cfg::kEpi0) >> 2;
-        const int row = quarter * 32 + lane;
-        const uint32_t taddrLane = tmemBase + ((uint32_t)(quarter * 32) << 16);
-        uint32_t r[32], r2[32];
-        for (int g = 0; g < nChunksMine; ++g) {
-            const int k = g / Cfg::kChunks, c = g - k * Cfg::kChunks, d = g & 1;
-            const long long tok = ((long long)first + (long long)k * step) * kRows + row;
-            mbarWait(base + lBarDFull + 8u * d, (uint32_t)(g >> 1) & 1u);
-            tcFenceAfter();
-            const int col0 = half * 48;
-            tmemLd32(taddrLane + (uint32_t)(d * 128 + col0), r);
-            tmemLd16(taddrLane + (uint32_t)(d * 128 + col0 + 32), r2);
-            tmemLdWait();
-            tcFenceBefore();
-            __syncwarp();
-            if (lane == 0) mbarArrive(base + lBarDEmpty + 8u * d);
-            if (tok < a.tokens) {
-                uint4* dst = reinterpret_cast<uint4*>(a.out + tok * Cfg::kN + c * Cfg::kNC + col0);
-#pragma unroll
-                for (int j = 0; j < 6; ++j) {
-                    float bias[8];
-                    loadF8(base + Cfg::kBias + 4u * (uint32_t)(c * Cfg::kNC + col0 + 8 * j), bias);
-                    uint4 o;
-                    __half2* oh = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float a0 = __uint_as_float(j < 4 ? r[8 * j + 2 * i] : r2[8 * (j - 4) + 2 * i]);
-                        const float a1 = __uint_as_float(j < 4 ? r[8 * j + 2 * i + 1] : r2[8 * (j - 4) + 2 * i + 1]);
-                        oh[i] = __floats2half2_rn(a0 + bias[2 * i], a1 + bias[2 * i + 1]);
-                    }
-                    dst[j] = o;
-                }
-            }
-        }
-    }
-
-    tcFenceBefore();
-    __syncthreads();
-    if (warp == Cfg::kMmaW) {
-        tcFenceAfter();
-        tmemDealloc(tmemBase, Cfg::kTmem);
-    }
-}
-
 }  // namespace
 
 struct SwinMlpPlan {
     MlpArgs args;
     int c = 0;
     bool stream = false;   // weights streamed per hidden chunk (swin_mlp_stream_kernel) instead of resident
-    bool linear = false;   // LayerNorm + Linear (swin_lnlinear_kernel) instead of the MLP
 };
 
 bool swinMlpSupported(int c, int hidden) { return (c == 96 || c == 192) && hidden == 2 * c; }
@@ -733,40 +579,9 @@ SwinMlpPlan* swinMlpCreatePlan(__half* x, int c, const float* gamma, const float
     return plan;
 }
 
-bool swinLnLinearSupported(int c, int n) { return (c == 96 || c == 192) && n == 3 * c; }
-
-// out[tokens][3c] = LayerNorm(x) w^T + bias, w = [3c][c] fp16 K-major
-SwinMlpPlan* swinLnLinearCreatePlan(const __half* x, int c, const float* gamma, const float* beta, float eps, const __half* w, const float* bias, __half* out) {
-    if (!swinLnLinearSupported(c, 3 * c)) throw Error("swin ln+linear: unsupported width");
-    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(out)) & 15) throw Error("swin ln+linear: operands must be 16-byte aligned");
-    SwinMlpPlan* plan = new SwinMlpPlan{};
-    plan->c = c;
-    plan->linear = true;
-    try {
-        encodeMatrixMap2d(&plan->args.tmW1, w, c, 3 * c, 32, 96, false);
-        plan->args.tmW2 = plan->args.tmW1;
-    } catch (...) {
-        delete plan;
-        throw;
-    }
-    plan->args.x = const_cast<__half*>(x);
-    plan->args.out = out;
-    plan->args.b1 = bias;
-    plan->args.b2 = bias;
-    plan->args.gamma = gamma;
-    plan->args.beta = beta;
-    plan->args.eps = eps;
-    return plan;
-}
-
 void swinMlpDestroyPlan(SwinMlpPlan* plan) { delete plan; }
 
 const char* swinMlpDescribe(const SwinMlpPlan* plan, char* buf, int cap) {
-    if (plan->linear) {
-        std::snprintf(buf, cap, "swin-lnlinear fused LN+Linear (tcgen05) c=%d n=%d rows=%d weights=streamed smem=%u", plan->c, 3 * plan->c, kRows,
-                      plan->c == 96 ? LinCfg<96>::kSmem : LinCfg<192>::kSmem);
-        return buf;
-    }
     const unsigned smem = !plan->stream ? kMlpSmem : plan->c == 96 ? StreamCfg<96>::kSmem : StreamCfg<192>::kSmem;
     std::snprintf(buf, cap, "swin-mlp fused LN+fc1+GELU+fc2+residual (tcgen05) c=%d hidden=%d rows=%d weights=%s smem=%u", plan->c, 2 * plan->c, kRows,
                   plan->stream ? "streamed" : "resident", smem);
@@ -783,8 +598,6 @@ void swinMlpLaunch(const SwinMlpPlan* plan, cudaStream_t s, long long tokens) {
         cudaFuncSetAttribute(swin_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMlpSmem);
         cudaFuncSetAttribute(swin_mlp_stream_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, StreamCfg<96>::kSmem);
         cudaFuncSetAttribute(swin_mlp_stream_kernel<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, StreamCfg<192>::kSmem);
-        cudaFuncSetAttribute(swin_lnlinear_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, LinCfg<96>::kSmem);
-        cudaFuncSetAttribute(swin_lnlinear_kernel<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, LinCfg<192>::kSmem);
         cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
         if (sms[dev] <= 0) sms[dev] = 148;
         attrSet[dev] = true;
@@ -795,9 +608,7 @@ void swinMlpLaunch(const SwinMlpPlan* plan, cudaStream_t s, long long tokens) {
     const long long tiles = (tokens + kRows - 1) / kRows;
     const dim3 grid((unsigned)(tiles < sms[dev] ? tiles : sms[dev]));
     cudaError_t e;
-    if (plan->linear && plan->c == 96) e = launchPdl(swin_lnlinear_kernel<96>, grid, dim3(LinCfg<96>::kThreadsL), LinCfg<96>::kSmem, s, a);
-    else if (plan->linear) e = launchPdl(swin_lnlinear_kernel<192>, grid, dim3(LinCfg<192>::kThreadsL), LinCfg<192>::kSmem, s, a);
-    else if (!plan->stream) e = launchPdl(swin_mlp_kernel, grid, dim3(kMlpThreads), kMlpSmem, s, a);
+    if (!plan->stream) e = launchPdl(swin_mlp_kernel, grid, dim3(kMlpThreads), kMlpSmem, s, a);
     else if (plan->c == 96) e = launchPdl(swin_mlp_stream_kernel<96>, grid, dim3(StreamCfg<96>::kThreadsS), StreamCfg<96>::kSmem, s, a);
     else e = launchPdl(swin_mlp_stream_kernel<192>, grid, dim3(StreamCfg<192>::kThreadsS), StreamCfg<192>::kSmem, s, a);
     if (e != cudaSuccess) throw Error(std::string("swin mlp launch: ") + cudaGetErrorString(e));

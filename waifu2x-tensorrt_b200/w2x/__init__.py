@@ -135,8 +135,6 @@ _SIGNATURES = {
     "w2x_infer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "w2x_selftest_conv": (C.c_double, [C.c_int] * 7 + [C.c_uint]),
     "w2x_run_conv_layer": (C.c_int, [C.c_int] * 8 + [C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.c_void_p, C.c_void_p]),
-    "w2x_run_swin_lnlinear": (C.c_int, [C.c_int, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
-                                        C.c_int, C.POINTER(C.c_float)]),
     "w2x_run_swin_attn": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_float)]),
     "w2x_run_swin_mlp": (C.c_int, [C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -342,23 +340,6 @@ def run_swin_attn(x: np.ndarray, gamma: np.ndarray, beta: np.ndarray, eps: float
                                  _ptr(wp) if wp is not None else None, _ptr(bp) if bp is not None else None, _ptr(f32[3]), int(reps), C.byref(ms))
     if not ok:
         raise RuntimeError("w2x_run_swin_attn failed")
-    return out, (ms.value if reps > 0 else None)
-
-
-def run_swin_lnlinear(x: np.ndarray, gamma: np.ndarray, beta: np.ndarray, eps: float, w: np.ndarray, bias: np.ndarray, reps: int = 0, device: int = 0):
-    """LayerNorm(x) w^T + bias through the fused LN + QKV kernel (include/w2x_dev.h: w2x_run_swin_lnlinear).  x: fp16 [tokens][c], c = 96 or
-    192; w fp16 [3c][c].  Returns (fp16 [tokens][3c], average ms of `reps` extra launches or None)."""
-    x = np.ascontiguousarray(x, np.float16)
-    assert x.ndim == 2 and x.shape[1] in (96, 192)
-    c = x.shape[1]
-    w = np.ascontiguousarray(w, np.float16)
-    assert w.shape == (3 * c, c)
-    f32 = [np.ascontiguousarray(a, np.float32) for a in (gamma, beta, bias)]
-    out = np.zeros((x.shape[0], 3 * c), np.float16)
-    ms = C.c_float(0)
-    ok = lib().w2x_run_swin_lnlinear(device, x.shape[0], c, _ptr(x), _ptr(f32[0]), _ptr(f32[1]), float(eps), _ptr(w), _ptr(f32[2]), _ptr(out), int(reps), C.byref(ms))
-    if not ok:
-        raise RuntimeError("w2x_run_swin_lnlinear failed")
     return out, (ms.value if reps > 0 else None)
 
 
