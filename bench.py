@@ -104,10 +104,11 @@ class ClockSampler:
                 self.proc.kill()
         sm, mx, pw, reasons = [], [], [], set()
         for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
+            try:   # a line cut short when the sampler is terminated, or an "[N/A]" field, drops the whole sample
+                vals = (float(r[0]), float(r[1]), float(r[2]))
             except Exception:
                 continue
+            sm.append(vals[0]); mx.append(vals[1]); pw.append(vals[2])
             for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
