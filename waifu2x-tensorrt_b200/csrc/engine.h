@@ -40,7 +40,7 @@ struct LayerExec {
     // squeeze/excite applied to p.out after the conv
     int seR = 0;
     const float *seW1 = nullptr, *seB1 = nullptr, *seW2 = nullptr, *seB2 = nullptr;
-    long long* sePartial = nullptr;  // [batch][C] exact fixed-point channel sums (2^14 scale)
+    long long* sePartial = nullptr;  // [batch][C] exact fixed-point channel sums (2^10 scale, kSeFixedScale)
     float* seScale = nullptr;
     int seBlocks = 0;
     struct FoldJob { const __half* w; __half* wOut; int npad, ktot, cin; };
