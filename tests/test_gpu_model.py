@@ -143,6 +143,32 @@ def test_pipelined_submit_equals_sync_render(built_lib, models_dir):
         p.free()
 
 
+@pytest.mark.parametrize("w,h", [(300, 260), (64, 200), (257, 65)])
+def test_render_bandwise_download_strided_destination(built_lib, models_dir, w, h):
+    """render() stitches and downloads the output band by band (rows that are final after a tile row) while later batches compute
+    (engine.cpp: renderOnStream / render).  Several tile rows, a batch size that does not divide a tile row, a destination with a row
+    stride larger than the row and guard bytes around it: the bytes inside must equal the single-stitch path (submit / wait), the guard
+    bytes must stay untouched."""
+    import w2x
+    e, _, msgs = _engine(models_dir, 2, 64, 3)
+    f = tiling.synthetic_frame(w, h, 17)
+    ow, oh = 2 * w, 2 * h
+    stride = ow * 3 + 40
+    buf = np.full((oh + 2) * stride, 0xA5, np.uint8)
+    dst = np.lib.stride_tricks.as_strided(buf[stride:], shape=(oh, ow, 3), strides=(stride, 3, 1))
+    assert e.render_into(f, dst), msgs
+    pin_in, pin_out = w2x.PinnedArray((h, w, 3)), w2x.PinnedArray((oh, ow, 3))
+    pin_in.array[...] = f
+    t = e.submit(pin_in.ptr, w, h, pin_out.ptr)
+    assert t >= 0 and e.wait(t), msgs
+    assert np.array_equal(dst, pin_out.array)
+    guard = buf.reshape(oh + 2, stride)
+    assert (guard[0] == 0xA5).all() and (guard[-1] == 0xA5).all() and (guard[1:-1, ow * 3:] == 0xA5).all()
+    e.close()
+    pin_in.free()
+    pin_out.free()
+
+
 def test_reload_and_changing_frame_sizes(built_lib, models_dir):
     """load may be called repeatedly (img2img_load.cpp:149-163,209-222 tears the engine down and re-allocates); frames of
     different sizes through one engine must not disturb each other."""
