@@ -47,6 +47,18 @@ W2X_API int w2x_run_swin_mlp(int device, long long tokens, int c, int variant, u
 W2X_API int w2x_run_swin_attn(int device, int n, int h, int w, int c, int heads, int shift, uint16_t* x, const float* gamma, const float* beta, float eps,
                               const uint16_t* wqkv, const float* bqkv, const uint16_t* wproj, const float* bproj, const float* relpos, int reps, float* ms_out);
 
+/* Host-only hooks (no GPU) behind the CPU tests of the fused Swin kernels' operand preparation:
+ *  - w2x_swin_attn_prepare: wqkv [3c][c] fp16 bits (rows q | k | v, head-major), bqkv [3c], relpos [heads][36][36] -> the operands
+ *    swin_attn_kernel reads: w_out [3c][c] regrouped per 32-channel chunk (q32 | k32 | v32) with the q rows multiplied by d^-1/2 log2(e),
+ *    b_out [3c] alike, rel_out [heads][36][pitch] = relpos * log2(e) (rows padded).  Returns pitch (floats per table row), 0 on error.
+ *  - w2x_compose_up_to_image: PatchUp (w_up [4*cmid][k] packed rows q0*cmid + c, b_up [4*cmid]) followed by ToImage with pixel shuffle 2
+ *    (w_img [16][cmid] packed rows q1*4 + c3, b_img [16]) -> one linear map w_out [64][k], b_out [64] with a pixel shuffle of 4
+ *    (row (oy*4 + ox)*4 + c3).  Returns 1 on success. */
+W2X_API int w2x_swin_attn_prepare(const uint16_t* wqkv, const float* bqkv, const float* relpos, int c, int heads, uint16_t* w_out, float* b_out,
+                                  float* rel_out);
+W2X_API int w2x_compose_up_to_image(const uint16_t* w_up, const float* b_up, const uint16_t* w_img, const float* b_img, int cmid, int k, uint16_t* w_out,
+                                    float* b_out);
+
 /* One convolution layer of the implicit-GEMM family on random data, tcgen05 kernel vs the scalar CUDA reference
  * kernel, for on-device self-checks: returns max |diff| (negative on error).  kind: 0 conv3x3, 1 conv2x2s2,
  * 2 convT2x2s2(+skip), 3 convT4x4s2p3->4ch, 4 conv3x3->3ch final(+skip,clamp), 5 = kind 4 through the image-head kernel,

@@ -319,6 +319,45 @@ int w2x_run_swin_mlp(int device, long long tokens, int c, int variant, uint16_t*
     return ok;
 }
 
+// host-only hooks for the CPU test suite: the operand preparation of the fused Swin kernels
+int w2x_swin_attn_prepare(const uint16_t* wqkv, const float* bqkv, const float* relpos, int c, int heads, uint16_t* w_out, float* b_out, float* rel_out) {
+    try {
+        if (!wqkv || !bqkv || !relpos || !w_out || !b_out || !rel_out) throw Error("invalid argument");
+        std::vector<uint16_t> w;
+        std::vector<float> b, r;
+        swinAttnPrepare(wqkv, bqkv, relpos, c, heads, w, b, r);
+        std::memcpy(w_out, w.data(), w.size() * 2);
+        std::memcpy(b_out, b.data(), b.size() * 4);
+        std::memcpy(rel_out, r.data(), r.size() * 4);
+        return (int)(r.size() / ((size_t)heads * 36));   // floats per bias-table row
+    } catch (const std::exception& ex) {
+        std::fprintf(stderr, "w2x_swin_attn_prepare: %s\n", ex.what());
+        return 0;
+    }
+}
+
+int w2x_compose_up_to_image(const uint16_t* w_up, const float* b_up, const uint16_t* w_img, const float* b_img, int cmid, int k, uint16_t* w_out, float* b_out) {
+    try {
+        if (!w_up || !b_up || !w_img || !b_img || !w_out || !b_out || cmid < 1 || k < 1) throw Error("invalid argument");
+        PackedLayer U, L;
+        U.kind = L_UPLIN; U.cout = (uint32_t)cmid; U.npad = 4u * (uint32_t)cmid; U.ktot = (uint32_t)k;
+        U.w.assign(w_up, w_up + (size_t)4 * cmid * k);
+        U.bias.assign(b_up, b_up + (size_t)4 * cmid);
+        L.kind = L_TOIMG; L.cout = 3; L.npad = 16; L.ktot = (uint32_t)cmid; L.upscale = 2;
+        L.w.assign(w_img, w_img + (size_t)16 * cmid);
+        L.bias.assign(b_img, b_img + 16);
+        std::vector<uint16_t> w;
+        std::vector<float> b;
+        composeUpToImage(U, L, w, b);
+        std::memcpy(w_out, w.data(), w.size() * 2);
+        std::memcpy(b_out, b.data(), b.size() * 4);
+        return 1;
+    } catch (const std::exception& ex) {
+        std::fprintf(stderr, "w2x_compose_up_to_image: %s\n", ex.what());
+        return 0;
+    }
+}
+
 int w2x_run_swin_attn(int device, int n, int h, int w, int c, int heads, int shift, uint16_t* x, const float* gamma, const float* beta, float eps, const uint16_t* wqkv,
                       const float* bqkv, const uint16_t* wproj, const float* bproj, const float* relpos, int reps, float* ms_out) {
     void* bufs[9] = {};

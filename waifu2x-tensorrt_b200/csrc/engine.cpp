@@ -717,29 +717,13 @@ void Engine::buildPlanSwin() {
         const float* dBiases = dBias[i];
         double flops = 2.0 * top.h * top.w * 3.0 * s * s * L.ktot;
         if (composeHead) {
-            const PackedLayer& U = model.layers[iu];   // rows q0 * cout + c (q0 = dy * 2 + dx), K = cin
-            const int cmid = (int)U.cout, K = (int)U.ktot;
-            keepW.emplace_back((size_t)64 * K, (uint16_t)0);
-            keepF.emplace_back(64, 0.f);
+            const PackedLayer& U = model.layers[iu];
+            const int K = (int)U.ktot;
+            keepW.emplace_back();
+            keepF.emplace_back();
             std::vector<uint16_t>& wc = keepW.back();
             std::vector<float>& bc = keepF.back();
-            std::vector<double> acc((size_t)K);
-            for (int q0 = 0; q0 < 4; ++q0)
-                for (int q1 = 0; q1 < 4; ++q1)
-                    for (int c3 = 0; c3 < 3; ++c3) {
-                        const int oy = 2 * (q0 >> 1) + (q1 >> 1), ox = 2 * (q0 & 1) + (q1 & 1);
-                        const int dst = (oy * 4 + ox) * 4 + c3, rowI = q1 * 4 + c3;
-                        std::fill(acc.begin(), acc.end(), 0.0);
-                        double b = L.bias[rowI];
-                        for (int c = 0; c < cmid; ++c) {
-                            const double wi = halfBitsToFloat(L.w[(size_t)rowI * cmid + c]);
-                            const uint16_t* urow = &U.w[(size_t)(q0 * cmid + c) * K];
-                            for (int k = 0; k < K; ++k) acc[k] += wi * halfBitsToFloat(urow[k]);
-                            b += wi * U.bias[q0 * cmid + c];
-                        }
-                        for (int k = 0; k < K; ++k) wc[(size_t)dst * K + k] = floatToHalfBits((float)acc[k]);
-                        bc[dst] = (float)b;
-                    }
+            composeUpToImage(U, L, wc, bc);
             __half* dWc = (__half*)dalloc(wc.size() * 2);
             uploadAsync(dWc, wc.data(), wc.size() * 2);
             dWeights = dWc;

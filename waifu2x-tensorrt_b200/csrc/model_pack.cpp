@@ -683,6 +683,32 @@ PackedModel packSwin(const OnnxGraph& g, int precision) {
 }
 }  // namespace
 
+void composeUpToImage(const PackedLayer& U, const PackedLayer& L, std::vector<uint16_t>& wc, std::vector<float>& bc) {
+    const int cmid = (int)U.cout, K = (int)U.ktot;
+    if (U.kind != L_UPLIN || L.kind != L_TOIMG || L.upscale != 2 || (int)L.ktot != cmid || (int)U.npad != 4 * cmid || U.w.size() != (size_t)4 * cmid * K ||
+        L.w.size() != (size_t)16 * cmid)
+        throw Error("compose: PatchUp / ToImage shapes do not match");
+    wc.assign((size_t)64 * K, 0);
+    bc.assign(64, 0.f);
+    std::vector<double> acc((size_t)K);
+    for (int q0 = 0; q0 < 4; ++q0)
+        for (int q1 = 0; q1 < 4; ++q1)
+            for (int c3 = 0; c3 < 3; ++c3) {
+                const int oy = 2 * (q0 >> 1) + (q1 >> 1), ox = 2 * (q0 & 1) + (q1 & 1);
+                const int dst = (oy * 4 + ox) * 4 + c3, rowI = q1 * 4 + c3;
+                std::fill(acc.begin(), acc.end(), 0.0);
+                double b = L.bias[rowI];
+                for (int c = 0; c < cmid; ++c) {
+                    const double wi = halfBitsToFloat(L.w[(size_t)rowI * cmid + c]);
+                    const uint16_t* urow = &U.w[(size_t)(q0 * cmid + c) * K];
+                    for (int k = 0; k < K; ++k) acc[k] += wi * halfBitsToFloat(urow[k]);
+                    b += wi * U.bias[q0 * cmid + c];
+                }
+                for (int k = 0; k < K; ++k) wc[(size_t)dst * K + k] = floatToHalfBits((float)acc[k]);
+                bc[dst] = (float)b;
+            }
+}
+
 PackedModel packFromOnnx(const OnnxGraph& g, int precision) {
     // SwinUNet exports carry LayerNorm (fused, or decomposed into ... Sqrt -> Div -> Mul -> Add below opset 17) and an Erf GELU / Softmax;
     // the cunet family has none of these

@@ -77,6 +77,10 @@ struct PackedModel {
 };
 
 PackedModel packFromOnnx(const OnnxGraph& g, int precision);
+// PatchUp (L_UPLIN: rows q0 * cout + c, q0 = dy * 2 + dx) followed by ToImage with pixel shuffle 2 (L_TOIMG: rows q1 * 4 + c3) and nothing in
+// between is one linear map with a pixel shuffle of 4: w [64][K] fp16 bits (row (oy * 4 + ox) * 4 + c3, oy = 2 dy + ey, ox = 2 dx + ex; rows with
+// c3 = 3 are zero), b [64].  Composed in double precision from the packed fp16 weights, rounded to fp16 once.
+void composeUpToImage(const PackedLayer& up, const PackedLayer& toImage, std::vector<uint16_t>& w, std::vector<float>& b);
 std::vector<uint8_t> serializePack(const PackedModel& m);
 PackedModel deserializePack(const std::vector<uint8_t>& blob);
 

@@ -135,6 +135,8 @@ _SIGNATURES = {
     "w2x_infer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "w2x_selftest_conv": (C.c_double, [C.c_int] * 7 + [C.c_uint]),
     "w2x_run_conv_layer": (C.c_int, [C.c_int] * 8 + [C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.c_void_p, C.c_void_p]),
+    "w2x_swin_attn_prepare": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "w2x_compose_up_to_image": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "w2x_run_swin_attn": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_float)]),
     "w2x_run_swin_mlp": (C.c_int, [C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -317,6 +319,34 @@ def run_swin_mlp(x: np.ndarray, gamma: np.ndarray, beta: np.ndarray, eps: float,
     if not ok:
         raise RuntimeError("w2x_run_swin_mlp failed")
     return out, (ms.value if reps > 0 else None)
+
+
+def swin_attn_prepare(wqkv: np.ndarray, bqkv: np.ndarray, relpos: np.ndarray, heads: int = 6):
+    """Host-side operand preparation of the fused attention kernel (include/w2x_dev.h: w2x_swin_attn_prepare; no GPU needed).
+    Returns (w' fp16 [3c][c], b' f32 [3c], bias tables f32 [heads][36][pitch])."""
+    wq = np.ascontiguousarray(wqkv, dtype=np.float16)
+    c = wq.shape[1]
+    b = np.ascontiguousarray(bqkv, dtype=np.float32)
+    r = np.ascontiguousarray(relpos, dtype=np.float32)
+    w_out, b_out, rel_out = np.zeros((3 * c, c), np.float16), np.zeros(3 * c, np.float32), np.zeros((heads, 36, 64), np.float32)
+    pitch = lib().w2x_swin_attn_prepare(_ptr(wq), _ptr(b), _ptr(r), c, int(heads), _ptr(w_out), _ptr(b_out), _ptr(rel_out))
+    if pitch <= 0 or pitch > 64:
+        raise RuntimeError("w2x_swin_attn_prepare failed")
+    return w_out, b_out, rel_out.reshape(-1)[: heads * 36 * pitch].reshape(heads, 36, pitch)
+
+
+def compose_up_to_image(w_up: np.ndarray, b_up: np.ndarray, w_img: np.ndarray, b_img: np.ndarray):
+    """PatchUp + ToImage(pixel shuffle 2) -> one linear map with a pixel shuffle of 4, from the PACKED layer operands
+    (include/w2x_dev.h: w2x_compose_up_to_image; no GPU needed).  Returns (w fp16 [64][k], b f32 [64])."""
+    wu, wi = np.ascontiguousarray(w_up, dtype=np.float16), np.ascontiguousarray(w_img, dtype=np.float16)
+    bu, bi = np.ascontiguousarray(b_up, dtype=np.float32), np.ascontiguousarray(b_img, dtype=np.float32)
+    cmid, k = wu.shape[0] // 4, wu.shape[1]
+    if wi.shape != (16, cmid) or bu.shape != (4 * cmid,) or bi.shape != (16,):
+        raise ValueError("compose_up_to_image: operand shapes")
+    w_out, b_out = np.zeros((64, k), np.float16), np.zeros(64, np.float32)
+    if not lib().w2x_compose_up_to_image(_ptr(wu), _ptr(bu), _ptr(wi), _ptr(bi), cmid, k, _ptr(w_out), _ptr(b_out)):
+        raise RuntimeError("w2x_compose_up_to_image failed")
+    return w_out, b_out
 
 
 def run_swin_attn(x: np.ndarray, gamma: np.ndarray, beta: np.ndarray, eps: float, wqkv: np.ndarray, bqkv: np.ndarray, wproj, bproj,
