@@ -20,15 +20,16 @@
 //   E3       D2 + bias + residual -> x (in place, scattered back to the tokens' positions)
 //
 // Roles (16 warps, four per scheduler; a warp reads the TMEM lane quarter given by its index modulo 4):
-//   warps 0-3    LayerNorm producers (swin_token.cuh, one token row per thread)
-//   warps 4-7    row warps: E1, E2 and E3 for the 32 rows of their quarter
+//   warps 0-3    LayerNorm producers (swin_token.cuh, one token row per thread) + E3 of the tile two behind (their index is the lane quarter)
+//   warps 4-7    row warps: E1 and E2 for the 32 rows of their quarter
 //   warp  12     issuer A: QKV and proj MMAs          warp 15   issuer B: S and PV MMAs (one elected lane each)
 //   warps 8-11, 13, 14   softmax: quarters 0 / 3 hold rows of one window (one warp), quarters 1 / 2 straddle two windows (one warp per
 //                window); every softmax warp runs one pass per head
 // Each hand-off (tcgen05.commit -> mbarrier -> waiting warp) then sits between DIFFERENT warps, so the row warps convert chunk g + 1 and
 // the issuers queue its MMAs while the softmax warps are still on chunk g.  (The first version ran SM, E1, E2, E3 in sequence on eight
 // epilogue warps: 0.18 ms per level-1 block, every warp latency-bound on its own chain of waits; profiles/r02_ncu_swin_attn_v1.txt.)
-// All weights (Wqkv' 54 KB, Wproj 18 KB) and the bias tables (6 heads x [36][44] fp32) stay resident.
+// At C = 96 all weights (Wqkv' 54 KB, Wproj 18 KB) and the bias tables (6 heads x [36][44] fp32) stay resident; the C = 192 instantiation
+// (one 32-wide head per chunk, Wqkv' streamed, no projection) is described at ACfg below.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
